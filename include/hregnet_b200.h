@@ -1,0 +1,164 @@
+/*
+ * hregnet_b200.h -- C ABI of libhregnet_b200.so: hand-written sm_100a CUDA kernels for the HRegNet
+ * registration forward path (reference: UpendraArun/pcd_reg_hregnet).
+ *
+ * Conventions
+ *   - extern "C", plain device pointers + sizes; no torch / ATen types.  `stream` is a cudaStream_t passed as void*.
+ *   - every buffer is CALLER-ALLOCATED device memory, contiguous, fp32 unless noted (the reference's wrappers
+ *     also leave allocation to the caller: models/utils.py:24-25,73,84).
+ *   - asynchronous on `stream`, no host synchronisation, no global state (re-entrant per stream).
+ *   - return 0 on success, a cudaError_t (< 1000) or HRN_ERR_* (>= 1000).  Never exits the process (the reference
+ *     kernels launchers call exit(-1): furthest_point_sampling_gpu.cu:34-38,247-251).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference repo root).
+ * The binding a reference maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef HREGNET_B200_H
+#define HREGNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRN_OK 0
+#define HRN_ERR_BAD_ARG 1001
+#define HRN_ERR_UNSUPPORTED 1002
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 1. models/PointUtils native module (pybind `point_utils_cuda`, point_utils_api.cpp:6-13)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Replaces furthest_point_sampling_wrapper (furthest_point_sampling.cpp:33-43, kernel .cu:84-252) and, with
+ * `weights != NULL`, weighted_furthest_point_sampling_wrapper (.cpp:45-56, kernel .cu:254-419).
+ *   xyz [B,N,3]; weights [B,N] or NULL; temp [B,N] scratch: if non-NULL its contents are the initial
+ *   min-distances (the reference's callers fill 1e10, models/utils.py:25,49) and it receives the final ones;
+ *   NULL = start from 1e10 and keep the array on chip (requires N <= 16384).  idx [B,M] int32 out.
+ * Bit-exact with the reference kernels (rounding fma(dz,dz,fma(dx,dx,dy*dy)), tie-break = reference's
+ * block-reduction order for T = opt_n_threads(N), cuda_utils.h:22-27). */
+int hrn_fps(const float* xyz, const float* weights, float* temp, int32_t* idx, int B, int N, int M, void* stream);
+
+/* Replaces gather_points_wrapper (furthest_point_sampling.cpp:10-19, kernel .cu:7-39).
+ *   points [B,C,N], idx [B,M] int32 -> out [B,C,M]. */
+int hrn_gather_points(const float* points, const int32_t* idx, float* out, int B, int C, int N, int M, void* stream);
+
+/* Replaces gather_points_grad_wrapper (furthest_point_sampling.cpp:21-31, kernel .cu:41-73).
+ *   grad_out [B,C,M], idx [B,M] -> grad_points [B,C,N] (caller pre-zeroes; atomically accumulated). */
+int hrn_gather_points_grad(const float* grad_out, const int32_t* idx, float* grad_points, int B, int C, int N, int M,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 2. pytorch3d.ops (third-party; imported at models/HRegNet/layers.py:7)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Replaces pytorch3d.ops.knn_points(p1, p2, K=K, return_nn=...) -- call sites layers.py:20,278,316,322,434.
+ *   p1 [B,M,D] queries, p2 [B,N,D] references.  If q_idx [B,M] int32 is non-NULL (D must be 3) the queries are
+ *   p2[b, q_idx[b,m], :] and p1 is ignored (fuses layers.py:139-143 into the search); q_out [B,M,3] receives them.
+ *   Outputs, each nullable: dists [B,M,K] squared L2 ascending; idx64 [B,M,K] int64 (pytorch3d dtype);
+ *   idx32 [B,M,K] int32 (internal consumers); nn [B,M,K,D] = p2[idx].
+ *   Contract: dist accumulated d = 0..D-1 with fma in fp32; order (dist asc, index asc).  K <= min(N, 64). */
+int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int D, int K, float* dists,
+            int64_t* idx64, int32_t* idx32, float* nn, float* q_out, void* stream);
+
+/* Replaces pytorch3d.ops.knn_gather(x, idx) -- call sites layers.py:25,279,288,303,309,317,323,352,358,437,443.
+ *   x [B,N,U], idx [B,M,K] int64 -> out [B,M,K,U]. */
+int hrn_knn_gather(const float* x, const int64_t* idx, float* out, int B, int N, int M, int K, int U, void* stream);
+
+/* Row gather with int32 indices: out[b,m,:] = x[b, idx[b,m], :]  (the gather_operation(x^T, idx)^T idiom of
+ * layers.py:140,143 without its two permute+contiguous passes). */
+int hrn_gather_rows(const float* x, const int32_t* idx, float* out, int B, int N, int M, int U, void* stream);
+
+/* [B,R,C] -> [B,C,R]: the permute(0,2,1).contiguous() between the reference's [B,C,N] API layout and the
+ * channels-last rows used internally (layers.py:27,274-275,435-436). */
+int hrn_transpose(const float* in, float* out, int B, int R, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 3. Shared-MLP building blocks (models/HRegNet/layers.py KeypointDetector / DescExtractor / CoarseReg / FineReg)
+ * ------------------------------------------------------------------------------------------------------- */
+
+enum { HRN_SEG_DIRECT = 0, HRN_SEG_BROADCAST = 1, HRN_SEG_GATHER = 2 };
+enum { HRN_ACT_NONE = 0, HRN_ACT_RELU = 1, HRN_ACT_SOFTPLUS_EPS = 2, HRN_ACT_SIGMOID = 3 };
+
+/* One column segment of a virtual [rows, K] activation matrix (see pcd_reg_hregnet_b200/csrc/rows.cuh). */
+typedef struct {
+    const float* ptr;        /* [src_rows, ld] row-major (channels-last) */
+    const float* row_scale;  /* NULL, or [rows] per-row multiplier (attention weights, layers.py:157-158) */
+    int32_t channels;        /* columns taken */
+    int32_t ld;              /* leading dimension in floats */
+    int32_t col0;            /* first source column */
+    int32_t mode;            /* HRN_SEG_DIRECT: src row r; BROADCAST: r / group (layers.py:281-282 repeat);
+                                GATHER: b*src_rows_per_batch + gather_idx[r] (knn_gather, layers.py:25,279,437) */
+} hrn_seg_t;
+
+typedef struct {
+    hrn_seg_t seg[4];
+    const int32_t* gather_idx;   /* [rows] */
+    int32_t n_seg;               /* 1..4 */
+    int32_t group;               /* k */
+    int32_t rows_per_batch;      /* M*k */
+    int32_t src_rows_per_batch;  /* N */
+} hrn_rows_t;
+
+/* Y[r,n] = act( sum_k X[r,k] W[n,k] + bias[n] ), X = concatenation of in->seg[*]; W [Cout,K] row-major with
+ * BatchNorm(eval) folded in.  Replaces Conv2d/Conv1d(1x1)+BatchNorm+ReLU triples (layers.py:118-121,186-198,
+ * 249-268,420-431) and the cat/repeat/knn_gather/permute tensors feeding them.  Exact-fp32 CUDA-core variant. */
+int hrn_layer_fp32(const hrn_rows_t* in, const float* W, const float* bias, int act, float* Y, int ldy,
+                   long long rows, int Cout, void* stream);
+
+/* a[g*k+j] = softmax_j( max_c E[g*k+j, c] )   (layers.py:151-152,330-331,385-386,447-448).  k <= 64. */
+int hrn_group_attention(const float* E, int ldE, int C, long long groups, int k, float* a, void* stream);
+
+/* out[g,c] = sum_j a[g*k+j] * V[row, c], row = g*k+j (idx NULL) or b*N + idx[g*k+j]
+ * (layers.py:154-159,332,337,388-390,449-450). */
+int hrn_group_weighted_sum(const float* a, const float* V, int ldV, int C, long long groups, int k, const int32_t* idx,
+                           int groups_per_batch, int N, float* out, int ldo, void* stream);
+
+/* out[g,c] = max_j X[g*k+j, c]   (layers.py:202,208). */
+int hrn_group_max(const float* X, int ldX, int C, long long groups, int k, float* out, int ldo, void* stream);
+
+/* Geometry channels of a grouped tensor (layers.py:20-23; 284-288,364-365; 318-319; 438-445).
+ *   q [B,M,3], p [B,N,3], idx [B,M,k] int32.  out [B*M*k, ldo]: cols 0..2 = p[idx]-q, 3 = |.|; if wq and wp are
+ *   given also 4..6 = q, 7..9 = p[idx], 10 = wq[b,m], 11 = wp[b,idx].  nn (nullable) [B*M*k,3] = p[idx]. */
+int hrn_group_geometry(const float* q, const float* p, const int32_t* idx, const float* wq, const float* wp, int B,
+                       int M, int k, int N, float* out, int ldo, float* nn, void* stream);
+
+/* w = (1/(sigma+1e-5)) / mean_m(1/(sigma+1e-5))   (models/HRegNet/models.py:30-32,36-38).  sigma, w [B,M]. */
+int hrn_sigma_to_weights(const float* sigma, float* w, int B, int M, void* stream);
+
+/* out[b,n,:] = R[b] x[b,n,:] + t[b]   (models.py:91-92,113-114).  x,out [B,N,3]; R [B,9]; t [B,3]. */
+int hrn_transform_points(const float* x, const float* R, const float* t, float* out, int B, int N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 4. CoarseReg similarity features (layers.py:29-41,290-313,339-362)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* S [B,N1,C], D [B,N2,C] channels-last descriptors -> cosm [B,N2,N1] = <D,S>/(|D||S|+1e-6), rowmax [B,N2]
+ * (max over n1), colmax [B,N1] (max over n2); nS [B,N1], nD [B,N2] scratch norms. */
+int hrn_cosine_matrix(const float* S, const float* D, int B, int N1, int N2, int C, float* nS, float* nD, float* cosm,
+                      float* rowmax, float* colmax, void* stream);
+
+/* out[r, col_src_dst] = cosm[b,idx[r],i]/(colmax[b,i]+1e-6); out[r, col_dst_src] = cosm[b,idx[r],i]/(rowmax[b,idx[r]]
+ * +1e-6), r = (b,i,j) -- the diagonal picks of layers.py:303-313,352-362 without the Python loops. */
+int hrn_cosine_pick(const float* cosm, const float* rowmax, const float* colmax, const int32_t* idx, int B, int N1,
+                    int N2, int k, float* out, int ldo, int col_src_dst, int col_dst_src, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 5. Pose head (layers.py:456-504 WeightedSVDHead; models.py:100-110,120-127 pose composition)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* src, cor [B,N,3]; w [B,N] -> R [B,9] row-major, t [B,3].  With R_prev/t_prev also R_cmp = R R_prev,
+ * t_cmp = R t_prev + t.  Degenerate covariance -> R = I, t = 0 (the reference's SVD-failure fallback). */
+int hrn_weighted_kabsch(const float* src, const float* cor, const float* w, int B, int N, const float* R_prev,
+                        const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, void* stream);
+
+/* Host-side evaluation of the closed form used by hrn_weighted_kabsch (H row-major 3x3, fp64); for tests. */
+int hrn_pose_from_covariance_host(const double* H9, const double* xbar, const double* ybar, double* R9, double* t3);
+
+/* Library / build identification: returns a static string "hregnet_b200 <version> sm_100a". */
+const char* hrn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HREGNET_B200_H */

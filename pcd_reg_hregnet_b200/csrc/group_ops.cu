@@ -1,0 +1,192 @@
+// Per-neighbourhood ("group" = the k rows of one keypoint) reductions and feature assembly, channels-last.
+//
+//   hrn_group_attention   <- layers.py:151-152, 330-331, 385-386, 447-448:  a = softmax_k( max_c E )
+//   hrn_group_weighted_sum<- layers.py:154-159, 332, 388-390, 449-450:      out[g,:] = sum_j a[g,j] * V[row(g,j),:]
+//   hrn_group_max         <- layers.py:202, 208:                            out[g,:] = max_j X[g*k+j,:]
+//   hrn_group_geometry    <- layers.py:20-23 (knn_group), 284-288, 318-319, 364-365, 438-445:
+//                            the small "geometry + weights" channels of every grouped feature tensor
+//   hrn_sigma_to_weights  <- models.py:30-32:  w = 1/(sigma+1e-5); w /= mean(w)
+//   hrn_transform_points  <- models.py:91-92,113-114:  x' = R x + t
+// All are HBM-bound single-pass kernels.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+// one CTA (128 threads) per group; E [G*k, C] (ld = ldE)
+__global__ void __launch_bounds__(128)
+group_attention_kernel(const float* __restrict__ E, int ldE, int C, int k, float* __restrict__ a) {
+    __shared__ float s_x[64];
+    const long long g = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < k; j += 4) {
+        const float* row = E + (g * k + j) * ldE;
+        float m = -CUDART_INF_F;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+        m = hrn_warp_max(m);
+        if (lane == 0) s_x[j] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float v0 = lane < k ? s_x[lane] : -CUDART_INF_F;
+        const float v1 = lane + 32 < k ? s_x[lane + 32] : -CUDART_INF_F;
+        const float mx = hrn_warp_max(fmaxf(v0, v1));
+        const float e0 = lane < k ? expf(v0 - mx) : 0.f;
+        const float e1 = lane + 32 < k ? expf(v1 - mx) : 0.f;
+        const float sum = hrn_warp_sum(e0 + e1);
+        if (lane < k) a[g * k + lane] = e0 / sum;
+        if (lane + 32 < k) a[g * k + lane + 32] = e1 / sum;
+    }
+}
+
+// out[g, c] = sum_j a[g*k+j] * V[src(g,j), c];  src = direct row g*k+j, or b*N + idx[g*k+j]
+__global__ void __launch_bounds__(128)
+group_weighted_sum_kernel(const float* __restrict__ a, const float* __restrict__ V, int ldV, int C, int k,
+                          const int32_t* __restrict__ idx, int groups_per_batch, int N, float* __restrict__ out,
+                          int ldo) {
+    const long long g = blockIdx.x;
+    const long long b = g / groups_per_batch;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const long long r = g * k + j;
+            const long long sr = idx ? b * N + idx[r] : r;
+            acc = fmaf(a[r], V[sr * ldV + c], acc);
+        }
+        out[g * ldo + c] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+group_max_kernel(const float* __restrict__ X, int ldX, int C, int k, float* __restrict__ out, int ldo) {
+    const long long g = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float m = -CUDART_INF_F;
+        for (int j = 0; j < k; ++j) m = fmaxf(m, X[(g * k + j) * ldX + c]);
+        out[g * ldo + c] = m;
+    }
+}
+
+// One thread per row r = (b, m, j).  q [B,M,3] queries, p [B,N,3] references, idx [B,M,k] int32.
+// Writes `out` [rows, ldo] columns:
+//   0..2 rel = p[idx] - q ; 3 = |rel| ;
+//   if (pair): 4..6 q ; 7..9 p[idx] ; 10 = wq[b,m] ; 11 = wp[b,idx]
+// Optionally nn [rows,3] = p[idx].
+__global__ void group_geometry_kernel(const float* __restrict__ q, const float* __restrict__ p,
+                                      const int32_t* __restrict__ idx, const float* __restrict__ wq,
+                                      const float* __restrict__ wp, int pair, long long rows, int M, int k, int N,
+                                      float* __restrict__ out, int ldo, float* __restrict__ nn) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const long long bm = r / k;
+    const long long b = bm / M;
+    const int n = idx[r];
+    const float* qq = q + bm * 3;
+    const float* pp = p + (b * N + n) * 3;
+    const float qx = qq[0], qy = qq[1], qz = qq[2], x = pp[0], y = pp[1], z = pp[2];
+    const float rx = x - qx, ry = y - qy, rz = z - qz;
+    float* o = out + r * ldo;
+    o[0] = rx; o[1] = ry; o[2] = rz;
+    o[3] = sqrtf(rx * rx + ry * ry + rz * rz);
+    if (pair) {
+        o[4] = qx; o[5] = qy; o[6] = qz;
+        o[7] = x; o[8] = y; o[9] = z;
+        o[10] = wq[bm];
+        o[11] = wp[b * N + n];
+    }
+    if (nn) { nn[r * 3 + 0] = x; nn[r * 3 + 1] = y; nn[r * 3 + 2] = z; }
+}
+
+// w[b,:] = (1/(sigma+1e-5)) / mean_m(1/(sigma+1e-5));  one CTA per cloud
+__global__ void __launch_bounds__(256)
+sigma_to_weights_kernel(const float* __restrict__ sigma, float* __restrict__ w, int M) {
+    __shared__ float s_part[8];
+    const float* s = sigma + (size_t)blockIdx.x * M;
+    float* o = w + (size_t)blockIdx.x * M;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) acc += 1.0f / (s[i] + 1e-5f);
+    acc = hrn_warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += s_part[i];
+    const float mean = tot / (float)M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) o[i] = (1.0f / (s[i] + 1e-5f)) / mean;
+}
+
+// out[b,n,:] = R[b] x[b,n,:] + t[b]
+__global__ void transform_points_kernel(const float* __restrict__ x, const float* __restrict__ R,
+                                        const float* __restrict__ t, float* __restrict__ out, long long total, int N) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / N;
+    const float* Rb = R + b * 9;
+    const float* tb = t + b * 3;
+    const float px = x[i * 3 + 0], py = x[i * 3 + 1], pz = x[i * 3 + 2];
+    out[i * 3 + 0] = fmaf(Rb[2], pz, fmaf(Rb[1], py, Rb[0] * px)) + tb[0];
+    out[i * 3 + 1] = fmaf(Rb[5], pz, fmaf(Rb[4], py, Rb[3] * px)) + tb[1];
+    out[i * 3 + 2] = fmaf(Rb[8], pz, fmaf(Rb[7], py, Rb[6] * px)) + tb[2];
+}
+
+}  // namespace
+
+HRN_API int hrn_group_attention(const float* E, int ldE, int C, long long groups, int k, float* a, void* stream) {
+    if (!E || !a || C <= 0 || k <= 0 || k > 64 || groups < 0) return HRN_ERR_BAD_ARG;
+    if (groups == 0) return HRN_OK;
+    group_attention_kernel<<<(unsigned)groups, 128, 0, (cudaStream_t)stream>>>(E, ldE, C, k, a);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_group_weighted_sum(const float* a, const float* V, int ldV, int C, long long groups, int k,
+                                   const int32_t* idx, int groups_per_batch, int N, float* out, int ldo,
+                                   void* stream) {
+    if (!a || !V || !out || C <= 0 || k <= 0 || groups < 0) return HRN_ERR_BAD_ARG;
+    if (groups == 0) return HRN_OK;
+    const int threads = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+    group_weighted_sum_kernel<<<(unsigned)groups, threads, 0, (cudaStream_t)stream>>>(a, V, ldV, C, k, idx,
+                                                                                     groups_per_batch, N, out, ldo);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_group_max(const float* X, int ldX, int C, long long groups, int k, float* out, int ldo,
+                          void* stream) {
+    if (!X || !out || C <= 0 || k <= 0 || groups < 0) return HRN_ERR_BAD_ARG;
+    if (groups == 0) return HRN_OK;
+    const int threads = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+    group_max_kernel<<<(unsigned)groups, threads, 0, (cudaStream_t)stream>>>(X, ldX, C, k, out, ldo);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_group_geometry(const float* q, const float* p, const int32_t* idx, const float* wq, const float* wp,
+                               int B, int M, int k, int N, float* out, int ldo, float* nn, void* stream) {
+    if (!q || !p || !idx || !out || B < 0 || M < 0 || k <= 0 || N <= 0) return HRN_ERR_BAD_ARG;
+    const int pair = (wq && wp) ? 1 : 0;
+    if (ldo < (pair ? 12 : 4)) return HRN_ERR_BAD_ARG;
+    const long long rows = (long long)B * M * k;
+    if (rows == 0) return HRN_OK;
+    group_geometry_kernel<<<hrn_divup(rows, 256), 256, 0, (cudaStream_t)stream>>>(q, p, idx, wq, wp, pair, rows, M, k,
+                                                                                 N, out, ldo, nn);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_sigma_to_weights(const float* sigma, float* w, int B, int M, void* stream) {
+    if (!sigma || !w || B < 0 || M <= 0) return HRN_ERR_BAD_ARG;
+    if (B == 0) return HRN_OK;
+    sigma_to_weights_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(sigma, w, M);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_transform_points(const float* x, const float* R, const float* t, float* out, int B, int N,
+                                 void* stream) {
+    if (!x || !R || !t || !out || B < 0 || N < 0) return HRN_ERR_BAD_ARG;
+    const long long total = (long long)B * N;
+    if (total == 0) return HRN_OK;
+    transform_points_kernel<<<hrn_divup(total, 256), 256, 0, (cudaStream_t)stream>>>(x, R, t, out, total, N);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}

@@ -1,0 +1,232 @@
+// Brute-force exact k-nearest-neighbours for sm_100a.
+//
+// Replaces pytorch3d.ops.knn_points (pytorch3d 0.7.8, third-party, not vendored in the reference); call sites
+// reference models/HRegNet/layers.py:20 (xyz, K=64/32/16), :278 (256-d descriptors, K=8), :316,:322 (self-kNN,
+// K=8), :434 (fine levels, K=8).
+//
+// Contract (stated in oracle/native_ops.c): dist = sum_d (q_d - r_d)^2 in fp32 accumulated
+// sequentially d = 0..D-1 with fma;  K smallest in (dist asc, index asc) order;  squared distances returned.
+//
+// Kernel shape: one WARP per query, the 32 lanes sweep the reference points of the cloud in chunks of 32 from a
+// shared-memory tile that the whole CTA (8 queries of the same cloud) streams through once; the running
+// top-K is a sorted list distributed over the lanes' registers (position s*32+lane), so a candidate test is one
+// compare against the broadcast K-th entry + a ballot, and an insertion is a register shift done with
+// shfl_up -- no shared or local memory per query, nothing spilled to global (pytorch3d keeps the K=64
+// running set of its one-thread-per-query kernel in global memory).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+template <int KPL>
+struct WarpTopK {
+    float d[KPL];
+    int i[KPL];
+    float thr_d;
+    int thr_i;
+    int K;
+    __device__ __forceinline__ void init(int K_) {
+        K = K_;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) { d[s] = CUDART_INF_F; i[s] = 0x7fffffff; }
+        thr_d = CUDART_INF_F; thr_i = 0x7fffffff;
+    }
+    // warp-uniform (xd, xi); keeps the list sorted ascending, drops the last element
+    __device__ __forceinline__ void insert(float xd, int xi, int lane) {
+        float pd[KPL]; int pi[KPL];
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            pd[s] = __shfl_up_sync(0xffffffffu, d[s], 1);
+            pi[s] = __shfl_up_sync(0xffffffffu, i[s], 1);
+            if (s > 0) {
+                const float cd = __shfl_sync(0xffffffffu, d[s - 1], 31);
+                const int ci = __shfl_sync(0xffffffffu, i[s - 1], 31);
+                if (lane == 0) { pd[s] = cd; pi[s] = ci; }
+            } else if (lane == 0) { pd[s] = -CUDART_INF_F; pi[s] = -1; }
+        }
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const bool cur_lt = cand_less(d[s], i[s], xd, xi);
+            const bool prev_lt = cand_less(pd[s], pi[s], xd, xi);
+            const float nd = cur_lt ? d[s] : (prev_lt ? xd : pd[s]);
+            const int ni = cur_lt ? i[s] : (prev_lt ? xi : pi[s]);
+            d[s] = nd; i[s] = ni;
+        }
+        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
+        float td = d[0]; int ti = i[0];
+#pragma unroll
+        for (int s = 1; s < KPL; ++s) if (ks == s) { td = d[s]; ti = i[s]; }
+        thr_d = __shfl_sync(0xffffffffu, td, kl);
+        thr_i = __shfl_sync(0xffffffffu, ti, kl);
+    }
+    // per-lane candidate (cd, ci) (cd = +inf for padding lanes)
+    __device__ __forceinline__ void offer(float cd, int ci, int lane) {
+        unsigned mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float xd = __shfl_sync(0xffffffffu, cd, src);
+            const int xi = __shfl_sync(0xffffffffu, ci, src);
+            if (cand_less(xd, xi, thr_d, thr_i)) insert(xd, xi, lane);
+        }
+    }
+    template <typename F>
+    __device__ __forceinline__ void for_each(int lane, F f) const {
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const int pos = s * 32 + lane;
+            if (pos < K) f(pos, d[s], i[s]);
+        }
+    }
+};
+
+constexpr int KNN_WARPS = 8;
+constexpr int KNN3_TILE = 2048;  // reference points per shared-memory tile (24 KB, AoS: stride-3 is conflict-free)
+
+// D == 3.  p2 [B,N,3]; queries either p1 [B,M,3] or p2 rows selected by q_idx [B,M] (fused FPS gather).
+template <int KPL>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, const float* __restrict__ p2,
+            float* __restrict__ out_d, int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32,
+            float* __restrict__ out_nn, float* __restrict__ out_q, int M, int N, int K) {
+    __shared__ float s_ref[KNN3_TILE * 3];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * KNN_WARPS + warp;
+    const bool qvalid = m < M;
+    p2 += (size_t)b * N * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (qvalid) {
+        const float* q = q_idx ? p2 + (size_t)q_idx[(size_t)b * M + m] * 3 : p1 + ((size_t)b * M + m) * 3;
+        qx = q[0]; qy = q[1]; qz = q[2];
+        if (out_q && lane < 3) out_q[((size_t)b * M + m) * 3 + lane] = q[lane];
+    }
+    WarpTopK<KPL> top;
+    top.init(K);
+    for (int t0 = 0; t0 < N; t0 += KNN3_TILE) {
+        const int tn = min(KNN3_TILE, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) s_ref[i] = __ldg(p2 + (size_t)t0 * 3 + i);
+        __syncthreads();
+        if (qvalid) {
+            for (int c = 0; c < tn; c += 32) {
+                const int n = c + lane;
+                float dist = CUDART_INF_F;
+                if (n < tn) {
+                    const float dx = qx - s_ref[n * 3 + 0], dy = qy - s_ref[n * 3 + 1], dz = qz - s_ref[n * 3 + 2];
+                    dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                }
+                top.offer(dist, t0 + n, lane);
+            }
+        }
+    }
+    if (!qvalid) return;
+    const size_t base = ((size_t)b * M + m) * K;
+    top.for_each(lane, [&](int pos, float d, int i) {
+        if (out_d) out_d[base + pos] = d;
+        if (out_i64) out_i64[base + pos] = (int64_t)i;
+        if (out_i32) out_i32[base + pos] = i;
+        if (out_nn) {
+            const float* r = p2 + (size_t)i * 3;
+            float* o = out_nn + (base + pos) * 3;
+            o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+        }
+    });
+}
+
+// Generic D (descriptor space, D = 256 in CoarseReg).  Sequential fma chain over d per (query, ref) pair.
+constexpr int KNND_REFS = 32;
+template <int KPL>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* __restrict__ out_d,
+            int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn, int M, int N,
+            int D, int K) {
+    extern __shared__ float smem[];
+    float* s_q = smem;                          // [KNN_WARPS][D]
+    float* s_r = smem + KNN_WARPS * D;          // [KNND_REFS][D+1]
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * KNN_WARPS, m = m0 + warp;
+    const bool qvalid = m < M;
+    p1 += (size_t)b * M * D;
+    p2 += (size_t)b * N * D;
+    for (int i = threadIdx.x; i < KNN_WARPS * D; i += blockDim.x) {
+        const int q = i / D;
+        s_q[i] = (m0 + q < M) ? p1[(size_t)(m0 + q) * D + (i - q * D)] : 0.f;
+    }
+    WarpTopK<KPL> top;
+    top.init(K);
+    const int ldr = D + 1;
+    for (int t0 = 0; t0 < N; t0 += KNND_REFS) {
+        const int tn = min(KNND_REFS, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * D; i += blockDim.x) {
+            const int r = i / D;
+            s_r[r * ldr + (i - r * D)] = __ldg(p2 + (size_t)(t0 + r) * D + (i - r * D));
+        }
+        __syncthreads();
+        float dist = CUDART_INF_F;
+        if (qvalid && lane < tn) {
+            dist = 0.f;
+            const float* q = s_q + warp * D;
+            const float* r = s_r + lane * ldr;
+#pragma unroll 8
+            for (int d = 0; d < D; ++d) {
+                const float diff = q[d] - r[d];
+                dist = __fmaf_rn(diff, diff, dist);
+            }
+        }
+        if (qvalid) top.offer(dist, t0 + lane, lane);
+    }
+    if (!qvalid) return;
+    const size_t base = ((size_t)b * M + m) * K;
+    top.for_each(lane, [&](int pos, float d, int i) {
+        if (out_d) out_d[base + pos] = d;
+        if (out_i64) out_i64[base + pos] = (int64_t)i;
+        if (out_i32) out_i32[base + pos] = i;
+    });
+    if (out_nn) {
+        __syncwarp();
+        for (int pos = 0; pos < K; ++pos) {
+            const int s = pos >> 5, l = pos & 31;
+            int iv = top.i[0];
+#pragma unroll
+            for (int t = 1; t < KPL; ++t) if (s == t) iv = top.i[t];
+            const int src = __shfl_sync(0xffffffffu, iv, l);
+            for (int d = lane; d < D; d += 32) out_nn[(base + pos) * D + d] = __ldg(p2 + (size_t)src * D + d);
+        }
+    }
+}
+
+}  // namespace
+
+// p1 [B,M,D] (ignored when q_idx != NULL: queries are p2[b, q_idx[b,m], :], D must be 3), p2 [B,N,D].
+// Outputs (each nullable): dists [B,M,K] f32 squared ascending; idx64 / idx32 [B,M,K]; nn [B,M,K,D];
+// q_out [B,M,3] (the gathered queries, only with q_idx).
+HRN_API int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int D, int K,
+                    float* dists, int64_t* idx64, int32_t* idx32, float* nn, float* q_out, void* stream) {
+    if (!p2 || (!p1 && !q_idx) || B < 0 || M < 0 || N <= 0 || D <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
+    if (K > N || K > 64) return HRN_ERR_UNSUPPORTED;
+    if (q_idx && D != 3) return HRN_ERR_BAD_ARG;
+    if (B == 0 || M == 0) return HRN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(hrn_divup(M, KNN_WARPS), B);
+    if (D == 3) {
+        if (K <= 32) knn3_kernel<1><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
+        else knn3_kernel<2><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
+    } else {
+        const size_t smem = ((size_t)KNN_WARPS * D + (size_t)KNND_REFS * (D + 1)) * sizeof(float);
+        if (smem > 200 * 1024) return HRN_ERR_UNSUPPORTED;
+        if (K <= 32) {
+            if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knnd_kernel<1><<<grid, KNN_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+        } else {
+            if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knnd_kernel<2><<<grid, KNN_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+        }
+    }
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}

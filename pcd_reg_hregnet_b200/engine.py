@@ -1,0 +1,293 @@
+"""Host-side orchestration of the sm_100a kernels for the HRegNet forward path.
+
+Everything here is plumbing: it allocates device buffers with torch, describes the virtual activation
+matrices ("rows", csrc/rows.cuh) and launches kernels through the C ABI on torch's current stream.  The
+arithmetic of the path lives in csrc/*.cu.  Internal layout is channels-last: a tensor of per-neighbour
+features is a [rows, C] matrix with rows = (cloud, keypoint, neighbour) flattened.
+
+Folded parameters (BatchNorm eval statistics merged into the 1x1 convolutions) come from fold.py.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADCAST, SEG_DIRECT, SEG_GATHER, Rows, call,
+                   ptr, stream)
+
+_PRECISION = "fp32"
+
+
+def set_precision(mode: str):
+    """'fp32' = exact CUDA-core FFMA layers; 'tc' = tcgen05 tensor-core layers (bf16x3 split, fp32 accumulate)."""
+    global _PRECISION
+    if mode not in ("fp32", "tc"):
+        raise ValueError(mode)
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _addr(t):
+    return None if t is None else t.data_ptr()
+
+
+class RowsView:
+    """Builder for hrn_rows_t; keeps the referenced tensors alive until the launch has been enqueued."""
+
+    def __init__(self, rows, group=1, gather_idx=None, rows_per_batch=0, src_rows_per_batch=0):
+        self.rows = int(rows)
+        self.c = Rows()
+        self.c.n_seg = 0
+        self.c.group = int(group)
+        self.c.gather_idx = _addr(gather_idx)
+        self.c.rows_per_batch = int(rows_per_batch)
+        self.c.src_rows_per_batch = int(src_rows_per_batch)
+        self.keep = [gather_idx]
+        self.gather_idx = gather_idx
+        self.segs = []          # python-side mirror of the struct (debugging / CPU emulation in tests)
+        self.K = 0
+
+    def add(self, mat, mode=SEG_DIRECT, channels=None, col0=0, row_scale=None):
+        """mat: 2-D view [src_rows, ld] (last dim contiguous)."""
+        assert mat.dim() == 2 and mat.stride(1) == 1 and mat.dtype == torch.float32
+        s = self.c.seg[self.c.n_seg]
+        s.ptr = mat.data_ptr()
+        s.row_scale = _addr(row_scale)
+        s.channels = int(channels if channels is not None else mat.shape[1] - col0)
+        s.ld = int(mat.stride(0))
+        s.col0 = int(col0)
+        s.mode = int(mode)
+        self.c.n_seg += 1
+        self.K += s.channels
+        self.keep += [mat, row_scale]
+        self.segs.append((mat, int(mode), s.channels, int(col0), row_scale))
+        return self
+
+
+def layer(view: RowsView, W, b, act, out=None):
+    """out [rows, Cout] = act(X W^T + b)."""
+    Cout, K = W.shape
+    assert K == view.K, (K, view.K)
+    if out is None:
+        out = torch.empty(view.rows, Cout, dtype=torch.float32, device=W.device)
+    if _PRECISION == "tc":
+        from . import engine_tc
+        return engine_tc.layer_tc(view, W, b, act, out)
+    _launch_layer_fp32(view, W, b, act, out)
+    return out
+
+
+def _launch_layer_fp32(view, W, b, act, out):
+    call("hrn_layer_fp32", ctypes.byref(view.c), ptr(W), ptr(b), act, ptr(out), out.stride(0), view.rows, W.shape[0],
+         stream())
+
+
+def stack(view: RowsView, layers, last_act=None):
+    """Chain of folded layers [(W, b, act), ...] starting from a virtual rows view."""
+    x = None
+    for li, (W, b, act) in enumerate(layers):
+        if li == len(layers) - 1 and last_act is not None:
+            act = last_act
+        v = view if li == 0 else RowsView(x.shape[0]).add(x)
+        x = layer(v, W, b, act)
+    return x
+
+
+def group_attention(E, k):
+    rows, C = E.shape
+    a = torch.empty(rows, dtype=torch.float32, device=E.device)
+    call("hrn_group_attention", ptr(E), E.stride(0), C, rows // k, k, ptr(a), stream())
+    return a
+
+
+def group_weighted_sum(a, V, k, idx=None, groups_per_batch=0, N=0):
+    """out[g,:] = sum_j a[g*k+j] V[row,:]; V is [rows, C] (idx None) or [B*N, C] gathered by idx."""
+    groups = a.shape[0] // k
+    C = V.shape[1]
+    out = torch.empty(groups, C, dtype=torch.float32, device=a.device)
+    call("hrn_group_weighted_sum", ptr(a), ptr(V), V.stride(0), C, groups, k, ptr(idx), groups_per_batch, N, ptr(out),
+         out.stride(0), stream())
+    return out
+
+
+def group_max(X, k):
+    rows, C = X.shape
+    out = torch.empty(rows // k, C, dtype=torch.float32, device=X.device)
+    call("hrn_group_max", ptr(X), X.stride(0), C, rows // k, k, ptr(out), out.stride(0), stream())
+    return out
+
+
+def group_geometry(q, p, idx, wq=None, wp=None, ld=None, want_nn=False):
+    """q [B,M,3], p [B,N,3], idx [B,M,k] int32 -> misc [B*M*k, ld] (+ nn [B*M*k,3])."""
+    B, M, k = idx.shape
+    N = p.shape[1]
+    ncol = 12 if wq is not None else 4
+    ld = ld or ncol
+    out = torch.empty(B * M * k, ld, dtype=torch.float32, device=q.device)
+    nn = torch.empty(B * M * k, 3, dtype=torch.float32, device=q.device) if want_nn else None
+    call("hrn_group_geometry", ptr(q), ptr(p), ptr(idx), ptr(wq), ptr(wp), B, M, k, N, ptr(out), ld, ptr(nn), stream())
+    return out, nn
+
+
+def knn_idx(p1, p2, K, q_idx=None):
+    """int32 neighbour indices [B,M,K] (+ gathered queries when q_idx is given)."""
+    B, N, D = p2.shape
+    M = q_idx.shape[1] if q_idx is not None else p1.shape[1]
+    idx = torch.empty(B, M, K, dtype=torch.int32, device=p2.device)
+    q_out = torch.empty(B, M, 3, dtype=torch.float32, device=p2.device) if q_idx is not None else None
+    call("hrn_knn", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, D, K, None, None, ptr(idx), None,
+         ptr(q_out), stream())
+    return idx, q_out
+
+
+def fps(xyz, M, weights=None):
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, M, dtype=torch.int32, device=xyz.device)
+    temp = None if N <= 16384 else torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+    call("hrn_fps", ptr(xyz), ptr(weights), ptr(temp), ptr(idx), B, N, M, stream())
+    return idx
+
+
+def transpose(x):
+    """[B,R,C] -> [B,C,R] contiguous."""
+    B, R, C = x.shape
+    out = torch.empty(B, C, R, dtype=torch.float32, device=x.device)
+    call("hrn_transpose", ptr(x), ptr(out), B, R, C, stream())
+    return out
+
+
+def sigma_to_weights(sigma):
+    B, M = sigma.shape
+    w = torch.empty_like(sigma)
+    call("hrn_sigma_to_weights", ptr(sigma), ptr(w), B, M, stream())
+    return w
+
+
+def transform_points(x, R, t):
+    B, N, _ = x.shape
+    out = torch.empty_like(x)
+    call("hrn_transform_points", ptr(x), ptr(R), ptr(t), ptr(out), B, N, stream())
+    return out
+
+
+def weighted_kabsch(src, cor, w, prev=None):
+    """-> (R [B,3,3], t [B,3]) and, with prev=(R_prev, t_prev), also the composed (R_c, t_c)."""
+    B, N, _ = src.shape
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=src.device)
+    t = torch.empty(B, 3, dtype=torch.float32, device=src.device)
+    if prev is None:
+        call("hrn_weighted_kabsch", ptr(src), ptr(cor), ptr(w), B, N, None, None, ptr(R), ptr(t), None, None, stream())
+        return R, t
+    Rc, tc = torch.empty_like(R), torch.empty_like(t)
+    call("hrn_weighted_kabsch", ptr(src), ptr(cor), ptr(w), B, N, ptr(prev[0]), ptr(prev[1]), ptr(R), ptr(t), ptr(Rc),
+         ptr(tc), stream())
+    return R, t, Rc, tc
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused stages
+# ------------------------------------------------------------------------------------------------------------------
+
+def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=False):
+    """One hierarchy level: KeypointDetector + DescExtractor (reference layers.py:134-165 + 200-209) without
+    materialising grouped_features / attentive_feature_map.
+
+    xyz [B,N,3]; feat_cl [B,N,C] channels-last or None; weights [B,N] or None (-> weighted FPS).
+    det / desc: folded parameter dicts (fold.py).  Returns dict(xyz [B,M,3], sigmas [B,M], af [B,M,C_o] ,
+    desc [B,M,desc_dim], and with want_maps also the rows-layout G, E, a, idx for the layer-level API)."""
+    B, N, _ = xyz.shape
+    fidx = fps(xyz, M, weights)
+    idx, q = knn_idx(None, xyz, k, q_idx=fidx)
+    geom, nn = group_geometry(q, xyz, idx, want_nn=True)
+    rows = B * M * k
+
+    def grouped():
+        v = RowsView(rows, group=k, gather_idx=idx, rows_per_batch=M * k, src_rows_per_batch=N).add(geom)
+        if feat_cl is not None:
+            v.add(feat_cl.view(B * N, -1), SEG_GATHER)
+        return v
+
+    E = stack(grouped(), det["convs"])
+    a = group_attention(E, k)
+    keypoints = group_weighted_sum(a, nn, k)
+    af = group_weighted_sum(a, E, k)
+    sig = stack(RowsView(B * M).add(af), det["mlp"], last_act=ACT_SOFTPLUS_EPS)
+
+    X1 = stack(grouped(), desc["convs"])
+    X1max = group_max(X1, k)
+    v = RowsView(rows, group=k).add(X1max, SEG_BROADCAST).add(X1).add(E, row_scale=a)
+    H = stack(v, desc["mlp"])
+    d = group_max(H, k)
+    out = dict(xyz=keypoints.view(B, M, 3), sigmas=sig.view(B, M), af=af.view(B, M, -1), desc=d.view(B, M, -1))
+    if want_maps:
+        out.update(geom=geom, E=E, a=a, idx=idx)
+    return out
+
+
+def _tail(F, a_k, idx, dxyz, B, N1, N2, head):
+    """softmax attention over the k candidates, correspondence + confidence (layers.py:385-394, 447-452)."""
+    a = group_attention(F, a_k)
+    cor = group_weighted_sum(a, dxyz.view(B * N2, 3), a_k, idx=idx, groups_per_batch=N1, N=N2)
+    af = group_weighted_sum(a, F, a_k)
+    w = stack(RowsView(B * N1).add(af), head, last_act=ACT_SIGMOID)
+    return cor.view(B, N1, 3), w.view(B, N1), af
+
+
+def fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k=8, want_af=False):
+    """FineReg.forward (reference layers.py:433-454) on channels-last features [B,N,C]."""
+    B, N1, _ = sxyz.shape
+    N2 = dxyz.shape[1]
+    idx, _ = knn_idx(sxyz, dxyz, k)
+    misc, _ = group_geometry(sxyz, dxyz, idx, ssig, dsig)
+    v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
+    v.add(misc).add(sfeat_cl.view(B * N1, -1), SEG_BROADCAST).add(dfeat_cl.view(B * N2, -1), SEG_GATHER)
+    F = stack(v, P["convs_1"])
+    cor, w, af = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
+    return (cor, w, af) if want_af else (cor, w)
+
+
+def _neighbour_aware(xyz, desc_cl, P, k):
+    """Neighbourhood-attentive descriptors (reference layers.py:316-337)."""
+    B, N, C = desc_cl.shape
+    nidx, _ = knn_idx(xyz, xyz, k)
+    geom, _ = group_geometry(xyz, xyz, nidx)
+    v = RowsView(B * N * k, group=k, gather_idx=nidx, rows_per_batch=N * k, src_rows_per_batch=N)
+    v.add(desc_cl.view(B * N, C), SEG_GATHER).add(geom)
+    E = stack(v, P["convs_2"])
+    a = group_attention(E, k)
+    return group_weighted_sum(a, desc_cl.view(B * N, C), k, idx=nidx, groups_per_batch=N, N=N).view(B, N, C)
+
+
+def _cosine_features(S, D, idx, misc, col_sd, col_ds):
+    B, N1, C = S.shape
+    N2 = D.shape[1]
+    k = idx.shape[2]
+    dev = S.device
+    nS = torch.empty(B, N1, device=dev)
+    nD = torch.empty(B, N2, device=dev)
+    cosm = torch.empty(B, N2, N1, device=dev)
+    rowmax = torch.empty(B, N2, device=dev)
+    colmax = torch.empty(B, N1, device=dev)
+    call("hrn_cosine_matrix", ptr(S), ptr(D), B, N1, N2, C, ptr(nS), ptr(nD), ptr(cosm), ptr(rowmax), ptr(colmax), stream())
+    call("hrn_cosine_pick", ptr(cosm), ptr(rowmax), ptr(colmax), ptr(idx), B, N1, N2, k, ptr(misc), misc.stride(0),
+         col_sd, col_ds, stream())
+
+
+def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8):
+    """CoarseReg.forward with use_sim=use_neighbor=True (reference layers.py:273-396)."""
+    B, N1, C = sdesc_cl.shape
+    N2 = dxyz.shape[1]
+    idx, _ = knn_idx(sdesc_cl, ddesc_cl, k)                      # 256-d descriptor space (layers.py:278)
+    misc, _ = group_geometry(sxyz, dxyz, idx, ssig, dsig, ld=16)  # cols 0..11; 12..15 = similarity features
+    _cosine_features(sdesc_cl, ddesc_cl, idx, misc, 12, 13)
+    s_nbr = _neighbour_aware(sxyz, sdesc_cl, P, k)
+    d_nbr = _neighbour_aware(dxyz, ddesc_cl, P, k)
+    _cosine_features(s_nbr, d_nbr, idx, misc, 14, 15)
+    v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
+    v.add(misc).add(sdesc_cl.view(B * N1, C), SEG_BROADCAST).add(ddesc_cl.view(B * N2, C), SEG_GATHER)
+    F = stack(v, P["convs_1"])
+    cor, w, _ = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
+    return cor, w

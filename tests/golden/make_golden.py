@@ -1,0 +1,77 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on the CPU through
+oracle/ref_harness.py (native ops = oracle C restatements).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Fixtures
+  nusc_feats_state.npz     the reference's pretrained HierFeatureExtraction weights (ckpt/pretrained/nusc_feats.pth,
+                           192 tensors) re-saved as npz -- realistic BatchNorm statistics for parity runs.
+  hregnet_b2_n2048.npz     HRegNet.forward (models/HRegNet/models.py:77-148) on 2 seeded synthetic pairs of 2048
+                           points: inputs, every returned tensor, the per-level FPS indices and the coarse kNN idx.
+  hregnet_uniform_b1_n1500.npz  same on the reference's own smoke-test distribution torch.rand (models.py:168-169).
+Registration-head weights are not in the reference repo (.MISSING_LARGE_BLOBS): they are torch.manual_seed(7)
+default initialisations + randomised BatchNorm statistics, re-created identically by tests/common.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import ref_harness as H, ref_layers as RL  # noqa: E402
+from pcd_reg_hregnet_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def flat(out):
+    d = {}
+    for k, v in out.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                d[f"{k}.{kk}"] = vv.numpy()
+        elif isinstance(v, list):
+            for i, vv in enumerate(v):
+                d[f"{k}.{i}"] = vv.numpy()
+        else:
+            d[k] = v.numpy()
+    return d
+
+
+def main():
+    torch.set_num_threads(8)
+    sd = torch.load(H.pretrained_feats_path(), map_location="cpu")
+    np.savez(os.path.join(OUT, "nusc_feats_state.npz"), **{k: v.numpy() for k, v in sd.items()})
+    net = H.build_reference_hregnet(seed=7)
+    full_sd = net.state_dict()
+    cases = {
+        "hregnet_b2_n2048": synth.make_batch([1000, 1001], 2048)[:2],
+        "hregnet_uniform_b1_n1500": (torch.rand(1, 1500, 3, generator=torch.Generator().manual_seed(3)),
+                                     torch.rand(1, 1500, 3, generator=torch.Generator().manual_seed(4))),
+    }
+    for name, (src, dst) in cases.items():
+        with torch.no_grad():
+            out = net(src, dst)
+            trace = {}
+            o2 = RL.hregnet_forward(full_sd, src, dst, trace=trace)      # oracle restatement, for the index traces
+        d = flat(out)
+        # the restatement must reproduce the reference before its traces are stored next to the reference outputs
+        for k, v in flat(o2).items():
+            assert np.allclose(v, d[k], rtol=0, atol=2e-4), (name, k, np.abs(v - d[k]).max())
+        d["src"], d["dst"] = src.numpy(), dst.numpy()
+        for side in ("src", "dst"):
+            for lv in (1, 2, 3):
+                d[f"{side}_fps_idx_{lv}"] = trace[f"{side}_trace"][f"fps_idx_{lv}"].numpy()
+        d["coarse_idx"] = trace["coarse_idx"].numpy()
+        d["fine2_idx"] = trace["fine2_idx"].numpy()
+        d["fine1_idx"] = trace["fine1_idx"].numpy()
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, {k: v.shape for k, v in d.items() if k.startswith("rotation")},
+              sum(v.nbytes for v in d.values()) / 1e6, "MB")
+
+
+if __name__ == "__main__":
+    main()

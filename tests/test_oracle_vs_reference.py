@@ -1,0 +1,80 @@
+"""CPU, build container only: pins the oracle restatement (oracle/ref_layers.py) and the golden fixtures to the
+UNMODIFIED reference Python graph (/root/reference/models/HRegNet) run through oracle/ref_harness.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_harness as H, ref_layers as RL
+from common import Args, build_product_hregnet, load_golden
+from pcd_reg_hregnet_b200 import synth
+
+pytestmark = pytest.mark.skipif(not H.available(), reason="/root/reference not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref_net():
+    torch.set_num_threads(8)
+    return H.build_reference_hregnet(seed=7)
+
+
+def test_feature_extraction_bit_identical(ref_net):
+    src, _, _, _ = synth.make_batch([11], 3000)
+    with torch.no_grad():
+        a = ref_net.feature_extraction(src)
+        b = RL.hier_feature_extraction(ref_net.state_dict(), "feature_extraction.", src)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_full_forward_matches_reference(ref_net):
+    src, dst, _, _ = synth.make_batch([21, 22], 2048)
+    with torch.no_grad():
+        a = ref_net(src, dst)
+        b = RL.hregnet_forward(ref_net.state_dict(), src, dst)
+    for lv in range(3):
+        assert float(RL.rotation_angle_deg(a["rotation"][lv], b["rotation"][lv]).max()) < 1e-4
+        assert float((a["translation"][lv] - b["translation"][lv]).abs().max()) < 1e-5
+    for k in ("src_xyz_corres_3", "src_xyz_corres_2", "src_xyz_corres_1"):
+        assert float((a[k] - b[k]).abs().max()) < 1e-4
+    for k in ("src_dst_weights_3", "src_dst_weights_2", "src_dst_weights_1"):
+        assert float((a[k] - b[k]).abs().max()) < 1e-6
+
+
+def test_layers_stagewise(ref_net):
+    L = H.load_reference().layers
+    sd = ref_net.state_dict()
+    g = torch.Generator().manual_seed(0)
+    sx, dx = torch.randn(2, 256, 3, generator=g) * 20, torch.randn(2, 256, 3, generator=g) * 20
+    sdsc, ddsc = torch.rand(2, 256, 256, generator=g), torch.rand(2, 256, 256, generator=g)
+    sw, dw = torch.rand(2, 256, generator=g) + 0.1, torch.rand(2, 256, generator=g) + 0.1
+    with torch.no_grad():
+        c0, w0 = ref_net.coarse_corres(sx, sdsc, dx, ddsc, sw, dw)
+        c1, w1 = RL.coarse_reg(sd, "coarse_corres.", sx, sdsc, dx, ddsc, sw, dw)
+        assert float((c0 - c1).abs().max()) < 1e-4 and float((w0 - w1).abs().max()) < 1e-6
+        f0 = ref_net.fine_corres_2(sx, sdsc[:, :128], dx, ddsc[:, :128], sw, dw)
+        f1 = RL.fine_reg(sd, "fine_corres_2.", sx, sdsc[:, :128], dx, ddsc[:, :128], sw, dw)
+        assert float((f0[0] - f1[0]).abs().max()) < 1e-4 and float((f0[1] - f1[1]).abs().max()) < 1e-6
+        r0, t0 = ref_net.svd_head(sx, c0, w0)
+        r1, t1 = RL.weighted_svd_head(sx, c0, w0)
+        assert float(RL.rotation_angle_deg(r0, r1).max()) < 1e-4 and float((t0 - t1).abs().max()) < 1e-5
+
+
+def test_product_state_dict_and_seeded_init_equal_reference(ref_net):
+    prod = build_product_hregnet(seed=7)
+    rs, ps = ref_net.state_dict(), prod.state_dict()
+    assert list(rs.keys()) == list(ps.keys())
+    for k in rs:
+        assert rs[k].shape == ps[k].shape and torch.equal(rs[k], ps[k]), k
+    # Model-level API: same constructor contract (args.use_fps, use_weights, freeze_*), models.py:62-75
+    assert sum(p.numel() for p in prod.parameters()) == 2467846
+
+
+def test_golden_fixtures_are_reference_outputs(ref_net):
+    for name in ("hregnet_b2_n2048", "hregnet_uniform_b1_n1500"):
+        gd = load_golden(name)
+        with torch.no_grad():
+            out = ref_net(gd["src"], gd["dst"])
+        for i in range(3):
+            assert torch.equal(out["rotation"][i], gd[f"rotation.{i}"])
+            assert torch.equal(out["translation"][i], gd[f"translation.{i}"])
+        assert torch.equal(out["src_feats"]["desc_3"], gd["src_feats.desc_3"])
