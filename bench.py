@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- HRegNet registration forward, pairs/sec (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs-per-gpu 32] [--points 16384]
+
+A "step" = one pass of the hot path (HRegNet.forward: FPS -> kNN -> grouping -> detector/descriptor MLPs ->
+coarse + fine correspondence -> weighted-SVD poses) over one batch of synthetic 16,384-point LiDAR pairs per GPU
+(BASELINE configs[1]: batch 32, keypoints 1024/512/256), followed -- for N > 1 -- by the NCCL all-gather of poses.
+Weak scaling: 32 pairs per GPU (N=8 -> the 256-pair job of configs[2]).
+
+  value     pairs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       pairs/s through the public API (pcd_reg_hregnet_b200.runner.Registrar) from pinned HOST buffers:
+            H2D copy of both clouds + forward + D2H of the poses inside the timed region
+  roofline  dominant kernel family (shared-MLP layers): algorithmic FLOP / CUDA-event time of those launches
+  cpu_baseline  the oracle port of the reference (oracle/ref_layers.py + oracle/native_ops.c) on the host cores,
+            bounded sample (rank 0, N=1 only)
+  --impl reference   times that CPU implementation as the reference arm (rank 0 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+METRIC = "registration pairs/sec (16k-pt HRegNet fwd)"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=32)
+    ap.add_argument("--points", type=int, default=16384)
+    ap.add_argument("--precision", default=os.environ.get("HRN_PRECISION", "auto"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_pairs_per_s(n_pairs, n_points, reps=1):
+    """The reference's CPU path (oracle port: reference graph restated in torch-CPU over the C native ops)."""
+    from common import build_product_hregnet
+    from oracle import ref_layers as RL
+    from pcd_reg_hregnet_b200 import synth
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd = build_product_hregnet(seed=7).state_dict()
+    src, dst, _, _ = synth.make_batch(range(1000, 1000 + n_pairs), n_points)
+    with torch.no_grad():
+        RL.hregnet_forward(sd, src[:1], dst[:1])                      # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for i in range(n_pairs):
+                RL.hregnet_forward(sd, src[i:i + 1], dst[i:i + 1])
+        dt = time.perf_counter() - t0
+    return n_pairs * reps / dt, cores, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    per_step = 2                                                       # bounded sample: 2 pairs per "step"
+    from common import build_product_hregnet
+    from oracle import ref_layers as RL
+    from pcd_reg_hregnet_b200 import synth
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd = build_product_hregnet(seed=7).state_dict()
+    src, dst, _, _ = synth.make_batch(range(1000, 1000 + per_step), args.points)
+    with torch.no_grad():
+        for _ in range(max(1, min(warm, 2))):
+            RL.hregnet_forward(sd, src[:1], dst[:1])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for i in range(per_step):
+                RL.hregnet_forward(sd, src[i:i + 1], dst[i:i + 1])
+        dt = time.perf_counter() - t0
+    v = steps * per_step / dt
+    sample = f"{per_step} pairs x {args.points} pts per step, B=1 forwards, {steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"HRegNet forward, synthetic {args.points}-pt LiDAR pairs, CPU oracle port of the reference",
+                   "pairs_per_step": per_step, "points": args.points},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from common import build_product_hregnet
+    from pcd_reg_hregnet_b200 import _lib, dist as hdist, engine, synth
+    from pcd_reg_hregnet_b200.runner import Registrar
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision
+    if precision == "auto":
+        precision = "tc" if hasattr(_lib.lib(), "hrn_layer_tc") else "fp32"
+    engine.set_precision(precision)
+
+    B, N = args.pairs_per_gpu, args.points
+    lo = rank * B
+    src_h, dst_h, _, _ = synth.make_batch(range(1000 + lo, 1000 + lo + B), N)
+    src_h, dst_h = src_h.pin_memory(), dst_h.pin_memory()
+    net = build_product_hregnet(seed=7, device=dev)
+    reg = Registrar(net, B, N, use_cuda_graph=not args.no_graph)
+    reg.load(src_h, dst_h)
+    reg.capture()
+
+    # kernel launch accounting (claims): count C-ABI calls of one eager forward
+    launches = _count_launches(reg)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step():
+        out = reg.run_device()
+        if world > 1:
+            hdist.gather_poses(out["rotation"][-1], out["translation"][-1])
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for s, e in ev:
+        flush.fill_(1)                                                  # L2 flush between timed iterations (untimed)
+        s.record()
+        step()
+        e.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_ms = sum(s.elapsed_time(e) for s, e in ev)
+
+    # ---- end to end through the public API, host buffers -------------------------------------------------------
+    for _ in range(2):
+        reg(src_h, dst_h)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R_h, t_h = reg(src_h, dst_h, sync=True)
+        if world > 1:
+            hdist.gather_poses(reg.out["rotation"][-1], reg.out["translation"][-1])
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+
+    tt = torch.tensor([t_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms, e2e_ms = tt.tolist()
+
+    # ---- per-kernel-family breakdown + roofline of the dominant family (rank 0) ---------------------------------
+    prof = _profile_families(reg, steps=min(args.steps, 3)) if rank == 0 else None
+
+    if rank == 0:
+        pk = peaks()
+        total_pairs = B * world * args.steps
+        value = total_pairs / (t_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32" if precision == "fp32" else "bf16x3 (tcgen05, fp32 accumulate) + fp32",
+            "data": "synthetic",
+            "config": {"workload": f"HRegNet baseline forward, batch {B} synthetic {N}-pt pairs per GPU (keypoints 1024/512/256)",
+                       "pairs_per_gpu": B, "points": N, "parallelism": f"pairs sharded over {world} GPU(s), pose all-gather",
+                       "l2": "L2 flushed (256 MiB write) between timed iterations", "cuda_graph": not args.no_graph,
+                       "precision": precision},
+            "clocks": clocks,
+            "e2e": {"value": total_pairs / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * B * N * 3 * 4, "d2h_bytes_per_step": B * 12 * 4},
+            "gpu_launches": launches * args.steps,
+            "kernel_breakdown_ms_per_step": prof["families"],
+            "roofline": prof["roofline"](pk),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, dt = cpu_reference_pairs_per_s(args.cpu_sample_pairs, N)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample_pairs} pairs x {N} pts, B=1 forwards, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# kernels launched per C-ABI call (for the gpu_launches claim)
+_KERNELS_PER_CALL = {"hrn_cosine_matrix": 4}
+
+
+def _count_launches(reg):
+    from pcd_reg_hregnet_b200 import engine
+    n = [0]
+    orig = engine.call
+
+    def counting(name, *a):
+        n[0] += _KERNELS_PER_CALL.get(name, 1)
+        return orig(name, *a)
+
+    engine.call = counting
+    try:
+        reg._forward()
+        torch.cuda.synchronize()
+    finally:
+        engine.call = orig
+    return n[0]
+
+
+def _profile_families(reg, steps=3):
+    """Eager (non-graph) instrumented passes: CUDA events around every C-ABI call on the launching stream,
+    aggregated per kernel family; algorithmic FLOP counted for the shared-MLP layer launches."""
+    from pcd_reg_hregnet_b200 import engine
+    rec = []
+    orig = engine.call
+
+    def timed(name, *a):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(name, *a)
+        e.record()
+        fl = 0.0
+        if name.startswith("hrn_layer"):
+            view_rows, cout = a[6], a[7]
+            rows_t = a[0]._obj
+            K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
+            fl = 2.0 * view_rows * K * cout
+        rec.append((name, s, e, fl))
+        return r
+
+    engine.call = timed
+    try:
+        for _ in range(steps):
+            reg._forward()
+        torch.cuda.synchronize()
+    finally:
+        engine.call = orig
+    fam, flops = {}, {}
+    for name, s, e, fl in rec:
+        fam[name] = fam.get(name, 0.0) + s.elapsed_time(e) / steps
+        flops[name] = flops.get(name, 0.0) + fl / steps
+    fam = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
+    layer_names = [n for n in fam if n.startswith("hrn_layer")]
+    layer_ms = sum(fam[n] for n in layer_names)
+    layer_fl = sum(flops[n] for n in layer_names)
+    n_layer = sum(1 for r in rec if r[0].startswith("hrn_layer")) / steps
+
+    def roofline(pk):
+        ach = layer_fl / (layer_ms / 1e3) / 1e12 if layer_ms > 0 else 0.0
+        return {"kernel": "+".join(layer_names) + " (shared-MLP layers)", "bound": "tensor", "achieved": ach,
+                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": n_layer, "ms_per_step": layer_ms, "share_of_step": layer_ms / sum(fam.values()),
+                "algorithmic_gflop_per_step": layer_fl / 1e9}
+
+    return {"families": {k: round(v, 4) for k, v in fam.items()}, "roofline": roofline}
+
+
+if __name__ == "__main__":
+    main()
