@@ -106,6 +106,13 @@ typedef struct {
 int hrn_layer_fp32(const hrn_rows_t* in, const float* W, const float* bias, int act, float* Y, int ldy,
                    long long rows, int Cout, void* stream);
 
+/* Tensor-core variant of hrn_layer_fp32 (tcgen05.mma kind::f16, bf16 hi/lo split of both operands, three products
+ * per MAC, fp32 accumulation in TMEM; relative error ~2^-16).  Wp = weights pre-split / pre-tiled on the host as
+ * [n_stage][hi|lo][4][NP][8] bf16 (pcd_reg_hregnet_b200/engine_tc.py), NP = Cout padded to a multiple of 16
+ * (512 if > 256), K padded per segment to a multiple of 8 and in total to 32 * n_stage. */
+int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
+                 int Cout, int NP, int n_stage, void* stream);
+
 /* a[g*k+j] = softmax_j( max_c E[g*k+j, c] )   (layers.py:151-152,330-331,385-386,447-448).  k <= 64. */
 int hrn_group_attention(const float* E, int ldE, int C, long long groups, int k, float* a, void* stream);
 

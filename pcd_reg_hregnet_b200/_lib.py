@@ -37,6 +37,7 @@ SIGNATURES = {
     "hrn_gather_rows": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_transpose": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_layer_fp32": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp],
+    "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
     "hrn_group_weighted_sum": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "hrn_group_max": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_vp],

@@ -1,0 +1,76 @@
+"""GPU: the tcgen05 shared-MLP layer (csrc/mlp_tc.cu, bf16x3 split) against an fp64 evaluation of the same
+virtual-rows GEMM, and against the exact-fp32 CUDA-core layer.  Tolerance: 1e-4 relative to the tensor maximum
+(the path's feature gate is 1e-3)."""
+import pytest
+import torch
+
+from pcd_reg_hregnet_b200 import engine
+from pcd_reg_hregnet_b200.engine import SEG_BROADCAST, SEG_GATHER, RowsView
+from pcd_reg_hregnet_b200._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ref(view_cols, W, b, act):
+    y = view_cols.double() @ W.double().t() + b.double()
+    if act == ACT_RELU:
+        y = torch.relu(y)
+    elif act == ACT_SIGMOID:
+        y = torch.sigmoid(y)
+    elif act == ACT_SOFTPLUS_EPS:
+        y = torch.nn.functional.softplus(y) + 0.001
+    return y
+
+
+def _check(view, cols, Cout, act, seed):
+    g = torch.Generator().manual_seed(seed)
+    K = cols.shape[1]
+    W = (torch.randn(Cout, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    want = _ref(cols, W, b, act)
+    engine.set_precision("tc")
+    try:
+        got = engine.layer(view, W, b, act)
+    finally:
+        engine.set_precision("fp32")
+    got32 = engine.layer(view, W, b, act)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    e_tc = float((got.double() - want).abs().max()) / scale
+    e_32 = float((got32.double() - want).abs().max()) / scale
+    assert e_32 < 1e-5, e_32
+    assert e_tc < 1e-4, (e_tc, e_32)
+    return e_tc
+
+
+@pytest.mark.parametrize("rows,K,Cout,act", [
+    (128, 32, 32, ACT_RELU), (256, 64, 64, ACT_RELU), (1000, 4, 32, ACT_RELU), (4096, 132, 128, ACT_RELU),
+    (640, 256, 256, ACT_RELU), (384, 528, 512, ACT_RELU), (300, 512, 1, ACT_SIGMOID), (777, 64, 1, ACT_SOFTPLUS_EPS),
+    (130, 768, 128, ACT_NONE), (65536, 32, 64, ACT_RELU),
+])
+def test_direct_rows(rows, K, Cout, act):
+    g = torch.Generator().manual_seed(rows + K)
+    X = torch.randn(rows, K, generator=g).to(DEV)
+    e = _check(RowsView(rows).add(X), X, Cout, act, seed=K + Cout)
+    print(f"rows={rows} K={K} Cout={Cout}: tc rel err {e:.2e}")
+
+
+def test_segments_gather_broadcast_scale():
+    g = torch.Generator().manual_seed(0)
+    B, M, k, N, C = 3, 40, 8, 100, 64
+    rows = B * M * k
+    misc = torch.randn(rows, 16, generator=g).to(DEV)
+    src = torch.randn(B * M, C, generator=g).to(DEV)
+    dst = torch.randn(B * N, C, generator=g).to(DEV)
+    a = torch.rand(rows, generator=g).to(DEV)
+    idx = torch.randint(0, N, (B, M, k), generator=g).int().to(DEV)
+    v = RowsView(rows, group=k, gather_idx=idx, rows_per_batch=M * k, src_rows_per_batch=N)
+    v.add(misc, channels=12).add(src, SEG_BROADCAST).add(dst, SEG_GATHER, row_scale=a)
+    r = torch.arange(rows, device=DEV)
+    gathered = dst[(r // (M * k)) * N + idx.view(-1).long()] * a[:, None]
+    cols = torch.cat([misc[:, :12], src[r // k], gathered], dim=1)
+    _check(v, cols, 128, ACT_RELU, seed=5)
+    # strided source / column offset
+    v2 = RowsView(rows).add(misc, channels=5, col0=3).add(misc, channels=4, col0=12)
+    _check(v2, torch.cat([misc[:, 3:8], misc[:, 12:16]], 1), 48, ACT_RELU, seed=6)
