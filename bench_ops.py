@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""PointUtils micro-benchmark sweep (BASELINE configs[4]): FPS / kNN / grouping-gather at N = 4k..131k points,
+CUDA-event timed through the public ops, optionally next to the recompiled reference kernels (oracle/_ref)."""
+import argparse
+import importlib.util
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from pcd_reg_hregnet_b200 import engine, ops  # noqa: E402
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+def ref_ext():
+    so = os.path.join(ROOT, "oracle", "_ref", "point_utils_cuda.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("point_utils_cuda", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="4096,8192,16384,32768,65536,131072")
+    ap.add_argument("--batches", default="1,32,64")
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    ref = ref_ext()
+    rows = []
+    for B in [int(b) for b in a.batches.split(",")]:
+        for N in [int(n) for n in a.sizes.split(",")]:
+            if B * N > 64 * 65536:
+                continue
+            xyz = torch.rand(B, N, 3, device="cuda") * 100
+            M = 1024
+            t_fps = timeit(lambda: ops.furthest_point_sample(xyz, M))
+            r = {"op": "fps", "B": B, "N": N, "M": M, "ms": t_fps, "us_per_iter": 1e3 * t_fps / (M - 1)}
+            if ref is not None and N <= 65536:
+                temp = torch.empty(B, N, device="cuda")
+                out = torch.empty(B, M, dtype=torch.int32, device="cuda")
+
+                def run_ref():
+                    temp.fill_(1e10)
+                    ref.furthest_point_sampling_wrapper(B, N, M, xyz, temp, out)
+                r["ref_kernel_ms"] = timeit(run_ref, reps=2, warm=1)
+            rows.append(r)
+            print(json.dumps(r), flush=True)
+            if a.quick:
+                continue
+            idx = ops.furthest_point_sample(xyz, M)
+            for K in (16, 32, 64):
+                t = timeit(lambda: engine.knn_idx(None, xyz, K, q_idx=idx))
+                r = {"op": "knn", "B": B, "N": N, "M": M, "K": K, "ms": t, "Gpair_per_s": B * M * N / t / 1e6}
+                rows.append(r)
+                print(json.dumps(r), flush=True)
+    return rows
+
+
+if __name__ == "__main__":
+    main()

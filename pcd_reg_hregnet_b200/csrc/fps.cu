@@ -164,6 +164,191 @@ fps_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, flo
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cluster variant: CS CTAs (thread-block cluster) cooperate on ONE cloud; every point lives in registers
+// (x, y, z, running min-distance [, weight]) -- no shared-memory traffic in the update loop at all.
+// Per iteration (3 CTA barriers; warps that are not on the critical path are parked at a hardware barrier, they
+// never spin):
+//   A. every thread updates its P points (8 FP instructions each), warp maximum by REDUX, barrier;
+//   B. only the warps that hold the CTA maximum resolve the reference's tie-break key and publish {key, xyz}, barrier;
+//   C. warp 0 picks the CTA winner and sends it as a 32-byte packet to the mailbox of every CTA of the cluster with
+//      st.async (distributed shared memory; the store itself performs complete_tx on the receiver's mbarrier), waits
+//      on its own mbarrier for the CS packets of this iteration, takes the best, barrier.
+// Mailboxes / mbarriers are double-buffered by iteration parity: a CTA can run at most one iteration ahead of its
+// peers because iteration j+1 needs every peer's packet j.
+struct __align__(16) FpsMail {
+    unsigned ordval, key;
+    float x, y;
+    float z;
+    unsigned pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int THREADS, int P, bool WEIGHTED>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, float* __restrict__ temp_io,
+                   int32_t* __restrict__ idx_out, int N, int M, int log2T, int CS) {
+    constexpr int NWARP = THREADS / 32;
+    __shared__ unsigned s_wmax[32];
+    __shared__ FpsMail s_slot[32];
+    __shared__ FpsMail s_mail[2][8];
+    __shared__ FpsMail s_best;
+    __shared__ __align__(8) uint64_t s_mbar[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int b = blockIdx.x / CS;
+    xyz += (size_t)b * N * 3;
+    if (WEIGHTED) weights += (size_t)b * N;
+    if (temp_io) temp_io += (size_t)b * N;
+    idx_out += (size_t)b * M;
+    const unsigned tmask = (1u << log2T) - 1u;
+    auto key_of = [&](int k) -> unsigned {
+        const unsigned r = (log2T > 0) ? (__brev((unsigned)k & tmask) >> (32 - log2T)) : 0u;
+        return (r << 12) | ((unsigned)k >> log2T);
+    };
+    const int stride = CS * THREADS;
+    const int k0 = (int)rank * THREADS + tid;
+
+    float px[P], py[P], pz[P], pt[P], pw[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int k = k0 + p * stride;
+        const bool valid = k < N;
+        px[p] = valid ? xyz[k * 3 + 0] : 0.f;
+        py[p] = valid ? xyz[k * 3 + 1] : 0.f;
+        pz[p] = valid ? xyz[k * 3 + 2] : 0.f;
+        pw[p] = (WEIGHTED && valid) ? weights[k] : 0.f;
+        pt[p] = valid ? (temp_io ? temp_io[k] : 1e10f) : -CUDART_INF_F;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&s_mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&s_mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
+    if (tid == 0 && rank == 0) idx_out[0] = 0;
+    __syncthreads();
+    if (CS > 1) {   // every CTA of the cluster has initialised its mbarriers before anyone signals them remotely
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+
+    for (int j = 1; j < M; ++j) {
+        // ---- A: update, warp maximum --------------------------------------------------------------------------
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            float d = fps_dist(px[p], py[p], pz[p], x1, y1, z1);
+            if (WEIGHTED) d = __fmul_rn(pw[p], d);
+            pt[p] = fminf(d, pt[p]);
+            m = fmaxf(m, pt[p]);
+        }
+        const unsigned om = hrn_ford(m);
+        const unsigned wm = __reduce_max_sync(0xffffffffu, om);
+        if (lane == 0) s_wmax[warp] = wm;
+        __syncthreads();
+        // ---- B: holders of the CTA maximum resolve the tie-break key ---------------------------------------------
+        const unsigned g = __reduce_max_sync(0xffffffffu, lane < NWARP ? s_wmax[lane] : 0u);
+        if (wm == g) {                                   // warp-uniform
+            unsigned key = 0xffffffffu;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            if (om == g) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const int k = k0 + p * stride;
+                    const unsigned kk = key_of(k);
+                    if (k < N && pt[p] == m && kk < key) { key = kk; cx = px[p]; cy = py[p]; cz = pz[p]; }
+                }
+            }
+            const unsigned wkey = __reduce_min_sync(0xffffffffu, key);
+            if (key == wkey && om == g) {
+                s_slot[warp].key = key; s_slot[warp].x = cx; s_slot[warp].y = cy; s_slot[warp].z = cz;
+            }
+        } else if (lane == 0) {
+            s_slot[warp].key = 0xffffffffu;
+        }
+        __syncthreads();
+        // ---- C: warp 0 = CTA winner, cluster exchange ------------------------------------------------------------
+        if (warp == 0) {
+            const unsigned k2 = lane < NWARP ? s_slot[lane].key : 0xffffffffu;
+            const unsigned kmin = __reduce_min_sync(0xffffffffu, k2);
+            const int src = __ffs(__ballot_sync(0xffffffffu, k2 == kmin)) - 1;
+            const float sx = s_slot[src].x, sy = s_slot[src].y, sz = s_slot[src].z;
+            unsigned bkey = kmin;
+            float bx = sx, by = sy, bz = sz;
+            if (CS > 1) {
+                const int par = j & 1;
+                const uint32_t mb = fps_smem_u32(&s_mbar[par]);
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(CS * 32) : "memory");
+                if (lane < CS) {
+                    uint32_t rbox, rbar;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbox) : "r"(fps_smem_u32(&s_mail[par][rank])), "r"((unsigned)lane));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(mb), "r"((unsigned)lane));
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                 ::"r"(rbox), "r"(g), "r"(kmin), "r"(__float_as_uint(sx)), "r"(__float_as_uint(sy)), "r"(rbar) : "memory");
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                 ::"r"(rbox + 16), "r"(__float_as_uint(sz)), "r"(0u), "r"(0u), "r"(0u), "r"(rbar) : "memory");
+                }
+                unsigned done;
+                const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;   // u-th use of mbarrier j&1, u = (j-1)/2
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+                } while (!done);
+                unsigned bval = 0u;
+                bkey = 0xffffffffu;
+#pragma unroll 1
+                for (int c = 0; c < CS; ++c) {
+                    const FpsMail mm = s_mail[par][c];
+                    if (mm.ordval > bval || (mm.ordval == bval && mm.key < bkey)) {
+                        bval = mm.ordval; bkey = mm.key; bx = mm.x; by = mm.y; bz = mm.z;
+                    }
+                }
+            }
+            if (lane == 0) { s_best.key = bkey; s_best.x = bx; s_best.y = by; s_best.z = bz; }
+        }
+        __syncthreads();
+        x1 = s_best.x; y1 = s_best.y; z1 = s_best.z;
+        if (tid == 0 && rank == 0) {
+            const unsigned bkey = s_best.key;
+            const unsigned r = bkey >> 12;
+            const int lo = (log2T > 0) ? (int)(__brev(r) >> (32 - log2T)) : 0;
+            idx_out[j] = lo + (int)((bkey & 0xfffu) << log2T);
+        }
+    }
+    if (temp_io) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int k = k0 + p * stride;
+            if (k < N) temp_io[k] = pt[p];
+        }
+    }
+    if (CS > 1) {   // nobody leaves while a peer may still write into its mailbox
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+}
+
+template <int THREADS, int P, bool W>
+int launch_fps_cluster(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
+                       int CS, cudaStream_t st) {
+    auto kern = fps_cluster_kernel<THREADS, P, W>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * CS);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    HRN_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, w, temp, idx, N, M, log2T, CS));
+    return HRN_OK;
+}
+
 template <int THREADS, int P, bool W>
 int launch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
                cudaStream_t st) {
@@ -180,13 +365,23 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
     // opt_n_threads (cuda_utils.h:22-27): 2^floor(log2 N) clamped to [1,1024]  (defines the tie-break only)
     int log2T = 0;
     while ((2 << log2T) <= N && log2T < 10) ++log2T;
-    if (N <= 256) return launch_fps<256, 1, W>(xyz, w, temp, idx, B, N, M, log2T, st);
-    if (N <= 512) return launch_fps<256, 2, W>(xyz, w, temp, idx, B, N, M, log2T, st);
-    if (N <= 1024) return launch_fps<256, 4, W>(xyz, w, temp, idx, B, N, M, log2T, st);
-    if (N <= 2048) return launch_fps<512, 4, W>(xyz, w, temp, idx, B, N, M, log2T, st);
-    if (N <= 4096) return launch_fps<512, 8, W>(xyz, w, temp, idx, B, N, M, log2T, st);
-    if (N <= 8192) return launch_fps<512, 16, W>(xyz, w, temp, idx, B, N, M, log2T, st);
-    if (N <= 16384) return launch_fps<512, 32, W>(xyz, w, temp, idx, B, N, M, log2T, st);
+    // all-in-registers cluster kernel: cluster size = largest of {8,4,2,1} that keeps one wave (B*CS <= 148 SMs)
+    // while P = ceil(N / (CS*THREADS)) <= 8 points per thread
+    if (N <= 1024) {
+        if (N <= 256) return launch_fps_cluster<256, 1, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
+        if (N <= 512) return launch_fps_cluster<256, 2, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
+        return launch_fps_cluster<256, 4, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
+    }
+    if (N <= 65536) {
+        int CS = 8;
+        while (CS > 1 && B * CS > 148) CS >>= 1;
+        while (CS < 8 && (N + CS - 1) / CS > (W ? 4096 : 8192)) CS <<= 1;
+        const int n_cta = (N + CS - 1) / CS;          // points per CTA
+        if (n_cta <= 1024) return launch_fps_cluster<1024, 1, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+        if (n_cta <= 2048) return launch_fps_cluster<1024, 2, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+        if (n_cta <= 4096) return launch_fps_cluster<1024, 4, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+        if (n_cta <= 8192 && !W) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    }
     if (N > (4096 << 10) || temp == nullptr) return HRN_ERR_BAD_ARG;   // streaming path needs the scratch buffer
     return launch_fps<1024, 0, W>(xyz, w, temp, idx, B, N, M, log2T, st);
 }

@@ -21,7 +21,7 @@
 //   epilogue: tcgen05.ld 32 columns at a time -> +bias -> activation -> 128-byte row segments to HBM.
 #include "common.cuh"
 #include "rows.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace {
 
@@ -29,79 +29,41 @@ constexpr int TM = 128;       // rows per CTA (UMMA M)
 constexpr int KC = 32;        // K per pipeline stage (two K=16 MMA steps)
 constexpr int A_STAGE_BYTES = 2 /*hi,lo*/ * (KC / 8) * TM * 16;   // 16 KB
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Per-thread description of the virtual row: up to 4 segments, resolved once per CTA.
+struct RowSrc {
+    const float* p[4];     // row base pointer per segment (nullptr: row out of range)
+    float sc[4];           // per-row scale per segment
+    int c0[5];             // first 8-wide K chunk of each segment; c0[4] = total chunks
+    int ch[4];             // channels per segment
+};
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
-// LBO = byte distance between the two K-halves (core matrices adjacent in K), SBO = between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-        "%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ float act_fn(float v, int act) {
-    if (act == HRN_ACT_RELU) return fmaxf(v, 0.f);
-    if (act == HRN_ACT_SOFTPLUS_EPS) return (v > 20.f ? v : log1pf(expf(v))) + 0.001f;
-    if (act == HRN_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
-    return v;
-}
-
-// split 8 floats into bf16 hi / lo and store both 16-byte core-matrix rows
-__device__ __forceinline__ void split_store8(const float (&x)[8], uint4* dst_hi, uint4* dst_lo) {
-    uint32_t hi[4], lo[4];
+// Fetch the 8 floats of global chunk `cg` of this thread's row as two predicated 16-byte loads (FAST: every
+// segment has channels % 4 == 0 and 16-byte aligned rows, checked on the host) -- no divergent control flow, so
+// the compiler batches the loads of a whole stage.
+template <bool FAST>
+__device__ __forceinline__ void load_chunk(const RowSrc& rs, int cg, float4& v0, float4& v1, float& sc) {
+    int sgi = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-        const float2 hf = __bfloat1622float2(h);
-        const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
-        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    for (int q = 1; q < 4; ++q) if (cg >= rs.c0[q]) sgi = q;
+    const float* p = rs.p[0]; int cs = rs.c0[0], chn = rs.ch[0]; sc = rs.sc[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) if (sgi == q) { p = rs.p[q]; cs = rs.c0[q]; chn = rs.ch[q]; sc = rs.sc[q]; }
+    const int ch0 = (cg - cs) << 3;
+    const int nvalid = (p != nullptr && cg < rs.c0[4]) ? chn - ch0 : 0;
+    v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
+    if (FAST) {
+        if (nvalid >= 4) v0 = __ldg(reinterpret_cast<const float4*>(p + ch0));
+        if (nvalid >= 8) v1 = __ldg(reinterpret_cast<const float4*>(p + ch0) + 1);
+    } else {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = (e < nvalid) ? __ldg(p + ch0 + e) : 0.f;
+        v0 = make_float4(x[0], x[1], x[2], x[3]); v1 = make_float4(x[4], x[5], x[6], x[7]);
     }
-    *dst_hi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *dst_lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // Wp: packed weights [n_stage][2 (hi,lo)][KC/8][NP][8] bf16;  NP = padded Cout (multiple of 16, <= 512)
+template <bool FAST>
 __global__ void __launch_bounds__(TM)
 layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
                 float* __restrict__ Y, int ldy, long long rows, int Cout, int NP, int n_stage, int tmem_cols) {
@@ -120,37 +82,46 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
     if (tid == 0) {
         for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // first weight stage can fly while TMEM is allocated and the rows are resolved
+        mbar_expect_tx(bar_w[0], w_stage_bytes);
+        bulk_g2s(smem_u32(sW[0]), Wp, w_stage_bytes, bar_w[0]);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
 
     // ---- per-thread row bookkeeping ------------------------------------------------------------------------
     const long long r = (long long)blockIdx.x * TM + tid;
     const bool rvalid = r < rows;
-    const float* sp[4];
-    float rscale[4];
-    int cstart[5];                     // first 8-wide K chunk of each segment
-    cstart[0] = 0;
+    RowSrc rs;
+    int run = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        sp[s] = nullptr; rscale[s] = 1.f;
-        int nch = 0;
+        rs.p[s] = nullptr; rs.sc[s] = 1.f; rs.ch[s] = 0;
+        rs.c0[s] = 0x7fffffff;                      // unused segments never match a chunk index
         if (s < in.n_seg) {
             const hrn_seg_t sg = in.seg[s];
-            nch = (sg.channels + 7) >> 3;
+            rs.c0[s] = run;
+            run += (sg.channels + 7) >> 3;
+            rs.ch[s] = sg.channels;
             if (rvalid) {
-                sp[s] = sg.ptr + hrn_src_row(in, sg.mode, r) * sg.ld + sg.col0;
-                if (sg.row_scale) rscale[s] = __ldg(sg.row_scale + r);
+                rs.p[s] = sg.ptr + hrn_src_row(in, sg.mode, r) * sg.ld + sg.col0;
+                if (sg.row_scale) rs.sc[s] = __ldg(sg.row_scale + r);
             }
         }
-        cstart[s + 1] = cstart[s] + nch;
     }
+    rs.c0[4] = run;                                 // total number of 8-wide chunks
+
+    float4 cur[KC / 4];
+    float csc[KC / 8];
+#pragma unroll
+    for (int c = 0; c < KC / 8; ++c) load_chunk<FAST>(rs, c, cur[2 * c], cur[2 * c + 1], csc[c]);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
 
     // instruction descriptor: D=f32, A=B=bf16, K-major both, N, M=128
     const int NH = NP > 256 ? 256 : NP;                       // columns per MMA
@@ -160,42 +131,21 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
     for (int i = 0; i < n_stage; ++i) {
         const int s = i & 1;
         if (i >= 2) mbar_wait(bar_m[s], ((i >> 1) - 1) & 1);          // MMAs of chunk i-2 have drained this stage
-        if (tid == 0) {
-            mbar_expect_tx(bar_w[s], w_stage_bytes);
-            bulk_g2s(smem_u32(sW[s]), Wp + (size_t)i * (w_stage_bytes / 2), w_stage_bytes, bar_w[s]);
-        }
-        // ---- A operand: this thread's row, KC/8 chunks of 8 -------------------------------------------------
+        // ---- A operand: split this thread's 32 fp32 into bf16 hi/lo core-matrix rows ------------------------
         uint4* a_hi = reinterpret_cast<uint4*>(sA[s]);
         uint4* a_lo = a_hi + (KC / 8) * TM;
 #pragma unroll
         for (int c = 0; c < KC / 8; ++c) {
-            const int cg = i * (KC / 8) + c;                          // global 8-chunk index
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = 0.f;
-            int sgi = 0;
-#pragma unroll
-            for (int q = 1; q < 4; ++q) if (cg >= cstart[q]) sgi = q;
-            if (rvalid && cg < cstart[4] && sgi < in.n_seg) {
-                const int ch0 = (cg - cstart[sgi]) << 3;
-                const int nvalid = min(8, in.seg[sgi].channels - ch0);
-                const float* p = sp[0];
-                float sc = rscale[0];
-#pragma unroll
-                for (int q = 1; q < 4; ++q) if (sgi == q) { p = sp[q]; sc = rscale[q]; }
-                p += ch0;
-                if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
-                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-                    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) if (e < nvalid) x[e] = __ldg(p + e);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] *= sc;
-            }
+            const float sc = csc[c];
+            const float x[8] = {cur[2 * c].x * sc, cur[2 * c].y * sc, cur[2 * c].z * sc, cur[2 * c].w * sc,
+                                cur[2 * c + 1].x * sc, cur[2 * c + 1].y * sc, cur[2 * c + 1].z * sc, cur[2 * c + 1].w * sc};
             split_store8(x, a_hi + c * TM + tid, a_lo + c * TM + tid);
+        }
+        // ---- prefetch the next stage's row data into registers (in flight behind the barrier + MMA issue) ---
+        if (i + 1 < n_stage) {
+#pragma unroll
+            for (int c = 0; c < KC / 8; ++c)
+                load_chunk<FAST>(rs, (i + 1) * (KC / 8) + c, cur[2 * c], cur[2 * c + 1], csc[c]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         __syncthreads();
@@ -221,6 +171,12 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
             }
             umma_commit(bar_m[s]);
             if (i == n_stage - 1) umma_commit(bar_done);
+            // weights of the next stage: its buffer is free once the MMAs of stage i-1 have drained
+            if (i + 1 < n_stage) {
+                if (i >= 1) mbar_wait(bar_m[s ^ 1], ((i - 1) >> 1) & 1);
+                mbar_expect_tx(bar_w[s ^ 1], w_stage_bytes);
+                bulk_g2s(smem_u32(sW[s ^ 1]), Wp + (size_t)(i + 1) * (w_stage_bytes / 2), w_stage_bytes, bar_w[s ^ 1]);
+            }
         }
     }
     // ---- epilogue ---------------------------------------------------------------------------------------------
@@ -276,11 +232,21 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     const size_t smem = 2 * (size_t)A_STAGE_BYTES + 2 * (size_t)NP * 128;
     static bool attr_set = false;
     if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * 128));
+        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * 128));
+        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * 128));
         attr_set = true;
     }
-    layer_tc_kernel<<<hrn_divup(rows, TM), TM, smem, (cudaStream_t)stream>>>(
-        *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, tmem_cols);
+    bool fast = true;   // 16-byte vector path: every segment 4-float aligned
+    for (int s = 0; s < in->n_seg; ++s) {
+        const hrn_seg_t& g = in->seg[s];
+        if ((g.channels & 3) || (g.ld & 3) || (g.col0 & 3) || ((uintptr_t)g.ptr & 15)) fast = false;
+    }
+    if (fast)
+        layer_tc_kernel<true><<<hrn_divup(rows, TM), TM, smem, (cudaStream_t)stream>>>(
+            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, tmem_cols);
+    else
+        layer_tc_kernel<false><<<hrn_divup(rows, TM), TM, smem, (cudaStream_t)stream>>>(
+            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, tmem_cols);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }

@@ -8,7 +8,7 @@ import ctypes
 
 import torch
 
-from ._lib import call, ptr, stream
+from . import engine
 
 KC = 32
 _cache = {}
@@ -46,6 +46,6 @@ def layer_tc(view, W, b, act, out):
     Wp, NP, n_stage, _ = pack_weights(W, seg_channels)
     if b is None:
         b = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device)
-    call("hrn_layer_tc", ctypes.byref(view.c), ptr(Wp), ptr(b), act, ptr(out), out.stride(0), view.rows, W.shape[0], NP,
-         n_stage, stream())
+    engine.call("hrn_layer_tc", ctypes.byref(view.c), engine.ptr(Wp), engine.ptr(b), act, engine.ptr(out), out.stride(0),
+                view.rows, W.shape[0], NP, n_stage, engine.stream())
     return out

@@ -10,6 +10,15 @@ from common import build_product_hregnet, load_golden, rel_err, unflatten
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+
+
+@pytest.fixture(autouse=True, params=["fp32", "tc"])
+def precision(request):
+    """Every test runs in both shared-MLP modes: exact-fp32 CUDA cores and tcgen05 bf16x3."""
+    from pcd_reg_hregnet_b200 import engine as _e
+    _e.set_precision(request.param)
+    yield request.param
+    _e.set_precision("fp32")
 FEAT_TOL = 1e-3          # per-tensor max|x-ref|/max|ref|
 
 
@@ -26,8 +35,9 @@ def _cl(x):
 
 
 @pytest.mark.parametrize("n_points", [2048, 16384])
-def test_feature_levels_teacher_forced(nets, n_points):
+def test_feature_levels_teacher_forced(nets, n_points, precision):
     cpu, gpu = nets
+    xyz_tol = 1e-5 if precision == "fp32" else 1e-4     # attention-weighted keypoints inherit the MLP's 4e-6 error
     src = synth.make_batch([31, 32], n_points)[0]
     trace = {}
     with torch.no_grad():
@@ -45,7 +55,7 @@ def test_feature_levels_teacher_forced(nets, n_points):
             q = trace[f"in_xyz_{lv}"][torch.arange(2)[:, None], trace[f"fps_idx_{lv}"].long()]
             _, i_o, _ = native.knn_points(q, trace[f"in_xyz_{lv}"], K=det.k)
             assert torch.equal(r["idx"].cpu().long(), i_o), f"kNN idx level {lv}"
-            assert rel_err(r["xyz"].cpu(), want[f"xyz_{lv}"]) < 1e-5
+            assert rel_err(r["xyz"].cpu(), want[f"xyz_{lv}"]) < xyz_tol
             assert rel_err(r["sigmas"].cpu(), want[f"sigmas_{lv}"]) < FEAT_TOL
             assert rel_err(_cl(r["desc"].cpu()), want[f"desc_{lv}"]) < FEAT_TOL
             assert rel_err(_cl(r["af"].cpu()), trace[f"af_{lv}"]) < FEAT_TOL

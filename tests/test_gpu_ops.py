@@ -31,6 +31,10 @@ def _clouds(kind, B, N, seed):
     ("lidar", 2, 8096, 1024), ("uniform", 2, 10000, 333), ("uniform", 4, 1024, 512), ("lattice", 3, 512, 256),
     ("uniform", 2, 1000, 1000), ("lattice", 2, 300, 64), ("uniform", 2, 37, 20), ("uniform", 1, 5, 5),
     ("uniform", 2, 2048, 1), ("lidar", 1, 20000, 300), ("dup", 1, 32768, 257),
+    # cluster-size coverage of the all-in-registers kernel: 64 clouds -> CS=2/P=8 (the bench shape), 20 -> CS=4/P=4,
+    # 40000 points -> CS=8/P=5->8, 70000 points -> streaming kernel
+    ("uniform", 64, 16384, 1024), ("uniform", 20, 16384, 256), ("uniform", 40, 8192, 128), ("uniform", 2, 40000, 200),
+    ("uniform", 1, 70000, 64),
 ])
 def test_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=N + M)
@@ -42,7 +46,8 @@ def test_fps_bit_exact(kind, B, N, M):
 
 @pytest.mark.parametrize("kind,B,N,M", [
     ("uniform", 4, 1024, 512), ("lidar", 2, 1024, 512), ("lattice", 3, 512, 256), ("uniform", 2, 512, 256),
-    ("dup", 2, 16384, 400), ("uniform", 1, 700, 128), ("lattice", 1, 24000, 100),
+    ("dup", 2, 16384, 400), ("uniform", 1, 700, 128), ("lattice", 1, 24000, 100), ("uniform", 64, 1024, 512),
+    ("uniform", 80, 9000, 100), ("uniform", 3, 50000, 50),
 ])
 def test_weighted_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=7 * N + M)
