@@ -1,0 +1,265 @@
+// Exact kNN in 3-D with spatial culling, for the large level-1 search (1024 queries x 16384 points, K = 64).
+//
+// Same contract as knn3_kernel (knn.cu): dist = fma(dz,dz, fma(dy,dy, dx*dx)), K smallest by (dist, index) -- the
+// result is bit-identical to the brute-force kernel, only the work changes:
+//   1. knn_sort_kernel   one CTA per cloud: Morton key of (x, y) on a fixed 0.25 m lattice, bitonic sort of
+//                        (key, index) in 128 KB of shared memory, points re-written in that order as float4
+//                        {x, y, z, original index}, and one axis-aligned box per 32 consecutive points.
+//   2. knn3_sorted_kernel one warp per query: distance to every box of the cloud (16 boxes per lane, a true lower
+//                        bound of the members' distances in fp32 because subtraction and fma round monotonically),
+//                        seed the running top-K from the 4 closest boxes, then visit only boxes whose bound does
+//                        not exceed the current K-th distance.  Typically ~20 of 512 boxes are opened.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace knn_sorted {
+
+__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+// Same distributed sorted list as knn.cu (kept local so the two translation units stay independent).
+template <int KPL>
+struct WarpTopK {
+    float d[KPL];
+    int i[KPL];
+    float thr_d;
+    int thr_i;
+    int K;
+    __device__ __forceinline__ void init(int K_) {
+        K = K_;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) { d[s] = CUDART_INF_F; i[s] = 0x7fffffff; }
+        thr_d = CUDART_INF_F; thr_i = 0x7fffffff;
+    }
+    __device__ __forceinline__ void insert(float xd, int xi, int lane) {
+        float pd[KPL]; int pi[KPL];
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            pd[s] = __shfl_up_sync(0xffffffffu, d[s], 1);
+            pi[s] = __shfl_up_sync(0xffffffffu, i[s], 1);
+            if (s > 0) {
+                const float cd = __shfl_sync(0xffffffffu, d[s - 1], 31);
+                const int ci = __shfl_sync(0xffffffffu, i[s - 1], 31);
+                if (lane == 0) { pd[s] = cd; pi[s] = ci; }
+            } else if (lane == 0) { pd[s] = -CUDART_INF_F; pi[s] = -1; }
+        }
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const bool cur_lt = cand_less(d[s], i[s], xd, xi);
+            const bool prev_lt = cand_less(pd[s], pi[s], xd, xi);
+            const float nd = cur_lt ? d[s] : (prev_lt ? xd : pd[s]);
+            const int ni = cur_lt ? i[s] : (prev_lt ? xi : pi[s]);
+            d[s] = nd; i[s] = ni;
+        }
+        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
+        float td = d[0]; int ti = i[0];
+#pragma unroll
+        for (int s = 1; s < KPL; ++s) if (ks == s) { td = d[s]; ti = i[s]; }
+        thr_d = __shfl_sync(0xffffffffu, td, kl);
+        thr_i = __shfl_sync(0xffffffffu, ti, kl);
+    }
+    __device__ __forceinline__ void offer(float cd, int ci, int lane) {
+        unsigned mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float xd = __shfl_sync(0xffffffffu, cd, src);
+            const int xi = __shfl_sync(0xffffffffu, ci, src);
+            if (cand_less(xd, xi, thr_d, thr_i)) insert(xd, xi, lane);
+        }
+    }
+};
+
+__device__ __forceinline__ unsigned part1by1(unsigned v) {
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+constexpr int SORT_THREADS = 1024;
+
+// pts_out [B, N2] float4 (x,y,z,idx bits; padding = +inf / 0x7fffffff), boxes [B, N2/32, 6] (min xyz, max xyz)
+__global__ void __launch_bounds__(SORT_THREADS)
+knn_sort_kernel(const float* __restrict__ xyz, float4* __restrict__ pts_out, float* __restrict__ boxes, int N, int N2) {
+    extern __shared__ unsigned long long s_key[];   // N2 entries: (morton << 32) | index
+    const int b = blockIdx.x, tid = threadIdx.x;
+    xyz += (size_t)b * N * 3;
+    for (int i = tid; i < N2; i += SORT_THREADS) {
+        unsigned long long k = 0xffffffffffffffffull;
+        if (i < N) {
+            const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1];
+            const int ix = min(1023, max(0, (int)floorf((x + 128.f) * 4.f)));
+            const int iy = min(1023, max(0, (int)floorf((y + 128.f) * 4.f)));
+            const unsigned m = part1by1((unsigned)ix) | (part1by1((unsigned)iy) << 1);
+            k = ((unsigned long long)m << 32) | (unsigned)i;
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= N2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (N2 >> 1); t += SORT_THREADS) {
+                const int lo = ((t / stride) * stride * 2) + (t % stride);
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = s_key[lo], c = s_key[hi];
+                if ((a > c) == up) { s_key[lo] = c; s_key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    float4* po = pts_out + (size_t)b * N2;
+    float* bo = boxes + (size_t)b * (N2 / 32) * 6;
+    const int lane = tid & 31;
+    for (int i = tid; i < N2; i += SORT_THREADS) {          // i / 32 is warp-uniform: one chunk per warp step
+        const unsigned long long k = s_key[i];
+        const int src = (int)(k & 0xffffffffu);
+        const bool valid = k != 0xffffffffffffffffull;
+        float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
+        if (valid) { x = xyz[src * 3 + 0]; y = xyz[src * 3 + 1]; z = xyz[src * 3 + 2]; }
+        po[i] = make_float4(x, y, z, __int_as_float(valid ? src : 0x7fffffff));
+        float mnx = x, mny = y, mnz = z;
+        float mxx = valid ? x : -CUDART_INF_F, mxy = valid ? y : -CUDART_INF_F, mxz = valid ? z : -CUDART_INF_F;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+        }
+        if (lane == 0) {
+            float* o6 = bo + (i >> 5) * 6;
+            o6[0] = mnx; o6[1] = mny; o6[2] = mnz; o6[3] = mxx; o6[4] = mxy; o6[5] = mxz;
+        }
+    }
+}
+
+constexpr int QWARPS = 8;
+constexpr int MAXBPL = 16;     // boxes per lane: up to 512 boxes = 16384 points
+
+template <int KPL>
+__global__ void __launch_bounds__(QWARPS * 32)
+knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, const float* __restrict__ p2,
+                   const float4* __restrict__ pts, const float* __restrict__ boxes, float* __restrict__ out_d,
+                   int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn,
+                   float* __restrict__ out_q, int M, int N, int N2, int K) {
+    extern __shared__ float s_box[];                        // [nbox][6]
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nbox = N2 >> 5;
+    const float* bsrc = boxes + (size_t)b * nbox * 6;
+    for (int i = threadIdx.x; i < nbox * 6; i += blockDim.x) s_box[i] = bsrc[i];
+    __syncthreads();
+    const int m = blockIdx.x * QWARPS + warp;
+    if (m >= M) return;
+    p2 += (size_t)b * N * 3;
+    pts += (size_t)b * N2;
+    const float* q = q_idx ? p2 + (size_t)q_idx[(size_t)b * M + m] * 3 : p1 + ((size_t)b * M + m) * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    if (out_q && lane < 3) out_q[((size_t)b * M + m) * 3 + lane] = q[lane];
+
+    // lower bound of the squared distance to every box (same operation order as the point distance)
+    float bd[MAXBPL];
+#pragma unroll
+    for (int g = 0; g < MAXBPL; ++g) {
+        const int bx = g * 32 + lane;
+        bd[g] = CUDART_NAN_F;                               // NaN = "never open": out of range or already visited
+        if (bx < nbox) {
+            const float* o = s_box + bx * 6;
+            const float dx = fmaxf(fmaxf(o[0] - qx, qx - o[3]), 0.f);
+            const float dy = fmaxf(fmaxf(o[1] - qy, qy - o[4]), 0.f);
+            const float dz = fmaxf(fmaxf(o[2] - qz, qz - o[5]), 0.f);
+            bd[g] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        }
+    }
+    WarpTopK<KPL> top;
+    top.init(K);
+    auto open_box = [&](int bx) {
+        const float4 p = __ldg(pts + bx * 32 + lane);
+        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+        const float dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // padding: inf -> never offered
+        top.offer(dist, __float_as_int(p.w), lane);
+    };
+    // seed: the closest boxes until the list holds K finite candidates (at least K/32 + 1 boxes)
+    const int n_seed = min(nbox, (K >> 5) + 2);
+    for (int sd = 0; sd < n_seed; ++sd) {
+        float best = CUDART_INF_F; int bg = 0;
+#pragma unroll
+        for (int g = 0; g < MAXBPL; ++g) if (bd[g] < best) { best = bd[g]; bg = g; }
+        const unsigned ob = hrn_ford(best);
+        const unsigned wmin = __reduce_min_sync(0xffffffffu, ob);
+        const int src = __ffs(__ballot_sync(0xffffffffu, ob == wmin)) - 1;
+        const int g_sel = __shfl_sync(0xffffffffu, bg, src);
+        if (wmin == hrn_ford(CUDART_INF_F)) break;
+        open_box(g_sel * 32 + src);
+        if (lane == src) {
+#pragma unroll
+            for (int g = 0; g < MAXBPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;   // visited
+        }
+    }
+    // sweep: every box whose bound can still beat the K-th candidate
+#pragma unroll
+    for (int g = 0; g < MAXBPL; ++g) {
+        if (g * 32 >= nbox) break;
+        unsigned mask = __ballot_sync(0xffffffffu, bd[g] <= top.thr_d);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float bnd = __shfl_sync(0xffffffffu, bd[g], src);
+            if (bnd <= top.thr_d) open_box(g * 32 + src);
+        }
+    }
+    const size_t base = ((size_t)b * M + m) * K;
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+        const int pos = s * 32 + lane;
+        if (pos < K) {
+            const float d = top.d[s];
+            const int i = top.i[s];
+            if (out_d) out_d[base + pos] = d;
+            if (out_i64) out_i64[base + pos] = (int64_t)i;
+            if (out_i32) out_i32[base + pos] = i;
+            if (out_nn) {
+                const float* rr = p2 + (size_t)i * 3;
+                float* o = out_nn + (base + pos) * 3;
+                o[0] = rr[0]; o[1] = rr[1]; o[2] = rr[2];
+            }
+        }
+    }
+}
+
+}  // namespace knn_sorted
+
+// Scratch the caller provides for the culled search: pts [B*N2] float4 and boxes [B*(N2/32)*6] floats, N2 = next
+// power of two >= N.  Returns HRN_ERR_UNSUPPORTED outside 1024 <= N <= 16384 (callers then use hrn_knn).
+HRN_API int hrn_knn3_sorted(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int K,
+                            void* scratch_pts, float* scratch_boxes, float* dists, int64_t* idx64, int32_t* idx32,
+                            float* nn, float* q_out, void* stream) {
+    using namespace knn_sorted;
+    if (!p2 || (!p1 && !q_idx) || !scratch_pts || !scratch_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
+    if (K > N || K > 64 || N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (B == 0 || M == 0) return HRN_OK;
+    int N2 = 1024;
+    while (N2 < N) N2 <<= 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sort_smem = (size_t)N2 * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        attr_set = true;
+    }
+    knn_sort_kernel<<<B, SORT_THREADS, sort_smem, st>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);
+    HRN_LAUNCH_CHECK();
+    dim3 grid(hrn_divup(M, QWARPS), B);
+    const size_t bsm = (size_t)(N2 / 32) * 6 * sizeof(float);
+    if (K <= 32)
+        knn3_sorted_kernel<1><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)scratch_pts, scratch_boxes, dists,
+                                                              idx64, idx32, nn, q_out, M, N, N2, K);
+    else
+        knn3_sorted_kernel<2><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)scratch_pts, scratch_boxes, dists,
+                                                              idx64, idx32, nn, q_out, M, N, N2, K);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}

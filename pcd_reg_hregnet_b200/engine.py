@@ -133,12 +133,29 @@ def group_geometry(q, p, idx, wq=None, wp=None, ld=None, want_nn=False):
     return out, nn
 
 
+_SORTED_KNN = True
+
+
+def knn_scratch(B, N, device):
+    """Scratch of the spatially culled search: Morton-ordered points (float4) and one box per 32 points."""
+    N2 = 1024
+    while N2 < N:
+        N2 *= 2
+    return (torch.empty(B * N2, 4, dtype=torch.float32, device=device),
+            torch.empty(B * (N2 // 32) * 6, dtype=torch.float32, device=device))
+
+
 def knn_idx(p1, p2, K, q_idx=None):
     """int32 neighbour indices [B,M,K] (+ gathered queries when q_idx is given)."""
     B, N, D = p2.shape
     M = q_idx.shape[1] if q_idx is not None else p1.shape[1]
     idx = torch.empty(B, M, K, dtype=torch.int32, device=p2.device)
     q_out = torch.empty(B, M, 3, dtype=torch.float32, device=p2.device) if q_idx is not None else None
+    if D == 3 and 2048 <= N <= 16384 and _SORTED_KNN:
+        pts, boxes = knn_scratch(B, N, p2.device)
+        call("hrn_knn3_sorted", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, K, ptr(pts), ptr(boxes),
+             None, None, ptr(idx), None, ptr(q_out), stream())
+        return idx, q_out
     call("hrn_knn", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, D, K, None, None, ptr(idx), None,
          ptr(q_out), stream())
     return idx, q_out

@@ -103,7 +103,13 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm: int = 2, K: int = 1, 
     dists = torch.empty(B, M, K, dtype=torch.float32, device=p1.device)
     idx = torch.empty(B, M, K, dtype=torch.int64, device=p1.device)
     nn = torch.empty(B, M, K, D, dtype=torch.float32, device=p1.device) if return_nn else None
-    call("hrn_knn", ptr(p1), None, ptr(p2), B, M, N, D, K, ptr(dists), ptr(idx), None, ptr(nn), None, stream())
+    if D == 3 and 2048 <= N <= 16384:      # spatially culled exact search (same results, see csrc/knn_sorted.cu)
+        from .engine import knn_scratch
+        pts, boxes = knn_scratch(B, N, p1.device)
+        call("hrn_knn3_sorted", ptr(p1), None, ptr(p2), B, M, N, K, ptr(pts), ptr(boxes), ptr(dists), ptr(idx), None, ptr(nn),
+             None, stream())
+    else:
+        call("hrn_knn", ptr(p1), None, ptr(p2), B, M, N, D, K, ptr(dists), ptr(idx), None, ptr(nn), None, stream())
     return _KNN(dists, idx, nn)
 
 

@@ -21,6 +21,8 @@ def _clouds(kind, B, N, seed):
         return torch.rand(B, N, 3, generator=g)
     if kind == "lattice":      # many exact ties
         return torch.randint(0, 6, (B, N, 3), generator=g).float()
+    if kind == "far":          # coordinates beyond the +-128 m Morton lattice (clamped keys, still exact)
+        return (torch.rand(B, N, 3, generator=g) - 0.5) * 2000
     if kind == "dup":          # dataset-style duplicate padding (dataset/dataset_utils.py:203-207)
         return torch.stack([synth.duplicate_padded_cloud(seed + b, N, max(N // 2, 1)) for b in range(B)])
     raise ValueError(kind)
@@ -124,6 +126,9 @@ def test_gather_forward_backward():
     ("lidar", 2, 1024, 16384, 64), ("uniform", 2, 512, 1024, 32), ("uniform", 2, 256, 512, 16),
     ("lattice", 2, 200, 3000, 64), ("lattice", 2, 256, 256, 8), ("dup", 1, 300, 5000, 32), ("uniform", 1, 7, 9, 9),
     ("uniform", 2, 1024, 1024, 8), ("uniform", 1, 100, 2049, 1),
+    # spatially culled path (2048 <= N <= 16384): ties, duplicates, non-power-of-two N, points outside the lattice
+    ("lattice", 2, 512, 16384, 64), ("dup", 2, 700, 8096, 32), ("lidar", 1, 64, 10000, 16), ("far", 1, 128, 4096, 8),
+    ("uniform", 64, 1024, 16384, 64),
 ])
 def test_knn_xyz_bit_exact(kind, B, M, N, K):
     p2 = _clouds(kind, B, N, seed=N + K)
