@@ -121,17 +121,19 @@ int hrn_layer_fp32(const hrn_rows_t* in, const float* W, const float* bias, int 
 int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
                  int Cout, int NP, int n_stage, void* stream);
 
-/* Level 1 of HierFeatureExtraction (models/HRegNet/models.py:27-28: detector_1 + desc_extractor_1, in_channels 0,
- * k = 64, widths 32/32/64, mlp 192->32->64) as ONE persistent tcgen05 kernel: grouping (layers.py:9-27), the two
- * conv stacks, attention / keypoints / attentive feature (layers.py:150-159) and the descriptor head
- * (layers.py:200-209) with every per-neighbour tensor kept in shared / tensor memory.
- *   q [B*M,3] sampled keypoints, xyz [B,N,3], idx [B*M*64] int32 neighbours; Wpack (hrn_level1_pack_bytes() bytes)
- *   and biases (hrn_level1_bias_count() floats) as laid out by pcd_reg_hregnet_b200/engine_tc.pack_level1.
- *   Outputs per keypoint: out_xyz [B*M,3], out_af [B*M,64], out_desc [B*M,64]. */
-int hrn_level1_fused(const float* q, const float* xyz, const int32_t* idx, const void* Wpack, const float* biases,
-                     float* out_xyz, float* out_af, float* out_desc, int B, int M, int N, int k, void* stream);
-int hrn_level1_pack_bytes(void);
-int hrn_level1_bias_count(void);
+/* Levels 1 and 2 of HierFeatureExtraction (models/HRegNet/models.py:27-28,33-34: detector_l + desc_extractor_l;
+ * level 1: in_channels 0, k = 64, widths 32/32/64, mlp 192->32->64; level 2: in_channels 64, k = 32, widths
+ * 64/64/128, mlp 384->64->128) as ONE persistent tcgen05 kernel each: grouping (layers.py:9-27), the two conv
+ * stacks, attention / keypoints / attentive feature (layers.py:150-159) and the descriptor head (layers.py:200-209)
+ * with every per-neighbour tensor kept in shared / tensor memory.
+ *   q [B*M,3] sampled keypoints, xyz [B,N,3], feat [B,N,CIN] channels-last (NULL at level 1), idx [B*M*k] int32;
+ *   Wpack (hrn_level_pack_bytes(level) bytes) and biases (hrn_level_bias_count(level) floats) as laid out by
+ *   pcd_reg_hregnet_b200/engine_tc.pack_level.  Outputs per keypoint: out_xyz [B*M,3], out_af [B*M,CO], out_desc [B*M,CD]. */
+int hrn_level_fused(int level, const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,
+                    const float* biases, float* out_xyz, float* out_af, float* out_desc, int B, int M, int N, int k,
+                    void* stream);
+int hrn_level_pack_bytes(int level);
+int hrn_level_bias_count(int level);
 
 /* a[g*k+j] = softmax_j( max_c E[g*k+j, c] )   (layers.py:151-152,330-331,385-386,447-448).  k <= 64. */
 int hrn_group_attention(const float* E, int ldE, int C, long long groups, int k, float* a, void* stream);

@@ -39,7 +39,7 @@ SIGNATURES = {
     "hrn_transpose": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_layer_fp32": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp],
     "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp],
-    "hrn_level1_fused": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "hrn_level_fused": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
     "hrn_group_weighted_sum": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "hrn_group_max": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_vp],
@@ -71,9 +71,9 @@ def lib():
             f.restype = c_int
         L.hrn_version.restype = ctypes.c_char_p
         L.hrn_version.argtypes = []
-        for name in ("hrn_level1_pack_bytes", "hrn_level1_bias_count"):
+        for name in ("hrn_level_pack_bytes", "hrn_level_bias_count"):
             getattr(L, name).restype = c_int
-            getattr(L, name).argtypes = []
+            getattr(L, name).argtypes = [c_int]
         _lib = L
     return _lib
 

@@ -1,21 +1,24 @@
-// Fused hierarchy level (level 1 of HierFeatureExtraction): grouping + KeypointDetector + DescExtractor in ONE
-// persistent kernel -- no per-neighbour tensor ever reaches HBM.
+// Fused hierarchy level of HierFeatureExtraction: grouping + KeypointDetector + DescExtractor in ONE persistent
+// kernel -- no per-neighbour tensor ever reaches HBM.
 //
-// Replaces, for the first level (reference models/HRegNet/models.py:27-28, in_channels = 0, k = 64):
+// Replaces, per level (reference models/HRegNet/models.py:27-28 / 33-34):
 //   knn_group (layers.py:9-27)  ->  KeypointDetector.convs / attention / keypoints / attentive feature
 //   (layers.py:150-159)  ->  DescExtractor.convs / max / cat / mlp1 / mlp2 / max (layers.py:200-209).
-// The unfused form of this level moves ~11 GB per 32-pair step through HBM (4.2 M rows x 64 channels x a dozen
-// passes); here the inputs are 16 B per row (neighbour index + coordinates) and the outputs are per KEYPOINT only
-// (xyz 12 B, attentive feature 256 B, descriptor 256 B).
+// Unfused, level 1 alone moves ~11 GB per 32-pair step through HBM (4.2 M rows x 64 channels x a dozen passes);
+// here the inputs are the neighbour index + coordinates (+ the gathered 64-channel feature row at level 2) and the
+// outputs are per KEYPOINT only (xyz, attentive feature, descriptor).
 //
-// CTA = 128 rows = 2 keypoints x 64 neighbours; thread t <-> row t <-> TMEM lane t; persistent over tiles, two
-// CTAs per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's epilogue math overlaps the other's MMAs.
-// All ten weight matrices of the level (60 KB as bf16 hi/lo UMMA tiles) stay resident in shared memory.
-// Chain per tile (every layer: A operand in smem -> tcgen05.mma bf16x3 -> TMEM -> tcgen05.ld -> bias+ReLU ->
-// bf16 hi/lo split -> written back IN PLACE as the next layer's A operand):
-//   G(4->16) -d1-> 32 -d2-> 32 -d3-> E(64, stays in TMEM)   | max_c, softmax over the 64 neighbours, keypoint
-//   G        -x1-> 32 -x2-> 32 -x3-> X1(64)                 | column max over the group
-//   mlp1 = Wb.X1 + Wa.max_k(X1) + Wc.(E*a)  (three K-segments accumulated in TMEM) -> 32 -mlp2-> 64 -> max_k
+// CTA = 128 rows = 128/k keypoints x k neighbours; thread t <-> row t <-> TMEM lane t; persistent over tiles.
+// Every layer: A operand in smem -> tcgen05.mma (bf16 hi/lo split of both operands, 3 MMAs per k-step, fp32
+// accumulate in TMEM) -> tcgen05.ld -> bias+ReLU -> bf16 hi/lo split -> written back IN PLACE as the next layer's
+// A operand.  Chain per tile:
+//   G -d1-> C1 -d2-> C2 -d3-> E(CO, stays in TMEM)   | max_c, softmax over the k neighbours, keypoint
+//   G -x1-> C1 -x2-> C2 -x3-> X1(CO)                 | column max over the group
+//   mlp1 = Wb.X1 + Wa.max_k(X1) + Wc.(E*a)  (three K-segments accumulated in TMEM) -> CMID -mlp2-> CD -> max_k
+// Weights (bf16 hi/lo UMMA tiles, execution order):
+//   level 1 (60 KB): RESIDENT in shared memory, two CTAs per SM overlap each other's MMA and epilogue phases;
+//   level 2 (264 KB): STREAMED layer by layer from L2 through a 2-slot ring with cp.async.bulk + mbarrier, the copy
+//   of layer l+2 is issued when layer l's MMAs have drained its slot.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
@@ -23,31 +26,42 @@
 namespace {
 
 constexpr int TMR = 128;
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-template <int KNBR, int C1, int C2, int CO, int CMID, int CD>
+template <int KNBR_, int CIN_, int C1_, int C2_, int CO_, int CMID_, int CD_, bool RESIDENT_>
 struct LevelCfg {
-    static constexpr int KG = 16;                                   // padded grouped-input channels (4 used)
-    // shared-memory weight tiles: per layer hi plane [K/8][N][16B] then lo plane
-    static constexpr int W_D1 = 0;
-    static constexpr int W_D2 = W_D1 + 4 * KG * C1;
-    static constexpr int W_D3 = W_D2 + 4 * C1 * C2;
-    static constexpr int W_X1 = W_D3 + 4 * C2 * CO;
-    static constexpr int W_X2 = W_X1 + 4 * KG * C1;
-    static constexpr int W_X3 = W_X2 + 4 * C1 * C2;
-    static constexpr int W_MA = W_X3 + 4 * C2 * CO;                 // mlp1, columns of max_k(X1)
-    static constexpr int W_MB = W_MA + 4 * CO * CMID;               // mlp1, columns of X1
-    static constexpr int W_MC = W_MB + 4 * CO * CMID;               // mlp1, columns of the attentive feature map
-    static constexpr int W_M2 = W_MC + 4 * CO * CMID;
-    static constexpr int W_BYTES = W_M2 + 4 * CMID * CD;
+    static constexpr int KNBR = KNBR_, CIN = CIN_, C1 = C1_, C2 = C2_, CO = CO_, CMID = CMID_, CD = CD_;
+    static constexpr bool RESIDENT = RESIDENT_;
+    static constexpr int KG = (CIN + 4 + 15) / 16 * 16;             // grouped input: [feat(CIN) | rel xyz, |rel| | 0-pad]
+    // weight blocks in execution order; block = hi plane [K/8][N][16 B] + lo plane = 4*K*N bytes
+    __host__ __device__ static constexpr int lk(int l) {            // K of layer l: d1 d2 d3 x1 x2 x3 mb ma mc m2
+        return (l == 0 || l == 3) ? KG : (l == 1 || l == 4) ? C1 : (l == 2 || l == 5) ? C2 : (l == 9) ? CMID : CO;
+    }
+    __host__ __device__ static constexpr int ln(int l) {
+        return (l == 0 || l == 3) ? C1 : (l == 1 || l == 4) ? C2 : (l == 2 || l == 5) ? CO : (l == 9) ? CD : CMID;
+    }
+    __host__ __device__ static constexpr int woff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += 4 * lk(i) * ln(i); return o; }
+    static constexpr int W_BYTES = woff(10);
+    static constexpr int SLOT = 4 * cmax(cmax(KG * C1, C2 * CO), cmax(CO * CMID, CMID * CD));
+    static constexpr int W_SMEM = RESIDENT ? W_BYTES : 2 * SLOT;
     // biases (floats): d1,d2,d3,x1,x2,x3,m1,m2
     static constexpr int B_D1 = 0, B_D2 = B_D1 + C1, B_D3 = B_D2 + C2, B_X1 = B_D3 + CO, B_X2 = B_X1 + C1,
                          B_X3 = B_X2 + C2, B_M1 = B_X3 + CO, B_M2 = B_M1 + CMID, B_COUNT = B_M2 + CD;
-    static constexpr int OPC = (CO > C1 ? CO : C1) / 8;             // chunks of the in-place operand buffer
+    static constexpr int OPC = cmax(cmax(C1, C2), cmax(CO, CMID)) / 8;   // chunks of the in-place operand buffer
     static constexpr int G_BYTES = 2 * (KG / 8) * TMR * 16;
     static constexpr int OP_BYTES = 2 * OPC * TMR * 16;
-    static constexpr int SMEM = W_BYTES + B_COUNT * 4 + G_BYTES + OP_BYTES + 4 * CO * 4 * 2 + 256;
-    // TMEM columns
-    static constexpr int T_ACC0 = 0, T_ACCM = 32, T_ACCE = 64, T_ACCX = 128, T_COLS = 256;
+    static constexpr int CW = cmax(CO, CD);
+    static constexpr int SMEM = W_SMEM + B_COUNT * 4 + G_BYTES + OP_BYTES + 2 * 4 * CW * 4 + 256;
+    // TMEM columns: [acc0 | accM share] [E] [X1 | descriptor]
+    static constexpr int T_ACC0 = 0;
+    static constexpr int T_ACCE = cmax(cmax(C1, C2), CMID);
+    static constexpr int T_ACCX = T_ACCE + CO;
+    static constexpr int T_USED = T_ACCX + cmax(CO, CD);
+    static constexpr int T_COLS = T_USED <= 32 ? 32 : T_USED <= 64 ? 64 : T_USED <= 128 ? 128 : T_USED <= 256 ? 256 : 512;
+    static constexpr int WPG = KNBR / 32;                           // warps per keypoint group (1 or 2)
+    static_assert(KNBR == 32 || KNBR == 64, "group reductions are written for 32 or 64 neighbours");
+    static_assert(T_USED <= 512, "TMEM");
+    static_assert(CIN % 8 == 0, "feature chunks must be 8-aligned");
 };
 
 __device__ __forceinline__ uint32_t make_idesc(int N) {
@@ -71,7 +85,7 @@ __device__ __forceinline__ void issue_layer(uint32_t a_hi, uint32_t a_lo, int K,
     }
 }
 
-// lane c receives op-reduction over the 32 lanes of v[c]  (31 shuffles)
+// lane c receives the op-reduction over the 32 lanes of v[c]  (31 shuffles)
 template <bool IS_MAX>
 __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
 #pragma unroll
@@ -88,41 +102,68 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
     return v[0];
 }
 
-template <class Cfg, int KNBR, int C1, int C2, int CO, int CMID, int CD>
-__global__ void __launch_bounds__(TMR, 2)
-level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, const int32_t* __restrict__ idx,
-                    const uint8_t* __restrict__ Wpack, const float* __restrict__ biases, float* __restrict__ out_xyz,
-                    float* __restrict__ out_af, float* __restrict__ out_desc, int M, int N, int n_tiles) {
-    static_assert(KNBR == 64, "row-group reductions are written for 64 neighbours (2 warps per keypoint)");
+template <class Cfg>
+__global__ void __launch_bounds__(TMR, Cfg::RESIDENT ? 2 : 1)
+level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, const float* __restrict__ feat,
+                   const int32_t* __restrict__ idx, const uint8_t* __restrict__ Wpack, const float* __restrict__ biases,
+                   float* __restrict__ out_xyz, float* __restrict__ out_af, float* __restrict__ out_desc, int M, int N,
+                   int n_tiles) {
+    constexpr int KNBR = Cfg::KNBR, CIN = Cfg::CIN, C1 = Cfg::C1, C2 = Cfg::C2, CO = Cfg::CO, CMID = Cfg::CMID,
+                  CD = Cfg::CD, WPG = Cfg::WPG, CW = Cfg::CW;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[3];                            // [0] MMA done, [1,2] weight slot landed
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[4][8];
 
     uint8_t* sW = smem;
-    float* sB = reinterpret_cast<float*>(smem + Cfg::W_BYTES);
-    uint8_t* sG = smem + Cfg::W_BYTES + Cfg::B_COUNT * 4;
+    float* sB = reinterpret_cast<float*>(smem + Cfg::W_SMEM);
+    uint8_t* sG = smem + Cfg::W_SMEM + Cfg::B_COUNT * 4;
     uint8_t* sOp = sG + Cfg::G_BYTES;
-    float* sCol = reinterpret_cast<float*>(sOp + Cfg::OP_BYTES);          // [2][4][CO] cross-warp column partials
+    float* sCol = reinterpret_cast<float*>(sOp + Cfg::OP_BYTES);          // [4][CW] per-warp column partials
+    float* sCol2 = sCol + 4 * CW;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = warp >> 1;                                            // keypoint of this row inside the tile
-    const uint32_t bar = smem_u32(&s_bar);
+    const int gw0 = (warp / WPG) * WPG;                                   // first warp of this row's keypoint group
+    const bool leader = (warp == gw0);
+    const uint32_t bar = smem_u32(&s_bar[0]);
+    const uint32_t bar_w[2] = {smem_u32(&s_bar[1]), smem_u32(&s_bar[2])};
     uint32_t phase = 0;
+    uint32_t lcount = 0;                                                  // layers executed by this CTA (streaming)
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total_layers = (uint32_t)my_tiles * 10u;
+    const uint32_t wbase = smem_u32(sW);
 
-    // ---- one-time: weights + biases resident, barrier, TMEM ---------------------------------------------------
-    for (int i = tid; i < Cfg::W_BYTES / 16; i += TMR)
-        reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
-    for (int i = tid; i < Cfg::B_COUNT; i += TMR) sB[i] = __ldg(biases + i);
-    {   // K padding chunk of G (channels 8..15) is zero forever
-        uint4* g_hi = reinterpret_cast<uint4*>(sG);
-        uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
-        g_hi[1 * TMR + tid] = make_uint4(0, 0, 0, 0);
-        g_lo[1 * TMR + tid] = make_uint4(0, 0, 0, 0);
-    }
+    auto stream_weights = [&](uint32_t L) {   // thread 0: fetch the weights of this CTA's L-th layer into slot L&1
+        const int li = (int)(L % 10u);
+        int off = 0, bytes = 0;
+#pragma unroll
+        for (int l = 0; l < 10; ++l) if (l == li) { off = Cfg::woff(l); bytes = 4 * Cfg::lk(l) * Cfg::ln(l); }
+        mbar_expect_tx(bar_w[L & 1], (uint32_t)bytes);
+        bulk_g2s(wbase + (L & 1) * Cfg::SLOT, Wpack + off, (uint32_t)bytes, bar_w[L & 1]);
+    };
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar_w[0], 1);
+        mbar_init(bar_w[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (!Cfg::RESIDENT) {
+            if (total_layers > 0) stream_weights(0);
+            if (total_layers > 1) stream_weights(1);
+        }
+    }
+    if (Cfg::RESIDENT)
+        for (int i = tid; i < Cfg::W_BYTES / 16; i += TMR)
+            reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
+    for (int i = tid; i < Cfg::B_COUNT; i += TMR) sB[i] = __ldg(biases + i);
+    {   // K padding chunks of G stay zero forever
+        uint4* g_hi = reinterpret_cast<uint4*>(sG);
+        uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
+        for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {
+            g_hi[c * TMR + tid] = make_uint4(0, 0, 0, 0);
+            g_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS) : "memory");
@@ -135,26 +176,35 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
     const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
     const uint32_t aG_hi = smem_u32(sG), aG_lo = aG_hi + (Cfg::KG / 8) * TMR * 16;
     const uint32_t aOp_hi = smem_u32(sOp), aOp_lo = aOp_hi + Cfg::OPC * TMR * 16;
-    const uint32_t wbase = smem_u32(sW);
+    uint4* g_hi = reinterpret_cast<uint4*>(sG);
+    uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
     uint4* op_hi = reinterpret_cast<uint4*>(sOp);
     uint4* op_lo = op_hi + Cfg::OPC * TMR;
 
-    // operand ready in smem -> one thread issues the layer -> everybody waits for the accumulator
-    auto run_layer = [&](uint32_t a_hi, uint32_t a_lo, int K, int w_off, int Nn, int tcol, bool acc) {
+    // operand ready in smem -> one thread issues layer `li` -> everybody waits for the accumulator
+    auto run_layer = [&](uint32_t a_hi, uint32_t a_lo, int li, int tcol, bool acc) {
+        const int K = Cfg::lk(li), Nn = Cfg::ln(li);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
+            uint32_t w_addr = wbase + Cfg::woff(li);
+            if (!Cfg::RESIDENT) {
+                mbar_wait(bar_w[lcount & 1], (lcount >> 1) & 1);
+                w_addr = wbase + (lcount & 1) * Cfg::SLOT;
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_layer(a_hi, a_lo, K, wbase + w_off, Nn, tmem + tcol, acc);
+            issue_layer(a_hi, a_lo, K, w_addr, Nn, tmem + tcol, acc);
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!Cfg::RESIDENT && tid == 0 && lcount + 2 < total_layers) stream_weights(lcount + 2);   // slot is free again
+        ++lcount;
     };
     // accumulator [tcol, tcol+Nn) -> relu(x + b) -> bf16 hi/lo operand (in place)
-    auto epi_to_operand = [&](int tcol, int Nn, const float* b) {
+    auto epi_to_operand = [&](int tcol, int Nn, const float* bb) {
         for (int c0 = 0; c0 < Nn; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + tcol + c0, v);
@@ -162,14 +212,20 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
             for (int ch = 0; ch < 4; ++ch) {
                 float x[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[ch * 8 + e]) + b[c0 + ch * 8 + e], 0.f);
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[ch * 8 + e]) + bb[c0 + ch * 8 + e], 0.f);
                 split_store8(x, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
             }
         }
     };
+    // value of column c for this row's keypoint group after the per-warp partials were published in `buf`
+    auto col_max = [&](const float* buf, int c) {
+        float v = buf[gw0 * CW + c];
+        if (WPG == 2) v = fmaxf(v, buf[(gw0 + 1) * CW + c]);
+        return v;
+    };
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- S0: grouped input  [rel xyz, |rel|] ------------------------------------------------------------
+        // ---- grouped input  [feat[idx] | rel xyz, |rel|] ----------------------------------------------------
         const long long r = (long long)tile * TMR + tid;
         const long long bm = r / KNBR;
         const long long b = bm / M;
@@ -178,17 +234,32 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
         const float* qq = q + bm * 3;
         const float nx = __ldg(pp), ny = __ldg(pp + 1), nz = __ldg(pp + 2);
         const float rx = nx - __ldg(qq), ry = ny - __ldg(qq + 1), rz = nz - __ldg(qq + 2);
+        if (CIN > 0) {
+            const float4* fr = reinterpret_cast<const float4*>(feat + (b * N + n) * CIN);
+            constexpr int HALF = CIN / 8 > 1 ? CIN / 16 : 1;          // chunks per batch of loads (bounds registers)
+#pragma unroll
+            for (int h = 0; h < (CIN / 8) / HALF; ++h) {
+                float4 fv[2 * HALF];
+#pragma unroll
+                for (int i = 0; i < 2 * HALF; ++i) fv[i] = __ldg(fr + h * 2 * HALF + i);
+#pragma unroll
+                for (int c = 0; c < HALF; ++c) {
+                    const float x[8] = {fv[2 * c].x, fv[2 * c].y, fv[2 * c].z, fv[2 * c].w,
+                                        fv[2 * c + 1].x, fv[2 * c + 1].y, fv[2 * c + 1].z, fv[2 * c + 1].w};
+                    split_store8(x, g_hi + (h * HALF + c) * TMR + tid, g_lo + (h * HALF + c) * TMR + tid);
+                }
+            }
+        }
         {
             const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 0.f, 0.f, 0.f, 0.f};
-            uint4* g_hi = reinterpret_cast<uint4*>(sG);
-            split_store8(x, g_hi + tid, g_hi + (Cfg::KG / 8) * TMR + tid);
+            split_store8(x, g_hi + (CIN / 8) * TMR + tid, g_lo + (CIN / 8) * TMR + tid);
         }
         // ---- detector chain ------------------------------------------------------------------------------------
-        run_layer(aG_hi, aG_lo, Cfg::KG, Cfg::W_D1, C1, Cfg::T_ACC0, false);
+        run_layer(aG_hi, aG_lo, 0, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_D1);
-        run_layer(aOp_hi, aOp_lo, C1, Cfg::W_D2, C2, Cfg::T_ACC0, false);
+        run_layer(aOp_hi, aOp_lo, 1, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_D2);
-        run_layer(aOp_hi, aOp_lo, C2, Cfg::W_D3, CO, Cfg::T_ACCE, false);
+        run_layer(aOp_hi, aOp_lo, 2, Cfg::T_ACCE, false);
         // ---- attention: a = softmax_k(max_c E), keypoint = sum_k a * nn -------------------------------------
         float x1 = 0.f;                                                   // post-ReLU values are >= 0
         for (int c0 = 0; c0 < CO; c0 += 32) {
@@ -197,27 +268,29 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
 #pragma unroll
             for (int e = 0; e < 32; ++e) x1 = fmaxf(x1, __uint_as_float(v[e]) + sB[Cfg::B_D3 + c0 + e]);
         }
-        float wm = hrn_warp_max(x1);
-        if (lane == 0) s_red[warp][0] = wm;
-        __syncthreads();
-        const float gmax = fmaxf(s_red[2 * grp][0], s_red[2 * grp + 1][0]);
+        float gmax = hrn_warp_max(x1);
+        if (WPG == 2) {
+            if (lane == 0) s_red[warp][0] = gmax;
+            __syncthreads();
+            gmax = fmaxf(s_red[gw0][0], s_red[gw0 + 1][0]);
+        }
         const float ex = expf(x1 - gmax);
         float s0 = hrn_warp_sum(ex), s1 = hrn_warp_sum(ex * nx), s2 = hrn_warp_sum(ex * ny), s3 = hrn_warp_sum(ex * nz);
-        if (lane == 0) { s_red[warp][1] = s0; s_red[warp][2] = s1; s_red[warp][3] = s2; s_red[warp][4] = s3; }
-        __syncthreads();
-        const float ssum = s_red[2 * grp][1] + s_red[2 * grp + 1][1];
-        const float a = ex / ssum;
-        if ((tid & 63) < 3) {
-            const int c = tid & 63;
-            out_xyz[bm * 3 + c] = (s_red[2 * grp][2 + c] + s_red[2 * grp + 1][2 + c]) / ssum;
+        if (WPG == 2) {
+            if (lane == 0) { s_red[warp][1] = s0; s_red[warp][2] = s1; s_red[warp][3] = s2; s_red[warp][4] = s3; }
+            __syncthreads();
+            s0 = s_red[gw0][1] + s_red[gw0 + 1][1]; s1 = s_red[gw0][2] + s_red[gw0 + 1][2];
+            s2 = s_red[gw0][3] + s_red[gw0 + 1][3]; s3 = s_red[gw0][4] + s_red[gw0 + 1][4];
         }
+        const float a = ex / s0;
+        if (leader && lane < 3) out_xyz[bm * 3 + lane] = (lane == 0 ? s1 : (lane == 1 ? s2 : s3)) / s0;
         // ---- descriptor chain ----------------------------------------------------------------------------------
-        run_layer(aG_hi, aG_lo, Cfg::KG, Cfg::W_X1, C1, Cfg::T_ACC0, false);
+        run_layer(aG_hi, aG_lo, 3, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_X1);
-        run_layer(aOp_hi, aOp_lo, C1, Cfg::W_X2, C2, Cfg::T_ACC0, false);
+        run_layer(aOp_hi, aOp_lo, 4, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_X2);
-        run_layer(aOp_hi, aOp_lo, C2, Cfg::W_X3, CO, Cfg::T_ACCX, false);
-        // X1 -> operand, and its column maximum over the 64 rows of the group
+        run_layer(aOp_hi, aOp_lo, 5, Cfg::T_ACCX, false);
+        // X1 -> operand, and its column maximum over the rows of the group
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
             float f[32];
@@ -231,21 +304,19 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
                 split_store8(x, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
             }
             const float cm = warp_transpose_reduce<true>(f, lane);
-            sCol[warp * CO + c0 + lane] = cm;
+            sCol[warp * CW + c0 + lane] = cm;
         }
-        run_layer(aOp_hi, aOp_lo, CO, Cfg::W_MB, CMID, Cfg::T_ACCM, false);      // (barrier inside also publishes sCol)
+        run_layer(aOp_hi, aOp_lo, 6, Cfg::T_ACC0, false);                 // mlp1 += Wb.X1 (barrier inside publishes sCol)
         // max_k(X1) broadcast over the group's rows as the next K-segment
-#pragma unroll
+#pragma unroll 4
         for (int ch = 0; ch < CO / 8; ++ch) {
             float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                x[e] = fmaxf(sCol[(2 * grp) * CO + ch * 8 + e], sCol[(2 * grp + 1) * CO + ch * 8 + e]);
+            for (int e = 0; e < 8; ++e) x[e] = col_max(sCol, ch * 8 + e);
             split_store8(x, op_hi + ch * TMR + tid, op_lo + ch * TMR + tid);
         }
-        run_layer(aOp_hi, aOp_lo, CO, Cfg::W_MA, CMID, Cfg::T_ACCM, true);
+        run_layer(aOp_hi, aOp_lo, 7, Cfg::T_ACC0, true);                  // mlp1 += Wa.max_k(X1)
         // attentive feature map E*a as the third K-segment; attentive feature = its column sum over the group
-        float* sCol2 = sCol + 4 * CO;
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
             float f[32];
@@ -259,16 +330,18 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
                 split_store8(x, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
             }
             const float cs = warp_transpose_reduce<false>(f, lane);
-            sCol2[warp * CO + c0 + lane] = cs;
+            sCol2[warp * CW + c0 + lane] = cs;
         }
-        run_layer(aOp_hi, aOp_lo, CO, Cfg::W_MC, CMID, Cfg::T_ACCM, true);
-        if ((tid & 63) < CO) {
-            const int c = tid & 63;
-            out_af[bm * CO + c] = sCol2[(2 * grp) * CO + c] + sCol2[(2 * grp + 1) * CO + c];
-        }
+        run_layer(aOp_hi, aOp_lo, 8, Cfg::T_ACC0, true);                  // mlp1 += Wc.(E*a)
+        if (leader)
+            for (int c = lane; c < CO; c += 32) {
+                float v = sCol2[gw0 * CW + c];
+                if (WPG == 2) v += sCol2[(gw0 + 1) * CW + c];
+                out_af[bm * CO + c] = v;
+            }
         // ---- mlp1 epilogue -> mlp2 -> descriptor = max_k -------------------------------------------------------
-        epi_to_operand(Cfg::T_ACCM, CMID, sB + Cfg::B_M1);
-        run_layer(aOp_hi, aOp_lo, CMID, Cfg::W_M2, CD, Cfg::T_ACCX, false);
+        epi_to_operand(Cfg::T_ACC0, CMID, sB + Cfg::B_M1);
+        run_layer(aOp_hi, aOp_lo, 9, Cfg::T_ACCX, false);
         for (int c0 = 0; c0 < CD; c0 += 32) {
             uint32_t v[32];
             float f[32];
@@ -276,13 +349,11 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
 #pragma unroll
             for (int e = 0; e < 32; ++e) f[e] = fmaxf(__uint_as_float(v[e]) + sB[Cfg::B_M2 + c0 + e], 0.f);
             const float cm = warp_transpose_reduce<true>(f, lane);
-            sCol[warp * CO + c0 + lane] = cm;
+            sCol[warp * CW + c0 + lane] = cm;
         }
         __syncthreads();
-        if ((tid & 63) < CD) {
-            const int c = tid & 63;
-            out_desc[bm * CD + c] = fmaxf(sCol[(2 * grp) * CO + c], sCol[(2 * grp + 1) * CO + c]);
-        }
+        if (leader)
+            for (int c = lane; c < CD; c += 32) out_desc[bm * CD + c] = col_max(sCol, c);
         // the next tile's first barrier (inside run_layer) orders these reads before sCol / s_red are rewritten
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -291,34 +362,44 @@ level1_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::T_COLS) : "memory");
 }
 
-using Cfg1 = LevelCfg<64, 32, 32, 64, 32, 64>;
+using CfgL1 = LevelCfg<64, 0, 32, 32, 64, 32, 64, true>;       // detector_1 / desc_extractor_1 (models.py:14,22)
+using CfgL2 = LevelCfg<32, 64, 64, 64, 128, 64, 128, false>;   // detector_2 / desc_extractor_2 (models.py:15,23)
 
-}  // namespace
-
-// Level-1 fused detector + descriptor.  q [B*M,3] sampled keypoint coordinates, xyz [B,N,3], idx [B*M*64] int32
-// neighbour indices; Wpack / biases from engine_tc.pack_level1 (layout = LevelCfg offsets).  Outputs per keypoint:
-// out_xyz [B*M,3], out_af [B*M,64], out_desc [B*M,64].
-HRN_API int hrn_level1_fused(const float* q, const float* xyz, const int32_t* idx, const void* Wpack, const float* biases,
-                             float* out_xyz, float* out_af, float* out_desc, int B, int M, int N, int k, void* stream) {
-    if (!q || !xyz || !idx || !Wpack || !biases || !out_xyz || !out_af || !out_desc || B < 0 || M <= 0 || N <= 0) return HRN_ERR_BAD_ARG;
-    if (k != 64 || ((long long)B * M * k) % TMR != 0) return HRN_ERR_UNSUPPORTED;
-    if (B == 0) return HRN_OK;
-    const int n_tiles = (int)((long long)B * M * k / TMR);
-    auto kern = level1_fused_kernel<Cfg1, 64, 32, 32, 64, 32, 64>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg1::SMEM));
-        attr_set = true;
-    }
+template <class Cfg>
+int launch_level(const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,
+                 const float* biases, float* out_xyz, float* out_af, float* out_desc, int B, int M, int N, cudaStream_t st) {
+    const int n_tiles = (int)((long long)B * M * Cfg::KNBR / TMR);
+    auto kern = level_fused_kernel<Cfg>;
+    HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
-    kern<<<grid, TMR, Cfg1::SMEM, (cudaStream_t)stream>>>(q, xyz, (const int32_t*)idx, (const uint8_t*)Wpack, biases, out_xyz,
-                                                          out_af, out_desc, M, N, n_tiles);
+    const int per_sm = Cfg::RESIDENT ? 2 : 1;
+    const int grid = n_tiles < per_sm * sms ? n_tiles : per_sm * sms;
+    kern<<<grid, TMR, Cfg::SMEM, st>>>(q, xyz, feat, idx, (const uint8_t*)Wpack, biases, out_xyz, out_af, out_desc, M, N,
+                                       n_tiles);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
 
-HRN_API int hrn_level1_pack_bytes(void) { return Cfg1::W_BYTES; }
-HRN_API int hrn_level1_bias_count(void) { return Cfg1::B_COUNT; }
+}  // namespace
+
+// Fused detector + descriptor of hierarchy level `level` (1 or 2).  q [B*M,3] sampled keypoint coordinates,
+// xyz [B,N,3], feat [B,N,CIN] channels-last previous-level attentive features (level 2; NULL for level 1),
+// idx [B*M*k] int32 neighbour indices; Wpack / biases from engine_tc.pack_level (LevelCfg layout, execution order).
+// Outputs per keypoint: out_xyz [B*M,3], out_af [B*M,CO], out_desc [B*M,CD].
+HRN_API int hrn_level_fused(int level, const float* q, const float* xyz, const float* feat, const int32_t* idx,
+                            const void* Wpack, const float* biases, float* out_xyz, float* out_af, float* out_desc,
+                            int B, int M, int N, int k, void* stream) {
+    if (!q || !xyz || !idx || !Wpack || !biases || !out_xyz || !out_af || !out_desc || B < 0 || M <= 0 || N <= 0) return HRN_ERR_BAD_ARG;
+    if (((long long)B * M * k) % TMR != 0) return HRN_ERR_UNSUPPORTED;
+    if (B == 0) return HRN_OK;
+    if (level == 1 && k == CfgL1::KNBR && !feat)
+        return launch_level<CfgL1>(q, xyz, nullptr, idx, Wpack, biases, out_xyz, out_af, out_desc, B, M, N, (cudaStream_t)stream);
+    if (level == 2 && k == CfgL2::KNBR && feat)
+        return launch_level<CfgL2>(q, xyz, feat, idx, Wpack, biases, out_xyz, out_af, out_desc, B, M, N, (cudaStream_t)stream);
+    return HRN_ERR_UNSUPPORTED;
+}
+
+HRN_API int hrn_level_pack_bytes(int level) { return level == 1 ? CfgL1::W_BYTES : level == 2 ? CfgL2::W_BYTES : -1; }
+HRN_API int hrn_level_bias_count(int level) { return level == 1 ? CfgL1::B_COUNT : level == 2 ? CfgL2::B_COUNT : -1; }

@@ -16,7 +16,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADC
                    ptr, stream)
 
 _PRECISION = "fp32"
-_FUSED_LEVEL1 = True     # tc mode: run level 1 (detector + descriptor) as one persistent tcgen05 kernel
+_FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
 
 
 def set_precision(mode: str):
@@ -219,13 +219,14 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
     B, N, _ = xyz.shape
     fidx = fps(xyz, M, weights)
     idx, q = knn_idx(None, xyz, k, q_idx=fidx)
-    if (_PRECISION == "tc" and _FUSED_LEVEL1 and feat_cl is None and k == 64 and not want_maps
-            and [tuple(W.shape) for W, _, _ in det["convs"]] == [(32, 4), (32, 32), (64, 32)]
-            and [tuple(W.shape) for W, _, _ in desc["mlp"]] == [(32, 192), (64, 32)] and (B * M * k) % 128 == 0):
+    if _PRECISION == "tc" and _FUSED_LEVELS and not want_maps and (B * M * k) % 128 == 0:
         from . import engine_tc
-        keypoints, af, d = engine_tc.level1_fused(q, xyz, idx, det, desc)
-        sig = stack(RowsView(B * M).add(af), det["mlp"], last_act=ACT_SOFTPLUS_EPS)
-        return dict(xyz=keypoints.view(B, M, 3), sigmas=sig.view(B, M), af=af.view(B, M, -1), desc=d.view(B, M, -1))
+        cin = 0 if feat_cl is None else feat_cl.shape[2]
+        lv = engine_tc.which_level(k, cin, det, desc)
+        if lv is not None:
+            keypoints, af, d = engine_tc.level_fused(lv, q, xyz, feat_cl, idx, det, desc)
+            sig = stack(RowsView(B * M).add(af), det["mlp"], last_act=ACT_SOFTPLUS_EPS)
+            return dict(xyz=keypoints.view(B, M, 3), sigmas=sig.view(B, M), af=af.view(B, M, -1), desc=d.view(B, M, -1))
     geom, nn = group_geometry(q, xyz, idx, want_nn=True)
     rows = B * M * k
 

@@ -52,13 +52,15 @@ def layer_tc(view, W, b, act, out):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# fused level-1 kernel (csrc/level_fused.cu)
+# fused level kernels (csrc/level_fused.cu)
 # ------------------------------------------------------------------------------------------------------------------
-_level1_cache = {}
+_level_cache = {}
+_LEVEL_DIMS = {1: dict(k=64, cin=0, c1=32, c2=32, co=64, cmid=32, cd=64),
+               2: dict(k=32, cin=64, c1=64, c2=64, co=128, cmid=64, cd=128)}
 
 
 def _umma_tiles(W, K_pad):
-    """fp32 [N, K] -> bytes of the resident UMMA B operand: hi plane [K_pad/8][N][8] bf16, then the lo plane."""
+    """fp32 [N, K] -> bytes of a UMMA B operand block: hi plane [K_pad/8][N][8] bf16, then the lo plane."""
     N, K = W.shape
     Wp = torch.zeros(N, K_pad, dtype=torch.float32, device=W.device)
     Wp[:, :K] = W
@@ -68,40 +70,60 @@ def _umma_tiles(W, K_pad):
     return torch.cat(planes).view(torch.uint8)
 
 
-def pack_level1(det, desc):
-    """det / desc: folded parameter dicts of detector_1 / desc_extractor_1 -> (Wpack uint8, biases fp32) in the
-    layout of LevelCfg<64,32,32,64,32,64> (csrc/level_fused.cu)."""
-    key = tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
-    hit = _level1_cache.get(key)
+def level_supported(level_dims, det, desc):
+    d = level_dims
+    shapes = [tuple(W.shape) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"]]
+    first = (d["c1"], d["cin"] + 4)
+    return shapes == [first, (d["c2"], d["c1"]), (d["co"], d["c2"])] * 2 + [(d["cmid"], 3 * d["co"]), (d["cd"], d["cmid"])]
+
+
+def which_level(k, cin, det, desc):
+    for lv, d in _LEVEL_DIMS.items():
+        if d["k"] == k and d["cin"] == cin and level_supported(d, det, desc):
+            return lv
+    return None
+
+
+def pack_level(level, det, desc):
+    """Folded parameter dicts of detector_l / desc_extractor_l -> (Wpack uint8, biases fp32) in the LevelCfg layout of
+    csrc/level_fused.cu: blocks in execution order d1 d2 d3 x1 x2 x3 mlp1[X1] mlp1[max X1] mlp1[E*a] mlp2.  The grouped
+    input channels are re-ordered from the reference's [rel(3), dist(1), feat(C)] (layers.py:21-26) to
+    [feat(C), rel(3), dist(1), 0-pad] so that the gathered feature row lands on 8-channel chunk boundaries."""
+    key = (level,) + tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
+    hit = _level_cache.get(key)
     if hit is not None:
         return hit
+    d = _LEVEL_DIMS[level]
     (d1, bd1, _), (d2, bd2, _), (d3, bd3, _) = det["convs"]
     (x1, bx1, _), (x2, bx2, _), (x3, bx3, _) = desc["convs"]
     (m1, bm1, _), (m2, bm2, _) = desc["mlp"]
-    CO = d3.shape[0]
-    assert d1.shape == (32, 4) and d2.shape == (32, 32) and d3.shape == (64, 32) and m1.shape == (32, 3 * CO) and m2.shape == (64, 32)
-    parts = [_umma_tiles(d1, 16), _umma_tiles(d2, 32), _umma_tiles(d3, 32),
-             _umma_tiles(x1, 16), _umma_tiles(x2, 32), _umma_tiles(x3, 32),
-             _umma_tiles(m1[:, :CO].contiguous(), CO), _umma_tiles(m1[:, CO:2 * CO].contiguous(), CO),
-             _umma_tiles(m1[:, 2 * CO:].contiguous(), CO), _umma_tiles(m2, 32)]
+    CO, cin = d["co"], d["cin"]
+    KG = (cin + 4 + 15) // 16 * 16
+    perm = list(range(4, 4 + cin)) + [0, 1, 2, 3]
+    parts = [_umma_tiles(d1[:, perm].contiguous(), KG), _umma_tiles(d2, d["c1"]), _umma_tiles(d3, d["c2"]),
+             _umma_tiles(x1[:, perm].contiguous(), KG), _umma_tiles(x2, d["c1"]), _umma_tiles(x3, d["c2"]),
+             _umma_tiles(m1[:, CO:2 * CO].contiguous(), CO), _umma_tiles(m1[:, :CO].contiguous(), CO),
+             _umma_tiles(m1[:, 2 * CO:].contiguous(), CO), _umma_tiles(m2, d["cmid"])]
     Wpack = torch.cat(parts).contiguous()
     biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()
     from ._lib import lib
-    assert Wpack.numel() == lib().hrn_level1_pack_bytes() and biases.numel() == lib().hrn_level1_bias_count()
+    assert Wpack.numel() == lib().hrn_level_pack_bytes(level) and biases.numel() == lib().hrn_level_bias_count(level)
     out = (Wpack, biases, [t[0] for t in det["convs"] + desc["convs"] + desc["mlp"]])
-    _level1_cache[key] = out
+    _level_cache[key] = out
     return out
 
 
-def level1_fused(q, xyz, idx, det, desc):
-    """q [B,M,3], xyz [B,N,3], idx [B,M,64] int32 -> keypoints [B*M,3], af [B*M,64], desc [B*M,64]."""
+def level_fused(level, q, xyz, feat_cl, idx, det, desc):
+    """q [B,M,3], xyz [B,N,3], feat_cl [B,N,C] | None, idx [B,M,k] int32 -> keypoints [B*M,3], af [B*M,CO], desc [B*M,CD]."""
     B, M, k = idx.shape
     N = xyz.shape[1]
-    Wpack, biases, _ = pack_level1(det, desc)
+    d = _LEVEL_DIMS[level]
+    Wpack, biases, _ = pack_level(level, det, desc)
     dev = xyz.device
     kp = torch.empty(B * M, 3, dtype=torch.float32, device=dev)
-    af = torch.empty(B * M, 64, dtype=torch.float32, device=dev)
-    d = torch.empty(B * M, 64, dtype=torch.float32, device=dev)
-    engine.call("hrn_level1_fused", engine.ptr(q), engine.ptr(xyz), engine.ptr(idx), engine.ptr(Wpack), engine.ptr(biases),
-                engine.ptr(kp), engine.ptr(af), engine.ptr(d), B, M, N, k, engine.stream())
-    return kp, af, d
+    af = torch.empty(B * M, d["co"], dtype=torch.float32, device=dev)
+    ds = torch.empty(B * M, d["cd"], dtype=torch.float32, device=dev)
+    engine.call("hrn_level_fused", level, engine.ptr(q), engine.ptr(xyz), engine.ptr(feat_cl), engine.ptr(idx),
+                engine.ptr(Wpack), engine.ptr(biases), engine.ptr(kp), engine.ptr(af), engine.ptr(ds), B, M, N, k,
+                engine.stream())
+    return kp, af, ds
