@@ -301,6 +301,12 @@ def _profile_families(reg, steps=3):
             rows_t = a[0]._obj
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
             fl = 2.0 * view_rows * K * cout
+        elif name == "hrn_level_fused":
+            # algorithmic MACs per neighbour row of a fused level: detector + descriptor conv stacks + mlp1 + mlp2
+            lv, Bc, Mc, kc = a[0], a[10], a[11], a[13]
+            cin, c1, c2, co, cm, cd = {1: (0, 32, 32, 64, 32, 64), 2: (64, 64, 64, 128, 64, 128)}[lv]
+            macs = 2 * ((cin + 4) * c1 + c1 * c2 + c2 * co) + 3 * co * cm + cm * cd
+            fl = 2.0 * Bc * Mc * kc * macs
         rec.append((name, s, e, fl))
         return r
 
@@ -316,14 +322,14 @@ def _profile_families(reg, steps=3):
         fam[name] = fam.get(name, 0.0) + s.elapsed_time(e) / steps
         flops[name] = flops.get(name, 0.0) + fl / steps
     fam = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
-    layer_names = [n for n in fam if n.startswith("hrn_layer")]
+    layer_names = [n for n in fam if n.startswith("hrn_layer") or n == "hrn_level_fused"]
     layer_ms = sum(fam[n] for n in layer_names)
     layer_fl = sum(flops[n] for n in layer_names)
-    n_layer = sum(1 for r in rec if r[0].startswith("hrn_layer")) / steps
+    n_layer = sum(1 for r in rec if r[0] in layer_names) / steps
 
     def roofline(pk):
         ach = layer_fl / (layer_ms / 1e3) / 1e12 if layer_ms > 0 else 0.0
-        return {"kernel": "+".join(layer_names) + " (shared-MLP layers)", "bound": "tensor", "achieved": ach,
+        return {"kernel": "+".join(layer_names) + " (shared-MLP tensor-core kernels)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                 "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": n_layer, "ms_per_step": layer_ms, "share_of_step": layer_ms / sum(fam.values()),

@@ -66,13 +66,28 @@ __device__ __forceinline__ void load_chunk(const RowSrc& rs, int cg, float4& v0,
 template <bool FAST>
 __global__ void __launch_bounds__(TM)
 layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
-                float* __restrict__ Y, int ldy, long long rows, int Cout, int NP, int n_stage, int tmem_cols) {
+                float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NP, int n_stage, int tmem_cols) {
+    // NPfull = padded Cout of the packed weights; NP = columns handled by this CTA (slice blockIdx.y of NPfull)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[5];     // [0,1] W landed, [2,3] stage consumed by MMA, [4] accumulator ready
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int n0 = blockIdx.y * NP;
     const uint32_t w_stage_bytes = (uint32_t)NP * 128u;                 // 2 * (KC/8) * NP * 16
+    const size_t w_full_stage = (size_t)NPfull * 64;                    // bf16 elements per packed stage
+    // one stage of this CTA's weight slice: 1 bulk copy (full width) or 8 (one per hi/lo plane and k-chunk)
+    auto fetch_w = [&](int stage, uint32_t dst, uint32_t barw) {
+        mbar_expect_tx(barw, w_stage_bytes);
+        const __nv_bfloat16* src = Wp + (size_t)stage * w_full_stage;
+        if (NP == NPfull) {
+            bulk_g2s(dst, src, w_stage_bytes, barw);
+        } else {
+#pragma unroll
+            for (int pc = 0; pc < 2 * (KC / 8); ++pc)
+                bulk_g2s(dst + pc * NP * 16, src + ((size_t)pc * NPfull + n0) * 8, (uint32_t)NP * 16, barw);
+        }
+    };
     uint8_t* sA[2] = {smem, smem + A_STAGE_BYTES};
     uint8_t* sW[2] = {smem + 2 * A_STAGE_BYTES, smem + 2 * A_STAGE_BYTES + w_stage_bytes};
     const uint32_t bar_w[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
@@ -83,8 +98,7 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // first weight stage can fly while TMEM is allocated and the rows are resolved
-        mbar_expect_tx(bar_w[0], w_stage_bytes);
-        bulk_g2s(smem_u32(sW[0]), Wp, w_stage_bytes, bar_w[0]);
+        fetch_w(0, smem_u32(sW[0]), bar_w[0]);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
@@ -174,33 +188,34 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
             // weights of the next stage: its buffer is free once the MMAs of stage i-1 have drained
             if (i + 1 < n_stage) {
                 if (i >= 1) mbar_wait(bar_m[s ^ 1], ((i - 1) >> 1) & 1);
-                mbar_expect_tx(bar_w[s ^ 1], w_stage_bytes);
-                bulk_g2s(smem_u32(sW[s ^ 1]), Wp + (size_t)(i + 1) * (w_stage_bytes / 2), w_stage_bytes, bar_w[s ^ 1]);
+                fetch_w(i + 1, smem_u32(sW[s ^ 1]), bar_w[s ^ 1]);
             }
         }
     }
     // ---- epilogue ---------------------------------------------------------------------------------------------
     mbar_wait(bar_done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* yrow = Y + r * ldy;
-    for (int c0 = 0; c0 < Cout; c0 += 32) {
+    float* yrow = Y + r * ldy + n0;
+    const float* brow = bias + n0;
+    const int ncols = min(NP, Cout - n0);                               // valid output columns of this slice
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
         if (rvalid) {
-            if (c0 + 32 <= Cout && ((reinterpret_cast<uintptr_t>(yrow + c0) & 15) == 0)) {
+            if (c0 + 32 <= ncols && ((reinterpret_cast<uintptr_t>(yrow + c0) & 15) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
-                    o.x = act_fn(__uint_as_float(v[j + 0]) + __ldg(bias + c0 + j + 0), act);
-                    o.y = act_fn(__uint_as_float(v[j + 1]) + __ldg(bias + c0 + j + 1), act);
-                    o.z = act_fn(__uint_as_float(v[j + 2]) + __ldg(bias + c0 + j + 2), act);
-                    o.w = act_fn(__uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3), act);
+                    o.x = act_fn(__uint_as_float(v[j + 0]) + __ldg(brow + c0 + j + 0), act);
+                    o.y = act_fn(__uint_as_float(v[j + 1]) + __ldg(brow + c0 + j + 1), act);
+                    o.z = act_fn(__uint_as_float(v[j + 2]) + __ldg(brow + c0 + j + 2), act);
+                    o.w = act_fn(__uint_as_float(v[j + 3]) + __ldg(brow + c0 + j + 3), act);
                     *reinterpret_cast<float4*>(yrow + c0 + j) = o;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (c0 + j < Cout) yrow[c0 + j] = act_fn(__uint_as_float(v[j]) + __ldg(bias + c0 + j), act);
+                    if (c0 + j < ncols) yrow[c0 + j] = act_fn(__uint_as_float(v[j]) + __ldg(brow + c0 + j), act);
             }
         }
     }
@@ -227,9 +242,15 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     }
     if (n_stage != (chunks * 8 + KC - 1) / KC) return HRN_ERR_BAD_ARG;
     if (rows == 0) return HRN_OK;
+    // few row tiles (per-keypoint heads, coarse level): split the output columns over blockIdx.y so that the grid
+    // still covers the 148 SMs
+    const int tiles = hrn_divup(rows, TM);
+    int NS = NP;
+    while (NS > 64 && (NS / 2) % 16 == 0 && tiles * (NP / NS) < 2 * 148) NS >>= 1;
+    const int n_split = NP / NS;
     int tmem_cols = 32;
-    while (tmem_cols < NP) tmem_cols <<= 1;
-    const size_t smem = 2 * (size_t)A_STAGE_BYTES + 2 * (size_t)NP * 128;
+    while (tmem_cols < NS) tmem_cols <<= 1;
+    const size_t smem = 2 * (size_t)A_STAGE_BYTES + 2 * (size_t)NS * 128;
     static bool attr_set = false;
     if (!attr_set) {
         HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * 128));
@@ -241,12 +262,13 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
         const hrn_seg_t& g = in->seg[s];
         if ((g.channels & 3) || (g.ld & 3) || (g.col0 & 3) || ((uintptr_t)g.ptr & 15)) fast = false;
     }
+    dim3 grid(tiles, n_split);
     if (fast)
-        layer_tc_kernel<true><<<hrn_divup(rows, TM), TM, smem, (cudaStream_t)stream>>>(
-            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, tmem_cols);
+        layer_tc_kernel<true><<<grid, TM, smem, (cudaStream_t)stream>>>(
+            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols);
     else
-        layer_tc_kernel<false><<<hrn_divup(rows, TM), TM, smem, (cudaStream_t)stream>>>(
-            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, tmem_cols);
+        layer_tc_kernel<false><<<grid, TM, smem, (cudaStream_t)stream>>>(
+            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }

@@ -302,15 +302,23 @@ def _cosine_features(S, D, idx, misc, col_sd, col_ds):
          col_sd, col_ds, stream())
 
 
-def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8):
-    """CoarseReg.forward with use_sim=use_neighbor=True (reference layers.py:273-396)."""
+def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None):
+    """CoarseReg.forward with use_sim=use_neighbor=True (reference layers.py:273-396).
+
+    both = (xyz [2B,N,3], desc_cl [2B,N,C]) with the source clouds in the first half and the target clouds in the
+    second (the model path has them contiguous): the two neighbour-aware branches (layers.py:316-337) then run as ONE
+    batch of 2B clouds instead of two."""
     B, N1, C = sdesc_cl.shape
     N2 = dxyz.shape[1]
     idx, _ = knn_idx(sdesc_cl, ddesc_cl, k)                      # 256-d descriptor space (layers.py:278)
     misc, _ = group_geometry(sxyz, dxyz, idx, ssig, dsig, ld=16)  # cols 0..11; 12..15 = similarity features
     _cosine_features(sdesc_cl, ddesc_cl, idx, misc, 12, 13)
-    s_nbr = _neighbour_aware(sxyz, sdesc_cl, P, k)
-    d_nbr = _neighbour_aware(dxyz, ddesc_cl, P, k)
+    if both is not None and N1 == N2:
+        nb = _neighbour_aware(both[0], both[1], P, k)
+        s_nbr, d_nbr = nb[:B], nb[B:]
+    else:
+        s_nbr = _neighbour_aware(sxyz, sdesc_cl, P, k)
+        d_nbr = _neighbour_aware(dxyz, ddesc_cl, P, k)
     _cosine_features(s_nbr, d_nbr, idx, misc, 14, 15)
     v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
     v.add(misc).add(sdesc_cl.view(B * N1, C), SEG_BROADCAST).add(ddesc_cl.view(B * N2, C), SEG_GATHER)

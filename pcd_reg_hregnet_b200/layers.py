@@ -162,8 +162,8 @@ class CoarseReg(_Folded):
         return engine.coarse_reg(src_xyz.contiguous(), _cl(src_desc), dst_xyz.contiguous(), _cl(dst_desc),
                                  src_weights.contiguous(), dst_weights.contiguous(), self.folded(), self.k)
 
-    def forward_cl(self, sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig):
-        return engine.coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, self.folded(), self.k)
+    def forward_cl(self, sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, both=None):
+        return engine.coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, self.folded(), self.k, both=both)
 
 
 class FineReg(_Folded):

@@ -72,7 +72,7 @@ class HRegNet(nn.Module):
         D = {k: v[B:] for k, v in both.items()}
 
         cor3, w3 = self.coarse_corres.forward_cl(S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"], S["sigmas_3"],
-                                                 D["sigmas_3"])
+                                                 D["sigmas_3"], both=(both["xyz_3"], both["desc_3"]))
         R3, t3 = engine.weighted_kabsch(S["xyz_3"], cor3, w3)
 
         xyz2_t = engine.transform_points(S["xyz_2"], R3, t3)

@@ -60,6 +60,10 @@ def _knn(p1, q_idx, p2, B, M, N, D, K, dists, idx64, idx32, nn, q_out, st):
     if nn is not None: nn.copy_(n)
 
 
+def _knn3_sorted(p1, q_idx, p2, B, M, N, K, pts, boxes, dists, idx64, idx32, nn, q_out, st):
+    _knn(p1, q_idx, p2, B, M, N, 3, K, dists, idx64, idx32, nn, q_out, st)       # same contract, same results
+
+
 def _gather_rows(x, idx, out, B, N, M, U, st):
     out.view(B, M, U).copy_(x.view(B, N, U)[torch.arange(B)[:, None], idx.view(B, M).long()])
 
@@ -152,7 +156,7 @@ def _weighted_kabsch(src, cor, w, B, N, Rp, tp, R, t, Rc, tc, st):
 
 
 _TABLE = {
-    "hrn_fps": _fps, "hrn_knn": _knn, "hrn_gather_rows": _gather_rows, "hrn_transpose": _transpose,
+    "hrn_fps": _fps, "hrn_knn": _knn, "hrn_knn3_sorted": _knn3_sorted, "hrn_gather_rows": _gather_rows, "hrn_transpose": _transpose,
     "hrn_group_geometry": _group_geometry, "hrn_group_attention": _group_attention,
     "hrn_group_weighted_sum": _group_weighted_sum, "hrn_group_max": _group_max,
     "hrn_sigma_to_weights": _sigma_to_weights, "hrn_transform_points": _transform_points,
