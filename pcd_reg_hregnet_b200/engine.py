@@ -16,6 +16,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADC
                    ptr, stream)
 
 _PRECISION = "fp32"
+_FUSED_CHAINS = True     # tc mode: three-layer conv stacks (<= 256 wide) + their group reductions in one kernel
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
 
 
@@ -95,6 +96,13 @@ def stack(view: RowsView, layers, last_act=None):
         v = view if li == 0 else RowsView(x.shape[0]).add(x)
         x = layer(v, W, b, act)
     return x
+
+
+def _chain_ok(view, layers, k):
+    if _PRECISION != "tc" or not _FUSED_CHAINS or k not in (8, 16, 32):
+        return False
+    from . import engine_tc
+    return engine_tc.chain_supported(view, layers)
 
 
 def group_attention(E, k):
@@ -236,6 +244,17 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
             v.add(feat_cl.view(B * N, -1), SEG_GATHER)
         return v
 
+    if _chain_ok(grouped(), det["convs"], k) and not want_maps:
+        from . import engine_tc
+        # detector stack + attention in one kernel: rows E*a (the attentive feature map), attentive feature, weights
+        Ea, af, a = engine_tc.chain3(grouped(), det["convs"], engine_tc.EPI_ATTN, k)
+        keypoints = group_weighted_sum(a, nn, k)
+        sig = stack(RowsView(B * M).add(af), det["mlp"], last_act=ACT_SOFTPLUS_EPS)
+        X1, X1max, _ = engine_tc.chain3(grouped(), desc["convs"], engine_tc.EPI_GROUPMAX, k)
+        v = RowsView(rows, group=k).add(X1max, SEG_BROADCAST).add(X1).add(Ea)
+        H = stack(v, desc["mlp"])
+        d = group_max(H, k)
+        return dict(xyz=keypoints.view(B, M, 3), sigmas=sig.view(B, M), af=af.view(B, M, -1), desc=d.view(B, M, -1))
     E = stack(grouped(), det["convs"])
     a = group_attention(E, k)
     keypoints = group_weighted_sum(a, nn, k)
@@ -270,8 +289,14 @@ def fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k=8, want_af=False):
     misc, _ = group_geometry(sxyz, dxyz, idx, ssig, dsig)
     v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
     v.add(misc).add(sfeat_cl.view(B * N1, -1), SEG_BROADCAST).add(dfeat_cl.view(B * N2, -1), SEG_GATHER)
-    F = stack(v, P["convs_1"])
-    cor, w, af = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
+    if _chain_ok(v, P["convs_1"], k):
+        from . import engine_tc
+        _, af, a = engine_tc.chain3(v, P["convs_1"], engine_tc.EPI_ATTN, k, want_rows=False)
+        cor = group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2).view(B, N1, 3)
+        w = stack(RowsView(B * N1).add(af), P["mlp"], last_act=ACT_SIGMOID).view(B, N1)
+    else:
+        F = stack(v, P["convs_1"])
+        cor, w, af = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
     return (cor, w, af) if want_af else (cor, w)
 
 
@@ -282,8 +307,11 @@ def _neighbour_aware(xyz, desc_cl, P, k):
     geom, _ = group_geometry(xyz, xyz, nidx)
     v = RowsView(B * N * k, group=k, gather_idx=nidx, rows_per_batch=N * k, src_rows_per_batch=N)
     v.add(desc_cl.view(B * N, C), SEG_GATHER).add(geom)
-    E = stack(v, P["convs_2"])
-    a = group_attention(E, k)
+    if _chain_ok(v, P["convs_2"], k):
+        from . import engine_tc
+        _, _, a = engine_tc.chain3(v, P["convs_2"], engine_tc.EPI_ATTN, k, want_rows=False, want_groups=False)
+    else:
+        a = group_attention(stack(v, P["convs_2"]), k)
     return group_weighted_sum(a, desc_cl.view(B * N, C), k, idx=nidx, groups_per_batch=N, N=N).view(B, N, C)
 
 

@@ -127,3 +127,68 @@ def level_fused(level, q, xyz, feat_cl, idx, det, desc):
                 engine.ptr(Wpack), engine.ptr(biases), engine.ptr(kp), engine.ptr(af), engine.ptr(ds), B, M, N, k,
                 engine.stream())
     return kp, af, ds
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# three-layer chain kernel (csrc/chain_tc.cu)
+# ------------------------------------------------------------------------------------------------------------------
+EPI_STORE, EPI_GROUPMAX, EPI_ATTN = 0, 1, 2
+_chain_cache = {}
+
+
+def _pieces(W, K_pad):
+    """fp32 [N, K] -> packed K=16 pieces: [piece][hi|lo][2 chunks][N][8] bf16 (as uint8)."""
+    N, K = W.shape
+    Wp = torch.zeros(N, K_pad, dtype=torch.float32, device=W.device)
+    Wp[:, :K] = W
+    hi = Wp.to(torch.bfloat16)
+    lo = (Wp - hi.float()).to(torch.bfloat16)
+    t = torch.stack([hi, lo], 0).view(2, N, K_pad // 16, 2, 8).permute(2, 0, 3, 1, 4).contiguous()
+    return t.view(-1).view(torch.uint8)
+
+
+def chain_supported(view, layers):
+    if len(layers) != 3 or view.rows % 128 != 0:
+        return False
+    from ._lib import ACT_RELU
+    for W, b, act in layers:
+        if act != ACT_RELU or W.shape[0] % 16 or W.shape[0] > 256:
+            return False
+    for mat, mode, ch, col0, scale in view.segs:
+        if ch % 4 or col0 % 4 or mat.stride(0) % 4 or mat.data_ptr() % 16:
+            return False
+    return True
+
+
+def pack_chain(layers, seg_channels):
+    key = tuple((W.data_ptr(), W._version) for W, _, _ in layers) + (tuple(seg_channels),)
+    hit = _chain_cache.get(key)
+    if hit is not None:
+        return hit
+    (W1, b1, _), (W2, b2, _), (W3, b3, _) = layers
+    chunks = sum((c + 7) // 8 for c in seg_channels)
+    chunks0 = (chunks + 1) // 2 * 2
+    W1p = torch.zeros(W1.shape[0], chunks0 * 8, dtype=torch.float32, device=W1.device)
+    src = dst = 0
+    for c in seg_channels:
+        W1p[:, dst:dst + c] = W1[:, src:src + c]
+        src += c
+        dst += (c + 7) // 8 * 8
+    Wpack = torch.cat([_pieces(W1p, chunks0 * 8), _pieces(W2, W2.shape[1]), _pieces(W3, W3.shape[1])]).contiguous()
+    bias = torch.cat([b1, b2, b3]).contiguous()
+    out = (Wpack, bias, chunks0, [W1, W2, W3])
+    _chain_cache[key] = out
+    return out
+
+
+def chain3(view, layers, mode, kseg, want_rows=True, want_groups=True):
+    """Runs the three folded layers on the virtual rows.  Returns (Y rows | None, G groups | None, a rows | None)."""
+    Wpack, bias, chunks0, _ = pack_chain(layers, [s[2] for s in view.segs])
+    n1, n2, n3 = (W.shape[0] for W, _, _ in layers)
+    dev = bias.device
+    Y = torch.empty(view.rows, n3, dtype=torch.float32, device=dev) if want_rows else None
+    G = torch.empty(view.rows // kseg, n3, dtype=torch.float32, device=dev) if (want_groups and mode != EPI_STORE) else None
+    a = torch.empty(view.rows, dtype=torch.float32, device=dev) if mode == EPI_ATTN else None
+    engine.call("hrn_chain3_tc", ctypes.byref(view.c), engine.ptr(Wpack), engine.ptr(bias), n1, n2, n3, chunks0, mode, kseg,
+                engine.ptr(Y), n3, engine.ptr(G), engine.ptr(a), view.rows, engine.stream())
+    return Y, G, a
