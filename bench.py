@@ -165,7 +165,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     precision = args.precision
     if precision == "auto":
-        precision = "tc" if hasattr(_lib.lib(), "hrn_layer_tc") else "fp32"
+        precision = "tc"
     engine.set_precision(precision)
 
     B, N = args.pairs_per_gpu, args.points

@@ -74,5 +74,23 @@ def main():
     return rows
 
 
+def knnd_bench():
+    """CoarseReg descriptor-space search: 256 queries x 256 refs x 256 dims, K=8, 32 pairs; and the level-1 search."""
+    p1 = torch.rand(32, 256, 256, device="cuda")
+    p2 = torch.rand(32, 256, 256, device="cuda")
+    t = timeit(lambda: engine.knn_idx(p1, p2, 8), reps=20)
+    print(json.dumps({"op": "knn_desc", "B": 32, "M": 256, "N": 256, "D": 256, "K": 8, "ms": t}), flush=True)
+    xyz = torch.rand(64, 16384, 3, device="cuda") * 100
+    idx = ops.furthest_point_sample(xyz, 1024)
+    for flag in (True, False):
+        engine._SORTED_KNN = flag
+        t = timeit(lambda: engine.knn_idx(None, xyz, 64, q_idx=idx))
+        print(json.dumps({"op": "knn_l1", "sorted": flag, "ms": t}), flush=True)
+    engine._SORTED_KNN = True
+
+
 if __name__ == "__main__":
-    main()
+    if "--knnd" in sys.argv:
+        knnd_bench()
+    else:
+        main()

@@ -137,65 +137,94 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
     });
 }
 
-// Generic D (descriptor space, D = 256 in CoarseReg).  Sequential fma chain over d per (query, ref) pair.
-constexpr int KNND_REFS = 32;
+// Generic D (descriptor space, D = 256 in CoarseReg).  Sequential fma chain over d per (query, ref) pair, so the
+// distances are bit-identical to the oracle; register-tiled: a CTA owns 32 queries, a warp 8 of them, a lane 4
+// references of the current 128-reference tile -> 32 independent accumulators per thread, 12 shared-memory loads per
+// 32 FMAs.  References stream through shared memory in [128 refs] x [64 dims] slices (padded rows: conflict-free).
+constexpr int KD_Q = 32;         // queries per CTA
+constexpr int KD_R = 128;        // references per tile
+constexpr int KD_D = 64;         // dims per slice
 template <int KPL>
-__global__ void __launch_bounds__(KNN_WARPS * 32)
+__global__ void __launch_bounds__(128)
 knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* __restrict__ out_d,
             int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn, int M, int N,
             int D, int K) {
     extern __shared__ float smem[];
-    float* s_q = smem;                          // [KNN_WARPS][D]
-    float* s_r = smem + KNN_WARPS * D;          // [KNND_REFS][D+1]
+    float* s_q = smem;                          // [KD_Q][D]
+    float* s_r = smem + KD_Q * D;               // [KD_R][KD_D + 1]
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * KNN_WARPS, m = m0 + warp;
-    const bool qvalid = m < M;
+    const int m0 = blockIdx.x * KD_Q;
     p1 += (size_t)b * M * D;
     p2 += (size_t)b * N * D;
-    for (int i = threadIdx.x; i < KNN_WARPS * D; i += blockDim.x) {
+    for (int i = threadIdx.x; i < KD_Q * D; i += blockDim.x) {
         const int q = i / D;
         s_q[i] = (m0 + q < M) ? p1[(size_t)(m0 + q) * D + (i - q * D)] : 0.f;
     }
-    WarpTopK<KPL> top;
-    top.init(K);
-    const int ldr = D + 1;
-    for (int t0 = 0; t0 < N; t0 += KNND_REFS) {
-        const int tn = min(KNND_REFS, N - t0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < tn * D; i += blockDim.x) {
-            const int r = i / D;
-            s_r[r * ldr + (i - r * D)] = __ldg(p2 + (size_t)(t0 + r) * D + (i - r * D));
-        }
-        __syncthreads();
-        float dist = CUDART_INF_F;
-        if (qvalid && lane < tn) {
-            dist = 0.f;
-            const float* q = s_q + warp * D;
-            const float* r = s_r + lane * ldr;
-#pragma unroll 8
-            for (int d = 0; d < D; ++d) {
-                const float diff = q[d] - r[d];
-                dist = __fmaf_rn(diff, diff, dist);
+    WarpTopK<KPL> top[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) top[q].init(K);
+    constexpr int LDR = KD_D + 1;
+    for (int t0 = 0; t0 < N; t0 += KD_R) {
+        float acc[8][4];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
+        for (int d0 = 0; d0 < D; d0 += KD_D) {
+            const int dn = min(KD_D, D - d0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < KD_R * KD_D; i += blockDim.x) {
+                const int rr = i / KD_D, dd = i - rr * KD_D;
+                s_r[rr * LDR + dd] = (t0 + rr < N && dd < dn) ? __ldg(p2 + (size_t)(t0 + rr) * D + d0 + dd) : 0.f;
+            }
+            __syncthreads();
+            const float* qb = s_q + (warp * 8) * D + d0;
+            for (int d = 0; d < dn; ++d) {
+                float rv[4], qv[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rv[j] = s_r[(lane + 32 * j) * LDR + d];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) qv[q] = qb[q * D + d];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float diff = qv[q] - rv[j];
+                        acc[q][j] = __fmaf_rn(diff, diff, acc[q][j]);
+                    }
             }
         }
-        if (qvalid) top.offer(dist, t0 + lane, lane);
-    }
-    if (!qvalid) return;
-    const size_t base = ((size_t)b * M + m) * K;
-    top.for_each(lane, [&](int pos, float d, int i) {
-        if (out_d) out_d[base + pos] = d;
-        if (out_i64) out_i64[base + pos] = (int64_t)i;
-        if (out_i32) out_i32[base + pos] = i;
-    });
-    if (out_nn) {
-        __syncwarp();
-        for (int pos = 0; pos < K; ++pos) {
-            const int s = pos >> 5, l = pos & 31;
-            int iv = top.i[0];
 #pragma unroll
-            for (int t = 1; t < KPL; ++t) if (s == t) iv = top.i[t];
-            const int src = __shfl_sync(0xffffffffu, iv, l);
-            for (int d = lane; d < D; d += 32) out_nn[(base + pos) * D + d] = __ldg(p2 + (size_t)src * D + d);
+        for (int q = 0; q < 8; ++q) {
+            if (m0 + warp * 8 + q < M) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = t0 + lane + 32 * j;
+                    top[q].offer(n < N ? acc[q][j] : CUDART_INF_F, n, lane);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int m = m0 + warp * 8 + q;
+        if (m >= M) continue;
+        const size_t base = ((size_t)b * M + m) * K;
+        top[q].for_each(lane, [&](int pos, float d, int i) {
+            if (out_d) out_d[base + pos] = d;
+            if (out_i64) out_i64[base + pos] = (int64_t)i;
+            if (out_i32) out_i32[base + pos] = i;
+        });
+        if (out_nn) {
+            __syncwarp();
+            for (int pos = 0; pos < K; ++pos) {
+                const int s = pos >> 5, l = pos & 31;
+                int iv = top[q].i[0];
+#pragma unroll
+                for (int t = 1; t < KPL; ++t) if (s == t) iv = top[q].i[t];
+                const int src = __shfl_sync(0xffffffffu, iv, l);
+                for (int d = lane; d < D; d += 32) out_nn[(base + pos) * D + d] = __ldg(p2 + (size_t)src * D + d);
+            }
         }
     }
 }
@@ -217,14 +246,15 @@ HRN_API int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int 
         if (K <= 32) knn3_kernel<1><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
         else knn3_kernel<2><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
     } else {
-        const size_t smem = ((size_t)KNN_WARPS * D + (size_t)KNND_REFS * (D + 1)) * sizeof(float);
+        const size_t smem = ((size_t)KD_Q * D + (size_t)KD_R * (KD_D + 1)) * sizeof(float);
         if (smem > 200 * 1024) return HRN_ERR_UNSUPPORTED;
+        dim3 gridd(hrn_divup(M, KD_Q), B);
         if (K <= 32) {
             if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnd_kernel<1><<<grid, KNN_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+            knnd_kernel<1><<<gridd, 128, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
         } else {
             if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnd_kernel<2><<<grid, KNN_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+            knnd_kernel<2><<<gridd, 128, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
         }
     }
     HRN_LAUNCH_CHECK();

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADCAST, SEG_DIRECT, SEG_GATHER, Rows, call,
                    ptr, stream)
 
-_PRECISION = "fp32"
+_PRECISION = "tc"       # "tc": tcgen05 kernels (bf16x3, fp32-class accuracy); "fp32": exact CUDA-core layers
 _FUSED_CHAINS = True     # tc mode: three-layer conv stacks (<= 256 wide) + their group reductions in one kernel
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
 

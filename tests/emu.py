@@ -167,6 +167,8 @@ _TABLE = {
 @contextlib.contextmanager
 def emulated_kernels():
     saved = (engine.ptr, engine.stream, engine.call, engine._launch_layer_fp32)
+    prec = engine.get_precision()
+    engine.set_precision("fp32")          # the emulation covers the exact-fp32 orchestration path
     engine.ptr = lambda t: t
     engine.stream = lambda: 0
     engine.call = lambda name, *a: _TABLE[name](*a)
@@ -175,3 +177,4 @@ def emulated_kernels():
         yield
     finally:
         engine.ptr, engine.stream, engine.call, engine._launch_layer_fp32 = saved
+        engine.set_precision(prec)

@@ -18,7 +18,7 @@ def precision(request):
     from pcd_reg_hregnet_b200 import engine as _e
     _e.set_precision(request.param)
     yield request.param
-    _e.set_precision("fp32")
+    _e.set_precision("tc")
 FEAT_TOL = 1e-3          # per-tensor max|x-ref|/max|ref|
 
 

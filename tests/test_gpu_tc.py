@@ -30,11 +30,12 @@ def _check(view, cols, Cout, act, seed):
     b = torch.randn(Cout, generator=g).to(DEV)
     want = _ref(cols, W, b, act)
     engine.set_precision("tc")
+    got = engine.layer(view, W, b, act)
+    engine.set_precision("fp32")
     try:
-        got = engine.layer(view, W, b, act)
+        got32 = engine.layer(view, W, b, act)
     finally:
-        engine.set_precision("fp32")
-    got32 = engine.layer(view, W, b, act)
+        engine.set_precision("tc")
     torch.cuda.synchronize()
     scale = float(want.abs().max())
     e_tc = float((got.double() - want).abs().max()) / scale
@@ -74,3 +75,42 @@ def test_segments_gather_broadcast_scale():
     # strided source / column offset
     v2 = RowsView(rows).add(misc, channels=5, col0=3).add(misc, channels=4, col0=12)
     _check(v2, torch.cat([misc[:, 3:8], misc[:, 12:16]], 1), 48, ACT_RELU, seed=6)
+
+
+@pytest.mark.parametrize("kseg,mode", [(8, 2), (16, 2), (16, 1), (32, 1), (32, 2), (8, 0)])
+def test_chain3_kernel(kseg, mode):
+    """csrc/chain_tc.cu against an fp64 evaluation of the three layers + group reduction."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    g = torch.Generator().manual_seed(kseg * 10 + mode)
+    B, M, N, C = 2, 128 * 8 // kseg, 300, 128
+    rows = B * M * kseg
+    misc = torch.randn(rows, 12, generator=g).to(DEV)
+    src = torch.randn(B * M, C, generator=g).to(DEV)
+    dst = torch.randn(B * N, C, generator=g).to(DEV)
+    idx = torch.randint(0, N, (B, M, kseg), generator=g).int().to(DEV)
+    v = RowsView(rows, group=kseg, gather_idx=idx, rows_per_batch=M * kseg, src_rows_per_batch=N)
+    v.add(misc).add(src, SEG_BROADCAST).add(dst, SEG_GATHER)
+    r = torch.arange(rows, device=DEV)
+    X = torch.cat([misc, src[r // kseg], dst[(r // (M * kseg)) * N + idx.view(-1).long()]], 1).double()
+    dims = [12 + 2 * C, 256, 128, 256]
+    layers = []
+    for i in range(3):
+        W = (torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5).to(DEV)
+        b = (torch.randn(dims[i + 1], generator=g) * 0.1).to(DEV)
+        layers.append((W, b, ACT_RELU))
+        X = torch.relu(X @ W.double().t() + b.double())
+    assert engine_tc.chain_supported(v, layers)
+    Y, G, a = engine_tc.chain3(v, layers, mode, kseg)
+    torch.cuda.synchronize()
+    Xg = X.view(-1, kseg, 256)
+    scale = float(X.abs().max())
+    if mode == 0:
+        assert float((Y.double() - X).abs().max()) / scale < 1e-4
+    elif mode == 1:
+        assert float((Y.double() - X).abs().max()) / scale < 1e-4
+        assert float((G.double() - Xg.max(dim=1)[0]).abs().max()) / scale < 1e-4
+    else:
+        a_ref = torch.softmax(Xg.max(dim=2)[0], dim=1)
+        assert float((a.double().view(-1, kseg) - a_ref).abs().max()) < 1e-4
+        assert float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale < 1e-4
+        assert float((Y.double().view(-1, kseg, 256) - a_ref[:, :, None] * Xg).abs().max()) / scale < 1e-4
