@@ -71,96 +71,6 @@ struct WarpTopK {
     }
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// Buffered variant of the running top-K: candidates that beat the (possibly stale) K-th entry are appended to a
-// 32-entry per-warp buffer in shared memory; a full buffer is sorted with a 32-lane bitonic network and merged into
-// the sorted list with bitonic half-cleaners (~230 instructions per 32 candidates instead of ~35 per candidate for
-// one-at-a-time insertion).  The threshold is only refreshed at a flush -- it can only be looser than the exact one,
-// so the final list is still the exact K smallest by (dist, index).
-__device__ __forceinline__ void cmpx(float& d, int& i, int j, bool keep_min) {
-    const float od = __shfl_xor_sync(0xffffffffu, d, j);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, j);
-    const bool self_less = cand_less(d, i, od, oi);
-    const bool take_self = (self_less == keep_min);
-    d = take_self ? d : od;
-    i = take_self ? i : oi;
-}
-__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) cmpx(d, i, j, ((lane & j) == 0) == ((lane & k) == 0));
-}
-__device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {   // bitonic in -> ascending out
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) cmpx(d, i, j, (lane & j) == 0);
-}
-
-template <int KPL>
-struct BufTopK {
-    float d[KPL];          // sorted list: position s*32 + lane
-    int i[KPL];
-    float thr_d;
-    int thr_i;
-    int K, cnt;
-    float2* buf;           // [32] (dist, index bits) per warp, shared memory
-    __device__ __forceinline__ void init(int K_, float2* b) {
-        K = K_; cnt = 0; buf = b;
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) { d[s] = CUDART_INF_F; i[s] = 0x7fffffff; }
-        thr_d = CUDART_INF_F; thr_i = 0x7fffffff;
-    }
-    __device__ __forceinline__ void flush(int lane) {
-        if (cnt == 0) return;
-        __syncwarp();
-        float cd = CUDART_INF_F; int ci = 0x7fffffff;
-        if (lane < cnt) { const float2 c = buf[lane]; cd = c.x; ci = __float_as_int(c.y); }
-        __syncwarp();
-        cnt = 0;
-        bitonic_sort32(cd, ci, lane);
-        // reversed candidates against the LAST list register: keep the 32 smallest of (last 32 | candidates)
-        {
-            const float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
-            const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
-            const bool keep = cand_less(d[KPL - 1], i[KPL - 1], rd, ri);
-            cd = keep ? d[KPL - 1] : rd;
-            ci = keep ? i[KPL - 1] : ri;
-            bitonic_merge32(cd, ci, lane);        // (cd, ci): sorted 32 smallest of the upper part
-        }
-        if (KPL == 2) {
-            // merge the two sorted 32-lists d[0] and (cd) into a sorted 64
-            const float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
-            const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
-            const bool lo_self = cand_less(d[0], i[0], rd, ri);
-            const float ld = lo_self ? d[0] : rd;  const int li = lo_self ? i[0] : ri;     // 32 smallest (bitonic)
-            float hd = lo_self ? rd : d[0];        int hi = lo_self ? ri : i[0];           // 32 largest (bitonic)
-            d[0] = ld; i[0] = li;
-            bitonic_merge32(d[0], i[0], lane);
-            bitonic_merge32(hd, hi, lane);
-            d[KPL - 1] = hd; i[KPL - 1] = hi;
-        } else {
-            d[0] = cd; i[0] = ci;
-        }
-        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
-        float td = d[0]; int ti = i[0];
-#pragma unroll
-        for (int s = 1; s < KPL; ++s) if (ks == s) { td = d[s]; ti = i[s]; }
-        thr_d = __shfl_sync(0xffffffffu, td, kl);
-        thr_i = __shfl_sync(0xffffffffu, ti, kl);
-    }
-    __device__ __forceinline__ void offer(float cd, int ci, int lane) {
-        unsigned mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
-        if (mask == 0) return;
-        if (cnt + __popc(mask) > 32) {
-            flush(lane);
-            mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
-            if (mask == 0) return;
-        }
-        if (mask & (1u << lane)) buf[cnt + __popc(mask & ((1u << lane) - 1u))] = make_float2(cd, __int_as_float(ci));
-        cnt += __popc(mask);
-    }
-};
-
 __device__ __forceinline__ unsigned part1by1(unsigned v) {
     v &= 0x0000ffffu;
     v = (v | (v << 8)) & 0x00ff00ffu;
@@ -237,7 +147,6 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
                    int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn,
                    float* __restrict__ out_q, int M, int N, int N2, int K) {
     extern __shared__ float s_box[];                        // [nbox][6]
-    __shared__ float2 s_cand[QWARPS][32];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbox = N2 >> 5;
     const float* bsrc = boxes + (size_t)b * nbox * 6;
@@ -265,8 +174,8 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             bd[g] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
         }
     }
-    BufTopK<KPL> top;
-    top.init(K, s_cand[warp]);
+    WarpTopK<KPL> top;
+    top.init(K);
     auto open_box = [&](int bx) {
         const float4 p = __ldg(pts + bx * 32 + lane);
         const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
@@ -285,7 +194,6 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         const int g_sel = __shfl_sync(0xffffffffu, bg, src);
         if (wmin == hrn_ford(CUDART_INF_F)) break;
         open_box(g_sel * 32 + src);
-        top.flush(lane);
         if (lane == src) {
 #pragma unroll
             for (int g = 0; g < MAXBPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;   // visited
@@ -302,9 +210,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             const float bnd = __shfl_sync(0xffffffffu, bd[g], src);
             if (bnd <= top.thr_d) open_box(g * 32 + src);
         }
-        top.flush(lane);              // refresh the threshold once per 32 boxes
     }
-    top.flush(lane);
     const size_t base = ((size_t)b * M + m) * K;
 #pragma unroll
     for (int s = 0; s < KPL; ++s) {
