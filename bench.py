@@ -133,7 +133,7 @@ def run_reference(args, rank):
         dt = time.perf_counter() - t0
     v = steps * per_step / dt
     sample = f"{per_step} pairs x {args.points} pts per step, B=1 forwards, {steps} steps"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -144,7 +144,20 @@ def run_reference(args, rank):
     }))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was re-routed to
+    stderr at the file-descriptor level by main()."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -255,7 +268,7 @@ def main():
             v, cores, dt = cpu_reference_pairs_per_s(args.cpu_sample_pairs, N)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample_pairs} pairs x {N} pts, B=1 forwards, {dt:.1f} s"}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

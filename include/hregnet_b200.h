@@ -121,14 +121,16 @@ int hrn_layer_fp32(const hrn_rows_t* in, const float* W, const float* bias, int 
 int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
                  int Cout, int NP, int n_stage, void* stream);
 
-/* Three fused shared-MLP layers (the reference's conv stacks `convs`, `convs_1`, `convs_2` with widths <= 256:
- * layers.py:118-121,249-260,420-423) with the activations kept in shared / tensor memory, plus the reduction that
- * consumes them: mode 0 = store Y rows (layers.py:201); 1 = Y rows and G[g,:] = max over the kseg rows of each group
- * (layers.py:202); 2 = a = softmax_k(max_c Y), G[g,:] = sum_k a*Y (attentive feature), Y (optional) = the rows Y*a
- * (layers.py:150-159,329-332,384-390,446-450).  W = K=16 weight pieces of the three layers in execution order
- * (pcd_reg_hregnet_b200/engine_tc.pack_chain), bias = b1|b2|b3, chunks0 = 8-wide K chunks of the virtual input. */
-int hrn_chain3_tc(const hrn_rows_t* in, const void* W, const float* bias, int n1, int n2, int n3, int chunks0, int mode,
-                  int kseg, float* Y, int ldy, float* G, float* a, long long rows, void* stream);
+/* Two or three fused shared-MLP layers with the activations kept in shared / tensor memory: the reference's conv
+ * stacks `convs`, `convs_1`, `convs_2` (layers.py:118-121,249-260,420-423), the descriptor head mlp1+mlp2
+ * (layers.py:193-198,207) and the per-keypoint heads mlp1/mlp2/mlp3 (layers.py:124-130,161-163,425-431,451-452) where
+ * the widths are <= 256, plus the reduction that consumes them: mode 0 = store Y rows; 1 = G[g,:] = max over the kseg
+ * rows of each group (+ Y rows if Y != NULL, layers.py:202,208); 2 = a = softmax_k(max_c Y), G[g,:] = sum_k a*Y, Y
+ * (optional) = the rows Y*a (layers.py:150-159,329-332,384-390,446-450).  Hidden activations ReLU, last = `act`.
+ * W = K=16 weight pieces of the layers in execution order (pcd_reg_hregnet_b200/engine_tc.pack_chain), bias = b1|b2|b3,
+ * n1..n3 = issued widths (multiples of 16; the last = cout padded), chunks0 = 8-wide K chunks of the virtual input. */
+int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl, int n1, int n2, int n3, int cout, int act,
+                 int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, void* stream);
 
 /* Levels 1 and 2 of HierFeatureExtraction (models/HRegNet/models.py:27-28,33-34: detector_l + desc_extractor_l;
  * level 1: in_channels 0, k = 64, widths 32/32/64, mlp 192->32->64; level 2: in_channels 64, k = 32, widths

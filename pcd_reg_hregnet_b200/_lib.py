@@ -40,8 +40,8 @@ SIGNATURES = {
     "hrn_layer_fp32": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp],
     "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp],
     "hrn_level_fused": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
-    "hrn_chain3_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_ll,
-                      c_vp],
+    "hrn_chain_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
+                     c_int, c_vp, c_vp, c_ll, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
     "hrn_group_weighted_sum": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "hrn_group_max": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_vp],

@@ -38,7 +38,10 @@ struct ChainArgs {
     float* a;                // rows: attention weights (EPI_ATTN)
     long long rows;
     int ldy;
-    int n[3];                // layer widths (multiples of 16, <= 256)
+    int n[3];                // layer widths as issued (multiples of 16, <= 256); n[nl-1] = padded last width
+    int nl;                  // number of layers (2 or 3)
+    int cout;                // real output columns of the last layer (<= n[nl-1])
+    int act;                 // activation of the last layer (HRN_ACT_*); hidden layers are ReLU
     int chunks0;             // 8-wide K chunks of the virtual input (segments padded to 8, total padded to even)
     int mode;
     int kseg;                // rows per group (8, 16 or 32)
@@ -105,7 +108,10 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_acc = smem_u32(&s_bar[2 * RING]);
-    const int n1 = A.n[0], n2 = A.n[1], n3 = A.n[2];
+    const int nl = A.nl;
+    const int n1 = A.n[0];
+    const int n3 = A.n[nl - 1];                       // issued width of the last layer
+    const int cout = A.cout;
 
     if (tid == 0) {
         for (int i = 0; i < 2 * RING + 1; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
@@ -115,7 +121,8 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < n1 + n2 + n3; i += CTM) sBias[i] = __ldg(A.bias + i);
+    const int nbias = A.n[0] + (nl == 3 ? A.n[1] : 0) + cout;
+    for (int i = tid; i < nbias; i += CTM) sBias[i] = __ldg(A.bias + i);
 
     // ---- row bookkeeping -----------------------------------------------------------------------------------
     const long long r = (long long)blockIdx.x * CTM + tid;
@@ -150,10 +157,10 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
     uint32_t g_next = 0;        // next piece to request
     uint32_t g_use = 0;         // next piece to consume
     size_t w_off = 0;           // byte offset of piece g_next in A.W
-    const uint32_t pieces[3] = {(uint32_t)(A.chunks0 / 2), (uint32_t)(n1 / 16), (uint32_t)(n2 / 16)};
+    const uint32_t pieces[3] = {(uint32_t)(A.chunks0 / 2), (uint32_t)(A.n[0] / 16), nl == 3 ? (uint32_t)(A.n[1] / 16) : 0u};
     const uint32_t g_total = pieces[0] + pieces[1] + pieces[2];
     auto piece_bytes = [&](uint32_t g) -> uint32_t {
-        const int N = g < pieces[0] ? n1 : (g < pieces[0] + pieces[1] ? n2 : n3);
+        const int N = g < pieces[0] ? A.n[0] : (g < pieces[0] + pieces[1] ? A.n[1] : A.n[2]);
         return (uint32_t)N * 64u;
     };
     auto prefetch = [&]() {     // keep up to RING-1 pieces in flight beyond the one being consumed
@@ -240,24 +247,27 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
         }
     };
     epi_to_operand(n1, sBias);
-    mma_pieces(n1 / 16, 0, n2, false);
-    epi_to_operand(n2, sBias + n1);
-    mma_pieces(n2 / 16, 0, n3, false);
+    mma_pieces(n1 / 16, 0, A.n[1], false);
+    if (nl == 3) {
+        epi_to_operand(A.n[1], sBias + n1);
+        mma_pieces(A.n[1] / 16, 0, n3, false);
+    }
 
     // ---- final epilogue -----------------------------------------------------------------------------------------
-    const float* b3 = sBias + n1 + n2;
+    const float* b3 = sBias + n1 + (nl == 3 ? A.n[1] : 0);
+    const int act = A.act;
     const int pos = lane % KSEG;                       // position inside the group
     const long long grp = r / KSEG;
     constexpr int PER = 32 / KSEG;                     // reduced columns per lane and 32-column chunk
     float a_w = 1.f;
     if (A.mode == EPI_ATTN) {
-        float x1 = 0.f;
-        for (int c0 = 0; c0 < n3; c0 += 32) {
+        float x1 = -CUDART_INF_F;
+        for (int c0 = 0; c0 < cout; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + c0, v);
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-                if (c0 + e < n3) x1 = fmaxf(x1, __uint_as_float(v[e]) + b3[c0 + e]);
+                if (c0 + e < cout) x1 = fmaxf(x1, fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f));   // EPI_ATTN: ReLU only
         }
         float gm = x1;
 #pragma unroll
@@ -269,26 +279,44 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
         a_w = ex / sm;
         if (rvalid && A.a) A.a[r] = a_w;
     }
-    for (int c0 = 0; c0 < n3; c0 += 32) {
+    const bool vec_ok = A.Y && ((cout & 3) == 0);
+    for (int c0 = 0; c0 < cout; c0 += 32) {
         uint32_t v[32];
         float f[32];
         tmem_ld32(tmem + lane_base + c0, v);
+        if (act == HRN_ACT_RELU) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) f[e] = (c0 + e < n3) ? fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f) * a_w : 0.f;
+            for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f) * a_w : 0.f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? act_fn(__uint_as_float(v[e]) + b3[c0 + e], act) : 0.f;
+        }
         if (rvalid && A.Y) {
             float* yr = A.Y + r * A.ldy + c0;
+            if (vec_ok) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                if (c0 + e < n3) *reinterpret_cast<float4*>(yr + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+                for (int e = 0; e < 32; e += 4)
+                    if (c0 + e < cout) *reinterpret_cast<float4*>(yr + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) if (c0 + e < cout) yr[e] = f[e];
+            }
         }
         if (A.mode != EPI_STORE && A.G) {
-            if (A.mode == EPI_GROUPMAX) seg_transpose_reduce<KSEG, true>(f, lane);
-            else seg_transpose_reduce<KSEG, false>(f, lane);
+            if (A.mode == EPI_GROUPMAX) {
+                if (act != HRN_ACT_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (c0 + e >= cout) f[e] = -CUDART_INF_F;
+                }
+                seg_transpose_reduce<KSEG, true>(f, lane);
+            } else {
+                seg_transpose_reduce<KSEG, false>(f, lane);
+            }
             if (rvalid) {
 #pragma unroll
                 for (int i = 0; i < PER; ++i) {
                     const int c = c0 + pos * PER + i;
-                    if (c < n3) A.G[grp * n3 + c] = f[i];
+                    if (c < cout) A.G[grp * cout + c] = f[i];
                 }
             }
         }
@@ -301,13 +329,18 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
 
 }  // namespace
 
-// Three fused layers on a virtual rows matrix.  W: packed K=16 pieces of the three layers in execution order
-// (engine_tc.pack_chain), bias = b1|b2|b3, widths n1,n2,n3 multiples of 16 and <= 256.  mode / outputs as in the file
-// header; `kseg` = rows per group (8, 16 or 32; rows must be a multiple of 128).
-HRN_API int hrn_chain3_tc(const hrn_rows_t* in, const void* W, const float* bias, int n1, int n2, int n3, int chunks0,
-                          int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, void* stream) {
-    if (!in || !W || !bias || rows < 0 || in->n_seg < 1 || in->n_seg > 4) return HRN_ERR_BAD_ARG;
-    if (n1 % 16 || n2 % 16 || n3 % 16 || n1 > 256 || n2 > 256 || n3 > 256 || n1 < 16 || n2 < 16 || n3 < 16) return HRN_ERR_UNSUPPORTED;
+// Two or three fused layers on a virtual rows matrix.  W: packed K=16 pieces of the layers in execution order
+// (engine_tc.pack_chain), bias = b1|b2|b3 (last: `cout` entries), issued widths n1,n2,(n3) multiples of 16 and <= 256
+// (the last one = cout padded to 16), hidden activations ReLU, last activation `act`.  mode / outputs as in the file
+// header; `kseg` = rows per group (8, 16 or 32; ignored for mode 0); rows must be a multiple of 128.
+HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl, int n1, int n2, int n3, int cout,
+                         int act, int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows,
+                         void* stream) {
+    if (!in || !W || !bias || rows < 0 || in->n_seg < 1 || in->n_seg > 4 || (nl != 2 && nl != 3)) return HRN_ERR_BAD_ARG;
+    const int nn[3] = {n1, n2, nl == 3 ? n3 : 16};
+    for (int l = 0; l < 3; ++l) if (nn[l] % 16 || nn[l] > 256 || nn[l] < 16) return HRN_ERR_UNSUPPORTED;
+    const int nlast = nl == 3 ? n3 : n2;
+    if (cout <= 0 || cout > nlast) return HRN_ERR_BAD_ARG;
     if (kseg != 8 && kseg != 16 && kseg != 32) return HRN_ERR_UNSUPPORTED;
     if (rows % CTM != 0 || (chunks0 & 1)) return HRN_ERR_UNSUPPORTED;
     int chunks = 0;
@@ -321,11 +354,13 @@ HRN_API int hrn_chain3_tc(const hrn_rows_t* in, const void* W, const float* bias
     }
     if (chunks0 != ((chunks + 1) & ~1)) return HRN_ERR_BAD_ARG;
     if (mode == EPI_STORE && !Y) return HRN_ERR_BAD_ARG;
-    if (Y && ((ldy & 3) || ((uintptr_t)Y & 15))) return HRN_ERR_UNSUPPORTED;
+    if (mode == EPI_ATTN && act != HRN_ACT_RELU) return HRN_ERR_UNSUPPORTED;
+    if (Y && (cout & 3) == 0 && ((ldy & 3) || ((uintptr_t)Y & 15))) return HRN_ERR_UNSUPPORTED;
     if (rows == 0) return HRN_OK;
     ChainArgs A;
     A.in = *in; A.W = (const uint8_t*)W; A.bias = bias; A.Y = Y; A.G = G; A.a = a; A.rows = rows; A.ldy = ldy;
-    A.n[0] = n1; A.n[1] = n2; A.n[2] = n3; A.chunks0 = chunks0; A.mode = mode; A.kseg = kseg;
+    A.n[0] = n1; A.n[1] = n2; A.n[2] = nl == 3 ? n3 : 16; A.nl = nl; A.cout = cout; A.act = act;
+    A.chunks0 = chunks0; A.mode = mode; A.kseg = kseg;
     static bool attr_set = false;
     if (!attr_set) {
         HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));

@@ -66,10 +66,11 @@ __device__ __forceinline__ void load_chunk(const RowSrc& rs, int cg, float4& v0,
 template <bool FAST>
 __global__ void __launch_bounds__(TM)
 layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
-                float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NP, int n_stage, int tmem_cols) {
+                float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NP, int n_stage, int tmem_cols, int NW) {
     // NPfull = padded Cout of the packed weights; NP = columns handled by this CTA (slice blockIdx.y of NPfull)
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar[5];     // [0,1] W landed, [2,3] stage consumed by MMA, [4] accumulator ready
+    // [0,1] A stage drained by its MMAs, [2] accumulator ready, [3..3+NW) W slot landed, [3+NW..3+2NW) W slot drained
+    __shared__ __align__(8) uint64_t s_bar[3 + 2 * 4];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -89,16 +90,17 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         }
     };
     uint8_t* sA[2] = {smem, smem + A_STAGE_BYTES};
-    uint8_t* sW[2] = {smem + 2 * A_STAGE_BYTES, smem + 2 * A_STAGE_BYTES + w_stage_bytes};
-    const uint32_t bar_w[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
-    const uint32_t bar_m[2] = {smem_u32(&s_bar[2]), smem_u32(&s_bar[3])};
-    const uint32_t bar_done = smem_u32(&s_bar[4]);
+    uint8_t* sWbase = smem + 2 * A_STAGE_BYTES;          // NW weight slots of w_stage_bytes each
+    const uint32_t bar_m[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
+    const uint32_t bar_done = smem_u32(&s_bar[2]);
+    const uint32_t bar_w0 = smem_u32(&s_bar[3]), bar_f0 = smem_u32(&s_bar[3 + NW]);
 
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+        for (int i = 0; i < 3 + 2 * 4; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // first weight stage can fly while TMEM is allocated and the rows are resolved
-        fetch_w(0, smem_u32(sW[0]), bar_w[0]);
+        for (int j = 0; j < NW - 1 && j < n_stage; ++j)        // NW-1 weight stages of look-ahead
+            fetch_w(j, smem_u32(sWbase) + j * w_stage_bytes, bar_w0 + 8 * j);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
@@ -164,10 +166,11 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
-            mbar_wait(bar_w[s], (i >> 1) & 1);
+            const int ws = i % NW;
+            mbar_wait(bar_w0 + 8 * ws, (i / NW) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_base = smem_u32(sA[s]);
-            const uint32_t w_base = smem_u32(sW[s]);
+            const uint32_t w_base = smem_u32(sWbase) + ws * w_stage_bytes;
             const uint32_t a_lbo = TM * 16, w_lbo = (uint32_t)NP * 16;
             const uint32_t a_lo_off = (KC / 8) * TM * 16, w_lo_off = (KC / 8) * (uint32_t)NP * 16;
 #pragma unroll
@@ -184,11 +187,15 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                 }
             }
             umma_commit(bar_m[s]);
+            umma_commit(bar_f0 + 8 * ws);
             if (i == n_stage - 1) umma_commit(bar_done);
             // weights of the next stage: its buffer is free once the MMAs of stage i-1 have drained
-            if (i + 1 < n_stage) {
-                if (i >= 1) mbar_wait(bar_m[s ^ 1], ((i - 1) >> 1) & 1);
-                fetch_w(i + 1, smem_u32(sW[s ^ 1]), bar_w[s ^ 1]);
+            // weights of stage i+NW-1 go into the slot of stage i-1, free once that stage's MMAs have drained
+            const int nx = i + NW - 1;
+            if (nx < n_stage) {
+                const int fs = nx % NW;
+                if (i >= 1) mbar_wait(bar_f0 + 8 * fs, ((i - 1) / NW) & 1);
+                fetch_w(nx, smem_u32(sWbase) + fs * w_stage_bytes, bar_w0 + 8 * fs);
             }
         }
     }
@@ -250,11 +257,13 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     const int n_split = NP / NS;
     int tmem_cols = 32;
     while (tmem_cols < NS) tmem_cols <<= 1;
-    const size_t smem = 2 * (size_t)A_STAGE_BYTES + 2 * (size_t)NS * 128;
+    int NW = (int)((226 * 1024 - 2 * A_STAGE_BYTES) / ((size_t)NS * 128));   // weight ring depth
+    NW = 2;   // measured: a 3- or 4-slot weight ring costs more in co-resident CTAs than it hides in copy latency
+    const size_t smem = 2 * (size_t)A_STAGE_BYTES + (size_t)NW * NS * 128;
     static bool attr_set = false;
     if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * 128));
-        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * 128));
+        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 3 * 512 * 128));
+        HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 3 * 512 * 128));
         attr_set = true;
     }
     bool fast = true;   // 16-byte vector path: every segment 4-float aligned
@@ -265,10 +274,10 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     dim3 grid(tiles, n_split);
     if (fast)
         layer_tc_kernel<true><<<grid, TM, smem, (cudaStream_t)stream>>>(
-            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols);
+            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols, NW);
     else
         layer_tc_kernel<false><<<grid, TM, smem, (cudaStream_t)stream>>>(
-            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols);
+            *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols, NW);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }

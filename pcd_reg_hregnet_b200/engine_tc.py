@@ -147,12 +147,17 @@ def _pieces(W, K_pad):
     return t.view(-1).view(torch.uint8)
 
 
-def chain_supported(view, layers):
-    if len(layers) != 3 or view.rows % 128 != 0:
-        return False
+def chain_supported(view, layers, last_relu_only=True):
+    """2 or 3 folded layers, widths <= 256 and multiples of 16 (the last one may be narrower: it is zero-padded),
+    hidden activations ReLU, rows a multiple of 128, every segment 16-byte aligned."""
     from ._lib import ACT_RELU
-    for W, b, act in layers:
-        if act != ACT_RELU or W.shape[0] % 16 or W.shape[0] > 256:
+    if len(layers) not in (2, 3) or view.rows % 128 != 0:
+        return False
+    for li, (W, b, act) in enumerate(layers):
+        last = li == len(layers) - 1
+        if W.shape[0] > 256 or (not last and (W.shape[0] % 16 or act != ACT_RELU)):
+            return False
+        if last and last_relu_only and act != ACT_RELU:
             return False
     for mat, mode, ch, col0, scale in view.segs:
         if ch % 4 or col0 % 4 or mat.stride(0) % 4 or mat.data_ptr() % 16:
@@ -165,7 +170,7 @@ def pack_chain(layers, seg_channels):
     hit = _chain_cache.get(key)
     if hit is not None:
         return hit
-    (W1, b1, _), (W2, b2, _), (W3, b3, _) = layers
+    W1 = layers[0][0]
     chunks = sum((c + 7) // 8 for c in seg_channels)
     chunks0 = (chunks + 1) // 2 * 2
     W1p = torch.zeros(W1.shape[0], chunks0 * 8, dtype=torch.float32, device=W1.device)
@@ -174,21 +179,35 @@ def pack_chain(layers, seg_channels):
         W1p[:, dst:dst + c] = W1[:, src:src + c]
         src += c
         dst += (c + 7) // 8 * 8
-    Wpack = torch.cat([_pieces(W1p, chunks0 * 8), _pieces(W2, W2.shape[1]), _pieces(W3, W3.shape[1])]).contiguous()
-    bias = torch.cat([b1, b2, b3]).contiguous()
-    out = (Wpack, bias, chunks0, [W1, W2, W3])
+    mats = [W1p] + [W for W, _, _ in layers[1:]]
+    cout = mats[-1].shape[0]
+    np_last = max(16, (cout + 15) // 16 * 16)
+    if np_last != cout:                                   # zero rows: padded output columns are never stored
+        pad = torch.zeros(np_last, mats[-1].shape[1], dtype=torch.float32, device=W1.device)
+        pad[:cout] = mats[-1]
+        mats[-1] = pad
+    Wpack = torch.cat([_pieces(m, m.shape[1]) for m in mats]).contiguous()
+    bias = torch.cat([b for _, b, _ in layers]).contiguous()
+    widths = [m.shape[0] for m in mats]
+    out = (Wpack, bias, chunks0, widths, cout, [W for W, _, _ in layers])
     _chain_cache[key] = out
     return out
 
 
-def chain3(view, layers, mode, kseg, want_rows=True, want_groups=True):
-    """Runs the three folded layers on the virtual rows.  Returns (Y rows | None, G groups | None, a rows | None)."""
-    Wpack, bias, chunks0, _ = pack_chain(layers, [s[2] for s in view.segs])
-    n1, n2, n3 = (W.shape[0] for W, _, _ in layers)
+def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act=None):
+    """Runs 2-3 folded layers on the virtual rows.  Returns (Y rows | None, G groups | None, a rows | None)."""
+    Wpack, bias, chunks0, widths, cout, _ = pack_chain(layers, [s[2] for s in view.segs])
+    nl = len(layers)
+    act = layers[-1][2] if last_act is None else last_act
+    n = widths + [16] * (3 - nl)
     dev = bias.device
-    Y = torch.empty(view.rows, n3, dtype=torch.float32, device=dev) if want_rows else None
-    G = torch.empty(view.rows // kseg, n3, dtype=torch.float32, device=dev) if (want_groups and mode != EPI_STORE) else None
+    Y = torch.empty(view.rows, cout, dtype=torch.float32, device=dev) if want_rows else None
+    G = torch.empty(view.rows // kseg, cout, dtype=torch.float32, device=dev) if (want_groups and mode != EPI_STORE) else None
     a = torch.empty(view.rows, dtype=torch.float32, device=dev) if mode == EPI_ATTN else None
-    engine.call("hrn_chain3_tc", ctypes.byref(view.c), engine.ptr(Wpack), engine.ptr(bias), n1, n2, n3, chunks0, mode, kseg,
-                engine.ptr(Y), n3, engine.ptr(G), engine.ptr(a), view.rows, engine.stream())
+    engine.call("hrn_chain_tc", ctypes.byref(view.c), engine.ptr(Wpack), engine.ptr(bias), nl, n[0], n[1], n[2], cout, act,
+                chunks0, mode, kseg, engine.ptr(Y), cout, engine.ptr(G), engine.ptr(a), view.rows, engine.stream())
     return Y, G, a
+
+
+def chain3(view, layers, mode, kseg, want_rows=True, want_groups=True):
+    return chain(view, layers, mode, kseg, want_rows, want_groups)

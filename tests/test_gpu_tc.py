@@ -114,3 +114,19 @@ def test_chain3_kernel(kseg, mode):
         assert float((a.double().view(-1, kseg) - a_ref).abs().max()) < 1e-4
         assert float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale < 1e-4
         assert float((Y.double().view(-1, kseg, 256) - a_ref[:, :, None] * Xg).abs().max()) / scale < 1e-4
+
+
+def test_chain_two_layers_narrow_output_and_activation():
+    """Generalised chain: 2 layers, last width 1 (zero-padded to 16), sigmoid; multi-pass K (> 256 input channels)."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    g = torch.Generator().manual_seed(3)
+    rows = 1024
+    X = torch.randn(rows, 320, generator=g).to(DEV)
+    W1 = (torch.randn(128, 320, generator=g) / 18).to(DEV); b1 = torch.randn(128, generator=g).to(DEV) * 0.1
+    W2 = (torch.randn(1, 128, generator=g) / 11).to(DEV); b2 = torch.randn(1, generator=g).to(DEV)
+    layers = [(W1, b1, ACT_RELU), (W2, b2, ACT_SIGMOID)]
+    v = RowsView(rows).add(X)
+    assert engine_tc.chain_supported(v, layers, last_relu_only=False)
+    Y, _, _ = engine_tc.chain(v, layers, engine_tc.EPI_STORE)
+    want = torch.sigmoid(torch.relu(X.double() @ W1.double().t() + b1.double()) @ W2.double().t() + b2.double())
+    assert Y.shape == (rows, 1) and float((Y.double() - want).abs().max()) < 1e-5
