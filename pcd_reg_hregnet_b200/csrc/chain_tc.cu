@@ -22,10 +22,8 @@ namespace {
 
 constexpr int CTM = 128;                 // rows per CTA
 constexpr int OPC_MAX = 32;              // operand buffer: 32 chunks of 8 channels = 256 wide
-constexpr int OP_PLANE = OPC_MAX * CTM * 16;
 constexpr int RING = 4;
-constexpr int SLOT_BYTES = 256 * 64;     // one K=16 piece of a 256-wide layer: 2 planes x 2 chunks x N x 16 B
-constexpr int CH_SMEM = 2 * OP_PLANE + RING * SLOT_BYTES + 3 * 256 * 4 + 64;
+constexpr int CH_SMEM_MAX = 2 * OPC_MAX * CTM * 16 + RING * 256 * 64 + 3 * 256 * 4 + 64;
 
 enum { EPI_STORE = 0, EPI_GROUPMAX = 1, EPI_ATTN = 2 };
 
@@ -42,6 +40,9 @@ struct ChainArgs {
     int nl;                  // number of layers (2 or 3)
     int cout;                // real output columns of the last layer (<= n[nl-1])
     int act;                 // activation of the last layer (HRN_ACT_*); hidden layers are ReLU
+    int opc;                 // chunks of the operand buffer = max(first pass, hidden widths / 8)
+    int slot_bytes;          // weight ring slot = widest layer x 64 B (one K=16 piece)
+    int tmem_cols;           // power of two >= widest layer
     int chunks0;             // 8-wide K chunks of the virtual input (segments padded to 8, total padded to even)
     int mode;
     int kseg;                // rows per group (8, 16 or 32)
@@ -95,11 +96,13 @@ __device__ __forceinline__ void seg_transpose_reduce(float (&v)[32], int lane) {
 }
 
 template <int KSEG>
-__global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
+__global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2 * RING + 1];    // [0..3] piece landed, [4..7] slot drained, [8] accumulator
     __shared__ uint32_t s_tmem;
 
+    const uint32_t OP_PLANE = (uint32_t)A.opc * CTM * 16;
+    const uint32_t SLOT_BYTES = (uint32_t)A.slot_bytes;
     uint8_t* sOp = smem;
     uint8_t* sRing = smem + 2 * OP_PLANE;
     float* sBias = reinterpret_cast<float*>(sRing + RING * SLOT_BYTES);
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(A.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int nbias = A.n[0] + (nl == 3 ? A.n[1] : 0) + cout;
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(CTM, 1) chain3_kernel(const ChainArgs A) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(A.tmem_cols) : "memory");
 }
 
 }  // namespace
@@ -361,11 +364,21 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
     A.in = *in; A.W = (const uint8_t*)W; A.bias = bias; A.Y = Y; A.G = G; A.a = a; A.rows = rows; A.ldy = ldy;
     A.n[0] = n1; A.n[1] = n2; A.n[2] = nl == 3 ? n3 : 16; A.nl = nl; A.cout = cout; A.act = act;
     A.chunks0 = chunks0; A.mode = mode; A.kseg = kseg;
+    int maxn = n1 > n2 ? n1 : n2;
+    if (nl == 3 && n3 > maxn) maxn = n3;
+    int opc = chunks0 < OPC_MAX ? chunks0 : OPC_MAX;
+    if (n1 / 8 > opc) opc = n1 / 8;
+    if (nl == 3 && n2 / 8 > opc) opc = n2 / 8;
+    A.opc = opc;
+    A.slot_bytes = maxn * 64;
+    A.tmem_cols = 32;
+    while (A.tmem_cols < maxn) A.tmem_cols <<= 1;
+    const int CH_SMEM = 2 * opc * CTM * 16 + RING * A.slot_bytes + 3 * 256 * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
+        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
+        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
         attr_set = true;
     }
     const int grid = (int)(rows / CTM);

@@ -256,11 +256,25 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
             unsigned key = 0xffffffffu;
             float cx = 0.f, cy = 0.f, cz = 0.f;
             if (om == g) {
+                if ((stride & (int)tmask) == 0) {
+                    // stride is a multiple of Tref: (k mod Tref) is the same for all of this thread's points, so the
+                    // reference key grows with p -> the winner is simply the first p that holds the maximum
+                    int pf = 0;
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const int k = k0 + p * stride;
-                    const unsigned kk = key_of(k);
-                    if (k < N && pt[p] == m && kk < key) { key = kk; cx = px[p]; cy = py[p]; cz = pz[p]; }
+                    for (int p = P - 1; p >= 0; --p)
+                        if (pt[p] == m && k0 + p * stride < N) pf = p;
+                    cx = px[0]; cy = py[0]; cz = pz[0];
+#pragma unroll
+                    for (int p = 1; p < P; ++p)
+                        if (pf == p) { cx = px[p]; cy = py[p]; cz = pz[p]; }
+                    key = key_of(k0 + pf * stride);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const int k = k0 + p * stride;
+                        const unsigned kk = key_of(k);
+                        if (k < N && pt[p] == m && kk < key) { key = kk; cx = px[p]; cy = py[p]; cz = pz[p]; }
+                    }
                 }
             }
             const unsigned wkey = __reduce_min_sync(0xffffffffu, key);
@@ -271,17 +285,15 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
             s_slot[warp].key = 0xffffffffu;
         }
         __syncthreads();
-        // ---- C: warp 0 = CTA winner, cluster exchange ------------------------------------------------------------
+        // ---- C: warp 0 = CTA winner; cluster exchange through the mailboxes ------------------------------------
+        const int par = j & 1;
+        const uint32_t mb = fps_smem_u32(&s_mbar[par]);
         if (warp == 0) {
             const unsigned k2 = lane < NWARP ? s_slot[lane].key : 0xffffffffu;
             const unsigned kmin = __reduce_min_sync(0xffffffffu, k2);
             const int src = __ffs(__ballot_sync(0xffffffffu, k2 == kmin)) - 1;
             const float sx = s_slot[src].x, sy = s_slot[src].y, sz = s_slot[src].z;
-            unsigned bkey = kmin;
-            float bx = sx, by = sy, bz = sz;
             if (CS > 1) {
-                const int par = j & 1;
-                const uint32_t mb = fps_smem_u32(&s_mbar[par]);
                 if (lane == 0)
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(CS * 32) : "memory");
                 if (lane < CS) {
@@ -293,28 +305,34 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
                     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                                  ::"r"(rbox + 16), "r"(__float_as_uint(sz)), "r"(0u), "r"(0u), "r"(0u), "r"(rbar) : "memory");
                 }
-                unsigned done;
-                const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;   // u-th use of mbarrier j&1, u = (j-1)/2
-                do {
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                                 : "=r"(done) : "r"(mb), "r"(parity) : "memory");
-                } while (!done);
-                unsigned bval = 0u;
-                bkey = 0xffffffffu;
+            } else if (lane == 0) {
+                s_best.key = kmin; s_best.x = sx; s_best.y = sy; s_best.z = sz;
+            }
+        }
+        unsigned bkey;
+        if (CS > 1) {
+            // every thread sleeps on the CTA's own mailbox barrier until the CS packets of iteration j have landed
+            // (hardware wait, no polling traffic), then takes the best of them -- no third CTA barrier
+            unsigned done;
+            const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;   // u-th use of mbarrier j&1, u = (j-1)/2
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+            } while (!done);
+            unsigned bval = 0u;
+            bkey = 0xffffffffu;
 #pragma unroll 1
-                for (int c = 0; c < CS; ++c) {
-                    const FpsMail mm = s_mail[par][c];
-                    if (mm.ordval > bval || (mm.ordval == bval && mm.key < bkey)) {
-                        bval = mm.ordval; bkey = mm.key; bx = mm.x; by = mm.y; bz = mm.z;
-                    }
+            for (int c = 0; c < CS; ++c) {
+                const FpsMail mm = s_mail[par][c];
+                if (mm.ordval > bval || (mm.ordval == bval && mm.key < bkey)) {
+                    bval = mm.ordval; bkey = mm.key; x1 = mm.x; y1 = mm.y; z1 = mm.z;
                 }
             }
-            if (lane == 0) { s_best.key = bkey; s_best.x = bx; s_best.y = by; s_best.z = bz; }
+        } else {
+            __syncthreads();
+            bkey = s_best.key; x1 = s_best.x; y1 = s_best.y; z1 = s_best.z;
         }
-        __syncthreads();
-        x1 = s_best.x; y1 = s_best.y; z1 = s_best.z;
         if (tid == 0 && rank == 0) {
-            const unsigned bkey = s_best.key;
             const unsigned r = bkey >> 12;
             const int lo = (log2T > 0) ? (int)(__brev(r) >> (32 - log2T)) : 0;
             idx_out[j] = lo + (int)((bkey & 0xfffu) << log2T);

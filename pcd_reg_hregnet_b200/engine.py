@@ -17,6 +17,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADC
 
 _PRECISION = "tc"       # "tc": tcgen05 kernels (bf16x3, fp32-class accuracy); "fp32": exact CUDA-core layers
 _FUSED_CHAINS = True     # tc mode: three-layer conv stacks (<= 256 wide) + their group reductions in one kernel
+_FUSED_HEADS = True      # tc mode: per-keypoint heads (mlp1/mlp2/mlp3, width <= 256) as one chain launch
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
 
 
@@ -89,6 +90,10 @@ def _launch_layer_fp32(view, W, b, act, out):
 
 def stack(view: RowsView, layers, last_act=None):
     """Chain of folded layers [(W, b, act), ...] starting from a virtual rows view."""
+    if _PRECISION == "tc" and _FUSED_CHAINS and _FUSED_HEADS and len(layers) == 3 and len(view.segs) == 1:
+        from . import engine_tc                      # per-keypoint heads mlp1 -> mlp2 -> mlp3 in one launch
+        if engine_tc.chain_supported(view, layers, last_relu_only=False):
+            return engine_tc.chain(view, layers, engine_tc.EPI_STORE, last_act=last_act)[0]
     x = None
     for li, (W, b, act) in enumerate(layers):
         if li == len(layers) - 1 and last_act is not None:
