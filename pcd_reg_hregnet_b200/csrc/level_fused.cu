@@ -59,6 +59,13 @@ struct LevelCfg {
     static constexpr int T_USED = T_ACCX + cmax(CO, CD);
     static constexpr int T_COLS = T_USED <= 32 ? 32 : T_USED <= 64 ? 64 : T_USED <= 128 ? 128 : T_USED <= 256 ? 256 : 512;
     static constexpr int WPG = KNBR / 32;                           // warps per keypoint group (1 or 2)
+    // RESIDENT: NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns,
+    // all sharing ONE resident copy of the weights (3 tiles in flight per SM instead of 2 CTAs x 1)
+    static constexpr int NG = RESIDENT ? 3 : 1;
+    static constexpr int GRP_SMEM = G_BYTES + OP_BYTES + 2 * 4 * CW * 4;
+    static constexpr int SMEM_NG = W_SMEM + B_COUNT * 4 + NG * GRP_SMEM + 256;
+    static constexpr int T_COLS_NG = NG * T_USED <= 256 ? 256 : 512;
+    static_assert(NG * T_USED <= 512, "TMEM (groups)");
     static_assert(KNBR == 32 || KNBR == 64, "group reductions are written for 32 or 64 neighbours");
     static_assert(T_USED <= 512, "TMEM");
     static_assert(CIN % 8 == 0, "feature chunks must be 8-aligned");
@@ -103,7 +110,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(TMR, Cfg::RESIDENT ? 2 : 1)
+__global__ void __launch_bounds__(TMR * Cfg::NG, 1)
 level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, const float* __restrict__ feat,
                    const int32_t* __restrict__ idx, const uint8_t* __restrict__ Wpack, const float* __restrict__ biases,
                    float* __restrict__ out_xyz, float* __restrict__ out_af, float* __restrict__ out_desc, int M, int N,
@@ -111,25 +118,34 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     constexpr int KNBR = Cfg::KNBR, CIN = Cfg::CIN, C1 = Cfg::C1, C2 = Cfg::C2, CO = Cfg::CO, CMID = Cfg::CMID,
                   CD = Cfg::CD, WPG = Cfg::WPG, CW = Cfg::CW;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar[3];                            // [0] MMA done, [1,2] weight slot landed
+    constexpr int NG = Cfg::NG;
+    __shared__ __align__(8) uint64_t s_bar[2 + NG];                       // [0,1] weight slot landed, [2+g] MMA done (group g)
     __shared__ uint32_t s_tmem;
-    __shared__ float s_red[4][8];
+    __shared__ float s_red_all[NG][4][8];
 
+    const int cta_tid = threadIdx.x;
+    const int grp_id = cta_tid / TMR;                                     // independent 128-thread group
+    const int tid = cta_tid % TMR, warp = tid >> 5, lane = tid & 31;      // group-local ids (warp = TMEM lane quarter)
+    float (*s_red)[8] = s_red_all[grp_id];
     uint8_t* sW = smem;
     float* sB = reinterpret_cast<float*>(smem + Cfg::W_SMEM);
-    uint8_t* sG = smem + Cfg::W_SMEM + Cfg::B_COUNT * 4;
+    uint8_t* sG = smem + Cfg::W_SMEM + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
     uint8_t* sOp = sG + Cfg::G_BYTES;
     float* sCol = reinterpret_cast<float*>(sOp + Cfg::OP_BYTES);          // [4][CW] per-warp column partials
     float* sCol2 = sCol + 4 * CW;
+    auto gsync = [&]() {                                                  // barrier of this group only
+        if (NG == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(grp_id + 1), "n"(TMR) : "memory");
+    };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gw0 = (warp / WPG) * WPG;                                   // first warp of this row's keypoint group
     const bool leader = (warp == gw0);
-    const uint32_t bar = smem_u32(&s_bar[0]);
-    const uint32_t bar_w[2] = {smem_u32(&s_bar[1]), smem_u32(&s_bar[2])};
+    const uint32_t bar = smem_u32(&s_bar[2 + grp_id]);
+    const uint32_t bar_w[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
     uint32_t phase = 0;
     uint32_t lcount = 0;                                                  // layers executed by this CTA (streaming)
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int vgrid = (int)gridDim.x * NG, vblock = (int)blockIdx.x * NG + grp_id;   // groups act as virtual CTAs
+    const int my_tiles = vblock < n_tiles ? (n_tiles - vblock + vgrid - 1) / vgrid : 0;
     const uint32_t total_layers = (uint32_t)my_tiles * 10u;
     const uint32_t wbase = smem_u32(sW);
 
@@ -143,10 +159,8 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     };
 
     // ---- one-time setup ---------------------------------------------------------------------------------------
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar_w[0], 1);
-        mbar_init(bar_w[1], 1);
+    if (cta_tid == 0) {
+        for (int i = 0; i < 2 + NG; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (!Cfg::RESIDENT) {
             if (total_layers > 0) stream_weights(0);
@@ -154,9 +168,9 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         }
     }
     if (Cfg::RESIDENT)
-        for (int i = tid; i < Cfg::W_BYTES / 16; i += TMR)
+        for (int i = cta_tid; i < Cfg::W_BYTES / 16; i += TMR * NG)
             reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
-    for (int i = tid; i < Cfg::B_COUNT; i += TMR) sB[i] = __ldg(biases + i);
+    for (int i = cta_tid; i < Cfg::B_COUNT; i += TMR * NG) sB[i] = __ldg(biases + i);
     {   // K padding chunks of G stay zero forever
         uint4* g_hi = reinterpret_cast<uint4*>(sG);
         uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
@@ -165,14 +179,15 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             g_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
         }
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS) : "memory");
+    if (cta_tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS_NG) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem_all = s_tmem;
+    const uint32_t tmem = tmem_all + grp_id * Cfg::T_USED;                // this group's accumulator columns
     const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
     const uint32_t aG_hi = smem_u32(sG), aG_lo = aG_hi + (Cfg::KG / 8) * TMR * 16;
     const uint32_t aOp_hi = smem_u32(sOp), aOp_lo = aOp_hi + Cfg::OPC * TMR * 16;
@@ -186,7 +201,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         const int K = Cfg::lk(li), Nn = Cfg::ln(li);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        gsync();
         if (tid == 0) {
             uint32_t w_addr = wbase + Cfg::woff(li);
             if (!Cfg::RESIDENT) {
@@ -224,7 +239,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         return v;
     };
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = vblock; tile < n_tiles; tile += vgrid) {
         // ---- grouped input  [feat[idx] | rel xyz, |rel|] ----------------------------------------------------
         const long long r = (long long)tile * TMR + tid;
         const long long bm = r / KNBR;
@@ -271,14 +286,14 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         float gmax = hrn_warp_max(x1);
         if (WPG == 2) {
             if (lane == 0) s_red[warp][0] = gmax;
-            __syncthreads();
+            gsync();
             gmax = fmaxf(s_red[gw0][0], s_red[gw0 + 1][0]);
         }
         const float ex = expf(x1 - gmax);
         float s0 = hrn_warp_sum(ex), s1 = hrn_warp_sum(ex * nx), s2 = hrn_warp_sum(ex * ny), s3 = hrn_warp_sum(ex * nz);
         if (WPG == 2) {
             if (lane == 0) { s_red[warp][1] = s0; s_red[warp][2] = s1; s_red[warp][3] = s2; s_red[warp][4] = s3; }
-            __syncthreads();
+            gsync();
             s0 = s_red[gw0][1] + s_red[gw0 + 1][1]; s1 = s_red[gw0][2] + s_red[gw0 + 1][2];
             s2 = s_red[gw0][3] + s_red[gw0 + 1][3]; s3 = s_red[gw0][4] + s_red[gw0 + 1][4];
         }
@@ -351,15 +366,15 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             const float cm = warp_transpose_reduce<true>(f, lane);
             sCol[warp * CW + c0 + lane] = cm;
         }
-        __syncthreads();
+        gsync();
         if (leader)
             for (int c = lane; c < CD; c += 32) out_desc[bm * CD + c] = col_max(sCol, c);
         // the next tile's first barrier (inside run_layer) orders these reads before sCol / s_red are rewritten
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::T_COLS) : "memory");
+    if (cta_tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(Cfg::T_COLS_NG) : "memory");
 }
 
 using CfgL1 = LevelCfg<64, 0, 32, 32, 64, 32, 64, true>;       // detector_1 / desc_extractor_1 (models.py:14,22)
@@ -370,13 +385,13 @@ int launch_level(const float* q, const float* xyz, const float* feat, const int3
                  const float* biases, float* out_xyz, float* out_af, float* out_desc, int B, int M, int N, cudaStream_t st) {
     const int n_tiles = (int)((long long)B * M * Cfg::KNBR / TMR);
     auto kern = level_fused_kernel<Cfg>;
-    HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_NG));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = Cfg::RESIDENT ? 2 : 1;
-    const int grid = n_tiles < per_sm * sms ? n_tiles : per_sm * sms;
-    kern<<<grid, TMR, Cfg::SMEM, st>>>(q, xyz, feat, idx, (const uint8_t*)Wpack, biases, out_xyz, out_af, out_desc, M, N,
+    const int want = (n_tiles + Cfg::NG - 1) / Cfg::NG;
+    const int grid = want < sms ? want : sms;
+    kern<<<grid, TMR * Cfg::NG, Cfg::SMEM_NG, st>>>(q, xyz, feat, idx, (const uint8_t*)Wpack, biases, out_xyz, out_af, out_desc, M, N,
                                        n_tiles);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
