@@ -11,6 +11,8 @@ Each function cites the reference lines it follows (paths relative to /root/refe
     fine_reg                models/HRegNet/layers.py:433-454
     weighted_svd_head       models/HRegNet/layers.py:469-504
     hregnet_forward         models/HRegNet/models.py:77-148
+    fine_reg2               models/model_v2/layers.py:464-501
+    model_v2_forward        models/model_v2/models.py:77-183
 
 Native ops underneath (FPS, gather, kNN) are oracle/native.py.  Pinning: tests/test_oracle_vs_reference.py runs
 these functions against the UNMODIFIED reference modules (oracle/ref_harness.py) on seeded inputs in the build
@@ -171,6 +173,46 @@ def fine_reg(sd, p, sxyz, sfeat, dxyz, dfeat, sw, dw, k=8, trace=None, name=""):
         trace[name + "idx"] = idx
     cor, w, af = _pair_tail(sd, p, feats, nbr_xyz)
     return cor, w
+
+
+def fine_reg2(sd, p, sxyz, sfeat, dxyz, dfeat, sw, dw, k=8):
+    """models/model_v2/layers.py:464-501 (FineReg2): FineReg + mlpx + two host-RNG batch shuffles, in that order."""
+    _, idx, nbr_xyz = native.knn_points(sxyz, dxyz, K=k, return_nn=True)
+    Sf, Df = sfeat.permute(0, 2, 1).contiguous(), dfeat.permute(0, 2, 1).contiguous()
+    sx = sxyz.unsqueeze(2).expand(-1, -1, k, -1)
+    rel = nbr_xyz - sx
+    feats = torch.cat([rel, torch.norm(rel, dim=-1, keepdim=True), sx, nbr_xyz,
+                       Sf.unsqueeze(2).expand(-1, -1, k, -1), native.knn_gather(Df, idx),
+                       sw[:, :, None, None].expand(-1, -1, k, 1), native.knn_gather(dw.unsqueeze(-1), idx)], dim=-1)
+    cor, w, af = _pair_tail(sd, p, feats, nbr_xyz)
+    fx = _conv1d_bn_relu(af, sd, p + "mlpx")
+    fx_prime = fx[torch.randperm(fx.size(0))]
+    w_prime = w[torch.randperm(w.size(0))]
+    return cor, w, w_prime, fx, fx_prime
+
+
+def model_v2_forward(sd, src, dst):
+    """models/model_v2/models.py:77-183."""
+    fe = "feature_extraction."
+    S = hier_feature_extraction(sd, fe, src)
+    D = hier_feature_extraction(sd, fe, dst)
+    cor3, w3 = coarse_reg(sd, "coarse_corres.", S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"], S["sigmas_3"], D["sigmas_3"])
+    R3, t3 = weighted_svd_head(S["xyz_3"], cor3, w3)
+    x2 = _apply(R3, t3, S["xyz_2"])
+    cor2, w2, w2p, f2, f2p = fine_reg2(sd, "fine_corres_2.", x2, S["desc_2"], D["xyz_2"], D["desc_2"], S["sigmas_2"], D["sigmas_2"])
+    R2_, t2_ = weighted_svd_head(x2, cor2, w2)
+    R2, t2 = _compose(R2_, t2_, R3, t3)
+    x1 = _apply(R2, t2, S["xyz_1"])
+    cor1, w1 = fine_reg(sd, "fine_corres_1.", x1, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"], D["sigmas_1"])
+    R1_, t1_ = weighted_svd_head(x1, cor1, w1)
+    R1, t1 = _compose(R1_, t1_, R2, t2)
+    return {
+        "src_xyz_corres_3": cor3, "src_xyz_corres_2": cor2, "src_xyz_corres_1": cor1,
+        "rotation": [R3, R2, R1], "translation": [t3, t2, t1],
+        "src_feats_desc_2": S["desc_2"], "src_feats_sigmas_2": S["sigmas_2"], "src_xyz_2_trans": x2, "dst_xyz_2": D["xyz_2"],
+        "src_dst_feats_2": f2, "src_dst_feats_2_prime": f2p, "src_dst_weights_2": w2, "src_dst_weights_2_prime": w2p,
+        "src_feats": S, "dst_feats": D,
+    }
 
 
 def weighted_svd_head(src, cor, weights, dtype=torch.float32):

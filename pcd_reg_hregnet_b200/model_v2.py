@@ -1,0 +1,93 @@
+"""Drop-in `Model_V2` ("Adaption-1": mutual-information loss after the coarse stage) and its `FineReg1` / `FineReg2`
+blocks -- reference models/model_v2/models.py:60-183 and models/model_v2/layers.py:368-501.  Same constructor, forward
+signature, returned keys / shapes and state_dict keys as the reference.  The backbone, CoarseReg, the SVD head and the
+pose cascade are the HRegNet ones (the reference duplicates them verbatim in model_v2/layers.py:55-366,503-551).
+
+`FineReg2` differs from `FineReg` by one more head `mlpx` (Conv1d 2C->C + BN + ReLU on the attentive features) and by
+two batch-shuffled copies (`*_prime`) drawn with the HOST generator `torch.randperm(B)` in the reference's order
+(layers.py:491-497) -- call `torch.manual_seed(s)` before forward to reproduce them.
+"""
+import torch
+import torch.nn as nn
+
+from . import engine, fold
+from .engine import RowsView
+from .layers import CoarseReg, FineReg, WeightedSVDHead, _cl
+from .models import HierFeatureExtraction
+
+
+class FineReg1(FineReg):
+    """Reference: model_v2/layers.py:368-424 (identical to HRegNet's FineReg)."""
+
+
+class FineReg2(FineReg):
+    """Reference: model_v2/layers.py:426-501.  forward(...) -> (corres_xyz [B,N,3], weights [B,N], weights_prime [B,N],
+    attentive_features [B,C,N], attentive_features_prime [B,C,N])."""
+
+    def __init__(self, k, in_channels):
+        super().__init__(k, in_channels)
+        self.mlpx = nn.Sequential(nn.Conv1d(in_channels * 2, in_channels, kernel_size=1), nn.BatchNorm1d(in_channels),
+                                  nn.ReLU())
+
+    def _fold(self):
+        P = super()._fold()
+        P["mlpx"] = fold.fold_sequential(self.mlpx)
+        return P
+
+    def forward_cl(self, sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig):
+        P = self.folded()
+        B, N1, _ = sxyz.shape
+        cor, w, af = engine.fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, self.k, want_af=True)
+        (Wx, bx, act), = P["mlpx"]
+        feats = engine.transpose(engine.layer(RowsView(B * N1).add(af), Wx, bx, act).view(B, N1, -1))   # [B,C,N]
+        feats_prime = feats[torch.randperm(feats.size(0))]          # host RNG, reference order (layers.py:493)
+        w_prime = w[torch.randperm(w.size(0))]                      # (layers.py:497)
+        return cor, w, w_prime, feats, feats_prime
+
+    def forward(self, src_xyz, src_feat, dst_xyz, dst_feat, src_weights, dst_weights):
+        return self.forward_cl(src_xyz.contiguous(), _cl(src_feat), dst_xyz.contiguous(), _cl(dst_feat),
+                               src_weights.contiguous(), dst_weights.contiguous())
+
+
+class Model_V2(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.feature_extraction = HierFeatureExtraction(args)
+        if args.freeze_feats:
+            for p in self.parameters():
+                p.requires_grad = False
+        self.coarse_corres = CoarseReg(k=8, in_channels=256, use_sim=True, use_neighbor=True)
+        self.fine_corres_2 = FineReg2(k=8, in_channels=128)
+        self.fine_corres_1 = FineReg1(k=8, in_channels=64)
+        self.svd_head = WeightedSVDHead()
+
+    def forward(self, src_points, dst_points):
+        B = src_points.shape[0]
+        both = self.feature_extraction.forward_cl(torch.cat([src_points, dst_points], dim=0))
+        S = {k: v[:B] for k, v in both.items()}
+        D = {k: v[B:] for k, v in both.items()}
+        cor3, w3 = self.coarse_corres.forward_cl(S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"], S["sigmas_3"],
+                                                 D["sigmas_3"], both=(both["xyz_3"], both["desc_3"]))
+        R3, t3 = engine.weighted_kabsch(S["xyz_3"], cor3, w3)
+        xyz2_t = engine.transform_points(S["xyz_2"], R3, t3)
+        cor2, w2, w2_prime, f2, f2_prime = self.fine_corres_2.forward_cl(xyz2_t, S["desc_2"], D["xyz_2"], D["desc_2"],
+                                                                         S["sigmas_2"], D["sigmas_2"])
+        _, _, R2, t2 = engine.weighted_kabsch(xyz2_t, cor2, w2, prev=(R3, t3))
+        xyz1_t = engine.transform_points(S["xyz_1"], R2, t2)
+        cor1, w1 = self.fine_corres_1.forward_cl(xyz1_t, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"],
+                                                 D["sigmas_1"])
+        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2))
+
+        def api(d):
+            return {k: (engine.transpose(v) if k.startswith("desc_") else v) for k, v in d.items()}
+
+        src_feats, dst_feats = api(S), api(D)
+        return {
+            "src_xyz_corres_3": cor3, "src_xyz_corres_2": cor2, "src_xyz_corres_1": cor1,
+            "rotation": [R3, R2, R1], "translation": [t3, t2, t1],
+            "src_feats_desc_2": src_feats["desc_2"], "src_feats_sigmas_2": src_feats["sigmas_2"],
+            "src_xyz_2_trans": xyz2_t, "dst_xyz_2": dst_feats["xyz_2"],
+            "src_dst_feats_2": f2, "src_dst_feats_2_prime": f2_prime,
+            "src_dst_weights_2": w2, "src_dst_weights_2_prime": w2_prime,
+            "src_feats": src_feats, "dst_feats": dst_feats,
+        }

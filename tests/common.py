@@ -48,3 +48,15 @@ def rel_err(a, b):
     """Per-tensor relative error  max|a-b| / max|b|  (element-wise relative error is
     meaningless on post-ReLU zeros)."""
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def build_product_model_v2(seed=7, device="cpu"):
+    """Model_V2 (Adaption-1) with the pretrained feature extractor and seeded heads, as build_product_hregnet."""
+    from pcd_reg_hregnet_b200.model_v2 import Model_V2
+    torch.manual_seed(seed)
+    net = Model_V2(Args())
+    net.feature_extraction.load_state_dict(pretrained_feats())
+    g = torch.Generator().manual_seed(seed + 1)
+    for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
+        H.randomize_bn_(getattr(net, name), g)
+    return net.eval().to(device)

@@ -85,3 +85,29 @@ def test_unmodified_reference_wrappers_run_on_new_kernels():
     assert torch.equal(idx, out)
     g = ops.gather_operation(xyz.permute(0, 2, 1).contiguous(), idx).permute(0, 2, 1)
     assert torch.equal(g, xyz[torch.arange(2, device=DEV)[:, None], idx.long()])
+
+
+def test_model_v2_fine_reg2_teacher_forced_and_forward(precision):
+    """Adaption-1: FineReg2 (mlpx + host-RNG shuffles) against the oracle on the oracle's inputs; full forward keys."""
+    from common import build_product_model_v2
+    cpu, gpu = build_product_model_v2(seed=7), build_product_model_v2(seed=7, device=DEV)
+    src, dst, _, _ = synth.make_batch([51, 52, 53], 2048)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        want = RL.model_v2_forward(cpu.state_dict(), src, dst)
+        S, D = want["src_feats"], want["dst_feats"]
+        g = lambda t: t.to(DEV).contiguous()
+        torch.manual_seed(0)
+        cor, w, wp, f, fp = gpu.fine_corres_2(g(want["src_xyz_2_trans"]), g(S["desc_2"]), g(D["xyz_2"]), g(D["desc_2"]),
+                                              g(S["sigmas_2"]), g(D["sigmas_2"]))
+        assert float((cor.cpu() - want["src_xyz_corres_2"]).abs().max()) < 1e-3 * float(want["src_xyz_corres_2"].abs().max())
+        assert float((w.cpu() - want["src_dst_weights_2"]).abs().max()) < 1e-3
+        assert rel_err(f.cpu(), want["src_dst_feats_2"]) < 1e-3
+        # the shuffles use the same host generator in the same order as the reference (model_v2/layers.py:493,497)
+        assert rel_err(fp.cpu(), want["src_dst_feats_2_prime"]) < 1e-3
+        assert float((wp.cpu() - want["src_dst_weights_2_prime"]).abs().max()) < 1e-3
+        torch.manual_seed(0)
+        out = gpu(src.to(DEV), dst.to(DEV))
+    assert set(out.keys()) == set(want.keys())
+    assert out["src_dst_feats_2"].shape == (3, 128, 512) and out["src_dst_weights_2_prime"].shape == (3, 512)
+    assert all(torch.isfinite(v).all() for v in out["rotation"] + out["translation"])

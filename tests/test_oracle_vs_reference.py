@@ -78,3 +78,31 @@ def test_golden_fixtures_are_reference_outputs(ref_net):
             assert torch.equal(out["rotation"][i], gd[f"rotation.{i}"])
             assert torch.equal(out["translation"][i], gd[f"translation.{i}"])
         assert torch.equal(out["src_feats"]["desc_3"], gd["src_feats.desc_3"])
+
+
+def test_model_v2_matches_reference():
+    """Adaption-1 (models/model_v2): state_dict keys, seeded init and forward (incl. the host-RNG shuffles)."""
+    from common import build_product_model_v2
+    ns = H.load_reference()
+    assert ns.Model_V2 is not None, getattr(ns, "v2_error", None)
+    torch.manual_seed(7)
+    ref = ns.Model_V2(Args())
+    ref.feature_extraction.load_state_dict(torch.load(H.pretrained_feats_path(), map_location="cpu"))
+    g = torch.Generator().manual_seed(8)
+    for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
+        H.randomize_bn_(getattr(ref, name), g)
+    ref.eval()
+    prod = build_product_model_v2(seed=7)
+    rs, ps = ref.state_dict(), prod.state_dict()
+    assert list(rs.keys()) == list(ps.keys()) and all(torch.equal(rs[k], ps[k]) for k in rs)
+    assert sum(p.numel() for p in prod.parameters()) == 2500998
+    src, dst, _, _ = synth.make_batch([41, 42, 43], 2048)
+    with torch.no_grad():
+        torch.manual_seed(0); a = ref(src, dst)
+        torch.manual_seed(0); b = RL.model_v2_forward(rs, src, dst)
+    assert set(a.keys()) == set(b.keys())
+    for k in ("src_dst_feats_2", "src_dst_feats_2_prime", "src_dst_weights_2", "src_dst_weights_2_prime"):
+        assert float((a[k] - b[k]).abs().max()) < 1e-5, k
+    for lv in range(3):
+        assert float(RL.rotation_angle_deg(a["rotation"][lv], b["rotation"][lv]).max()) < 1e-4
+        assert float((a["translation"][lv] - b["translation"][lv]).abs().max()) < 1e-5
