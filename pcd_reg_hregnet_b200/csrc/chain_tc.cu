@@ -22,8 +22,8 @@ namespace {
 
 constexpr int CTM = 128;                 // rows per CTA
 constexpr int OPC_MAX = 32;              // operand buffer: 32 chunks of 8 channels = 256 wide
-constexpr int RING = 4;
-constexpr int CH_SMEM_MAX = 2 * OPC_MAX * CTM * 16 + RING * 256 * 64 + 3 * 256 * 4 + 64;
+constexpr int RING_MAX = 4;
+constexpr int CH_SMEM_MAX = 2 * OPC_MAX * CTM * 16 + RING_MAX * 256 * 64 + 3 * 256 * 4 + 64;
 
 enum { EPI_STORE = 0, EPI_GROUPMAX = 1, EPI_ATTN = 2 };
 
@@ -43,6 +43,7 @@ struct ChainArgs {
     int opc;                 // chunks of the operand buffer = max(first pass, hidden widths / 8)
     int slot_bytes;          // weight ring slot = widest layer x 64 B (one K=16 piece)
     int tmem_cols;           // power of two >= widest layer
+    int ring;                // weight ring slots (2..4)
     int chunks0;             // 8-wide K chunks of the virtual input (segments padded to 8, total padded to even)
     int mode;
     int kseg;                // rows per group (8, 16 or 32)
@@ -98,9 +99,10 @@ __device__ __forceinline__ void seg_transpose_reduce(float (&v)[32], int lane) {
 template <int KSEG>
 __global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar[2 * RING + 1];    // [0..3] piece landed, [4..7] slot drained, [8] accumulator
+    __shared__ __align__(8) uint64_t s_bar[2 * RING_MAX + 1];    // [0..3] piece landed, [4..7] slot drained, [8] accumulator
     __shared__ uint32_t s_tmem;
 
+    const int RING = A.ring;
     const uint32_t OP_PLANE = (uint32_t)A.opc * CTM * 16;
     const uint32_t SLOT_BYTES = (uint32_t)A.slot_bytes;
     uint8_t* sOp = smem;
@@ -110,14 +112,14 @@ __global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
     uint4* op_lo = reinterpret_cast<uint4*>(sOp + OP_PLANE);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_acc = smem_u32(&s_bar[2 * RING]);
+    const uint32_t bar_acc = smem_u32(&s_bar[2 * RING_MAX]);
     const int nl = A.nl;
     const int n1 = A.n[0];
     const int n3 = A.n[nl - 1];                       // issued width of the last layer
     const int cout = A.cout;
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * RING + 1; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+        for (int i = 0; i < 2 * RING_MAX + 1; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
     auto prefetch = [&]() {     // keep up to RING-1 pieces in flight beyond the one being consumed
         while (g_next < g_total && g_next < g_use + RING) {
             const uint32_t slot = g_next % RING;
-            if (g_next >= RING) mbar_wait(smem_u32(&s_bar[RING + slot]), ((g_next / RING) - 1) & 1);
+            if (g_next >= (uint32_t)RING) mbar_wait(smem_u32(&s_bar[RING_MAX + slot]), ((g_next / RING) - 1) & 1);
             const uint32_t bytes = piece_bytes(g_next);
             mbar_expect_tx(smem_u32(&s_bar[slot]), bytes);
             bulk_g2s(ring_a + slot * SLOT_BYTES, A.W + w_off, bytes, smem_u32(&s_bar[slot]));
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
                 umma_bf16(tmem, ah, wh, idesc, (accumulate || p > 0) ? 1u : 0u);
                 umma_bf16(tmem, al, wh, idesc, 1u);
                 umma_bf16(tmem, ah, wl, idesc, 1u);
-                umma_commit(smem_u32(&s_bar[RING + slot]));
+                umma_commit(smem_u32(&s_bar[RING_MAX + slot]));
                 ++g_use;
             }
             umma_commit(bar_acc);
@@ -373,7 +375,13 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
     A.slot_bytes = maxn * 64;
     A.tmem_cols = 32;
     while (A.tmem_cols < maxn) A.tmem_cols <<= 1;
-    const int CH_SMEM = 2 * opc * CTM * 16 + RING * A.slot_bytes + 3 * 256 * 4 + 64;
+    // 4 weight slots normally; 2 when that lets two CTAs share an SM (<= 113 KB each) -- overlapping two tiles'
+    // load / MMA / epilogue phases is worth more than look-ahead depth
+    const int fixed = 2 * opc * CTM * 16 + 3 * 256 * 4 + 64;
+    int ring = RING_MAX;
+    if (fixed + RING_MAX * A.slot_bytes > 113 * 1024 && fixed + 2 * A.slot_bytes <= 113 * 1024 && A.tmem_cols <= 256) ring = 2;
+    A.ring = ring;
+    const int CH_SMEM = fixed + ring * A.slot_bytes;
     static bool attr_set = false;
     if (!attr_set) {
         HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));

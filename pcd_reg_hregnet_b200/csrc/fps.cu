@@ -391,8 +391,10 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
         return launch_fps_cluster<256, 4, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
     }
     if (N <= 65536) {
+        // cluster size: as many CTAs per cloud as keep one wave (B*CS <= 148) but at least ~4096 points per CTA --
+        // below that the DSMEM exchange costs more than the shorter update loop saves
         int CS = 8;
-        while (CS > 1 && B * CS > 148) CS >>= 1;
+        while (CS > 1 && (B * CS > 148 || N / CS < 4096)) CS >>= 1;
         while (CS < 8 && (N + CS - 1) / CS > (W ? 4096 : 8192)) CS <<= 1;
         const int n_cta = (N + CS - 1) / CS;          // points per CTA
         if (n_cta <= 1024) return launch_fps_cluster<1024, 1, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
