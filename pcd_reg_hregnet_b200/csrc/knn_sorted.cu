@@ -71,6 +71,26 @@ struct WarpTopK {
     }
 };
 
+// 32-lane bitonic networks on (dist, index) pairs -- used to build the initial top-K from whole boxes at once
+__device__ __forceinline__ void cmpx(float& d, int& i, int j, bool keep_min) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, j);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, j);
+    const bool self_less = cand_less(d, i, od, oi);
+    const bool take_self = (self_less == keep_min);
+    d = take_self ? d : od;
+    i = take_self ? i : oi;
+}
+__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) cmpx(d, i, j, ((lane & j) == 0) == ((lane & k) == 0));
+}
+__device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {   // bitonic in -> ascending out
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) cmpx(d, i, j, (lane & j) == 0);
+}
+
 __device__ __forceinline__ unsigned part1by1(unsigned v) {
     v &= 0x0000ffffu;
     v = (v | (v << 8)) & 0x00ff00ffu;
@@ -182,21 +202,59 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         const float dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // padding: inf -> never offered
         top.offer(dist, __float_as_int(p.w), lane);
     };
-    // seed: the closest boxes until the list holds K finite candidates (at least K/32 + 1 boxes)
-    const int n_seed = min(nbox, (K >> 5) + 2);
-    for (int sd = 0; sd < n_seed; ++sd) {
+    // pick the box with the smallest bound among the not yet visited ones (warp-uniform result, -1 = none left)
+    auto closest_box = [&]() -> int {
         float best = CUDART_INF_F; int bg = 0;
 #pragma unroll
         for (int g = 0; g < MAXBPL; ++g) if (bd[g] < best) { best = bd[g]; bg = g; }
         const unsigned ob = hrn_ford(best);
         const unsigned wmin = __reduce_min_sync(0xffffffffu, ob);
+        if (wmin == hrn_ford(CUDART_INF_F)) return -1;
         const int src = __ffs(__ballot_sync(0xffffffffu, ob == wmin)) - 1;
         const int g_sel = __shfl_sync(0xffffffffu, bg, src);
-        if (wmin == hrn_ford(CUDART_INF_F)) break;
-        open_box(g_sel * 32 + src);
         if (lane == src) {
 #pragma unroll
             for (int g = 0; g < MAXBPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;   // visited
+        }
+        return g_sel * 32 + src;
+    };
+    auto box_dist = [&](int bx, float& dist, int& pid) {
+        const float4 p = __ldg(pts + bx * 32 + lane);
+        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+        dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        pid = __float_as_int(p.w);
+    };
+    // seed: the KPL closest boxes are SORTED into the list with a bitonic network (one box per list register) instead
+    // of K one-at-a-time insertions, then two more boxes tighten the threshold before the sweep
+    {
+        int nb = 0;
+#pragma unroll
+        for (int s = 0; s < KPL; ++s) {
+            const int bx = closest_box();
+            if (bx >= 0) { box_dist(bx, top.d[s], top.i[s]); ++nb; }
+            bitonic_sort32(top.d[s], top.i[s], lane);
+        }
+        if (KPL == 2) {          // merge the two sorted boxes into one ascending list of 64
+            const float rd = __shfl_sync(0xffffffffu, top.d[1], 31 - lane);
+            const int ri = __shfl_sync(0xffffffffu, top.i[1], 31 - lane);
+            const bool lo_self = cand_less(top.d[0], top.i[0], rd, ri);
+            const float hd = lo_self ? rd : top.d[0];
+            const int hi = lo_self ? ri : top.i[0];
+            if (!lo_self) { top.d[0] = rd; top.i[0] = ri; }
+            top.d[1] = hd; top.i[1] = hi;
+            bitonic_merge32(top.d[0], top.i[0], lane);
+            bitonic_merge32(top.d[1], top.i[1], lane);
+        }
+        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
+        float td = top.d[0]; int ti = top.i[0];
+#pragma unroll
+        for (int s = 1; s < KPL; ++s) if (ks == s) { td = top.d[s]; ti = top.i[s]; }
+        top.thr_d = __shfl_sync(0xffffffffu, td, kl);
+        top.thr_i = __shfl_sync(0xffffffffu, ti, kl);
+        for (int extra = 0; extra < 2; ++extra) {
+            const int bx = closest_box();
+            if (bx < 0) break;
+            open_box(bx);
         }
     }
     // sweep: every box whose bound can still beat the K-th candidate
