@@ -347,11 +347,18 @@ def _profile_families(reg, steps=3):
     layer_fl = sum(flops[n] for n in layer_names)
     n_layer = sum(1 for r in rec if r[0] in layer_names) / steps
 
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):          # DRAM bytes of the same kernel family over one step, from the committed ncu capture
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["tensor_family_dram_bytes_per_step"], tj["source"]
+
     def roofline(pk):
         ach = layer_fl / (layer_ms / 1e3) / 1e12 if layer_ms > 0 else 0.0
         return {"kernel": "+".join(layer_names) + " (shared-MLP tensor-core kernels)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_unit": "bytes per step over the family's launches (ncu dram__bytes_read+write)",
+                "traffic_source": traffic_src, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": n_layer, "ms_per_step": layer_ms, "share_of_step": layer_ms / sum(fam.values()),
                 "algorithmic_gflop_per_step": layer_fl / 1e9}
 

@@ -17,6 +17,17 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADC
 
 _PRECISION = "tc"       # "tc": tcgen05 kernels (bf16x3, fp32-class accuracy); "fp32": exact CUDA-core layers
 _FUSED_CHAINS = True     # tc mode: three-layer conv stacks (<= 256 wide) + their group reductions in one kernel
+_SIDE_STREAM = True      # overlap independent branches of CoarseReg on a second CUDA stream
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 _FUSED_HEADS = True      # tc mode: per-keypoint heads (mlp1/mlp2/mlp3, width <= 256) as one chain launch
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
 
@@ -344,15 +355,35 @@ def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None):
     batch of 2B clouds instead of two."""
     B, N1, C = sdesc_cl.shape
     N2 = dxyz.shape[1]
-    idx, _ = knn_idx(sdesc_cl, ddesc_cl, k)                      # 256-d descriptor space (layers.py:278)
-    misc, _ = group_geometry(sxyz, dxyz, idx, ssig, dsig, ld=16)  # cols 0..11; 12..15 = similarity features
-    _cosine_features(sdesc_cl, ddesc_cl, idx, misc, 12, 13)
-    if both is not None and N1 == N2:
-        nb = _neighbour_aware(both[0], both[1], P, k)
-        s_nbr, d_nbr = nb[:B], nb[B:]
+
+    def descriptor_branch():
+        i, _ = knn_idx(sdesc_cl, ddesc_cl, k)                      # 256-d descriptor space (layers.py:278)
+        m, _ = group_geometry(sxyz, dxyz, i, ssig, dsig, ld=16)     # cols 0..11; 12..15 = similarity features
+        _cosine_features(sdesc_cl, ddesc_cl, i, m, 12, 13)
+        return i, m
+
+    def neighbour_branch():
+        if both is not None and N1 == N2:
+            nb = _neighbour_aware(both[0], both[1], P, k)
+            return nb[:B], nb[B:]
+        return _neighbour_aware(sxyz, sdesc_cl, P, k), _neighbour_aware(dxyz, ddesc_cl, P, k)
+
+    if _SIDE_STREAM and sxyz.is_cuda:
+        # the descriptor-space search + plain similarity features and the neighbour-aware branch (layers.py:316-337) are
+        # independent until the second similarity pick: run the former on a side stream (fork/join with events, also
+        # valid under CUDA-graph capture)
+        main = torch.cuda.current_stream(sxyz.device)
+        side = _side_stream(sxyz.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            idx, misc = descriptor_branch()
+        s_nbr, d_nbr = neighbour_branch()
+        main.wait_stream(side)
+        idx.record_stream(main)
+        misc.record_stream(main)
     else:
-        s_nbr = _neighbour_aware(sxyz, sdesc_cl, P, k)
-        d_nbr = _neighbour_aware(dxyz, ddesc_cl, P, k)
+        idx, misc = descriptor_branch()
+        s_nbr, d_nbr = neighbour_branch()
     _cosine_features(s_nbr, d_nbr, idx, misc, 14, 15)
     v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
     v.add(misc).add(sdesc_cl.view(B * N1, C), SEG_BROADCAST).add(ddesc_cl.view(B * N2, C), SEG_GATHER)
