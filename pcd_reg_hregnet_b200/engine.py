@@ -175,7 +175,7 @@ def knn_idx(p1, p2, K, q_idx=None):
     M = q_idx.shape[1] if q_idx is not None else p1.shape[1]
     idx = torch.empty(B, M, K, dtype=torch.int32, device=p2.device)
     q_out = torch.empty(B, M, 3, dtype=torch.float32, device=p2.device) if q_idx is not None else None
-    if D == 3 and 2048 <= N <= 16384 and _SORTED_KNN:
+    if D == 3 and 1024 <= N <= 16384 and _SORTED_KNN:
         pts, boxes = knn_scratch(B, N, p2.device)
         call("hrn_knn3_sorted", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, K, ptr(pts), ptr(boxes),
              None, None, ptr(idx), None, ptr(q_out), stream())
