@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the per-layer tensor-core shared-MLP kernel (hrn_layer_tc) on the shapes of the headline workload.
+
+    python bench_layers.py            # one JSON line per shape: us, useful TFLOP/s, max |err| against fp64 matmul
+
+Shapes (32 pairs x 16,384 points): the coarse-level `convs_1` stack (65,536 rows, 528 -> 512 -> 512 ->
+512, first layer over a gathered 3-segment virtual row), the level-3 descriptor `mlp1`/`mlp2` (262,144 rows, 768 -> 256
+-> 256) and the per-keypoint confidence head (8,192 rows).  Timing: CUDA events, L2 flushed between iterations.
+"""
+import argparse
+import json
+import sys
+
+import torch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring filter on the case name")
+    args = ap.parse_args()
+    from pcd_reg_hregnet_b200 import engine, engine_tc
+    from pcd_reg_hregnet_b200.engine import RowsView, SEG_BROADCAST, SEG_GATHER, ACT_RELU
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def rnd(*s):
+        return torch.randn(*s, device=dev, generator=g)
+
+    cases = []
+    # (name, rows, view builder, Cout)
+    B, N1, k, C = 32, 256, 8, 256
+    idx = torch.randint(0, N1, (B, N1, k), device=dev, generator=g, dtype=torch.int64)
+    misc, S, D = rnd(B * N1 * k, 16), rnd(B * N1, C), rnd(B * N1, C)
+
+    def coarse_view():
+        v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N1)
+        return v.add(misc).add(S, SEG_BROADCAST).add(D, SEG_GATHER)
+
+    cases.append(("coarse convs_1[0] 528->512 (gathered)", coarse_view, 512))
+    X512 = rnd(B * N1 * k, 512)
+    cases.append(("coarse convs_1[1] 512->512", lambda: RowsView(B * N1 * k).add(X512), 512))
+    X768 = rnd(262144, 768)
+    cases.append(("L3 mlp1 768->256", lambda: RowsView(262144).add(X768), 256))
+    X256 = rnd(262144, 256)
+    cases.append(("L3 mlp2 256->256", lambda: RowsView(262144).add(X256), 256))
+    X64 = rnd(1 << 20, 64)
+    cases.append(("1M rows 64->64", lambda: RowsView(1 << 20).add(X64), 64))
+    Xh = rnd(8192, 512)
+    cases.append(("head 512->512 (8192 rows)", lambda: RowsView(8192).add(Xh), 512))
+    cases.append(("head 512->1 (8192 rows)", lambda: RowsView(8192).add(Xh), 1))
+
+    for name, mk, cout in cases:
+        if args.only and args.only not in name:
+            continue
+        v = mk()
+        K = sum(s[2] for s in v.segs)
+        W = rnd(cout, K) / K ** 0.5
+        b = rnd(cout)
+        out = torch.empty(v.rows, cout, device=dev)
+        engine_tc.layer_tc(v, W, b, ACT_RELU, out)
+        torch.cuda.synchronize()
+        # accuracy on a row sample against fp64
+        if len(v.segs) == 1:
+            X = v.segs[0][0]
+            sel = torch.arange(0, v.rows, max(1, v.rows // 4096), device=dev)
+            ref = torch.relu(X[sel].double() @ W.double().t() + b.double())
+            err = (out[sel].double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        else:
+            err = None
+        ts = []
+        for _ in range(args.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engine_tc.layer_tc(v, W, b, ACT_RELU, out)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        us = ts[len(ts) // 2]
+        print(json.dumps({"layer": name, "rows": v.rows, "K": K, "N": cout, "us": round(us, 1),
+                          "useful_tflops": round(2.0 * v.rows * K * cout / us / 1e6, 1), "rel_err": err}))
+        sys.stdout.flush()
+
+
+if __name__ == "__main__":
+    main()

@@ -232,6 +232,322 @@ layer_tc_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised persistent variant (one CTA per SM, all 512 TMEM columns, ~200 KB of shared memory):
+//
+//   warps 0-3   epilogue   TMEM lane quadrant = warp; drain accumulator b while the MMAs fill accumulator b^1
+//   warps 4-11  producers  thread <-> (row, k-half): gather 16 fp32 of the row per stage (two stages of loads in
+//                          flight in registers), split to bf16 hi/lo, write the UMMA core-matrix layout
+//   warp 12     MMA        one thread issues tcgen05.mma for every stage as soon as its operands have landed
+//   warp 13     weights    one thread streams the packed weight slab of every stage with cp.async.bulk
+//
+// A work item is (128-row tile, <=256-column block); CTA c takes items c, c + grid, ...  Each ring stage holds the
+// A slab (16 KB) and the weight slab (NS * 128 B) of one 32-wide K chunk:  full[s] collects 8 producer-warp arrivals
+// + the bulk-copy transaction bytes, empty[s] is armed by tcgen05.commit.  Nothing in the loop is a CTA-wide barrier:
+// the gather latency, the weight stream, the MMAs and the previous item's epilogue all overlap.
+constexpr int WS_EPI_WARPS = 4, WS_PROD_WARPS = 8;
+constexpr int WS_THREADS = (WS_EPI_WARPS + WS_PROD_WARPS + 2) * 32;   // 448
+constexpr int WS_MAX_STAGES = 8;
+constexpr int WS_TP = 36;                                              // epilogue transpose tile pitch (floats)
+constexpr int WS_TILE_BYTES = WS_EPI_WARPS * 32 * WS_TP * 4;        // 18 KB
+constexpr int WS_RAW = 4;                                             // raw fp32 stages (cp.async) in flight per CTA
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
+                float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NS, int n_split, int n_stage,
+                int S, int n_items) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_full[WS_MAX_STAGES], s_empty[WS_MAX_STAGES], s_accf[2], s_acce[2];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t w_bytes = (uint32_t)NS * 128u;
+    const uint32_t stage_bytes = A_STAGE_BYTES + w_bytes;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
+    const uint32_t accf0 = smem_u32(&s_accf[0]), acce0 = smem_u32(&s_acce[0]);
+
+    if (tid == 0) {
+        for (int i = 0; i < WS_MAX_STAGES; ++i) { mbar_init(full0 + 8 * i, WS_PROD_WARPS + 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accf0 + 8 * i, 1); mbar_init(acce0 + 8 * i, WS_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp < WS_EPI_WARPS) {
+        // ================= epilogue: accumulator -> +bias -> activation -> HBM ==================================
+        int ph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ph) {
+            const int m = it / n_split, n0 = (it - m * n_split) * NS, b = ph & 1;
+            const long long r = (long long)m * TM + warp * 32 + lane;
+            const bool rvalid = r < rows;
+            float* yrow = Y + r * ldy + n0;
+            const float* brow = bias + n0;
+            const int ncols = min(NS, Cout - n0);
+            mbar_wait(accf0 + 8 * b, (ph >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(Y + n0) | reinterpret_cast<uintptr_t>(brow)) & 15) == 0 && (ldy & 3) == 0;
+            float* tile = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes) + warp * (32 * WS_TP);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * 256 + c0, v);
+                if (c0 + 32 <= ncols && vec_ok) {
+                    // transpose through shared memory so that a store instruction covers 4 rows x 128 contiguous bytes
+                    // (4 cache lines per request instead of 32 with one row per lane)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(tile + lane * WS_TP + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+                    const int piece = lane & 7;
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(brow + c0) + piece);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = (lane >> 3) + 4 * i;
+                        const float4 t = *reinterpret_cast<const float4*>(tile + rl * WS_TP + piece * 4);
+                        const long long rr = (long long)m * TM + warp * 32 + rl;
+                        float4 o;
+                        o.x = act_fn(t.x + bb.x, act); o.y = act_fn(t.y + bb.y, act);
+                        o.z = act_fn(t.z + bb.z, act); o.w = act_fn(t.w + bb.w, act);
+                        if (rr < rows) *reinterpret_cast<float4*>(Y + rr * ldy + n0 + c0 + piece * 4) = o;
+                    }
+                    __syncwarp();
+                } else if (rvalid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < ncols) yrow[c0 + j] = act_fn(__uint_as_float(v[j]) + __ldg(brow + c0 + j), act);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce0 + 8 * b);
+        }
+    } else if (warp < WS_EPI_WARPS + WS_PROD_WARPS) {
+        // ================= producers: gather + split the A operand ==============================================
+        // Coalesced gather: a warp owns 16 rows of the tile as two groups of 8.  Per copy instruction lane l moves
+        // 16 bytes of row (l & 7) -> 8 rows x 64 contiguous bytes per request (8 cache lines; one row per lane would
+        // be 32 and saturates the L1 tag pipeline).  The copies are cp.async (LDGSTS, L2 -> shared memory, no
+        // registers, no scoreboard): WS_RAW stages of them stay in flight per thread across item boundaries, which is
+        // what covers the HBM latency.  (Register prefetching cannot: ptxas puts every stage's loads on one scoreboard,
+        // so waiting for the oldest stage waits for the newest.)  Each lane later reads back exactly the 16-byte slots
+        // it copied, so cp.async.wait_group is the only synchronisation the raw ring needs.
+        // Lanes l and l ^ 8 hold the two halves of one 8-wide core-matrix row: they swap bf16 halves so that one
+        // stores the hi row, the other the lo row (16-byte stores, 8 consecutive rows per quarter warp: conflict-free).
+        const int pw = warp - WS_EPI_WARPS;
+        const int rsub = lane & 7, hf = (lane >> 3) & 1, cl = lane >> 4;
+        int c0s[5], chs[4];                                    // segment table: first 8-wide chunk, channels
+        {
+            int run = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                chs[s] = 0; c0s[s] = 0x7fffffff;
+                if (s < in.n_seg) { c0s[s] = run; run += (in.seg[s].channels + 7) >> 3; chs[s] = in.seg[s].channels; }
+            }
+            c0s[4] = run;
+        }
+        int direct_mask = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) if (s < in.n_seg && in.seg[s].mode == HRN_SEG_DIRECT) direct_mask |= 1 << s;
+        const float* rp[2][4];                                 // row base pointers of this lane's two rows
+        float rsc[2][4];
+        int st = 0; uint32_t par = 0;                          // ring position of the next stage to fill
+        float sc[WS_RAW][4];                                   // per-piece row scale of the stages in flight
+        int lit = blockIdx.x, li = 0;                          // copy cursor: item, stage within the item
+        uint8_t* raw0 = smem + (size_t)S * stage_bytes + WS_TILE_BYTES + (size_t)(pw * 4) * 512 + lane * 16;
+        const bool small = rows < 0x7fffffffLL;
+        auto resolve = [&](int it) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const long long r = (long long)(it / n_split) * TM + pw * 16 + g * 8 + rsub;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    rp[g][s] = nullptr; rsc[g][s] = 1.f;
+                    if (s < in.n_seg && r < rows) {
+                        const hrn_seg_t sg = in.seg[s];
+                        long long sr;
+                        if (small) {                               // 32-bit divisions
+                            const unsigned ru = (unsigned)r;
+                            sr = sg.mode == HRN_SEG_DIRECT ? (long long)ru
+                               : sg.mode == HRN_SEG_BROADCAST ? (long long)(ru / (unsigned)in.group)
+                               : (long long)(ru / (unsigned)in.rows_per_batch) * in.src_rows_per_batch + in.gather_idx[r];
+                        } else {
+                            sr = hrn_src_row(in, sg.mode, r);
+                        }
+                        rp[g][s] = sg.ptr + sr * sg.ld + sg.col0;
+                        if (sg.row_scale) rsc[g][s] = __ldg(sg.row_scale + r);
+                    }
+                }
+            }
+        };
+        // async copy of the 4 floats [4 hf, 4 hf + 4) of 8-wide chunk cg of one row (zero-filled out of range)
+        auto copy_piece = [&](const float* const (&pp)[4], const float (&ps)[4], int cg, uint8_t* dst, float& osc) {
+            int sgi = 0;
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if (cg >= c0s[q]) sgi = q;
+            const float* p = pp[0]; int cs = c0s[0], chn = chs[0]; osc = ps[0];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if (sgi == q) { p = pp[q]; cs = c0s[q]; chn = chs[q]; osc = ps[q]; }
+            const int ch0 = ((cg - cs) << 3) + 4 * hf;
+            const bool ok = p != nullptr && cg < c0s[4] && chn - ch0 >= 4;
+            const void* src = ok ? (const void*)(p + ch0) : (const void*)Wp;
+            // streamed rows bypass L1; broadcast / gathered rows are shared by the rows of a group -> keep them in L1
+            if (direct_mask >> sgi & 1)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        };
+        auto issue = [&](int slot, float (&ss)[4]) {
+            if (lit < n_items) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        copy_piece(rp[g], rsc[g], li * 4 + 2 * j + cl, raw0 + (size_t)slot * A_STAGE_BYTES + (g * 2 + j) * 512, ss[2 * g + j]);
+                if (++li == n_stage) {
+                    li = 0; lit += gridDim.x;
+                    if (lit < n_items) resolve(lit);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto fill = [&](int slot, const float (&ss)[4]) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(WS_RAW - 1) : "memory");
+            float4 vv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) vv[e] = *reinterpret_cast<const float4*>(raw0 + (size_t)slot * A_STAGE_BYTES + e * 512);
+            mbar_wait(empty0 + 8 * st, par ^ 1);
+            uint4* a_hi = reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes);
+            uint4* a_lo = a_hi + (KC / 8) * TM;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 t = vv[2 * g + j];
+                    const float s_ = ss[2 * g + j];
+                    const float x0 = t.x * s_, x1 = t.y * s_, x2 = t.z * s_, x3 = t.w * s_;
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
+                    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
+                    const uint32_t H0 = *reinterpret_cast<const uint32_t*>(&h0), H1 = *reinterpret_cast<const uint32_t*>(&h1);
+                    const uint32_t L0 = *reinterpret_cast<const uint32_t*>(&l0), L1 = *reinterpret_cast<const uint32_t*>(&l1);
+                    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hf ? H0 : L0, 8);
+                    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, hf ? H1 : L1, 8);
+                    const int slot_a = (2 * j + cl) * TM + pw * 16 + g * 8 + rsub;
+                    if (hf == 0) a_hi[slot_a] = make_uint4(H0, H1, r0, r1);
+                    else         a_lo[slot_a] = make_uint4(r0, r1, L0, L1);
+                }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * st);
+            if (++st == S) { st = 0; par ^= 1; }
+        };
+        int my_items = 0;
+        if ((int)blockIdx.x < n_items) my_items = (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+        const int total = my_items * n_stage;
+        if (total > 0) resolve(lit);
+#pragma unroll
+        for (int d = 0; d < WS_RAW; ++d) issue(d, sc[d]);
+        for (int q = 0; q < total; q += WS_RAW) {
+#pragma unroll
+            for (int d = 0; d < WS_RAW; ++d) {
+                if (q + d < total) { fill(d, sc[d]); issue(d, sc[d]); }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp == WS_EPI_WARPS + WS_PROD_WARPS) {
+        // ================= MMA issue ==============================================================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t a_lbo = TM * 16, w_lbo = (uint32_t)NS * 16;
+            const uint32_t a_lo_off = (KC / 8) * TM * 16, w_lo_off = (KC / 8) * (uint32_t)NS * 16;
+            int st = 0; uint32_t par = 0; int ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ph) {
+                const int b = ph & 1;
+                mbar_wait(acce0 + 8 * b, ((ph >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem + b * 256;
+                for (int i = 0; i < n_stage; ++i) {
+                    mbar_wait(full0 + 8 * st, par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_base = smem0 + st * stage_bytes, w_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k) {
+                        const uint64_t ah = umma_desc(a_base + k * 2 * a_lbo, a_lbo, 128);
+                        const uint64_t al = umma_desc(a_base + a_lo_off + k * 2 * a_lbo, a_lbo, 128);
+                        const uint64_t wh = umma_desc(w_base + k * 2 * w_lbo, w_lbo, 128);
+                        const uint64_t wl = umma_desc(w_base + w_lo_off + k * 2 * w_lbo, w_lbo, 128);
+                        umma_bf16(d, ah, wh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(d, al, wh, idesc, 1u);
+                        umma_bf16(d, ah, wl, idesc, 1u);
+                    }
+                    umma_commit(empty0 + 8 * st);
+                    if (++st == S) { st = 0; par ^= 1; }
+                }
+                umma_commit(accf0 + 8 * b);
+            }
+        }
+    } else {
+        // ================= weight stream ==========================================================================
+        if (lane == 0) {
+            const size_t w_full_stage = (size_t)NPfull * 64;                // bf16 elements per packed stage
+            int st = 0; uint32_t par = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int n0 = (it % n_split) * NS;
+                for (int i = 0; i < n_stage; ++i) {
+                    mbar_wait(empty0 + 8 * st, par ^ 1);
+                    const uint32_t barw = full0 + 8 * st;
+                    const uint32_t dst = smem0 + st * stage_bytes + A_STAGE_BYTES;
+                    const __nv_bfloat16* src = Wp + (size_t)i * w_full_stage;
+                    mbar_expect_tx(barw, w_bytes);
+                    if (NS == NPfull) {
+                        bulk_g2s(dst, src, w_bytes, barw);
+                    } else {
+#pragma unroll
+                        for (int pc = 0; pc < 2 * (KC / 8); ++pc)
+                            bulk_g2s(dst + pc * NS * 16, src + ((size_t)pc * NPfull + n0) * 8, (uint32_t)NS * 16, barw);
+                    }
+                    if (++st == S) { st = 0; par ^= 1; }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
+                    int Cout, int NP, int n_stage, cudaStream_t stream) {
+    const int tiles = hrn_divup(rows, TM);
+    int NS = NP > 256 ? 256 : NP;
+    while (NS > 32 && (NS / 2) % 16 == 0 && tiles * (NP / NS) < 148) NS >>= 1;
+    const int n_split = NP / NS;
+    const int n_items = tiles * n_split;
+    const size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)NS * 128;
+    const size_t fixed = WS_TILE_BYTES + (size_t)WS_RAW * A_STAGE_BYTES;
+    const size_t budget = 226 * 1024;
+    int S = (int)((budget - fixed) / stage_bytes);
+    if (S > WS_MAX_STAGES) S = WS_MAX_STAGES;
+    const size_t smem = (size_t)S * stage_bytes + fixed;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        attr_set = true;
+    }
+    const int grid = n_items < 148 ? n_items : 148;
+    layer_ws_kernel<<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS,
+                                                        n_split, n_stage, S, n_items);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
 }  // namespace
 
 // Wp = weights packed by hrn_pack_weights_layout (see engine_tc.pack_weights): [n_stage][2][4][NP][8] bf16.
@@ -249,6 +565,11 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     }
     if (n_stage != (chunks * 8 + KC - 1) / KC) return HRN_ERR_BAD_ARG;
     if (rows == 0) return HRN_OK;
+    bool fast = true;   // 16-byte vector path: every segment 4-float aligned
+    for (int s = 0; s < in->n_seg; ++s) {
+        const hrn_seg_t& g = in->seg[s];
+        if ((g.channels & 3) || (g.ld & 3) || (g.col0 & 3) || ((uintptr_t)g.ptr & 15)) fast = false;
+    }
     // few row tiles (per-keypoint heads, coarse level): split the output columns over blockIdx.y so that the grid
     // still covers the 148 SMs
     const int tiles = hrn_divup(rows, TM);
@@ -266,11 +587,10 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
         HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 3 * 512 * 128));
         attr_set = true;
     }
-    bool fast = true;   // 16-byte vector path: every segment 4-float aligned
-    for (int s = 0; s < in->n_seg; ++s) {
-        const hrn_seg_t& g = in->seg[s];
-        if ((g.channels & 3) || (g.ld & 3) || (g.col0 & 3) || ((uintptr_t)g.ptr & 15)) fast = false;
-    }
+    // 16-byte aligned segments (every call of the registration path): persistent warp-specialised kernel; the
+    // one-CTA-per-tile kernel below remains as the general fallback (odd channel counts, unaligned views)
+    if (fast)
+        return layer_ws_launch(in, Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, (cudaStream_t)stream);
     dim3 grid(tiles, n_split);
     if (fast)
         layer_tc_kernel<true><<<grid, TM, smem, (cudaStream_t)stream>>>(
