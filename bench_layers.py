@@ -18,7 +18,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="", help="substring filter on the case name")
+    ap.add_argument("--chains", action="store_true", help="time the fused chains instead of single layers")
     args = ap.parse_args()
+    if args.chains:
+        return chains(args)
     from pcd_reg_hregnet_b200 import engine, engine_tc
     from pcd_reg_hregnet_b200.engine import RowsView, SEG_BROADCAST, SEG_GATHER, ACT_RELU
 
@@ -83,6 +86,61 @@ def main():
         us = ts[len(ts) // 2]
         print(json.dumps({"layer": name, "rows": v.rows, "K": K, "N": cout, "us": round(us, 1),
                           "useful_tflops": round(2.0 * v.rows * K * cout / us / 1e6, 1), "rel_err": err}))
+        sys.stdout.flush()
+
+
+def chains(args):
+    """Fused 3-layer chains (hrn_chain_tc) on the shapes of the headline workload."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    from pcd_reg_hregnet_b200.engine import RowsView, SEG_BROADCAST, SEG_GATHER, ACT_RELU
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def rnd(*s):
+        return torch.randn(*s, device=dev, generator=g)
+
+    def grouped_view(B, N, k, C, geom):
+        idx = torch.randint(0, N, (B, N, k), device=dev, generator=g, dtype=torch.int64)
+        misc, S, D = rnd(B * N * k, geom), rnd(B * N, C), rnd(B * N, C)
+        v = RowsView(B * N * k, group=k, gather_idx=idx, rows_per_batch=N * k, src_rows_per_batch=N)
+        return v.add(misc).add(S, SEG_BROADCAST).add(D, SEG_GATHER)
+
+    cases = [
+        ("fine L2 convs_1 12+128+128 -> 256x3 attn k8", lambda: grouped_view(32, 512, 8, 128, 12), [256, 256, 256], engine_tc.EPI_ATTN, 8, False),
+        ("fine L1 convs_1 12+64+64 -> 128x3 attn k8", lambda: grouped_view(32, 1024, 8, 64, 12), [128, 128, 128], engine_tc.EPI_ATTN, 8, False),
+        ("L3 convs 132 -> 128,128,256 groupmax k16 +rows", lambda: RowsView(262144).add(rnd(262144, 132)), [128, 128, 256], engine_tc.EPI_GROUPMAX, 16, True),
+        ("direct 272 -> 256x3 attn k8", lambda: RowsView(131072).add(rnd(131072, 272)), [256, 256, 256], engine_tc.EPI_ATTN, 8, False),
+    ]
+    for name, mk, widths, mode, kseg, want_rows in cases:
+        if args.only and args.only not in name:
+            continue
+        v = mk()
+        K = sum(s[2] for s in v.segs)
+        layers, kin = [], K
+        for w in widths:
+            layers.append((rnd(w, kin) / kin ** 0.5, rnd(w) * 0.1, ACT_RELU))
+            kin = w
+        if not engine_tc.chain_supported(v, layers):
+            print(json.dumps({"chain": name, "unsupported": True}))
+            continue
+        engine_tc.chain3(v, layers, mode, kseg, want_rows=want_rows)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engine_tc.chain3(v, layers, mode, kseg, want_rows=want_rows)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        us = ts[len(ts) // 2]
+        flops = 2.0 * v.rows * sum(a * b for a, b in zip([K] + widths[:-1], widths))
+        print(json.dumps({"chain": name, "rows": v.rows, "K": K, "widths": widths, "us": round(us, 1),
+                          "useful_tflops": round(flops / us / 1e6, 1)}))
         sys.stdout.flush()
 
 

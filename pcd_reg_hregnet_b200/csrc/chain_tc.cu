@@ -9,21 +9,18 @@
 //   EPI_GROUPMAX  Y rows and max over the k rows of each group              (layers.py:202)
 //   EPI_ATTN      a = softmax_k(max_c Y), AF[g,:] = sum_k a Y, optionally the rows Y*a
 //                 (layers.py:150-159, 329-332, 384-390, 446-450)
-// Per-layer kernels write and re-read every [rows, C] intermediate (3 launches, 6 HBM passes); here a CTA owns 128
-// rows, the first operand is gathered from the virtual rows into shared memory, each layer's result goes
-// TMEM -> registers -> bias+ReLU -> bf16 hi/lo split -> back IN PLACE as the next layer's A operand, and weights
-// stream from L2 in K=16 pieces through a 4-slot cp.async.bulk ring (3 pieces of look-ahead).  bf16x3 products,
-// fp32 accumulation, same numerics as mlp_tc.cu.
+// Per-layer kernels write and re-read every [rows, C] intermediate (3 launches, 6 HBM passes); here a tile of 128
+// rows goes through all layers on chip: the first operand is gathered from the virtual rows, each layer's result goes
+// TMEM -> registers -> bias+ReLU -> bf16 hi/lo split -> shared memory as the next layer's A operand, and the weights
+// stream from L2 in K=16 pieces through a cp.async.bulk ring.  bf16x3 products, fp32 accumulation, same numerics as
+// mlp_tc.cu.  The kernel is persistent and warp-specialised (see chain_ws_kernel below).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
 
 namespace {
 
-constexpr int CTM = 128;                 // rows per CTA
-constexpr int OPC_MAX = 32;              // operand buffer: 32 chunks of 8 channels = 256 wide
-constexpr int RING_MAX = 4;
-constexpr int CH_SMEM_MAX = 2 * OPC_MAX * CTM * 16 + RING_MAX * 256 * 64 + 3 * 256 * 4 + 64;
+constexpr int CTM = 128;                 // rows per tile (UMMA M)
 
 enum { EPI_STORE = 0, EPI_GROUPMAX = 1, EPI_ATTN = 2 };
 
@@ -40,10 +37,8 @@ struct ChainArgs {
     int nl;                  // number of layers (2 or 3)
     int cout;                // real output columns of the last layer (<= n[nl-1])
     int act;                 // activation of the last layer (HRN_ACT_*); hidden layers are ReLU
-    int opc;                 // chunks of the operand buffer = max(first pass, hidden widths / 8)
     int slot_bytes;          // weight ring slot = widest layer x 64 B (one K=16 piece)
-    int tmem_cols;           // power of two >= widest layer
-    int ring;                // weight ring slots (2..4)
+    int ring;                // weight ring slots
     int chunks0;             // 8-wide K chunks of the virtual input (segments padded to 8, total padded to even)
     int mode;
     int kseg;                // rows per group (8, 16 or 32)
@@ -51,27 +46,6 @@ struct ChainArgs {
 
 __device__ __forceinline__ uint32_t ch_idesc(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(CTM >> 4) << 24);
-}
-
-struct RowSrcC {
-    const float* p[4];
-    float sc[4];
-    int c0[5];
-    int ch[4];
-};
-
-__device__ __forceinline__ void ch_load_chunk(const RowSrcC& rs, int cg, float4& v0, float4& v1, float& sc) {
-    int sgi = 0;
-#pragma unroll
-    for (int q = 1; q < 4; ++q) if (cg >= rs.c0[q]) sgi = q;
-    const float* p = rs.p[0]; int cs = rs.c0[0], chn = rs.ch[0]; sc = rs.sc[0];
-#pragma unroll
-    for (int q = 1; q < 4; ++q) if (sgi == q) { p = rs.p[q]; cs = rs.c0[q]; chn = rs.ch[q]; sc = rs.sc[q]; }
-    const int ch0 = (cg - cs) << 3;
-    const int nvalid = (p != nullptr && cg < rs.c0[4]) ? chn - ch0 : 0;
-    v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
-    if (nvalid >= 4) v0 = __ldg(reinterpret_cast<const float4*>(p + ch0));
-    if (nvalid >= 8) v1 = __ldg(reinterpret_cast<const float4*>(p + ch0) + 1);
 }
 
 // segmented transpose-reduce: lanes form groups of KSEG consecutive lanes; after the call, the lane at position p of
@@ -96,232 +70,426 @@ __device__ __forceinline__ void seg_transpose_reduce(float (&v)[32], int lane) {
     }
 }
 
-template <int KSEG>
-__global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent warp-specialised chain (one CTA per SM, all 512 TMEM columns = two accumulators used alternately by
+// consecutive layers).  No tile-sized operand buffer: both kinds of A operand travel through small rings of 16 KB
+// stages (128 rows x 32 K, bf16 hi + lo), which leaves the shared memory to a deep weight ring.
+//
+//   warps 0-7   epilogue   (warp & 3 = TMEM lane quadrant, warp >> 2 = group; the groups take alternate 32-column
+//                          blocks).  Hidden layers: accumulator -> relu(x + b) -> bf16 hi/lo -> ring H, one block (two
+//                          K=16 pieces) at a time, so the NEXT layer's MMAs run while this layer is still being
+//                          drained; last layer: the STORE / GROUPMAX / ATTN epilogue, overlapped with the next tile
+//   warps 8-15  producers  coalesced cp.async gather of the virtual rows into a raw fp32 ring, then split to bf16
+//                          hi/lo into ring G; they run ahead of the MMAs across tile boundaries
+//   warp 16     MMA        issues every K=16 piece as soon as its operand stage and its weights have landed
+//   warp 17     weights    streams the packed K=16 weight pieces of all layers through a cp.async.bulk ring
+constexpr int CW_EPI_WARPS = 8, CW_PROD_WARPS = 8;                    // epilogue: two warps per TMEM lane quadrant
+constexpr int CW_THREADS = (CW_EPI_WARPS + CW_PROD_WARPS + 2) * 32;   // 576
+constexpr int CW_STAGE_BYTES = 4 * CTM * 32;                          // 4 chunks x 128 rows x (8 fp32 | 8 bf16 hi + lo) = 16 KB
+constexpr int CW_RING_MAX = 8;                                        // weight slots
+constexpr int CW_GS_MAX = 4, CW_HS_MAX = 4;                           // operand ring depths
+constexpr int CW_TP = 36;
+constexpr int CW_TILE_BYTES = CW_EPI_WARPS * 32 * CW_TP * 4;
+
+struct ChainWsArgs {
+    ChainArgs c;
+    int n_tiles;
+    int use_tile;            // transpose tile for coalesced Y stores present
+    int gs, hs;              // depths of ring G (gathered input stages) and ring H (hidden-layer blocks)
+    int acc_stride, nbuf;    // TMEM accumulators: nbuf = 512 / acc_stride buffers (4 x 128 or 2 x 256 columns), used round-robin
+};
+
+template <int KSEG, int RAW>
+__global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsArgs AW) {
+    const ChainArgs& A = AW.c;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar[2 * RING_MAX + 1];    // [0..3] piece landed, [4..7] slot drained, [8] accumulator
+    __shared__ __align__(8) uint64_t s_wfull[CW_RING_MAX], s_wempty[CW_RING_MAX], s_gfull[CW_GS_MAX], s_gempty[CW_GS_MAX],
+        s_hfull[CW_HS_MAX], s_hempty[CW_HS_MAX], s_accf[4], s_fin[4];
     __shared__ uint32_t s_tmem;
 
-    const int RING = A.ring;
-    const uint32_t OP_PLANE = (uint32_t)A.opc * CTM * 16;
+    const int RING = A.ring, GS = AW.gs, HS = AW.hs;
+    const int ACC = AW.acc_stride, BM = AW.nbuf - 1;       // accumulator of layer L: columns (L & BM) * ACC
     const uint32_t SLOT_BYTES = (uint32_t)A.slot_bytes;
-    uint8_t* sOp = smem;
-    uint8_t* sRing = smem + 2 * OP_PLANE;
-    float* sBias = reinterpret_cast<float*>(sRing + RING * SLOT_BYTES);
-    uint4* op_hi = reinterpret_cast<uint4*>(sOp);
-    uint4* op_lo = reinterpret_cast<uint4*>(sOp + OP_PLANE);
+    uint8_t* sG = smem;
+    uint8_t* sH = sG + GS * CW_STAGE_BYTES;
+    uint8_t* sRing = sH + HS * CW_STAGE_BYTES;
+    uint8_t* sRaw = sRing + RING * SLOT_BYTES;
+    float* sBias = reinterpret_cast<float*>(sRaw + RAW * CW_STAGE_BYTES);
+    float* sX = sBias + 3 * 256;                            // [2][128] row maxima exchanged by the epilogue groups
+    float* sTile = sX + 2 * CTM;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_acc = smem_u32(&s_bar[2 * RING_MAX]);
     const int nl = A.nl;
-    const int n1 = A.n[0];
-    const int n3 = A.n[nl - 1];                       // issued width of the last layer
+    const int n_tiles = AW.n_tiles;
+    const int n_st0 = (A.chunks0 + 3) >> 2;                 // 32-wide input stages per tile
     const int cout = A.cout;
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * RING_MAX + 1; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+        for (int i = 0; i < CW_RING_MAX; ++i) { mbar_init(smem_u32(&s_wfull[i]), 1); mbar_init(smem_u32(&s_wempty[i]), 1); }
+        for (int i = 0; i < CW_GS_MAX; ++i) { mbar_init(smem_u32(&s_gfull[i]), CW_PROD_WARPS); mbar_init(smem_u32(&s_gempty[i]), 1); }
+        for (int i = 0; i < CW_HS_MAX; ++i) { mbar_init(smem_u32(&s_hfull[i]), 4); mbar_init(smem_u32(&s_hempty[i]), 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&s_accf[i]), 1); mbar_init(smem_u32(&s_fin[i]), CW_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(A.tmem_cols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int nbias = A.n[0] + (nl == 3 ? A.n[1] : 0) + cout;
-    for (int i = tid; i < nbias; i += CTM) sBias[i] = __ldg(A.bias + i);
-
-    // ---- row bookkeeping -----------------------------------------------------------------------------------
-    const long long r = (long long)blockIdx.x * CTM + tid;
-    const bool rvalid = r < A.rows;
-    RowSrcC rs;
-    int run = 0;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        rs.p[s] = nullptr; rs.sc[s] = 1.f; rs.ch[s] = 0; rs.c0[s] = 0x7fffffff;
-        if (s < A.in.n_seg) {
-            const hrn_seg_t sg = A.in.seg[s];
-            rs.c0[s] = run;
-            run += (sg.channels + 7) >> 3;
-            rs.ch[s] = sg.channels;
-            if (rvalid) {
-                rs.p[s] = sg.ptr + hrn_src_row(A.in, sg.mode, r) * sg.ld + sg.col0;
-                if (sg.row_scale) rs.sc[s] = __ldg(sg.row_scale + r);
-            }
-        }
-    }
-    rs.c0[4] = run;
-
+    for (int i = tid; i < nbias; i += CW_THREADS) sBias[i] = __ldg(A.bias + i);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
-    const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
-    const uint32_t op_hi_a = smem_u32(sOp), op_lo_a = op_hi_a + OP_PLANE;
     const uint32_t ring_a = smem_u32(sRing);
-
-    // weight piece stream (thread 0 only): global piece counters
-    uint32_t g_next = 0;        // next piece to request
-    uint32_t g_use = 0;         // next piece to consume
-    size_t w_off = 0;           // byte offset of piece g_next in A.W
     const uint32_t pieces[3] = {(uint32_t)(A.chunks0 / 2), (uint32_t)(A.n[0] / 16), nl == 3 ? (uint32_t)(A.n[1] / 16) : 0u};
-    const uint32_t g_total = pieces[0] + pieces[1] + pieces[2];
-    auto piece_bytes = [&](uint32_t g) -> uint32_t {
-        const int N = g < pieces[0] ? A.n[0] : (g < pieces[0] + pieces[1] ? A.n[1] : A.n[2]);
-        return (uint32_t)N * 64u;
-    };
-    auto prefetch = [&]() {     // keep up to RING-1 pieces in flight beyond the one being consumed
-        while (g_next < g_total && g_next < g_use + RING) {
-            const uint32_t slot = g_next % RING;
-            if (g_next >= (uint32_t)RING) mbar_wait(smem_u32(&s_bar[RING_MAX + slot]), ((g_next / RING) - 1) & 1);
-            const uint32_t bytes = piece_bytes(g_next);
-            mbar_expect_tx(smem_u32(&s_bar[slot]), bytes);
-            bulk_g2s(ring_a + slot * SLOT_BYTES, A.W + w_off, bytes, smem_u32(&s_bar[slot]));
-            w_off += bytes;
-            ++g_next;
-        }
-    };
-    if (tid == 0) prefetch();
 
-    uint32_t acc_phase = 0;
-    // issue `np` K=16 pieces of a layer of width N, A operand chunks starting at chunk a0 of the operand buffer
-    auto mma_pieces = [&](int np, int a0, int N, bool accumulate) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t idesc = ch_idesc(N);
-            const uint32_t a_lbo = CTM * 16, w_lbo = (uint32_t)N * 16;
-            for (int p = 0; p < np; ++p) {
-                prefetch();
-                const uint32_t slot = g_use % RING;
-                mbar_wait(smem_u32(&s_bar[slot]), (g_use / RING) & 1);
+    if (warp < CW_EPI_WARPS) {
+        // ================= epilogue warps ======================================================================
+        const int eg = warp >> 2, wq = warp & 3;             // group (alternate blocks), TMEM lane quadrant
+        const int rt = wq * 32 + lane;                       // row inside the tile = TMEM lane
+        const uint32_t lane_base = ((uint32_t)(wq * 32) << 16);
+        uint32_t accph = 0;                                  // phase bits of s_accf[4]
+        int L = 0;                                           // layers completed by this CTA -> accumulator L & BM
+        int hs = 0; uint32_t hpar = 0; int hq = 0;           // ring H position, global block counter
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long r = (long long)tile * CTM + rt;
+            for (int l = 0; l + 1 < nl; ++l, ++L) {
+                const int b = L & BM, N = A.n[l];
+                const float* bb = sBias + (l == 0 ? 0 : A.n[0]);
+                mbar_wait(smem_u32(&s_accf[b]), (accph >> b) & 1); accph ^= 1u << b;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t w_hi = ring_a + slot * SLOT_BYTES, w_lo = w_hi + 2 * w_lbo;
-                const uint64_t ah = umma_desc(op_hi_a + (a0 + 2 * p) * a_lbo, a_lbo, 128);
-                const uint64_t al = umma_desc(op_lo_a + (a0 + 2 * p) * a_lbo, a_lbo, 128);
-                const uint64_t wh = umma_desc(w_hi, w_lbo, 128);
-                const uint64_t wl = umma_desc(w_lo, w_lbo, 128);
-                umma_bf16(tmem, ah, wh, idesc, (accumulate || p > 0) ? 1u : 0u);
-                umma_bf16(tmem, al, wh, idesc, 1u);
-                umma_bf16(tmem, ah, wl, idesc, 1u);
-                umma_commit(smem_u32(&s_bar[RING_MAX + slot]));
-                ++g_use;
+                for (int c0 = 0; c0 < N; c0 += 32, ++hq) {
+                    if ((hq & 1) == eg) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem + lane_base + b * ACC + c0, v);
+                        mbar_wait(smem_u32(&s_hempty[hs]), hpar ^ 1);
+                        uint4* h_hi = reinterpret_cast<uint4*>(sH + (size_t)hs * CW_STAGE_BYTES);
+                        uint4* h_lo = h_hi + 4 * CTM;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) {
+                            if (c0 + ch * 8 < N) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(bb + c0 + ch * 8);
+                                const float4 b1 = *reinterpret_cast<const float4*>(bb + c0 + ch * 8 + 4);
+                                const float x[8] = {fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, 0.f),
+                                                    fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, 0.f),
+                                                    fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, 0.f),
+                                                    fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, 0.f)};
+                                split_store8(x, h_hi + ch * CTM + rt, h_lo + ch * CTM + rt);
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&s_hfull[hs]));
+                    }
+                    if (++hs == HS) { hs = 0; hpar ^= 1; }
+                }
             }
-            umma_commit(bar_acc);
-            prefetch();
+            // ---- last layer: the groups take alternate 32-column chunks --------------------------------------------
+            const int b = L & BM;
+            ++L;
+            mbar_wait(smem_u32(&s_accf[b]), (accph >> b) & 1); accph ^= 1u << b;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + lane_base + b * ACC;
+            const float* b3 = sBias + A.n[0] + (nl == 3 ? A.n[1] : 0);
+            const int act = A.act;
+            const int pos = lane % KSEG;
+            const long long grp = r / KSEG;
+            constexpr int PER = 32 / KSEG;
+            float a_w = 1.f;
+            if (A.mode == EPI_ATTN) {
+                float x1 = -CUDART_INF_F;
+                for (int c0 = eg * 32; c0 < cout; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld32(acc + c0, v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < cout) x1 = fmaxf(x1, fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f));
+                }
+                sX[eg * CTM + rt] = x1;
+                asm volatile("bar.sync 1, 256;" ::: "memory");             // the 8 epilogue warps
+                x1 = fmaxf(x1, sX[(eg ^ 1) * CTM + rt]);
+                float gm = x1;
+#pragma unroll
+                for (int o = KSEG / 2; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+                const float ex = expf(x1 - gm);
+                float sm = ex;
+#pragma unroll
+                for (int o = KSEG / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                a_w = ex / sm;
+                if (A.a && eg == 0) A.a[r] = a_w;
+            }
+            const bool vec_ok = A.Y && ((cout & 3) == 0);
+            float* tile_w = sTile + warp * (32 * CW_TP);
+            for (int c0 = eg * 32; c0 < cout; c0 += 64) {
+                uint32_t v[32];
+                float f[32];
+                tmem_ld32(acc + c0, v);
+                if (act == HRN_ACT_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f) * a_w : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? act_fn(__uint_as_float(v[e]) + b3[c0 + e], act) : 0.f;
+                }
+                if (A.Y) {
+                    if (vec_ok && AW.use_tile && c0 + 32 <= cout) {
+                        // transpose through shared memory: a store instruction covers 4 rows x 128 contiguous bytes
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(tile_w + lane * CW_TP + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+                        __syncwarp();
+                        const int piece = lane & 7;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = (lane >> 3) + 4 * i;
+                            const float4 t = *reinterpret_cast<const float4*>(tile_w + rl * CW_TP + piece * 4);
+                            *reinterpret_cast<float4*>(A.Y + ((long long)tile * CTM + wq * 32 + rl) * A.ldy + c0 + piece * 4) = t;
+                        }
+                        __syncwarp();
+                    } else {
+                        float* yr = A.Y + r * A.ldy + c0;
+                        if (vec_ok) {
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4)
+                                if (c0 + e < cout) *reinterpret_cast<float4*>(yr + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) if (c0 + e < cout) yr[e] = f[e];
+                        }
+                    }
+                }
+                if (A.mode != EPI_STORE && A.G) {
+                    if (A.mode == EPI_GROUPMAX) {
+                        if (act != HRN_ACT_RELU) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) if (c0 + e >= cout) f[e] = -CUDART_INF_F;
+                        }
+                        seg_transpose_reduce<KSEG, true>(f, lane);
+                    } else {
+                        seg_transpose_reduce<KSEG, false>(f, lane);
+                    }
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const int c = c0 + pos * PER + i;
+                        if (c < cout) A.G[grp * cout + c] = f[i];
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_fin[b]));
         }
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    };
-
-    // ---- layer 1: virtual rows -> operand buffer, in passes of <= 32 chunks --------------------------------
-    for (int c_base = 0; c_base < A.chunks0; c_base += OPC_MAX) {
-        const int nc = min(OPC_MAX, A.chunks0 - c_base);
-        for (int c4 = 0; c4 < nc; c4 += 4) {
-            float4 v[8];
-            float sc[4];
+    } else if (warp < CW_EPI_WARPS + CW_PROD_WARPS) {
+        // ================= producers (same lane mapping as layer_ws_kernel, mlp_tc.cu) ==========================
+        const hrn_rows_t& in = A.in;
+        const int pw = warp - CW_EPI_WARPS;
+        const int rsub = lane & 7, hf = (lane >> 3) & 1, cl = lane >> 4;
+        int c0s[5], chs[4];
+        {
+            int run = 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) ch_load_chunk(rs, c_base + c4 + c, v[2 * c], v[2 * c + 1], sc[c]);
+            for (int s = 0; s < 4; ++s) {
+                chs[s] = 0; c0s[s] = 0x7fffffff;
+                if (s < in.n_seg) { c0s[s] = run; run += (in.seg[s].channels + 7) >> 3; chs[s] = in.seg[s].channels; }
+            }
+            c0s[4] = run;
+        }
+        int direct_mask = 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c4 + c < nc) {
-                    const float s = sc[c];
-                    const float x[8] = {v[2 * c].x * s, v[2 * c].y * s, v[2 * c].z * s, v[2 * c].w * s,
-                                        v[2 * c + 1].x * s, v[2 * c + 1].y * s, v[2 * c + 1].z * s, v[2 * c + 1].w * s};
-                    split_store8(x, op_hi + (c4 + c) * CTM + tid, op_lo + (c4 + c) * CTM + tid);
+        for (int s = 0; s < 4; ++s) if (s < in.n_seg && in.seg[s].mode == HRN_SEG_DIRECT) direct_mask |= 1 << s;
+        const float* rp[2][4];
+        float rsc[2][4];
+        float sc[RAW][4];
+        int ltile = blockIdx.x, li = 0;                      // copy cursor: tile, stage within the tile
+        int gs = 0; uint32_t gpar = 0;                       // ring G position
+        uint8_t* raw0 = sRaw + (size_t)(pw * 4) * 512 + lane * 16;
+        auto resolve = [&](int tile) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const unsigned ru = (unsigned)tile * CTM + pw * 16 + g * 8 + rsub;     // rows < 2^31 (checked on the host)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    rp[g][s] = nullptr; rsc[g][s] = 1.f;
+                    if (s < in.n_seg) {
+                        const hrn_seg_t sg = in.seg[s];
+                        const long long sr = sg.mode == HRN_SEG_DIRECT ? (long long)ru
+                                           : sg.mode == HRN_SEG_BROADCAST ? (long long)(ru / (unsigned)in.group)
+                                           : (long long)(ru / (unsigned)in.rows_per_batch) * in.src_rows_per_batch + in.gather_idx[ru];
+                        rp[g][s] = sg.ptr + sr * sg.ld + sg.col0;
+                        if (sg.row_scale) rsc[g][s] = __ldg(sg.row_scale + ru);
+                    }
+                }
+            }
+        };
+        auto copy_piece = [&](const float* const (&pp)[4], const float (&ps)[4], int cg, uint8_t* dst, float& osc) {
+            int sgi = 0;
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if (cg >= c0s[q]) sgi = q;
+            const float* p = pp[0]; int cs = c0s[0], chn = chs[0]; osc = ps[0];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if (sgi == q) { p = pp[q]; cs = c0s[q]; chn = chs[q]; osc = ps[q]; }
+            const int ch0 = ((cg - cs) << 3) + 4 * hf;
+            const bool ok = p != nullptr && cg < c0s[4] && chn - ch0 >= 4;
+            const void* src = ok ? (const void*)(p + ch0) : (const void*)A.W;
+            if (direct_mask >> sgi & 1)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        };
+        auto issue = [&](int slot, float (&ss)[4]) {
+            if (ltile < n_tiles) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        copy_piece(rp[g], rsc[g], li * 4 + 2 * j + cl, raw0 + (size_t)slot * CW_STAGE_BYTES + (g * 2 + j) * 512, ss[2 * g + j]);
+                if (++li == n_st0) {
+                    li = 0; ltile += gridDim.x;
+                    if (ltile < n_tiles) resolve(ltile);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto fill = [&](int slot, const float (&ss)[4]) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RAW - 1) : "memory");
+            float4 vv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) vv[e] = *reinterpret_cast<const float4*>(raw0 + (size_t)slot * CW_STAGE_BYTES + e * 512);
+            mbar_wait_backoff(smem_u32(&s_gempty[gs]), gpar ^ 1);
+            uint4* g_hi = reinterpret_cast<uint4*>(sG + (size_t)gs * CW_STAGE_BYTES);
+            uint4* g_lo = g_hi + 4 * CTM;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 t = vv[2 * g + j];
+                    const float s_ = ss[2 * g + j];
+                    const float x0 = t.x * s_, x1 = t.y * s_, x2 = t.z * s_, x3 = t.w * s_;
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
+                    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
+                    const uint32_t H0 = *reinterpret_cast<const uint32_t*>(&h0), H1 = *reinterpret_cast<const uint32_t*>(&h1);
+                    const uint32_t L0 = *reinterpret_cast<const uint32_t*>(&l0), L1 = *reinterpret_cast<const uint32_t*>(&l1);
+                    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hf ? H0 : L0, 8);
+                    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, hf ? H1 : L1, 8);
+                    const int slot_a = (2 * j + cl) * CTM + pw * 16 + g * 8 + rsub;
+                    if (hf == 0) g_hi[slot_a] = make_uint4(H0, H1, r0, r1);
+                    else         g_lo[slot_a] = make_uint4(r0, r1, L0, L1);
+                }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_gfull[gs]));
+            if (++gs == GS) { gs = 0; gpar ^= 1; }
+        };
+        int my_tiles = 0;
+        if ((int)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+        const int total = my_tiles * n_st0;
+        if (total > 0) resolve(ltile);
+#pragma unroll
+        for (int d = 0; d < RAW; ++d) issue(d, sc[d]);
+        for (int q = 0; q < total; q += RAW) {
+#pragma unroll
+            for (int d = 0; d < RAW; ++d) {
+                if (q + d < total) { fill(d, sc[d]); issue(d, sc[d]); }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp == CW_EPI_WARPS + CW_PROD_WARPS) {
+        // ================= MMA issue ==============================================================================
+        // One thread feeds the tensor core; its instruction stream per K=16 piece is kept minimal (no divisions, shared
+        // memory descriptors = hoisted constant + 14-bit address field): at ~80 instructions per piece this thread, not
+        // the tensor pipe, was the limiter of the whole kernel.
+        if (lane == 0) {
+            constexpr uint64_t DESC_FIXED = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);          // SBO = 128 B, version bit
+            const uint64_t a_desc0 = DESC_FIXED | ((uint64_t)((CTM * 16) >> 4) << 16);             // LBO = 2048 B
+            const uint32_t g_a = smem_u32(sG) >> 4, h_a = smem_u32(sH) >> 4;                        // ring bases, 16-byte units
+            constexpr uint32_t ST16 = CW_STAGE_BYTES >> 4, LO16 = (4 * CTM * 16) >> 4, P16 = (2 * CTM * 16) >> 4;
+            const uint32_t slot16 = SLOT_BYTES >> 4;
+            const uint32_t wfull0 = smem_u32(&s_wfull[0]), wempty0 = smem_u32(&s_wempty[0]);
+            uint32_t ws = 0, wpar = 0;                        // weight ring position / parity
+            int gs = 0, hs = 0; uint32_t gpar = 0, hpar = 0;  // operand ring positions
+            int L = 0, ti = 0;
+            uint32_t fin_pending = 0, finph = 0;              // per accumulator: last result not yet drained by the epilogue / phase
+            auto claim = [&](int b) {                         // before the first MMA of a layer into accumulator b
+                if (fin_pending >> b & 1) {
+                    mbar_wait(smem_u32(&s_fin[b]), (finph >> b) & 1);
+                    finph ^= 1u << b; fin_pending &= ~(1u << b);
+                }
+            };
+            // one K=16 piece: A = chunks [2p, 2p+2) of the operand stage whose hi plane starts at a16 (16-byte units)
+            auto piece_mma = [&](uint32_t a16, uint64_t w_desc0, uint32_t wlo16, uint32_t idesc, uint32_t d, uint32_t accumulate) {
+                mbar_wait(wfull0 + 8 * ws, wpar);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t w16 = (ring_a >> 4) + ws * slot16;
+                const uint64_t ah = a_desc0 | a16, al = a_desc0 | (a16 + LO16);
+                const uint64_t wh = w_desc0 | w16, wl = w_desc0 | (w16 + wlo16);
+                umma_bf16(d, ah, wh, idesc, accumulate);
+                umma_bf16(d, al, wh, idesc, 1u);
+                umma_bf16(d, ah, wl, idesc, 1u);
+                umma_commit(wempty0 + 8 * ws);
+                if (++ws == (uint32_t)RING) { ws = 0; wpar ^= 1; }
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                // ---- layer 1: input stages as the producers deliver them ----
+                {
+                    const int b = L & BM;
+                    const uint32_t d = tmem + b * ACC;
+                    claim(b);
+                    if (nl == 1) fin_pending |= 1u << b;
+                    const uint32_t N = (uint32_t)A.n[0], idesc = ch_idesc(A.n[0]);
+                    const uint64_t w_desc0 = DESC_FIXED | ((uint64_t)N << 16);                      // LBO = N * 16 B
+                    const uint32_t wlo16 = 2 * N;                                                   // lo plane: + 2 * N * 16 B
+                    int left = (int)pieces[0];
+                    for (int s = 0; s < n_st0; ++s, left -= 2) {
+                        mbar_wait(smem_u32(&s_gfull[gs]), gpar);
+                        const uint32_t a16 = g_a + gs * ST16;
+                        piece_mma(a16, w_desc0, wlo16, idesc, d, s > 0 ? 1u : 0u);
+                        if (left > 1) piece_mma(a16 + P16, w_desc0, wlo16, idesc, d, 1u);
+                        umma_commit(smem_u32(&s_gempty[gs]));
+                        if (++gs == GS) { gs = 0; gpar ^= 1; }
+                    }
+                    umma_commit(smem_u32(&s_accf[b]));
+                    ++L;
+                }
+                // ---- later layers: 32-column blocks as the epilogue warps convert them ----
+                for (int l = 1; l < nl; ++l, ++L) {
+                    const int b = L & BM;
+                    const uint32_t d = tmem + b * ACC;
+                    claim(b);
+                    if (l == nl - 1) fin_pending |= 1u << b;
+                    const uint32_t N = (uint32_t)A.n[l], idesc = ch_idesc(A.n[l]);
+                    const uint64_t w_desc0 = DESC_FIXED | ((uint64_t)N << 16);
+                    const uint32_t wlo16 = 2 * N;
+                    int left = A.n[l - 1] / 16;
+                    for (int j = 0; left > 0; ++j, left -= 2) {
+                        mbar_wait(smem_u32(&s_hfull[hs]), hpar);
+                        const uint32_t a16 = h_a + hs * ST16;
+                        piece_mma(a16, w_desc0, wlo16, idesc, d, j > 0 ? 1u : 0u);
+                        if (left > 1) piece_mma(a16 + P16, w_desc0, wlo16, idesc, d, 1u);
+                        umma_commit(smem_u32(&s_hempty[hs]));
+                        if (++hs == HS) { hs = 0; hpar ^= 1; }
+                    }
+                    umma_commit(smem_u32(&s_accf[b]));
                 }
             }
         }
-        mma_pieces(nc / 2, 0, n1, c_base > 0);
-    }
-    // accumulator -> relu(x + b) -> operand (in place)
-    auto epi_to_operand = [&](int N, const float* bb) {
-        for (int c0 = 0; c0 < N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_base + c0, v);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                if (c0 + ch * 8 < N) {
-                    float x[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[ch * 8 + e]) + bb[c0 + ch * 8 + e], 0.f);
-                    split_store8(x, op_hi + (c0 / 8 + ch) * CTM + tid, op_lo + (c0 / 8 + ch) * CTM + tid);
-                }
-            }
-        }
-    };
-    epi_to_operand(n1, sBias);
-    mma_pieces(n1 / 16, 0, A.n[1], false);
-    if (nl == 3) {
-        epi_to_operand(A.n[1], sBias + n1);
-        mma_pieces(A.n[1] / 16, 0, n3, false);
-    }
-
-    // ---- final epilogue -----------------------------------------------------------------------------------------
-    const float* b3 = sBias + n1 + (nl == 3 ? A.n[1] : 0);
-    const int act = A.act;
-    const int pos = lane % KSEG;                       // position inside the group
-    const long long grp = r / KSEG;
-    constexpr int PER = 32 / KSEG;                     // reduced columns per lane and 32-column chunk
-    float a_w = 1.f;
-    if (A.mode == EPI_ATTN) {
-        float x1 = -CUDART_INF_F;
-        for (int c0 = 0; c0 < cout; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_base + c0, v);
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-                if (c0 + e < cout) x1 = fmaxf(x1, fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f));   // EPI_ATTN: ReLU only
-        }
-        float gm = x1;
-#pragma unroll
-        for (int o = KSEG / 2; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-        const float ex = expf(x1 - gm);
-        float sm = ex;
-#pragma unroll
-        for (int o = KSEG / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-        a_w = ex / sm;
-        if (rvalid && A.a) A.a[r] = a_w;
-    }
-    const bool vec_ok = A.Y && ((cout & 3) == 0);
-    for (int c0 = 0; c0 < cout; c0 += 32) {
-        uint32_t v[32];
-        float f[32];
-        tmem_ld32(tmem + lane_base + c0, v);
-        if (act == HRN_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f) * a_w : 0.f;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? act_fn(__uint_as_float(v[e]) + b3[c0 + e], act) : 0.f;
-        }
-        if (rvalid && A.Y) {
-            float* yr = A.Y + r * A.ldy + c0;
-            if (vec_ok) {
-#pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    if (c0 + e < cout) *reinterpret_cast<float4*>(yr + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) if (c0 + e < cout) yr[e] = f[e];
-            }
-        }
-        if (A.mode != EPI_STORE && A.G) {
-            if (A.mode == EPI_GROUPMAX) {
-                if (act != HRN_ACT_RELU) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) if (c0 + e >= cout) f[e] = -CUDART_INF_F;
-                }
-                seg_transpose_reduce<KSEG, true>(f, lane);
-            } else {
-                seg_transpose_reduce<KSEG, false>(f, lane);
-            }
-            if (rvalid) {
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const int c = c0 + pos * PER + i;
-                    if (c < cout) A.G[grp * cout + c] = f[i];
+    } else {
+        // ================= weight stream ==========================================================================
+        if (lane == 0) {
+            uint32_t ws = 0, wpar = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint8_t* src = A.W;
+                for (int l = 0; l < nl; ++l) {
+                    const uint32_t bytes = (uint32_t)A.n[l] * 64u;
+                    for (uint32_t p = 0; p < pieces[l]; ++p) {
+                        mbar_wait_backoff(smem_u32(&s_wempty[ws]), wpar ^ 1);
+                        mbar_expect_tx(smem_u32(&s_wfull[ws]), bytes);
+                        bulk_g2s(ring_a + ws * SLOT_BYTES, src, bytes, smem_u32(&s_wfull[ws]));
+                        src += bytes;
+                        if (++ws == (uint32_t)RING) { ws = 0; wpar ^= 1; }
+                    }
                 }
             }
         }
@@ -329,7 +497,7 @@ __global__ void __launch_bounds__(CTM) chain3_kernel(const ChainArgs A) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(A.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 }  // namespace
@@ -368,32 +536,54 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
     A.chunks0 = chunks0; A.mode = mode; A.kseg = kseg;
     int maxn = n1 > n2 ? n1 : n2;
     if (nl == 3 && n3 > maxn) maxn = n3;
-    int opc = chunks0 < OPC_MAX ? chunks0 : OPC_MAX;
-    if (n1 / 8 > opc) opc = n1 / 8;
-    if (nl == 3 && n2 / 8 > opc) opc = n2 / 8;
-    A.opc = opc;
     A.slot_bytes = maxn * 64;
-    A.tmem_cols = 32;
-    while (A.tmem_cols < maxn) A.tmem_cols <<= 1;
-    // 4 weight slots normally; 2 when that lets two CTAs share an SM (<= 113 KB each) -- overlapping two tiles'
-    // load / MMA / epilogue phases is worth more than look-ahead depth
-    const int fixed = 2 * opc * CTM * 16 + 3 * 256 * 4 + 64;
-    int ring = RING_MAX;
-    if (fixed + RING_MAX * A.slot_bytes > 113 * 1024 && fixed + 2 * A.slot_bytes <= 113 * 1024 && A.tmem_cols <= 256) ring = 2;
-    A.ring = ring;
-    const int CH_SMEM = fixed + ring * A.slot_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
-        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
-        HRN_CUDA(cudaFuncSetAttribute(chain3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
-        attr_set = true;
-    }
-    const int grid = (int)(rows / CTM);
     cudaStream_t st = (cudaStream_t)stream;
-    if (kseg == 8) chain3_kernel<8><<<grid, CTM, CH_SMEM, st>>>(A);
-    else if (kseg == 16) chain3_kernel<16><<<grid, CTM, CH_SMEM, st>>>(A);
-    else chain3_kernel<32><<<grid, CTM, CH_SMEM, st>>>(A);
-    HRN_LAUNCH_CHECK();
-    return HRN_OK;
+    if (rows >= 0x7fffffffLL) return HRN_ERR_UNSUPPORTED;        // 32-bit row arithmetic in the producers
+    {
+        // shared memory: ring G + ring H (16 KB stages) | weight ring | raw fp32 ring | biases | optional store tile
+        const int budget = 227 * 1024 - 1024;
+        const bool narrow = maxn <= 128;
+        const int raw = narrow ? 4 : 2;
+        const int tile_b = Y ? CW_TILE_BYTES : 0;
+        int gs = 3, hs = 3, fixed = 0, ring = 0, use_tile = Y ? 1 : 0;
+        for (int attempt = 0; attempt < 4; ++attempt) {            // keep >= 4 weight slots: shrink the operand rings, then drop the tile
+            gs = attempt >= 1 ? 2 : 3; hs = attempt >= 2 ? 2 : 3;
+            use_tile = (Y && attempt < 3) ? 1 : 0;
+            fixed = (gs + hs + raw) * CW_STAGE_BYTES + 3 * 256 * 4 + 2 * CTM * 4;
+            ring = (budget - fixed - (use_tile ? tile_b : 0)) / A.slot_bytes;
+            if (ring >= 4) break;
+        }
+        if (ring > CW_RING_MAX) ring = CW_RING_MAX;
+        A.ring = ring;
+        ChainWsArgs AW;
+        AW.c = A;
+        AW.n_tiles = (int)(rows / CTM);
+        AW.use_tile = use_tile;
+        AW.gs = gs; AW.hs = hs;
+        AW.acc_stride = narrow ? 128 : 256;
+        AW.nbuf = 512 / AW.acc_stride;
+        const int smem_ws = fixed + ring * A.slot_bytes + (use_tile ? CW_TILE_BYTES : 0);
+        static bool attr_ws = false;
+        if (!attr_ws) {
+            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            attr_ws = true;
+        }
+        const int grid_ws = AW.n_tiles < 148 ? AW.n_tiles : 148;
+        if (narrow) {
+            if (kseg == 8) chain_ws_kernel<8, 4><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
+            else if (kseg == 16) chain_ws_kernel<16, 4><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
+            else chain_ws_kernel<32, 4><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
+        } else {
+            if (kseg == 8) chain_ws_kernel<8, 2><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
+            else if (kseg == 16) chain_ws_kernel<16, 2><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
+            else chain_ws_kernel<32, 2><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
+        }
+        HRN_LAUNCH_CHECK();
+        return HRN_OK;
+    }
 }
