@@ -48,20 +48,24 @@ struct LevelCfg {
     static constexpr int B_D1 = 0, B_D2 = B_D1 + C1, B_D3 = B_D2 + C2, B_X1 = B_D3 + CO, B_X2 = B_X1 + C1,
                          B_X3 = B_X2 + C2, B_M1 = B_X3 + CO, B_M2 = B_M1 + CMID, B_COUNT = B_M2 + CD;
     static constexpr int OPC = cmax(cmax(C1, C2), cmax(CO, CMID)) / 8;   // chunks of the in-place operand buffer
-    static constexpr int G_BYTES = 2 * (KG / 8) * TMR * 16;
+    // level 1 (no gathered features): the grouped input is 4 numbers per row, rebuilt from registers before each of the
+    // two first layers, so it lives in the operand buffer instead of its own region
+    static constexpr bool G_ALIAS = (CIN == 0);
+    static constexpr int G_BYTES = G_ALIAS ? 0 : 2 * (KG / 8) * TMR * 16;
     static constexpr int OP_BYTES = 2 * OPC * TMR * 16;
     static constexpr int CW = cmax(CO, CD);
     static constexpr int SMEM = W_SMEM + B_COUNT * 4 + G_BYTES + OP_BYTES + 2 * 4 * CW * 4 + 256;
-    // TMEM columns: [acc0 | accM share] [E] [X1 | descriptor]
-    static constexpr int T_ACC0 = 0;
-    static constexpr int T_ACCE = cmax(cmax(C1, C2), CMID);
-    static constexpr int T_ACCX = T_ACCE + CO;
-    static constexpr int T_USED = T_ACCX + cmax(CO, CD);
+    // TMEM columns: [E] [work: hidden layers / mlp1 accumulator / X1 / descriptor].  One work region is enough: every
+    // result in it is drained (to the operand buffer or to HBM) before the next layer that targets it is issued.
+    static constexpr int T_ACCE = 0;
+    static constexpr int T_ACC0 = CO;
+    static constexpr int T_ACCX = CO;
+    static constexpr int T_USED = CO + cmax(cmax(cmax(C1, C2), CMID), cmax(CO, CD));
     static constexpr int T_COLS = T_USED <= 32 ? 32 : T_USED <= 64 ? 64 : T_USED <= 128 ? 128 : T_USED <= 256 ? 256 : 512;
     static constexpr int WPG = KNBR / 32;                           // warps per keypoint group (1 or 2)
     // RESIDENT: NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns,
-    // all sharing ONE resident copy of the weights (3 tiles in flight per SM instead of 2 CTAs x 1)
-    static constexpr int NG = RESIDENT ? 3 : 1;
+    // all sharing ONE resident copy of the weights (4 tiles in flight per SM instead of 2 CTAs x 1)
+    static constexpr int NG = RESIDENT ? 4 : 1;
     static constexpr int GRP_SMEM = G_BYTES + OP_BYTES + 2 * 4 * CW * 4;
     static constexpr int SMEM_NG = W_SMEM + B_COUNT * 4 + NG * GRP_SMEM + 256;
     static constexpr int T_COLS_NG = NG * T_USED <= 256 ? 256 : 512;
@@ -89,6 +93,19 @@ __device__ __forceinline__ void issue_layer(uint32_t a_hi, uint32_t a_lo, int K,
         umma_bf16(tmem_d, ah, wh, idesc, (accumulate || k > 0) ? 1u : 0u);
         umma_bf16(tmem_d, al, wh, idesc, 1u);
         umma_bf16(tmem_d, ah, wl, idesc, 1u);
+    }
+}
+
+// f[e] = relu(acc[e] + bias[e]) for 32 consecutive columns; the biases come from shared memory as 8 x 16-byte loads
+// (one scalar LDS per element was a quarter of the epilogue's instruction count)
+__device__ __forceinline__ void bias_relu32(const uint32_t (&v)[32], const float* __restrict__ bb, float (&f)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * q);
+        f[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
+        f[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
+        f[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
+        f[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
     }
 }
 
@@ -171,7 +188,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         for (int i = cta_tid; i < Cfg::W_BYTES / 16; i += TMR * NG)
             reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
     for (int i = cta_tid; i < Cfg::B_COUNT; i += TMR * NG) sB[i] = __ldg(biases + i);
-    {   // K padding chunks of G stay zero forever
+    if (!Cfg::G_ALIAS) {   // K padding chunks of G stay zero forever
         uint4* g_hi = reinterpret_cast<uint4*>(sG);
         uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
         for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {
@@ -189,12 +206,13 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     const uint32_t tmem_all = s_tmem;
     const uint32_t tmem = tmem_all + grp_id * Cfg::T_USED;                // this group's accumulator columns
     const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
-    const uint32_t aG_hi = smem_u32(sG), aG_lo = aG_hi + (Cfg::KG / 8) * TMR * 16;
     const uint32_t aOp_hi = smem_u32(sOp), aOp_lo = aOp_hi + Cfg::OPC * TMR * 16;
-    uint4* g_hi = reinterpret_cast<uint4*>(sG);
-    uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
+    const uint32_t aG_hi = Cfg::G_ALIAS ? aOp_hi : smem_u32(sG);
+    const uint32_t aG_lo = Cfg::G_ALIAS ? aOp_lo : aG_hi + (Cfg::KG / 8) * TMR * 16;
     uint4* op_hi = reinterpret_cast<uint4*>(sOp);
     uint4* op_lo = op_hi + Cfg::OPC * TMR;
+    uint4* g_hi = Cfg::G_ALIAS ? op_hi : reinterpret_cast<uint4*>(sG);
+    uint4* g_lo = Cfg::G_ALIAS ? op_lo : g_hi + (Cfg::KG / 8) * TMR;
 
     // operand ready in smem -> one thread issues layer `li` -> everybody waits for the accumulator
     auto run_layer = [&](uint32_t a_hi, uint32_t a_lo, int li, int tcol, bool acc) {
@@ -222,12 +240,13 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     auto epi_to_operand = [&](int tcol, int Nn, const float* bb) {
         for (int c0 = 0; c0 < Nn; c0 += 32) {
             uint32_t v[32];
+            float f[32];
             tmem_ld32(tmem + lane_base + tcol + c0, v);
+            bias_relu32(v, bb + c0, f);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-                float x[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[ch * 8 + e]) + bb[c0 + ch * 8 + e], 0.f);
+                const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
+                                    f[ch * 8 + 6], f[ch * 8 + 7]};
                 split_store8(x, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
             }
         }
@@ -265,10 +284,18 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
                 }
             }
         }
-        {
+        auto store_geometry = [&]() {
             const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 0.f, 0.f, 0.f, 0.f};
             split_store8(x, g_hi + (CIN / 8) * TMR + tid, g_lo + (CIN / 8) * TMR + tid);
-        }
+            if (Cfg::G_ALIAS) {
+#pragma unroll
+                for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {
+                    g_hi[c * TMR + tid] = make_uint4(0, 0, 0, 0);
+                    g_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
+                }
+            }
+        };
+        store_geometry();
         // ---- detector chain ------------------------------------------------------------------------------------
         run_layer(aG_hi, aG_lo, 0, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_D1);
@@ -281,7 +308,11 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCE + c0, v);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) x1 = fmaxf(x1, __uint_as_float(v[e]) + sB[Cfg::B_D3 + c0 + e]);
+            for (int q = 0; q < 8; ++q) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_D3 + c0 + 4 * q);
+                x1 = fmaxf(x1, fmaxf(fmaxf(__uint_as_float(v[4 * q]) + b4.x, __uint_as_float(v[4 * q + 1]) + b4.y),
+                                     fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, __uint_as_float(v[4 * q + 3]) + b4.w)));
+            }
         }
         float gmax = hrn_warp_max(x1);
         if (WPG == 2) {
@@ -300,6 +331,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         const float a = ex / s0;
         if (leader && lane < 3) out_xyz[bm * 3 + lane] = (lane == 0 ? s1 : (lane == 1 ? s2 : s3)) / s0;
         // ---- descriptor chain ----------------------------------------------------------------------------------
+        if (Cfg::G_ALIAS) store_geometry();          // the operand buffer has been reused since the detector's first layer
         run_layer(aG_hi, aG_lo, 3, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_X1);
         run_layer(aOp_hi, aOp_lo, 4, Cfg::T_ACC0, false);
@@ -310,8 +342,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCX + c0, v);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = fmaxf(__uint_as_float(v[e]) + sB[Cfg::B_X3 + c0 + e], 0.f);
+            bias_relu32(v, sB + Cfg::B_X3 + c0, f);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
@@ -336,8 +367,9 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCE + c0, v);
+            bias_relu32(v, sB + Cfg::B_D3 + c0, f);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = fmaxf(__uint_as_float(v[e]) + sB[Cfg::B_D3 + c0 + e], 0.f) * a;
+            for (int e = 0; e < 32; ++e) f[e] *= a;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
@@ -361,8 +393,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCX + c0, v);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = fmaxf(__uint_as_float(v[e]) + sB[Cfg::B_M2 + c0 + e], 0.f);
+            bias_relu32(v, sB + Cfg::B_M2 + c0, f);
             const float cm = warp_transpose_reduce<true>(f, lane);
             sCol[warp * CW + c0 + lane] = cm;
         }
