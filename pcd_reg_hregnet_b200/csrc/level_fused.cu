@@ -11,14 +11,17 @@
 // CTA = 128 rows = 128/k keypoints x k neighbours; thread t <-> row t <-> TMEM lane t; persistent over tiles.
 // Every layer: A operand in smem -> tcgen05.mma (bf16 hi/lo split of both operands, 3 MMAs per k-step, fp32
 // accumulate in TMEM) -> tcgen05.ld -> bias+ReLU -> bf16 hi/lo split -> written back IN PLACE as the next layer's
-// A operand.  Chain per tile:
-//   G -d1-> C1 -d2-> C2 -d3-> E(CO, stays in TMEM)   | max_c, softmax over the k neighbours, keypoint
-//   G -x1-> C1 -x2-> C2 -x3-> X1(CO)                 | column max over the group
+// A operand.  Chain per tile (9 MMA steps):
+//   G -[d1;x1]-> C1d | C1x   (the two first layers share their input: ONE step with the weights stacked along N)
+//   C1d -d2-> C2 -d3-> E(CO, stays in TMEM)          | max_c, softmax over the k neighbours, keypoint
+//   C1x -x2-> C2 -x3-> X1(CO)                        | column max over the group
 //   mlp1 = Wb.X1 + Wa.max_k(X1) + Wc.(E*a)  (three K-segments accumulated in TMEM) -> CMID -mlp2-> CD -> max_k
-// Weights (bf16 hi/lo UMMA tiles, execution order):
-//   level 1 (60 KB): RESIDENT in shared memory, two CTAs per SM overlap each other's MMA and epilogue phases;
-//   level 2 (264 KB): STREAMED layer by layer from L2 through a 2-slot ring with cp.async.bulk + mbarrier, the copy
-//   of layer l+2 is issued when layer l's MMAs have drained its slot.
+// Several independent 128-thread groups per CTA, each with its own tile, operand buffer and TMEM columns, overlap each
+// other's MMA / epilogue phases.  Weights (bf16 hi/lo UMMA tiles, execution order):
+//   level 1 (60 KB): RESIDENT in shared memory, 4 groups;
+//   level 2 (264 KB): STREAMED block by block from L2 through a 2-slot ring (cp.async.bulk + mbarrier) shared by 2
+//   groups that run the same block sequence: a slot is refilled with block l+2 when both groups' MMAs of block l
+//   have completed.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
@@ -34,39 +37,37 @@ struct LevelCfg {
     static constexpr bool RESIDENT = RESIDENT_;
     static constexpr int KG = (CIN + 4 + 15) / 16 * 16;             // grouped input: [feat(CIN) | rel xyz, |rel| | 0-pad]
     // weight blocks in execution order; block = hi plane [K/8][N][16 B] + lo plane = 4*K*N bytes
-    __host__ __device__ static constexpr int lk(int l) {            // K of layer l: d1 d2 d3 x1 x2 x3 mb ma mc m2
-        return (l == 0 || l == 3) ? KG : (l == 1 || l == 4) ? C1 : (l == 2 || l == 5) ? C2 : (l == 9) ? CMID : CO;
+    static constexpr int NL = 9;                                    // blocks: [d1;x1] d2 d3 x2 x3 mb ma mc m2
+    __host__ __device__ static constexpr int lk(int l) {            // K of block l
+        return l == 0 ? KG : (l == 1 || l == 3) ? C1 : (l == 2 || l == 4) ? C2 : (l == 8) ? CMID : CO;
     }
     __host__ __device__ static constexpr int ln(int l) {
-        return (l == 0 || l == 3) ? C1 : (l == 1 || l == 4) ? C2 : (l == 2 || l == 5) ? CO : (l == 9) ? CD : CMID;
+        return l == 0 ? 2 * C1 : (l == 1 || l == 3) ? C2 : (l == 2 || l == 4) ? CO : (l == 8) ? CD : CMID;
     }
     __host__ __device__ static constexpr int woff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += 4 * lk(i) * ln(i); return o; }
-    static constexpr int W_BYTES = woff(10);
-    static constexpr int SLOT = 4 * cmax(cmax(KG * C1, C2 * CO), cmax(CO * CMID, CMID * CD));
+    static constexpr int W_BYTES = woff(NL);
+    static constexpr int SLOT = 4 * cmax(cmax(KG * 2 * C1, C2 * CO), cmax(CO * CMID, CMID * CD));
     static constexpr int W_SMEM = RESIDENT ? W_BYTES : 2 * SLOT;
     // biases (floats): d1,d2,d3,x1,x2,x3,m1,m2
     static constexpr int B_D1 = 0, B_D2 = B_D1 + C1, B_D3 = B_D2 + C2, B_X1 = B_D3 + CO, B_X2 = B_X1 + C1,
                          B_X3 = B_X2 + C2, B_M1 = B_X3 + CO, B_M2 = B_M1 + CMID, B_COUNT = B_M2 + CD;
-    static constexpr int OPC = cmax(cmax(C1, C2), cmax(CO, CMID)) / 8;   // chunks of the in-place operand buffer
-    // level 1 (no gathered features): the grouped input is 4 numbers per row, rebuilt from registers before each of the
-    // two first layers, so it lives in the operand buffer instead of its own region
-    static constexpr bool G_ALIAS = (CIN == 0);
-    static constexpr int G_BYTES = G_ALIAS ? 0 : 2 * (KG / 8) * TMR * 16;
+    // in-place operand buffer (chunks of 8 channels); the grouped input is consumed by one step, so it lives here too
+    static constexpr int OPC = cmax(cmax(cmax(C1, C2), cmax(CO, CMID)), KG) / 8;
     static constexpr int OP_BYTES = 2 * OPC * TMR * 16;
     static constexpr int CW = cmax(CO, CD);
-    static constexpr int SMEM = W_SMEM + B_COUNT * 4 + G_BYTES + OP_BYTES + 2 * 4 * CW * 4 + 256;
     // TMEM columns: [E] [work: hidden layers / mlp1 accumulator / X1 / descriptor].  One work region is enough: every
     // result in it is drained (to the operand buffer or to HBM) before the next layer that targets it is issued.
     static constexpr int T_ACCE = 0;
     static constexpr int T_ACC0 = CO;
     static constexpr int T_ACCX = CO;
-    static constexpr int T_USED = CO + cmax(cmax(cmax(C1, C2), CMID), cmax(CO, CD));
+    static constexpr int T_USED = CO + cmax(cmax(cmax(2 * C1, C2), CMID), cmax(CO, CD));
+    static_assert(C2 <= C1, "the second detector layer must not overwrite the parked first descriptor layer");
     static constexpr int T_COLS = T_USED <= 32 ? 32 : T_USED <= 64 ? 64 : T_USED <= 128 ? 128 : T_USED <= 256 ? 256 : 512;
     static constexpr int WPG = KNBR / 32;                           // warps per keypoint group (1 or 2)
     // RESIDENT: NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns,
     // all sharing ONE resident copy of the weights (4 tiles in flight per SM instead of 2 CTAs x 1)
-    static constexpr int NG = RESIDENT ? 4 : 1;
-    static constexpr int GRP_SMEM = G_BYTES + OP_BYTES + 2 * 4 * CW * 4;
+    static constexpr int NG = RESIDENT ? 4 : 2;
+    static constexpr int GRP_SMEM = OP_BYTES + 2 * 4 * CW * 4;
     static constexpr int SMEM_NG = W_SMEM + B_COUNT * 4 + NG * GRP_SMEM + 256;
     static constexpr int T_COLS_NG = NG * T_USED <= 256 ? 256 : 512;
     static_assert(NG * T_USED <= 512, "TMEM (groups)");
@@ -138,6 +139,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     constexpr int NG = Cfg::NG;
     __shared__ __align__(8) uint64_t s_bar[2 + NG];                       // [0,1] weight slot landed, [2+g] MMA done (group g)
     __shared__ uint32_t s_tmem;
+    __shared__ unsigned int s_done[2];                                    // groups that have finished with weight slot 0 / 1
     __shared__ float s_red_all[NG][4][8];
 
     const int cta_tid = threadIdx.x;
@@ -146,8 +148,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     float (*s_red)[8] = s_red_all[grp_id];
     uint8_t* sW = smem;
     float* sB = reinterpret_cast<float*>(smem + Cfg::W_SMEM);
-    uint8_t* sG = smem + Cfg::W_SMEM + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
-    uint8_t* sOp = sG + Cfg::G_BYTES;
+    uint8_t* sOp = smem + Cfg::W_SMEM + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
     float* sCol = reinterpret_cast<float*>(sOp + Cfg::OP_BYTES);          // [4][CW] per-warp column partials
     float* sCol2 = sCol + 4 * CW;
     auto gsync = [&]() {                                                  // barrier of this group only
@@ -162,15 +163,18 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     uint32_t phase = 0;
     uint32_t lcount = 0;                                                  // layers executed by this CTA (streaming)
     const int vgrid = (int)gridDim.x * NG, vblock = (int)blockIdx.x * NG + grp_id;   // groups act as virtual CTAs
-    const int my_tiles = vblock < n_tiles ? (n_tiles - vblock + vgrid - 1) / vgrid : 0;
-    const uint32_t total_layers = (uint32_t)my_tiles * 10u;
+    // every group of a CTA runs the same number of rounds (streaming: the weight slots advance in lockstep); a group
+    // without a tile in the last round only takes part in the slot accounting
+    const int vfirst = (int)blockIdx.x * NG;
+    const int rounds = vfirst < n_tiles ? (n_tiles - vfirst + vgrid - 1) / vgrid : 0;
+    const uint32_t total_layers = (uint32_t)rounds * (uint32_t)Cfg::NL;
     const uint32_t wbase = smem_u32(sW);
 
     auto stream_weights = [&](uint32_t L) {   // thread 0: fetch the weights of this CTA's L-th layer into slot L&1
-        const int li = (int)(L % 10u);
+        const int li = (int)(L % (uint32_t)Cfg::NL);
         int off = 0, bytes = 0;
 #pragma unroll
-        for (int l = 0; l < 10; ++l) if (l == li) { off = Cfg::woff(l); bytes = 4 * Cfg::lk(l) * Cfg::ln(l); }
+        for (int l = 0; l < Cfg::NL; ++l) if (l == li) { off = Cfg::woff(l); bytes = 4 * Cfg::lk(l) * Cfg::ln(l); }
         mbar_expect_tx(bar_w[L & 1], (uint32_t)bytes);
         bulk_g2s(wbase + (L & 1) * Cfg::SLOT, Wpack + off, (uint32_t)bytes, bar_w[L & 1]);
     };
@@ -178,6 +182,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     // ---- one-time setup ---------------------------------------------------------------------------------------
     if (cta_tid == 0) {
         for (int i = 0; i < 2 + NG; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+        s_done[0] = 0; s_done[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (!Cfg::RESIDENT) {
             if (total_layers > 0) stream_weights(0);
@@ -188,14 +193,6 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         for (int i = cta_tid; i < Cfg::W_BYTES / 16; i += TMR * NG)
             reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
     for (int i = cta_tid; i < Cfg::B_COUNT; i += TMR * NG) sB[i] = __ldg(biases + i);
-    if (!Cfg::G_ALIAS) {   // K padding chunks of G stay zero forever
-        uint4* g_hi = reinterpret_cast<uint4*>(sG);
-        uint4* g_lo = g_hi + (Cfg::KG / 8) * TMR;
-        for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {
-            g_hi[c * TMR + tid] = make_uint4(0, 0, 0, 0);
-            g_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
-        }
-    }
     if (cta_tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS_NG) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -207,13 +204,17 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     const uint32_t tmem = tmem_all + grp_id * Cfg::T_USED;                // this group's accumulator columns
     const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
     const uint32_t aOp_hi = smem_u32(sOp), aOp_lo = aOp_hi + Cfg::OPC * TMR * 16;
-    const uint32_t aG_hi = Cfg::G_ALIAS ? aOp_hi : smem_u32(sG);
-    const uint32_t aG_lo = Cfg::G_ALIAS ? aOp_lo : aG_hi + (Cfg::KG / 8) * TMR * 16;
     uint4* op_hi = reinterpret_cast<uint4*>(sOp);
     uint4* op_lo = op_hi + Cfg::OPC * TMR;
-    uint4* g_hi = Cfg::G_ALIAS ? op_hi : reinterpret_cast<uint4*>(sG);
-    uint4* g_lo = Cfg::G_ALIAS ? op_lo : g_hi + (Cfg::KG / 8) * TMR;
 
+    // streaming: this group is done with the weights of its block `lcount`; the last group to get here refills the slot
+    auto release_slot = [&]() {
+        unsigned int* cnt = &s_done[lcount & 1];
+        if (atomicAdd(cnt, 1u) == (unsigned)(NG - 1)) {
+            *cnt = 0;
+            if (lcount + 2 < total_layers) stream_weights(lcount + 2);
+        }
+    };
     // operand ready in smem -> one thread issues layer `li` -> everybody waits for the accumulator
     auto run_layer = [&](uint32_t a_hi, uint32_t a_lo, int li, int tcol, bool acc) {
         const int K = Cfg::lk(li), Nn = Cfg::ln(li);
@@ -233,7 +234,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!Cfg::RESIDENT && tid == 0 && lcount + 2 < total_layers) stream_weights(lcount + 2);   // slot is free again
+        if (!Cfg::RESIDENT && tid == 0) release_slot();
         ++lcount;
     };
     // accumulator [tcol, tcol+Nn) -> relu(x + b) -> bf16 hi/lo operand (in place)
@@ -258,8 +259,18 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         return v;
     };
 
-    for (int tile = vblock; tile < n_tiles; tile += vgrid) {
-        // ---- grouped input  [feat[idx] | rel xyz, |rel|] ----------------------------------------------------
+    for (int round = 0; round < rounds; ++round) {
+        const int tile = vblock + round * vgrid;
+        if (tile >= n_tiles) {                       // no tile left for this group: keep the weight slots moving
+            if (!Cfg::RESIDENT && tid == 0)
+                for (int l = 0; l < Cfg::NL; ++l) {
+                    mbar_wait(bar_w[lcount & 1], (lcount >> 1) & 1);       // stay in step with the groups that use the block
+                    release_slot();
+                    ++lcount;
+                }
+            continue;
+        }
+        // ---- grouped input  [feat[idx] | rel xyz, |rel|] -> operand buffer ------------------------------------
         const long long r = (long long)tile * TMR + tid;
         const long long bm = r / KNBR;
         const long long b = bm / M;
@@ -280,24 +291,22 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
                 for (int c = 0; c < HALF; ++c) {
                     const float x[8] = {fv[2 * c].x, fv[2 * c].y, fv[2 * c].z, fv[2 * c].w,
                                         fv[2 * c + 1].x, fv[2 * c + 1].y, fv[2 * c + 1].z, fv[2 * c + 1].w};
-                    split_store8(x, g_hi + (h * HALF + c) * TMR + tid, g_lo + (h * HALF + c) * TMR + tid);
+                    split_store8(x, op_hi + (h * HALF + c) * TMR + tid, op_lo + (h * HALF + c) * TMR + tid);
                 }
             }
         }
-        auto store_geometry = [&]() {
+        {
             const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 0.f, 0.f, 0.f, 0.f};
-            split_store8(x, g_hi + (CIN / 8) * TMR + tid, g_lo + (CIN / 8) * TMR + tid);
-            if (Cfg::G_ALIAS) {
+            split_store8(x, op_hi + (CIN / 8) * TMR + tid, op_lo + (CIN / 8) * TMR + tid);
 #pragma unroll
-                for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {
-                    g_hi[c * TMR + tid] = make_uint4(0, 0, 0, 0);
-                    g_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
-                }
+            for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {             // K padding
+                op_hi[c * TMR + tid] = make_uint4(0, 0, 0, 0);
+                op_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
             }
-        };
-        store_geometry();
+        }
+        // ---- first layer of both chains: work columns [0, C1) = detector, [C1, 2 C1) = descriptor (parked) ------
+        run_layer(aOp_hi, aOp_lo, 0, Cfg::T_ACC0, false);
         // ---- detector chain ------------------------------------------------------------------------------------
-        run_layer(aG_hi, aG_lo, 0, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_D1);
         run_layer(aOp_hi, aOp_lo, 1, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_D2);
@@ -331,12 +340,10 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         const float a = ex / s0;
         if (leader && lane < 3) out_xyz[bm * 3 + lane] = (lane == 0 ? s1 : (lane == 1 ? s2 : s3)) / s0;
         // ---- descriptor chain ----------------------------------------------------------------------------------
-        if (Cfg::G_ALIAS) store_geometry();          // the operand buffer has been reused since the detector's first layer
-        run_layer(aG_hi, aG_lo, 3, Cfg::T_ACC0, false);
-        epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_X1);
-        run_layer(aOp_hi, aOp_lo, 4, Cfg::T_ACC0, false);
+        epi_to_operand(Cfg::T_ACC0 + C1, C1, sB + Cfg::B_X1);
+        run_layer(aOp_hi, aOp_lo, 3, Cfg::T_ACC0, false);
         epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_X2);
-        run_layer(aOp_hi, aOp_lo, 5, Cfg::T_ACCX, false);
+        run_layer(aOp_hi, aOp_lo, 4, Cfg::T_ACCX, false);
         // X1 -> operand, and its column maximum over the rows of the group
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
@@ -352,7 +359,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             const float cm = warp_transpose_reduce<true>(f, lane);
             sCol[warp * CW + c0 + lane] = cm;
         }
-        run_layer(aOp_hi, aOp_lo, 6, Cfg::T_ACC0, false);                 // mlp1 += Wb.X1 (barrier inside publishes sCol)
+        run_layer(aOp_hi, aOp_lo, 5, Cfg::T_ACC0, false);                 // mlp1 += Wb.X1 (barrier inside publishes sCol)
         // max_k(X1) broadcast over the group's rows as the next K-segment
 #pragma unroll 4
         for (int ch = 0; ch < CO / 8; ++ch) {
@@ -361,7 +368,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             for (int e = 0; e < 8; ++e) x[e] = col_max(sCol, ch * 8 + e);
             split_store8(x, op_hi + ch * TMR + tid, op_lo + ch * TMR + tid);
         }
-        run_layer(aOp_hi, aOp_lo, 7, Cfg::T_ACC0, true);                  // mlp1 += Wa.max_k(X1)
+        run_layer(aOp_hi, aOp_lo, 6, Cfg::T_ACC0, true);                  // mlp1 += Wa.max_k(X1)
         // attentive feature map E*a as the third K-segment; attentive feature = its column sum over the group
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
@@ -379,7 +386,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             const float cs = warp_transpose_reduce<false>(f, lane);
             sCol2[warp * CW + c0 + lane] = cs;
         }
-        run_layer(aOp_hi, aOp_lo, 8, Cfg::T_ACC0, true);                  // mlp1 += Wc.(E*a)
+        run_layer(aOp_hi, aOp_lo, 7, Cfg::T_ACC0, true);                  // mlp1 += Wc.(E*a)
         if (leader)
             for (int c = lane; c < CO; c += 32) {
                 float v = sCol2[gw0 * CW + c];
@@ -388,7 +395,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             }
         // ---- mlp1 epilogue -> mlp2 -> descriptor = max_k -------------------------------------------------------
         epi_to_operand(Cfg::T_ACC0, CMID, sB + Cfg::B_M1);
-        run_layer(aOp_hi, aOp_lo, 9, Cfg::T_ACCX, false);
+        run_layer(aOp_hi, aOp_lo, 8, Cfg::T_ACCX, false);
         for (int c0 = 0; c0 < CD; c0 += 32) {
             uint32_t v[32];
             float f[32];

@@ -86,7 +86,7 @@ def which_level(k, cin, det, desc):
 
 def pack_level(level, det, desc):
     """Folded parameter dicts of detector_l / desc_extractor_l -> (Wpack uint8, biases fp32) in the LevelCfg layout of
-    csrc/level_fused.cu: blocks in execution order d1 d2 d3 x1 x2 x3 mlp1[X1] mlp1[max X1] mlp1[E*a] mlp2.  The grouped
+    csrc/level_fused.cu: blocks in execution order [d1;x1] d2 d3 x2 x3 mlp1[X1] mlp1[max X1] mlp1[E*a] mlp2.  The grouped
     input channels are re-ordered from the reference's [rel(3), dist(1), feat(C)] (layers.py:21-26) to
     [feat(C), rel(3), dist(1), 0-pad] so that the gathered feature row lands on 8-channel chunk boundaries."""
     key = (level,) + tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
@@ -100,8 +100,9 @@ def pack_level(level, det, desc):
     CO, cin = d["co"], d["cin"]
     KG = (cin + 4 + 15) // 16 * 16
     perm = list(range(4, 4 + cin)) + [0, 1, 2, 3]
-    parts = [_umma_tiles(d1[:, perm].contiguous(), KG), _umma_tiles(d2, d["c1"]), _umma_tiles(d3, d["c2"]),
-             _umma_tiles(x1[:, perm].contiguous(), KG), _umma_tiles(x2, d["c1"]), _umma_tiles(x3, d["c2"]),
+    first = torch.cat([d1[:, perm], x1[:, perm]], 0).contiguous()       # both chains read the same grouped input
+    parts = [_umma_tiles(first, KG), _umma_tiles(d2, d["c1"]), _umma_tiles(d3, d["c2"]),
+             _umma_tiles(x2, d["c1"]), _umma_tiles(x3, d["c2"]),
              _umma_tiles(m1[:, CO:2 * CO].contiguous(), CO), _umma_tiles(m1[:, :CO].contiguous(), CO),
              _umma_tiles(m1[:, 2 * CO:].contiguous(), CO), _umma_tiles(m2, d["cmid"])]
     Wpack = torch.cat(parts).contiguous()
