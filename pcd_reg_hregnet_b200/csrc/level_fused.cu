@@ -62,7 +62,6 @@ struct LevelCfg {
     static constexpr int T_ACCX = CO;
     static constexpr int T_USED = CO + cmax(cmax(cmax(2 * C1, C2), CMID), cmax(CO, CD));
     static_assert(C2 <= C1, "the second detector layer must not overwrite the parked first descriptor layer");
-    static constexpr int T_COLS = T_USED <= 32 ? 32 : T_USED <= 64 ? 64 : T_USED <= 128 ? 128 : T_USED <= 256 ? 256 : 512;
     static constexpr int WPG = KNBR / 32;                           // warps per keypoint group (1 or 2)
     // RESIDENT: NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns,
     // all sharing ONE resident copy of the weights (4 tiles in flight per SM instead of 2 CTAs x 1)
@@ -84,16 +83,17 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {
 __device__ __forceinline__ void issue_layer(uint32_t a_hi, uint32_t a_lo, int K, uint32_t w_hi, int N, uint32_t tmem_d,
                                             bool accumulate) {
     const uint32_t idesc = make_idesc(N);
-    const uint32_t a_lbo = TMR * 16, w_lbo = (uint32_t)N * 16;
-    const uint32_t w_lo = w_hi + (uint32_t)(K / 8) * N * 16;
+    const uint32_t w_lbo = (uint32_t)N * 16;
+    const uint64_t a_fix = umma_desc_fixed(TMR * 16, 128), w_fix = umma_desc_fixed(w_lbo, 128);
+    // start addresses in 16-byte units (shared memory < 256 KB: they fit the 14-bit field); one k-step = two chunks
+    uint32_t ah = a_hi >> 4, al = a_lo >> 4, wh = w_hi >> 4, wl = (w_hi + (uint32_t)(K / 8) * w_lbo) >> 4;
+    const uint32_t a_step = (2 * TMR * 16) >> 4, w_step = (2 * w_lbo) >> 4;
+#pragma unroll 4
     for (int k = 0; k < K / 16; ++k) {
-        const uint64_t ah = umma_desc(a_hi + k * 2 * a_lbo, a_lbo, 128);
-        const uint64_t al = umma_desc(a_lo + k * 2 * a_lbo, a_lbo, 128);
-        const uint64_t wh = umma_desc(w_hi + k * 2 * w_lbo, w_lbo, 128);
-        const uint64_t wl = umma_desc(w_lo + k * 2 * w_lbo, w_lbo, 128);
-        umma_bf16(tmem_d, ah, wh, idesc, (accumulate || k > 0) ? 1u : 0u);
-        umma_bf16(tmem_d, al, wh, idesc, 1u);
-        umma_bf16(tmem_d, ah, wl, idesc, 1u);
+        umma_bf16(tmem_d, a_fix | ah, w_fix | wh, idesc, (accumulate || k > 0) ? 1u : 0u);
+        umma_bf16(tmem_d, a_fix | al, w_fix | wh, idesc, 1u);
+        umma_bf16(tmem_d, a_fix | ah, w_fix | wl, idesc, 1u);
+        ah += a_step; al += a_step; wh += w_step; wl += w_step;
     }
 }
 

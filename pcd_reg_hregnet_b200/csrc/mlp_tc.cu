@@ -464,28 +464,27 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         // ================= MMA issue ==============================================================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint32_t a_lbo = TM * 16, w_lbo = (uint32_t)NS * 16;
-            const uint32_t a_lo_off = (KC / 8) * TM * 16, w_lo_off = (KC / 8) * (uint32_t)NS * 16;
+            const uint32_t w_lbo = (uint32_t)NS * 16;
+            const uint64_t a_fix = umma_desc_fixed(TM * 16, 128), w_fix = umma_desc_fixed(w_lbo, 128);
+            // offsets inside a stage, 16-byte units: lo planes, second k-step
+            constexpr uint32_t A_LO = ((KC / 8) * TM * 16) >> 4, A_K1 = (2 * TM * 16) >> 4;
+            const uint32_t w_lo = ((KC / 8) * w_lbo) >> 4, w_k1 = (2 * w_lbo) >> 4;
+            const uint32_t stage16 = stage_bytes >> 4;
             int st = 0; uint32_t par = 0; int ph = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ph) {
                 const int b = ph & 1;
                 mbar_wait(acce0 + 8 * b, ((ph >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem + b * 256;
                 for (int i = 0; i < n_stage; ++i) {
                     mbar_wait(full0 + 8 * st, par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_base = smem0 + st * stage_bytes, w_base = a_base + A_STAGE_BYTES;
-#pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
-                        const uint64_t ah = umma_desc(a_base + k * 2 * a_lbo, a_lbo, 128);
-                        const uint64_t al = umma_desc(a_base + a_lo_off + k * 2 * a_lbo, a_lbo, 128);
-                        const uint64_t wh = umma_desc(w_base + k * 2 * w_lbo, w_lbo, 128);
-                        const uint64_t wl = umma_desc(w_base + w_lo_off + k * 2 * w_lbo, w_lbo, 128);
-                        umma_bf16(d, ah, wh, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                        umma_bf16(d, al, wh, idesc, 1u);
-                        umma_bf16(d, ah, wl, idesc, 1u);
-                    }
+                    const uint32_t a16 = (smem0 >> 4) + st * stage16, w16 = a16 + (A_STAGE_BYTES >> 4);
+                    umma_bf16(d, a_fix | a16, w_fix | w16, idesc, i > 0 ? 1u : 0u);
+                    umma_bf16(d, a_fix | (a16 + A_LO), w_fix | w16, idesc, 1u);
+                    umma_bf16(d, a_fix | a16, w_fix | (w16 + w_lo), idesc, 1u);
+                    umma_bf16(d, a_fix | (a16 + A_K1), w_fix | (w16 + w_k1), idesc, 1u);
+                    umma_bf16(d, a_fix | (a16 + A_K1 + A_LO), w_fix | (w16 + w_k1), idesc, 1u);
+                    umma_bf16(d, a_fix | (a16 + A_K1), w_fix | (w16 + w_k1 + w_lo), idesc, 1u);
                     umma_commit(empty0 + 8 * st);
                     if (++st == S) { st = 0; par ^= 1; }
                 }

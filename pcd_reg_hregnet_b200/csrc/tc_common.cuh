@@ -59,6 +59,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// The same descriptor as  fixed part | 14-bit start address: the issuing thread keeps the fixed part in registers and
+// only adds to the address field (its instruction stream, not the tensor pipe, limits small MMAs).
+__device__ __forceinline__ uint64_t umma_desc_fixed(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
