@@ -34,6 +34,26 @@ __device__ __forceinline__ float fps_dist(float x, float y, float z, float x1, f
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100): two points per instruction, each half rounded exactly
+// like the scalar __fsub_rn / __fmul_rn / __fmaf_rn -- the update loop is issue-bound, this halves its arithmetic.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+    f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+// fps_dist of two points against the same centre
+__device__ __forceinline__ f32x2_t fps_dist2(f32x2_t x, f32x2_t y, f32x2_t z, f32x2_t cx, f32x2_t cy, f32x2_t cz) {
+    const f32x2_t dx = f2_sub(x, cx), dy = f2_sub(y, cy), dz = f2_sub(z, cz);
+    return f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+}
+
 // P > 0: thread tid holds the P points k = tid + p*THREADS in registers, temp in shared memory.
 // P == 0: streaming (xyz from global, temp in the caller's global scratch).
 // The thread<->point mapping is free: the reference's tie-break is carried as an explicit key computed
@@ -239,12 +259,26 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
     for (int j = 1; j < M; ++j) {
         // ---- A: update, warp maximum --------------------------------------------------------------------------
         float m = -CUDART_INF_F;
+        if (P % 2 == 0) {
+            const f32x2_t cx2 = f2_pack(x1, x1), cy2 = f2_pack(y1, y1), cz2 = f2_pack(z1, z1);
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            float d = fps_dist(px[p], py[p], pz[p], x1, y1, z1);
-            if (WEIGHTED) d = __fmul_rn(pw[p], d);
-            pt[p] = fminf(d, pt[p]);
-            m = fmaxf(m, pt[p]);
+            for (int p = 0; p < P; p += 2) {
+                f32x2_t d2 = fps_dist2(f2_pack(px[p], px[p + 1]), f2_pack(py[p], py[p + 1]), f2_pack(pz[p], pz[p + 1]), cx2, cy2, cz2);
+                if (WEIGHTED) d2 = f2_mul(f2_pack(pw[p], pw[p + 1]), d2);
+                float d0, d1;
+                f2_unpack(d2, d0, d1);
+                pt[p] = fminf(d0, pt[p]);
+                pt[p + 1] = fminf(d1, pt[p + 1]);
+                m = fmaxf(m, fmaxf(pt[p], pt[p + 1]));
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float d = fps_dist(px[p], py[p], pz[p], x1, y1, z1);
+                if (WEIGHTED) d = __fmul_rn(pw[p], d);
+                pt[p] = fminf(d, pt[p]);
+                m = fmaxf(m, pt[p]);
+            }
         }
         const unsigned om = hrn_ford(m);
         const unsigned wm = __reduce_max_sync(0xffffffffu, om);
