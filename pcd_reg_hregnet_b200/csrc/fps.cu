@@ -34,20 +34,6 @@ __device__ __forceinline__ float fps_dist(float x, float y, float z, float x1, f
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
-// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100): two points per instruction, each half rounded exactly
-// like the scalar __fsub_rn / __fmul_rn / __fmaf_rn -- the update loop is issue-bound, this halves its arithmetic.
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
-    f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
-    f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
-}
 // fps_dist of two points against the same centre
 __device__ __forceinline__ f32x2_t fps_dist2(f32x2_t x, f32x2_t y, f32x2_t z, f32x2_t cx, f32x2_t cy, f32x2_t cz) {
     const f32x2_t dx = f2_sub(x, cx), dy = f2_sub(y, cy), dz = f2_sub(z, cz);

@@ -140,7 +140,8 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
 // Generic D (descriptor space, D = 256 in CoarseReg).  Sequential fma chain over d per (query, ref) pair, so the
 // distances are bit-identical to the oracle; register-tiled: a CTA owns 32 queries, a warp 8 of them, a lane 4
 // references of the current 128-reference tile -> 32 independent accumulators per thread, 12 shared-memory loads per
-// 32 FMAs.  References stream through shared memory in [128 refs] x [64 dims] slices (padded rows: conflict-free).
+// 32 FMAs.  References stream through shared memory in [128 refs] x [64 dims] slices (padded rows: conflict-free),
+// double-buffered with cp.async.
 constexpr int KD_Q = 32;         // queries per CTA
 constexpr int KD_R = 128;        // references per tile
 constexpr int KD_D = 64;         // dims per slice
@@ -164,43 +165,59 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
 #pragma unroll
     for (int q = 0; q < 8; ++q) top[q].init(K);
     constexpr int LDR = KD_D + 1;
+    // reference slices [128 refs] x [64 dims] are double-buffered with 4-byte cp.async (the padded rows that make the
+    // column reads conflict-free are not 16-byte aligned): slice s+1 is in flight while slice s is consumed
+    const int n_dslice = (D + KD_D - 1) / KD_D;
+    const int n_slice = ((N + KD_R - 1) / KD_R) * n_dslice;
+    auto fill = [&](int sl, int buf) {
+        const int t0s = (sl / n_dslice) * KD_R, d0s = (sl % n_dslice) * KD_D;
+        float* dst = s_r + buf * (KD_R * LDR);
+        for (int i = threadIdx.x; i < KD_R * KD_D; i += blockDim.x) {
+            const int rr = i / KD_D, dd = i - rr * KD_D;
+            const bool ok = t0s + rr < N && d0s + dd < D;
+            const float* src = ok ? p2 + (size_t)(t0s + rr) * D + d0s + dd : p2;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + rr * LDR + dd)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fill(0, 0);
+    int sl = 0;
     for (int t0 = 0; t0 < N; t0 += KD_R) {
-        float acc[8][4];
+        // accumulators of references (lane, lane+32) and (lane+64, lane+96) packed as fp32x2: FADD2 / FFMA2 round each
+        // half like the scalar instructions, so the sequential chain over d stays bit-identical to the oracle
+        f32x2_t acc[8][2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
-        for (int d0 = 0; d0 < D; d0 += KD_D) {
+        for (int q = 0; q < 8; ++q) { acc[q][0] = f2_pack(0.f, 0.f); acc[q][1] = acc[q][0]; }
+        for (int d0 = 0; d0 < D; d0 += KD_D, ++sl) {
             const int dn = min(KD_D, D - d0);
-            __syncthreads();
-            for (int i = threadIdx.x; i < KD_R * KD_D; i += blockDim.x) {
-                const int rr = i / KD_D, dd = i - rr * KD_D;
-                s_r[rr * LDR + dd] = (t0 + rr < N && dd < dn) ? __ldg(p2 + (size_t)(t0 + rr) * D + d0 + dd) : 0.f;
-            }
-            __syncthreads();
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                   // slice sl visible; everybody is done with slice sl-1
+            if (sl + 1 < n_slice) fill(sl + 1, (sl + 1) & 1);
+            const float* sr = s_r + (sl & 1) * (KD_R * LDR);
             const float* qb = s_q + (warp * 8) * D + d0;
             for (int d = 0; d < dn; ++d) {
-                float rv[4], qv[8];
+                const f32x2_t r01 = f2_pack(sr[lane * LDR + d], sr[(lane + 32) * LDR + d]);
+                const f32x2_t r23 = f2_pack(sr[(lane + 64) * LDR + d], sr[(lane + 96) * LDR + d]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) rv[j] = s_r[(lane + 32 * j) * LDR + d];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) qv[q] = qb[q * D + d];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float diff = qv[q] - rv[j];
-                        acc[q][j] = __fmaf_rn(diff, diff, acc[q][j]);
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    const float qv = qb[q * D + d];
+                    const f32x2_t q2 = f2_pack(qv, qv);
+                    const f32x2_t e0 = f2_sub(q2, r01), e1 = f2_sub(q2, r23);
+                    acc[q][0] = f2_fma(e0, e0, acc[q][0]);
+                    acc[q][1] = f2_fma(e1, e1, acc[q][1]);
+                }
             }
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (m0 + warp * 8 + q < M) {
+                float a[4];
+                f2_unpack(acc[q][0], a[0], a[1]);
+                f2_unpack(acc[q][1], a[2], a[3]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = t0 + lane + 32 * j;
-                    top[q].offer(n < N ? acc[q][j] : CUDART_INF_F, n, lane);
+                    top[q].offer(n < N ? a[j] : CUDART_INF_F, n, lane);
                 }
             }
         }
@@ -246,7 +263,7 @@ HRN_API int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int 
         if (K <= 32) knn3_kernel<1><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
         else knn3_kernel<2><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
     } else {
-        const size_t smem = ((size_t)KD_Q * D + (size_t)KD_R * (KD_D + 1)) * sizeof(float);
+        const size_t smem = ((size_t)KD_Q * D + 2 * (size_t)KD_R * (KD_D + 1)) * sizeof(float);
         if (smem > 200 * 1024) return HRN_ERR_UNSUPPORTED;
         dim3 gridd(hrn_divup(M, KD_Q), B);
         if (K <= 32) {
