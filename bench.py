@@ -321,6 +321,11 @@ def _profile_families(reg, steps=3):
             rows_t = a[0]._obj
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
             fl = 2.0 * view_rows * K * cout
+        elif name == "hrn_chain_tc":
+            rows_t, nl, n1, n2, cout, view_rows = a[0]._obj, a[3], a[4], a[5], a[7], a[16]
+            K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
+            macs = K * n1 + (n1 * n2 + n2 * cout if nl == 3 else n1 * cout)
+            fl = 2.0 * view_rows * macs
         elif name == "hrn_level_fused":
             # algorithmic MACs per neighbour row of a fused level: detector + descriptor conv stacks + mlp1 + mlp2
             lv, Bc, Mc, kc = a[0], a[10], a[11], a[13]
@@ -342,7 +347,7 @@ def _profile_families(reg, steps=3):
         fam[name] = fam.get(name, 0.0) + s.elapsed_time(e) / steps
         flops[name] = flops.get(name, 0.0) + fl / steps
     fam = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
-    layer_names = [n for n in fam if n.startswith("hrn_layer") or n == "hrn_level_fused"]
+    layer_names = [n for n in fam if n.startswith("hrn_layer") or n in ("hrn_level_fused", "hrn_chain_tc")]
     layer_ms = sum(fam[n] for n in layer_names)
     layer_fl = sum(flops[n] for n in layer_names)
     n_layer = sum(1 for r in rec if r[0] in layer_names) / steps

@@ -1,5 +1,5 @@
 """Per-kernel breakdown of ONE 32-pair step from an ncu launch list that carries gpu__time_duration.sum and the two
-dram__bytes counters (step boundaries = successive knn_sort_kernel launches).  Writes the table to stdout and the
+dram__bytes counters (step boundaries = successive level-1 FPS launches).  Writes the table to stdout and the
 DRAM traffic of the tensor-core kernel family to profiles/r01_traffic.json (read by bench.py for roofline.traffic).
 usage: python profiles/step_breakdown.py gpurun_out/launches_final.csv > profiles/r01_launches_final.txt"""
 import collections
@@ -20,10 +20,11 @@ for r in csv.DictReader(lines):
     else:
         d[r["Metric Name"]] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 ids = sorted(by)
-marks = [n for n, i in enumerate(ids) if "knn_sort_kernel" in by[i]["name"]]
-a = marks[0] - 1                                       # the level-1 FPS launch precedes the sort
+# a step starts with the level-1 furthest-point sampling: the only fps launch over the full clouds
+marks = [n for n, i in enumerate(ids) if "fps_cluster_kernel<512" in by[i]["name"]]
+a = marks[0]
 if len(marks) > 1:
-    b = marks[1] - 1
+    b = marks[1]
 else:                                                  # window holds one step start: the step ends at the last pose kernel
     b = max(n for n, i in enumerate(ids) if "kabsch_kernel" in by[i]["name"] and n > a) + 1
 fam = collections.defaultdict(lambda: [0, 0.0, 0.0])
@@ -39,7 +40,7 @@ print(f"# one 32-pair step (ncu launch list, cold-cache serialised: compare SHAR
 print(f"{'us':>10} {'share':>6} {'n':>4} {'dram MB':>10}  kernel")
 for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     print(f"{v[1]:10.1f} {100 * v[1] / tot:5.1f}% {v[0]:4d} {v[2] / 1e6:10.1f}  {k}")
-tc = [k for k in fam if any(s in k for s in ("level_fused", "chain3", "layer_tc"))]
+tc = [k for k in fam if any(s in k for s in ("level_fused", "chain3", "chain_ws", "layer_tc", "layer_ws"))]
 out = {"tensor_family_dram_bytes_per_step": sum(fam[k][2] for k in tc),
        "tensor_family_us_per_step_ncu": sum(fam[k][1] for k in tc), "n_launches": sum(fam[k][0] for k in tc),
        "share_of_step_ncu": sum(fam[k][1] for k in tc) / tot,
