@@ -252,6 +252,9 @@ constexpr int WS_TP = 36;                                              // epilog
 constexpr int WS_TILE_BYTES = WS_EPI_WARPS * 32 * WS_TP * 4;        // 18 KB
 constexpr int WS_RAW = 4;                                             // raw fp32 stages (cp.async) in flight per CTA
 
+// SIMPLE: the input is one DIRECT segment without a row scale (every layer that reads the previous layer's output):
+// no segment table, no per-row source resolution -- the producers' instruction stream is what bounds these launches.
+template <bool SIMPLE>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
                 float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NS, int n_split, int n_stage,
@@ -368,7 +371,9 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     rp[g][s] = nullptr; rsc[g][s] = 1.f;
-                    if (s < in.n_seg && r < rows) {
+                    if (SIMPLE) {
+                        if (s == 0 && r < rows) rp[g][0] = in.seg[0].ptr + r * in.seg[0].ld + in.seg[0].col0;
+                    } else if (s < in.n_seg && r < rows) {
                         const hrn_seg_t sg = in.seg[s];
                         long long sr;
                         if (small) {                               // 32-bit divisions
@@ -387,6 +392,14 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         };
         // async copy of the 4 floats [4 hf, 4 hf + 4) of 8-wide chunk cg of one row (zero-filled out of range)
         auto copy_piece = [&](const float* const (&pp)[4], const float (&ps)[4], int cg, uint8_t* dst, float& osc) {
+            if (SIMPLE) {
+                const int ch0 = (cg << 3) + 4 * hf;
+                const bool ok = pp[0] != nullptr && ch0 < chs[0];
+                const void* src = ok ? (const void*)(pp[0] + ch0) : (const void*)Wp;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                osc = 1.f;
+                return;
+            }
             int sgi = 0;
 #pragma unroll
             for (int q = 1; q < 4; ++q) if (cg >= c0s[q]) sgi = q;
@@ -429,8 +442,9 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const float4 t = vv[2 * g + j];
-                    const float s_ = ss[2 * g + j];
-                    const float x0 = t.x * s_, x1 = t.y * s_, x2 = t.z * s_, x3 = t.w * s_;
+                    const float s_ = SIMPLE ? 1.f : ss[2 * g + j];
+                    const float x0 = SIMPLE ? t.x : t.x * s_, x1 = SIMPLE ? t.y : t.y * s_;
+                    const float x2 = SIMPLE ? t.z : t.z * s_, x3 = SIMPLE ? t.w : t.w * s_;
                     const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
                     const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
                     const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
@@ -537,12 +551,18 @@ int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int
     const size_t smem = (size_t)S * stage_bytes + fixed;
     static bool attr_set = false;
     if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set = true;
     }
     const int grid = n_items < 148 ? n_items : 148;
-    layer_ws_kernel<<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS,
-                                                        n_split, n_stage, S, n_items);
+    const bool simple = in->n_seg == 1 && in->seg[0].mode == HRN_SEG_DIRECT && !in->seg[0].row_scale;
+    if (simple)
+        layer_ws_kernel<true><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
+                                                                  NP, NS, n_split, n_stage, S, n_items);
+    else
+        layer_ws_kernel<false><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
+                                                                   NP, NS, n_split, n_stage, S, n_items);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
