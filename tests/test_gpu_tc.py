@@ -130,3 +130,47 @@ def test_chain_two_layers_narrow_output_and_activation():
     Y, _, _ = engine_tc.chain(v, layers, engine_tc.EPI_STORE)
     want = torch.sigmoid(torch.relu(X.double() @ W1.double().t() + b1.double()) @ W2.double().t() + b2.double())
     assert Y.shape == (rows, 1) and float((Y.double() - want).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,K0,dims,mode,kseg", [
+    (128 * 700, 140, [128, 128, 128], 2, 8),      # narrow: 4 TMEM accumulators in rotation, ~5 tiles per CTA
+    (128 * 450, 132, [128, 128, 256], 1, 16),     # wide last layer with the row store through the transpose tile
+    (128, 64, [64, 32, 48], 0, 8),                # a single tile, odd (multiple-of-16) widths
+    (128 * 149, 776, [256, 256, 256], 2, 32),     # one tile more than the grid; 25 input stages (> the operand rings)
+    (128 * 300, 96, [128, 64], 1, 8),             # two layers
+])
+def test_chain_persistent_schedule(rows, K0, dims, mode, kseg):
+    """Persistent warp-specialised chain: several tiles per CTA (ring / accumulator hand-offs across tiles), wide
+    inputs, two layers -- against fp64 on a strided row sample (every tile is hit)."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    g = torch.Generator().manual_seed(rows % 1000 + K0)
+    X = torch.randn(rows, K0, generator=g).to(DEV)
+    layers, kin = [], K0
+    for w in dims:
+        layers.append(((torch.randn(w, kin, generator=g) / kin ** 0.5).to(DEV), (torch.randn(w, generator=g) * 0.1).to(DEV), ACT_RELU))
+        kin = w
+    v = RowsView(rows).add(X)
+    assert engine_tc.chain_supported(v, layers)
+    Y, G, a = engine_tc.chain(v, layers, mode, kseg)
+    torch.cuda.synchronize()
+    # fp64 on whole groups taken from every tile: groups g = 0, s, 2s, ... with s chosen so that ~4096 rows are checked
+    ngrp = rows // kseg
+    step = max(1, ngrp // (4096 // kseg))
+    gsel = torch.arange(0, ngrp, step, device=DEV)
+    rsel = (gsel[:, None] * kseg + torch.arange(kseg, device=DEV)[None, :]).reshape(-1)
+    R = X[rsel].double()
+    for W, b, _ in layers:
+        R = torch.relu(R @ W.double().t() + b.double())
+    C = dims[-1]
+    Rg = R.view(-1, kseg, C)
+    scale = float(R.abs().max())
+    if mode == 0:
+        assert float((Y[rsel].double() - R).abs().max()) / scale < 1e-4
+    elif mode == 1:
+        assert float((Y[rsel].double() - R).abs().max()) / scale < 1e-4
+        assert float((G[gsel].double() - Rg.max(dim=1)[0]).abs().max()) / scale < 1e-4
+    else:
+        a_ref = torch.softmax(Rg.max(dim=2)[0], dim=1)
+        assert float((a[rsel].double().view(-1, kseg) - a_ref).abs().max()) < 1e-4
+        assert float((G[gsel].double() - (a_ref[:, :, None] * Rg).sum(1)).abs().max()) / scale < 1e-4
+        assert float((Y[rsel].double().view(-1, kseg, C) - a_ref[:, :, None] * Rg).abs().max()) / scale < 1e-4
