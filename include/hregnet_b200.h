@@ -192,6 +192,15 @@ int hrn_cosine_pick(const float* cosm, const float* rowmax, const float* colmax,
 int hrn_weighted_kabsch(const float* src, const float* cor, const float* w, int B, int N, const float* R_prev,
                         const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, void* stream);
 
+/* Pose-error metrics fused after the pose head / the pose all-gather.  Replaces
+ * losses/losses.py:138-164 (calc_rot_rre_err, calc_tran_rte_err), models/utils.py:132-138 (calc_error_np) [mode 0:
+ * R_err = pred_R^T gt_R, t_err = pred_t - gt_t] and metrics/calibeval.py:72-106,172-196 (add_batch, geodesic_distance)
+ * [mode 1: error = pred_tf . gt_tf].  pred_R, gt_R [B,9] row-major, pred_t, gt_t [B,3].  Outputs, each nullable:
+ * geo [B] geodesic angle in degrees, eucl [B] = ||t_err||, euler [B,3] Euler XYZ angles of R_err in degrees, terr [B,3],
+ * sums [8] = sum over the batch of (geo, eucl, |euler| xyz, |terr| xyz), ACCUMULATED (zero it before the first batch). */
+int hrn_pose_errors(const float* pred_R, const float* pred_t, const float* gt_R, const float* gt_t, int B, int mode,
+                    float* geo, float* eucl, float* euler, float* terr, float* sums, void* stream);
+
 /* Host-side evaluation of the closed form used by hrn_weighted_kabsch (H row-major 3x3, fp64); for tests. */
 int hrn_pose_from_covariance_host(const double* H9, const double* xbar, const double* ybar, double* R9, double* t3);
 

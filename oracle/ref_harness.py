@@ -113,6 +113,29 @@ def load_reference():
     return ns
 
 
+_losses = None
+
+
+def load_reference_losses():
+    """The reference's losses/losses.py, unmodified, loaded as a stand-alone module (its package __init__ pulls in
+    unrelated losses with absent dependencies).  pytorch3d.transforms.matrix_to_euler_angles is absent: the restated
+    conversion of oracle/ref_metrics.py is injected for it, so only the non-Euler outputs are pinned by the reference."""
+    global _losses
+    if _losses is not None:
+        return _losses
+    import importlib.util
+    import numpy as np
+    from . import ref_metrics
+    load_reference()                                            # CPU redirections + pytorch3d stubs
+    spec = importlib.util.spec_from_file_location("_ref_losses", os.path.join(REF, "losses", "losses.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.matrix_to_euler_angles = lambda M, convention="XYZ": torch.from_numpy(
+        ref_metrics.matrix_to_euler_angles_xyz(M.detach().cpu().numpy())).to(M.dtype)
+    _losses = mod
+    return mod
+
+
 class Args:
     use_fps = True
     use_weights = True

@@ -51,6 +51,7 @@ SIGNATURES = {
     "hrn_cosine_matrix": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_cosine_pick": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_weighted_kabsch": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "hrn_pose_errors": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_pose_from_covariance_host": [c_vp, c_vp, c_vp, c_vp, c_vp],
 }
 

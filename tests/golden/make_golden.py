@@ -1,9 +1,13 @@
 """Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on the CPU through
 oracle/ref_harness.py (native ops = oracle C restatements).  Run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # model fixtures
+    python tests/golden/make_golden.py metrics    # pose_metrics.npz only
 
 Fixtures
+  pose_metrics.npz         64 seeded random pose pairs and the outputs of the reference's own metric functions
+                           (models/utils.py:132-138 calc_error_np, losses/losses.py:138-164 calc_rot_rre_err /
+                           calc_tran_rte_err) on them.
   nusc_feats_state.npz     the reference's pretrained HierFeatureExtraction weights (ckpt/pretrained/nusc_feats.pth,
                            192 tensors) re-saved as npz -- realistic BatchNorm statistics for parity runs.
   hregnet_b2_n2048.npz     HRegNet.forward (models/HRegNet/models.py:77-148) on 2 seeded synthetic pairs of 2048
@@ -73,5 +77,36 @@ def main():
               sum(v.nbytes for v in d.values()) / 1e6, "MB")
 
 
+def random_poses(B, seed, max_deg=25.0, max_t=0.6):
+    """Rotations from random axis-angles (|angle| <= max_deg) and translations in [-max_t, max_t]^3, fp32."""
+    g = torch.Generator().manual_seed(seed)
+    ax = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=1)
+    ang = (torch.rand(B, generator=g) * 2 - 1) * np.deg2rad(max_deg)
+    K = torch.zeros(B, 3, 3)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 2], ax[:, 1], ax[:, 2], -ax[:, 0], -ax[:, 1], ax[:, 0]
+    R = torch.eye(3)[None] + torch.sin(ang)[:, None, None] * K + (1 - torch.cos(ang))[:, None, None] * (K @ K)
+    t = (torch.rand(B, 3, generator=g) * 2 - 1) * max_t
+    return R.float(), t.float()
+
+
+def pose_metrics_golden():
+    """Outputs of the reference's own metric functions (models/utils.py:132-138, losses/losses.py:138-164) on seeded random
+    poses; the Euler part goes through the injected conversion (see oracle/ref_harness.load_reference_losses)."""
+    U = H.load_reference().utils
+    Ls = H.load_reference_losses()
+    pred_R, pred_t = random_poses(64, 11)
+    gt_R, gt_t = random_poses(64, 12)
+    err_np = np.array([U.calc_error_np(pred_R[i].numpy(), pred_t[i].numpy(), gt_R[i].numpy(), gt_t[i].numpy()) for i in range(64)])
+    R_err_deg, geo = Ls.calc_rot_rre_err(pred_R, gt_R)
+    T_err_mean, eucl = Ls.calc_tran_rte_err(pred_t, gt_t)
+    np.savez_compressed(os.path.join(OUT, "pose_metrics.npz"), pred_R=pred_R.numpy(), pred_t=pred_t.numpy(), gt_R=gt_R.numpy(),
+                        gt_t=gt_t.numpy(), calc_error_np=err_np.astype(np.float64), R_err_deg=R_err_deg.numpy(),
+                        geo=geo.numpy(), T_err_mean=T_err_mean.numpy(), eucl=eucl.numpy())
+    print("pose_metrics.npz written")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        pose_metrics_golden()
+        sys.exit(0)
     main()

@@ -26,3 +26,18 @@ def test_oracle_reproduces_golden(name):
     for lv in (3, 2, 1):
         assert float((out[f"src_xyz_corres_{lv}"] - gd[f"src_xyz_corres_{lv}"]).abs().max()) < 1e-4
         assert float((out[f"src_dst_weights_{lv}"] - gd[f"src_dst_weights_{lv}"]).abs().max()) < 1e-6
+
+
+def test_metrics_oracle_reproduces_reference_outputs():
+    """oracle/ref_metrics.py against tests/golden/pose_metrics.npz = outputs of the reference's calc_error_np,
+    calc_rot_rre_err and calc_tran_rte_err (fp32 torch in the reference, fp64 numpy in the oracle)."""
+    import numpy as np
+    from oracle import ref_metrics as RM
+    g = {k: v.numpy() for k, v in load_golden("pose_metrics").items()}
+    per_pair = np.array([RM.calc_error_np(g["pred_R"][i], g["pred_t"][i], g["gt_R"][i], g["gt_t"][i]) for i in range(64)])
+    d = np.abs(per_pair - g["calc_error_np"])                        # calc_error_np ran in fp32 numpy
+    assert d[:, 0].max() < 2e-3 and d[:, 1].max() < 1e-6
+    R_err_deg, geo, _ = RM.calc_rot_rre_err(g["pred_R"], g["gt_R"])
+    T_err_mean, eucl, _ = RM.calc_tran_rte_err(g["pred_t"], g["gt_t"])
+    assert np.abs(geo - g["geo"]).max() < 2e-3 and np.abs(R_err_deg - g["R_err_deg"]).max() < 2e-3   # fp32 acos / atan2
+    assert np.abs(eucl - g["eucl"]).max() < 1e-6 and np.abs(T_err_mean - g["T_err_mean"]).max() < 1e-6

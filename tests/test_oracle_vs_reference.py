@@ -106,3 +106,28 @@ def test_model_v2_matches_reference():
     for lv in range(3):
         assert float(RL.rotation_angle_deg(a["rotation"][lv], b["rotation"][lv]).max()) < 1e-4
         assert float((a["translation"][lv] - b["translation"][lv]).abs().max()) < 1e-5
+
+
+def test_metrics_oracle_matches_reference_functions():
+    """oracle/ref_metrics.py against the UNMODIFIED models/utils.py:calc_error_np and losses/losses.py:calc_rot_rre_err /
+    calc_tran_rte_err (Euler conversion injected, see ref_harness.load_reference_losses) on fresh random poses."""
+    import numpy as np
+    from oracle import ref_metrics as RM
+    sys_path_tests = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mk", __import__("os").path.join(sys_path_tests, "make_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    U, Ls = H.load_reference().utils, H.load_reference_losses()
+    pred_R, pred_t = mk.random_poses(32, 101)
+    gt_R, gt_t = mk.random_poses(32, 102)
+    for i in range(32):
+        want = U.calc_error_np(pred_R[i].numpy(), pred_t[i].numpy(), gt_R[i].numpy(), gt_t[i].numpy())
+        got = RM.calc_error_np(pred_R[i].numpy(), pred_t[i].numpy(), gt_R[i].numpy(), gt_t[i].numpy())
+        assert abs(want[0] - got[0]) < 1e-3 and abs(want[1] - got[1]) < 1e-6
+    R_err_deg, geo = Ls.calc_rot_rre_err(pred_R, gt_R)
+    T_err_mean, eucl = Ls.calc_tran_rte_err(pred_t, gt_t)
+    o_deg, o_geo, _ = RM.calc_rot_rre_err(pred_R.numpy(), gt_R.numpy())
+    o_tm, o_eu, _ = RM.calc_tran_rte_err(pred_t.numpy(), gt_t.numpy())
+    assert np.abs(o_geo - geo.numpy()).max() < 2e-3 and np.abs(o_deg - R_err_deg.numpy()).max() < 2e-3
+    assert np.abs(o_eu - eucl.numpy()).max() < 1e-6 and np.abs(o_tm - T_err_mean.numpy()).max() < 1e-6
