@@ -37,12 +37,39 @@ def ref_ext():
     return mod
 
 
+def around_the_path():
+    """SURVEY 8(f) rows 1-2 on the device: range filter + resampling + perturbation of 32 raw 120k-point sweeps into the
+    [32,16384,3] pair batch, and the pose-error metrics of a 256-pair batch.  HBM-bound kernels: GB/s of algorithmic bytes."""
+    from pcd_reg_hregnet_b200 import metrics, preprocess
+    B, Nraw, n = 32, 120000, 16384
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sweeps = [torch.randn(Nraw, 3, device="cuda", generator=g) * 40 for _ in range(B)]
+    cat = torch.cat(sweeps, 0)
+    offs = torch.arange(0, (B + 1) * Nraw, Nraw, device="cuda", dtype=torch.int64)
+    tw = torch.randn(B, 6, device="cuda", generator=g) * 0.1
+    t = timeit(lambda: preprocess.remove_points_by_range_batched(cat, None, offs, 80.0, Nraw))
+    _, _, cnt = preprocess.remove_points_by_range_batched(cat, None, offs, 80.0, Nraw)
+    kept = int(cnt.sum())
+    r = {"op": "range_filter", "sweeps": B, "points": Nraw, "kept": kept, "ms": t,
+         "GBps": (B * Nraw * 12 + kept * 12) / t / 1e6}
+    print(json.dumps(r), flush=True)
+    t = timeit(lambda: preprocess.prepare_pairs(sweeps, 80.0, n, tw))
+    print(json.dumps({"op": "prepare_pairs (filter + resample + SE3 perturbation, incl. host glue)", "pairs": B, "ms": t}), flush=True)
+    R = torch.linalg.qr(torch.randn(256, 3, 3, device="cuda", generator=g))[0]
+    tt = torch.randn(256, 3, device="cuda", generator=g)
+    t = timeit(lambda: metrics.pose_errors(R, tt, R.flip(0), tt.flip(0)))
+    print(json.dumps({"op": "pose_errors", "pairs": 256, "ms": t}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="4096,8192,16384,32768,65536,131072")
     ap.add_argument("--batches", default="1,32,64")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--around", action="store_true", help="time the steps around the path (input pipeline, metrics) instead")
     a = ap.parse_args()
+    if a.around:
+        return around_the_path()
     ref = ref_ext()
     rows = []
     for B in [int(b) for b in a.batches.split(",")]:

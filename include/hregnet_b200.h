@@ -192,6 +192,29 @@ int hrn_cosine_pick(const float* cosm, const float* rowmax, const float* colmax,
 int hrn_weighted_kabsch(const float* src, const float* cor, const float* w, int B, int N, const float* R_prev,
                         const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * 6. Steps around the path: input pipeline in front of it, evaluation metrics behind it
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* dataset/dataset_utils.py:113-125 remove_points_by_range for a batch of sweeps: stable compaction of the points with
+ * ||p|| < max_range (numpy float32 norm semantics, bit-identical kept set).  xyz [total,3], intensity [total]
+ * (nullable), offsets [n_sweeps+1] int64 on the device; max_sweep_points >= the largest sweep (host value);
+ * scratch [n_sweeps * ceil(max_sweep_points/4096)] int32.  Kept points of sweep s land in rows
+ * [offsets[s], offsets[s]+count[s]) of the outputs; count [n_sweeps] int32.  Not in place. */
+int hrn_range_filter(const float* xyz, const float* intensity, const long long* offsets, int n_sweeps,
+                     long long max_sweep_points, float max_range, float* xyz_out, float* intensity_out, int* count,
+                     int* scratch, void* stream);
+
+/* dataset/dataset_utils.py:188-223 PointCloudResampler for a batch of filtered sweeps (hrn_range_filter layout):
+ * out[b,i,:] = sweep_b[j], j = i for i < count[b] when count[b] <= n (the cloud, then its padding picks idx[b,i]),
+ * j = idx[b,i] otherwise (the subset drawn without replacement).  idx [B,n] int32; out [B,n,3]. */
+int hrn_resample_gather(const float* xyz, const long long* offsets, const int* count, const int* idx, int B, int n,
+                        float* out, void* stream);
+
+/* transform/rodrigues.py:526-550 SE3.exp: twist [B,6] = (w, v) -> g [B,16] row-major 4x4 (the perturbation applied by
+ * transform/dataset_transforms.py:128-140; apply it with hrn_transform_points). */
+int hrn_se3_exp(const float* twist, int B, float* g, void* stream);
+
 /* Pose-error metrics fused after the pose head / the pose all-gather.  Replaces
  * losses/losses.py:138-164 (calc_rot_rre_err, calc_tran_rte_err), models/utils.py:132-138 (calc_error_np) [mode 0:
  * R_err = pred_R^T gt_R, t_err = pred_t - gt_t] and metrics/calibeval.py:72-106,172-196 (add_batch, geodesic_distance)

@@ -136,6 +136,18 @@ def load_reference_losses():
     return mod
 
 
+def load_reference_file(rel_path, name, stubs=()):
+    """An unmodified reference source file loaded as a stand-alone module; `stubs` = names of absent third-party modules
+    (e.g. open3d) registered as empty modules first -- the functions exercised by the tests do not touch them."""
+    import importlib.util
+    for st in stubs:
+        sys.modules.setdefault(st, types.ModuleType(st))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel_path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 class Args:
     use_fps = True
     use_weights = True

@@ -3,8 +3,11 @@ oracle/ref_harness.py (native ops = oracle C restatements).  Run in the build co
 
     python tests/golden/make_golden.py            # model fixtures
     python tests/golden/make_golden.py metrics    # pose_metrics.npz only
+    python tests/golden/make_golden.py preprocess # preprocess.npz only
 
 Fixtures
+  preprocess.npz           two raw clouds through the reference's range filter + fixed-size resampler (pad and
+                           subsample cases, the numpy-drawn index lists included) and 16 twists through SE3.exp.
   pose_metrics.npz         64 seeded random pose pairs and the outputs of the reference's own metric functions
                            (models/utils.py:132-138 calc_error_np, losses/losses.py:138-164 calc_rot_rre_err /
                            calc_tran_rte_err) on them.
@@ -105,8 +108,38 @@ def pose_metrics_golden():
     print("pose_metrics.npz written")
 
 
+def preprocess_golden():
+    """Outputs of the reference's own PointCloudFilter.remove_points_by_range, PointCloudResampler (seeded numpy RNG; the
+    drawn index lists are stored) and SE3.exp (dataset/dataset_utils.py:113-125,177-223, transform/rodrigues.py:526-550)."""
+    DU = H.load_reference_file("dataset/dataset_utils.py", "_ref_dataset_utils", stubs=("open3d",))
+    RO = H.load_reference_file("transform/rodrigues.py", "_ref_rodrigues")
+    rng = np.random.default_rng(5)
+    d = {}
+    for name, n, num in (("a", 6000, 4096), ("b", 3000, 4096)):          # a: subsample, b: pad
+        pc = (rng.normal(size=(n, 3)) * np.array([40.0, 40.0, 3.0])).astype(np.float32)
+        it = rng.random(n).astype(np.float32)
+        fp, fi = DU.PointCloudFilter(max_range=60.0).remove_points_by_range(pc, it)
+        np.random.seed(17)
+        m = fp.shape[0]
+        idx = np.random.choice(m, num - m, replace=True) if m <= num else np.random.choice(m, num, replace=False)
+        np.random.seed(17)
+        rp, ri = DU.PointCloudResampler(num)(fp, fi)
+        d.update({f"{name}_pc": pc, f"{name}_int": it, f"{name}_filtered": fp, f"{name}_filtered_int": fi,
+                  f"{name}_idx": idx.astype(np.int64), f"{name}_resampled": rp, f"{name}_resampled_int": ri})
+    x = torch.tensor(rng.normal(size=(16, 6)) * 0.3, dtype=torch.float32)
+    x[0] *= 1e-3                                                          # Taylor branch of the sinc functions
+    x[1, :3] = 0.0
+    d["twist"] = x.numpy()
+    d["se3_exp"] = RO.SE3().exp(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **d)
+    print("preprocess.npz written")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         pose_metrics_golden()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        preprocess_golden()
         sys.exit(0)
     main()

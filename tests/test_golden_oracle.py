@@ -41,3 +41,17 @@ def test_metrics_oracle_reproduces_reference_outputs():
     T_err_mean, eucl, _ = RM.calc_tran_rte_err(g["pred_t"], g["gt_t"])
     assert np.abs(geo - g["geo"]).max() < 2e-3 and np.abs(R_err_deg - g["R_err_deg"]).max() < 2e-3   # fp32 acos / atan2
     assert np.abs(eucl - g["eucl"]).max() < 1e-6 and np.abs(T_err_mean - g["T_err_mean"]).max() < 1e-6
+
+
+def test_preprocess_oracle_reproduces_reference_outputs():
+    """oracle/ref_preprocess.py against tests/golden/preprocess.npz (reference PointCloudFilter / PointCloudResampler /
+    SE3.exp outputs): kept sets and resampled clouds bit-identical, SE3.exp within fp32 rounding."""
+    import numpy as np
+    from oracle import ref_preprocess as RP
+    g = {k: v.numpy() for k, v in load_golden("preprocess").items()}
+    for n in ("a", "b"):
+        fp, fi = RP.remove_points_by_range(g[f"{n}_pc"], g[f"{n}_int"], 60.0)
+        assert np.array_equal(fp, g[f"{n}_filtered"]) and np.array_equal(fi, g[f"{n}_filtered_int"])
+        rp, ri = RP.resample(fp, fi, 4096, g[f"{n}_idx"])
+        assert np.array_equal(rp, g[f"{n}_resampled"]) and np.array_equal(ri, g[f"{n}_resampled_int"])
+    assert np.abs(RP.se3_exp(g["twist"]) - g["se3_exp"]).max() < 1e-6

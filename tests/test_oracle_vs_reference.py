@@ -131,3 +131,29 @@ def test_metrics_oracle_matches_reference_functions():
     o_tm, o_eu, _ = RM.calc_tran_rte_err(pred_t.numpy(), gt_t.numpy())
     assert np.abs(o_geo - geo.numpy()).max() < 2e-3 and np.abs(o_deg - R_err_deg.numpy()).max() < 2e-3
     assert np.abs(o_eu - eucl.numpy()).max() < 1e-6 and np.abs(o_tm - T_err_mean.numpy()).max() < 1e-6
+
+
+def test_preprocess_oracle_matches_reference_classes():
+    """oracle/ref_preprocess.py against the UNMODIFIED dataset/dataset_utils.py (PointCloudFilter.remove_points_by_range,
+    PointCloudResampler under a seeded numpy RNG) and transform/rodrigues.py (SE3.exp) on fresh inputs."""
+    import numpy as np
+    from oracle import ref_preprocess as RP
+    DU = H.load_reference_file("dataset/dataset_utils.py", "_ref_dataset_utils", stubs=("open3d",))
+    RO = H.load_reference_file("transform/rodrigues.py", "_ref_rodrigues")
+    rng = np.random.default_rng(77)
+    for n, num in ((9000, 2048), (1500, 2048), (2048, 2048)):
+        pc = (rng.normal(size=(n, 3)) * 35).astype(np.float32)
+        it = rng.random(n).astype(np.float32)
+        a, b = DU.PointCloudFilter(max_range=50.0).remove_points_by_range(pc, it)
+        c, d = RP.remove_points_by_range(pc, it, 50.0)
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+        m = a.shape[0]
+        np.random.seed(n)
+        idx = np.random.choice(m, num - m, replace=True) if m <= num else np.random.choice(m, num, replace=False)
+        np.random.seed(n)
+        r1 = DU.PointCloudResampler(num)(a, b)
+        r2 = RP.resample(a, b, num, idx)
+        assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1])
+    x = torch.tensor(rng.normal(size=(32, 6)) * 0.4, dtype=torch.float32)
+    x[:4] *= 1e-3
+    assert np.abs(RO.SE3().exp(x).numpy() - RP.se3_exp(x.numpy())).max() < 1e-6
