@@ -171,10 +171,13 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                             if (c0 + ch * 8 < N) {
                                 const float4 b0 = *reinterpret_cast<const float4*>(bb + c0 + ch * 8);
                                 const float4 b1 = *reinterpret_cast<const float4*>(bb + c0 + ch * 8 + 4);
-                                const float x[8] = {fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, 0.f),
-                                                    fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, 0.f),
-                                                    fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, 0.f),
-                                                    fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, 0.f)};
+                                float s[8];                       // bias additions as packed fp32x2 adds
+                                f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1])), f2_pack(b0.x, b0.y)), s[0], s[1]);
+                                f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])), f2_pack(b0.z, b0.w)), s[2], s[3]);
+                                f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])), f2_pack(b1.x, b1.y)), s[4], s[5]);
+                                f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])), f2_pack(b1.z, b1.w)), s[6], s[7]);
+                                const float x[8] = {fmaxf(s[0], 0.f), fmaxf(s[1], 0.f), fmaxf(s[2], 0.f), fmaxf(s[3], 0.f),
+                                                    fmaxf(s[4], 0.f), fmaxf(s[5], 0.f), fmaxf(s[6], 0.f), fmaxf(s[7], 0.f)};
                                 split_store8(x, h_hi + ch * CTM + rt, h_lo + ch * CTM + rt);
                             }
                         }
@@ -367,11 +370,9 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     const float4 t = vv[2 * g + j];
                     const float s_ = ss[2 * g + j];
                     const float x0 = t.x * s_, x1 = t.y * s_, x2 = t.z * s_, x3 = t.w * s_;
-                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
-                    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
-                    const uint32_t H0 = *reinterpret_cast<const uint32_t*>(&h0), H1 = *reinterpret_cast<const uint32_t*>(&h1);
-                    const uint32_t L0 = *reinterpret_cast<const uint32_t*>(&l0), L1 = *reinterpret_cast<const uint32_t*>(&l1);
+                    uint32_t H0, H1, L0, L1;
+                    split_pair(x0, x1, H0, L0);
+                    split_pair(x2, x3, H1, L1);
                     const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hf ? H0 : L0, 8);
                     const uint32_t r1 = __shfl_xor_sync(0xffffffffu, hf ? H1 : L1, 8);
                     const int slot_a = (2 * j + cl) * CTM + pw * 16 + g * 8 + rsub;

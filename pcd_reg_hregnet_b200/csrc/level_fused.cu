@@ -103,10 +103,13 @@ __device__ __forceinline__ void bias_relu32(const uint32_t (&v)[32], const float
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * q);
-        f[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
-        f[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
-        f[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
-        f[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
+        float s0, s1, s2, s3;                                   // two packed fp32x2 adds for the four bias additions
+        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), f2_pack(b4.x, b4.y)), s0, s1);
+        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), f2_pack(b4.z, b4.w)), s2, s3);
+        f[4 * q + 0] = fmaxf(s0, 0.f);
+        f[4 * q + 1] = fmaxf(s1, 0.f);
+        f[4 * q + 2] = fmaxf(s2, 0.f);
+        f[4 * q + 3] = fmaxf(s3, 0.f);
     }
 }
 

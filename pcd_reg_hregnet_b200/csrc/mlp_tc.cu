@@ -445,11 +445,9 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                     const float s_ = SIMPLE ? 1.f : ss[2 * g + j];
                     const float x0 = SIMPLE ? t.x : t.x * s_, x1 = SIMPLE ? t.y : t.y * s_;
                     const float x2 = SIMPLE ? t.z : t.z * s_, x3 = SIMPLE ? t.w : t.w * s_;
-                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
-                    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
-                    const uint32_t H0 = *reinterpret_cast<const uint32_t*>(&h0), H1 = *reinterpret_cast<const uint32_t*>(&h1);
-                    const uint32_t L0 = *reinterpret_cast<const uint32_t*>(&l0), L1 = *reinterpret_cast<const uint32_t*>(&l1);
+                    uint32_t H0, H1, L0, L1;
+                    split_pair(x0, x1, H0, L0);
+                    split_pair(x2, x3, H1, L1);
                     const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hf ? H0 : L0, 8);
                     const uint32_t r1 = __shfl_xor_sync(0xffffffffu, hf ? H1 : L1, 8);
                     const int slot_a = (2 * j + cl) * TM + pw * 16 + g * 8 + rsub;

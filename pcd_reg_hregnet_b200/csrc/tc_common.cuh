@@ -84,26 +84,30 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     return v;
 }
 
+// bf16 hi / lo split of a pair: hi = rn_bf16(x) packed, lo = rn_bf16(x - float(hi)) packed; the two residuals are taken
+// with one packed fp32x2 subtract (each half rounds like the scalar FADD)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked in place
+    const unsigned long long hf = ((unsigned long long)(hb & 0xffff0000u) << 32) | (unsigned long long)(hb << 16);
+    unsigned long long xv, rv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(x0), "f"(x1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rv) : "l"(xv), "l"(hf));
+    float r0, r1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(rv));
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    hi = hb;
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // split 8 floats into bf16 hi / lo and store both 16-byte core-matrix rows.  The residuals x - float(hi) are taken two
 // at a time with the packed fp32x2 subtract (each half rounds like the scalar FADD): the conversion loops are bound by
 // their instruction count.
 __device__ __forceinline__ void split_store8(const float (&x)[8], uint4* dst_hi, uint4* dst_lo) {
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-        // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked in place
-        const unsigned long long hf = ((unsigned long long)(hb & 0xffff0000u) << 32) | (unsigned long long)(hb << 16);
-        unsigned long long xv, rv;
-        asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(x[2 * i]), "f"(x[2 * i + 1]));
-        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rv) : "l"(xv), "l"(hf));
-        float r0, r1;
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(rv));
-        const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
-        hi[i] = hb;
-        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-    }
+    for (int i = 0; i < 4; ++i) split_pair(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
     *dst_hi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *dst_lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
