@@ -229,7 +229,18 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(acc + c0, v);
-                if (act == HRN_ACT_RELU) {
+                if (act == HRN_ACT_RELU && c0 + 32 <= cout) {
+                    const f32x2_t a2 = f2_pack(a_w, a_w);             // packed fp32x2 bias add / attention scaling
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(b3 + c0 + e);
+                        float s0, s1, s2, s3;
+                        f2_unpack(f2_add(f2_pack(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), f2_pack(b4.x, b4.y)), s0, s1);
+                        f2_unpack(f2_add(f2_pack(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])), f2_pack(b4.z, b4.w)), s2, s3);
+                        f2_unpack(f2_mul(f2_pack(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), a2), f[e], f[e + 1]);
+                        f2_unpack(f2_mul(f2_pack(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), a2), f[e + 2], f[e + 3]);
+                    }
+                } else if (act == HRN_ACT_RELU) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) f[e] = (c0 + e < cout) ? fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f) * a_w : 0.f;
                 } else {

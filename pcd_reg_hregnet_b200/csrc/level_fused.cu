@@ -322,8 +322,10 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_D3 + c0 + 4 * q);
-                x1 = fmaxf(x1, fmaxf(fmaxf(__uint_as_float(v[4 * q]) + b4.x, __uint_as_float(v[4 * q + 1]) + b4.y),
-                                     fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, __uint_as_float(v[4 * q + 3]) + b4.w)));
+                float s0, s1, s2, s3;
+                f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), f2_pack(b4.x, b4.y)), s0, s1);
+                f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), f2_pack(b4.z, b4.w)), s2, s3);
+                x1 = fmaxf(x1, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
             }
         }
         float gmax = hrn_warp_max(x1);
@@ -378,8 +380,9 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCE + c0, v);
             bias_relu32(v, sB + Cfg::B_D3 + c0, f);
+            const f32x2_t a2 = f2_pack(a, a);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] *= a;
+            for (int e = 0; e < 32; e += 2) f2_unpack(f2_mul(f2_pack(f[e], f[e + 1]), a2), f[e], f[e + 1]);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
