@@ -206,9 +206,21 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                 for (int c0 = eg * 32; c0 < cout; c0 += 64) {
                     uint32_t v[32];
                     tmem_ld32(acc + c0, v);
+                    if (c0 + 32 <= cout) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (c0 + e < cout) x1 = fmaxf(x1, fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f));
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(b3 + c0 + e);
+                            float s0, s1, s2, s3;
+                            f2_unpack(f2_add(f2_pack(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), f2_pack(b4.x, b4.y)), s0, s1);
+                            f2_unpack(f2_add(f2_pack(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])), f2_pack(b4.z, b4.w)), s2, s3);
+                            x1 = fmaxf(x1, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
+                        }
+                        x1 = fmaxf(x1, 0.f);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < cout) x1 = fmaxf(x1, fmaxf(__uint_as_float(v[e]) + b3[c0 + e], 0.f));
+                    }
                 }
                 sX[eg * CTM + rt] = x1;
                 asm volatile("bar.sync 1, 256;" ::: "memory");             // the 8 epilogue warps
