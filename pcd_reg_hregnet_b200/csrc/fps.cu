@@ -173,35 +173,46 @@ fps_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, flo
 
 // ---------------------------------------------------------------------------------------------------------------
 // Cluster variant: CS CTAs (thread-block cluster) cooperate on ONE cloud; every point lives in registers
-// (x, y, z, running min-distance [, weight]) -- no shared-memory traffic in the update loop at all.
-// Per iteration (3 CTA barriers; warps that are not on the critical path are parked at a hardware barrier, they
-// never spin):
-//   A. every thread updates its P points (8 FP instructions each), warp maximum by REDUX, barrier;
-//   B. only the warps that hold the CTA maximum resolve the reference's tie-break key and publish {key, xyz}, barrier;
-//   C. warp 0 picks the CTA winner and sends it as a 32-byte packet to the mailbox of every CTA of the cluster with
-//      st.async (distributed shared memory; the store itself performs complete_tx on the receiver's mbarrier), waits
-//      on its own mbarrier for the CS packets of this iteration, takes the best, barrier.
-// Mailboxes / mbarriers are double-buffered by iteration parity: a CTA can run at most one iteration ahead of its
-// peers because iteration j+1 needs every peer's packet j.
-struct __align__(16) FpsMail {
-    unsigned ordval, key;
-    float x, y;
-    float z;
-    unsigned pad0, pad1, pad2;
-};
+// (x, y, z, running min-distance [, weight]) -- no shared-memory traffic in the update loop at all -- and the
+// iteration has NO barrier of any kind (no CTA barrier, no mbarrier, no leader warp):
+//   A. every thread updates its P points (packed fp32x2), warp maximum by REDUX;
+//   B. every warp resolves the reference's tie-break key among its own holders of the warp maximum (REDUX min) and
+//      writes ONE self-validating 8-byte packet {ordered max | key + iteration tag} into the mailbox slot (rank, warp)
+//      of EVERY CTA of the cluster, its own included (one relaxed store per destination CTA);
+//   C. every warp polls the CS*NWARP packets of this iteration (one or a few per lane) until all tags match, reduces
+//      them with two REDUX, decodes the winner's point index from the key and reads its coordinates from a copy of
+//      the whole cloud in shared memory (FULL: N <= 18 K points) or from global memory / L2 (larger clouds).
+// What the ncu source view and tools/fps_probe.cu showed on B200: with 16 warps per SM the iteration is bound by the
+// ISSUE slots of the per-warp bookkeeping (300 instructions per warp and iteration in the first barrier-free version,
+// only 75 of them the distance update) and by branch-resolve stalls, not by the DSMEM round trip or the barriers -- three
+// different synchronisation schemes (CTA barriers + st.async/mbarrier leader exchange, st.async packets per warp,
+// polled packets per warp) all took 2130 cycles per iteration.  Hence the 8-byte packet (no coordinates, no select
+// chains, no REDUX.OR broadcasts) and the branch-free send.
+// 8-byte aligned stores/loads are single-copy atomic and every packet validates itself.  Mailboxes are double-buffered
+// by iteration parity: iteration j+1 of any warp needs packet j of every warp of the cluster, so nobody can be more
+// than one iteration ahead of anybody else, and buffer j&1 is only rewritten (iteration j+2) after every warp has
+// consumed it.  Packet: low word = ordered maximum, high word = key (22 bits) | (j & 1023) << 22; the mailboxes start
+// as all-ones, which matches no tag in use before it has been overwritten.
+#ifdef FPS_PROBE
+__device__ long long g_fps_probe[64 * 8];
+__device__ unsigned g_fps_sink;
+#define FPS_STAMP(i) do { if (blockIdx.x == 0 && tid == FPS_PROBE_TID && j >= 500 && j < 564) g_fps_probe[(j - 500) * 8 + (i)] = clock64(); } while (0)
+#else
+#define FPS_STAMP(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int THREADS, int P, bool WEIGHTED>
+template <int THREADS, int P, bool WEIGHTED, bool MONO, bool FULL>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, float* __restrict__ temp_io,
                    int32_t* __restrict__ idx_out, int N, int M, int log2T, int CS) {
     constexpr int NWARP = THREADS / 32;
-    __shared__ unsigned s_wmax[32];
-    __shared__ FpsMail s_slot[32];
-    __shared__ FpsMail s_mail[2][8];
-    __shared__ FpsMail s_best;
-    __shared__ __align__(8) uint64_t s_mbar[2];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int S = CS * NWARP;                              // packets per iteration and mailbox
+    unsigned long long* s_mail = reinterpret_cast<unsigned long long*>(s_dyn);      // [2][S]
+    float* s_cloud = reinterpret_cast<float*>(s_mail + 2 * S);                       // FULL: [N][3]
+    __shared__ __align__(8) uint64_t s_mbar[2];                 // MBAR only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned rank;
@@ -218,6 +229,15 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
     };
     const int stride = CS * THREADS;
     const int k0 = (int)rank * THREADS + tid;
+    // MONO (chosen by the launcher): stride is a multiple of Tref, so (k mod Tref) is the same for all of this thread's
+    // points and key(k0 + p*stride) = key(k0) + p * (stride / Tref): the thread's winner is simply the first p that
+    // holds its maximum
+    const unsigned key_base = key_of(k0), key_step = (unsigned)stride >> log2T;
+    unsigned pkey[MONO ? 1 : P];                           // general case: the key of every point of the thread
+    if (!MONO) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) pkey[p] = (k0 + p * stride < N) ? key_of(k0 + p * stride) : 0xffffffffu;
+    }
 
     float px[P], py[P], pz[P], pt[P], pw[P];
 #pragma unroll
@@ -230,20 +250,51 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
         pw[p] = (WEIGHTED && valid) ? weights[k] : 0.f;
         pt[p] = valid ? (temp_io ? temp_io[k] : 1e10f) : -CUDART_INF_F;
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&s_mbar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&s_mbar[1])) : "memory");
+    if (FULL)
+        for (int i = tid; i < 3 * N; i += THREADS) s_cloud[i] = xyz[i];
+    for (int i = tid; i < 2 * S; i += THREADS) s_mail[i] = ~0ull;
+    // lane c < CS writes this warp's packet into CTA c: generic address of the slot (parity 0; parity 1 = + S*8 bytes)
+    const uint32_t mail_u32 = fps_smem_u32(s_mail);
+    const uint32_t mail_par_bytes = (uint32_t)S * 8u;
+    // How a warp waits for the packets (measured, tools/fps_probe.cu): with 8 warps per CTA plain polling of the tagged
+    // packets is fastest (342 vs 414 ns per iteration at N = 1024); with 16 warps the polling loads of the early warps
+    // fight the late warps for issue slots and the shared-memory port (a tight poll loop: 1710 ns, a lazier one: 815 ns
+    // at N = 16384), so those kernels sleep on an mbarrier instead and the packets arrive by st.async (807 ns).
+    constexpr bool MBAR = THREADS > 256;
+    // st.async delivers the packet and counts its 8 bytes on the receiver's mbarrier; the waiters sleep in hardware
+    const uint32_t mbar_u32 = fps_smem_u32(&s_mbar[0]);
+    const unsigned tx_bytes = (unsigned)S * 8u;
+    uint32_t rslot32 = 0u, rbar32 = 0u;
+    unsigned long long rslot = 0ull;
+    if (MBAR && lane < CS) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot32)
+                     : "r"(mail_u32 + (uint32_t)((int)rank * NWARP + warp) * 8u), "r"((unsigned)lane));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar32) : "r"(mbar_u32), "r"((unsigned)lane));
+    }
+    if (MBAR && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_u32) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_u32 + 8u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // iterations 1 (parity 1) and 2 (parity 0) are armed here, iteration j+2 right after iteration j completed
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_u32), "r"(tx_bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_u32 + 8u), "r"(tx_bytes) : "memory");
+    }
+    if (!MBAR && lane < CS) {
+        uint32_t r32;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r32)
+                     : "r"(mail_u32 + (uint32_t)((int)rank * NWARP + warp) * 8u), "r"((unsigned)lane));
+        asm volatile("cvta.shared::cluster.u64 %0, %1;" : "=l"(rslot) : "l"((unsigned long long)r32));
     }
     float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
     if (tid == 0 && rank == 0) idx_out[0] = 0;
     __syncthreads();
-    if (CS > 1) {   // every CTA of the cluster has initialised its mbarriers before anyone signals them remotely
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    }
+    // every CTA of the cluster has initialised its mailboxes before anyone writes into them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
+#pragma unroll 1
     for (int j = 1; j < M; ++j) {
         // ---- A: update, warp maximum --------------------------------------------------------------------------
+        FPS_STAMP(0);
         float m = -CUDART_INF_F;
         if (P % 2 == 0) {
             const f32x2_t cx2 = f2_pack(x1, x1), cy2 = f2_pack(y1, y1), cz2 = f2_pack(z1, z1);
@@ -266,97 +317,84 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
                 m = fmaxf(m, pt[p]);
             }
         }
-        const unsigned om = hrn_ford(m);
+        // unweighted distances are >= +0 (or -inf for padding): flipping the sign bit is order preserving there
+        const unsigned om = WEIGHTED ? hrn_ford(m) : (__float_as_uint(m) ^ 0x80000000u);
         const unsigned wm = __reduce_max_sync(0xffffffffu, om);
-        if (lane == 0) s_wmax[warp] = wm;
-        __syncthreads();
-        // ---- B: holders of the CTA maximum resolve the tie-break key ---------------------------------------------
-        const unsigned g = __reduce_max_sync(0xffffffffu, lane < NWARP ? s_wmax[lane] : 0u);
-        if (wm == g) {                                   // warp-uniform
-            unsigned key = 0xffffffffu;
-            float cx = 0.f, cy = 0.f, cz = 0.f;
-            if (om == g) {
-                if ((stride & (int)tmask) == 0) {
-                    // stride is a multiple of Tref: (k mod Tref) is the same for all of this thread's points, so the
-                    // reference key grows with p -> the winner is simply the first p that holds the maximum
-                    int pf = 0;
+        FPS_STAMP(1);
+        // ---- B: the warp's winner (reference tie-break key among the holders of the warp maximum), packet out ------
+        // (a thread without any valid point holds -inf: its warp can only tie with it if the whole warp is padding, and
+        // such a packet never wins: some warp of the cluster always holds a valid point with a distance >= 0)
+        unsigned key;
+        if (MONO) {
+            key = key_base + (unsigned)(P - 1) * key_step;
 #pragma unroll
-                    for (int p = P - 1; p >= 0; --p)
-                        if (pt[p] == m && k0 + p * stride < N) pf = p;
-                    cx = px[0]; cy = py[0]; cz = pz[0];
+            for (int p = P - 2; p >= 0; --p)
+                if (pt[p] == m) key = key_base + (unsigned)p * key_step;         // per-thread constants
+        } else {
+            key = 0xffffffffu;
 #pragma unroll
-                    for (int p = 1; p < P; ++p)
-                        if (pf == p) { cx = px[p]; cy = py[p]; cz = pz[p]; }
-                    key = key_of(k0 + pf * stride);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const int k = k0 + p * stride;
-                        const unsigned kk = key_of(k);
-                        if (k < N && pt[p] == m && kk < key) { key = kk; cx = px[p]; cy = py[p]; cz = pz[p]; }
-                    }
-                }
-            }
-            const unsigned wkey = __reduce_min_sync(0xffffffffu, key);
-            if (key == wkey && om == g) {
-                s_slot[warp].key = key; s_slot[warp].x = cx; s_slot[warp].y = cy; s_slot[warp].z = cz;
-            }
-        } else if (lane == 0) {
-            s_slot[warp].key = 0xffffffffu;
+            for (int p = 0; p < P; ++p)
+                if (pt[p] == m && pkey[p] < key) key = pkey[p];
         }
-        __syncthreads();
-        // ---- C: warp 0 = CTA winner; cluster exchange through the mailboxes ------------------------------------
+        if (om != wm) key = 0xffffffffu;
+        const unsigned wkey = __reduce_min_sync(0xffffffffu, key);
         const int par = j & 1;
-        const uint32_t mb = fps_smem_u32(&s_mbar[par]);
-        if (warp == 0) {
-            const unsigned k2 = lane < NWARP ? s_slot[lane].key : 0xffffffffu;
-            const unsigned kmin = __reduce_min_sync(0xffffffffu, k2);
-            const int src = __ffs(__ballot_sync(0xffffffffu, k2 == kmin)) - 1;
-            const float sx = s_slot[src].x, sy = s_slot[src].y, sz = s_slot[src].z;
-            if (CS > 1) {
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(CS * 32) : "memory");
-                if (lane < CS) {
-                    uint32_t rbox, rbar;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbox) : "r"(fps_smem_u32(&s_mail[par][rank])), "r"((unsigned)lane));
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(mb), "r"((unsigned)lane));
-                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                                 ::"r"(rbox), "r"(g), "r"(kmin), "r"(__float_as_uint(sx)), "r"(__float_as_uint(sy)), "r"(rbar) : "memory");
-                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                                 ::"r"(rbox + 16), "r"(__float_as_uint(sz)), "r"(0u), "r"(0u), "r"(0u), "r"(rbar) : "memory");
-                }
-            } else if (lane == 0) {
-                s_best.key = kmin; s_best.x = sx; s_best.y = sy; s_best.z = sz;
-            }
+        const unsigned tag = ((unsigned)j & 0x3ffu) << 22;
+        if (lane < CS) {
+            const unsigned long long v = ((unsigned long long)((wkey & 0x3fffffu) | tag) << 32) | wm;
+            if (MBAR)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                         ::"r"(rslot32 + (par ? mail_par_bytes : 0u)), "l"(v), "r"(rbar32 + (par ? 8u : 0u)) : "memory");
+            else
+            asm volatile("st.relaxed.cluster.b64 [%0], %1;" ::"l"(rslot + (par ? mail_par_bytes : 0u)), "l"(v) : "memory");
         }
-        unsigned bkey;
-        if (CS > 1) {
-            // every thread sleeps on the CTA's own mailbox barrier until the CS packets of iteration j have landed
-            // (hardware wait, no polling traffic), then takes the best of them -- no third CTA barrier
-            unsigned done;
+        FPS_STAMP(2);
+        if (MBAR) {
+            const uint32_t mb = mbar_u32 + (par ? 8u : 0u);
             const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;   // u-th use of mbarrier j&1, u = (j-1)/2
+            unsigned done;
             do {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(done) : "r"(mb), "r"(parity) : "memory");
             } while (!done);
-            unsigned bval = 0u;
-            bkey = 0xffffffffu;
-#pragma unroll 1
-            for (int c = 0; c < CS; ++c) {
-                const FpsMail mm = s_mail[par][c];
-                if (mm.ordval > bval || (mm.ordval == bval && mm.key < bkey)) {
-                    bval = mm.ordval; bkey = mm.key; x1 = mm.x; y1 = mm.y; z1 = mm.z;
+            if (tid == 0 && j + 2 < M)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tx_bytes) : "memory");
+        }
+        // ---- C: poll this iteration's packets (one or a few per lane), pick the winner ---------------------------------
+        unsigned bo = 0u, bk = 0x3fffffu;
+        {
+            const uint32_t mail = mail_u32 + (par ? mail_par_bytes : 0u) + (uint32_t)lane * 8u;
+            if (lane < S) {
+                unsigned h;
+                for (;;) {
+                    asm volatile("ld.relaxed.cluster.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(bo), "=r"(h) : "r"(mail) : "memory");
+                    if ((h & 0xffc00000u) == tag) break;
                 }
+                bk = h & 0x3fffffu;
             }
+            for (int sl = 32; sl < S; sl += 32) {                  // S is a multiple of 32 here (NWARP >= 8, CS >= 4)
+                unsigned o, h;
+                do {
+                    asm volatile("ld.relaxed.cluster.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(o), "=r"(h) : "r"(mail + (uint32_t)sl * 8u) : "memory");
+                } while ((h & 0xffc00000u) != tag);
+                h &= 0x3fffffu;
+                if (o > bo || (o == bo && h < bk)) { bo = o; bk = h; }
+            }
+        }
+        FPS_STAMP(3);
+        const unsigned g = __reduce_max_sync(0xffffffffu, bo);
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, (bo == g) ? bk : 0xffffffffu);
+        const int kw = ((log2T > 0) ? (int)(__brev(kmin >> 12) >> (32 - log2T)) : 0) + (int)((kmin & 0xfffu) << log2T);
+        if (FULL) {
+            x1 = s_cloud[kw * 3 + 0]; y1 = s_cloud[kw * 3 + 1]; z1 = s_cloud[kw * 3 + 2];
         } else {
-            __syncthreads();
-            bkey = s_best.key; x1 = s_best.x; y1 = s_best.y; z1 = s_best.z;
+            x1 = __ldg(xyz + kw * 3 + 0); y1 = __ldg(xyz + kw * 3 + 1); z1 = __ldg(xyz + kw * 3 + 2);
         }
-        if (tid == 0 && rank == 0) {
-            const unsigned r = bkey >> 12;
-            const int lo = (log2T > 0) ? (int)(__brev(r) >> (32 - log2T)) : 0;
-            idx_out[j] = lo + (int)((bkey & 0xfffu) << log2T);
-        }
+#ifdef FPS_PROBE
+        if (__float_as_uint(x1) + __float_as_uint(y1) + __float_as_uint(z1) == 0x12345u) g_fps_sink = 3;   // consume
+#endif
+        FPS_STAMP(4);
+        if (tid == 0 && rank == 0) idx_out[j] = kw;
     }
     if (temp_io) {
 #pragma unroll
@@ -365,19 +403,20 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
             if (k < N) temp_io[k] = pt[p];
         }
     }
-    if (CS > 1) {   // nobody leaves while a peer may still write into its mailbox
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    }
+    // nobody leaves while a peer may still write into its mailbox
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int THREADS, int P, bool W>
-int launch_fps_cluster(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
-                       int CS, cudaStream_t st) {
-    auto kern = fps_cluster_kernel<THREADS, P, W>;
+template <int THREADS, int P, bool W, bool MONO, bool FULL>
+int launch_fps_cluster_t(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
+                         int CS, cudaStream_t st) {
+    auto kern = fps_cluster_kernel<THREADS, P, W, MONO, FULL>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * CS);
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = 0;
+    const size_t smem = (size_t)2 * CS * (THREADS / 32) * 8 + (FULL ? (size_t)N * 12 : 0);
+    if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -385,6 +424,23 @@ int launch_fps_cluster(const float* xyz, const float* w, float* temp, int32_t* i
     cfg.attrs = attr; cfg.numAttrs = 1;
     HRN_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, w, temp, idx, N, M, log2T, CS));
     return HRN_OK;
+}
+
+template <int THREADS, int P, bool W>
+int launch_fps_cluster(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
+                       int CS, cudaStream_t st) {
+    const bool mono = ((CS * THREADS) % (1 << log2T)) == 0;       // see MONO in the kernel
+    const bool full = (size_t)N * 12 + (size_t)2 * CS * (THREADS / 32) * 8 <= 200 * 1024;   // whole cloud fits in shared memory
+    // instantiated: the general key path only for P <= 8 (keys in registers), the L2 coordinate lookup only for the
+    // 8192-points-per-CTA kernel (the only one used for clouds that do not fit)
+    if constexpr (P <= 8) {
+        if (!mono && full) return launch_fps_cluster_t<THREADS, P, W, false, true>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    }
+    if constexpr (THREADS == 512 && P >= 8) {
+        if (mono && !full) return launch_fps_cluster_t<THREADS, P, W, true, false>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    }
+    if (mono && full) return launch_fps_cluster_t<THREADS, P, W, true, true>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    return HRN_ERR_UNSUPPORTED;
 }
 
 template <int THREADS, int P, bool W>
@@ -403,24 +459,25 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
     // opt_n_threads (cuda_utils.h:22-27): 2^floor(log2 N) clamped to [1,1024]  (defines the tie-break only)
     int log2T = 0;
     while ((2 << log2T) <= N && log2T < 10) ++log2T;
-    // all-in-registers cluster kernel: cluster size = largest of {8,4,2,1} that keeps one wave (B*CS <= 148 SMs)
-    // while P = ceil(N / (CS*THREADS)) <= 8 points per thread
+    // all-in-registers cluster kernels.  Few, fat warps: the per-warp bookkeeping of an iteration costs more issue
+    // slots than the distance update of 16 points per thread, so 512 threads x 16 points (8192 points per CTA) and the
+    // smallest cluster that holds the cloud; clusters of >= 2 CTAs keep the stride a multiple of Tref (MONO).
+    // B * CS may exceed the SM count: clusters are independent, the surplus simply runs as a second wave.
     if (N <= 1024) {
         if (N <= 256) return launch_fps_cluster<256, 1, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
         if (N <= 512) return launch_fps_cluster<256, 2, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
         return launch_fps_cluster<256, 4, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
     }
-    if (N <= 65536) {
-        // cluster size: as many CTAs per cloud as keep one wave (B*CS <= 148) but at least ~4096 points per CTA --
-        // below that the DSMEM exchange costs more than the shorter update loop saves
-        int CS = 8;
-        while (CS > 1 && (B * CS > 148 || N / CS < 4096)) CS >>= 1;
-        while (CS < 8 && (N + CS - 1) / CS > (W ? 4096 : 8192)) CS <<= 1;
-        const int n_cta = (N + CS - 1) / CS;          // points per CTA
-        if (n_cta <= 1024) return launch_fps_cluster<1024, 1, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
-        if (n_cta <= 2048) return launch_fps_cluster<1024, 2, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
-        if (n_cta <= 4096) return launch_fps_cluster<1024, 4, W>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
-        if (n_cta <= 8192 && !W) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    if (N <= 2048) return launch_fps_cluster<512, 4, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
+    if (N <= 4096) return launch_fps_cluster<512, 8, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
+    if (N <= 8192) return launch_fps_cluster<512, 8, W>(xyz, w, temp, idx, B, N, M, log2T, 2, st);
+    if (W) {                                            // 5 registers per point: 4096 points per CTA
+        if (N <= 16384) return launch_fps_cluster<512, 8, true>(xyz, w, temp, idx, B, N, M, log2T, 4, st);
+        if (N <= 32768) return launch_fps_cluster<512, 8, true>(xyz, w, temp, idx, B, N, M, log2T, 8, st);
+    } else {
+        if (N <= 16384) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 2, st);
+        if (N <= 32768) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 4, st);
+        if (N <= 65536) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 8, st);
     }
     if (N > (4096 << 10) || temp == nullptr) return HRN_ERR_BAD_ARG;   // streaming path needs the scratch buffer
     return launch_fps<1024, 0, W>(xyz, w, temp, idx, B, N, M, log2T, st);
