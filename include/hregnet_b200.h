@@ -69,6 +69,14 @@ int hrn_knn3_sorted(const float* p1, const int32_t* q_idx, const float* p2, int 
                     float* scratch_boxes, float* dists, int64_t* idx64, int32_t* idx32, float* nn, float* q_out,
                     void* stream);
 
+/* The two halves of hrn_knn3_sorted on their own (same argument rules).  The sort depends on the reference cloud only:
+ * a caller may run it on a second stream while the queries are still being chosen (furthest-point sampling), then
+ * search on the stream that holds the queries once both are done. */
+int hrn_knn3_sort(const float* p2, int B, int N, void* scratch_pts, float* scratch_boxes, void* stream);
+int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int K,
+                    const void* sorted_pts, const float* sorted_boxes, float* dists, int64_t* idx64, int32_t* idx32,
+                    float* nn, float* q_out, void* stream);
+
 /* Replaces pytorch3d.ops.knn_gather(x, idx) -- call sites layers.py:25,279,288,303,309,317,323,352,358,437,443.
  *   x [B,N,U], idx [B,M,K] int64 -> out [B,M,K,U]. */
 int hrn_knn_gather(const float* x, const int64_t* idx, float* out, int B, int N, int M, int K, int U, void* stream);

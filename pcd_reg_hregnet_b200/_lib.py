@@ -34,6 +34,8 @@ SIGNATURES = {
     "hrn_gather_points_grad": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_knn": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_knn3_sorted": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "hrn_knn3_sort": [c_vp, c_int, c_int, c_vp, c_vp, c_vp],
+    "hrn_knn3_search": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_knn_gather": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "hrn_gather_rows": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_transpose": [c_vp, c_vp, c_int, c_int, c_int, c_vp],

@@ -292,32 +292,58 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
 
 // Scratch the caller provides for the culled search: pts [B*N2] float4 and boxes [B*(N2/32)*6] floats, N2 = next
 // power of two >= N.  Returns HRN_ERR_UNSUPPORTED outside 1024 <= N <= 16384 (callers then use hrn_knn).
-HRN_API int hrn_knn3_sorted(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int K,
-                            void* scratch_pts, float* scratch_boxes, float* dists, int64_t* idx64, int32_t* idx32,
-                            float* nn, float* q_out, void* stream) {
-    using namespace knn_sorted;
-    if (!p2 || (!p1 && !q_idx) || !scratch_pts || !scratch_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
-    if (K > N || K > 64 || N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
-    if (B == 0 || M == 0) return HRN_OK;
+// The two halves are also exported on their own: the sort depends on the reference cloud only, so a caller can run it
+// on a second stream while the queries are still being chosen (FPS).
+static int knn3_pow2(int N) {
     int N2 = 1024;
     while (N2 < N) N2 <<= 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t sort_smem = (size_t)N2 * 8;
+    return N2;
+}
+
+HRN_API int hrn_knn3_sort(const float* p2, int B, int N, void* scratch_pts, float* scratch_boxes, void* stream) {
+    using namespace knn_sorted;
+    if (!p2 || !scratch_pts || !scratch_boxes || B < 0 || N <= 0) return HRN_ERR_BAD_ARG;
+    if (N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (B == 0) return HRN_OK;
+    const int N2 = knn3_pow2(N);
     static bool attr_set = false;
     if (!attr_set) {
         HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         attr_set = true;
     }
-    knn_sort_kernel<<<B, SORT_THREADS, sort_smem, st>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);
+    knn_sort_kernel<<<B, SORT_THREADS, (size_t)N2 * 8, (cudaStream_t)stream>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);
     HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int K,
+                            const void* sorted_pts, const float* sorted_boxes, float* dists, int64_t* idx64,
+                            int32_t* idx32, float* nn, float* q_out, void* stream) {
+    using namespace knn_sorted;
+    if (!p2 || (!p1 && !q_idx) || !sorted_pts || !sorted_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
+    if (K > N || K > 64 || N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (B == 0 || M == 0) return HRN_OK;
+    const int N2 = knn3_pow2(N);
+    cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(hrn_divup(M, QWARPS), B);
     const size_t bsm = (size_t)(N2 / 32) * 6 * sizeof(float);
     if (K <= 32)
-        knn3_sorted_kernel<1><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)scratch_pts, scratch_boxes, dists,
+        knn3_sorted_kernel<1><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts, sorted_boxes, dists,
                                                               idx64, idx32, nn, q_out, M, N, N2, K);
     else
-        knn3_sorted_kernel<2><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)scratch_pts, scratch_boxes, dists,
+        knn3_sorted_kernel<2><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts, sorted_boxes, dists,
                                                               idx64, idx32, nn, q_out, M, N, N2, K);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
+}
+
+HRN_API int hrn_knn3_sorted(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int K,
+                            void* scratch_pts, float* scratch_boxes, float* dists, int64_t* idx64, int32_t* idx32,
+                            float* nn, float* q_out, void* stream) {
+    if (!p2 || (!p1 && !q_idx) || !scratch_pts || !scratch_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
+    if (K > N || K > 64 || N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (B == 0 || M == 0) return HRN_OK;
+    const int rc = hrn_knn3_sort(p2, B, N, scratch_pts, scratch_boxes, stream);
+    if (rc != HRN_OK) return rc;
+    return hrn_knn3_search(p1, q_idx, p2, B, M, N, K, scratch_pts, scratch_boxes, dists, idx64, idx32, nn, q_out, stream);
 }

@@ -169,12 +169,45 @@ def knn_scratch(B, N, device):
             torch.empty(B * (N2 // 32) * 6, dtype=torch.float32, device=device))
 
 
-def knn_idx(p1, p2, K, q_idx=None):
+class KnnPresort:
+    """Morton sort + boxes of the culled search on the side stream: it depends on the cloud only, so it runs on the SMs
+    the sampling kernel leaves idle (one cluster of 2 SMs per cloud: 128 of 148 at 64 clouds) while the queries are still
+    being chosen.  Usage: ps = KnnPresort.fork(xyz) BEFORE the sampling is launched (records the fork point),
+    ps.launch() right AFTER it (so the sampling clusters are placed first), knn_idx(..., presorted=ps) joins."""
+
+    def __init__(self, p2, pts, boxes, side):
+        self.p2, self.pts, self.boxes, self.side = p2, pts, boxes, side
+
+    @staticmethod
+    def fork(p2):
+        B, N, D = p2.shape
+        if not (_SORTED_KNN and _SIDE_STREAM and D == 3 and 8192 <= N <= 16384):
+            return None
+        pts, boxes = knn_scratch(B, N, p2.device)
+        side = _side_stream(p2.device)
+        side.wait_stream(torch.cuda.current_stream(p2.device))
+        return KnnPresort(p2, pts, boxes, side)
+
+    def launch(self):
+        B, N, _ = self.p2.shape
+        with torch.cuda.stream(self.side):
+            call("hrn_knn3_sort", ptr(self.p2), B, N, ptr(self.pts), ptr(self.boxes), stream())
+        self.pts.record_stream(self.side)
+        self.boxes.record_stream(self.side)
+
+
+def knn_idx(p1, p2, K, q_idx=None, presorted=None):
     """int32 neighbour indices [B,M,K] (+ gathered queries when q_idx is given)."""
     B, N, D = p2.shape
     M = q_idx.shape[1] if q_idx is not None else p1.shape[1]
     idx = torch.empty(B, M, K, dtype=torch.int32, device=p2.device)
     q_out = torch.empty(B, M, 3, dtype=torch.float32, device=p2.device) if q_idx is not None else None
+    if presorted is not None:
+        pts, boxes = presorted.pts, presorted.boxes
+        torch.cuda.current_stream(p2.device).wait_stream(presorted.side)
+        call("hrn_knn3_search", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, K, ptr(pts), ptr(boxes),
+             None, None, ptr(idx), None, ptr(q_out), stream())
+        return idx, q_out
     if D == 3 and 1024 <= N <= 16384 and _SORTED_KNN:
         pts, boxes = knn_scratch(B, N, p2.device)
         call("hrn_knn3_sorted", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, K, ptr(pts), ptr(boxes),
@@ -241,8 +274,11 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
     det / desc: folded parameter dicts (fold.py).  Returns dict(xyz [B,M,3], sigmas [B,M], af [B,M,C_o] ,
     desc [B,M,desc_dim], and with want_maps also the rows-layout G, E, a, idx for the layer-level API)."""
     B, N, _ = xyz.shape
+    presorted = KnnPresort.fork(xyz)
     fidx = fps(xyz, M, weights)
-    idx, q = knn_idx(None, xyz, k, q_idx=fidx)
+    if presorted is not None:
+        presorted.launch()
+    idx, q = knn_idx(None, xyz, k, q_idx=fidx, presorted=presorted)
     if _PRECISION == "tc" and _FUSED_LEVELS and not want_maps and (B * M * k) % 128 == 0:
         from . import engine_tc
         cin = 0 if feat_cl is None else feat_cl.shape[2]

@@ -64,6 +64,14 @@ def _knn3_sorted(p1, q_idx, p2, B, M, N, K, pts, boxes, dists, idx64, idx32, nn,
     _knn(p1, q_idx, p2, B, M, N, 3, K, dists, idx64, idx32, nn, q_out, st)       # same contract, same results
 
 
+def _knn3_sort(p2, B, N, pts, boxes, st):
+    pass                                                                          # the emulated search needs no scratch
+
+
+def _knn3_search(p1, q_idx, p2, B, M, N, K, pts, boxes, dists, idx64, idx32, nn, q_out, st):
+    _knn(p1, q_idx, p2, B, M, N, 3, K, dists, idx64, idx32, nn, q_out, st)
+
+
 def _gather_rows(x, idx, out, B, N, M, U, st):
     out.view(B, M, U).copy_(x.view(B, N, U)[torch.arange(B)[:, None], idx.view(B, M).long()])
 
@@ -156,7 +164,7 @@ def _weighted_kabsch(src, cor, w, B, N, Rp, tp, R, t, Rc, tc, st):
 
 
 _TABLE = {
-    "hrn_fps": _fps, "hrn_knn": _knn, "hrn_knn3_sorted": _knn3_sorted, "hrn_gather_rows": _gather_rows, "hrn_transpose": _transpose,
+    "hrn_fps": _fps, "hrn_knn": _knn, "hrn_knn3_sorted": _knn3_sorted, "hrn_knn3_sort": _knn3_sort, "hrn_knn3_search": _knn3_search, "hrn_gather_rows": _gather_rows, "hrn_transpose": _transpose,
     "hrn_group_geometry": _group_geometry, "hrn_group_attention": _group_attention,
     "hrn_group_weighted_sum": _group_weighted_sum, "hrn_group_max": _group_max,
     "hrn_sigma_to_weights": _sigma_to_weights, "hrn_transform_points": _transform_points,
