@@ -7,8 +7,9 @@
 //                        {x, y, z, original index}, and one axis-aligned box per 32 consecutive points.
 //   2. knn3_sorted_kernel one warp per query: distance to every box of the cloud (16 boxes per lane, a true lower
 //                        bound of the members' distances in fp32 because subtraction and fma round monotonically),
-//                        seed the running top-K from the 4 closest boxes, then visit only boxes whose bound does
-//                        not exceed the current K-th distance.  Typically ~20 of 512 boxes are opened.
+//                        seed the running top-K (an unsorted set with a tracked maximum) from the closest boxes,
+//                        then visit only boxes whose bound does not exceed the current K-th distance (typically
+//                        ~20 of 512 boxes are opened), and sort the K survivors once at the end.
 #include "common.cuh"
 #include <math_constants.h>
 
@@ -18,55 +19,42 @@ __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) {
     return da < db || (da == db && ia < ib);
 }
 
-// Same distributed sorted list as knn.cu (kept local so the two translation units stay independent).
+// The K best candidates so far as an UNSORTED set spread over the warp (slot s of lane l), plus its largest member
+// (thr_d, thr_i) in (dist, index) order.  A better candidate replaces the largest member and the maximum is found again
+// with two REDUX -- ~16 instructions per insertion instead of ~40 for keeping the list sorted across lanes with
+// shuffles; the set is sorted once, at the end.  The search is bound by the instruction count of these insertions.
+// Members are unique: real points by their index, +inf padding / "empty" entries get distinct indices above every real
+// one, and the lanes beyond K (K < 32*KPL) hold dummies (-1, -1) that can never be the maximum (distances are >= 0;
+// the REDUX runs on the float bits as SIGNED integers, which orders {-1} < [0, +inf]).
 template <int KPL>
-struct WarpTopK {
+struct WarpSet {
     float d[KPL];
     int i[KPL];
     float thr_d;
     int thr_i;
-    int K;
-    __device__ __forceinline__ void init(int K_) {
-        K = K_;
+    __device__ __forceinline__ void refresh() {
+        float ld = d[0]; int li = i[0];
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) { d[s] = CUDART_INF_F; i[s] = 0x7fffffff; }
-        thr_d = CUDART_INF_F; thr_i = 0x7fffffff;
+        for (int s = 1; s < KPL; ++s)
+            if (d[s] > ld || (d[s] == ld && i[s] > li)) { ld = d[s]; li = i[s]; }
+        const int md = __reduce_max_sync(0xffffffffu, __float_as_int(ld));
+        thr_i = __reduce_max_sync(0xffffffffu, (__float_as_int(ld) == md) ? li : (int)0x80000000);
+        thr_d = __int_as_float(md);
     }
-    __device__ __forceinline__ void insert(float xd, int xi, int lane) {
-        float pd[KPL]; int pi[KPL];
+    __device__ __forceinline__ void replace_max(float xd, int xi) {
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) {
-            pd[s] = __shfl_up_sync(0xffffffffu, d[s], 1);
-            pi[s] = __shfl_up_sync(0xffffffffu, i[s], 1);
-            if (s > 0) {
-                const float cd = __shfl_sync(0xffffffffu, d[s - 1], 31);
-                const int ci = __shfl_sync(0xffffffffu, i[s - 1], 31);
-                if (lane == 0) { pd[s] = cd; pi[s] = ci; }
-            } else if (lane == 0) { pd[s] = -CUDART_INF_F; pi[s] = -1; }
-        }
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) {
-            const bool cur_lt = cand_less(d[s], i[s], xd, xi);
-            const bool prev_lt = cand_less(pd[s], pi[s], xd, xi);
-            const float nd = cur_lt ? d[s] : (prev_lt ? xd : pd[s]);
-            const int ni = cur_lt ? i[s] : (prev_lt ? xi : pi[s]);
-            d[s] = nd; i[s] = ni;
-        }
-        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
-        float td = d[0]; int ti = i[0];
-#pragma unroll
-        for (int s = 1; s < KPL; ++s) if (ks == s) { td = d[s]; ti = i[s]; }
-        thr_d = __shfl_sync(0xffffffffu, td, kl);
-        thr_i = __shfl_sync(0xffffffffu, ti, kl);
+        for (int s = 0; s < KPL; ++s)
+            if (d[s] == thr_d && i[s] == thr_i) { d[s] = xd; i[s] = xi; }
+        refresh();
     }
-    __device__ __forceinline__ void offer(float cd, int ci, int lane) {
+    __device__ __forceinline__ void offer(float cd, int ci) {
         unsigned mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
             const float xd = __shfl_sync(0xffffffffu, cd, src);
             const int xi = __shfl_sync(0xffffffffu, ci, src);
-            if (cand_less(xd, xi, thr_d, thr_i)) insert(xd, xi, lane);
+            if (cand_less(xd, xi, thr_d, thr_i)) replace_max(xd, xi);
         }
     }
 };
@@ -194,14 +182,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             bd[g] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
         }
     }
-    WarpTopK<KPL> top;
-    top.init(K);
-    auto open_box = [&](int bx) {
-        const float4 p = __ldg(pts + bx * 32 + lane);
-        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-        const float dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // padding: inf -> never offered
-        top.offer(dist, __float_as_int(p.w), lane);
-    };
+    WarpSet<KPL> top;
     // pick the box with the smallest bound among the not yet visited ones (warp-uniform result, -1 = none left)
     auto closest_box = [&]() -> int {
         float best = CUDART_INF_F; int bg = 0;
@@ -218,23 +199,24 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         }
         return g_sel * 32 + src;
     };
-    auto box_dist = [&](int bx, float& dist, int& pid) {
+    // candidate of this lane in box bx; padding (+inf) gets a distinct index above every real one
+    auto box_dist = [&](int bx, float& dist, int& pid, int uniq) {
         const float4 p = __ldg(pts + bx * 32 + lane);
         const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
         dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
         pid = __float_as_int(p.w);
+        if (pid == 0x7fffffff) pid -= uniq;
     };
-    // seed: the KPL closest boxes are SORTED into the list with a bitonic network (one box per list register) instead
-    // of K one-at-a-time insertions, then two more boxes tighten the threshold before the sweep
-    {
-        int nb = 0;
+    auto open_box = [&](int bx) {
+        float dist; int pid;
+        box_dist(bx, dist, pid, 0);                         // padding: inf is never below the threshold -> never offered
+        top.offer(dist, pid);
+    };
+    // sorts the set ascending by (dist, index): rank r ends up in slot r / 32 of lane r % 32
+    auto sort_set = [&]() {
 #pragma unroll
-        for (int s = 0; s < KPL; ++s) {
-            const int bx = closest_box();
-            if (bx >= 0) { box_dist(bx, top.d[s], top.i[s]); ++nb; }
-            bitonic_sort32(top.d[s], top.i[s], lane);
-        }
-        if (KPL == 2) {          // merge the two sorted boxes into one ascending list of 64
+        for (int s = 0; s < KPL; ++s) bitonic_sort32(top.d[s], top.i[s], lane);
+        if (KPL == 2) {          // merge the two sorted halves into one ascending list of 64
             const float rd = __shfl_sync(0xffffffffu, top.d[1], 31 - lane);
             const int ri = __shfl_sync(0xffffffffu, top.i[1], 31 - lane);
             const bool lo_self = cand_less(top.d[0], top.i[0], rd, ri);
@@ -245,12 +227,23 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             bitonic_merge32(top.d[0], top.i[0], lane);
             bitonic_merge32(top.d[1], top.i[1], lane);
         }
-        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
-        float td = top.d[0]; int ti = top.i[0];
+    };
+    // seed: the KPL closest boxes fill the set as they are (no sorting), then two more boxes tighten the threshold
+    // before the sweep
+    {
 #pragma unroll
-        for (int s = 1; s < KPL; ++s) if (ks == s) { td = top.d[s]; ti = top.i[s]; }
-        top.thr_d = __shfl_sync(0xffffffffu, td, kl);
-        top.thr_i = __shfl_sync(0xffffffffu, ti, kl);
+        for (int s = 0; s < KPL; ++s) {
+            const int bx = closest_box();
+            top.d[s] = CUDART_INF_F; top.i[s] = 0x7fffffff - (s * 32 + lane);           // "empty", distinct
+            if (bx >= 0) box_dist(bx, top.d[s], top.i[s], s * 32 + lane);
+        }
+        if (K < 32 * KPL) {      // keep the K best of the seed, the other 32*KPL - K positions become dummies
+            sort_set();
+#pragma unroll
+            for (int s = 0; s < KPL; ++s)
+                if (s * 32 + lane >= K) { top.d[s] = -1.f; top.i[s] = -1; }
+        }
+        top.refresh();
         for (int extra = 0; extra < 2; ++extra) {
             const int bx = closest_box();
             if (bx < 0) break;
@@ -269,11 +262,13 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             if (bnd <= top.thr_d) open_box(g * 32 + src);
         }
     }
+    sort_set();                                             // dummies (-1, -1) sort first
+    const int ndummy = 32 * KPL - K;
     const size_t base = ((size_t)b * M + m) * K;
 #pragma unroll
     for (int s = 0; s < KPL; ++s) {
-        const int pos = s * 32 + lane;
-        if (pos < K) {
+        const int pos = s * 32 + lane - ndummy;
+        if (pos >= 0) {
             const float d = top.d[s];
             const int i = top.i[s];
             if (out_d) out_d[base + pos] = d;
