@@ -203,11 +203,12 @@ __device__ unsigned g_fps_sink;
 
 __device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int THREADS, int P, bool WEIGHTED, bool MONO, bool FULL>
+template <int THREADS, int Q, int R, bool WEIGHTED, bool MONO, bool FULL>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, float* __restrict__ temp_io,
                    int32_t* __restrict__ idx_out, int N, int M, int log2T, int CS) {
     constexpr int NWARP = THREADS / 32;
+    constexpr int P = Q * R;                               // points per thread: R residues (mod stride) x Q points each
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int S = CS * NWARP;                              // packets per iteration and mailbox
     unsigned long long* s_mail = reinterpret_cast<unsigned long long*>(s_dyn);      // [2][S]
@@ -227,22 +228,28 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
         const unsigned r = (log2T > 0) ? (__brev((unsigned)k & tmask) >> (32 - log2T)) : 0u;
         return (r << 12) | ((unsigned)k >> log2T);
     };
-    const int stride = CS * THREADS;
+    // thread <-> points: k(p) = k0 + r * (CS*THREADS) + q * stride with p = r*Q + q, stride = R * CS * THREADS: few,
+    // fat warps (the per-warp bookkeeping, not the distance update, bounds an iteration) without giving up MONO
+    const int span = CS * THREADS, stride = R * span;
     const int k0 = (int)rank * THREADS + tid;
-    // MONO (chosen by the launcher): stride is a multiple of Tref, so (k mod Tref) is the same for all of this thread's
-    // points and key(k0 + p*stride) = key(k0) + p * (stride / Tref): the thread's winner is simply the first p that
-    // holds its maximum
-    const unsigned key_base = key_of(k0), key_step = (unsigned)stride >> log2T;
+    auto k_of = [&](int p) -> int { return k0 + (p / Q) * span + (p % Q) * stride; };
+    // MONO (chosen by the launcher): stride is a multiple of Tref, so (k mod Tref) is the same for the Q points of a
+    // residue and key(k0 + r*span + q*stride) = key(k0 + r*span) + q * (stride / Tref): the winner inside a residue is
+    // simply the first q that holds the thread's maximum
+    const unsigned key_step = (unsigned)stride >> log2T;
+    unsigned key_base[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) key_base[r] = key_of(k0 + r * span);
     unsigned pkey[MONO ? 1 : P];                           // general case: the key of every point of the thread
     if (!MONO) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) pkey[p] = (k0 + p * stride < N) ? key_of(k0 + p * stride) : 0xffffffffu;
+        for (int p = 0; p < P; ++p) pkey[p] = (k_of(p) < N) ? key_of(k_of(p)) : 0xffffffffu;
     }
 
     float px[P], py[P], pz[P], pt[P], pw[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        const int k = k0 + p * stride;
+        const int k = k_of(p);
         const bool valid = k < N;
         px[p] = valid ? xyz[k * 3 + 0] : 0.f;
         py[p] = valid ? xyz[k * 3 + 1] : 0.f;
@@ -326,10 +333,15 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
         // such a packet never wins: some warp of the cluster always holds a valid point with a distance >= 0)
         unsigned key;
         if (MONO) {
-            key = key_base + (unsigned)(P - 1) * key_step;
+            key = 0xffffffffu;
 #pragma unroll
-            for (int p = P - 2; p >= 0; --p)
-                if (pt[p] == m) key = key_base + (unsigned)p * key_step;         // per-thread constants
+            for (int r = 0; r < R; ++r) {
+                unsigned kk = (R == 1) ? key_base[r] + (unsigned)(Q - 1) * key_step : 0xffffffffu;
+#pragma unroll
+                for (int q = (R == 1) ? Q - 2 : Q - 1; q >= 0; --q)
+                    if (pt[r * Q + q] == m) kk = key_base[r] + (unsigned)q * key_step;   // per-thread constants
+                key = min(key, kk);
+            }
         } else {
             key = 0xffffffffu;
 #pragma unroll
@@ -399,7 +411,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
     if (temp_io) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const int k = k0 + p * stride;
+            const int k = k_of(p);
             if (k < N) temp_io[k] = pt[p];
         }
     }
@@ -407,10 +419,10 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int THREADS, int P, bool W, bool MONO, bool FULL>
+template <int THREADS, int Q, int R, bool W, bool MONO, bool FULL>
 int launch_fps_cluster_t(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
                          int CS, cudaStream_t st) {
-    auto kern = fps_cluster_kernel<THREADS, P, W, MONO, FULL>;
+    auto kern = fps_cluster_kernel<THREADS, Q, R, W, MONO, FULL>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * CS);
     cfg.blockDim = dim3(THREADS);
@@ -426,20 +438,21 @@ int launch_fps_cluster_t(const float* xyz, const float* w, float* temp, int32_t*
     return HRN_OK;
 }
 
-template <int THREADS, int P, bool W>
+template <int THREADS, int Q, bool W, int R = 1>
 int launch_fps_cluster(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
                        int CS, cudaStream_t st) {
-    const bool mono = ((CS * THREADS) % (1 << log2T)) == 0;       // see MONO in the kernel
+    constexpr int P = Q * R;
+    const bool mono = ((R * CS * THREADS) % (1 << log2T)) == 0;   // see MONO in the kernel
     const bool full = (size_t)N * 12 + (size_t)2 * CS * (THREADS / 32) * 8 <= 200 * 1024;   // whole cloud fits in shared memory
     // instantiated: the general key path only for P <= 8 (keys in registers), the L2 coordinate lookup only for the
     // 8192-points-per-CTA kernel (the only one used for clouds that do not fit)
     if constexpr (P <= 8) {
-        if (!mono && full) return launch_fps_cluster_t<THREADS, P, W, false, true>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+        if (!mono && full) return launch_fps_cluster_t<THREADS, Q, R, W, false, true>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
     }
-    if constexpr (THREADS == 512 && P >= 8) {
-        if (mono && !full) return launch_fps_cluster_t<THREADS, P, W, true, false>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    if constexpr (P >= 8) {
+        if (mono && !full) return launch_fps_cluster_t<THREADS, Q, R, W, true, false>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
     }
-    if (mono && full) return launch_fps_cluster_t<THREADS, P, W, true, true>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
+    if (mono && full) return launch_fps_cluster_t<THREADS, Q, R, W, true, true>(xyz, w, temp, idx, B, N, M, log2T, CS, st);
     return HRN_ERR_UNSUPPORTED;
 }
 
@@ -475,6 +488,8 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
         if (N <= 16384) return launch_fps_cluster<512, 8, true>(xyz, w, temp, idx, B, N, M, log2T, 4, st);
         if (N <= 32768) return launch_fps_cluster<512, 8, true>(xyz, w, temp, idx, B, N, M, log2T, 8, st);
     } else {
+        // (8 warps x 32 points -- two residues per thread, <256, 16, false, 2> -- is 4 % faster alone, 794 vs 827 us at 64
+        // clouds, but not inside the step, where the Morton sort runs beside it: 6.30 vs 6.32 ms)
         if (N <= 16384) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 2, st);
         if (N <= 32768) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 4, st);
         if (N <= 65536) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 8, st);

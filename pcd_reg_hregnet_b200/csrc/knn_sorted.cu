@@ -146,9 +146,9 @@ knn_sort_kernel(const float* __restrict__ xyz, float4* __restrict__ pts_out, flo
 }
 
 constexpr int QWARPS = 8;
-constexpr int MAXBPL = 16;     // boxes per lane: up to 512 boxes = 16384 points
 
-template <int KPL>
+// KPL: list registers per lane (K <= 32*KPL); BPL: boxes per lane (cloud <= 1024*BPL points)
+template <int KPL, int BPL>
 __global__ void __launch_bounds__(QWARPS * 32)
 knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, const float* __restrict__ p2,
                    const float4* __restrict__ pts, const float* __restrict__ boxes, float* __restrict__ out_d,
@@ -169,9 +169,9 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
     if (out_q && lane < 3) out_q[((size_t)b * M + m) * 3 + lane] = q[lane];
 
     // lower bound of the squared distance to every box (same operation order as the point distance)
-    float bd[MAXBPL];
+    float bd[BPL];
 #pragma unroll
-    for (int g = 0; g < MAXBPL; ++g) {
+    for (int g = 0; g < BPL; ++g) {
         const int bx = g * 32 + lane;
         bd[g] = CUDART_NAN_F;                               // NaN = "never open": out of range or already visited
         if (bx < nbox) {
@@ -187,7 +187,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
     auto closest_box = [&]() -> int {
         float best = CUDART_INF_F; int bg = 0;
 #pragma unroll
-        for (int g = 0; g < MAXBPL; ++g) if (bd[g] < best) { best = bd[g]; bg = g; }
+        for (int g = 0; g < BPL; ++g) if (bd[g] < best) { best = bd[g]; bg = g; }
         const unsigned ob = hrn_ford(best);
         const unsigned wmin = __reduce_min_sync(0xffffffffu, ob);
         if (wmin == hrn_ford(CUDART_INF_F)) return -1;
@@ -195,7 +195,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         const int g_sel = __shfl_sync(0xffffffffu, bg, src);
         if (lane == src) {
 #pragma unroll
-            for (int g = 0; g < MAXBPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;   // visited
+            for (int g = 0; g < BPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;   // visited
         }
         return g_sel * 32 + src;
     };
@@ -252,7 +252,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
     }
     // sweep: every box whose bound can still beat the K-th candidate
 #pragma unroll
-    for (int g = 0; g < MAXBPL; ++g) {
+    for (int g = 0; g < BPL; ++g) {
         if (g * 32 >= nbox) break;
         unsigned mask = __ballot_sync(0xffffffffu, bd[g] <= top.thr_d);
         while (mask) {
@@ -322,12 +322,19 @@ HRN_API int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(hrn_divup(M, QWARPS), B);
     const size_t bsm = (size_t)(N2 / 32) * 6 * sizeof(float);
-    if (K <= 32)
-        knn3_sorted_kernel<1><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts, sorted_boxes, dists,
-                                                              idx64, idx32, nn, q_out, M, N, N2, K);
-    else
-        knn3_sorted_kernel<2><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts, sorted_boxes, dists,
-                                                              idx64, idx32, nn, q_out, M, N, N2, K);
+#define HRN_KNN3_LAUNCH(KPL, BPL)                                                                                     \
+    knn3_sorted_kernel<KPL, BPL><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts, sorted_boxes, \
+                                                                 dists, idx64, idx32, nn, q_out, M, N, N2, K)
+    if (K <= 32) {
+        if (N2 <= 1024) HRN_KNN3_LAUNCH(1, 1);
+        else if (N2 <= 4096) HRN_KNN3_LAUNCH(1, 4);
+        else HRN_KNN3_LAUNCH(1, 16);
+    } else {
+        if (N2 <= 1024) HRN_KNN3_LAUNCH(2, 1);
+        else if (N2 <= 4096) HRN_KNN3_LAUNCH(2, 4);
+        else HRN_KNN3_LAUNCH(2, 16);
+    }
+#undef HRN_KNN3_LAUNCH
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }

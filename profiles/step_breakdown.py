@@ -17,7 +17,7 @@ for r in csv.DictReader(lines):
     u = r["Metric Unit"]
     if r["Metric Name"] == "gpu__time_duration.sum":
         d["us"] = {"ns": v / 1e3, "us": v, "ms": v * 1e3}[u]
-    else:
+    elif r["Metric Name"].startswith("dram__bytes"):
         d[r["Metric Name"]] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 ids = sorted(by)
 # a step starts with the level-1 furthest-point sampling: the only fps launch over the full clouds

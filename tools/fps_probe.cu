@@ -10,7 +10,12 @@
 int main(int argc, char** argv) {
     const int B = argc > 1 ? atoi(argv[1]) : 64, N = argc > 2 ? atoi(argv[2]) : 16384, M = argc > 3 ? atoi(argv[3]) : 1024;
     const bool weighted = argc > 4 && atoi(argv[4]);
-    const int directCS = argc > 5 ? atoi(argv[5]) : 0, directLog2T = argc > 6 ? atoi(argv[6]) : 10;   // direct <512,16> launch
+    const int directCS = argc > 5 ? atoi(argv[5]) : 0, directLog2T = argc > 6 ? atoi(argv[6]) : 10;   // direct launch
+    const int variant = argc > 7 ? atoi(argv[7]) : 0;           // 0: <512,16> one residue, 1: <256,16> two residues per thread
+    auto direct = [&](float* xyz, int32_t* idx) -> int {
+        if (variant == 1) return launch_fps_cluster<256, 16, false, 2>(xyz, nullptr, nullptr, idx, B, N, M, directLog2T, directCS, 0);
+        return launch_fps_cluster<512, 16, false>(xyz, nullptr, nullptr, idx, B, N, M, directLog2T, directCS, 0);
+    };
     std::vector<float> h((size_t)B * N * 3), hw((size_t)B * N);
     srand(1);
     for (auto& v : h) v = 100.f * rand() / RAND_MAX;
@@ -21,18 +26,26 @@ int main(int argc, char** argv) {
     cudaMemcpy(w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int it = 0; it < 3; ++it) {
-        int rc = directCS ? launch_fps_cluster<512, 16, false>(xyz, nullptr, nullptr, idx, B, N, M, directLog2T, directCS, 0)
-                          : hrn_fps(xyz, weighted ? w : nullptr, nullptr, idx, B, N, M, nullptr);
+        int rc = directCS ? direct(xyz, idx) : hrn_fps(xyz, weighted ? w : nullptr, nullptr, idx, B, N, M, nullptr);
         if (rc) { printf("hrn_fps rc=%d\n", rc); return 1; }
     }
     cudaEventRecord(e0);
     for (int it = 0; it < 5; ++it) {
-        if (directCS) launch_fps_cluster<512, 16, false>(xyz, nullptr, nullptr, idx, B, N, M, directLog2T, directCS, 0);
+        if (directCS) direct(xyz, idx);
         else hrn_fps(xyz, weighted ? w : nullptr, nullptr, idx, B, N, M, nullptr);
     }
     cudaEventRecord(e1);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("sync failed\n"); return 1; }
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+    if (directCS) {     // same picks as the library's own dispatch?
+        std::vector<int32_t> a((size_t)B * M), b2((size_t)B * M);
+        cudaMemcpy(a.data(), idx, a.size() * 4, cudaMemcpyDeviceToHost);
+        hrn_fps(xyz, nullptr, nullptr, idx, B, N, M, nullptr);
+        cudaMemcpy(b2.data(), idx, a.size() * 4, cudaMemcpyDeviceToHost);
+        size_t bad = 0;
+        for (size_t i = 0; i < a.size(); ++i) bad += a[i] != b2[i];
+        printf("[variant %d vs dispatch: %zu mismatches] ", variant, bad);
+    }
     printf("B=%d N=%d M=%d w=%d CS=%d: %.4f ms, %.1f ns/iter\n", B, N, M, (int)weighted, directCS, ms, ms * 1e6 / (M - 1));
 #ifdef FPS_PROBE
     long long p[64 * 8];
