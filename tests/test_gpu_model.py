@@ -111,3 +111,21 @@ def test_model_v2_fine_reg2_teacher_forced_and_forward(precision):
     assert set(out.keys()) == set(want.keys())
     assert out["src_dst_feats_2"].shape == (3, 128, 512) and out["src_dst_weights_2_prime"].shape == (3, 512)
     assert all(torch.isfinite(v).all() for v in out["rotation"] + out["translation"])
+
+
+def test_registrar_map_equals_call(net, precision):
+    """Public host-buffer API: the pipelined form (Registrar.map: H2D of the next batch and D2H of the previous one
+    overlap the forward) returns, batch by batch, exactly what the synchronous call returns."""
+    from pcd_reg_hregnet_b200.runner import Registrar
+    B, N = 2, 4096
+    batches = []
+    for s in range(3):
+        src, dst, _, _ = synth.make_batch([50 + 2 * s, 51 + 2 * s], N)
+        batches.append((src.pin_memory(), dst.pin_memory()))
+    reg = Registrar(net, B, N)
+    want = [tuple(x.clone() for x in reg(s, d)) for s, d in batches]
+    got = [tuple(x.clone() for x in rt) for rt in reg.map(batches)]
+    assert len(got) == len(want)
+    for (R0, t0), (R1, t1) in zip(want, got):
+        assert torch.equal(R0, R1) and torch.equal(t0, t1)
+    assert not torch.equal(want[0][0], want[1][0])                   # the batches really differ
