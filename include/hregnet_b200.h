@@ -129,6 +129,13 @@ int hrn_layer_fp32(const hrn_rows_t* in, const float* W, const float* bias, int 
 int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
                  int Cout, int NP, int n_stage, void* stream);
 
+/* The same layer with the reference's max over the k neighbours (x.max(dim=3), layers.py:208) taken in the epilogue:
+ * G [rows / k, ldg] = max over each k consecutive rows of act(W x + b); the per-row result is never written.
+ * k = 8, 16 or 32; act = none or ReLU; Cout a multiple of 32 (= NP); 16-byte aligned segments, G and bias --
+ * HRN_ERR_UNSUPPORTED otherwise (callers then run hrn_layer_tc + hrn_group_max). */
+int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* G, int ldg,
+                          long long rows, int Cout, int NP, int n_stage, int k, void* stream);
+
 /* Two or three fused shared-MLP layers with the activations kept in shared / tensor memory: the reference's conv
  * stacks `convs`, `convs_1`, `convs_2` (layers.py:118-121,249-260,420-423), the descriptor head mlp1+mlp2
  * (layers.py:193-198,207) and the per-keypoint heads mlp1/mlp2/mlp3 (layers.py:124-130,161-163,425-431,451-452) where

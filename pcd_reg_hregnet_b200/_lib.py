@@ -41,6 +41,7 @@ SIGNATURES = {
     "hrn_transpose": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_layer_fp32": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp],
     "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp],
+    "hrn_layer_tc_groupmax": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_vp],
     "hrn_level_fused": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_chain_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                      c_int, c_vp, c_vp, c_ll, c_vp],

@@ -258,7 +258,10 @@ template <bool SIMPLE>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
                 float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NS, int n_split, int n_stage,
-                int S, int n_items) {
+                int S, int n_items, int gk) {
+    // gk = 0: Y [rows, ldy] = act(W x + b).  gk = 8 / 16 / 32: Y [rows / gk, ldy] = max over each group of gk consecutive
+    // rows of act(W x + b) -- the reference's x.max(dim=3) after the last descriptor layer (layers.py:208) taken in the
+    // epilogue, so the per-row result never reaches HBM (launcher: act monotone, Cout % 32 == 0, aligned Y).
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[WS_MAX_STAGES], s_empty[WS_MAX_STAGES], s_accf[2], s_acce[2];
     __shared__ uint32_t s_tmem;
@@ -310,6 +313,50 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                     __syncwarp();
                     const int piece = lane & 7;
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(brow + c0) + piece);
+                    if (gk) {
+                        // lane (piece, rsub = lane >> 3) holds rows rsub + 4 i of the warp's 32: the group of row rl is
+                        // rl / gk = i / (gk / 4).  Local maximum per group, then over the 4 rsub lanes (shuffles 8, 16);
+                        // max_i act(x_i + b) = act(max_i x_i + b) exactly (rounding and act are monotone).
+                        const int ipg = gk >> 2;                            // i's per group: 2, 4 or 8
+                        const long long g0 = ((long long)m * TM + warp * 32) / gk;
+                        float4 mx[4];                                      // up to 4 groups per warp (gk = 8)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) mx[g] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = (lane >> 3) + 4 * i;
+                            const float4 t = *reinterpret_cast<const float4*>(tile + rl * WS_TP + piece * 4);
+                            const bool ok = (long long)m * TM + warp * 32 + rl < rows;
+                            const int g = i / ipg;
+#pragma unroll
+                            for (int gg = 0; gg < 4; ++gg)
+                                if (gg == g && ok) {
+                                    mx[gg].x = fmaxf(mx[gg].x, t.x); mx[gg].y = fmaxf(mx[gg].y, t.y);
+                                    mx[gg].z = fmaxf(mx[gg].z, t.z); mx[gg].w = fmaxf(mx[gg].w, t.w);
+                                }
+                        }
+                        const int ng = 32 / gk;                             // groups in this warp's 32 rows
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (g < ng) {
+#pragma unroll
+                                for (int o = 8; o <= 16; o <<= 1) {
+                                    mx[g].x = fmaxf(mx[g].x, __shfl_xor_sync(0xffffffffu, mx[g].x, o));
+                                    mx[g].y = fmaxf(mx[g].y, __shfl_xor_sync(0xffffffffu, mx[g].y, o));
+                                    mx[g].z = fmaxf(mx[g].z, __shfl_xor_sync(0xffffffffu, mx[g].z, o));
+                                    mx[g].w = fmaxf(mx[g].w, __shfl_xor_sync(0xffffffffu, mx[g].w, o));
+                                }
+                                if ((lane >> 3) == (g & 3) && (g0 + g) * gk < rows) {   // spread the stores over the rsub lanes
+                                    float4 o4;
+                                    o4.x = act_fn(mx[g].x + bb.x, act); o4.y = act_fn(mx[g].y + bb.y, act);
+                                    o4.z = act_fn(mx[g].z + bb.z, act); o4.w = act_fn(mx[g].w + bb.w, act);
+                                    *reinterpret_cast<float4*>(Y + (g0 + g) * ldy + n0 + c0 + piece * 4) = o4;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        continue;
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rl = (lane >> 3) + 4 * i;
@@ -535,7 +582,7 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
 }
 
 int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
-                    int Cout, int NP, int n_stage, cudaStream_t stream) {
+                    int Cout, int NP, int n_stage, cudaStream_t stream, int gk = 0) {
     const int tiles = hrn_divup(rows, TM);
     int NS = NP > 256 ? 256 : NP;
     while (NS > 32 && (NS / 2) % 16 == 0 && tiles * (NP / NS) < 148) NS >>= 1;
@@ -557,10 +604,10 @@ int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int
     const bool simple = in->n_seg == 1 && in->seg[0].mode == HRN_SEG_DIRECT && !in->seg[0].row_scale;
     if (simple)
         layer_ws_kernel<true><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
-                                                                  NP, NS, n_split, n_stage, S, n_items);
+                                                                  NP, NS, n_split, n_stage, S, n_items, gk);
     else
         layer_ws_kernel<false><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
-                                                                   NP, NS, n_split, n_stage, S, n_items);
+                                                                   NP, NS, n_split, n_stage, S, n_items, gk);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
@@ -617,4 +664,28 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
             *in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_stage, tmem_cols, NW);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
+}
+
+// Same layer with the group maximum taken in the epilogue: G [rows / k, ldg] = max over each k consecutive rows of
+// act(W x + b)  (k = 8, 16 or 32; act = none / ReLU; Cout a multiple of 32; 16-byte aligned segments, G and bias).
+// Replaces hrn_layer_tc + hrn_group_max for the last DescExtractor layer (reference layers.py:207-208).
+HRN_API int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* G, int ldg,
+                                  long long rows, int Cout, int NP, int n_stage, int k, void* stream) {
+    if (!in || !Wp || !bias || !G || rows < 0 || Cout <= 0 || in->n_seg < 1 || in->n_seg > 4) return HRN_ERR_BAD_ARG;
+    if (k != 8 && k != 16 && k != 32) return HRN_ERR_UNSUPPORTED;
+    if (act != HRN_ACT_NONE && act != HRN_ACT_RELU) return HRN_ERR_UNSUPPORTED;
+    if (rows % k != 0 || Cout % 32 != 0 || NP != Cout || NP > 512 || (NP > 256 && NP != 512)) return HRN_ERR_UNSUPPORTED;
+    if ((ldg & 3) || ((uintptr_t)G & 15) || ((uintptr_t)bias & 15)) return HRN_ERR_UNSUPPORTED;
+    int chunks = 0;
+    for (int s = 0; s < in->n_seg; ++s) {
+        const hrn_seg_t& g = in->seg[s];
+        if (!g.ptr || g.channels <= 0) return HRN_ERR_BAD_ARG;
+        if (g.mode == HRN_SEG_GATHER && !in->gather_idx) return HRN_ERR_BAD_ARG;
+        if (g.mode == HRN_SEG_BROADCAST && in->group <= 0) return HRN_ERR_BAD_ARG;
+        if ((g.channels & 3) || (g.ld & 3) || (g.col0 & 3) || ((uintptr_t)g.ptr & 15)) return HRN_ERR_UNSUPPORTED;
+        chunks += (g.channels + 7) / 8;
+    }
+    if (n_stage != (chunks * 8 + KC - 1) / KC) return HRN_ERR_BAD_ARG;
+    if (rows == 0) return HRN_OK;
+    return layer_ws_launch(in, Wp, bias, act, G, ldg, rows, Cout, NP, n_stage, (cudaStream_t)stream, k);
 }

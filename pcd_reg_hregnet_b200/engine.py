@@ -114,6 +114,22 @@ def stack(view: RowsView, layers, last_act=None):
     return x
 
 
+def stack_group_max(view: RowsView, layers, k):
+    """group_max(stack(view, layers), k) with the maximum taken in the last layer's epilogue when the tensor-core
+    kernel supports it (the per-row output of the last layer is then never written)."""
+    if _PRECISION == "tc" and len(layers) >= 1:
+        from . import engine_tc
+        W, b, act = layers[-1]
+        x = None
+        for li, (Wl, bl, al) in enumerate(layers[:-1]):
+            x = layer(view if li == 0 else RowsView(x.shape[0]).add(x), Wl, bl, al)
+        v = view if x is None else RowsView(x.shape[0]).add(x)
+        if engine_tc.layer_tc_groupmax_ok(v, W, act, k):
+            return engine_tc.layer_tc_groupmax(v, W, b, act, k)
+        return group_max(layer(v, W, b, act), k)
+    return group_max(stack(view, layers), k)
+
+
 def _chain_ok(view, layers, k):
     if _PRECISION != "tc" or not _FUSED_CHAINS or k not in (8, 16, 32):
         return False
@@ -306,7 +322,7 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
         v = RowsView(rows, group=k).add(X1max, SEG_BROADCAST).add(X1).add(Ea)
         # (mlp1+mlp2 through the chain kernel measured 1.2 ms vs 0.69 ms for two per-layer launches + group_max:
         #  K0 = 768 needs three operand passes per tile, each exposing the gather latency)
-        d = group_max(stack(v, desc["mlp"]), k)
+        d = stack_group_max(v, desc["mlp"], k)
         return dict(xyz=keypoints.view(B, M, 3), sigmas=sig.view(B, M), af=af.view(B, M, -1), desc=d.view(B, M, -1))
     E = stack(grouped(), det["convs"])
     a = group_attention(E, k)

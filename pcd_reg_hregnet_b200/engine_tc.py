@@ -51,6 +51,31 @@ def layer_tc(view, W, b, act, out):
     return out
 
 
+def layer_tc_groupmax_ok(view, W, act, k):
+    """Preconditions of hrn_layer_tc_groupmax (include/hregnet_b200.h)."""
+    if k not in (8, 16, 32) or act not in (engine.ACT_NONE, engine.ACT_RELU) or view.rows % k:
+        return False
+    cout = W.shape[0]
+    if cout % 32 or cout > 512 or (cout > 256 and cout != 512):
+        return False
+    for mat, mode, ch, col0, scale in view.segs:
+        if ch % 4 or col0 % 4 or mat.stride(0) % 4 or mat.data_ptr() % 16:
+            return False
+    return True
+
+
+def layer_tc_groupmax(view, W, b, act, k):
+    """G [rows / k, Cout] = max over each k consecutive rows of act(W x + b): layer + reference max(dim=3) in one launch."""
+    seg_channels = [s[2] for s in view.segs]
+    Wp, NP, n_stage, _ = pack_weights(W, seg_channels)
+    if b is None:
+        b = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device)
+    out = torch.empty(view.rows // k, W.shape[0], dtype=torch.float32, device=W.device)
+    engine.call("hrn_layer_tc_groupmax", ctypes.byref(view.c), engine.ptr(Wp), engine.ptr(b), act, engine.ptr(out),
+                out.stride(0), view.rows, W.shape[0], NP, n_stage, k, engine.stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # fused level kernels (csrc/level_fused.cu)
 # ------------------------------------------------------------------------------------------------------------------

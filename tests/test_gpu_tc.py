@@ -174,3 +174,21 @@ def test_chain_persistent_schedule(rows, K0, dims, mode, kseg):
         assert float((a[rsel].double().view(-1, kseg) - a_ref).abs().max()) < 1e-4
         assert float((G[gsel].double() - (a_ref[:, :, None] * Rg).sum(1)).abs().max()) / scale < 1e-4
         assert float((Y[rsel].double().view(-1, kseg, C) - a_ref[:, :, None] * Rg).abs().max()) / scale < 1e-4
+
+
+@pytest.mark.parametrize("k,rows,K,N", [(16, 4096, 256, 256), (8, 1024 + 128, 64, 512), (32, 2048, 96, 64)])
+def test_layer_groupmax_epilogue_equals_layer_then_group_max(k, rows, K, N):
+    """hrn_layer_tc_groupmax == hrn_group_max(hrn_layer_tc): max_i act(x_i + b) = act(max_i x_i + b) exactly."""
+    from pcd_reg_hregnet_b200 import engine, engine_tc
+    from pcd_reg_hregnet_b200.engine import RowsView, ACT_RELU
+    g = torch.Generator(device="cuda").manual_seed(k)
+    X = torch.randn(rows, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    engine.set_precision("tc")
+    v = RowsView(rows).add(X)
+    assert engine_tc.layer_tc_groupmax_ok(v, W, ACT_RELU, k)
+    got = engine_tc.layer_tc_groupmax(v, W, b, ACT_RELU, k)
+    want = engine.group_max(engine.layer(RowsView(rows).add(X), W, b, ACT_RELU), k)
+    assert got.shape == (rows // k, N)
+    assert torch.equal(got, want)
