@@ -9,80 +9,17 @@
 //
 // Kernel shape: one WARP per query, the 32 lanes sweep the reference points of the cloud in chunks of 32 from a
 // shared-memory tile that the whole CTA (8 queries of the same cloud) streams through once; the running
-// top-K is a sorted list distributed over the lanes' registers (position s*32+lane), so a candidate test is one
-// compare against the broadcast K-th entry + a ballot, and an insertion is a register shift done with
-// shfl_up -- no shared or local memory per query, nothing spilled to global (pytorch3d keeps the K=64
-// running set of its one-thread-per-query kernel in global memory).
+// top-K is an unsorted set distributed over the lanes' registers with a REDUX-tracked maximum (knn_select.cuh), so a
+// candidate test is one compare against the broadcast K-th entry + a ballot, and an insertion replaces the maximum --
+// no shared or local memory per query, nothing spilled to global (pytorch3d keeps the K=64 running set of its
+// one-thread-per-query kernel in global memory); the set is sorted once at the end.
 #include "common.cuh"
+#include "knn_select.cuh"
 #include <math_constants.h>
 
 namespace {
 
-__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) {
-    return da < db || (da == db && ia < ib);
-}
-
-template <int KPL>
-struct WarpTopK {
-    float d[KPL];
-    int i[KPL];
-    float thr_d;
-    int thr_i;
-    int K;
-    __device__ __forceinline__ void init(int K_) {
-        K = K_;
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) { d[s] = CUDART_INF_F; i[s] = 0x7fffffff; }
-        thr_d = CUDART_INF_F; thr_i = 0x7fffffff;
-    }
-    // warp-uniform (xd, xi); keeps the list sorted ascending, drops the last element
-    __device__ __forceinline__ void insert(float xd, int xi, int lane) {
-        float pd[KPL]; int pi[KPL];
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) {
-            pd[s] = __shfl_up_sync(0xffffffffu, d[s], 1);
-            pi[s] = __shfl_up_sync(0xffffffffu, i[s], 1);
-            if (s > 0) {
-                const float cd = __shfl_sync(0xffffffffu, d[s - 1], 31);
-                const int ci = __shfl_sync(0xffffffffu, i[s - 1], 31);
-                if (lane == 0) { pd[s] = cd; pi[s] = ci; }
-            } else if (lane == 0) { pd[s] = -CUDART_INF_F; pi[s] = -1; }
-        }
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) {
-            const bool cur_lt = cand_less(d[s], i[s], xd, xi);
-            const bool prev_lt = cand_less(pd[s], pi[s], xd, xi);
-            const float nd = cur_lt ? d[s] : (prev_lt ? xd : pd[s]);
-            const int ni = cur_lt ? i[s] : (prev_lt ? xi : pi[s]);
-            d[s] = nd; i[s] = ni;
-        }
-        const int ks = (K - 1) >> 5, kl = (K - 1) & 31;
-        float td = d[0]; int ti = i[0];
-#pragma unroll
-        for (int s = 1; s < KPL; ++s) if (ks == s) { td = d[s]; ti = i[s]; }
-        thr_d = __shfl_sync(0xffffffffu, td, kl);
-        thr_i = __shfl_sync(0xffffffffu, ti, kl);
-    }
-    // per-lane candidate (cd, ci) (cd = +inf for padding lanes)
-    __device__ __forceinline__ void offer(float cd, int ci, int lane) {
-        unsigned mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float xd = __shfl_sync(0xffffffffu, cd, src);
-            const int xi = __shfl_sync(0xffffffffu, ci, src);
-            if (cand_less(xd, xi, thr_d, thr_i)) insert(xd, xi, lane);
-        }
-    }
-    template <typename F>
-    __device__ __forceinline__ void for_each(int lane, F f) const {
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) {
-            const int pos = s * 32 + lane;
-            if (pos < K) f(pos, d[s], i[s]);
-        }
-    }
-};
+using namespace knn_sel;
 
 constexpr int KNN_WARPS = 8;
 constexpr int KNN3_TILE = 2048;  // reference points per shared-memory tile (24 KB, AoS: stride-3 is conflict-free)
@@ -104,8 +41,8 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
         qx = q[0]; qy = q[1]; qz = q[2];
         if (out_q && lane < 3) out_q[((size_t)b * M + m) * 3 + lane] = q[lane];
     }
-    WarpTopK<KPL> top;
-    top.init(K);
+    WarpSet<KPL> top;
+    top.init_empty(K, lane);
     for (int t0 = 0; t0 < N; t0 += KNN3_TILE) {
         const int tn = min(KNN3_TILE, N - t0);
         __syncthreads();
@@ -119,13 +56,14 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
                     const float dx = qx - s_ref[n * 3 + 0], dy = qy - s_ref[n * 3 + 1], dz = qz - s_ref[n * 3 + 2];
                     dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
                 }
-                top.offer(dist, t0 + n, lane);
+                top.offer(dist, n < tn ? t0 + n : 0x7fffffff);
             }
         }
     }
     if (!qvalid) return;
+    top.sort_set(lane);
     const size_t base = ((size_t)b * M + m) * K;
-    top.for_each(lane, [&](int pos, float d, int i) {
+    top.for_each_sorted(K, lane, [&](int pos, float d, int i) {
         if (out_d) out_d[base + pos] = d;
         if (out_i64) out_i64[base + pos] = (int64_t)i;
         if (out_i32) out_i32[base + pos] = i;
@@ -161,9 +99,9 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         const int q = i / D;
         s_q[i] = (m0 + q < M) ? p1[(size_t)(m0 + q) * D + (i - q * D)] : 0.f;
     }
-    WarpTopK<KPL> top[8];
+    WarpSet<KPL> top[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) top[q].init(K);
+    for (int q = 0; q < 8; ++q) top[q].init_empty(K, lane);
     constexpr int LDR = KD_D + 1;
     // reference slices [128 refs] x [64 dims] are double-buffered with 4-byte cp.async (the padded rows that make the
     // column reads conflict-free are not 16-byte aligned): slice s+1 is in flight while slice s is consumed
@@ -217,7 +155,7 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = t0 + lane + 32 * j;
-                    top[q].offer(n < N ? a[j] : CUDART_INF_F, n, lane);
+                    top[q].offer(n < N ? a[j] : CUDART_INF_F, n < N ? n : 0x7fffffff);
                 }
             }
         }
@@ -227,7 +165,8 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         const int m = m0 + warp * 8 + q;
         if (m >= M) continue;
         const size_t base = ((size_t)b * M + m) * K;
-        top[q].for_each(lane, [&](int pos, float d, int i) {
+        top[q].sort_set(lane);
+        top[q].for_each_sorted(K, lane, [&](int pos, float d, int i) {
             if (out_d) out_d[base + pos] = d;
             if (out_i64) out_i64[base + pos] = (int64_t)i;
             if (out_i32) out_i32[base + pos] = i;
@@ -235,7 +174,8 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         if (out_nn) {
             __syncwarp();
             for (int pos = 0; pos < K; ++pos) {
-                const int s = pos >> 5, l = pos & 31;
+                const int sp = pos + 32 * KPL - K;              // sorted position (dummies first)
+                const int s = sp >> 5, l = sp & 31;
                 int iv = top[q].i[0];
 #pragma unroll
                 for (int t = 1; t < KPL; ++t) if (s == t) iv = top[q].i[t];

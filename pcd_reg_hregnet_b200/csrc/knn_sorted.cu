@@ -11,73 +11,12 @@
 //                        then visit only boxes whose bound does not exceed the current K-th distance (typically
 //                        ~20 of 512 boxes are opened), and sort the K survivors once at the end.
 #include "common.cuh"
+#include "knn_select.cuh"
 #include <math_constants.h>
 
 namespace knn_sorted {
 
-__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) {
-    return da < db || (da == db && ia < ib);
-}
-
-// The K best candidates so far as an UNSORTED set spread over the warp (slot s of lane l), plus its largest member
-// (thr_d, thr_i) in (dist, index) order.  A better candidate replaces the largest member and the maximum is found again
-// with two REDUX -- ~16 instructions per insertion instead of ~40 for keeping the list sorted across lanes with
-// shuffles; the set is sorted once, at the end.  The search is bound by the instruction count of these insertions.
-// Members are unique: real points by their index, +inf padding / "empty" entries get distinct indices above every real
-// one, and the lanes beyond K (K < 32*KPL) hold dummies (-1, -1) that can never be the maximum (distances are >= 0;
-// the REDUX runs on the float bits as SIGNED integers, which orders {-1} < [0, +inf]).
-template <int KPL>
-struct WarpSet {
-    float d[KPL];
-    int i[KPL];
-    float thr_d;
-    int thr_i;
-    __device__ __forceinline__ void refresh() {
-        float ld = d[0]; int li = i[0];
-#pragma unroll
-        for (int s = 1; s < KPL; ++s)
-            if (d[s] > ld || (d[s] == ld && i[s] > li)) { ld = d[s]; li = i[s]; }
-        const int md = __reduce_max_sync(0xffffffffu, __float_as_int(ld));
-        thr_i = __reduce_max_sync(0xffffffffu, (__float_as_int(ld) == md) ? li : (int)0x80000000);
-        thr_d = __int_as_float(md);
-    }
-    __device__ __forceinline__ void replace_max(float xd, int xi) {
-#pragma unroll
-        for (int s = 0; s < KPL; ++s)
-            if (d[s] == thr_d && i[s] == thr_i) { d[s] = xd; i[s] = xi; }
-        refresh();
-    }
-    __device__ __forceinline__ void offer(float cd, int ci) {
-        unsigned mask = __ballot_sync(0xffffffffu, cand_less(cd, ci, thr_d, thr_i));
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float xd = __shfl_sync(0xffffffffu, cd, src);
-            const int xi = __shfl_sync(0xffffffffu, ci, src);
-            if (cand_less(xd, xi, thr_d, thr_i)) replace_max(xd, xi);
-        }
-    }
-};
-
-// 32-lane bitonic networks on (dist, index) pairs -- used to build the initial top-K from whole boxes at once
-__device__ __forceinline__ void cmpx(float& d, int& i, int j, bool keep_min) {
-    const float od = __shfl_xor_sync(0xffffffffu, d, j);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, j);
-    const bool self_less = cand_less(d, i, od, oi);
-    const bool take_self = (self_less == keep_min);
-    d = take_self ? d : od;
-    i = take_self ? i : oi;
-}
-__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) cmpx(d, i, j, ((lane & j) == 0) == ((lane & k) == 0));
-}
-__device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {   // bitonic in -> ascending out
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) cmpx(d, i, j, (lane & j) == 0);
-}
+using namespace knn_sel;
 
 __device__ __forceinline__ unsigned part1by1(unsigned v) {
     v &= 0x0000ffffu;
@@ -212,22 +151,6 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         box_dist(bx, dist, pid, 0);                         // padding: inf is never below the threshold -> never offered
         top.offer(dist, pid);
     };
-    // sorts the set ascending by (dist, index): rank r ends up in slot r / 32 of lane r % 32
-    auto sort_set = [&]() {
-#pragma unroll
-        for (int s = 0; s < KPL; ++s) bitonic_sort32(top.d[s], top.i[s], lane);
-        if (KPL == 2) {          // merge the two sorted halves into one ascending list of 64
-            const float rd = __shfl_sync(0xffffffffu, top.d[1], 31 - lane);
-            const int ri = __shfl_sync(0xffffffffu, top.i[1], 31 - lane);
-            const bool lo_self = cand_less(top.d[0], top.i[0], rd, ri);
-            const float hd = lo_self ? rd : top.d[0];
-            const int hi = lo_self ? ri : top.i[0];
-            if (!lo_self) { top.d[0] = rd; top.i[0] = ri; }
-            top.d[1] = hd; top.i[1] = hi;
-            bitonic_merge32(top.d[0], top.i[0], lane);
-            bitonic_merge32(top.d[1], top.i[1], lane);
-        }
-    };
     // seed: the KPL closest boxes fill the set as they are (no sorting), then two more boxes tighten the threshold
     // before the sweep
     {
@@ -238,7 +161,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             if (bx >= 0) box_dist(bx, top.d[s], top.i[s], s * 32 + lane);
         }
         if (K < 32 * KPL) {      // keep the K best of the seed, the other 32*KPL - K positions become dummies
-            sort_set();
+            top.sort_set(lane);
 #pragma unroll
             for (int s = 0; s < KPL; ++s)
                 if (s * 32 + lane >= K) { top.d[s] = -1.f; top.i[s] = -1; }
@@ -262,7 +185,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             if (bnd <= top.thr_d) open_box(g * 32 + src);
         }
     }
-    sort_set();                                             // dummies (-1, -1) sort first
+    top.sort_set(lane);                                     // dummies (-1, -1) sort first
     const int ndummy = 32 * KPL - K;
     const size_t base = ((size_t)b * M + m) * K;
 #pragma unroll
