@@ -9,3 +9,4 @@ from .model_v2 import FineReg1, FineReg2, Model_V2  # noqa: F401
 from .models import HierFeatureExtraction, HRegNet  # noqa: F401
 from .ops import (furthest_point_sample, gather_operation, knn_gather, knn_points,  # noqa: F401
                   weighted_furthest_point_sample)
+from . import runner  # noqa: F401,E402  (Registrar: host-buffer serving API)
