@@ -37,6 +37,8 @@ def _clouds(kind, B, N, seed):
     # 40000 points -> CS=8/P=5->8, 70000 points -> streaming kernel
     ("uniform", 64, 16384, 1024), ("uniform", 20, 16384, 256), ("uniform", 40, 8192, 128), ("uniform", 2, 40000, 200),
     ("uniform", 1, 70000, 64),
+    # more samples than the 10-bit iteration tag of the exchange packets counts (tags wrap, buffers alternate)
+    ("uniform", 2, 4096, 3000), ("lidar", 1, 16384, 2500), ("uniform", 2, 1024, 1024),
 ])
 def test_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=N + M)
@@ -57,6 +59,19 @@ def test_weighted_fps_bit_exact(kind, B, N, M):
     w = torch.rand(B, N, generator=g) * 3 + 0.05
     if kind == "lattice":
         w = torch.randint(1, 3, (B, N), generator=g).float()
+    want = native.fps(xyz, M, w)
+    got = ops.weighted_furthest_point_sample(xyz.to(DEV), w.to(DEV), M)
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("N,M", [(1024, 300), (3000, 200), (16384, 150)])
+def test_weighted_fps_with_negative_and_zero_weights(N, M):
+    """The reference multiplies the distance by whatever weight it is given (furthest_point_sampling_gpu.cu:299);
+    negative and zero weights make the "distances" negative / zero -- the ordered-key reductions must still agree."""
+    xyz = _clouds("uniform", 2, N, seed=N)
+    g = torch.Generator().manual_seed(N + 1)
+    w = torch.rand(2, N, generator=g) * 3 - 1
+    w[:, ::7] = 0.0
     want = native.fps(xyz, M, w)
     got = ops.weighted_furthest_point_sample(xyz.to(DEV), w.to(DEV), M)
     assert torch.equal(got.cpu(), want)
