@@ -1,4 +1,4 @@
-// Exact kNN in 3-D with spatial culling, for the large level-1 search (1024 queries x 16384 points, K = 64).
+// Exact kNN in 3-D with spatial culling, for clouds of 1024 .. 32768 points (level 1: 1024 queries x 16384 points, K = 64).
 //
 // Same contract as knn3_kernel (knn.cu): dist = fma(dz,dz, fma(dy,dy, dx*dx)), K smallest by (dist, index) -- the
 // result is bit-identical to the brute-force kernel, only the work changes:
@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "knn_select.cuh"
 #include <math_constants.h>
+#include <type_traits>
 
 namespace knn_sorted {
 
@@ -29,20 +30,34 @@ __device__ __forceinline__ unsigned part1by1(unsigned v) {
 
 constexpr int SORT_THREADS = 1024;
 
-// pts_out [B, N2] float4 (x,y,z,idx bits; padding = +inf / 0x7fffffff), boxes [B, N2/32, 6] (min xyz, max xyz)
+// pts_out [B, N2] float4 (x,y,z,idx bits; padding = +inf / 0x7fffffff), boxes [B, N2/32, 6] (min xyz, max xyz).
+// WIDE (N2 <= 16384): 8-byte keys (20-bit Morton code of the 0.25 m lattice << 32 | index), 128 KB of shared memory.
+// !WIDE (N2 = 32768): 4-byte keys (17-bit Morton code: 0.5 m cells in x, 1 m in y, << 15 | 15-bit index) -- the same
+// 128 KB hold twice the points; coarser cells only make the boxes a little larger, the search stays exact.
+template <bool WIDE>
 __global__ void __launch_bounds__(SORT_THREADS)
 knn_sort_kernel(const float* __restrict__ xyz, float4* __restrict__ pts_out, float* __restrict__ boxes, int N, int N2) {
-    extern __shared__ unsigned long long s_key[];   // N2 entries: (morton << 32) | index
+    using Key = typename std::conditional<WIDE, unsigned long long, unsigned>::type;
+    extern __shared__ __align__(8) unsigned char s_raw[];
+    Key* s_key = reinterpret_cast<Key*>(s_raw);     // N2 entries
+    const Key PAD = ~(Key)0;                        // padding sorts last
     const int b = blockIdx.x, tid = threadIdx.x;
     xyz += (size_t)b * N * 3;
     for (int i = tid; i < N2; i += SORT_THREADS) {
-        unsigned long long k = 0xffffffffffffffffull;
+        Key k = PAD;
         if (i < N) {
             const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1];
-            const int ix = min(1023, max(0, (int)floorf((x + 128.f) * 4.f)));
-            const int iy = min(1023, max(0, (int)floorf((y + 128.f) * 4.f)));
-            const unsigned m = part1by1((unsigned)ix) | (part1by1((unsigned)iy) << 1);
-            k = ((unsigned long long)m << 32) | (unsigned)i;
+            if (WIDE) {
+                const int ix = min(1023, max(0, (int)floorf((x + 128.f) * 4.f)));
+                const int iy = min(1023, max(0, (int)floorf((y + 128.f) * 4.f)));
+                const unsigned m = part1by1((unsigned)ix) | (part1by1((unsigned)iy) << 1);
+                k = (Key)(((unsigned long long)m << 32) | (unsigned)i);
+            } else {
+                const int ix = min(511, max(0, (int)floorf((x + 128.f) * 2.f)));
+                const int iy = min(255, max(0, (int)floorf(y + 128.f)));
+                const unsigned m = part1by1((unsigned)ix) | (part1by1((unsigned)iy) << 1);     // 17 bits
+                k = (Key)((m << 15) | (unsigned)i);
+            }
         }
         s_key[i] = k;
     }
@@ -53,7 +68,7 @@ knn_sort_kernel(const float* __restrict__ xyz, float4* __restrict__ pts_out, flo
                 const int lo = ((t / stride) * stride * 2) + (t % stride);
                 const int hi = lo + stride;
                 const bool up = ((lo & size) == 0);
-                const unsigned long long a = s_key[lo], c = s_key[hi];
+                const Key a = s_key[lo], c = s_key[hi];
                 if ((a > c) == up) { s_key[lo] = c; s_key[hi] = a; }
             }
             __syncthreads();
@@ -63,9 +78,9 @@ knn_sort_kernel(const float* __restrict__ xyz, float4* __restrict__ pts_out, flo
     float* bo = boxes + (size_t)b * (N2 / 32) * 6;
     const int lane = tid & 31;
     for (int i = tid; i < N2; i += SORT_THREADS) {          // i / 32 is warp-uniform: one chunk per warp step
-        const unsigned long long k = s_key[i];
-        const int src = (int)(k & 0xffffffffu);
-        const bool valid = k != 0xffffffffffffffffull;
+        const Key k = s_key[i];
+        const bool valid = i < N;                           // the N2 - N padding keys are the largest: they sort last
+        const int src = WIDE ? (int)((unsigned long long)k & 0xffffffffu) : (int)((unsigned)k & 0x7fffu);
         float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
         if (valid) { x = xyz[src * 3 + 0]; y = xyz[src * 3 + 1]; z = xyz[src * 3 + 2]; }
         po[i] = make_float4(x, y, z, __int_as_float(valid ? src : 0x7fffffff));
@@ -209,7 +224,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
 }  // namespace knn_sorted
 
 // Scratch the caller provides for the culled search: pts [B*N2] float4 and boxes [B*(N2/32)*6] floats, N2 = next
-// power of two >= N.  Returns HRN_ERR_UNSUPPORTED outside 1024 <= N <= 16384 (callers then use hrn_knn).
+// power of two >= N.  Returns HRN_ERR_UNSUPPORTED outside 1024 <= N <= 32768 (callers then use hrn_knn).
 // The two halves are also exported on their own: the sort depends on the reference cloud only, so a caller can run it
 // on a second stream while the queries are still being chosen (FPS).
 static int knn3_pow2(int N) {
@@ -221,15 +236,19 @@ static int knn3_pow2(int N) {
 HRN_API int hrn_knn3_sort(const float* p2, int B, int N, void* scratch_pts, float* scratch_boxes, void* stream) {
     using namespace knn_sorted;
     if (!p2 || !scratch_pts || !scratch_boxes || B < 0 || N <= 0) return HRN_ERR_BAD_ARG;
-    if (N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0) return HRN_OK;
     const int N2 = knn3_pow2(N);
     static bool attr_set = false;
     if (!attr_set) {
-        HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
         attr_set = true;
     }
-    knn_sort_kernel<<<B, SORT_THREADS, (size_t)N2 * 8, (cudaStream_t)stream>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);
+    if (N2 <= 16384)
+        knn_sort_kernel<true><<<B, SORT_THREADS, (size_t)N2 * 8, (cudaStream_t)stream>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);
+    else
+        knn_sort_kernel<false><<<B, SORT_THREADS, (size_t)N2 * 4, (cudaStream_t)stream>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
@@ -239,7 +258,7 @@ HRN_API int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* 
                             int32_t* idx32, float* nn, float* q_out, void* stream) {
     using namespace knn_sorted;
     if (!p2 || (!p1 && !q_idx) || !sorted_pts || !sorted_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
-    if (K > N || K > 64 || N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (K > N || K > 64 || N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0 || M == 0) return HRN_OK;
     const int N2 = knn3_pow2(N);
     cudaStream_t st = (cudaStream_t)stream;
@@ -251,11 +270,13 @@ HRN_API int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* 
     if (K <= 32) {
         if (N2 <= 1024) HRN_KNN3_LAUNCH(1, 1);
         else if (N2 <= 4096) HRN_KNN3_LAUNCH(1, 4);
-        else HRN_KNN3_LAUNCH(1, 16);
+        else if (N2 <= 16384) HRN_KNN3_LAUNCH(1, 16);
+        else HRN_KNN3_LAUNCH(1, 32);
     } else {
         if (N2 <= 1024) HRN_KNN3_LAUNCH(2, 1);
         else if (N2 <= 4096) HRN_KNN3_LAUNCH(2, 4);
-        else HRN_KNN3_LAUNCH(2, 16);
+        else if (N2 <= 16384) HRN_KNN3_LAUNCH(2, 16);
+        else HRN_KNN3_LAUNCH(2, 32);
     }
 #undef HRN_KNN3_LAUNCH
     HRN_LAUNCH_CHECK();
@@ -266,7 +287,7 @@ HRN_API int hrn_knn3_sorted(const float* p1, const int32_t* q_idx, const float* 
                             void* scratch_pts, float* scratch_boxes, float* dists, int64_t* idx64, int32_t* idx32,
                             float* nn, float* q_out, void* stream) {
     if (!p2 || (!p1 && !q_idx) || !scratch_pts || !scratch_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
-    if (K > N || K > 64 || N < 1024 || N > 16384) return HRN_ERR_UNSUPPORTED;
+    if (K > N || K > 64 || N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0 || M == 0) return HRN_OK;
     const int rc = hrn_knn3_sort(p2, B, N, scratch_pts, scratch_boxes, stream);
     if (rc != HRN_OK) return rc;

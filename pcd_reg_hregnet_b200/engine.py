@@ -197,7 +197,7 @@ class KnnPresort:
     @staticmethod
     def fork(p2):
         B, N, D = p2.shape
-        if not (_SORTED_KNN and _SIDE_STREAM and D == 3 and 8192 <= N <= 16384):
+        if not (_SORTED_KNN and _SIDE_STREAM and D == 3 and 8192 <= N <= 32768):
             return None
         pts, boxes = knn_scratch(B, N, p2.device)
         side = _side_stream(p2.device)
@@ -224,7 +224,7 @@ def knn_idx(p1, p2, K, q_idx=None, presorted=None):
         call("hrn_knn3_search", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, K, ptr(pts), ptr(boxes),
              None, None, ptr(idx), None, ptr(q_out), stream())
         return idx, q_out
-    if D == 3 and 1024 <= N <= 16384 and _SORTED_KNN:
+    if D == 3 and 1024 <= N <= 32768 and _SORTED_KNN:
         pts, boxes = knn_scratch(B, N, p2.device)
         call("hrn_knn3_sorted", ptr(p1) if q_idx is None else None, ptr(q_idx), ptr(p2), B, M, N, K, ptr(pts), ptr(boxes),
              None, None, ptr(idx), None, ptr(q_out), stream())

@@ -144,6 +144,9 @@ def test_gather_forward_backward():
     # spatially culled path (2048 <= N <= 16384): ties, duplicates, non-power-of-two N, points outside the lattice
     ("lattice", 2, 512, 16384, 64), ("dup", 2, 700, 8096, 32), ("lidar", 1, 64, 10000, 16), ("far", 1, 128, 4096, 8),
     ("uniform", 64, 1024, 16384, 64),
+    # 4-byte sort keys (16384 < N <= 32768): full and ragged clouds, ties, duplicates; beyond: brute force
+    ("lidar", 2, 512, 32768, 64), ("lattice", 1, 300, 20000, 32), ("dup", 1, 256, 32768, 16), ("far", 1, 100, 25000, 8),
+    ("uniform", 1, 64, 40000, 16),
 ])
 def test_knn_xyz_bit_exact(kind, B, M, N, K):
     p2 = _clouds(kind, B, N, seed=N + K)
