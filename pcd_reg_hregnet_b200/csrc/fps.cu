@@ -357,6 +357,8 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
             if (MBAR)
             asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
                          ::"r"(rslot32 + (par ? mail_par_bytes : 0u)), "l"(v), "r"(rbar32 + (par ? 8u : 0u)) : "memory");
+            else if (CS == 1)   // single-CTA launch: plain shared-memory store, no trip through the cluster window
+            asm volatile("st.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mail_u32 + (uint32_t)warp * 8u + (par ? mail_par_bytes : 0u)), "l"(v) : "memory");
             else
             asm volatile("st.relaxed.cluster.b64 [%0], %1;" ::"l"(rslot + (par ? mail_par_bytes : 0u)), "l"(v) : "memory");
         }
