@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--points", type=int, default=16384)
     ap.add_argument("--precision", default=os.environ.get("HRN_PRECISION", "auto"))
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=8)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="hregnet", choices=["hregnet", "v2"],
                     help="hregnet = BASELINE configs[1] (default); v2 = Adaption-1 / Model_V2 (configs[3], use --points 32768)")
@@ -274,6 +274,7 @@ def main():
             "gpu_launches": launches * args.steps,
             "kernel_breakdown_ms_per_step": prof["families"],
             "roofline": prof["roofline"](pk),
+            "kernel_rooflines": prof["kernel_rooflines"](pk, clocks.get("sm_mhz") or 1965),
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, dt = cpu_reference_pairs_per_s(args.cpu_sample_pairs, N)
@@ -312,6 +313,7 @@ def _profile_families(reg, steps=3):
     aggregated per kernel family; algorithmic FLOP counted for the shared-MLP layer launches."""
     from pcd_reg_hregnet_b200 import engine
     rec = []
+    other = {}                      # algorithmic work per step of the non-tensor kernel families
     orig = engine.call
 
     def timed(name, *a):
@@ -336,6 +338,15 @@ def _profile_families(reg, steps=3):
             cin, c1, c2, co, cm, cd = {1: (0, 32, 32, 64, 32, 64), 2: (64, 64, 64, 128, 64, 128)}[lv]
             macs = 2 * ((cin + 4) * c1 + c1 * c2 + c2 * co) + 3 * co * cm + cm * cd
             fl = 2.0 * Bc * Mc * kc * macs
+        elif name == "hrn_fps":
+            # (M-1)*N distance updates x 9 lane-instructions (3 FADD, FMUL, 2 FFMA, FMNMX, FSETP, SEL)
+            Bc, Nc, Mc = a[4], a[5], a[6]
+            other["hrn_fps"] = other.get("hrn_fps", 0.0) + 9.0 * Bc * max(Mc - 1, 0) * Nc / steps
+        elif name in ("hrn_knn", "hrn_knn3_sorted", "hrn_knn3_search"):
+            # brute-force-equivalent work of the exact search: M*N pair distances x (3D - 1) flop (8 at D = 3)
+            Bc, Mc, Nc = a[3], a[4], a[5]
+            Dc = a[6] if name == "hrn_knn" else 3
+            other["knn"] = other.get("knn", 0.0) + float(Bc) * Mc * Nc * (3 * Dc - 1) / steps
         rec.append((name, s, e, fl))
         return r
 
@@ -371,7 +382,25 @@ def _profile_families(reg, steps=3):
                 "launches_per_step": n_layer, "ms_per_step": layer_ms, "share_of_step": layer_ms / sum(fam.values()),
                 "algorithmic_gflop_per_step": layer_fl / 1e9}
 
-    return {"families": {k: round(v, 4) for k, v in fam.items()}, "roofline": roofline}
+    def kernel_rooflines(pk, sm_mhz):
+        """The sampling and neighbour-search families against the FP32 issue rate of the chip at the measured clock
+        (they are on-chip bound: their HBM traffic is a few MB per step).  kNN counts the brute-force-equivalent work of
+        the exact search, so the culled kernels can exceed what a brute-force search could reach."""
+        lanes = 148 * 128 * sm_mhz * 1e6                    # lane-instructions per second
+        out = {}
+        if "hrn_fps" in other and fam.get("hrn_fps"):
+            ach = other["hrn_fps"] / (fam["hrn_fps"] / 1e3)
+            out["hrn_fps"] = {"bound": "fp32 issue (on-chip)", "achieved": ach / 1e12, "peak": lanes / 1e12,
+                              "unit": "T lane-instr/s", "frac": ach / lanes, "ms_per_step": fam["hrn_fps"]}
+        knn_ms = sum(fam.get(n, 0.0) for n in ("hrn_knn", "hrn_knn3_sorted", "hrn_knn3_search"))
+        if "knn" in other and knn_ms > 0:
+            ach = other["knn"] / (knn_ms / 1e3)
+            out["knn (search kernels)"] = {"bound": "fp32 (on-chip), brute-force-equivalent flop", "achieved": ach / 1e12,
+                                           "peak": 2 * lanes / 1e12, "unit": "TFLOP/s", "frac": ach / (2 * lanes),
+                                           "ms_per_step": knn_ms}
+        return out
+
+    return {"families": {k: round(v, 4) for k, v in fam.items()}, "roofline": roofline, "kernel_rooflines": kernel_rooflines}
 
 
 if __name__ == "__main__":

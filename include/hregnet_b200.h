@@ -169,6 +169,13 @@ int hrn_group_attention(const float* E, int ldE, int C, long long groups, int k,
 int hrn_group_weighted_sum(const float* a, const float* V, int ldV, int C, long long groups, int k, const int32_t* idx,
                            int groups_per_batch, int N, float* out, int ldo, void* stream);
 
+/* hrn_group_attention + the two hrn_group_weighted_sum calls of the correspondence heads in one pass over the rows
+ * (reference layers.py:385-390, 447-450): a [groups*k] (nullable) = softmax_k(max_c E), af [groups, ldaf] = sum_j a_j
+ * E[g*k+j,:], cor [groups,3] (nullable) = sum_j a_j xyz[b*N + idx[g*k+j],:] with b = g / groups_per_batch.
+ * C % 4 == 0, 16-byte aligned rows, k*C*4 <= 96 KB -- HRN_ERR_UNSUPPORTED otherwise. */
+int hrn_group_attend(const float* E, int ldE, int C, long long groups, int k, float* a, float* af, int ldaf,
+                     const float* xyz, const int32_t* idx, int groups_per_batch, int N, float* cor, void* stream);
+
 /* out[g,c] = max_j X[g*k+j, c]   (layers.py:202,208). */
 int hrn_group_max(const float* X, int ldX, int C, long long groups, int k, float* out, int ldo, void* stream);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
                      c_int, c_vp, c_vp, c_ll, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
     "hrn_group_weighted_sum": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp],
+    "hrn_group_attend": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "hrn_group_max": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_vp],
     "hrn_group_geometry": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp],
     "hrn_sigma_to_weights": [c_vp, c_vp, c_int, c_int, c_vp],

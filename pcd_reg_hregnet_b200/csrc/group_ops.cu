@@ -57,6 +57,56 @@ group_weighted_sum_kernel(const float* __restrict__ a, const float* __restrict__
     }
 }
 
+// Attention tail of the correspondence heads in ONE pass over the k rows of a group (layers.py:385-390, 447-450):
+//   a = softmax_k(max_c E), af[g,:] = sum_j a_j E[g*k+j,:], cor[g,:] = sum_j a_j xyz[b*N + idx[g*k+j],:]
+// The rows are read once (float4, coalesced) into shared memory while their maxima are taken; the three separate
+// kernels read the [rows, C] tensor twice (134 MB each at the coarse level).  Same operation order as
+// group_attention_kernel / group_weighted_sum_kernel, hence the same bits.
+__global__ void __launch_bounds__(128)
+group_attend_kernel(const float* __restrict__ E, int ldE, int C, int k, float* __restrict__ a_out,
+                    float* __restrict__ af, int ldaf, const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                    int groups_per_batch, int N, float* __restrict__ cor) {
+    extern __shared__ __align__(16) float s_E[];            // [k][C]
+    __shared__ float s_x[64], s_a[64];
+    const long long g = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C4 = C >> 2;
+    for (int j = warp; j < k; j += 4) {
+        const float4* row = reinterpret_cast<const float4*>(E + (g * k + j) * ldE);
+        float4* dst = reinterpret_cast<float4*>(s_E + j * C);
+        float m = -CUDART_INF_F;
+        for (int c = lane; c < C4; c += 32) {
+            const float4 v = __ldg(row + c);
+            dst[c] = v;
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+        m = hrn_warp_max(m);
+        if (lane == 0) s_x[j] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float v0 = lane < k ? s_x[lane] : -CUDART_INF_F;
+        const float v1 = lane + 32 < k ? s_x[lane + 32] : -CUDART_INF_F;
+        const float mx = hrn_warp_max(fmaxf(v0, v1));
+        const float e0 = lane < k ? expf(v0 - mx) : 0.f;
+        const float e1 = lane + 32 < k ? expf(v1 - mx) : 0.f;
+        const float sum = hrn_warp_sum(e0 + e1);
+        if (lane < k) { s_a[lane] = e0 / sum; if (a_out) a_out[g * k + lane] = e0 / sum; }
+        if (lane + 32 < k) { s_a[lane + 32] = e1 / sum; if (a_out) a_out[g * k + lane + 32] = e1 / sum; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) acc = fmaf(s_a[j], s_E[j * C + c], acc);
+        af[g * ldaf + c] = acc;
+    }
+    if (cor && threadIdx.x < 3) {
+        const long long b = g / groups_per_batch;
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) acc = fmaf(s_a[j], xyz[(b * N + idx[g * k + j]) * 3 + threadIdx.x], acc);
+        cor[g * 3 + threadIdx.x] = acc;
+    }
+}
 __global__ void __launch_bounds__(128)
 group_max_kernel(const float* __restrict__ X, int ldX, int C, int k, float* __restrict__ out, int ldo) {
     const long long g = blockIdx.x;
@@ -150,6 +200,25 @@ HRN_API int hrn_group_weighted_sum(const float* a, const float* V, int ldV, int 
     return HRN_OK;
 }
 
+HRN_API int hrn_group_attend(const float* E, int ldE, int C, long long groups, int k, float* a, float* af, int ldaf,
+                             const float* xyz, const int32_t* idx, int groups_per_batch, int N, float* cor,
+                             void* stream) {
+    if (!E || !af || C <= 0 || k <= 0 || k > 64 || groups < 0) return HRN_ERR_BAD_ARG;
+    if (cor && (!xyz || !idx || groups_per_batch <= 0 || N <= 0)) return HRN_ERR_BAD_ARG;
+    if ((C & 3) || (ldE & 3) || ((uintptr_t)E & 15)) return HRN_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)k * C * sizeof(float);
+    if (smem > 96 * 1024) return HRN_ERR_UNSUPPORTED;
+    if (groups == 0) return HRN_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HRN_CUDA(cudaFuncSetAttribute(group_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    group_attend_kernel<<<(unsigned)groups, 128, smem, (cudaStream_t)stream>>>(E, ldE, C, k, a, af, ldaf, xyz, idx,
+                                                                              groups_per_batch, N, cor);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
 HRN_API int hrn_group_max(const float* X, int ldX, int C, long long groups, int k, float* out, int ldo,
                           void* stream) {
     if (!X || !out || C <= 0 || k <= 0 || groups < 0) return HRN_ERR_BAD_ARG;

@@ -343,9 +343,17 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
 
 def _tail(F, a_k, idx, dxyz, B, N1, N2, head):
     """softmax attention over the k candidates, correspondence + confidence (layers.py:385-394, 447-452)."""
-    a = group_attention(F, a_k)
-    cor = group_weighted_sum(a, dxyz.view(B * N2, 3), a_k, idx=idx, groups_per_batch=N1, N=N2)
-    af = group_weighted_sum(a, F, a_k)
+    rows, C = F.shape
+    if C % 4 == 0 and F.stride(0) % 4 == 0 and F.data_ptr() % 16 == 0 and a_k * C * 4 <= 96 * 1024:
+        # attention, attentive feature and correspondence in one pass over F
+        af = torch.empty(rows // a_k, C, dtype=torch.float32, device=F.device)
+        cor = torch.empty(rows // a_k, 3, dtype=torch.float32, device=F.device)
+        call("hrn_group_attend", ptr(F), F.stride(0), C, rows // a_k, a_k, None, ptr(af), af.stride(0),
+             ptr(dxyz), ptr(idx), N1, N2, ptr(cor), stream())
+    else:
+        a = group_attention(F, a_k)
+        cor = group_weighted_sum(a, dxyz.view(B * N2, 3), a_k, idx=idx, groups_per_batch=N1, N=N2)
+        af = group_weighted_sum(a, F, a_k)
     w = stack(RowsView(B * N1).add(af), head, last_act=ACT_SIGMOID)
     return cor.view(B, N1, 3), w.view(B, N1), af
 

@@ -112,6 +112,18 @@ def _group_weighted_sum(a, V, ldV, C, groups, k, idx, gpb, N, out, ldo, st):
     out.copy_((a.view(groups, k, 1) * v).sum(dim=1))
 
 
+def _group_attend(E, ldE, C, groups, k, a, af, ldaf, xyz, idx, gpb, N, cor, st):
+    Ek = E.view(groups, k, -1)[..., :C]
+    w = torch.softmax(Ek.max(dim=-1)[0], dim=-1)
+    if a is not None:
+        a.copy_(w.reshape(-1))
+    af.copy_((w.unsqueeze(-1) * Ek).sum(dim=1))
+    if cor is not None:
+        b = (torch.arange(groups * k) // k) // gpb
+        v = xyz.reshape(-1, 3)[b * N + idx.reshape(-1).long()].view(groups, k, 3)
+        cor.copy_((w.unsqueeze(-1) * v).sum(dim=1))
+
+
 def _group_max(X, ldX, C, groups, k, out, ldo, st):
     out.copy_(X.view(groups, k, -1)[..., :C].max(dim=1)[0])
 
@@ -166,7 +178,7 @@ def _weighted_kabsch(src, cor, w, B, N, Rp, tp, R, t, Rc, tc, st):
 _TABLE = {
     "hrn_fps": _fps, "hrn_knn": _knn, "hrn_knn3_sorted": _knn3_sorted, "hrn_knn3_sort": _knn3_sort, "hrn_knn3_search": _knn3_search, "hrn_gather_rows": _gather_rows, "hrn_transpose": _transpose,
     "hrn_group_geometry": _group_geometry, "hrn_group_attention": _group_attention,
-    "hrn_group_weighted_sum": _group_weighted_sum, "hrn_group_max": _group_max,
+    "hrn_group_weighted_sum": _group_weighted_sum, "hrn_group_max": _group_max, "hrn_group_attend": _group_attend,
     "hrn_sigma_to_weights": _sigma_to_weights, "hrn_transform_points": _transform_points,
     "hrn_cosine_matrix": _cosine_matrix, "hrn_cosine_pick": _cosine_pick, "hrn_weighted_kabsch": _weighted_kabsch,
 }

@@ -124,3 +124,20 @@ def test_pose_head_recovers_exact_transform(nets):
     # degenerate input (all weights zero) -> identity / zero, the reference's SVD-failure fallback
     R0, t0 = engine.weighted_kabsch(src.to(DEV), cor.to(DEV), torch.zeros(4, 1024, device=DEV))
     assert torch.equal(R0.cpu(), torch.eye(3).expand(4, 3, 3)) and float(t0.abs().max()) == 0.0
+
+
+def test_group_attend_equals_separate_kernels():
+    """hrn_group_attend == hrn_group_attention + 2 x hrn_group_weighted_sum, bit for bit (same operation order)."""
+    from pcd_reg_hregnet_b200.engine import call, ptr, stream
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, N1, N2, k, C = 3, 64, 80, 8, 512
+    F = torch.randn(B * N1 * k, C, device=DEV, generator=g)
+    dxyz = torch.randn(B, N2, 3, device=DEV, generator=g)
+    idx = torch.randint(0, N2, (B, N1, k), device=DEV, generator=g, dtype=torch.int32)
+    a = engine.group_attention(F, k)
+    cor = engine.group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2)
+    af = engine.group_weighted_sum(a, F, k)
+    a2, af2, cor2 = torch.empty_like(a), torch.empty_like(af), torch.empty_like(cor)
+    call("hrn_group_attend", ptr(F), F.stride(0), C, B * N1, k, ptr(a2), ptr(af2), af2.stride(0), ptr(dxyz), ptr(idx),
+         N1, N2, ptr(cor2), stream())
+    assert torch.equal(a, a2) and torch.equal(af, af2) and torch.equal(cor, cor2)
