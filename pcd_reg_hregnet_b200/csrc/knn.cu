@@ -76,15 +76,18 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
 }
 
 // Generic D (descriptor space, D = 256 in CoarseReg).  Sequential fma chain over d per (query, ref) pair, so the
-// distances are bit-identical to the oracle; register-tiled: a CTA owns 32 queries, a warp 8 of them, a lane 4
-// references of the current 128-reference tile -> 32 independent accumulators per thread, 12 shared-memory loads per
-// 32 FMAs.  References stream through shared memory in [128 refs] x [64 dims] slices (padded rows: conflict-free),
+// distances are bit-identical to the oracle; register-tiled: a CTA owns 32 queries, a warp 4 of them, a lane 4
+// references of the current 128-reference tile -> 16 independent accumulators per thread, 8 shared-memory loads per
+// 16 FMAs.  8 warps per CTA: with 4 warps x 8 queries the coarse-level search (32 pairs x 256 x 256 x 256) put fewer
+// than two warps on a scheduler and ran at the dependent-issue latency of a single warp (175 us, ncu: 33 % issue).  References stream through shared memory in [128 refs] x [64 dims] slices (padded rows: conflict-free),
 // double-buffered with cp.async.
 constexpr int KD_Q = 32;         // queries per CTA
 constexpr int KD_R = 128;        // references per tile
 constexpr int KD_D = 64;         // dims per slice
+constexpr int KD_WARPS = 8;      // warps per CTA
+constexpr int KD_QW = KD_Q / KD_WARPS;   // queries per warp
 template <int KPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KD_WARPS * 32)
 knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* __restrict__ out_d,
             int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn, int M, int N,
             int D, int K) {
@@ -99,9 +102,9 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         const int q = i / D;
         s_q[i] = (m0 + q < M) ? p1[(size_t)(m0 + q) * D + (i - q * D)] : 0.f;
     }
-    WarpSet<KPL> top[8];
+    WarpSet<KPL> top[KD_QW];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) top[q].init_empty(K, lane);
+    for (int q = 0; q < KD_QW; ++q) top[q].init_empty(K, lane);
     constexpr int LDR = KD_D + 1;
     // reference slices [128 refs] x [64 dims] are double-buffered with 4-byte cp.async (the padded rows that make the
     // column reads conflict-free are not 16-byte aligned): slice s+1 is in flight while slice s is consumed
@@ -123,21 +126,21 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
     for (int t0 = 0; t0 < N; t0 += KD_R) {
         // accumulators of references (lane, lane+32) and (lane+64, lane+96) packed as fp32x2: FADD2 / FFMA2 round each
         // half like the scalar instructions, so the sequential chain over d stays bit-identical to the oracle
-        f32x2_t acc[8][2];
+        f32x2_t acc[KD_QW][2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { acc[q][0] = f2_pack(0.f, 0.f); acc[q][1] = acc[q][0]; }
+        for (int q = 0; q < KD_QW; ++q) { acc[q][0] = f2_pack(0.f, 0.f); acc[q][1] = acc[q][0]; }
         for (int d0 = 0; d0 < D; d0 += KD_D, ++sl) {
             const int dn = min(KD_D, D - d0);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();                                   // slice sl visible; everybody is done with slice sl-1
             if (sl + 1 < n_slice) fill(sl + 1, (sl + 1) & 1);
             const float* sr = s_r + (sl & 1) * (KD_R * LDR);
-            const float* qb = s_q + (warp * 8) * D + d0;
+            const float* qb = s_q + (warp * KD_QW) * D + d0;
             for (int d = 0; d < dn; ++d) {
                 const f32x2_t r01 = f2_pack(sr[lane * LDR + d], sr[(lane + 32) * LDR + d]);
                 const f32x2_t r23 = f2_pack(sr[(lane + 64) * LDR + d], sr[(lane + 96) * LDR + d]);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < KD_QW; ++q) {
                     const float qv = qb[q * D + d];
                     const f32x2_t q2 = f2_pack(qv, qv);
                     const f32x2_t e0 = f2_sub(q2, r01), e1 = f2_sub(q2, r23);
@@ -147,8 +150,8 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
             }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (m0 + warp * 8 + q < M) {
+        for (int q = 0; q < KD_QW; ++q) {
+            if (m0 + warp * KD_QW + q < M) {
                 float a[4];
                 f2_unpack(acc[q][0], a[0], a[1]);
                 f2_unpack(acc[q][1], a[2], a[3]);
@@ -161,8 +164,8 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int m = m0 + warp * 8 + q;
+    for (int q = 0; q < KD_QW; ++q) {
+        const int m = m0 + warp * KD_QW + q;
         if (m >= M) continue;
         const size_t base = ((size_t)b * M + m) * K;
         top[q].sort_set(lane);
@@ -208,10 +211,10 @@ HRN_API int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int 
         dim3 gridd(hrn_divup(M, KD_Q), B);
         if (K <= 32) {
             if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnd_kernel<1><<<gridd, 128, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+            knnd_kernel<1><<<gridd, KD_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
         } else {
             if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnd_kernel<2><<<gridd, 128, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+            knnd_kernel<2><<<gridd, KD_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
         }
     }
     HRN_LAUNCH_CHECK();
