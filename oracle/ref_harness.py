@@ -109,6 +109,12 @@ def load_reference():
         ns.layers_v2, ns.Model_V2 = L2, Model_V2
     except Exception as e:  # pragma: no cover
         ns.layers_v2, ns.Model_V2, ns.v2_error = None, None, e
+    try:
+        from models.model_v4 import layers as L4
+        from models.model_v4.models import Model_V4
+        ns.layers_v4, ns.Model_V4 = L4, Model_V4
+    except Exception as e:  # pragma: no cover
+        ns.layers_v4, ns.Model_V4, ns.v4_error = None, None, e
     _loaded = ns
     return ns
 

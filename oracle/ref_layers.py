@@ -13,6 +13,8 @@ Each function cites the reference lines it follows (paths relative to /root/refe
     hregnet_forward         models/HRegNet/models.py:77-148
     fine_reg2               models/model_v2/layers.py:464-501
     model_v2_forward        models/model_v2/models.py:77-183
+    coarse_reg(want_dists)  models/model_v4/layers.py:237-369 (coord_dist :252, feats_dist :282)
+    model_v4_forward        models/model_v4/models.py:77-183
 
 Native ops underneath (FPS, gather, kNN) are oracle/native.py.  Pinning: tests/test_oracle_vs_reference.py runs
 these functions against the UNMODIFIED reference modules (oracle/ref_harness.py) on seeded inputs in the build
@@ -142,7 +144,7 @@ def _pair_tail(sd, p, feats, nbr_xyz):
     return cor, torch.sigmoid(_head(af, sd, p)), af
 
 
-def coarse_reg(sd, p, sxyz, sdesc, dxyz, ddesc, sw, dw, k=8, trace=None):
+def coarse_reg(sd, p, sxyz, sdesc, dxyz, ddesc, sw, dw, k=8, trace=None, want_dists=False):
     S, D = sdesc.permute(0, 2, 1).contiguous(), ddesc.permute(0, 2, 1).contiguous()
     _, idx, Dk = native.knn_points(S, D, K=k, return_nn=True)
     nbr_xyz = native.knn_gather(dxyz, idx)
@@ -158,6 +160,8 @@ def coarse_reg(sd, p, sxyz, sdesc, dxyz, ddesc, sw, dw, k=8, trace=None):
     if trace is not None:
         trace.update(coarse_idx=idx, coarse_feats=feats, src_nbr_desc=s_n, dst_nbr_desc=d_n)
     cor, w, _ = _pair_tail(sd, p, feats, nbr_xyz)
+    if want_dists:                                                     # model_v4/layers.py:252,282
+        return cor, w, torch.norm(rel, dim=-1).contiguous(), 1 - ds_cos
     return cor, w
 
 
@@ -212,6 +216,31 @@ def model_v2_forward(sd, src, dst):
         "src_feats_desc_2": S["desc_2"], "src_feats_sigmas_2": S["sigmas_2"], "src_xyz_2_trans": x2, "dst_xyz_2": D["xyz_2"],
         "src_dst_feats_2": f2, "src_dst_feats_2_prime": f2p, "src_dst_weights_2": w2, "src_dst_weights_2_prime": w2p,
         "src_feats": S, "dst_feats": D,
+    }
+
+
+def model_v4_forward(sd, src, dst):
+    """models/model_v4/models.py:77-183: Model_V2's cascade, the coarse stage also returning coord_dist / feats_dist."""
+    fe = "feature_extraction."
+    S = hier_feature_extraction(sd, fe, src)
+    D = hier_feature_extraction(sd, fe, dst)
+    cor3, w3, coord_dist, feats_dist = coarse_reg(sd, "coarse_corres.", S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"],
+                                                  S["sigmas_3"], D["sigmas_3"], want_dists=True)
+    R3, t3 = weighted_svd_head(S["xyz_3"], cor3, w3)
+    x2 = _apply(R3, t3, S["xyz_2"])
+    cor2, w2, w2p, f2, f2p = fine_reg2(sd, "fine_corres_2.", x2, S["desc_2"], D["xyz_2"], D["desc_2"], S["sigmas_2"], D["sigmas_2"])
+    R2_, t2_ = weighted_svd_head(x2, cor2, w2)
+    R2, t2 = _compose(R2_, t2_, R3, t3)
+    x1 = _apply(R2, t2, S["xyz_1"])
+    cor1, w1 = fine_reg(sd, "fine_corres_1.", x1, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"], D["sigmas_1"])
+    R1_, t1_ = weighted_svd_head(x1, cor1, w1)
+    R1, t1 = _compose(R1_, t1_, R2, t2)
+    return {
+        "rotation": [R3, R2, R1], "translation": [t3, t2, t1],
+        "src_feats_desc_2": S["desc_2"], "src_feats_sigmas_2": S["sigmas_2"], "src_xyz_2_trans": x2, "dst_xyz_2": D["xyz_2"],
+        "src_dst_feats_2": f2, "src_dst_feats_2_prime": f2p, "src_dst_weights_2": w2, "src_dst_weights_2_prime": w2p,
+        "coord_dist": coord_dist, "feats_dist": feats_dist,
+        "_stage_inputs": {"S": S, "D": D},                             # (not a reference key: teacher-forcing in the tests)
     }
 
 

@@ -407,7 +407,7 @@ def _cosine_features(S, D, idx, misc, col_sd, col_ds):
          col_sd, col_ds, stream())
 
 
-def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None):
+def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None, want_dists=False):
     """CoarseReg.forward with use_sim=use_neighbor=True (reference layers.py:273-396).
 
     both = (xyz [2B,N,3], desc_cl [2B,N,C]) with the source clouds in the first half and the target clouds in the
@@ -449,4 +449,10 @@ def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None):
     v.add(misc).add(sdesc_cl.view(B * N1, C), SEG_BROADCAST).add(ddesc_cl.view(B * N2, C), SEG_GATHER)
     F = stack(v, P["convs_1"])
     cor, w, _ = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
+    if want_dists:
+        # model_v4's CoarseReg also returns two by-products of the feature assembly (model_v4/layers.py:252,282):
+        # coord_dist = |candidate - source keypoint| (geometry column 3) and feats_dist = 1 - the normalised
+        # dst->src cosine similarity picked at the candidates (similarity column 13)
+        m3 = misc.view(B, N1, k, -1)
+        return cor, w, m3[..., 3].contiguous(), 1.0 - m3[..., 13]
     return cor, w

@@ -60,3 +60,15 @@ def build_product_model_v2(seed=7, device="cpu"):
     for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
         H.randomize_bn_(getattr(net, name), g)
     return net.eval().to(device)
+
+
+def build_product_model_v4(seed=7, device="cpu"):
+    """Model_V4 (coarse stage with coord_dist / feats_dist) with the pretrained feature extractor and seeded heads."""
+    from pcd_reg_hregnet_b200.model_v4 import Model_V4
+    torch.manual_seed(seed)
+    net = Model_V4(Args())
+    net.feature_extraction.load_state_dict(pretrained_feats())
+    g = torch.Generator().manual_seed(seed + 1)
+    for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
+        H.randomize_bn_(getattr(net, name), g)
+    return net.eval().to(device)

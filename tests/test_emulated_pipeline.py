@@ -79,3 +79,19 @@ def test_layer_level_api_shapes(net):
         d = desc(grouped, afm)
         want = RL.hier_feature_extraction(net.state_dict(), "feature_extraction.", xyz, levels=((1, 1024, 64),))
         assert rel_err(d, want["desc_1"]) < 1e-4 and rel_err(kp, want["xyz_1"]) < 1e-5
+
+
+def test_model_v4_coarse_stage_extra_outputs():
+    """models/model_v4: coord_dist / feats_dist of the coarse stage through the product's host orchestration."""
+    from common import build_product_model_v4
+    net4 = build_product_model_v4(seed=7)
+    gd = load_golden("hregnet_b2_n2048")
+    S, D = unflatten(gd, "src_feats."), unflatten(gd, "dst_feats.")
+    with torch.no_grad():
+        want = RL.coarse_reg(net4.state_dict(), "coarse_corres.", S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"],
+                             S["sigmas_3"], D["sigmas_3"], want_dists=True)
+        with emu.emulated_kernels():
+            got = net4.coarse_corres(S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"], S["sigmas_3"], D["sigmas_3"])
+    assert len(got) == 4 and got[2].shape == (2, 256, 8) and got[3].shape == (2, 256, 8)
+    assert float((got[2] - want[2]).abs().max()) < 1e-5 and float((got[3] - want[3]).abs().max()) < 1e-5
+    assert float((got[0] - want[0]).abs().max()) < 2e-4 and float((got[1] - want[1]).abs().max()) < 1e-5

@@ -113,6 +113,32 @@ def test_model_v2_fine_reg2_teacher_forced_and_forward(precision):
     assert all(torch.isfinite(v).all() for v in out["rotation"] + out["translation"])
 
 
+def test_model_v4_coarse_stage_teacher_forced_and_forward(precision):
+    """models/model_v4: the coarse stage's extra outputs coord_dist / feats_dist against the oracle on the oracle's
+    inputs (same candidates: the descriptor-space kNN is bit-exact), and the keys / shapes of the full forward."""
+    from common import build_product_model_v4
+    cpu, gpu = build_product_model_v4(seed=7), build_product_model_v4(seed=7, device=DEV)
+    src, dst, _, _ = synth.make_batch([61, 62], 2048)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        want = RL.model_v4_forward(cpu.state_dict(), src, dst)
+        S, D = want["_stage_inputs"]["S"], want["_stage_inputs"]["D"]
+        g = lambda t: t.to(DEV).contiguous()
+        cor, w, cd, fd = gpu.coarse_corres(g(S["xyz_3"]), g(S["desc_3"]), g(D["xyz_3"]), g(D["desc_3"]), g(S["sigmas_3"]),
+                                           g(D["sigmas_3"]))
+        assert cd.shape == (2, 256, 8) and fd.shape == (2, 256, 8)
+        assert float((cd.cpu() - want["coord_dist"]).abs().max()) < 1e-4 * float(want["coord_dist"].abs().max())
+        assert float((fd.cpu() - want["feats_dist"]).abs().max()) < 1e-5
+        assert float((w.cpu() - RL.coarse_reg(cpu.state_dict(), "coarse_corres.", S["xyz_3"], S["desc_3"], D["xyz_3"],
+                                              D["desc_3"], S["sigmas_3"], D["sigmas_3"])[1]).abs().max()) < 1e-3
+        torch.manual_seed(0)
+        out = gpu(src.to(DEV), dst.to(DEV))
+    want.pop("_stage_inputs")
+    assert set(out.keys()) == set(want.keys())
+    assert out["coord_dist"].shape == (2, 256, 8) and out["src_feats_desc_2"].shape == (2, 128, 512)
+    assert all(torch.isfinite(v).all() for v in out["rotation"] + out["translation"])
+
+
 def test_registrar_map_equals_call(net, precision):
     """Public host-buffer API: the pipelined form (Registrar.map: H2D of the next batch and D2H of the previous one
     overlap the forward) returns, batch by batch, exactly what the synchronous call returns."""

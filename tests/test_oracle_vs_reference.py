@@ -108,6 +108,37 @@ def test_model_v2_matches_reference():
         assert float((a["translation"][lv] - b["translation"][lv]).abs().max()) < 1e-5
 
 
+def test_model_v4_matches_reference():
+    """models/model_v4 (coarse stage returning coord_dist / feats_dist): state_dict keys, seeded init and forward."""
+    from common import build_product_model_v4
+    ns = H.load_reference()
+    assert ns.Model_V4 is not None, getattr(ns, "v4_error", None)
+    torch.manual_seed(7)
+    ref = ns.Model_V4(Args())
+    ref.feature_extraction.load_state_dict(torch.load(H.pretrained_feats_path(), map_location="cpu"))
+    g = torch.Generator().manual_seed(8)
+    for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
+        H.randomize_bn_(getattr(ref, name), g)
+    ref.eval()
+    prod = build_product_model_v4(seed=7)
+    rs, ps = ref.state_dict(), prod.state_dict()
+    assert list(rs.keys()) == list(ps.keys()) and all(torch.equal(rs[k], ps[k]) for k in rs)
+    src, dst, _, _ = synth.make_batch([44, 45], 2048)
+    with torch.no_grad():
+        torch.manual_seed(0); a = ref(src, dst)
+        torch.manual_seed(0); b = RL.model_v4_forward(rs, src, dst)
+    b.pop("_stage_inputs")
+    assert set(a.keys()) == set(b.keys())
+    assert a["coord_dist"].shape == (2, 256, 8) and a["feats_dist"].shape == (2, 256, 8)
+    assert float((a["coord_dist"] - b["coord_dist"]).abs().max()) < 1e-5
+    assert float((a["feats_dist"] - b["feats_dist"]).abs().max()) < 1e-5
+    for k in ("src_dst_feats_2", "src_dst_weights_2", "src_dst_weights_2_prime"):
+        assert float((a[k] - b[k]).abs().max()) < 1e-5, k
+    for lv in range(3):
+        assert float(RL.rotation_angle_deg(a["rotation"][lv], b["rotation"][lv]).max()) < 1e-4
+        assert float((a["translation"][lv] - b["translation"][lv]).abs().max()) < 1e-5
+
+
 def test_metrics_oracle_matches_reference_functions():
     """oracle/ref_metrics.py against the UNMODIFIED models/utils.py:calc_error_np and losses/losses.py:calc_rot_rre_err /
     calc_tran_rte_err (Euler conversion injected, see ref_harness.load_reference_losses) on fresh random poses."""
