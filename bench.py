@@ -47,8 +47,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="hregnet", choices=["hregnet", "v2"],
-                    help="hregnet = BASELINE configs[1] (default); v2 = Adaption-1 / Model_V2 (configs[3], use --points 32768)")
+    ap.add_argument("--model", default="hregnet", choices=["hregnet", "v2", "v4"],
+                    help="hregnet = BASELINE configs[1] (default); v2 = Adaption-1 / Model_V2 (configs[3], use --points 32768); "
+                         "v4 = Model_V4 (Model_V2 + coord_dist / feats_dist of the coarse stage)")
     return ap.parse_args()
 
 
@@ -188,9 +189,9 @@ def main():
     lo = rank * B
     src_h, dst_h, _, _ = synth.make_batch(range(1000 + lo, 1000 + lo + B), N)
     src_h, dst_h = src_h.pin_memory(), dst_h.pin_memory()
-    if args.model == "v2":
-        from common import build_product_model_v2
-        net = build_product_model_v2(seed=7, device=dev)
+    if args.model in ("v2", "v4"):
+        from common import build_product_model_v2, build_product_model_v4
+        net = (build_product_model_v2 if args.model == "v2" else build_product_model_v4)(seed=7, device=dev)
         args.no_graph = True      # FineReg2 draws its batch shuffles from the host RNG every forward (model_v2/layers.py:493)
     else:
         net = build_product_hregnet(seed=7, device=dev)
@@ -264,7 +265,7 @@ def main():
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32" if precision == "fp32" else "bf16x3 (tcgen05, fp32 accumulate) + fp32",
             "data": "synthetic",
-            "config": {"workload": f"{'HRegNet baseline' if args.model == 'hregnet' else 'Adaption-1 (Model_V2)'} forward, batch {B} synthetic {N}-pt pairs per GPU (keypoints 1024/512/256)",
+            "config": {"workload": f"{dict(hregnet='HRegNet baseline', v2='Adaption-1 (Model_V2)', v4='Model_V4')[args.model]} forward, batch {B} synthetic {N}-pt pairs per GPU (keypoints 1024/512/256)",
                        "pairs_per_gpu": B, "points": N, "parallelism": f"pairs sharded over {world} GPU(s), pose all-gather",
                        "l2": "L2 flushed (256 MiB write) between timed iterations", "cuda_graph": not args.no_graph,
                        "precision": precision},

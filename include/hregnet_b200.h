@@ -81,6 +81,17 @@ int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* p2, int 
  *   x [B,N,U], idx [B,M,K] int64 -> out [B,M,K,U]. */
 int hrn_knn_gather(const float* x, const int64_t* idx, float* out, int B, int N, int M, int K, int U, void* stream);
 
+/* Backward passes of the two pytorch3d stand-ins (pytorch3d's autograd functions provide them to the
+ * reference's training scripts, train/train_reg_v0.py:281-296):
+ *   hrn_knn_gather_grad: grad_x [B,N,U] (pre-zeroed) += scatter of grad_out [B,M,K,U] through idx [B,M,K] (fp32 atomics);
+ *   hrn_knn_dists_grad:  for dists[b,m,k] = |p1[b,m] - p2[b,idx]|^2 and grad_dists [B,M,K]:
+ *                        grad_p1 [B,M,D] (nullable) = sum_k 2 g (p1 - p2[idx]), grad_p2 [B,N,D] (nullable, pre-zeroed)
+ *                        -= 2 g (p1 - p2[idx]) (fp32 atomics). */
+int hrn_knn_gather_grad(const float* grad_out, const int64_t* idx, float* grad_x, int B, int N, int M, int K, int U,
+                        void* stream);
+int hrn_knn_dists_grad(const float* p1, const float* p2, const int64_t* idx, const float* grad_dists, float* grad_p1,
+                       float* grad_p2, int B, int M, int N, int D, int K, void* stream);
+
 /* Row gather with int32 indices: out[b,m,:] = x[b, idx[b,m], :]  (the gather_operation(x^T, idx)^T idiom of
  * layers.py:140,143 without its two permute+contiguous passes). */
 int hrn_gather_rows(const float* x, const int32_t* idx, float* out, int B, int N, int M, int U, void* stream);

@@ -37,6 +37,8 @@ SIGNATURES = {
     "hrn_knn3_sort": [c_vp, c_int, c_int, c_vp, c_vp, c_vp],
     "hrn_knn3_search": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_knn_gather": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
+    "hrn_knn_gather_grad": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
+    "hrn_knn_dists_grad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "hrn_gather_rows": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_transpose": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_layer_fp32": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp],

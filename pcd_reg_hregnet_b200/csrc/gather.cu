@@ -5,6 +5,8 @@
 //   hrn_gather_rows         <- the `gather_operation(xyz^T, idx)^T` idiom of layers.py:140,143 without the two
 //                              permute+contiguous passes: out[b,m,:] = x[b,idx[b,m],:] (row gather, int32 idx)
 //   hrn_knn_gather          <- pytorch3d.ops.knn_gather (call sites layers.py:25,279,288,303,...): int64 idx
+//   hrn_knn_gather_grad, hrn_knn_dists_grad <- the backward passes of knn_gather / knn_points that pytorch3d's autograd
+//                              functions provide to the reference's training scripts (train/train_reg_v0.py:281-296)
 //   hrn_transpose_bcn_bnc   <- the permute(0,2,1).contiguous() glue between the [B,C,N] API layout and the
 //                              channels-last rows the kernels consume (tiled through shared memory)
 #include "common.cuh"
@@ -36,6 +38,41 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const IdxT* __re
         const int u = (int)(i - r * U);
         const long long b = r / rows_per_batch;
         out[i] = __ldg(x + ((size_t)b * N + (size_t)idx[r]) * U + u);
+    }
+}
+
+// Backward of knn_gather: grad_x[b, idx[b,m,k], u] += grad_out[b,m,k,u]  (grad_x pre-zeroed by the caller; fp32 atomics,
+// like the reference's own gather gradient, furthest_point_sampling_gpu.cu:41-55)
+__global__ void knn_gather_grad_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                                       float* __restrict__ grad_x, long long total, int rows_per_batch, int N, int U) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / U;
+        const int u = (int)(i - r * U);
+        const long long b = r / rows_per_batch;
+        atomicAdd(grad_x + ((size_t)b * N + (size_t)idx[r]) * U + u, grad_out[i]);
+    }
+}
+
+// Backward of knn_points' squared distances  d[b,m,k] = sum_j (p1[b,m,j] - p2[b,idx,j])^2 :
+//   grad_p1[b,m,j]   = sum_k 2 g[b,m,k] (p1 - p2[idx])          (one thread per (b,m,j): plain sum over k)
+//   grad_p2[b,idx,j] -=       2 g[b,m,k] (p1 - p2[idx])          (atomics; pre-zeroed by the caller)
+__global__ void knn_dists_grad_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                      const int64_t* __restrict__ idx, const float* __restrict__ g,
+                                      float* __restrict__ grad_p1, float* __restrict__ grad_p2, long long total, int M,
+                                      int N, int D, int K) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long bm = i / D;
+        const int j = (int)(i - bm * D);
+        const long long b = bm / M;
+        const float q = p1[i];
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const size_t n = (size_t)b * N + (size_t)idx[bm * K + k];
+            const float t = 2.f * g[bm * K + k] * (q - p2[n * D + j]);
+            acc += t;
+            if (grad_p2) atomicAdd(grad_p2 + n * D + j, -t);
+        }
+        if (grad_p1) grad_p1[i] = acc;
     }
 }
 
@@ -96,6 +133,30 @@ HRN_API int hrn_knn_gather(const float* x, const int64_t* idx, float* out, int B
     if (total == 0) return HRN_OK;
     const int blocks = (int)((total + 255) / 256 < 148LL * 16 ? (total + 255) / 256 : 148LL * 16);
     gather_rows_kernel<int64_t><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, idx, out, total, M * K, N, U);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_knn_gather_grad(const float* grad_out, const int64_t* idx, float* grad_x, int B, int N, int M, int K,
+                                int U, void* stream) {
+    if (!grad_out || !idx || !grad_x || B < 0 || N <= 0 || M < 0 || K < 0 || U <= 0) return HRN_ERR_BAD_ARG;
+    const long long total = (long long)B * M * K * U;
+    if (total == 0) return HRN_OK;
+    const int blocks = (int)((total + 255) / 256 < 148LL * 16 ? (total + 255) / 256 : 148LL * 16);
+    knn_gather_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, idx, grad_x, total, M * K, N, U);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
+HRN_API int hrn_knn_dists_grad(const float* p1, const float* p2, const int64_t* idx, const float* grad_dists,
+                               float* grad_p1, float* grad_p2, int B, int M, int N, int D, int K, void* stream) {
+    if (!p1 || !p2 || !idx || !grad_dists || (!grad_p1 && !grad_p2) || B < 0 || M < 0 || N <= 0 || D <= 0 || K <= 0)
+        return HRN_ERR_BAD_ARG;
+    const long long total = (long long)B * M * D;
+    if (total == 0) return HRN_OK;
+    const int blocks = (int)((total + 255) / 256 < 148LL * 16 ? (total + 255) / 256 : 148LL * 16);
+    knn_dists_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p1, p2, idx, grad_dists, grad_p1, grad_p2, total, M, N,
+                                                                    D, K);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }

@@ -86,44 +86,91 @@ gather_operation = GatherOperation.apply
 _KNN = namedtuple("KNN", "dists idx knn")
 
 
+def _knn_forward(p1, p2, K):
+    B, M, D = p1.shape
+    N = p2.shape[1]
+    dists = torch.empty(B, M, K, dtype=torch.float32, device=p1.device)
+    idx = torch.empty(B, M, K, dtype=torch.int64, device=p1.device)
+    if D == 3 and 1024 <= N <= 32768:      # spatially culled exact search (same results, see csrc/knn_sorted.cu)
+        from .engine import knn_scratch
+        pts, boxes = knn_scratch(B, N, p1.device)
+        call("hrn_knn3_sorted", ptr(p1), None, ptr(p2), B, M, N, K, ptr(pts), ptr(boxes), ptr(dists), ptr(idx), None, None,
+             None, stream())
+    else:
+        call("hrn_knn", ptr(p1), None, ptr(p2), B, M, N, D, K, ptr(dists), ptr(idx), None, None, None, stream())
+    return dists, idx
+
+
+class _KnnPoints(Function):
+    """dists / idx of the exact search; differentiable w.r.t. both clouds through the squared distances
+    (d dists / d p1 = 2 (p1 - p2[idx]), scattered with the opposite sign into p2), like pytorch3d's _knn_points."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, K):
+        dists, idx = _knn_forward(p1, p2, K)
+        ctx.save_for_backward(p1, p2, idx)
+        ctx.mark_non_differentiable(idx)
+        return dists, idx
+
+    @staticmethod
+    def backward(ctx, grad_dists, grad_idx):
+        p1, p2, idx = ctx.saved_tensors
+        B, M, D = p1.shape
+        N, K = p2.shape[1], idx.shape[2]
+        g = grad_dists.contiguous().float()
+        gp1 = torch.empty_like(p1) if ctx.needs_input_grad[0] else None
+        gp2 = torch.zeros_like(p2) if ctx.needs_input_grad[1] else None
+        if gp1 is not None or gp2 is not None:
+            call("hrn_knn_dists_grad", ptr(p1), ptr(p2), ptr(idx), ptr(g), ptr(gp1), ptr(gp2), B, M, N, D, K, stream())
+        return gp1, gp2, None
+
+
+class _KnnGather(Function):
+    """x [B,N,U], idx [B,M,K] int64 -> [B,M,K,U]; differentiable w.r.t. x (scatter-add)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        B, N, U = x.shape
+        _, M, K = idx.shape
+        out = torch.empty(B, M, K, U, dtype=torch.float32, device=x.device)
+        call("hrn_knn_gather", ptr(x), ptr(idx), ptr(out), B, N, M, K, U, stream())
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, N, M, K, U)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, = ctx.saved_tensors
+        B, N, M, K, U = ctx.dims
+        g = grad_out.contiguous().float()
+        gx = torch.zeros(B, N, U, dtype=torch.float32, device=g.device)
+        call("hrn_knn_gather_grad", ptr(g), ptr(idx), ptr(gx), B, N, M, K, U, stream())
+        return gx, None
+
+
 def knn_points(p1, p2, lengths1=None, lengths2=None, norm: int = 2, K: int = 1, version: int = -1,
                return_nn: bool = False, return_sorted: bool = True):
     """pytorch3d.ops.knn_points stand-in: (dists [B,M,K] squared, ascending; idx int64; nn [B,M,K,D] | None).
 
-    Deterministic order (dist asc, index asc).  `lengths*` (ragged batches) and norm != 2 are not used by the
-    reference (layers.py:20,278,316,322,434) and are rejected."""
+    Deterministic order (dist asc, index asc).  Differentiable like pytorch3d's: `dists` w.r.t. p1 and p2, `knn` w.r.t.
+    p2 (it is knn_gather(p2, idx)).  `lengths*` (ragged batches) and norm != 2 are not used by the reference
+    (layers.py:20,278,316,322,434) and are rejected."""
     if lengths1 is not None or lengths2 is not None or norm != 2:
         raise NotImplementedError("ragged batches / L1 norm are not part of the HRegNet path")
     p1 = p1.contiguous()
     p2 = p2.contiguous()
     if p1.dtype != torch.float32 or p2.dtype != torch.float32:
         raise TypeError("knn_points expects float32")
-    B, M, D = p1.shape
-    N = p2.shape[1]
-    dists = torch.empty(B, M, K, dtype=torch.float32, device=p1.device)
-    idx = torch.empty(B, M, K, dtype=torch.int64, device=p1.device)
-    nn = torch.empty(B, M, K, D, dtype=torch.float32, device=p1.device) if return_nn else None
-    if D == 3 and 1024 <= N <= 32768:      # spatially culled exact search (same results, see csrc/knn_sorted.cu)
-        from .engine import knn_scratch
-        pts, boxes = knn_scratch(B, N, p1.device)
-        call("hrn_knn3_sorted", ptr(p1), None, ptr(p2), B, M, N, K, ptr(pts), ptr(boxes), ptr(dists), ptr(idx), None, ptr(nn),
-             None, stream())
-    else:
-        call("hrn_knn", ptr(p1), None, ptr(p2), B, M, N, D, K, ptr(dists), ptr(idx), None, ptr(nn), None, stream())
+    dists, idx = _KnnPoints.apply(p1, p2, K)
+    nn = _KnnGather.apply(p2, idx) if return_nn else None
     return _KNN(dists, idx, nn)
 
 
 def knn_gather(x, idx, lengths=None):
-    """pytorch3d.ops.knn_gather stand-in: x [B,N,U], idx [B,M,K] int64 -> [B,M,K,U]."""
+    """pytorch3d.ops.knn_gather stand-in: x [B,N,U], idx [B,M,K] int64 -> [B,M,K,U]; differentiable w.r.t. x."""
     if lengths is not None:
         raise NotImplementedError("ragged batches are not part of the HRegNet path")
-    x = x.contiguous()
-    idx = idx.contiguous()
-    B, N, U = x.shape
-    _, M, K = idx.shape
-    out = torch.empty(B, M, K, U, dtype=torch.float32, device=x.device)
-    call("hrn_knn_gather", ptr(x), ptr(idx), ptr(out), B, N, M, K, U, stream())
-    return out
+    return _KnnGather.apply(x.contiguous(), idx.contiguous())
 
 
 class _PointUtilsShim:

@@ -199,3 +199,36 @@ def test_full_size_properties():
     # kNN is idempotent under re-query with K' < K (prefix)
     d2, i2, _ = ops.knn_points(q, xyz, K=16)
     assert torch.equal(i2, i[..., :16]) and torch.equal(d2, d[..., :16])
+
+
+@pytest.mark.parametrize("B,M,N,D,K", [(2, 300, 2048, 3, 16), (2, 64, 200, 3, 8), (1, 40, 96, 32, 8)])
+def test_knn_points_and_knn_gather_backward(B, M, N, D, K):
+    """The pytorch3d stand-ins are differentiable like the originals: gradients of the squared distances
+    w.r.t. both clouds, of `knn` w.r.t. p2 and of knn_gather w.r.t. x, against fp64 autograd of the same formulas on
+    the CPU (the neighbour indices are the forward's, bit-exact)."""
+    g = torch.Generator().manual_seed(B * M + K)
+    p1 = torch.randn(B, M, D, generator=g)
+    p2 = torch.randn(B, N, D, generator=g)
+    wd, wn = torch.randn(B, M, K, generator=g), torch.randn(B, M, K, D, generator=g)
+    a1, a2 = p1.to(DEV).requires_grad_(True), p2.to(DEV).requires_grad_(True)
+    d, i, nn = ops.knn_points(a1, a2, K=K, return_nn=True)
+    ((d * wd.to(DEV)).sum() + (nn * wn.to(DEV)).sum()).backward()
+    c1, c2 = p1.double().requires_grad_(True), p2.double().requires_grad_(True)
+    bidx = torch.arange(B)[:, None, None]
+    nn_c = c2[bidx, i.cpu()]
+    d_c = ((c1[:, :, None, :] - nn_c) ** 2).sum(-1)
+    ((d_c * wd.double()).sum() + (nn_c * wn.double()).sum()).backward()
+    assert torch.allclose(d.detach().cpu().double(), d_c.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a1.grad.cpu().double(), c1.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(a2.grad.cpu().double(), c2.grad, rtol=1e-4, atol=1e-4)
+    # knn_gather alone
+    x = torch.randn(B, N, 7, generator=g)
+    w = torch.randn(B, M, K, 7, generator=g)
+    ax = x.to(DEV).requires_grad_(True)
+    (ops.knn_gather(ax, i) * w.to(DEV)).sum().backward()
+    cx = x.double().requires_grad_(True)
+    (cx[bidx, i.cpu()] * w.double()).sum().backward()
+    assert torch.allclose(ax.grad.cpu().double(), cx.grad, rtol=1e-4, atol=1e-4)
+    # no gradient requested -> plain forward, indices unchanged
+    d2, i2, _ = ops.knn_points(p1.to(DEV), p2.to(DEV), K=K)
+    assert torch.equal(i2, i) and torch.equal(d2, d.detach())
