@@ -93,9 +93,14 @@ def main():
             if a.quick:
                 continue
             idx = ops.furthest_point_sample(xyz, M)
+            q = xyz[torch.arange(B, device="cuda")[:, None], idx.long()]
             for K in (16, 32, 64):
                 t = timeit(lambda: engine.knn_idx(None, xyz, K, q_idx=idx))
                 r = {"op": "knn", "B": B, "N": N, "M": M, "K": K, "ms": t, "Gpair_per_s": B * M * N / t / 1e6}
+                if B * M * N <= (1 << 30):
+                    # "reference GPU path" bar: pytorch3d is not installable offline, so the library route to
+                    # the same result -- torch.cdist + topk (distances not bit-identical: cdist uses the GEMM expansion)
+                    r["torch_cdist_topk_ms"] = timeit(lambda: torch.cdist(q, xyz).topk(K, dim=2, largest=False), reps=2, warm=1)
                 rows.append(r)
                 print(json.dumps(r), flush=True)
     return rows
