@@ -430,6 +430,7 @@ int launch_fps_cluster_t(const float* xyz, const float* w, float* temp, int32_t*
     cfg.blockDim = dim3(THREADS);
     const size_t smem = (size_t)2 * CS * (THREADS / 32) * 8 + (FULL ? (size_t)N * 12 : 0);
     if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16 CTAs: opt-in
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -495,6 +496,11 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
         if (N <= 16384) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 2, st);
         if (N <= 32768) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 4, st);
         if (N <= 65536) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 8, st);
+        if (N <= 131072) {                              // 16-CTA clusters (non-portable size); else the streaming kernel below
+            const int rc = launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 16, st);
+            if (rc == HRN_OK) return rc;
+            (void)cudaGetLastError();
+        }
     }
     if (N > (4096 << 10) || temp == nullptr) return HRN_ERR_BAD_ARG;   // streaming path needs the scratch buffer
     return launch_fps<1024, 0, W>(xyz, w, temp, idx, B, N, M, log2T, st);

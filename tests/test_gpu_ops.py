@@ -39,6 +39,8 @@ def _clouds(kind, B, N, seed):
     ("uniform", 1, 70000, 64),
     # more samples than the 10-bit iteration tag of the exchange packets counts (tags wrap, buffers alternate)
     ("uniform", 2, 4096, 3000), ("lidar", 1, 16384, 2500), ("uniform", 2, 1024, 1024),
+    # 16-CTA clusters (65536 < N <= 131072), streaming kernel beyond
+    ("uniform", 2, 131072, 100), ("lattice", 1, 100000, 64), ("uniform", 1, 140000, 40),
 ])
 def test_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=N + M)
