@@ -230,14 +230,16 @@ def main():
     t_ms = sum(s.elapsed_time(e) for s, e in ev)
 
     # ---- end to end through the public API, host buffers -------------------------------------------------------
+    post = (lambda out: hdist.gather_poses(out["rotation"][-1], out["translation"][-1])) if world > 1 else None
     for _ in range(2):
         reg(src_h, dst_h)
+    for _ in reg.map(((src_h, dst_h) for _ in range(4)), post=post):      # untimed: captures the second lane, warms the pipeline
+        pass
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     # throughput form of the public API: every batch is copied H2D from pinned memory and its poses D2H inside the
     # timed region; Registrar.map only takes the copies of batch i+1 / i-1 off the critical path of batch i
-    post = (lambda out: hdist.gather_poses(out["rotation"][-1], out["translation"][-1])) if world > 1 else None
     t0 = time.perf_counter()
     n_done = 0
     for R_h, t_h in reg.map(((src_h, dst_h) for _ in range(args.steps)), post=post):
@@ -271,7 +273,8 @@ def main():
                        "precision": precision},
             "clocks": clocks,
             "e2e": {"value": total_pairs / (e2e_ms / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": 2 * B * N * 3 * 4, "d2h_bytes_per_step": B * 12 * 4},
+                    "h2d_bytes_per_step": 2 * B * N * 3 * 4, "d2h_bytes_per_step": B * 12 * 4,
+                    "api": f"Registrar.map, {len(reg._pipe['lanes'])} forward(s) in flight"},
             "gpu_launches": launches * args.steps,
             "kernel_breakdown_ms_per_step": prof["families"],
             "roofline": prof["roofline"](pk),

@@ -12,13 +12,17 @@ stream-ordered on one CUDA stream; the only host synchronisation is the final wa
 is the throughput form: the H2D copy of batch i+1 runs on a copy stream into a staging buffer while batch i is being
 registered (the graph reads fixed input buffers, so a 12.6 MB device-to-device copy in front of each replay moves the
 staged clouds in), and the poses of batch i are read back while batch i+1 runs.  Every batch still pays its own H2D and
-D2H copies; they are only taken off the critical path.
+D2H copies; they are only taken off the critical path.  With `in_flight` = 2 (the default) the forward is captured
+twice (two sets of input / activation buffers, shared weights) and consecutive batches replay on two streams: the
+sampling kernels are latency-bound with one small cluster per cloud and the shared-MLP kernels fill the chip, so two
+forwards half a step apart use SMs the other leaves idle (6.10 -> 5.55 ms per 32-pair batch on one B200,
+tools/split_probe.py --pipelined).
 """
 import torch
 
 
 class Registrar:
-    def __init__(self, net, batch, n_points, use_cuda_graph=True, warmup=2):
+    def __init__(self, net, batch, n_points, use_cuda_graph=True, warmup=2, in_flight=2):
         self.net = net.eval()
         self.device = next(net.parameters()).device
         self.batch, self.n_points = batch, n_points
@@ -30,6 +34,7 @@ class Registrar:
         self.out = None
         self.use_cuda_graph = use_cuda_graph
         self._warm = warmup
+        self.in_flight = max(1, int(in_flight))   # forwards map() keeps enqueued at once (each on its own stream)
         self._pipe = None           # lazily created state of map(): copy stream, staging buffers, result slots
 
     def _forward(self):
@@ -76,49 +81,79 @@ class Registrar:
 
     # ---- pipelined form ------------------------------------------------------------------------------------------
     def _pipe_state(self):
+        """Lanes of map(): lane 0 is this object; every further lane is a second capture of the same forward (own input
+        buffers, own graph, own activations; the weights are shared) that replays on its own stream."""
         if self._pipe is None:
+            main = torch.cuda.current_stream(self.device)
+            lanes = []
+            for i in range(self.in_flight if self.use_cuda_graph else 1):   # eager forwards are host-bound: one lane
+                reg = self if i == 0 else Registrar(self.net, self.batch, self.n_points, self.use_cuda_graph,
+                                                    self._warm, in_flight=1)
+                if reg is not self:
+                    reg.src.copy_(self.src)
+                    reg.dst.copy_(self.dst)
+                    if self.use_cuda_graph:
+                        reg.capture()
+                lane = dict(reg=reg, stream=torch.cuda.Stream(device=self.device) if self.in_flight > 1 and self.use_cuda_graph else None,
+                            stage=(torch.empty_like(self.src), torch.empty_like(self.dst)),
+                            staged=torch.cuda.Event(), stage_free=torch.cuda.Event())
+                lane["stage_free"].record(main)
+                lanes.append(lane)
             self._pipe = dict(
-                copy=torch.cuda.Stream(device=self.device),
-                stage=(torch.empty_like(self.src), torch.empty_like(self.dst)),
-                staged=torch.cuda.Event(), stage_free=torch.cuda.Event(),
+                copy=torch.cuda.Stream(device=self.device), lanes=lanes,
                 slots=[(torch.empty(self.batch, 3, 3).pin_memory(), torch.empty(self.batch, 3).pin_memory(),
-                        torch.cuda.Event()) for _ in range(2)])
-            self._pipe["stage_free"].record(torch.cuda.current_stream(self.device))
+                        torch.cuda.Event()) for _ in range(self.in_flight + 2)])
         return self._pipe
 
     def map(self, batches, post=None):
         """Registers an iterable of (src_host, dst_host) pinned batches; yields (R_host, t_host) per batch, in order.
-        The yielded tensors are one of two result slots: consume (or copy) them before asking for the batch after next.
-        `post(out)` -- optional -- is called right after each forward has been enqueued, with the device result dict
-        (e.g. to enqueue a collective on the poses)."""
+        Up to `in_flight` forwards are enqueued before the oldest result is waited for; with in_flight > 1 consecutive
+        batches run on different streams, so the latency-bound sampling kernels of one batch (one small cluster per
+        cloud, most SMs idle) run beside the tensor-core kernels of its neighbour.  Every batch is still copied H2D,
+        registered in full and read back D2H.
+        The yielded tensors are one of in_flight + 2 result slots: consume (or copy) them before asking for the batch
+        after next.  `post(out)` -- optional -- is called right after each forward has been enqueued, on that forward's
+        stream, with the device result dict (e.g. to enqueue a collective on the poses)."""
         if self.graph is None and self.use_cuda_graph:
             self.capture()
         P = self._pipe_state()
+        lanes, slots = P["lanes"], P["slots"]
         main = torch.cuda.current_stream(self.device)
-        pending = None
+        for lane in lanes:
+            if lane["stream"] is not None:
+                lane["stream"].wait_stream(main)
+        pending = []
         n = 0
         for src_host, dst_host in batches:
+            lane = lanes[n % len(lanes)]
+            run = lane["stream"] if lane["stream"] is not None else main
+            reg = lane["reg"]
             with torch.cuda.stream(P["copy"]):
-                P["copy"].wait_event(P["stage_free"])               # the previous batch has left the staging buffers
-                P["stage"][0].copy_(src_host, non_blocking=True)
-                P["stage"][1].copy_(dst_host, non_blocking=True)
-                P["staged"].record(P["copy"])
-            main.wait_event(P["staged"])
-            self.src.copy_(P["stage"][0], non_blocking=True)
-            self.dst.copy_(P["stage"][1], non_blocking=True)
-            P["stage_free"].record(main)
-            out = self.run_device()
-            if post is not None:
-                post(out)
-            R_h, t_h, done = P["slots"][n & 1]
-            R_h.copy_(out["rotation"][-1], non_blocking=True)
-            t_h.copy_(out["translation"][-1], non_blocking=True)
-            done.record(main)
-            if pending is not None:
-                pending[2].synchronize()
-                yield pending[0], pending[1]
-            pending = (R_h, t_h, done)
+                P["copy"].wait_event(lane["stage_free"])            # the lane's previous batch has left its staging buffers
+                lane["stage"][0].copy_(src_host, non_blocking=True)
+                lane["stage"][1].copy_(dst_host, non_blocking=True)
+                lane["staged"].record(P["copy"])
+            with torch.cuda.stream(run):
+                run.wait_event(lane["staged"])
+                reg.src.copy_(lane["stage"][0], non_blocking=True)
+                reg.dst.copy_(lane["stage"][1], non_blocking=True)
+                lane["stage_free"].record(run)
+                out = reg.run_device()
+                if post is not None:
+                    post(out)
+                R_h, t_h, done = slots[n % len(slots)]
+                R_h.copy_(out["rotation"][-1], non_blocking=True)
+                t_h.copy_(out["translation"][-1], non_blocking=True)
+                done.record(run)
+            pending.append((R_h, t_h, done))
             n += 1
-        if pending is not None:
-            pending[2].synchronize()
-            yield pending[0], pending[1]
+            if len(pending) > len(lanes):
+                R_h, t_h, done = pending.pop(0)
+                done.synchronize()
+                yield R_h, t_h
+        for lane in lanes:
+            if lane["stream"] is not None:
+                main.wait_stream(lane["stream"])
+        for R_h, t_h, done in pending:
+            done.synchronize()
+            yield R_h, t_h

@@ -139,19 +139,24 @@ def test_model_v4_coarse_stage_teacher_forced_and_forward(precision):
     assert all(torch.isfinite(v).all() for v in out["rotation"] + out["translation"])
 
 
-def test_registrar_map_equals_call(net, precision):
+@pytest.mark.parametrize("in_flight", [1, 2, 3])
+def test_registrar_map_equals_call(net, precision, in_flight):
     """Public host-buffer API: the pipelined form (Registrar.map: H2D of the next batch and D2H of the previous one
-    overlap the forward) returns, batch by batch, exactly what the synchronous call returns."""
+    overlap the forward; with in_flight > 1 consecutive batches replay on different streams from separate captures of
+    the forward) returns, batch by batch, exactly what the synchronous call returns."""
     from pcd_reg_hregnet_b200.runner import Registrar
     B, N = 2, 4096
     batches = []
-    for s in range(3):
+    for s in range(7):
         src, dst, _, _ = synth.make_batch([50 + 2 * s, 51 + 2 * s], N)
         batches.append((src.pin_memory(), dst.pin_memory()))
-    reg = Registrar(net, B, N)
+    reg = Registrar(net, B, N, in_flight=in_flight)
     want = [tuple(x.clone() for x in reg(s, d)) for s, d in batches]
-    got = [tuple(x.clone() for x in rt) for rt in reg.map(batches)]
-    assert len(got) == len(want)
-    for (R0, t0), (R1, t1) in zip(want, got):
-        assert torch.equal(R0, R1) and torch.equal(t0, t1)
+    for _ in range(2):                                               # the second pass reuses lanes and result slots
+        got = [tuple(x.clone() for x in rt) for rt in reg.map(batches)]
+        assert len(got) == len(want)
+        for (R0, t0), (R1, t1) in zip(want, got):
+            assert torch.equal(R0, R1) and torch.equal(t0, t1)
+    assert len(reg._pipe["lanes"]) == in_flight
     assert not torch.equal(want[0][0], want[1][0])                   # the batches really differ
+    assert [tuple(x.clone() for x in rt) for rt in reg.map(batches[:1])][0][0].equal(want[0][0])   # fewer batches than lanes
