@@ -11,7 +11,10 @@ Weak scaling: 32 pairs per GPU (N=8 -> the 256-pair job of configs[2]).
   value     pairs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       pairs/s through the public API (pcd_reg_hregnet_b200.runner.Registrar.map) from pinned HOST buffers:
             per batch the H2D copy of both clouds + forward + D2H of the poses, all inside the timed region (the
-            copies of neighbouring batches overlap the forward on a copy stream)
+            copies of neighbouring batches overlap the forward on a copy stream, and two forwards are in flight on
+            two streams)
+  in_flight pairs/s of the same K steps from device-resident inputs with map()'s two forwards in flight (rotating
+            input batches larger than L2 instead of a flush) -- what e2e is bounded by; `value` stays one forward at a time
   roofline  dominant kernel family (shared-MLP layers): algorithmic FLOP / CUDA-event time of those launches
   cpu_baseline  the oracle port of the reference (oracle/ref_layers.py + oracle/native_ops.c) on the host cores,
             bounded sample (rank 0, N=1 only)
@@ -247,12 +250,49 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     assert n_done == args.steps
+
+    # ---- device-resident throughput with the forwards of map() in flight (explains e2e > value) -----------------
+    # `value` above times one forward at a time with an L2 flush in front of each; map() keeps two in flight.  Here
+    # the same K steps run back to back on map()'s lanes from 16 rotating device-resident input batches (201 MB at the
+    # default size: larger than the 126 MB L2, so no flush), each step copying its batch into the lane's input buffers.
+    lanes = reg._pipe["lanes"]
+    n_rot = 16
+    rot = [(reg.src.clone(), reg.dst.clone()) for _ in range(n_rot)]
+    main_s = torch.cuda.current_stream(dev)
+
+    def pipelined(K):
+        for ln in lanes:
+            if ln["stream"] is not None:
+                ln["stream"].wait_stream(main_s)
+        for k in range(K):
+            ln = lanes[k % len(lanes)]
+            with torch.cuda.stream(ln["stream"] if ln["stream"] is not None else main_s):
+                ln["reg"].src.copy_(rot[k % n_rot][0], non_blocking=True)
+                ln["reg"].dst.copy_(rot[k % n_rot][1], non_blocking=True)
+                out = ln["reg"].run_device()
+                if post is not None:
+                    post(out)
+        for ln in lanes:
+            if ln["stream"] is not None:
+                main_s.wait_stream(ln["stream"])
+
+    pipelined(4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    pipelined(args.steps)
+    p1.record()
+    torch.cuda.synchronize()
+    pipe_ms = p0.elapsed_time(p1)
+    del rot
     clocks = sampler.stop()
 
-    tt = torch.tensor([t_ms, e2e_ms], device=dev, dtype=torch.float64)
+    tt = torch.tensor([t_ms, e2e_ms, pipe_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms, e2e_ms = tt.tolist()
+    t_ms, e2e_ms, pipe_ms = tt.tolist()
 
     # ---- per-kernel-family breakdown + roofline of the dominant family (rank 0) ---------------------------------
     prof = _profile_families(reg, steps=min(args.steps, 3)) if rank == 0 else None
@@ -275,6 +315,11 @@ def main():
             "e2e": {"value": total_pairs / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * B * N * 3 * 4, "d2h_bytes_per_step": B * 12 * 4,
                     "api": f"Registrar.map, {len(reg._pipe['lanes'])} forward(s) in flight"},
+            "in_flight": {"value": total_pairs / (pipe_ms / 1e3), "unit": UNIT, "ms_per_step": pipe_ms / args.steps,
+                          "forwards_in_flight": len(lanes),
+                          "note": "same K steps, device-resident inputs, back to back on Registrar.map's lanes; "
+                                  f"{n_rot} rotating input batches ({n_rot * 2 * B * N * 12 / 1e6:.0f} MB), no L2 flush; "
+                                  "`value` is one forward at a time with an L2 flush in front of each"},
             "gpu_launches": launches * args.steps,
             "kernel_breakdown_ms_per_step": prof["families"],
             "roofline": prof["roofline"](pk),
