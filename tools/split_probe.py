@@ -88,7 +88,7 @@ def main():
         print(f"{name:28s}: median {ms[len(ms) // 2]:.3f} ms  min {ms[0]:.3f}  max {ms[-1]:.3f}  per {B} pairs")
 
 
-def pipelined():
+def pipelined(B=32, depths=(1, 2, 3)):
     """Throughput form: whole batches alternate between two graphs on two streams (consecutive batches overlap)."""
     from common import build_product_hregnet
     from pcd_reg_hregnet_b200 import engine, synth
@@ -97,10 +97,10 @@ def pipelined():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     engine.set_precision("tc")
-    B, N = 32, 16384
+    N = 16384
     src_h, dst_h, _, _ = synth.make_batch(range(1000, 1000 + B), N)
     net = build_product_hregnet(seed=7, device=dev)
-    for depth in (1, 2, 3):
+    for depth in depths:
         regs = []
         for i in range(depth):
             r = Registrar(net, B, N)
@@ -123,12 +123,15 @@ def pipelined():
                     main_s.wait_stream(s)
                 t1.record()
                 torch.cuda.synchronize()
-            print(f"depth {depth}: {K} batches of {B} pairs back to back: {t0.elapsed_time(t1) / K:.3f} ms per batch")
+            print(f"depth {depth}: {K} batches of {B} pairs back to back: {t0.elapsed_time(t1) / K:.3f} ms per batch = "
+                  f"{t0.elapsed_time(t1) / K * 32 / B:.3f} ms per 32 pairs")
         del regs
 
 
 if __name__ == "__main__":
-    if "--pipelined" in sys.argv:
-        pipelined()
+    if "--pipelined" in sys.argv:          # --pipelined [pairs per batch] [depths, comma-separated]
+        i = sys.argv.index("--pipelined")
+        rest = sys.argv[i + 1:]
+        pipelined(int(rest[0]) if rest else 32, tuple(int(x) for x in rest[1].split(",")) if len(rest) > 1 else (1, 2, 3))
         sys.exit(0)
     main()
