@@ -432,8 +432,8 @@ def _profile_families(reg, steps=3):
                 "algorithmic_gflop_per_step": layer_fl / 1e9,
                 # precision == "tc": every useful MAC is three bf16 tensor-core MACs (hi*hi + lo*hi + hi*lo), so the
                 # tensor pipe itself runs at 3x `frac`; 1/3 is the ceiling of `frac` for this arithmetic
-                "tensor_macs_per_useful_mac": 3 if engine.precision() == "tc" else 0,
-                "frac_of_tensor_pipe_issued": (3 * ach / pk["bf16_tflops_sustained"]) if engine.precision() == "tc" else None}
+                "tensor_macs_per_useful_mac": 3 if engine.get_precision() == "tc" else 0,
+                "frac_of_tensor_pipe_issued": (3 * ach / pk["bf16_tflops_sustained"]) if engine.get_precision() == "tc" else None}
 
     def kernel_rooflines(pk, sm_mhz):
         """The sampling and neighbour-search families against the FP32 issue rate of the chip at the measured clock
