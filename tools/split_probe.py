@@ -72,8 +72,21 @@ def main():
         for s in streams:
             main_s.wait_stream(s)
 
+    def run_staggered(delay_ms):
+        def fn():
+            for i, (s, r) in enumerate(zip(streams, parts)):
+                s.wait_stream(main_s)
+                with torch.cuda.stream(s):
+                    if i and delay_ms > 0:
+                        torch.cuda._sleep(int(i * delay_ms * 1.965e6))       # one spinning thread: part i starts late
+                    r.run_device()
+            for s in streams:
+                main_s.wait_stream(s)
+        return fn
+
+    stag = [("%d graphs, staggered %.1f ms" % (P, d), run_staggered(d)) for d in (0.4, 0.8, 1.0, 1.3, 1.7, 2.2)]
     for name, fn in (("one graph, %d pairs" % B, run_whole), ("%d graphs, one stream" % P, run_serial),
-                     ("%d graphs, %d streams" % (P, P), run_parallel), ("one graph again", run_whole)):
+                     ("%d graphs, %d streams" % (P, P), run_parallel), *stag, ("one graph again", run_whole)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
