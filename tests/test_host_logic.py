@@ -112,3 +112,35 @@ def test_module_signatures_match_reference_api():
     for n in ("furthest_point_sampling_wrapper", "weighted_furthest_point_sampling_wrapper", "gather_points_wrapper",
               "gather_points_grad_wrapper"):
         assert hasattr(ops.point_utils_cuda, n)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly ONE JSON line on stdout with the
+    contract's keys, exit 0, no GPU needed.  Tiny sample so that it runs in seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--points", "1024",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_refuses_to_run_without_a_gpu():
+    """Our own arm has no CPU fallback: without a CUDA device it fails loudly instead of printing a number."""
+    import subprocess
+    import sys
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode != 0 and p.stdout.strip() == ""
+    assert "needs a CUDA device" in p.stderr
