@@ -160,3 +160,23 @@ def test_registrar_map_equals_call(net, precision, in_flight):
     assert len(reg._pipe["lanes"]) == in_flight
     assert not torch.equal(want[0][0], want[1][0])                   # the batches really differ
     assert [tuple(x.clone() for x in rt) for rt in reg.map(batches[:1])][0][0].equal(want[0][0])   # fewer batches than lanes
+
+
+def test_registrar_two_forwards_in_flight_at_full_size(net):
+    """Two forwards really overlap at the BASELINE cloud size (16384 points, multi-millisecond forwards on two
+    streams): every batch's poses equal the one-at-a-time result bit for bit, over repeated passes."""
+    from pcd_reg_hregnet_b200 import engine
+    from pcd_reg_hregnet_b200.runner import Registrar
+    engine.set_precision("tc")
+    B, N = 8, 16384
+    batches = []
+    for s in range(5):
+        src, dst, _, _ = synth.make_batch(range(300 + B * s, 300 + B * (s + 1)), N)
+        batches.append((src.pin_memory(), dst.pin_memory()))
+    reg = Registrar(net, B, N, in_flight=2)
+    want = [tuple(x.clone() for x in reg(s, d)) for s, d in batches]
+    for _ in range(3):
+        got = [tuple(x.clone() for x in rt) for rt in reg.map(batches * 2)]
+        assert len(got) == 2 * len(want)
+        for i, (R1, t1) in enumerate(got):
+            assert torch.equal(want[i % len(want)][0], R1) and torch.equal(want[i % len(want)][1], t1), i
