@@ -267,9 +267,10 @@ def main():
         for k in range(K):
             ln = lanes[k % len(lanes)]
             with torch.cuda.stream(ln["stream"] if ln["stream"] is not None else main_s):
-                ln["reg"].src.copy_(rot[k % n_rot][0], non_blocking=True)
-                ln["reg"].dst.copy_(rot[k % n_rot][1], non_blocking=True)
-                out = ln["reg"].run_device()
+                r = ln["reg"] if ln["reg"] is not None else reg
+                r.src.copy_(rot[k % n_rot][0], non_blocking=True)
+                r.dst.copy_(rot[k % n_rot][1], non_blocking=True)
+                out = r.run_device()
                 if post is not None:
                     post(out)
         for ln in lanes:

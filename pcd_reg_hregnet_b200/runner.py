@@ -18,6 +18,8 @@ sampling kernels are latency-bound with one small cluster per cloud and the shar
 forwards half a step apart use SMs the other leaves idle (6.10 -> 5.55 ms per 32-pair batch on one B200,
 tools/split_probe.py --pipelined).
 """
+import gc
+
 import torch
 
 
@@ -55,9 +57,19 @@ class Registrar:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         if self.use_cuda_graph:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.out = self._forward()
+            # No garbage collection inside the capture: a collected CUDA graph / tensor cycle frees device memory
+            # (cudaFree synchronises with the legacy stream), which invalidates a capture in progress
+            # (cudaErrorStreamCaptureImplicit).  Collect what is pending first, then keep the collector off.
+            gc.collect()
+            was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.out = self._forward()
+            finally:
+                if was_enabled:
+                    gc.enable()
         return self
 
     def run_device(self):
@@ -87,9 +99,11 @@ class Registrar:
             main = torch.cuda.current_stream(self.device)
             lanes = []
             for i in range(self.in_flight if self.use_cuda_graph else 1):   # eager forwards are host-bound: one lane
-                reg = self if i == 0 else Registrar(self.net, self.batch, self.n_points, self.use_cuda_graph,
+                # lane 0 is this object, stored as None: a reference to self here would make a cycle, and a Registrar
+                # that waits for the cycle collector may release its graphs in the middle of somebody's capture
+                reg = None if i == 0 else Registrar(self.net, self.batch, self.n_points, self.use_cuda_graph,
                                                     self._warm, in_flight=1)
-                if reg is not self:
+                if reg is not None:
                     reg.src.copy_(self.src)
                     reg.dst.copy_(self.dst)
                     if self.use_cuda_graph:
@@ -127,7 +141,7 @@ class Registrar:
         for src_host, dst_host in batches:
             lane = lanes[n % len(lanes)]
             run = lane["stream"] if lane["stream"] is not None else main
-            reg = lane["reg"]
+            reg = lane["reg"] if lane["reg"] is not None else self
             with torch.cuda.stream(P["copy"]):
                 P["copy"].wait_event(lane["stage_free"])            # the lane's previous batch has left its staging buffers
                 lane["stage"][0].copy_(src_host, non_blocking=True)

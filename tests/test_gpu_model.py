@@ -180,3 +180,9 @@ def test_registrar_two_forwards_in_flight_at_full_size(net):
         assert len(got) == 2 * len(want)
         for i, (R1, t1) in enumerate(got):
             assert torch.equal(want[i % len(want)][0], R1) and torch.equal(want[i % len(want)][1], t1), i
+    # no reference cycle: dropping the last reference releases the graphs at once, not whenever the cycle collector runs
+    # (a CUDA graph freed in the middle of somebody else's capture invalidates that capture)
+    import weakref
+    alive = weakref.ref(reg)
+    del reg
+    assert alive() is None
