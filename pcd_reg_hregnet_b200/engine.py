@@ -242,6 +242,16 @@ def fps(xyz, M, weights=None):
     return idx
 
 
+def stack_clouds(src, dst):
+    """[src; dst] as one batch of 2B clouds.  When the two already lie back to back in one allocation (the Registrar
+    keeps them that way) this is a view; otherwise a copy (torch.cat)."""
+    if (src.shape == dst.shape and src.dtype == dst.dtype and src.is_contiguous() and dst.is_contiguous()
+            and src.untyped_storage().data_ptr() == dst.untyped_storage().data_ptr()
+            and dst.storage_offset() == src.storage_offset() + src.numel()):
+        return src.as_strided((2 * src.shape[0],) + tuple(src.shape[1:]), src.stride(), src.storage_offset())
+    return torch.cat([src, dst], dim=0)
+
+
 def transpose(x):
     """[B,R,C] -> [B,C,R] contiguous."""
     B, R, C = x.shape

@@ -67,7 +67,7 @@ class HRegNet(nn.Module):
 
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]
-        both = self.feature_extraction.forward_cl(torch.cat([src_points, dst_points], dim=0))
+        both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points))
         S = {k: v[:B] for k, v in both.items()}
         D = {k: v[B:] for k, v in both.items()}
 

@@ -28,8 +28,8 @@ class Registrar:
         self.net = net.eval()
         self.device = next(net.parameters()).device
         self.batch, self.n_points = batch, n_points
-        self.src = torch.zeros(batch, n_points, 3, device=self.device)
-        self.dst = torch.zeros(batch, n_points, 3, device=self.device)
+        both = torch.zeros(2 * batch, n_points, 3, device=self.device)   # back to back: the forward stacks them as a view
+        self.src, self.dst = both[:batch], both[batch:]
         self.R_host = torch.empty(batch, 3, 3).pin_memory()
         self.t_host = torch.empty(batch, 3).pin_memory()
         self.graph = None

@@ -144,3 +144,19 @@ def test_bench_refuses_to_run_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert p.returncode != 0 and p.stdout.strip() == ""
     assert "needs a CUDA device" in p.stderr
+
+
+def test_stack_clouds_is_a_view_when_the_clouds_are_adjacent():
+    from pcd_reg_hregnet_b200 import engine
+    both = torch.arange(2 * 3 * 5 * 3, dtype=torch.float32).reshape(6, 5, 3)
+    src, dst = both[:3], both[3:]
+    st = engine.stack_clouds(src, dst)
+    assert st.data_ptr() == both.data_ptr() and st.shape == both.shape and torch.equal(st, both)
+    # not adjacent / different allocations / swapped order: a copy with the same contents
+    for a, b in ((src.clone(), dst.clone()), (dst, src), (both[:2], both[3:5])):
+        st = engine.stack_clouds(a, b)
+        assert st.data_ptr() not in (a.data_ptr(), b.data_ptr()) and torch.equal(st, torch.cat([a, b]))
+    # a view in the middle of an allocation
+    big = torch.randn(10, 5, 3)
+    st = engine.stack_clouds(big[2:4], big[4:6])
+    assert st.data_ptr() == big[2:].data_ptr() and torch.equal(st, big[2:6])
