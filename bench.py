@@ -195,7 +195,6 @@ def main():
     if args.model in ("v2", "v4"):
         from common import build_product_model_v2, build_product_model_v4
         net = (build_product_model_v2 if args.model == "v2" else build_product_model_v4)(seed=7, device=dev)
-        args.no_graph = True      # FineReg2 draws its batch shuffles from the host RNG every forward (model_v2/layers.py:493)
     else:
         net = build_product_hregnet(seed=7, device=dev)
     reg = Registrar(net, B, N, use_cuda_graph=not args.no_graph)

@@ -34,14 +34,39 @@ class FineReg2(FineReg):
         P["mlpx"] = fold.fold_sequential(self.mlpx)
         return P
 
+    # The two batch shuffles are HOST draws in the reference.  For a forward captured in a CUDA graph they cannot be
+    # drawn inside the forward: draw_permutations() draws them before each replay -- same generator, same order as the
+    # reference (layers.py:493, :497) -- into two device index buffers which the captured forward reads.
+    use_drawn = False       # True only while a Registrar warms up / captures: an eager forward draws for itself
+
+    def _perm_buffers(self, batch, device, create=False):
+        # one pair of buffers per (batch, device), never reallocated: captured graphs hold their addresses
+        if "_perm" not in self.__dict__:
+            self.__dict__["_perm"] = {}
+        key = (int(batch), torch.device(device))
+        if key not in self._perm and create:
+            self._perm[key] = (torch.empty(batch, dtype=torch.int64, device=device),
+                               torch.empty(batch, dtype=torch.int64, device=device))
+        return self._perm.get(key)
+
+    def draw_permutations(self, batch, device):
+        p = self._perm_buffers(batch, device, create=True)
+        p[0].copy_(torch.randperm(batch))
+        p[1].copy_(torch.randperm(batch))
+
     def forward_cl(self, sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig):
         P = self.folded()
         B, N1, _ = sxyz.shape
         cor, w, af = engine.fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, self.k, want_af=True)
         (Wx, bx, act), = P["mlpx"]
         feats = engine.transpose(engine.layer(RowsView(B * N1).add(af), Wx, bx, act).view(B, N1, -1))   # [B,C,N]
-        feats_prime = feats[torch.randperm(feats.size(0))]          # host RNG, reference order (layers.py:493)
-        w_prime = w[torch.randperm(w.size(0))]                      # (layers.py:497)
+        drawn = self._perm_buffers(B, feats.device) if self.use_drawn else None
+        if drawn is not None:                                       # drawn ahead of a captured forward
+            feats_prime = feats.index_select(0, drawn[0])
+            w_prime = w.index_select(0, drawn[1])
+        else:
+            feats_prime = feats[torch.randperm(feats.size(0))]      # host RNG, reference order (layers.py:493)
+            w_prime = w[torch.randperm(w.size(0))]                  # (layers.py:497)
         return cor, w, w_prime, feats, feats_prime
 
     def forward(self, src_xyz, src_feat, dst_xyz, dst_feat, src_weights, dst_weights):
@@ -60,6 +85,15 @@ class Model_V2(nn.Module):
         self.fine_corres_2 = FineReg2(k=8, in_channels=128)
         self.fine_corres_1 = FineReg1(k=8, in_channels=64)
         self.svd_head = WeightedSVDHead()
+
+    def host_prologue(self, batch, device):
+        """What a forward draws from the HOST generator, drawn ahead of it (runner.Registrar calls this before every
+        graph replay): the two batch shuffles of FineReg2."""
+        self.fine_corres_2.draw_permutations(batch, device)
+
+    def bind_host_draws(self, on):
+        """on: forwards read the permutations host_prologue() drew (set while a forward is being captured)."""
+        self.fine_corres_2.use_drawn = bool(on)
 
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]

@@ -41,6 +41,13 @@ class Model_V4(nn.Module):
         self.fine_corres_1 = FineReg1(k=8, in_channels=64)
         self.svd_head = WeightedSVDHead()
 
+    def host_prologue(self, batch, device):
+        """See Model_V2.host_prologue."""
+        self.fine_corres_2.draw_permutations(batch, device)
+
+    def bind_host_draws(self, on):
+        self.fine_corres_2.use_drawn = bool(on)
+
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]
         both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points))

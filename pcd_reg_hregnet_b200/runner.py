@@ -37,7 +37,14 @@ class Registrar:
         self.use_cuda_graph = use_cuda_graph
         self._warm = warmup
         self.in_flight = max(1, int(in_flight))   # forwards map() keeps enqueued at once (each on its own stream)
+        if hasattr(net, "host_prologue"):
+            self.in_flight = 1                    # the buffers the prologue fills belong to the net, not to a lane
         self._pipe = None           # lazily created state of map(): copy stream, staging buffers, result slots
+
+    def _prologue(self):
+        # host-side draws of the forward (Model_V2 / Model_V4: FineReg2's batch shuffles), ahead of a captured forward
+        if self.use_cuda_graph and hasattr(self.net, "host_prologue"):
+            self.net.host_prologue(self.batch, self.device)
 
     def _forward(self):
         with torch.no_grad():
@@ -49,10 +56,22 @@ class Registrar:
 
     def capture(self):
         """Warm up (folds BN, sets kernel attributes, fills the allocator) and capture the forward."""
+        bind = getattr(self.net, "bind_host_draws", None) if self.use_cuda_graph else None
+        if bind is not None:
+            bind(True)
+        try:
+            self._capture()
+        finally:
+            if bind is not None:
+                bind(False)
+        return self
+
+    def _capture(self):
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(self._warm):
+                self._prologue()
                 self.out = self._forward()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
@@ -70,11 +89,11 @@ class Registrar:
             finally:
                 if was_enabled:
                     gc.enable()
-        return self
 
     def run_device(self):
         """Forward on the clouds already resident in self.src / self.dst; returns the device result dict."""
         if self.graph is not None:
+            self._prologue()
             self.graph.replay()
         else:
             self.out = self._forward()

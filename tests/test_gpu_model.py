@@ -186,3 +186,39 @@ def test_registrar_two_forwards_in_flight_at_full_size(net):
     alive = weakref.ref(reg)
     del reg
     assert alive() is None
+
+
+@pytest.mark.parametrize("which", ["v2", "v4"])
+def test_model_v2_v4_through_a_captured_graph(which):
+    """Model_V2 / Model_V4 draw two batch shuffles from the HOST generator every forward (model_v2/layers.py:493,497).
+    Through the Registrar the forward is a CUDA graph: the shuffles are drawn ahead of every replay, with the same
+    generator in the same order, so a replay equals the eager forward under the same seed -- every time."""
+    from common import build_product_model_v2, build_product_model_v4
+    from pcd_reg_hregnet_b200 import engine
+    from pcd_reg_hregnet_b200.runner import Registrar
+    engine.set_precision("tc")
+    net = (build_product_model_v2 if which == "v2" else build_product_model_v4)(seed=7, device=DEV)
+    B, N = 4, 2048
+    src, dst, _, _ = synth.make_batch([61, 62, 63, 64], N)
+    reg = Registrar(net, B, N)
+    assert reg.in_flight == 1                      # the drawn permutations belong to the net: one forward at a time
+    reg.load(src, dst)
+    reg.capture()
+    assert reg.graph is not None
+    keys = ["src_dst_feats_2", "src_dst_feats_2_prime", "src_dst_weights_2", "src_dst_weights_2_prime"]
+    primes = []
+    for seed in (0, 3, 0):                         # seeds 0 and 3 differ in both draws of randperm(4)
+        with torch.no_grad():
+            torch.manual_seed(seed)
+            want = net(src.to(DEV), dst.to(DEV))                       # eager: draws inside the forward
+            want = {k: want[k].clone() for k in keys} | {"R": want["rotation"][-1].clone()}
+            torch.manual_seed(seed)
+            out = reg.run_device()
+        for k in keys:
+            assert torch.equal(out[k], want[k]), (seed, k)
+        assert torch.equal(out["rotation"][-1], want["R"])
+        primes.append(out["src_dst_weights_2_prime"].clone())
+    assert torch.equal(primes[0], primes[2]) and not torch.equal(primes[0], primes[1])   # the draws really change
+    # the pipelined public API works for these models too (single lane)
+    got = [tuple(x.clone() for x in rt) for rt in reg.map([(src.pin_memory(), dst.pin_memory())] * 3)]
+    assert all(torch.equal(got[0][0], g[0]) for g in got)
