@@ -4,6 +4,7 @@ oracle/ref_harness.py (native ops = oracle C restatements).  Run in the build co
     python tests/golden/make_golden.py            # model fixtures
     python tests/golden/make_golden.py metrics    # pose_metrics.npz only
     python tests/golden/make_golden.py preprocess # preprocess.npz only
+    python tests/golden/make_golden.py variants   # model_v2_b2_n2048.npz, model_v4_b2_n2048.npz only
 
 Fixtures
   preprocess.npz           two raw clouds through the reference's range filter + fixed-size resampler (pad and
@@ -16,6 +17,10 @@ Fixtures
   hregnet_b2_n2048.npz     HRegNet.forward (models/HRegNet/models.py:77-148) on 2 seeded synthetic pairs of 2048
                            points: inputs, every returned tensor, the per-level FPS indices and the coarse kNN idx.
   hregnet_uniform_b1_n1500.npz  same on the reference's own smoke-test distribution torch.rand (models.py:168-169).
+  model_v2_b2_n2048.npz    Model_V2.forward (models/model_v2/models.py:77-183) after torch.manual_seed(0) (its two batch
+                           shuffles come from the host generator) on 2 seeded pairs of 2048 points: inputs, poses,
+                           correspondences, weights, the FineReg2 features and both *_prime shuffles.
+  model_v4_b2_n2048.npz    Model_V4.forward (models/model_v4/models.py:60-183) likewise, plus coord_dist / feats_dist.
 Registration-head weights are not in the reference repo (.MISSING_LARGE_BLOBS): they are torch.manual_seed(7)
 default initialisations + randomised BatchNorm statistics, re-created identically by tests/common.py.
 """
@@ -135,7 +140,33 @@ def preprocess_golden():
     print("preprocess.npz written")
 
 
+def variants_golden():
+    """Model_V2 / Model_V4 of the UNMODIFIED reference on CPU (seeded like tests/common.build_product_model_v2 / _v4)."""
+    from common import Args
+    ns = H.load_reference()
+    for name, cls, seeds in (("model_v2_b2_n2048", ns.Model_V2, [41, 42]), ("model_v4_b2_n2048", ns.Model_V4, [44, 45])):
+        assert cls is not None
+        torch.manual_seed(7)
+        ref = cls(Args())
+        ref.feature_extraction.load_state_dict(torch.load(H.pretrained_feats_path(), map_location="cpu"))
+        g = torch.Generator().manual_seed(8)
+        for part in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
+            H.randomize_bn_(getattr(ref, part), g)
+        ref.eval()
+        src, dst, _, _ = synth.make_batch(seeds, 2048)
+        with torch.no_grad():
+            torch.manual_seed(0)
+            out = ref(src, dst)
+        d = {k: v for k, v in flat(out).items() if not k.startswith(("src_feats.", "dst_feats."))}
+        d["src"], d["dst"] = src.numpy(), dst.numpy()
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, sorted(d.keys()), sum(v.nbytes for v in d.values()) / 1e6, "MB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variants_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         pose_metrics_golden()
         sys.exit(0)

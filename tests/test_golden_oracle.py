@@ -55,3 +55,30 @@ def test_preprocess_oracle_reproduces_reference_outputs():
         rp, ri = RP.resample(fp, fi, 4096, g[f"{n}_idx"])
         assert np.array_equal(rp, g[f"{n}_resampled"]) and np.array_equal(ri, g[f"{n}_resampled_int"])
     assert np.abs(RP.se3_exp(g["twist"]) - g["se3_exp"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("which", ["v2", "v4"])
+def test_oracle_reproduces_golden_model_variants(which):
+    """oracle/ref_layers.model_v2_forward / model_v4_forward against the committed outputs of the UNMODIFIED reference
+    classes (tests/golden/model_v{2,4}_b2_n2048.npz, made by make_golden.py variants) -- the pin of the oracle for these
+    two models that travels to boxes without /root/reference.  torch.manual_seed(0) reproduces the host-generator
+    batch shuffles of FineReg2 (model_v2/layers.py:493,497)."""
+    from common import build_product_model_v2, build_product_model_v4
+    torch.set_num_threads(8)
+    gd = load_golden(f"model_{which}_b2_n2048")
+    sd = (build_product_model_v2 if which == "v2" else build_product_model_v4)(seed=7).state_dict()
+    with torch.no_grad():
+        torch.manual_seed(0)
+        out = (RL.model_v2_forward if which == "v2" else RL.model_v4_forward)(sd, gd["src"], gd["dst"])
+    for i in range(3):
+        assert float(RL.rotation_angle_deg(out["rotation"][i], gd[f"rotation.{i}"]).max()) < 1e-4
+        assert float((out["translation"][i] - gd[f"translation.{i}"]).abs().max()) < 1e-5
+    for k in ("src_dst_feats_2", "src_dst_feats_2_prime", "src_dst_weights_2", "src_dst_weights_2_prime",
+              "src_xyz_2_trans", "dst_xyz_2", "src_feats_desc_2", "src_feats_sigmas_2"):
+        assert float((out[k] - gd[k]).abs().max()) < 2e-5 * max(1.0, float(gd[k].abs().max())), k
+    if which == "v2":
+        for lv in (3, 2, 1):
+            assert float((out[f"src_xyz_corres_{lv}"] - gd[f"src_xyz_corres_{lv}"]).abs().max()) < 1e-4
+    else:
+        assert float((out["coord_dist"] - gd["coord_dist"]).abs().max()) < 1e-5 * max(1.0, float(gd["coord_dist"].abs().max()))
+        assert float((out["feats_dist"] - gd["feats_dist"]).abs().max()) < 1e-5
