@@ -222,3 +222,38 @@ def test_model_v2_v4_through_a_captured_graph(which):
     # the pipelined public API works for these models too (single lane)
     got = [tuple(x.clone() for x in rt) for rt in reg.map([(src.pin_memory(), dst.pin_memory())] * 3)]
     assert all(torch.equal(got[0][0], g[0]) for g in got)
+
+
+@pytest.mark.parametrize("which", ["v2", "v4"])
+def test_golden_end_to_end_model_variants(which, precision):
+    """Free-running Model_V2 / Model_V4 against the committed outputs of the unmodified reference classes.  As for
+    HRegNet, a pair whose weighted-FPS picks flipped on a sub-ulp sigma difference is skipped; the others must meet
+    the feature / pose gates, and when no pair flipped the host-generator shuffles must match too."""
+    from common import build_product_model_v2, build_product_model_v4
+    gd = load_golden(f"model_{which}_b2_n2048")
+    gpu = (build_product_model_v2 if which == "v2" else build_product_model_v4)(seed=7, device=DEV)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        out = gpu(gd["src"].to(DEV), gd["dst"].to(DEV))
+    B = gd["src"].shape[0]
+    if which == "v2":       # level 1 involves no learned weights before FPS / kNN: it must agree regardless of chaos
+        cpu_sd = {k: v.cpu() for k, v in gpu.state_dict().items()}
+        with torch.no_grad():
+            want1 = RL.hier_feature_extraction(cpu_sd, "feature_extraction.", gd["src"], levels=RL.LEVELS[:1])
+        assert rel_err(out["src_feats"]["xyz_1"].cpu(), want1["xyz_1"]) < 1e-4
+        assert rel_err(out["src_feats"]["desc_1"].cpu(), want1["desc_1"]) < 1e-3
+    ok = [b for b in range(B) if rel_err(out["dst_xyz_2"][b].cpu(), gd["dst_xyz_2"][b]) < 1e-4
+          and rel_err(out["src_feats_sigmas_2"][b].cpu(), gd["src_feats_sigmas_2"][b]) < 1e-3]
+    for b in ok:
+        assert rel_err(out["src_feats_desc_2"][b].cpu(), gd["src_feats_desc_2"][b]) < 1e-3
+        if rel_err(out["src_xyz_2_trans"][b].cpu(), gd["src_xyz_2_trans"][b]) > 1e-4:
+            continue                                   # level 3 flipped: the coarse pose differs legitimately
+        assert rel_err(out["src_dst_feats_2"][b].cpu(), gd["src_dst_feats_2"][b]) < 1e-3
+        assert float((out["src_dst_weights_2"][b].cpu() - gd["src_dst_weights_2"][b]).abs().max()) < 1e-3
+    if len(ok) == B and rel_err(out["src_xyz_2_trans"].cpu(), gd["src_xyz_2_trans"]) < 1e-4:
+        assert rel_err(out["src_dst_feats_2_prime"].cpu(), gd["src_dst_feats_2_prime"]) < 1e-3
+        assert float((out["src_dst_weights_2_prime"].cpu() - gd["src_dst_weights_2_prime"]).abs().max()) < 1e-3
+        if which == "v4":
+            assert rel_err(out["coord_dist"].cpu(), gd["coord_dist"]) < 1e-3
+            assert float((out["feats_dist"].cpu() - gd["feats_dist"]).abs().max()) < 1e-3
+    print(f"model_{which}: {len(ok)}/{B} pairs had identical level-2 keypoint sets")
