@@ -37,20 +37,21 @@ class FineReg2(FineReg):
     # The two batch shuffles are HOST draws in the reference.  For a forward captured in a CUDA graph they cannot be
     # drawn inside the forward: draw_permutations() draws them before each replay -- same generator, same order as the
     # reference (layers.py:493, :497) -- into two device index buffers which the captured forward reads.
-    use_drawn = False       # True only while a Registrar warms up / captures: an eager forward draws for itself
+    drawn_slot = None       # set only while a Registrar warms up / captures a forward: an eager forward draws for itself
 
-    def _perm_buffers(self, batch, device, create=False):
-        # one pair of buffers per (batch, device), never reallocated: captured graphs hold their addresses
+    def _perm_buffers(self, batch, device, slot, create=False):
+        # one pair of buffers per (batch, device, slot), never reallocated: captured graphs hold their addresses
+        # (slot = which of a Registrar's captures of this net reads them; forwards in flight must not share a pair)
         if "_perm" not in self.__dict__:
             self.__dict__["_perm"] = {}
-        key = (int(batch), torch.device(device))
+        key = (int(batch), torch.device(device), int(slot))
         if key not in self._perm and create:
             self._perm[key] = (torch.empty(batch, dtype=torch.int64, device=device),
                                torch.empty(batch, dtype=torch.int64, device=device))
         return self._perm.get(key)
 
-    def draw_permutations(self, batch, device):
-        p = self._perm_buffers(batch, device, create=True)
+    def draw_permutations(self, batch, device, slot=0):
+        p = self._perm_buffers(batch, device, slot, create=True)
         p[0].copy_(torch.randperm(batch))
         p[1].copy_(torch.randperm(batch))
 
@@ -60,7 +61,7 @@ class FineReg2(FineReg):
         cor, w, af = engine.fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, self.k, want_af=True)
         (Wx, bx, act), = P["mlpx"]
         feats = engine.transpose(engine.layer(RowsView(B * N1).add(af), Wx, bx, act).view(B, N1, -1))   # [B,C,N]
-        drawn = self._perm_buffers(B, feats.device) if self.use_drawn else None
+        drawn = self._perm_buffers(B, feats.device, self.drawn_slot) if self.drawn_slot is not None else None
         if drawn is not None:                                       # drawn ahead of a captured forward
             feats_prime = feats.index_select(0, drawn[0])
             w_prime = w.index_select(0, drawn[1])
@@ -86,14 +87,15 @@ class Model_V2(nn.Module):
         self.fine_corres_1 = FineReg1(k=8, in_channels=64)
         self.svd_head = WeightedSVDHead()
 
-    def host_prologue(self, batch, device):
+    def host_prologue(self, batch, device, slot=0):
         """What a forward draws from the HOST generator, drawn ahead of it (runner.Registrar calls this before every
-        graph replay): the two batch shuffles of FineReg2."""
-        self.fine_corres_2.draw_permutations(batch, device)
+        graph replay, with the slot of the capture it is about to replay): the two batch shuffles of FineReg2."""
+        self.fine_corres_2.draw_permutations(batch, device, slot)
 
-    def bind_host_draws(self, on):
-        """on: forwards read the permutations host_prologue() drew (set while a forward is being captured)."""
-        self.fine_corres_2.use_drawn = bool(on)
+    def bind_host_draws(self, slot):
+        """slot (int): forwards read the permutations host_prologue(..., slot) drew -- set while a forward is being
+        captured; None: forwards draw for themselves."""
+        self.fine_corres_2.drawn_slot = slot
 
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]

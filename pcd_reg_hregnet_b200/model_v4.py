@@ -41,12 +41,12 @@ class Model_V4(nn.Module):
         self.fine_corres_1 = FineReg1(k=8, in_channels=64)
         self.svd_head = WeightedSVDHead()
 
-    def host_prologue(self, batch, device):
+    def host_prologue(self, batch, device, slot=0):
         """See Model_V2.host_prologue."""
-        self.fine_corres_2.draw_permutations(batch, device)
+        self.fine_corres_2.draw_permutations(batch, device, slot)
 
-    def bind_host_draws(self, on):
-        self.fine_corres_2.use_drawn = bool(on)
+    def bind_host_draws(self, slot):
+        self.fine_corres_2.drawn_slot = slot
 
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]

@@ -24,7 +24,7 @@ import torch
 
 
 class Registrar:
-    def __init__(self, net, batch, n_points, use_cuda_graph=True, warmup=2, in_flight=2):
+    def __init__(self, net, batch, n_points, use_cuda_graph=True, warmup=2, in_flight=2, slot=0):
         self.net = net.eval()
         self.device = next(net.parameters()).device
         self.batch, self.n_points = batch, n_points
@@ -37,14 +37,13 @@ class Registrar:
         self.use_cuda_graph = use_cuda_graph
         self._warm = warmup
         self.in_flight = max(1, int(in_flight))   # forwards map() keeps enqueued at once (each on its own stream)
-        if hasattr(net, "host_prologue"):
-            self.in_flight = 1                    # the buffers the prologue fills belong to the net, not to a lane
+        self._slot = slot                         # which capture of `net` this is (lanes of map(): 0, 1, ...)
         self._pipe = None           # lazily created state of map(): copy stream, staging buffers, result slots
 
     def _prologue(self):
         # host-side draws of the forward (Model_V2 / Model_V4: FineReg2's batch shuffles), ahead of a captured forward
         if self.use_cuda_graph and hasattr(self.net, "host_prologue"):
-            self.net.host_prologue(self.batch, self.device)
+            self.net.host_prologue(self.batch, self.device, self._slot)
 
     def _forward(self):
         with torch.no_grad():
@@ -58,12 +57,12 @@ class Registrar:
         """Warm up (folds BN, sets kernel attributes, fills the allocator) and capture the forward."""
         bind = getattr(self.net, "bind_host_draws", None) if self.use_cuda_graph else None
         if bind is not None:
-            bind(True)
+            bind(self._slot)
         try:
             self._capture()
         finally:
             if bind is not None:
-                bind(False)
+                bind(None)
         return self
 
     def _capture(self):
@@ -121,7 +120,7 @@ class Registrar:
                 # lane 0 is this object, stored as None: a reference to self here would make a cycle, and a Registrar
                 # that waits for the cycle collector may release its graphs in the middle of somebody's capture
                 reg = None if i == 0 else Registrar(self.net, self.batch, self.n_points, self.use_cuda_graph,
-                                                    self._warm, in_flight=1)
+                                                    self._warm, in_flight=1, slot=self._slot + i)
                 if reg is not None:
                     reg.src.copy_(self.src)
                     reg.dst.copy_(self.dst)

@@ -201,7 +201,6 @@ def test_model_v2_v4_through_a_captured_graph(which):
     B, N = 4, 2048
     src, dst, _, _ = synth.make_batch([61, 62, 63, 64], N)
     reg = Registrar(net, B, N)
-    assert reg.in_flight == 1                      # the drawn permutations belong to the net: one forward at a time
     reg.load(src, dst)
     reg.capture()
     assert reg.graph is not None
@@ -219,9 +218,20 @@ def test_model_v2_v4_through_a_captured_graph(which):
         assert torch.equal(out["rotation"][-1], want["R"])
         primes.append(out["src_dst_weights_2_prime"].clone())
     assert torch.equal(primes[0], primes[2]) and not torch.equal(primes[0], primes[1])   # the draws really change
-    # the pipelined public API works for these models too (single lane)
-    got = [tuple(x.clone() for x in rt) for rt in reg.map([(src.pin_memory(), dst.pin_memory())] * 3)]
-    assert all(torch.equal(got[0][0], g[0]) for g in got)
+    # the pipelined public API works for these models too: two forwards in flight, each capture with its own pair of
+    # permutation buffers (slot), drawn in batch order
+    want_R = out["rotation"][-1].cpu()
+    got = [tuple(x.clone() for x in rt) for rt in reg.map([(src.pin_memory(), dst.pin_memory())] * 5)]
+    assert len(reg._pipe["lanes"]) == 2 and all(torch.equal(want_R, g[0]) for g in got)
+    lane1 = reg._pipe["lanes"][1]["reg"]
+    torch.manual_seed(3)
+    reg.run_device()                                                   # slot 0 draws first ...
+    o1 = lane1.run_device()                                            # ... then slot 1: the generator's next two draws
+    torch.manual_seed(3)
+    torch.randperm(B); torch.randperm(B)
+    p_f, p_w = torch.randperm(B), torch.randperm(B)
+    assert torch.equal(o1["src_dst_weights_2_prime"], o1["src_dst_weights_2"][p_w.to(DEV)])
+    assert torch.equal(o1["src_dst_feats_2_prime"], o1["src_dst_feats_2"][p_f.to(DEV)])
 
 
 @pytest.mark.parametrize("which", ["v2", "v4"])
