@@ -24,6 +24,13 @@ import torch
 
 
 class Registrar:
+    """net: HRegNet / Model_V2 / Model_V4 of this package on a CUDA device (eval mode is forced).
+    batch, n_points: the fixed shape [batch, n_points, 3] of both clouds of a call.
+    use_cuda_graph: capture the forward once and replay it (False: eager launches, one forward at a time).
+    warmup: eager forwards before the capture.  in_flight: forwards map() keeps enqueued at once (captures of the
+    forward, each replayed on its own stream; 1 = single stream).  slot: which capture of `net` this object is -- the
+    lanes of map() number themselves; nets that draw from the host generator keep one set of buffers per slot."""
+
     def __init__(self, net, batch, n_points, use_cuda_graph=True, warmup=2, in_flight=2, slot=0):
         self.net = net.eval()
         self.device = next(net.parameters()).device
