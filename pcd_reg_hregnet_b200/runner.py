@@ -163,36 +163,38 @@ class Registrar:
                 lane["stream"].wait_stream(main)
         pending = []
         n = 0
-        for src_host, dst_host in batches:
-            lane = lanes[n % len(lanes)]
-            run = lane["stream"] if lane["stream"] is not None else main
-            reg = lane["reg"] if lane["reg"] is not None else self
-            with torch.cuda.stream(P["copy"]):
-                P["copy"].wait_event(lane["stage_free"])            # the lane's previous batch has left its staging buffers
-                lane["stage"][0].copy_(src_host, non_blocking=True)
-                lane["stage"][1].copy_(dst_host, non_blocking=True)
-                lane["staged"].record(P["copy"])
-            with torch.cuda.stream(run):
-                run.wait_event(lane["staged"])
-                reg.src.copy_(lane["stage"][0], non_blocking=True)
-                reg.dst.copy_(lane["stage"][1], non_blocking=True)
-                lane["stage_free"].record(run)
-                out = reg.run_device()
-                if post is not None:
-                    post(out)
-                R_h, t_h, done = slots[n % len(slots)]
-                R_h.copy_(out["rotation"][-1], non_blocking=True)
-                t_h.copy_(out["translation"][-1], non_blocking=True)
-                done.record(run)
-            pending.append((R_h, t_h, done))
-            n += 1
-            if len(pending) > len(lanes):
-                R_h, t_h, done = pending.pop(0)
-                done.synchronize()
-                yield R_h, t_h
-        for lane in lanes:
-            if lane["stream"] is not None:
-                main.wait_stream(lane["stream"])
+        try:
+            for src_host, dst_host in batches:
+                lane = lanes[n % len(lanes)]
+                run = lane["stream"] if lane["stream"] is not None else main
+                reg = lane["reg"] if lane["reg"] is not None else self
+                with torch.cuda.stream(P["copy"]):
+                    P["copy"].wait_event(lane["stage_free"])            # the lane's previous batch has left its staging buffers
+                    lane["stage"][0].copy_(src_host, non_blocking=True)
+                    lane["stage"][1].copy_(dst_host, non_blocking=True)
+                    lane["staged"].record(P["copy"])
+                with torch.cuda.stream(run):
+                    run.wait_event(lane["staged"])
+                    reg.src.copy_(lane["stage"][0], non_blocking=True)
+                    reg.dst.copy_(lane["stage"][1], non_blocking=True)
+                    lane["stage_free"].record(run)
+                    out = reg.run_device()
+                    if post is not None:
+                        post(out)
+                    R_h, t_h, done = slots[n % len(slots)]
+                    R_h.copy_(out["rotation"][-1], non_blocking=True)
+                    t_h.copy_(out["translation"][-1], non_blocking=True)
+                    done.record(run)
+                pending.append((R_h, t_h, done))
+                n += 1
+                if len(pending) > len(lanes):
+                    R_h, t_h, done = pending.pop(0)
+                    done.synchronize()
+                    yield R_h, t_h
+        finally:                                   # also when the caller abandons the generator early
+            for lane in lanes:
+                if lane["stream"] is not None:
+                    main.wait_stream(lane["stream"])
         for R_h, t_h, done in pending:
             done.synchronize()
             yield R_h, t_h

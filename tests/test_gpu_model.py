@@ -160,6 +160,13 @@ def test_registrar_map_equals_call(net, precision, in_flight):
     assert len(reg._pipe["lanes"]) == in_flight
     assert not torch.equal(want[0][0], want[1][0])                   # the batches really differ
     assert [tuple(x.clone() for x in rt) for rt in reg.map(batches[:1])][0][0].equal(want[0][0])   # fewer batches than lanes
+    # a caller that abandons the generator early: the lanes are joined, the next map() starts clean
+    it = reg.map(batches)
+    first = next(it)
+    assert torch.equal(first[0], want[0][0])
+    it.close()
+    got = [tuple(x.clone() for x in rt) for rt in reg.map(batches[:3])]
+    assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(want, got))
 
 
 def test_registrar_two_forwards_in_flight_at_full_size(net):
