@@ -28,16 +28,32 @@ def _worker(rank, world, port, n_pairs, q):
     dist.destroy_process_group()
 
 
-def _run(n_pairs, world=2):
+def _run_once(n_pairs, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     ps = [ctx.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
     [p.start() for p in ps]
-    res = [q.get(timeout=120) for _ in range(world)]
-    [p.join(60) for p in ps]
-    assert all(p.exitcode == 0 for p in ps)
+    try:
+        res = [q.get(timeout=120) for _ in range(world)]
+        [p.join(60) for p in ps]
+    finally:
+        for p in ps:
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in ps), [p.exitcode for p in ps]
     return res
+
+
+def _run(n_pairs, world=2, attempts=3):
+    """The rendezvous port is picked by binding port 0 and releasing it, and gloo's store teardown can race between
+    the ranks: neither is what this test is about, so a failed launch is retried; the results are never relaxed."""
+    for a in range(attempts):
+        try:
+            return _run_once(n_pairs, world)
+        except Exception:                                              # noqa: BLE001 -- queue.Empty, AssertionError
+            if a == attempts - 1:
+                raise
 
 
 def test_shard_ranges_cover_everything():
