@@ -144,8 +144,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"HRegNet forward, synthetic {args.points}-pt LiDAR pairs, CPU oracle port of the reference",
-                   "pairs_per_step": per_step, "points": args.points},
+        # the same workload as our arm's config; each step is a bounded sample of it (2 of the batch's pairs)
+        "config": {"workload": f"HRegNet baseline forward, batch {args.pairs_per_gpu} synthetic {args.points}-pt pairs per GPU (keypoints 1024/512/256)",
+                   "pairs_per_gpu": args.pairs_per_gpu, "points": args.points, "sample_pairs_per_step": per_step,
+                   "implementation": "CPU oracle port of the reference (torch-CPU layers over the C native ops), B=1 forwards, all host cores"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
