@@ -34,6 +34,8 @@ class Registrar:
     def __init__(self, net, batch, n_points, use_cuda_graph=True, warmup=2, in_flight=2, slot=0):
         self.net = net.eval()
         self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("Registrar needs the net on a CUDA device: there is no CPU path (move it with .cuda())")
         self.batch, self.n_points = batch, n_points
         both = torch.zeros(2 * batch, n_points, 3, device=self.device)   # back to back: the forward stacks them as a view
         self.src, self.dst = both[:batch], both[batch:]

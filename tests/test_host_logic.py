@@ -160,3 +160,9 @@ def test_stack_clouds_is_a_view_when_the_clouds_are_adjacent():
     big = torch.randn(10, 5, 3)
     st = engine.stack_clouds(big[2:4], big[4:6])
     assert st.data_ptr() == big[2:].data_ptr() and torch.equal(st, big[2:6])
+
+
+def test_registrar_refuses_a_cpu_net():
+    from pcd_reg_hregnet_b200.runner import Registrar
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        Registrar(build_product_hregnet(seed=7), batch=2, n_points=1024)
