@@ -69,9 +69,10 @@ def knn_group(xyz1, xyz2, features2, k):
     return torch.cat(parts, dim=-1).permute(0, 3, 1, 2).contiguous(), nn
 
 
-def keypoint_detector(sd, p, xyz, features, weights, nsample, k):
-    """-> keypoints [B,M,3], sigmas [B,M], attentive_feature [B,C,M], grouped [B,4+C,M,k], afm [B,C,M,k], fps_idx"""
-    fps_idx = native.fps(xyz, nsample, weights)
+def keypoint_detector(sd, p, xyz, features, weights, nsample, k, sample_idx=None):
+    """-> keypoints [B,M,3], sigmas [B,M], attentive_feature [B,C,M], grouped [B,4+C,M,k], afm [B,C,M,k], fps_idx
+    sample_idx [B,M]: the fps=False branch (layers.py:144-147) -- the caller draws torch.randperm(N)[:nsample]."""
+    fps_idx = native.fps(xyz, nsample, weights) if sample_idx is None else sample_idx
     B = xyz.shape[0]
     sampled = xyz[torch.arange(B)[:, None], fps_idx.long()]
     grouped, nn = knn_group(sampled, xyz, features, k)

@@ -99,20 +99,45 @@ def check(code: int, what: str):
         raise HrnError(f"{what} failed: {msg} ({code})")
 
 
+_pending_dev = None      # device of the tensors whose pointers were taken for the next call()
+
+
 def ptr(t):
-    """Device pointer of a contiguous CUDA tensor (or None)."""
+    """Device pointer of a contiguous CUDA tensor (or None).  Remembers the tensor's device for the launch: call()
+    runs the kernel on THAT device and on its current stream, whatever the process-wide current device is."""
+    global _pending_dev
     if t is None:
         return None
     if not t.is_cuda:
         raise HrnError("hregnet_b200 kernels need CUDA tensors (no CPU fallback)")
     if not t.is_contiguous():
         raise HrnError("tensor must be contiguous")
+    d = t.device.index
+    _pending_dev = d if _pending_dev in (None, d) else -1          # -1: mixed devices, refused by call()
     return t.data_ptr()
 
 
+class _CurrentStream:
+    """Placeholder argument: call() replaces it by the current stream of the device the launch goes to."""
+
+
+_CUR = _CurrentStream()
+
+
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    return _CUR
 
 
 def call(name, *args):
-    check(getattr(lib(), name)(*args), name)
+    global _pending_dev
+    dev, _pending_dev = _pending_dev, None
+    if dev == -1:
+        raise HrnError(f"{name}: the tensors of one kernel launch live on different devices")
+    f = getattr(lib(), name)
+    if dev is None or dev == torch.cuda.current_device():
+        st = torch.cuda.current_stream().cuda_stream
+        check(f(*[st if a is _CUR else a for a in args]), name)
+        return
+    with torch.cuda.device(dev):      # a net on cuda:1 while cuda:0 is current: launch where the data lives
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(f(*[st if a is _CUR else a for a in args]), name)

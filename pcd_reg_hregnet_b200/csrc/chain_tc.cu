@@ -587,15 +587,14 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
         AW.acc_stride = narrow ? 128 : 256;
         AW.nbuf = 512 / AW.acc_stride;
         const int smem_ws = fixed + ring * A.slot_bytes + (use_tile ? CW_TILE_BYTES : 0);
-        static bool attr_ws = false;
-        if (!attr_ws) {
+        static hrn_once_per_device attr_ws;
+        if (attr_ws.need()) {
             HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            attr_ws = true;
         }
         const int grid_ws = AW.n_tiles < 148 ? AW.n_tiles : 148;
         if (narrow) {

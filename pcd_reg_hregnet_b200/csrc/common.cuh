@@ -22,6 +22,18 @@
         if (e__ != cudaSuccess) return (int)e__;             \
     } while (0)
 
+// cudaFuncSetAttribute is PER DEVICE: a call site that raises a kernel's dynamic shared-memory limit must do so once on
+// every device the process launches on (one process may drive several GPUs), not once per process.
+struct hrn_once_per_device {
+    unsigned long long mask = 0;
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 63) return true;
+        const unsigned long long bit = 1ull << d;
+        return (__atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED) & bit) == 0;
+    }
+};
+
 static inline int hrn_divup(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Order-preserving map float -> uint32 (a < b  <=>  ord(a) < ord(b) for non-NaN a, b).

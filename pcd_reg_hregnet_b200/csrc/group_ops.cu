@@ -147,20 +147,25 @@ __global__ void group_geometry_kernel(const float* __restrict__ q, const float* 
     if (nn) { nn[r * 3 + 0] = x; nn[r * 3 + 1] = y; nn[r * 3 + 2] = z; }
 }
 
-// w[b,:] = (1/(sigma+1e-5)) / mean_m(1/(sigma+1e-5));  one CTA per cloud
+// w[b,:] = (1/(sigma+1e-5)) / mean_m(1/(sigma+1e-5));  one CTA per cloud (reference models.py:30-32).
+// The mean is accumulated in fp64 and rounded once, i.e. it is the correctly rounded fp32 mean of the fp32 terms --
+// independent of any summation order.  torch.mean (the reference) sums in fp32 with its own vectorised order and can
+// differ from that value by an ulp; a 1-ulp difference of the weights can flip a weighted-FPS pick downstream, which is
+// why the index gates are applied teacher-forced.
 __global__ void __launch_bounds__(256)
 sigma_to_weights_kernel(const float* __restrict__ sigma, float* __restrict__ w, int M) {
-    __shared__ float s_part[8];
+    __shared__ double s_part[8];
     const float* s = sigma + (size_t)blockIdx.x * M;
     float* o = w + (size_t)blockIdx.x * M;
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < M; i += blockDim.x) acc += 1.0f / (s[i] + 1e-5f);
-    acc = hrn_warp_sum(acc);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) acc += (double)(1.0f / (s[i] + 1e-5f));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
     __syncthreads();
-    float tot = 0.f;
+    double tot = 0.0;
     for (int i = 0; i < 8; ++i) tot += s_part[i];
-    const float mean = tot / (float)M;
+    const float mean = (float)(tot / (double)M);
     for (int i = threadIdx.x; i < M; i += blockDim.x) o[i] = (1.0f / (s[i] + 1e-5f)) / mean;
 }
 
@@ -209,10 +214,9 @@ HRN_API int hrn_group_attend(const float* E, int ldE, int C, long long groups, i
     const size_t smem = (size_t)k * C * sizeof(float);
     if (smem > 96 * 1024) return HRN_ERR_UNSUPPORTED;
     if (groups == 0) return HRN_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static hrn_once_per_device attr_set;
+    if (attr_set.need()) {
         HRN_CUDA(cudaFuncSetAttribute(group_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
     }
     group_attend_kernel<<<(unsigned)groups, 128, smem, (cudaStream_t)stream>>>(E, ldE, C, k, a, af, ldaf, xyz, idx,
                                                                               groups_per_batch, N, cor);

@@ -62,6 +62,7 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
     }
     if (!qvalid) return;
     top.sort_set(lane);
+    top.sanitize(N);
     const size_t base = ((size_t)b * M + m) * K;
     top.for_each_sorted(K, lane, [&](int pos, float d, int i) {
         if (out_d) out_d[base + pos] = d;
@@ -169,6 +170,7 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         if (m >= M) continue;
         const size_t base = ((size_t)b * M + m) * K;
         top[q].sort_set(lane);
+        top[q].sanitize(N);
         top[q].for_each_sorted(K, lane, [&](int pos, float d, int i) {
             if (out_d) out_d[base + pos] = d;
             if (out_i64) out_i64[base + pos] = (int64_t)i;

@@ -97,6 +97,19 @@ struct WarpSet {
             bitonic_merge32(d[KPL - 1], i[KPL - 1], lane);
         }
     }
+    // "Empty" members that survived the search (fewer than K candidates with a comparable distance: NaN coordinates in
+    // the query or the cloud -- a NaN distance never passes cand_less) carry indices above every real point.  The callers
+    // of knn_points dereference the indices unchecked, so they are mapped into [0, N) before anything is written:
+    // member 0x7fffffff - p becomes point p (distinct, in range; its distance stays +inf).  pytorch3d likewise returns
+    // in-range indices and lets the NaN propagate through the values.
+    __device__ __forceinline__ void sanitize(int N) {
+#pragma unroll
+        for (int s = 0; s < KPL; ++s)
+            if (i[s] != -1 && (unsigned)i[s] >= (unsigned)N) {
+                const int p = 0x7fffffff - i[s];
+                i[s] = (p >= 0 && p < N) ? p : 0;
+            }
+    }
     // after sort_set: f(pos, dist, index) for the K members, pos = 0..K-1 ascending
     template <typename F>
     __device__ __forceinline__ void for_each_sorted(int K, int lane, F f) const {

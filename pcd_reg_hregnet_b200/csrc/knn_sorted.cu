@@ -201,6 +201,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         }
     }
     top.sort_set(lane);                                     // dummies (-1, -1) sort first
+    top.sanitize(N);
     const int ndummy = 32 * KPL - K;
     const size_t base = ((size_t)b * M + m) * K;
 #pragma unroll
@@ -239,11 +240,10 @@ HRN_API int hrn_knn3_sort(const float* p2, int B, int N, void* scratch_pts, floa
     if (N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0) return HRN_OK;
     const int N2 = knn3_pow2(N);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static hrn_once_per_device attr_set;
+    if (attr_set.need()) {
         HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         HRN_CUDA(cudaFuncSetAttribute(knn_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-        attr_set = true;
     }
     if (N2 <= 16384)
         knn_sort_kernel<true><<<B, SORT_THREADS, (size_t)N2 * 8, (cudaStream_t)stream>>>(p2, (float4*)scratch_pts, scratch_boxes, N, N2);

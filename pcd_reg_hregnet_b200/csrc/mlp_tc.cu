@@ -594,11 +594,10 @@ int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int
     int S = (int)((budget - fixed) / stage_bytes);
     if (S > WS_MAX_STAGES) S = WS_MAX_STAGES;
     const size_t smem = (size_t)S * stage_bytes + fixed;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static hrn_once_per_device attr_set;
+    if (attr_set.need()) {
         HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        attr_set = true;
     }
     const int grid = n_items < 148 ? n_items : 148;
     const bool simple = in->n_seg == 1 && in->seg[0].mode == HRN_SEG_DIRECT && !in->seg[0].row_scale;
@@ -645,11 +644,10 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     int NW = (int)((226 * 1024 - 2 * A_STAGE_BYTES) / ((size_t)NS * 128));   // weight ring depth
     NW = 2;   // measured: a 3- or 4-slot weight ring costs more in co-resident CTAs than it hides in copy latency
     const size_t smem = 2 * (size_t)A_STAGE_BYTES + (size_t)NW * NS * 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static hrn_once_per_device attr_set;
+    if (attr_set.need()) {
         HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 3 * 512 * 128));
         HRN_CUDA(cudaFuncSetAttribute(layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 3 * 512 * 128));
-        attr_set = true;
     }
     // 16-byte aligned segments (every call of the registration path): persistent warp-specialised kernel; the
     // one-CTA-per-tile kernel below remains as the general fallback (odd channel counts, unaligned views)

@@ -292,16 +292,29 @@ def weighted_kabsch(src, cor, w, prev=None):
 # fused stages
 # ------------------------------------------------------------------------------------------------------------------
 
-def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=False):
+def random_sample_idx(n_points, n_sample, batch_sizes, device):
+    """The `fps=False` branch of KeypointDetector (reference layers.py:144-147): `torch.randperm(N)[:nsample]` drawn from
+    the HOST generator, ONE draw per detector call, shared by every cloud of that call.  batch_sizes = clouds per
+    reference call (the model path stacks the source and the target call into one batch: two draws, in call order).
+    Returns int32 [sum(batch_sizes), n_sample] on `device`."""
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("use_fps=False draws the sample on the host in every forward (layers.py:146): it cannot be "
+                           "captured in a CUDA graph -- use Registrar(..., use_cuda_graph=False) or call the net eagerly")
+    rows = [torch.randperm(n_points)[:n_sample].to(torch.int32)[None].expand(b, n_sample) for b in batch_sizes]
+    return torch.cat(rows, 0).contiguous().to(device)
+
+
+def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=False, sample_idx=None):
     """One hierarchy level: KeypointDetector + DescExtractor (reference layers.py:134-165 + 200-209) without
     materialising grouped_features / attentive_feature_map.
 
     xyz [B,N,3]; feat_cl [B,N,C] channels-last or None; weights [B,N] or None (-> weighted FPS).
     det / desc: folded parameter dicts (fold.py).  Returns dict(xyz [B,M,3], sigmas [B,M], af [B,M,C_o] ,
-    desc [B,M,desc_dim], and with want_maps also the rows-layout G, E, a, idx for the layer-level API)."""
+    desc [B,M,desc_dim], and with want_maps also the rows-layout G, E, a, idx for the layer-level API).
+    sample_idx int32 [B,M]: use these samples instead of (weighted) FPS (the reference's fps=False branch)."""
     B, N, _ = xyz.shape
     presorted = KnnPresort.fork(xyz)
-    fidx = fps(xyz, M, weights)
+    fidx = fps(xyz, M, weights) if sample_idx is None else sample_idx
     if presorted is not None:
         presorted.launch()
     idx, q = knn_idx(None, xyz, k, q_idx=fidx, presorted=presorted)

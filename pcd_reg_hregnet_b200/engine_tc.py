@@ -5,6 +5,7 @@ multiple of 8 (and in total to a multiple of 32), Cout padded to a multiple of 1
 [n_stage][hi|lo][K/8 within stage = 4][NP][8] so that one stage is one contiguous cp.async.bulk.
 Packed weights are cached per (weight tensor, segment signature)."""
 import ctypes
+import weakref
 
 import torch
 
@@ -12,6 +13,15 @@ from . import engine
 
 KC = 32
 _cache = {}
+
+
+def _remember(cache, key, owner, value):
+    """Packed copies live exactly as long as the folded weight tensor they were made from: when a module re-folds
+    (load_state_dict, an eval between training epochs) the old folded tensors die and their packs go with them --
+    the caches do not grow over time.  Keys hold data_ptr / version only; `owner` is referenced weakly."""
+    cache[key] = value
+    weakref.finalize(owner, cache.pop, key, None)
+    return value
 
 
 def pack_weights(W, seg_channels):
@@ -36,9 +46,7 @@ def pack_weights(W, seg_channels):
     hi = Wp.to(torch.bfloat16)
     lo = (Wp - hi.float()).to(torch.bfloat16)
     t = torch.stack([hi, lo], 0).view(2, NP, n_stage, KC // 8, 8).permute(2, 0, 3, 1, 4).contiguous()
-    out = (t, NP, n_stage, W)          # keep W alive so data_ptr keys stay unique
-    _cache[key] = out
-    return out
+    return _remember(_cache, key, W, (t, NP, n_stage, None))
 
 
 def layer_tc(view, W, b, act, out):
@@ -134,9 +142,7 @@ def pack_level(level, det, desc):
     biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()
     from ._lib import lib
     assert Wpack.numel() == lib().hrn_level_pack_bytes(level) and biases.numel() == lib().hrn_level_bias_count(level)
-    out = (Wpack, biases, [t[0] for t in det["convs"] + desc["convs"] + desc["mlp"]])
-    _level_cache[key] = out
-    return out
+    return _remember(_level_cache, key, d1, (Wpack, biases, None))
 
 
 def level_fused(level, q, xyz, feat_cl, idx, det, desc):
@@ -215,9 +221,7 @@ def pack_chain(layers, seg_channels):
     Wpack = torch.cat([_pieces(m, m.shape[1]) for m in mats]).contiguous()
     bias = torch.cat([b for _, b, _ in layers]).contiguous()
     widths = [m.shape[0] for m in mats]
-    out = (Wpack, bias, chunks0, widths, cout, [W for W, _, _ in layers])
-    _chain_cache[key] = out
-    return out
+    return _remember(_chain_cache, key, layers[0][0], (Wpack, bias, chunks0, widths, cout, None))
 
 
 def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act=None):

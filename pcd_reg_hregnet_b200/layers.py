@@ -69,14 +69,14 @@ class KeypointDetector(_Folded):
         return dict(convs=fold.fold_sequential(self.convs), mlp=fold.fold_head(self.mlp1, self.mlp2, self.mlp3))
 
     def forward(self, xyz, features, weights=None):
-        if not self.fps:
-            raise NotImplementedError("fps=False (host randperm sampling, layers.py:145-147) is not on the B200 path")
         B, N, _ = xyz.shape
         M, k = self.nsample, self.k
         feat_cl = _cl(features) if features is not None else None
         P = self.folded()
+        # fps=False: one host permutation per call, shared by the clouds of the batch (layers.py:144-147)
+        sample = None if self.fps else engine.random_sample_idx(N, M, [B], xyz.device)
         # detector-only use of the fused level: run the detector half of the stage
-        lv = _detector_only(xyz.contiguous(), feat_cl, weights, P, M, k)
+        lv = _detector_only(xyz.contiguous(), feat_cl, weights, P, M, k, sample)
         E, a, geom, idx = lv["E"], lv["a"], lv["geom"], lv["idx"]
         rows = B * M * k
         if feat_cl is not None:
@@ -91,9 +91,9 @@ class KeypointDetector(_Folded):
         return lv["xyz"], lv["sigmas"], engine.transpose(lv["af"]), grouped, afm
 
 
-def _detector_only(xyz, feat_cl, weights, P, M, k):
+def _detector_only(xyz, feat_cl, weights, P, M, k, sample_idx=None):
     B, N, _ = xyz.shape
-    fidx = engine.fps(xyz, M, weights)
+    fidx = engine.fps(xyz, M, weights) if sample_idx is None else sample_idx
     idx, q = engine.knn_idx(None, xyz, k, q_idx=fidx)
     geom, nn_xyz = engine.group_geometry(q, xyz, idx, want_nn=True)
     v = RowsView(B * M * k, group=k, gather_idx=idx, rows_per_batch=M * k, src_rows_per_batch=N).add(geom)

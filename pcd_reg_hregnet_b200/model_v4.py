@@ -50,7 +50,7 @@ class Model_V4(nn.Module):
 
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]
-        both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points))
+        both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points), calls=2)
         S = {k: v[:B] for k, v in both.items()}
         D = {k: v[B:] for k, v in both.items()}
         cor3, w3, coord_dist, feats_dist = self.coarse_corres.forward_cl(

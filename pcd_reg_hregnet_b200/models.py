@@ -34,15 +34,28 @@ class HierFeatureExtraction(nn.Module):
                     DescExtractor(in_channels=cin[lv], out_channels=widths[lv], C_detector=widths[lv][-1],
                                   desc_dim=widths[lv][-1]))
 
-    def forward_cl(self, points):
-        """Channels-last internal result: per level l: xyz_l [B,M,3], sigmas_l [B,M], desc_l [B,M,C]."""
-        if not self.use_fps:
-            raise NotImplementedError("use_fps=False (host randperm sampling) is not on the B200 path")
+    def forward_cl(self, points, calls=1):
+        """Channels-last internal result: per level l: xyz_l [B,M,3], sigmas_l [B,M], desc_l [B,M,C].
+        calls: how many reference calls of the extractor this batch stands for (HRegNet stacks the source and the target
+        call, models.py:79-80, into one batch: calls=2).  Only the use_fps=False branch cares: it draws one host
+        permutation per detector per call, in the reference's order (call 1: levels 1,2,3; then call 2)."""
         xyz, feat, w = points.contiguous(), None, None
         out = {}
+        draws = None
+        if not self.use_fps:
+            per = points.shape[0] // calls
+            n_in = [points.shape[1], self.detector_1.nsample, self.detector_2.nsample]
+            host = [[torch.randperm(n_in[l])[:getattr(self, f"detector_{l + 1}").nsample].to(torch.int32) for l in range(3)]
+                    for _ in range(calls)]
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("use_fps=False draws its samples on the host in every forward (layers.py:146); "
+                                   "run it eagerly (Registrar(..., use_cuda_graph=False))")
+            draws = [torch.cat([host[c][l][None].expand(per, -1) for c in range(calls)], 0).contiguous().to(points.device)
+                     for l in range(3)]
         for lv in (1, 2, 3):
             det, desc = getattr(self, f"detector_{lv}"), getattr(self, f"desc_extractor_{lv}")
-            r = engine.detector_descriptor_level(xyz, feat, w, det.folded(), desc.folded(), det.nsample, det.k)
+            r = engine.detector_descriptor_level(xyz, feat, w, det.folded(), desc.folded(), det.nsample, det.k,
+                                                 sample_idx=None if draws is None else draws[lv - 1])
             out[f"xyz_{lv}"], out[f"sigmas_{lv}"], out[f"desc_{lv}"] = r["xyz"], r["sigmas"], r["desc"]
             xyz, feat = r["xyz"], r["af"]
             w = engine.sigma_to_weights(r["sigmas"]) if self.use_weights else None
@@ -67,7 +80,7 @@ class HRegNet(nn.Module):
 
     def forward(self, src_points, dst_points):
         B = src_points.shape[0]
-        both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points))
+        both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points), calls=2)
         S = {k: v[:B] for k, v in both.items()}
         D = {k: v[B:] for k, v in both.items()}
 

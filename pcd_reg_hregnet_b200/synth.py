@@ -73,3 +73,60 @@ def duplicate_padded_cloud(seed: int, n_points: int, n_unique: int):
     base = _sample_cloud(gen, n_unique, _scene_planes(gen))
     pad = base[torch.randint(0, n_unique, (n_points - n_unique,), generator=gen)]
     return torch.cat([base, pad], 0).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# seeded networks for benchmarks / smoke runs / tests (no checkpoint of the registration heads is reachable offline)
+# ------------------------------------------------------------------------------------------------------------------
+import os as _os
+
+PRETRAINED_FEATS = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests", "golden",
+                                 "nusc_feats_state.npz")
+
+
+class Args:
+    """The 4-attribute `args` contract of the reference models (models/HRegNet/models.py:11-12,18,67)."""
+    use_fps = True
+    use_weights = True
+    freeze_detector = False
+    freeze_feats = False
+
+
+def pretrained_feats(path=None):
+    """The reference's pretrained HierFeatureExtraction state_dict (ckpt/pretrained/nusc_feats.pth re-saved as npz)."""
+    import numpy as np
+    with np.load(path or PRETRAINED_FEATS) as z:
+        return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def randomize_bn_(module, gen):
+    """Non-trivial BatchNorm running statistics / affine parameters for the seeded registration heads (default
+    statistics would make BatchNorm folding a no-op).  Draw order is part of the fixture contract (tests/golden)."""
+    for m in module.modules():
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            n = m.num_features
+            m.running_mean.copy_(torch.randn(n, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(n, generator=gen) * 0.5 + 0.75)
+            m.weight.data.copy_(torch.rand(n, generator=gen) * 0.5 + 0.75)
+            m.bias.data.copy_(torch.randn(n, generator=gen) * 0.1)
+
+
+def build_net(model="hregnet", seed=7, device="cpu", args=None):
+    """HRegNet / Model_V2 / Model_V4 of this package in eval mode: the reference's pretrained feature extractor +
+    `torch.manual_seed(seed)` default-initialised registration heads with randomised BatchNorm statistics -- exactly
+    the weights of the committed golden fixtures (tests/golden/make_golden.py builds the reference classes the same way)."""
+    if model == "hregnet":
+        from .models import HRegNet as cls
+    elif model == "v2":
+        from .model_v2 import Model_V2 as cls
+    elif model == "v4":
+        from .model_v4 import Model_V4 as cls
+    else:
+        raise ValueError(model)
+    torch.manual_seed(seed)
+    net = cls(args or Args())
+    net.feature_extraction.load_state_dict(pretrained_feats())
+    g = torch.Generator().manual_seed(seed + 1)
+    for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
+        randomize_bn_(getattr(net, name), g)
+    return net.eval().to(device)

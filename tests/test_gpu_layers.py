@@ -141,3 +141,185 @@ def test_group_attend_equals_separate_kernels():
     call("hrn_group_attend", ptr(F), F.stride(0), C, B * N1, k, ptr(a2), ptr(af2), af2.stride(0), ptr(dxyz), ptr(idx),
          N1, N2, ptr(cor2), stream())
     assert torch.equal(a, a2) and torch.equal(af, af2) and torch.equal(cor, cor2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: pose cascade on the reference's own correspondences, the BASELINE configs[1] shape, the layer-class API
+# ------------------------------------------------------------------------------------------------------------------
+POSE_DEG, POSE_M = 1e-4, 1e-5        # BASELINE.json north_star: R|t within 1e-4 deg / 1e-5 m
+
+
+@pytest.mark.parametrize("name", ["hregnet_b2_n2048", "hregnet_uniform_b1_n1500"])
+def test_golden_pose_cascade_teacher_forced(name):
+    """The pose stages on the UNMODIFIED reference's own intermediate results (tests/golden, models.py:87-127): golden
+    keypoints / correspondences / weights of every level -> hrn_weighted_kabsch (+ fused composition with the golden
+    previous pose) -> golden rotation / translation, at the north-star tolerance."""
+    gd = load_golden(name)
+    S = unflatten(gd, "src_feats.")
+    g = lambda t: t.to(DEV).contiguous()
+    B = gd["src"].shape[0]
+    worst = [0.0, 0.0]
+    prev = None
+    for i, lv in enumerate((3, 2, 1)):
+        src = S[f"xyz_{lv}"] if prev is None else RL._apply(prev[0], prev[1], S[f"xyz_{lv}"])     # models.py:91-92,113-114
+        if prev is not None:
+            xt = engine.transform_points(g(S[f"xyz_{lv}"]), g(prev[0]), g(prev[1])).cpu()
+            assert float((xt - src).abs().max()) < 2e-5
+        cor, w = gd[f"src_xyz_corres_{lv}"], gd[f"src_dst_weights_{lv}"]
+        if prev is None:
+            R, t = engine.weighted_kabsch(g(src), g(cor), g(w))
+        else:
+            _, _, R, t = engine.weighted_kabsch(g(src), g(cor), g(w), prev=(g(prev[0]), g(prev[1])))
+        R, t = R.cpu(), t.cpu()
+        Rg, tg = gd[f"rotation.{i}"], gd[f"translation.{i}"]
+        ang = float(RL.rotation_angle_deg(R, Rg).max())
+        dt = float((t - tg).abs().max())
+        worst = [max(worst[0], ang), max(worst[1], dt)]
+        assert ang < POSE_DEG and dt < POSE_M, (name, lv, ang, dt)
+        prev = (Rg, tg)
+    print(f"{name}: cascade on golden correspondences, B={B}: worst {worst[0]:.2e} deg / {worst[1]:.2e} m")
+
+
+def test_level1_at_baseline_config_shape(nets, precision):
+    """BASELINE configs[1] shape: 32 clouds x 16,384 points through level 1 (the level whose inputs involve no learned
+    weights, so it is teacher-forced by construction): FPS + kNN indices bit-exact, keypoints / sigmas / descriptors /
+    attentive features within the feature gate, through the product path (the fused tcgen05 level kernel in tc modes)."""
+    cpu, gpu = nets
+    src = synth.make_batch(range(1000, 1032), 16384)[0]
+    fe = gpu.feature_extraction
+    det, desc = fe.detector_1, fe.desc_extractor_1
+    xyz_tol = 1e-5 if precision == "fp32" else 1e-4
+    with torch.no_grad():
+        xg = src.to(DEV)
+        fidx = engine.fps(xg, 1024)
+        idx, _ = engine.knn_idx(None, xg, 64, q_idx=fidx)
+        r = engine.detector_descriptor_level(xg, None, None, det.folded(), desc.folded(), 1024, 64)
+        torch.cuda.synchronize()
+        for c0 in range(0, 32, 8):                       # the oracle in chunks of 8 clouds (its cat tensor is 0.4 GB each)
+            trace = {}
+            want = RL.hier_feature_extraction(cpu.state_dict(), "feature_extraction.", src[c0:c0 + 8], levels=RL.LEVELS[:1],
+                                              trace=trace)
+            assert torch.equal(fidx[c0:c0 + 8].cpu(), trace["fps_idx_1"]), "FPS idx"
+            q = src[c0:c0 + 8][torch.arange(8)[:, None], trace["fps_idx_1"].long()]
+            _, i_o, _ = native.knn_points(q, src[c0:c0 + 8], K=64)
+            assert torch.equal(idx[c0:c0 + 8].cpu().long(), i_o), "kNN idx"
+            assert rel_err(r["xyz"][c0:c0 + 8].cpu(), want["xyz_1"]) < xyz_tol
+            assert rel_err(r["sigmas"][c0:c0 + 8].cpu(), want["sigmas_1"]) < FEAT_TOL
+            assert rel_err(_cl(r["desc"][c0:c0 + 8].cpu()), want["desc_1"]) < FEAT_TOL
+            assert rel_err(_cl(r["af"][c0:c0 + 8].cpu()), trace["af_1"]) < FEAT_TOL
+
+
+@pytest.mark.parametrize("lv", [1, 2])
+def test_layer_class_api_outputs(nets, lv, precision):
+    """The drop-in layer classes called the way the reference's model graph calls them (channel-first tensors in and out):
+    KeypointDetector.forward's five results incl. grouped_features / attentive_feature_map (layers.py:134-165),
+    DescExtractor.forward on them (layers.py:200-209), knn_group (layers.py:9-27), calc_cosine_similarity (layers.py:29-41)."""
+    from pcd_reg_hregnet_b200 import layers as PL
+    cpu, gpu = nets
+    sd = cpu.state_dict()
+    src = synth.make_batch([41, 42], 2048)[0]
+    g = lambda t: t.to(DEV).contiguous()
+    with torch.no_grad():
+        if lv == 1:
+            xyz, feat, w = src, None, None
+        else:
+            k1, s1, af1, _, _, _ = RL.keypoint_detector(sd, "feature_extraction.detector_1.", src, None, None, 1024, 64)
+            xyz, feat, w = k1, af1, RL.sigma_weights(s1)
+        M, k = (1024, 64) if lv == 1 else (512, 32)
+        p = f"feature_extraction.detector_{lv}."
+        kp_o, sig_o, af_o, G_o, afm_o, fidx_o = RL.keypoint_detector(sd, p, xyz, feat, w, M, k)
+        det = getattr(gpu.feature_extraction, f"detector_{lv}")
+        kp, sig, af, G, afm = det(g(xyz), g(feat) if feat is not None else None, g(w) if w is not None else None)
+        assert G.shape == G_o.shape and afm.shape == afm_o.shape and af.shape == af_o.shape
+        assert rel_err(kp.cpu(), kp_o) < (1e-5 if precision == "fp32" else 1e-4)
+        assert rel_err(sig.cpu(), sig_o) < FEAT_TOL and rel_err(af.cpu(), af_o) < FEAT_TOL
+        # grouped_features is index work + subtractions of identical inputs: the gathered channels are exact copies
+        assert torch.equal(G[:, 4:].cpu(), G_o[:, 4:])
+        assert float((G[:, :4].cpu() - G_o[:, :4]).abs().max()) < 1e-5
+        assert rel_err(afm.cpu(), afm_o) < FEAT_TOL
+        ext = getattr(gpu.feature_extraction, f"desc_extractor_{lv}")
+        d = ext(g(G_o), g(afm_o))                                                   # teacher-forced on the oracle's maps
+        d_o = RL.desc_extractor(sd, f"feature_extraction.desc_extractor_{lv}.", G_o, afm_o)
+        assert d.shape == d_o.shape and rel_err(d.cpu(), d_o) < FEAT_TOL
+        # knn_group: the reference's free function
+        q = xyz[torch.arange(2)[:, None], fidx_o.long()]
+        Gk, nn = PL.knn_group(g(q), g(xyz), g(feat) if feat is not None else None, k)
+        Gk_o, nn_o = RL.knn_group(q, xyz, feat, k)
+        assert torch.equal(nn.cpu(), nn_o) and torch.equal(Gk[:, 4:].cpu(), Gk_o[:, 4:])
+        assert float((Gk[:, :4].cpu() - Gk_o[:, :4]).abs().max()) < 1e-5
+    a, b = torch.randn(2, 50, 7, 64), torch.randn(2, 50, 7, 64)
+    want = (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1) + 1e-6)
+    assert torch.allclose(PL.calc_cosine_similarity(g(a), g(b)).cpu(), want, atol=1e-6)
+
+
+def test_use_fps_false_branch(nets):
+    """args.use_fps=False (layers.py:144-147, models.py:11): one HOST permutation per detector call, shared by the clouds
+    of the call, drawn in the reference's order (source call: levels 1, 2, 3, then the target call)."""
+    from pcd_reg_hregnet_b200 import synth as sy
+    from pcd_reg_hregnet_b200.models import HRegNet
+
+    class A(sy.Args):
+        use_fps = False
+
+    cpu, _ = nets
+    net = HRegNet(A())
+    net.load_state_dict(cpu.state_dict())
+    net = net.eval().to(DEV)
+    src, dst = synth.make_batch([71, 72], 2048)[:2]
+    sd = cpu.state_dict()
+    with torch.no_grad():
+        torch.manual_seed(5)
+        out = net(src.to(DEV), dst.to(DEV))
+        torch.manual_seed(5)
+        draws = [torch.randperm(n) for _ in range(2) for n in (2048, 1024, 512)]    # src call: levels 1,2,3; dst call
+        for side, pts, d1 in (("src", src, draws[0]), ("dst", dst, draws[3])):
+            # level 1 has no learned input: it is teacher-forced by construction and pins the draw order of both calls
+            idx = d1[:1024][None].expand(2, 1024)
+            kp, sig, af, G, afm, _ = RL.keypoint_detector(sd, "feature_extraction.detector_1.", pts, None, None, 1024, 64,
+                                                          sample_idx=idx)
+            got = out[f"{side}_feats"]
+            assert rel_err(got["xyz_1"].cpu(), kp) < 1e-4, side
+            assert rel_err(got["sigmas_1"].cpu(), sig) < FEAT_TOL
+            assert rel_err(got["desc_1"].cpu(), RL.desc_extractor(sd, "feature_extraction.desc_extractor_1.", G, afm)) < FEAT_TOL
+        assert all(torch.isfinite(v).all() for v in out["rotation"] + out["translation"])
+        # the layer class alone, with input features (level 2), teacher-forced on the oracle's level-1 result
+        det2 = net.feature_extraction.detector_2
+        torch.manual_seed(9)
+        kp2 = det2(kp.to(DEV), af.to(DEV), None)[0]
+        torch.manual_seed(9)
+        idx2 = torch.randperm(1024)[:512][None].expand(2, 512)
+        kp2_o = RL.keypoint_detector(sd, "feature_extraction.detector_2.", kp, af, None, 512, 32, sample_idx=idx2)[0]
+        assert rel_err(kp2.cpu(), kp2_o) < 1e-4
+
+
+def test_knn_nan_point_does_not_fault():
+    """A NaN point in a cloud: pytorch3d returns in-range indices and lets the NaN propagate; so do we --
+    no sentinel index ever reaches a consumer (the level kernels dereference idx unchecked)."""
+    from pcd_reg_hregnet_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    for N, M, K in ((4096, 256, 64), (600, 64, 16), (2048, 128, 8)):
+        p2 = torch.rand(2, N, 3, generator=g) * 50
+        p2[0, 17] = float("nan")
+        p1 = p2[:, :M].clone()                              # query 17 of cloud 0 is NaN as well
+        d, i, nn = ops.knn_points(p1.to(DEV), p2.to(DEV), K=K, return_nn=True)
+        torch.cuda.synchronize()
+        assert int(i.min()) >= 0 and int(i.max()) < N
+        ok = torch.ones(2, M, dtype=torch.bool); ok[0, 17] = False
+        # every other query: the NaN point is never a neighbour, results equal the search on the cloud without it
+        p2c = p2.clone(); p2c[0, 17] = 1e6
+        _, i_c, _ = native.knn_points(p1, p2c, K=K)
+        assert torch.equal(i.cpu()[ok], i_c[ok])
+    # descriptor space (D = 256) with a NaN descriptor
+    S, D = torch.randn(1, 256, 256, generator=g), torch.randn(1, 256, 256, generator=g)
+    D[0, 5] = float("nan"); S[0, 9, 3] = float("nan")
+    idx, _ = engine.knn_idx(S.to(DEV), D.to(DEV), 8)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 256
+    # end to end: one NaN input point -> no fault, the forward completes
+    net = build_product_hregnet(seed=7, device=DEV)
+    src, dst = synth.make_batch([81], 4096)[:2]
+    src[0, 100] = float("nan")
+    with torch.no_grad():
+        out = net(src.to(DEV), dst.to(DEV))
+    torch.cuda.synchronize()
+    assert out["rotation"][-1].shape == (1, 3, 3)

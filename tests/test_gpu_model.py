@@ -22,6 +22,14 @@ def precision(request):
     _e.set_precision("tc")
 
 
+POSE_DEG, POSE_M = 1e-4, 1e-5        # BASELINE.json north_star: R|t within 1e-4 deg / 1e-5 m
+# Free-running whole-model runs: pairs per fixture whose level-2/3 keypoint sets must survive the cascade (weighted FPS
+# consumes network outputs).  The exact modes reproduce the reference's picks on the committed
+# fixtures; the fp16 modes (relative feature error ~1e-4) change sigma enough to flip picks and are gated stage-wise
+# (tests/test_gpu_layers.py) -- free-running they must still reproduce level 1 and return a finite, proper pose.
+MIN_CHECKED = {"fp32": 1, "tc": 1, "tc2": 0, "tc1": 0}
+
+
 @pytest.fixture(scope="module")
 def net():
     return build_product_hregnet(seed=7, device=DEV)
@@ -40,7 +48,7 @@ def test_golden_end_to_end(net, name, precision):
         assert rel_err(f["xyz_1"].cpu(), gd[f"{side}_feats.xyz_1"]) < xyz_tol
         assert rel_err(f["desc_1"].cpu(), gd[f"{side}_feats.desc_1"]) < 1e-3
         assert rel_err(f["sigmas_1"].cpu(), gd[f"{side}_feats.sigmas_1"]) < 1e-3
-    n_checked = 0
+    n_checked, worst = 0, (0.0, 0.0)
     for b in range(B):
         same = all(rel_err(out[f"{s}_feats"][f"xyz_{lv}"][b].cpu(), gd[f"{s}_feats.xyz_{lv}"][b]) < 1e-4
                    for s in ("src", "dst") for lv in (2, 3))
@@ -50,8 +58,12 @@ def test_golden_end_to_end(net, name, precision):
         for lv in range(3):
             ang = float(RL.rotation_angle_deg(out["rotation"][lv][b].cpu(), gd[f"rotation.{lv}"][b]))
             dt = float((out["translation"][lv][b].cpu() - gd[f"translation.{lv}"][b]).abs().max())
-            assert ang < 1e-3 and dt < 1e-4, (b, lv, ang, dt)
-    print(f"{name}: {n_checked}/{B} pairs had identical keypoint sets and met the pose gate")
+            worst = (max(worst[0], ang), max(worst[1], dt))
+            assert ang < POSE_DEG and dt < POSE_M, (b, lv, ang, dt)
+    print(f"{name} [{precision}]: {n_checked}/{B} pairs had identical keypoint sets; worst pose delta "
+          f"{worst[0]:.2e} deg / {worst[1]:.2e} m")
+    # not vacuous: every fixture keeps at least one pair whose keypoint sets survive the cascade in this mode
+    assert n_checked >= MIN_CHECKED[precision], (name, precision, n_checked)
 
 
 def test_full_size_forward_is_deterministic_and_sane(net):
@@ -273,4 +285,5 @@ def test_golden_end_to_end_model_variants(which, precision):
         if which == "v4":
             assert rel_err(out["coord_dist"].cpu(), gd["coord_dist"]) < 1e-3
             assert float((out["feats_dist"].cpu() - gd["feats_dist"]).abs().max()) < 1e-3
-    print(f"model_{which}: {len(ok)}/{B} pairs had identical level-2 keypoint sets")
+    print(f"model_{which} [{precision}]: {len(ok)}/{B} pairs had identical level-2 keypoint sets")
+    assert len(ok) >= MIN_CHECKED[precision], (which, precision, len(ok))
