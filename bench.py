@@ -16,8 +16,13 @@ Weak scaling: 32 pairs per GPU (N=8 -> the 256-pair job of configs[2]).
   in_flight pairs/s of the same K steps from device-resident inputs with map()'s two forwards in flight (rotating
             input batches larger than L2 instead of a flush) -- what e2e is bounded by; `value` stays one forward at a time
   roofline  dominant kernel family (shared-MLP layers): algorithmic FLOP / CUDA-event time of those launches
-  cpu_baseline  the oracle port of the reference (oracle/ref_layers.py + oracle/native_ops.c) on the host cores,
-            bounded sample (rank 0, N=1 only)
+  cpu_baseline  the reference's CPU path on the box's host cores, bounded sample (rank 0, N=1 only): the UNMODIFIED
+            reference graph (baseline/_ref, staged by __graft_entry__.build()) run batched on the CPU through
+            oracle/ref_harness.py, native ops = the oracle's C restatement (kind "reference"); where the staged reference
+            is absent, the oracle port of the graph (kind "port")
+  gpu_reference the UNMODIFIED reference graph on the same B200 (its own CUDA extension recompiled for sm_100a in
+            oracle/_ref + torch cdist/topk standing in for the uninstallable pytorch3d), CUDA-event timed
+  parity    free-running index agreement per level and pose deltas of the first pairs of the bench batch vs the oracle
   --impl reference   times that CPU implementation as the reference arm (rank 0 only)
 """
 import argparse
@@ -30,7 +35,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
@@ -48,8 +52,12 @@ def parse():
     ap.add_argument("--points", type=int, default=16384)
     ap.add_argument("--precision", default=os.environ.get("HRN_PRECISION", "auto"))
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=32)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=4, help="pairs per batched CPU reference forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--total-pairs", type=int, default=256,
+                    help="N > 1: also time the strong-scaling job of BASELINE configs[2] (this many pairs sharded over the GPUs)")
     ap.add_argument("--model", default="hregnet", choices=["hregnet", "v2", "v4"],
                     help="hregnet = BASELINE configs[1] (default); v2 = Adaption-1 / Model_V2 (configs[3], use --points 32768); "
                          "v4 = Model_V4 (Model_V2 + coord_dist / feats_dist of the coarse stage)")
@@ -99,58 +107,129 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_pairs_per_s(n_pairs, n_points, reps=1):
-    """The reference's CPU path (oracle port: reference graph restated in torch-CPU over the C native ops)."""
-    from common import build_product_hregnet
-    from oracle import ref_layers as RL
+def workload_config(args, world):
+    """`config` of the JSON line -- the same dict for both arms (the reference arm runs a bounded sample of it)."""
+    name = dict(hregnet="HRegNet baseline", v2="Adaption-1 (Model_V2)", v4="Model_V4")[args.model]
+    return {"workload": f"{name} forward, batch {args.pairs_per_gpu} synthetic {args.points}-pt pairs per GPU (keypoints 1024/512/256)",
+            "pairs_per_gpu": args.pairs_per_gpu, "points": args.points,
+            "parallelism": f"pairs sharded over {world} GPU(s), pose all-gather"}
+
+
+def cpu_reference_forward(n_points, batch):
+    """-> (callable running ONE batched forward of `batch` pairs on the CPU, kind, description).
+    kind "reference": the unmodified reference graph (oracle/ref_harness.py; /root/reference or the staged baseline/_ref)
+    with the oracle's C restatement of the CUDA-only native ops underneath; kind "port": the oracle's restatement of
+    the graph too (only where the reference files are absent)."""
+    from oracle import ref_harness as H
     from pcd_reg_hregnet_b200 import synth
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    sd = build_product_hregnet(seed=7).state_dict()
-    src, dst, _, _ = synth.make_batch(range(1000, 1000 + n_pairs), n_points)
-    with torch.no_grad():
-        RL.hregnet_forward(sd, src[:1], dst[:1])                      # warm-up
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            for i in range(n_pairs):
-                RL.hregnet_forward(sd, src[i:i + 1], dst[i:i + 1])
-        dt = time.perf_counter() - t0
-    return n_pairs * reps / dt, cores, dt
+    src, dst, _, _ = synth.make_batch(range(1000, 1000 + batch), n_points)
+    if H.available():
+        net = H.build_reference_hregnet(seed=7)
+        return (lambda: net(src, dst)), "reference", ("unmodified reference graph (models/HRegNet/models.py:77-148) on the CPU, "
+                                                      "native ops = oracle C restatement, torch-CPU for the layers")
+    from oracle import ref_layers as RL
+    sd = synth.build_net("hregnet", 7).state_dict()
+    return (lambda: RL.hregnet_forward(sd, src, dst)), "port", "oracle port of the reference graph (torch-CPU over the C native ops)"
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    per_step = 2                                                       # bounded sample: 2 pairs per "step"
-    from common import build_product_hregnet
-    from oracle import ref_layers as RL
-    from pcd_reg_hregnet_b200 import synth
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    sd = build_product_hregnet(seed=7).state_dict()
-    src, dst, _, _ = synth.make_batch(range(1000, 1000 + per_step), args.points)
+    per_step = max(1, args.cpu_sample_pairs)                           # bounded sample: one batched forward per "step"
+    fwd, kind, what = cpu_reference_forward(args.points, per_step)
     with torch.no_grad():
         for _ in range(max(1, min(warm, 2))):
-            RL.hregnet_forward(sd, src[:1], dst[:1])
+            fwd()
         t0 = time.perf_counter()
         for _ in range(steps):
-            for i in range(per_step):
-                RL.hregnet_forward(sd, src[i:i + 1], dst[i:i + 1])
+            fwd()
         dt = time.perf_counter() - t0
     v = steps * per_step / dt
-    sample = f"{per_step} pairs x {args.points} pts per step, B=1 forwards, {steps} steps"
+    sample = f"{per_step} pairs x {args.points} pts per step as ONE batched forward (B={per_step}), {steps} steps, {dt:.1f} s"
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        # the same workload as our arm's config; each step is a bounded sample of it (2 of the batch's pairs)
-        "config": {"workload": f"HRegNet baseline forward, batch {args.pairs_per_gpu} synthetic {args.points}-pt pairs per GPU (keypoints 1024/512/256)",
-                   "pairs_per_gpu": args.pairs_per_gpu, "points": args.points, "sample_pairs_per_step": per_step,
-                   "implementation": "CPU oracle port of the reference (torch-CPU layers over the C native ops), B=1 forwards, all host cores"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.gpus),
+        "implementation": what + f"; all {cores} host cores",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def cpu_baseline_subprocess(args):
+    """The CPU leg in its own process (the CPU harness redirects torch's .cuda() entry points: it must not share a
+    process with the GPU arm).  Bounded: 1 warm-up + 3 batched forwards."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--points", str(args.points), "--cpu-sample-pairs", str(args.cpu_sample_pairs)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+        return {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "unavailable", "sample": repr(e)[:200]}
+
+
+def gpu_reference(args, dev):
+    """The UNMODIFIED reference graph on this GPU: its own CUDA extension recompiled for sm_100a
+    (oracle/_ref/point_utils_cuda.so) + torch.cdist/topk for the uninstallable pytorch3d, same batch, CUDA events."""
+    try:
+        from oracle import ref_harness as H
+        from pcd_reg_hregnet_b200 import synth
+        if not H.available():
+            return {"unavailable": "reference files not staged (baseline/_ref)"}
+        net = H.build_reference_hregnet(seed=7, device="cuda")
+        B, N = args.pairs_per_gpu, args.points
+        src, dst, _, _ = synth.make_batch(range(1000, 1000 + B), N)
+        src, dst = src.to(dev), dst.to(dev)
+        with torch.no_grad():
+            net(src, dst)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); net(src, dst); e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+        ms = sorted(ts)[1]
+        del net
+        torch.cuda.empty_cache()
+        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+                "what": "unmodified reference HRegNet.forward on the same B200: reference PointUtils kernels recompiled for sm_100a "
+                        "(oracle/_ref), torch.cdist+topk in place of pytorch3d.knn_points, eager PyTorch 2.11 (cuDNN/cuBLAS/cuSOLVER)"}
+    except Exception as e:
+        return {"unavailable": repr(e)[:300]}
+
+
+def parity_report(out, src_h, dst_h, n_pairs=2):
+    """Free-running parity of the bench batch's first pairs against the oracle (CPU, seconds): index-agreement rate of
+    the keypoint sets per level and the pose deltas.  Weighted FPS makes levels 2/3 chaotic: the
+    stage-wise gates are the teacher-forced tests; this is the reported free-running picture."""
+    from oracle import ref_layers as RL
+    from pcd_reg_hregnet_b200 import synth
+    sd = synth.build_net("hregnet", 7).state_dict()
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    rep = {"pairs": n_pairs, "keypoints_equal": {}, "pose": []}
+    with torch.no_grad():
+        want = RL.hregnet_forward(sd, src_h[:n_pairs].clone(), dst_h[:n_pairs].clone())
+    for lv in (1, 2, 3):
+        same = []
+        for s in ("src", "dst"):
+            a = out[f"{s}_feats"][f"xyz_{lv}"][:n_pairs].cpu().double()
+            b = want[f"{s}_feats"][f"xyz_{lv}"].double()
+            same.append(float(((a - b).abs().amax(dim=2) < 1e-3).double().mean()))
+        rep["keypoints_equal"][f"level_{lv}"] = sum(same) / len(same)
+    d1 = out["src_feats"]["desc_1"][:n_pairs].cpu().double()
+    w1 = want["src_feats"]["desc_1"].double()
+    rep["desc_1_rel_err"] = float((d1 - w1).abs().max() / w1.abs().max())
+    for lv in range(3):
+        ang = RL.rotation_angle_deg(out["rotation"][lv][:n_pairs].cpu(), want["rotation"][lv])
+        dt = (out["translation"][lv][:n_pairs].cpu() - want["translation"][lv]).abs().amax(dim=1)
+        rep["pose"].append({"level": 3 - lv, "max_deg": float(ang.max()), "max_m": float(dt.max())})
+    return rep
 
 
 _REAL_STDOUT = None
@@ -176,7 +255,6 @@ def main():
         return
 
     import torch.distributed as dist
-    from common import build_product_hregnet
     from pcd_reg_hregnet_b200 import _lib, dist as hdist, engine, synth
     from pcd_reg_hregnet_b200.runner import Registrar
 
@@ -194,11 +272,7 @@ def main():
     lo = rank * B
     src_h, dst_h, _, _ = synth.make_batch(range(1000 + lo, 1000 + lo + B), N)
     src_h, dst_h = src_h.pin_memory(), dst_h.pin_memory()
-    if args.model in ("v2", "v4"):
-        from common import build_product_model_v2, build_product_model_v4
-        net = (build_product_model_v2 if args.model == "v2" else build_product_model_v4)(seed=7, device=dev)
-    else:
-        net = build_product_hregnet(seed=7, device=dev)
+    net = synth.build_net(args.model, seed=7, device=dev)
     reg = Registrar(net, B, N, use_cuda_graph=not args.no_graph)
     reg.load(src_h, dst_h)
     reg.capture()
@@ -298,6 +372,50 @@ def main():
 
     # ---- per-kernel-family breakdown + roofline of the dominant family (rank 0) ---------------------------------
     prof = _profile_families(reg, steps=min(args.steps, 3)) if rank == 0 else None
+    parity = None
+    if rank == 0 and world == 1 and args.model == "hregnet" and not args.no_parity:
+        try:
+            parity = parity_report(reg.run_device(), src_h, dst_h)
+        except Exception as e:  # reported picture, never a reason to lose the bench line
+            parity = {"unavailable": repr(e)[:200]}
+
+    # ---- strong scaling (BASELINE configs[2] as worded: a fixed job of --total-pairs pairs sharded over the GPUs) ----
+    strong = None
+    if world > 1 and args.total_pairs >= world and args.model == "hregnet":
+        Bs = args.total_pairs // world
+        k_s = max(2, min(args.steps, 5))
+        s_src, s_dst, _, _ = synth.make_batch([1000 + (rank * Bs + i) % 64 for i in range(Bs)], N)   # 64 distinct scenes
+        if Bs == B:
+            reg_s = reg
+        else:
+            reg_s = Registrar(net, Bs, N, use_cuda_graph=not args.no_graph, in_flight=1)
+            reg_s.load(s_src.pin_memory(), s_dst.pin_memory())
+            reg_s.capture()
+
+        def step_s():
+            o = reg_s.run_device()
+            hdist.gather_poses(o["rotation"][-1], o["translation"][-1])
+
+        for _ in range(3):
+            step_s()
+        torch.cuda.synchronize()
+        dist.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_s)]
+        for s0, e0 in evs:
+            flush.fill_(1)
+            s0.record()
+            step_s()
+            e0.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ts = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"total_pairs": Bs * world, "pairs_per_gpu": Bs, "steps": k_s, "ms_per_step": float(ts) / k_s,
+                  "value": Bs * world * k_s / (float(ts) / 1e3), "unit": UNIT, "scaling": "strong",
+                  "note": "BASELINE configs[2]: a fixed job of 256 pairs sharded contiguously over the GPUs, poses all-gathered; "
+                          "same timing rules as `value`"}
+        if reg_s is not reg:
+            del reg_s
 
     if rank == 0:
         pk = peaks()
@@ -309,10 +427,9 @@ def main():
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32" if precision == "fp32" else "bf16x3 (tcgen05, fp32 accumulate) + fp32",
             "data": "synthetic",
-            "config": {"workload": f"{dict(hregnet='HRegNet baseline', v2='Adaption-1 (Model_V2)', v4='Model_V4')[args.model]} forward, batch {B} synthetic {N}-pt pairs per GPU (keypoints 1024/512/256)",
-                       "pairs_per_gpu": B, "points": N, "parallelism": f"pairs sharded over {world} GPU(s), pose all-gather",
-                       "l2": "L2 flushed (256 MiB write) between timed iterations", "cuda_graph": not args.no_graph,
-                       "precision": precision},
+            "config": workload_config(args, world),
+            "run": {"l2": "L2 flushed (256 MiB write) between timed iterations", "cuda_graph": not args.no_graph,
+                    "precision": precision},
             "clocks": clocks,
             "e2e": {"value": total_pairs / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * B * N * 3 * 4, "d2h_bytes_per_step": B * 12 * 4,
@@ -327,10 +444,16 @@ def main():
             "roofline": prof["roofline"](pk),
             "kernel_rooflines": prof["kernel_rooflines"](pk, clocks.get("sm_mhz") or 1965),
         }
+        if parity is not None:
+            line["parity"] = parity
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if world == 1 and args.model == "hregnet" and not args.no_gpu_reference:
+            del reg
+            torch.cuda.empty_cache()
+            line["gpu_reference"] = gpu_reference(args, dev)
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, dt = cpu_reference_pairs_per_s(args.cpu_sample_pairs, N)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample_pairs} pairs x {N} pts, B=1 forwards, {dt:.1f} s"}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args)
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -41,5 +41,28 @@ def build(verbose: bool = False) -> str:
     return so
 
 
+STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+# what the reference arm of bench.py needs of the reference, relative to /root/reference:
+STAGED = ("models/utils.py", "models/HRegNet/layers.py", "models/HRegNet/models.py", "models/model_v2/layers.py",
+          "models/model_v2/models.py", "models/model_v4/layers.py", "models/model_v4/models.py",
+          "ckpt/pretrained/nusc_feats.pth")
+
+
+def stage_reference(ref_root: str = "/root/reference") -> str:
+    """Stages the UNMODIFIED reference files of the path under baseline/_ref/ (git-ignored: never part of this
+    repository's history, but it travels to the GPU box with the gpurun snapshot, where /root/reference does not exist).
+    `bench.py --impl reference` and the `gpu_reference` leg import the reference's own model graph from there, byte for
+    byte what the reference ships; nothing under pcd_reg_hregnet_b200/ reads it."""
+    import shutil
+    if not os.path.isdir(ref_root):
+        raise FileNotFoundError(ref_root)
+    for rel in STAGED:
+        dst = os.path.join(STAGE, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(ref_root, rel), dst)
+    return STAGE
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print(stage_reference())

@@ -23,7 +23,19 @@ import torch
 
 from . import native
 
-REF = os.environ.get("HREGNET_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the staged copy baseline/_ref (oracle/build_ref.py:
+    stage_reference, git-ignored, unmodified files)."""
+    for cand in (os.environ.get("HREGNET_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "HRegNet", "layers.py")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_reference()
 
 
 def available() -> bool:
@@ -77,22 +89,66 @@ def _fake_pytorch3d():
 
 
 _loaded = None
+_loaded_device = None
 
 
-def load_reference():
-    """Returns a namespace with the reference's HRegNet / Model_V2 classes and its layers module."""
-    global _loaded
+def _gpu_pytorch3d():
+    """pytorch3d stand-in for the reference graph ON THE GPU (BASELINE.md plan B3): pytorch3d cannot be installed offline,
+    so `knn_points` is the torch-library route to the same result, torch.cdist + topk (squared distances, ascending),
+    and `knn_gather` the index gather it is.  Timing stand-in only -- never a parity oracle."""
+    mods = _fake_pytorch3d()
+
+    def knn_points(p1, p2, K=1, return_nn=False, **kw):
+        d = torch.cdist(p1, p2) ** 2
+        dists, idx = d.topk(K, dim=2, largest=False, sorted=True)
+        nn = knn_gather(p2, idx) if return_nn else None
+        return dists, idx, nn
+
+    def knn_gather(x, idx):
+        B, M, K = idx.shape
+        return x[torch.arange(B, device=x.device)[:, None, None], idx]
+
+    mods["pytorch3d.ops"].knn_points = knn_points
+    mods["pytorch3d.ops"].knn_gather = knn_gather
+    return mods
+
+
+def _real_point_utils():
+    """The reference's own extension compiled for sm_100a from its unmodified sources (oracle/build_ref.py)."""
+    import importlib.util
+    so = os.path.join(_ROOT, "oracle", "_ref", "point_utils_cuda.so")
+    if not os.path.exists(so):
+        raise FileNotFoundError(f"{so} not built (oracle/build_ref.py, build container only)")
+    spec = importlib.util.spec_from_file_location("point_utils_cuda", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference(device="cpu"):
+    """Returns a namespace with the reference's HRegNet / Model_V2 classes and its layers module.
+    device="cpu": the four CPU redirections + oracle native ops (parity oracle, CPU reference arm).
+    device="cuda": nothing redirected -- the reference's own CUDA extension (oracle/_ref) and a torch cdist+topk
+    stand-in for pytorch3d: the reference graph as it runs on the GPU box (timing only).  One mode per process."""
+    global _loaded, _loaded_device
     if _loaded is not None:
+        if _loaded_device != device:
+            raise RuntimeError(f"reference already loaded for {_loaded_device}")
         return _loaded
     if not available():
         raise FileNotFoundError(f"reference not found under {REF}")
-    # CPU redirection of the hard-coded device moves
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
-    torch.cuda.IntTensor = lambda *s: torch.empty(*s, dtype=torch.int32)
-    torch.cuda.FloatTensor = lambda *s: torch.empty(*s, dtype=torch.float32)
-    sys.modules["point_utils_cuda"] = _fake_point_utils()
-    sys.modules.update(_fake_pytorch3d())
+    if device == "cuda":
+        sys.modules["point_utils_cuda"] = _real_point_utils()
+        sys.modules.update(_gpu_pytorch3d())
+    else:
+        # CPU redirection of the hard-coded device moves
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        torch.cuda.IntTensor = lambda *s: torch.empty(*s, dtype=torch.int32)
+        torch.cuda.FloatTensor = lambda *s: torch.empty(*s, dtype=torch.float32)
+        sys.modules["point_utils_cuda"] = _fake_point_utils()
+        sys.modules.update(_fake_pytorch3d())
+    _loaded_device = device
     # models/__init__.py imports the spconv-based model_v6 (absent here): register a bare package instead
     pkg = types.ModuleType("models")
     pkg.__path__ = [os.path.join(REF, "models")]
@@ -176,9 +232,9 @@ def randomize_bn_(module, gen):
             m.bias.data.copy_(torch.randn(n, generator=gen) * 0.1)
 
 
-def build_reference_hregnet(seed=7, pretrained=True, randomize_bn=True):
+def build_reference_hregnet(seed=7, pretrained=True, randomize_bn=True, device="cpu"):
     """HRegNet(args).eval(): feature extractor from ckpt/pretrained/nusc_feats.pth, registration heads seeded."""
-    ns = load_reference()
+    ns = load_reference(device)
     torch.manual_seed(seed)
     net = ns.HRegNet(Args())
     if pretrained and os.path.isfile(pretrained_feats_path()):
@@ -187,4 +243,4 @@ def build_reference_hregnet(seed=7, pretrained=True, randomize_bn=True):
         g = torch.Generator().manual_seed(seed + 1)
         for name in ("coarse_corres", "fine_corres_2", "fine_corres_1"):
             randomize_bn_(getattr(net, name), g)
-    return net.eval()
+    return net.eval().to(device) if device != "cpu" else net.eval()

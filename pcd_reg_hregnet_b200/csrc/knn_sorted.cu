@@ -174,6 +174,9 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
             const int bx = closest_box();
             top.d[s] = CUDART_INF_F; top.i[s] = 0x7fffffff - (s * 32 + lane);           // "empty", distinct
             if (bx >= 0) box_dist(bx, top.d[s], top.i[s], s * 32 + lane);
+            // the seed enters the set without a comparison: a NaN distance (NaN query or NaN point) would break the
+            // ordering of the set and of the final sort; +inf keeps the member last and comparable
+            if (!(top.d[s] == top.d[s])) top.d[s] = CUDART_INF_F;
         }
         if (K < 32 * KPL) {      // keep the K best of the seed, the other 32*KPL - K positions become dummies
             top.sort_set(lane);

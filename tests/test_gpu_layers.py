@@ -149,7 +149,7 @@ def test_group_attend_equals_separate_kernels():
 POSE_DEG, POSE_M = 1e-4, 1e-5        # BASELINE.json north_star: R|t within 1e-4 deg / 1e-5 m
 
 
-@pytest.mark.parametrize("name", ["hregnet_b2_n2048", "hregnet_uniform_b1_n1500"])
+@pytest.mark.parametrize("name", ["hregnet_b2_n2048", "hregnet_b3_n2048_stable", "hregnet_uniform_b1_n1500"])
 def test_golden_pose_cascade_teacher_forced(name):
     """The pose stages on the UNMODIFIED reference's own intermediate results (tests/golden, models.py:87-127): golden
     keypoints / correspondences / weights of every level -> hrn_weighted_kabsch (+ fused composition with the golden

@@ -129,7 +129,11 @@ def test_bench_reference_arm_json_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the unmodified reference graph (/root/reference here, the staged baseline/_ref on the GPU box);
+    # "port" only where neither exists
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert set(d["config"]) == {"workload", "pairs_per_gpu", "points", "parallelism"}       # the same dict as our arm's
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
