@@ -51,6 +51,12 @@ def test_golden_end_to_end(net, name, precision):
         assert rel_err(f["xyz_1"].cpu(), gd[f"{side}_feats.xyz_1"]) < xyz_tol
         assert rel_err(f["desc_1"].cpu(), gd[f"{side}_feats.desc_1"]) < 1e-3
         assert rel_err(f["sigmas_1"].cpu(), gd[f"{side}_feats.sigmas_1"]) < 1e-3
+    # FREE-RUNNING translation: 1e-5 m is 1-3 ulp of fp32 at LiDAR range (ulp(64..128 m) = 7.6e-6 m),
+    # and here the correspondences themselves come from a different (equally valid) fp32 summation order -- the gate is
+    # 1e-5 m or 3 ulp of the coordinate range, whichever is larger.  The strict 1e-5 m gate is held where it is
+    # meaningful: on identical correspondences (tests/test_gpu_layers.py::test_golden_pose_cascade_teacher_forced).
+    ulp = float(torch.finfo(torch.float32).eps * 2.0 ** torch.floor(torch.log2(gd["src"].abs().max())))
+    tol_m = max(POSE_M, 3 * ulp)
     n_checked, worst = 0, (0.0, 0.0)
     for b in range(B):
         same = all(rel_err(out[f"{s}_feats"][f"xyz_{lv}"][b].cpu(), gd[f"{s}_feats.xyz_{lv}"][b]) < 1e-4
