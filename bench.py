@@ -512,6 +512,13 @@ def _profile_families(reg, steps=3):
             cin, c1, c2, co, cm, cd = {1: (0, 32, 32, 64, 32, 64), 2: (64, 64, 64, 128, 64, 128)}[lv]
             macs = 2 * ((cin + 4) * c1 + c1 * c2 + c2 * co) + 3 * co * cm + cm * cd
             fl = 2.0 * Bc * Mc * kc * macs
+        elif name == "hrn_level_ws":
+            # the reference's algorithmic MACs per neighbour row of the level (incl. the repeated max_k(X1) block of mlp1,
+            # layers.py:203-205, which this kernel evaluates once per keypoint instead of once per neighbour)
+            lv, Bc, Mc, kc = a[0], a[11], a[12], a[14]
+            cin, c = {2: (64, 64), 3: (128, 128)}[lv]
+            macs = 2 * ((cin + 4) * c + c * c + c * 2 * c) + 3 * 2 * c * c + c * 2 * c
+            fl = 2.0 * Bc * Mc * kc * macs
         elif name == "hrn_fps":
             # (M-1)*N distance updates x 9 lane-instructions (3 FADD, FMUL, 2 FFMA, FMNMX, FSETP, SEL)
             Bc, Nc, Mc = a[4], a[5], a[6]
@@ -536,7 +543,7 @@ def _profile_families(reg, steps=3):
         fam[name] = fam.get(name, 0.0) + s.elapsed_time(e) / steps
         flops[name] = flops.get(name, 0.0) + fl / steps
     fam = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
-    layer_names = [n for n in fam if n.startswith("hrn_layer") or n in ("hrn_level_fused", "hrn_chain_tc")]
+    layer_names = [n for n in fam if n.startswith("hrn_layer") or n in ("hrn_level_fused", "hrn_level_ws", "hrn_chain_tc")]
     layer_ms = sum(fam[n] for n in layer_names)
     layer_fl = sum(flops[n] for n in layer_names)
     n_layer = sum(1 for r in rec if r[0] in layer_names) / steps

@@ -172,6 +172,19 @@ int hrn_level_fused(int level, const float* q, const float* xyz, const float* fe
 int hrn_level_pack_bytes(int level);
 int hrn_level_bias_count(int level);
 
+/* Levels 2 and 3 of HierFeatureExtraction (models/HRegNet/models.py:33-34,39-40; level 3: in_channels 128, k = 16,
+ * widths 128/128/256, mlp 768->128->256) as ONE persistent, warp-specialised tcgen05 kernel: same stage as
+ * hrn_level_fused, for the levels whose weights have to stream (K=16 pieces through a cp.async.bulk ring); the next
+ * layer's MMAs are issued block by block while the current accumulator is still being drained, and the reference's
+ * repeated max_k(X1) input of mlp1 (layers.py:203-205) enters as a per-keypoint bias evaluated once per keypoint in fp32.
+ *   Wpack (hrn_level_ws_pack_bytes(level) bytes), WaT [2C, C] fp32 and biases (hrn_level_ws_bias_count(level) floats)
+ *   as laid out by pcd_reg_hregnet_b200/engine_tc.pack_level_ws.  Arguments and outputs as hrn_level_fused. */
+int hrn_level_ws(int level, const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,
+                 const float* WaT, const float* biases, float* out_xyz, float* out_af, float* out_desc, int B, int M,
+                 int N, int k, void* stream);
+int hrn_level_ws_pack_bytes(int level);
+int hrn_level_ws_bias_count(int level);
+
 /* a[g*k+j] = softmax_j( max_c E[g*k+j, c] )   (layers.py:151-152,330-331,385-386,447-448).  k <= 64. */
 int hrn_group_attention(const float* E, int ldE, int C, long long groups, int k, float* a, void* stream);
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp],
     "hrn_layer_tc_groupmax": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_vp],
     "hrn_level_fused": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "hrn_level_ws": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_chain_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                      c_int, c_vp, c_vp, c_ll, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
@@ -83,7 +84,7 @@ def lib():
             f.restype = c_int
         L.hrn_version.restype = ctypes.c_char_p
         L.hrn_version.argtypes = []
-        for name in ("hrn_level_pack_bytes", "hrn_level_bias_count"):
+        for name in ("hrn_level_pack_bytes", "hrn_level_bias_count", "hrn_level_ws_pack_bytes", "hrn_level_ws_bias_count"):
             getattr(L, name).restype = c_int
             getattr(L, name).argtypes = [c_int]
         _lib = L

@@ -30,6 +30,7 @@ def _side_stream(device):
 
 _FUSED_HEADS = True      # tc mode: per-keypoint heads (mlp1/mlp2/mlp3, width <= 256) as one chain launch
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
+_LEVEL_WS = (2, 3)         # tc mode: levels that run on the warp-specialised fused level kernel (csrc/level_ws.cu)
 
 
 def set_precision(mode: str):
@@ -321,6 +322,11 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
     if _PRECISION == "tc" and _FUSED_LEVELS and not want_maps and (B * M * k) % 128 == 0:
         from . import engine_tc
         cin = 0 if feat_cl is None else feat_cl.shape[2]
+        lw = engine_tc.which_level_ws(k, cin, det, desc) if feat_cl is not None else None
+        if lw is not None and lw in _LEVEL_WS:
+            keypoints, af, d = engine_tc.level_ws(lw, q, xyz, feat_cl, idx, det, desc)
+            sig = stack(RowsView(B * M).add(af), det["mlp"], last_act=ACT_SOFTPLUS_EPS)
+            return dict(xyz=keypoints.view(B, M, 3), sigmas=sig.view(B, M), af=af.view(B, M, -1), desc=d.view(B, M, -1))
         lv = engine_tc.which_level(k, cin, det, desc)
         if lv is not None:
             keypoints, af, d = engine_tc.level_fused(lv, q, xyz, feat_cl, idx, det, desc)

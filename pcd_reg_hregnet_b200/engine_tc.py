@@ -162,6 +162,67 @@ def level_fused(level, q, xyz, feat_cl, idx, det, desc):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# warp-specialised fused level kernel (csrc/level_ws.cu): levels 2 and 3
+# ------------------------------------------------------------------------------------------------------------------
+_level_ws_cache = {}
+_LEVEL_WS_DIMS = {2: dict(k=32, cin=64, c=64), 3: dict(k=16, cin=128, c=128)}
+
+
+def which_level_ws(k, cin, det, desc):
+    for lv, d in _LEVEL_WS_DIMS.items():
+        dims = dict(k=d["k"], cin=d["cin"], c1=d["c"], c2=d["c"], co=2 * d["c"], cmid=d["c"], cd=2 * d["c"])
+        if d["k"] == k and d["cin"] == cin and level_supported(dims, det, desc):
+            return lv
+    return None
+
+
+def pack_level_ws(level, det, desc):
+    """Folded parameter dicts of detector_l / desc_extractor_l -> (Wpack uint8, WaT fp32 [2C, C], biases fp32) in the
+    LwCfg layout of csrc/level_ws.cu: K=16 weight pieces of the 8 MMA layers in execution order
+    [d1;x1] d2 d3 mlp1[E*a] x2 x3 mlp1[X1] mlp2; the max_k(X1) block of mlp1 (its first 2C input channels,
+    layers.py:203-205) goes to the CUDA cores as the transposed fp32 matrix WaT.  Grouped input channels re-ordered as in
+    pack_level: [feat(C), rel(3), dist(1), 0-pad]."""
+    key = (level,) + tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
+    hit = _level_ws_cache.get(key)
+    if hit is not None:
+        return hit
+    d = _LEVEL_WS_DIMS[level]
+    C, cin = d["c"], d["cin"]
+    CO = 2 * C
+    (d1, bd1, _), (d2, bd2, _), (d3, bd3, _) = det["convs"]
+    (x1, bx1, _), (x2, bx2, _), (x3, bx3, _) = desc["convs"]
+    (m1, bm1, _), (m2, bm2, _) = desc["mlp"]
+    KG = (cin + 4 + 15) // 16 * 16
+    perm = list(range(4, 4 + cin)) + [0, 1, 2, 3]
+    first = torch.zeros(2 * C, KG, dtype=torch.float32, device=d1.device)
+    first[:, :cin + 4] = torch.cat([d1[:, perm], x1[:, perm]], 0)
+    parts = [_pieces(first, KG), _pieces(d2, C), _pieces(d3, C), _pieces(m1[:, 2 * CO:].contiguous(), CO),
+             _pieces(x2, C), _pieces(x3, C), _pieces(m1[:, CO:2 * CO].contiguous(), CO), _pieces(m2, C)]
+    Wpack = torch.cat(parts).contiguous()
+    WaT = m1[:, :CO].t().contiguous().view(CO // 4, 4, C).permute(0, 2, 1).contiguous()     # [CO/4][C][4]
+    biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()
+    from ._lib import lib
+    assert Wpack.numel() == lib().hrn_level_ws_pack_bytes(level) and biases.numel() == lib().hrn_level_ws_bias_count(level)
+    return _remember(_level_ws_cache, key, d1, (Wpack, WaT, biases))
+
+
+def level_ws(level, q, xyz, feat_cl, idx, det, desc):
+    """q [B,M,3], xyz [B,N,3], feat_cl [B,N,C], idx [B,M,k] int32 -> keypoints [B*M,3], af [B*M,2C], desc [B*M,2C]."""
+    B, M, k = idx.shape
+    N = xyz.shape[1]
+    CO = 2 * _LEVEL_WS_DIMS[level]["c"]
+    Wpack, WaT, biases = pack_level_ws(level, det, desc)
+    dev = xyz.device
+    kp = torch.empty(B * M, 3, dtype=torch.float32, device=dev)
+    af = torch.empty(B * M, CO, dtype=torch.float32, device=dev)
+    ds = torch.empty(B * M, CO, dtype=torch.float32, device=dev)
+    engine.call("hrn_level_ws", level, engine.ptr(q), engine.ptr(xyz), engine.ptr(feat_cl), engine.ptr(idx),
+                engine.ptr(Wpack), engine.ptr(WaT), engine.ptr(biases), engine.ptr(kp), engine.ptr(af), engine.ptr(ds),
+                B, M, N, k, engine.stream())
+    return kp, af, ds
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # three-layer chain kernel (csrc/chain_tc.cu)
 # ------------------------------------------------------------------------------------------------------------------
 EPI_STORE, EPI_GROUPMAX, EPI_ATTN = 0, 1, 2

@@ -59,6 +59,16 @@ def test_feature_levels_teacher_forced(nets, n_points, precision):
             assert rel_err(r["sigmas"].cpu(), want[f"sigmas_{lv}"]) < FEAT_TOL
             assert rel_err(_cl(r["desc"].cpu()), want[f"desc_{lv}"]) < FEAT_TOL
             assert rel_err(_cl(r["af"].cpu()), trace[f"af_{lv}"]) < FEAT_TOL
+            # the same stage through the path the model runs (tc modes: the fused level kernels level_fused.cu /
+            # level_ws.cu; want_maps above forces the layer-by-layer path, which is what exposes idx / E / a)
+            f = engine.detector_descriptor_level(trace[f"in_xyz_{lv}"].to(DEV).contiguous(),
+                                                 _cl(feat).to(DEV) if feat is not None else None,
+                                                 w.to(DEV) if w is not None else None,
+                                                 det.folded(), desc.folded(), det.nsample, det.k)
+            errs = (rel_err(f["xyz"].cpu(), want[f"xyz_{lv}"]), rel_err(f["sigmas"].cpu(), want[f"sigmas_{lv}"]),
+                    rel_err(_cl(f["desc"].cpu()), want[f"desc_{lv}"]), rel_err(_cl(f["af"].cpu()), trace[f"af_{lv}"]))
+            print(f"level {lv} [{precision}, N={n_points}] fused path: xyz {errs[0]:.1e} sigmas {errs[1]:.1e} desc {errs[2]:.1e} af {errs[3]:.1e}")
+            assert errs[0] < xyz_tol and max(errs[1:]) < FEAT_TOL, (lv, errs)
 
 
 def test_coarse_fine_and_pose_teacher_forced(nets):

@@ -22,7 +22,8 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert declared - {"hrn_version", "hrn_level_pack_bytes", "hrn_level_bias_count"} == set(_lib.SIGNATURES), "python binding table out of sync with the header"
+    assert declared - {"hrn_version", "hrn_level_pack_bytes", "hrn_level_bias_count", "hrn_level_ws_pack_bytes",
+                       "hrn_level_ws_bias_count"} == set(_lib.SIGNATURES), "python binding table out of sync with the header"
     assert b"sm_100a" in _lib.lib().hrn_version()
 
 
