@@ -234,9 +234,17 @@ int hrn_cosine_pick(const float* cosm, const float* rowmax, const float* colmax,
  * ------------------------------------------------------------------------------------------------------- */
 
 /* src, cor [B,N,3]; w [B,N] -> R [B,9] row-major, t [B,3].  With R_prev/t_prev also R_cmp = R R_prev,
- * t_cmp = R t_prev + t.  Degenerate covariance -> R = I, t = 0 (the reference's SVD-failure fallback). */
+ * t_cmp = R t_prev + t.  Degenerate covariance -> R = I, t = 0 (the reference's SVD-failure fallback).
+ * pose12 (nullable) [B,12]: the final pose of the call (composed when R_prev is given) as packed rows [R | t] -- the
+ * message of the multi-GPU pose gather. */
 int hrn_weighted_kabsch(const float* src, const float* cor, const float* w, int B, int N, const float* R_prev,
-                        const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, void* stream);
+                        const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, float* pose12, void* stream);
+
+/* RegressionHead (models/model_v2/layers.py:625-668; the pose head of model_v3): w' = w / (sum w + 1e-4); the two weighted
+ * means [sum w' src | sum w' cor] go through two perceptrons 6 -> H1 -> H2 -> n_rot / 3 (ReLU between).  params = 12 device
+ * pointers: {W1,b1,W2,b2,W3,b3} of the rotation branch, then of the translation branch (nn.Linear layout [out,in], fp32). */
+int hrn_regression_head(const float* src, const float* cor, const float* w, int B, int N, const float* const* params,
+                        int H1, int H2, int n_rot, float* rot_out, float* trans_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * 6. Steps around the path: input pipeline in front of it, evaluation metrics behind it

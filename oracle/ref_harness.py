@@ -198,6 +198,33 @@ def load_reference_losses():
     return mod
 
 
+def load_reference_calibeval():
+    """The reference's metrics/calibeval.py, unmodified, as a stand-alone module.  Its imports `config.Config` and
+    `transform.SO3` (a type annotation and an unused member) are satisfied by empty stand-ins; pytorch3d's
+    matrix_to_euler_angles is absent, so the restated conversion of oracle/ref_metrics.py is injected for it (as for the
+    losses) -- the evaluator's own arithmetic, bookkeeping and dictionary layout are the reference's."""
+    import importlib.util
+    from . import ref_metrics
+    load_reference()
+    cfg = types.ModuleType("config"); cfg.Config = object
+    tr = types.ModuleType("transform"); tr.SO3 = lambda *a, **k: None
+    saved = {k: sys.modules.get(k) for k in ("config", "transform")}
+    sys.modules["config"], sys.modules["transform"] = cfg, tr
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_calibeval", os.path.join(REF, "metrics", "calibeval.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    mod.matrix_to_euler_angles = lambda M, convention="XYZ": torch.from_numpy(
+        ref_metrics.matrix_to_euler_angles_xyz(M.detach().cpu().numpy())).to(M.dtype)
+    return mod
+
+
 def load_reference_file(rel_path, name, stubs=()):
     """An unmodified reference source file loaded as a stand-alone module; `stubs` = names of absent third-party modules
     (e.g. open3d) registered as empty modules first -- the functions exercised by the tests do not touch them."""

@@ -14,6 +14,7 @@ Each function cites the reference lines it follows (paths relative to /root/refe
     fine_reg2               models/model_v2/layers.py:464-501
     model_v2_forward        models/model_v2/models.py:77-183
     coarse_reg(want_dists)  models/model_v4/layers.py:237-369 (coord_dist :252, feats_dist :282)
+    regression_head         models/model_v2/layers.py:625-668
     model_v4_forward        models/model_v4/models.py:77-183
 
 Native ops underneath (FPS, gather, kNN) are oracle/native.py.  Pinning: tests/test_oracle_vs_reference.py runs
@@ -261,6 +262,18 @@ def weighted_svd_head(src, cor, weights, dtype=torch.float32):
     R = torch.matmul(V, torch.matmul(Dm, U.transpose(1, 2)))
     t = cm.transpose(1, 2) - torch.matmul(R, sm.transpose(1, 2))
     return R, t.view(-1, 3)
+
+
+def regression_head(sd, p, src, cor, weights):
+    """RegressionHead.forward (models/model_v2/layers.py:636-668) on a state_dict with prefix p."""
+    w = (weights / (weights.sum(dim=1, keepdim=True) + 1e-4)).unsqueeze(2)
+    x = torch.cat([(w * src).sum(dim=1), (w * cor).sum(dim=1)], dim=1)
+    out = []
+    for br in ("rot", "trans"):
+        h = torch.relu(F.linear(x, sd[f"{p}fc1_{br}.weight"], sd[f"{p}fc1_{br}.bias"]))
+        h = torch.relu(F.linear(h, sd[f"{p}fc2_{br}.weight"], sd[f"{p}fc2_{br}.bias"]))
+        out.append(F.linear(h, sd[f"{p}fc3_{br}.weight"], sd[f"{p}fc3_{br}.bias"]))
+    return out[0], out[1]
 
 
 def _compose(Ra, ta, Rb, tb):

@@ -7,6 +7,7 @@ Follows (reference file:line):
   calc_tran_rte_err        losses/losses.py:154-164
   geodesic_distance        metrics/calibeval.py:172-196
   add_batch error          metrics/calibeval.py:83-84 (error = pred_tf.bmm(gt_tf))
+  calib_eval_results       metrics/calibeval.py:72-164, 45-70 (CalibEval.add_batch / get_stats / getSD / get_results)
 
 Pinned against the unmodified reference functions run on CPU by tests/test_oracle_vs_reference.py (calc_error_np directly;
 calc_rot_rre_err / calc_tran_rte_err with the Euler conversion below injected for the absent pytorch3d).
@@ -48,3 +49,25 @@ def calib_error(gt_tf, pred_tf):
     """error = pred_tf @ gt_tf; -> (geodesic degrees [B], translation norm [B])."""
     err = np.asarray(pred_tf, np.float64) @ np.asarray(gt_tf, np.float64)
     return _geo_deg(err[:, :3, :3]), np.linalg.norm(err[:, :3, 3], axis=1)
+
+
+def calib_eval_results(batches):
+    """CalibEval over `batches` = [(gt_tf [B,4,4], pred_tf [B,4,4]), ...] -> the dictionary of CalibEval.get_results
+    (metrics/calibeval.py:45-70): per-sample Euler XYZ angles (degrees) / translations of error = pred_tf . gt_tf and of the
+    prediction, per-BATCH mean geodesic / Euclidean distances, their |.| means and standard deviations.  The reference
+    unpacks getSD() as `sd_t, sd_r, ...` although it returns (rotation, translation, ...) (:50 vs :152-164): "sd" therefore
+    lists the translation deviations first, and so does this restatement."""
+    loss_r, loss_t, pred, geo = [], [], [], []
+    for gt_tf, pred_tf in batches:
+        gt_tf, pred_tf = np.asarray(gt_tf, np.float64), np.asarray(pred_tf, np.float64)
+        err = pred_tf @ gt_tf
+        loss_r.append(np.degrees(matrix_to_euler_angles_xyz(err[:, :3, :3])))
+        loss_t.append(err[:, :3, 3])
+        pred.append(np.concatenate([np.degrees(matrix_to_euler_angles_xyz(pred_tf[:, :3, :3])), pred_tf[:, :3, 3]], 1))
+        geo.append([_geo_deg(err[:, :3, :3]).mean(), np.linalg.norm(err[:, :3, 3], axis=1).mean()])
+    loss_r, loss_t, pred, geo = np.concatenate(loss_r), np.concatenate(loss_t), np.concatenate(pred), np.asarray(geo)
+    r, t, g = np.abs(loss_r).mean(0), np.abs(loss_t).mean(0), geo.mean(0)
+    sd_t, sd_r, sd_dR, sd_dT = np.abs(loss_r).std(0), np.abs(loss_t).std(0), np.abs(geo[:, 0]).std(0), np.abs(geo[:, 1]).std(0)
+    return {"pred_calib": pred.tolist(), "error_calib": np.concatenate((loss_r, loss_t), 1).tolist(),
+            "mean_error": sum([r.tolist(), t.tolist(), g.tolist()], []), "sd": sum([sd_r.tolist(), sd_t.tolist()], []),
+            "mean_sd": [float(np.mean(sd_r)), float(np.mean(sd_t))], "mean_sd_dRT": [float(np.mean(sd_dR)), float(np.mean(sd_dT))]}

@@ -57,7 +57,8 @@ SIGNATURES = {
     "hrn_transform_points": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
     "hrn_cosine_matrix": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_cosine_pick": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
-    "hrn_weighted_kabsch": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "hrn_weighted_kabsch": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "hrn_regression_head": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "hrn_range_filter": [c_vp, c_vp, c_vp, c_int, c_ll, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_se3_exp": [c_vp, c_int, c_vp, c_vp],
     "hrn_resample_gather": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],

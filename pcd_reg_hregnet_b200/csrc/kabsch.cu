@@ -114,7 +114,7 @@ __host__ __device__ inline void pose_from_covariance(const double* H9, const dou
 __global__ void __launch_bounds__(256)
 kabsch_kernel(const float* __restrict__ src, const float* __restrict__ cor, const float* __restrict__ w, int N,
               const float* __restrict__ R_prev, const float* __restrict__ t_prev, float* __restrict__ R_out,
-              float* __restrict__ t_out, float* __restrict__ R_cmp, float* __restrict__ t_cmp) {
+              float* __restrict__ t_out, float* __restrict__ R_cmp, float* __restrict__ t_cmp, float* __restrict__ pose12) {
     __shared__ double s_red[8 * 9];
     const int b = blockIdx.x;
     src += (size_t)b * N * 3; cor += (size_t)b * N * 3; w += (size_t)b * N;
@@ -174,18 +174,26 @@ kabsch_kernel(const float* __restrict__ src, const float* __restrict__ cor, cons
             t_cmp[b * 3 + i] = fmaf(Rf[i * 3 + 2], tp[2], fmaf(Rf[i * 3 + 1], tp[1], Rf[i * 3] * tp[0])) + tf[i];
         }
     }
+    if (pose12) {  // the final pose of this call (composed when a previous pose is given) as one [R | t] row: the message
+                   // of the multi-GPU pose gather, written here so that no packing kernel runs in front of the collective
+        const float* Rs = R_cmp ? R_cmp + b * 9 : R_out + b * 9;
+        const float* ts = R_cmp ? t_cmp + b * 3 : t_out + b * 3;
+        for (int i = 0; i < 9; ++i) pose12[b * 12 + i] = Rs[i];
+        for (int i = 0; i < 3; ++i) pose12[b * 12 + 9 + i] = ts[i];
+    }
 }
 
 }  // namespace
 
 // src, cor [B,N,3]; w [B,N] -> R [B,9] row-major, t [B,3].  If R_prev/t_prev are given, also the composed pose
-// R_cmp = R R_prev, t_cmp = R t_prev + t.
+// R_cmp = R R_prev, t_cmp = R t_prev + t.  pose12 (nullable) [B,12]: the final pose of the call as packed rows [R | t].
 HRN_API int hrn_weighted_kabsch(const float* src, const float* cor, const float* w, int B, int N, const float* R_prev,
-                                const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, void* stream) {
+                                const float* t_prev, float* R, float* t, float* R_cmp, float* t_cmp, float* pose12,
+                                void* stream) {
     if (!src || !cor || !w || !R || !t || B < 0 || N <= 0) return HRN_ERR_BAD_ARG;
     if ((R_cmp || t_cmp) && !(R_prev && t_prev && R_cmp && t_cmp)) return HRN_ERR_BAD_ARG;
     if (B == 0) return HRN_OK;
-    kabsch_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(src, cor, w, N, R_prev, t_prev, R, t, R_cmp, t_cmp);
+    kabsch_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(src, cor, w, N, R_prev, t_prev, R, t, R_cmp, t_cmp, pose12);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
@@ -197,5 +205,92 @@ HRN_API int hrn_pose_from_covariance_host(const double* H9, const double* xbar, 
     double R[3][3], tt[3];
     pose_from_covariance(H9, xbar, ybar, R, tt);
     for (int i = 0; i < 3; ++i) { t3[i] = tt[i]; for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R[i][j]; }
+    return HRN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RegressionHead (reference models/model_v2/layers.py:625-668, used by model_v3): the pose is REGRESSED from the two
+// weighted means instead of solved -- w' = w / (sum w + 1e-4); x = [sum w' src | sum w' cor] (6 values);
+// rotation = fc3_rot(relu(fc2_rot(relu(fc1_rot(x))))), translation likewise through the *_trans layers.  One CTA per
+// pair: the means (fp64 sums of the fp32 products), then both three-layer perceptrons from shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct RegMlp {
+    const float *W1, *b1, *W2, *b2, *W3, *b3;      // nn.Linear layout [out, in]
+};
+
+__global__ void __launch_bounds__(128)
+regression_head_kernel(const float* __restrict__ src, const float* __restrict__ cor, const float* __restrict__ w, int N,
+                       RegMlp rot, RegMlp trn, int H1, int H2, int n_rot, float* __restrict__ rot_out,
+                       float* __restrict__ trans_out) {
+    __shared__ double s_red[4][7];
+    __shared__ float s_x[6], s_h1[2][256], s_h2[2][256];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* sp = src + (size_t)b * N * 3;
+    const float* cp = cor + (size_t)b * N * 3;
+    const float* wp = w + (size_t)b * N;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < N; i += blockDim.x) acc[6] += (double)wp[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[6] += __shfl_xor_sync(0xffffffffu, acc[6], o);
+    if (lane == 0) s_red[warp][6] = acc[6];
+    __syncthreads();
+    const float wsum = (float)(s_red[0][6] + s_red[1][6] + s_red[2][6] + s_red[3][6]) + 1e-4f;   // layers.py:648
+    for (int i = tid; i < N; i += blockDim.x) {
+        const float wn = wp[i] / wsum;                                                            // layers.py:649
+        acc[0] += (double)(wn * sp[3 * i]); acc[1] += (double)(wn * sp[3 * i + 1]); acc[2] += (double)(wn * sp[3 * i + 2]);
+        acc[3] += (double)(wn * cp[3 * i]); acc[4] += (double)(wn * cp[3 * i + 1]); acc[5] += (double)(wn * cp[3 * i + 2]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == 0) s_red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < 6) s_x[tid] = (float)(s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid]);
+    __syncthreads();
+    for (int j = tid; j < 2 * H1; j += blockDim.x) {                 // fc1 of both branches
+        const RegMlp& m = j < H1 ? rot : trn;
+        const int o = j < H1 ? j : j - H1;
+        float v = m.b1[o];
+        for (int k = 0; k < 6; ++k) v = fmaf(m.W1[o * 6 + k], s_x[k], v);
+        s_h1[j < H1 ? 0 : 1][o] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    for (int j = tid; j < 2 * H2; j += blockDim.x) {                 // fc2
+        const int br = j < H2 ? 0 : 1;
+        const RegMlp& m = br ? trn : rot;
+        const int o = br ? j - H2 : j;
+        float v = m.b2[o];
+        for (int k = 0; k < H1; ++k) v = fmaf(m.W2[o * H1 + k], s_h1[br][k], v);
+        s_h2[br][o] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    if (tid < n_rot + 3) {                                           // fc3
+        const int br = tid < n_rot ? 0 : 1;
+        const RegMlp& m = br ? trn : rot;
+        const int o = br ? tid - n_rot : tid;
+        float v = m.b3[o];
+        for (int k = 0; k < H2; ++k) v = fmaf(m.W3[o * H2 + k], s_h2[br][k], v);
+        if (br) trans_out[b * 3 + o] = v; else rot_out[b * n_rot + o] = v;
+    }
+}
+
+}  // namespace
+
+// src, cor [B,N,3]; w [B,N]; params = 12 device pointers {W1,b1,W2,b2,W3,b3} of the rotation branch then of the translation
+// branch (nn.Linear layout, fp32): 6 -> H1 -> H2 -> n_rot / 3 (H1, H2 <= 256).  rot_out [B,n_rot], trans_out [B,3].
+HRN_API int hrn_regression_head(const float* src, const float* cor, const float* w, int B, int N, const float* const* params,
+                                int H1, int H2, int n_rot, float* rot_out, float* trans_out, void* stream) {
+    if (!src || !cor || !w || !params || !rot_out || !trans_out || B < 0 || N <= 0) return HRN_ERR_BAD_ARG;
+    for (int i = 0; i < 12; ++i) if (!params[i]) return HRN_ERR_BAD_ARG;
+    if (H1 <= 0 || H2 <= 0 || H1 > 256 || H2 > 256 || n_rot <= 0 || n_rot > 9) return HRN_ERR_UNSUPPORTED;
+    if (B == 0) return HRN_OK;
+    RegMlp r{params[0], params[1], params[2], params[3], params[4], params[5]};
+    RegMlp t{params[6], params[7], params[8], params[9], params[10], params[11]};
+    regression_head_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(src, cor, w, N, r, t, H1, H2, n_rot, rot_out, trans_out);
+    HRN_LAUNCH_CHECK();
     return HRN_OK;
 }

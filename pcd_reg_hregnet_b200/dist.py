@@ -25,7 +25,10 @@ def gather_poses(R, t, n_pairs=None, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return R, t
     world = dist.get_world_size(group)
-    local = pack_pose(R, t)
+    # the pose kernel of the model path leaves the packed rows next to R (engine.weighted_kabsch(packed=True))
+    local = getattr(R, "hrn_pose12", None)
+    if local is None:
+        local = pack_pose(R, t)
     if n_pairs is None or n_pairs % world == 0:
         out = torch.empty(world * local.shape[0], 12, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local, group=group)

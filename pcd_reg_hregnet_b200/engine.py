@@ -275,17 +275,24 @@ def transform_points(x, R, t):
     return out
 
 
-def weighted_kabsch(src, cor, w, prev=None):
-    """-> (R [B,3,3], t [B,3]) and, with prev=(R_prev, t_prev), also the composed (R_c, t_c)."""
+def weighted_kabsch(src, cor, w, prev=None, packed=False):
+    """-> (R [B,3,3], t [B,3]) and, with prev=(R_prev, t_prev), also the composed (R_c, t_c).
+    packed=True: the final pose is also written as rows [R | t] of a [B,12] tensor attached to the returned final
+    rotation as `.hrn_pose12` -- what dist.gather_poses sends, so no packing kernel runs in front of the collective."""
     B, N, _ = src.shape
     R = torch.empty(B, 3, 3, dtype=torch.float32, device=src.device)
     t = torch.empty(B, 3, dtype=torch.float32, device=src.device)
+    p12 = torch.empty(B, 12, dtype=torch.float32, device=src.device) if packed else None
     if prev is None:
-        call("hrn_weighted_kabsch", ptr(src), ptr(cor), ptr(w), B, N, None, None, ptr(R), ptr(t), None, None, stream())
+        call("hrn_weighted_kabsch", ptr(src), ptr(cor), ptr(w), B, N, None, None, ptr(R), ptr(t), None, None, ptr(p12), stream())
+        if packed:
+            R.hrn_pose12 = p12
         return R, t
     Rc, tc = torch.empty_like(R), torch.empty_like(t)
     call("hrn_weighted_kabsch", ptr(src), ptr(cor), ptr(w), B, N, ptr(prev[0]), ptr(prev[1]), ptr(R), ptr(t), ptr(Rc),
-         ptr(tc), stream())
+         ptr(tc), ptr(p12), stream())
+    if packed:
+        Rc.hrn_pose12 = p12
     return R, t, Rc, tc
 
 

@@ -84,3 +84,110 @@ class PoseErrorMeter:
     def result(self):
         m = (self.sums / max(self.count, 1)).tolist()
         return dict(geodesic_deg=m[0], translation=m[1], euler_abs_deg=m[2:5], t_abs=m[5:8], count=self.count)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's evaluators, same class names / methods / result dictionaries (metrics/calibeval.py:11-337, 344-380)
+# ------------------------------------------------------------------------------------------------------------------
+class CalibEval:
+    """Reference: metrics/calibeval.py:11-337.  add_batch(gt_tf [B,4,4], pred_tf [B,4,4]) accumulates, per sample, the Euler
+    XYZ angles (degrees) and translation of the error transform pred_tf . gt_tf and of the prediction, and per batch the
+    mean geodesic / Euclidean distance -- everything stays on the device (one kernel launch per batch, no .cpu() sync);
+    get_stats / getSD / get_results / save_results produce the reference's numbers, keys and JSON layout."""
+
+    def __init__(self, config=None, translation_threshold=None, rotation_threshold=None):
+        self.config = config
+        self.translation_threshold = translation_threshold
+        self.rotation_threshold = rotation_threshold
+        self.reset()
+
+    def reset(self):
+        self._err_euler, self._err_trans, self._pred, self._geo = [], [], [], []
+        self.success_idx = []                  # the reference never fills it (its threshold code is commented out, :103-106)
+        self.results = {}
+
+    def add_batch(self, gt_tf, pred_tf, idx=None, return_results=False):
+        B = gt_tf.shape[0]
+        pR, pt = pred_tf[:, :3, :3], pred_tf[:, :3, 3]
+        geo, eucl, e_euler, e_t = pose_errors(pR, pt, gt_tf[:, :3, :3], gt_tf[:, :3, 3], mode=1)
+        eye = torch.eye(3, device=gt_tf.device).expand(B, 3, 3)
+        z = torch.zeros(B, 3, device=gt_tf.device)
+        _, _, p_euler, _ = pose_errors(eye, z, pR, z)                   # R_err = I^T pred_R: Euler angles of the prediction
+        self._err_euler.append(e_euler)
+        self._err_trans.append(e_t)
+        self._pred.append(torch.cat([p_euler, pt.reshape(B, 3).float()], dim=1))
+        self._geo.append(torch.stack([geo.mean(), eucl.mean()]))       # per batch, like the reference (:99, :196)
+
+    # -- host side: one read-back ------------------------------------------------------------------------------------
+    def _host(self):
+        import numpy as np
+        if not self._err_euler:
+            raise ValueError("no batches added")
+        loss_r = torch.cat(self._err_euler).double().cpu().numpy()
+        loss_t = torch.cat(self._err_trans).double().cpu().numpy()
+        pred = torch.cat(self._pred).double().cpu().numpy()
+        geo = torch.stack(self._geo).double().cpu().numpy()
+        return np, loss_r, loss_t, pred, geo
+
+    def get_stats(self):
+        np, loss_r, loss_t, _, geo = self._host()
+        return np.abs(loss_r).mean(axis=0), np.abs(loss_t).mean(axis=0), geo.mean(axis=0)
+
+    def getSD(self):
+        np, loss_r, loss_t, _, geo = self._host()
+        return np.abs(loss_r).std(axis=0), np.abs(loss_t).std(axis=0), np.abs(geo[:, 0]).std(axis=0), np.abs(geo[:, 1]).std(axis=0)
+
+    def compute_recall(self):
+        n = sum(int(t.shape[0]) for t in self._err_euler)
+        return len(self.success_idx) / n if n else 0.0
+
+    def get_results(self):
+        np, loss_r, loss_t, pred, _ = self._host()
+        r, t, g = self.get_stats()
+        sd_t, sd_r, sd_dR, sd_dT = self.getSD()        # the reference unpacks getSD() in this order (calibeval.py:50, :295)
+        self.results = {
+            "pred_calib": pred.tolist(),
+            "error_calib": np.concatenate((loss_r, loss_t), axis=1).tolist(),
+            "mean_error": sum([r.tolist(), t.tolist(), g.tolist()], []),
+            "sd": sum([sd_r.tolist(), sd_t.tolist()], []),
+            "mean_sd": [np.mean(sd_r).tolist(), np.mean(sd_t).tolist()],
+            "mean_sd_dRT": [np.mean(sd_dR).tolist(), np.mean(sd_dT).tolist()],
+        }
+        return self.results
+
+    def save_results(self):
+        import json
+        import os
+        self.get_results()
+        dc = self.config.dataset_config
+        name = "results_" + "_" + self.config.dataset + "_" + dc.distribution + "_" + str(dc.max_rot_error) + "_" + \
+            str(dc.max_trans_error) + ".json"                             # calibeval.py:321-327
+        with open(os.path.join(dc.results_path, name), "w") as f:
+            json.dump(self.results, f, indent=4)
+
+
+class MultiLayerCalibEval:
+    """Reference: metrics/calibeval.py:344-380 -- one CalibEval per pose level, one combined JSON file."""
+
+    def __init__(self, config=None, num_layers=3, translation_threshold=None, rotation_threshold=None):
+        self.config = config
+        self.num_layers = num_layers
+        self.evaluators = {layer: CalibEval(config, translation_threshold, rotation_threshold) for layer in range(num_layers)}
+
+    def reset(self):
+        for ev in self.evaluators.values():
+            ev.reset()
+
+    def add_batch(self, layer, gt_tf, pred_tf, idx=None, return_results=False):
+        if layer not in self.evaluators:
+            raise ValueError(f"Layer {layer} is not valid. Valid layers: 0 to {self.num_layers - 1}.")
+        self.evaluators[layer].add_batch(gt_tf, pred_tf, idx, return_results)
+
+    def save_all_results(self, output_file):
+        import json
+        combined = {f"layer_{layer}": ev.get_results() for layer, ev in self.evaluators.items()}
+        dc = self.config.dataset_config
+        combined.update({"dataset": self.config.dataset + dc.version, "model": dc.model, "translation": dc.max_trans_error,
+                         "rotation": dc.max_rot_error, "distribution": dc.distribution})
+        with open(output_file, "w") as f:
+            json.dump(combined, f, indent=4)

@@ -75,6 +75,61 @@ class FineReg2(FineReg):
                                src_weights.contiguous(), dst_weights.contiguous())
 
 
+class RegressionHead(nn.Module):
+    """Reference: model_v2/layers.py:625-668 (the pose head of model_v3): the pose is regressed from the two weighted means.
+    forward(src [B,N,3], src_corres [B,N,3], weights [B,N]) -> (rotation [B,3], translation [B,3]).  Same parameter names
+    / shapes (fc{1,2,3}_{rot,trans}); one kernel launch (csrc/kabsch.cu: hrn_regression_head)."""
+    DIMS = (128, 64, 3)
+
+    def __init__(self):
+        super().__init__()
+        h1, h2, n_rot = self.DIMS
+        self.fc1_rot, self.fc2_rot, self.fc3_rot = nn.Linear(6, h1), nn.Linear(h1, h2), nn.Linear(h2, n_rot)
+        self.fc1_trans, self.fc2_trans, self.fc3_trans = nn.Linear(6, h1), nn.Linear(h1, h2), nn.Linear(h2, 3)
+
+    def _regress(self, src, src_corres, weights):
+        import ctypes
+        h1, h2, n_rot = self.DIMS
+        B, N, _ = src.shape
+        ps = [p.detach() for fc in (self.fc1_rot, self.fc2_rot, self.fc3_rot, self.fc1_trans, self.fc2_trans, self.fc3_trans)
+              for p in (fc.weight, fc.bias)]
+        arr = (ctypes.c_void_p * 12)(*[engine.ptr(p) for p in ps])
+        rot = torch.empty(B, n_rot, dtype=torch.float32, device=src.device)
+        trans = torch.empty(B, 3, dtype=torch.float32, device=src.device)
+        engine.call("hrn_regression_head", engine.ptr(src.contiguous()), engine.ptr(src_corres.contiguous()),
+                    engine.ptr(weights.contiguous()), B, N, arr, h1, h2, n_rot, engine.ptr(rot), engine.ptr(trans), engine.stream())
+        return rot, trans
+
+    def forward(self, src, src_corres, weights):
+        return self._regress(src, src_corres, weights)
+
+
+class Regression_6dR_3dt_Head(RegressionHead):
+    """Reference: model_v2/layers.py:555-623.  As shipped, the reference's translation branch cannot run: `fc3_trans` is
+    Linear(64, 3) but receives the 32 outputs of `fc2_trans` (layers.py:566 vs :595-596), so its forward raises in
+    F.linear.  The constructor (parameter names and shapes, the mismatch included, so checkpoints load) and that error
+    behaviour are kept; `compute_rotation_matrix_from_6d` (layers.py:605-622) is provided on the device."""
+    DIMS = (64, 32, 6)
+
+    def __init__(self):
+        super().__init__()
+        self.fc3_trans = nn.Linear(64, 3)            # sic (layers.py:566)
+
+    def forward(self, src, src_corres, weights):
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx32 and 64x3): the reference's "
+                           "Regression_6dR_3dt_Head.fc3_trans expects 64 inputs (model_v2/layers.py:566,596)" % src.shape[0])
+
+    @staticmethod
+    def compute_rotation_matrix_from_6d(x):
+        b = x.view(x.shape[0], 3, 2)
+
+        def l2n(v):
+            return v / (torch.sqrt(torch.sum(v ** 2, dim=1, keepdim=True)) + 1e-6)
+        b1 = l2n(b[:, :, 0])
+        b2 = l2n(b[:, :, 1] - b1 * torch.sum(b1 * b[:, :, 1], dim=1, keepdim=True))
+        return torch.stack([b1, b2, torch.cross(b1, b2, dim=1)], dim=-1)
+
+
 class Model_V2(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -112,7 +167,7 @@ class Model_V2(nn.Module):
         xyz1_t = engine.transform_points(S["xyz_1"], R2, t2)
         cor1, w1 = self.fine_corres_1.forward_cl(xyz1_t, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"],
                                                  D["sigmas_1"])
-        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2))
+        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2), packed=True)
 
         def api(d):
             return {k: (engine.transpose(v) if k.startswith("desc_") else v) for k, v in d.items()}

@@ -63,7 +63,7 @@ class Model_V4(nn.Module):
         xyz1_t = engine.transform_points(S["xyz_1"], R2, t2)
         cor1, w1 = self.fine_corres_1.forward_cl(xyz1_t, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"],
                                                  D["sigmas_1"])
-        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2))
+        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2), packed=True)
         return {
             "rotation": [R3, R2, R1], "translation": [t3, t2, t1],
             "src_feats_desc_2": engine.transpose(S["desc_2"]), "src_feats_sigmas_2": S["sigmas_2"],

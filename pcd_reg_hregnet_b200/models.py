@@ -96,7 +96,7 @@ class HRegNet(nn.Module):
         xyz1_t = engine.transform_points(S["xyz_1"], R2, t2)
         cor1, w1 = self.fine_corres_1.forward_cl(xyz1_t, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"],
                                                  D["sigmas_1"])
-        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2))
+        _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2), packed=True)
 
         def api(d):
             return {k: (engine.transpose(v) if k.startswith("desc_") else v) for k, v in d.items()}

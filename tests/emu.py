@@ -154,7 +154,7 @@ def _cosine_pick(cosm, rowmax, colmax, idx, B, N1, N2, k, out, ldo, c_sd, c_ds, 
     o[..., c_ds] = c / (rowmax[b, i] + 1e-6)
 
 
-def _weighted_kabsch(src, cor, w, B, N, Rp, tp, R, t, Rc, tc, st):
+def _weighted_kabsch(src, cor, w, B, N, Rp, tp, R, t, Rc, tc, p12, st):
     """fp64 sums + the library's own host closed form (hrn_pose_from_covariance_host)."""
     L = _lib.lib()
     for b in range(B):
@@ -173,6 +173,9 @@ def _weighted_kabsch(src, cor, w, B, N, Rp, tp, R, t, Rc, tc, st):
         if Rc is not None:
             Rc[b] = R[b] @ Rp[b]
             tc[b] = R[b] @ tp[b] + t[b]
+        if p12 is not None:
+            p12[b, :9] = (Rc if Rc is not None else R)[b].reshape(9)
+            p12[b, 9:] = (tc if tc is not None else t)[b]
 
 
 _TABLE = {

@@ -3,6 +3,7 @@ oracle/ref_harness.py (native ops = oracle C restatements).  Run in the build co
 
     python tests/golden/make_golden.py            # model fixtures
     python tests/golden/make_golden.py metrics    # pose_metrics.npz only
+    python tests/golden/make_golden.py calib      # calib_eval.json only (the reference's MultiLayerCalibEval JSON)
     python tests/golden/make_golden.py preprocess # preprocess.npz only
     python tests/golden/make_golden.py variants   # model_v2_b2_n2048.npz, model_v4_b2_n2048.npz only
 
@@ -118,6 +119,48 @@ def pose_metrics_golden():
     print("pose_metrics.npz written")
 
 
+def random_transforms(B, seed):
+    R, t = random_poses(B, seed)
+    T = torch.eye(4).repeat(B, 1, 1)
+    T[:, :3, :3], T[:, :3, 3] = R, t
+    return T
+
+
+def calib_eval_golden():
+    """The reference's own MultiLayerCalibEval (metrics/calibeval.py:344-380) fed 3 layers x 3 batches of seeded transforms:
+    the JSON file it writes, next to the inputs' seeds (tests rebuild the inputs with random_transforms)."""
+    import json
+    import types
+    CE = H.load_reference_calibeval()
+    cfg = types.SimpleNamespace(dataset="synthetic", dataset_config=types.SimpleNamespace(
+        version="_v0", model="HRegNet", max_trans_error=0.5, max_rot_error=20.0, distribution="uniform", results_path=OUT))
+    ev = CE.MultiLayerCalibEval(cfg, num_layers=3)
+    for layer in range(3):
+        for bi, B in enumerate((5, 8, 3)):
+            ev.add_batch(layer, random_transforms(B, 100 + 10 * layer + bi), random_transforms(B, 200 + 10 * layer + bi))
+    path = os.path.join(OUT, "calib_eval.json")
+    ev.save_all_results(path)
+    print("calib_eval.json written", os.path.getsize(path))
+
+
+def regression_head_golden():
+    """The reference's RegressionHead (models/model_v2/layers.py:625-668; torch.manual_seed(11) default initialisation) on
+    seeded correspondences: inputs, parameters and outputs."""
+    L2 = H.load_reference().layers_v2
+    torch.manual_seed(11)
+    head = L2.RegressionHead().eval()
+    g = torch.Generator().manual_seed(12)
+    src = (torch.rand(4, 256, 3, generator=g) * 2 - 1) * torch.tensor([40.0, 40.0, 3.0])
+    cor = src + 0.3 * torch.randn(4, 256, 3, generator=g)
+    w = torch.rand(4, 256, generator=g)
+    with torch.no_grad():
+        rot, trans = head(src, cor, w)
+    d = {"src": src.numpy(), "cor": cor.numpy(), "w": w.numpy(), "rotation": rot.numpy(), "translation": trans.numpy()}
+    d.update({"sd." + k: v.numpy() for k, v in head.state_dict().items()})
+    np.savez_compressed(os.path.join(OUT, "regression_head.npz"), **d)
+    print("regression_head.npz written", sorted(k for k in d if k.startswith("sd.")))
+
+
 def preprocess_golden():
     """Outputs of the reference's own PointCloudFilter.remove_points_by_range, PointCloudResampler (seeded numpy RNG; the
     drawn index lists are stored) and SE3.exp (dataset/dataset_utils.py:113-125,177-223, transform/rodrigues.py:526-550)."""
@@ -171,6 +214,12 @@ def variants_golden():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         variants_golden()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "reghead":
+        regression_head_golden()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "calib":
+        calib_eval_golden()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         pose_metrics_golden()

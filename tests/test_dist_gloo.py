@@ -22,6 +22,9 @@ def _worker(rank, world, port, n_pairs, q):
     ids = torch.arange(lo, hi, dtype=torch.float32)
     R = ids[:, None, None] + torch.arange(9, dtype=torch.float32).view(1, 3, 3)     # pose "of pair id"
     t = ids[:, None] * 10 + torch.arange(3, dtype=torch.float32)
+    if n_pairs % world == 0 and rank == 0:
+        # the model path: the pose kernel left the packed [R | t] rows next to R -- the gather sends those as they are
+        R.hrn_pose12 = hd.pack_pose(R, t)
     Rg, tg = hd.gather_poses(R, t, n_pairs=n_pairs)
     q.put((rank, Rg.clone(), tg.clone()))
     dist.barrier()

@@ -43,6 +43,45 @@ def test_metrics_oracle_reproduces_reference_outputs():
     assert np.abs(eucl - g["eucl"]).max() < 1e-6 and np.abs(T_err_mean - g["T_err_mean"]).max() < 1e-6
 
 
+def _calib_inputs():
+    """The seeded transforms tests/golden/make_golden.py::calib_eval_golden fed to the reference's MultiLayerCalibEval."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("_mk", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    return {layer: [(mk.random_transforms(B, 100 + 10 * layer + bi), mk.random_transforms(B, 200 + 10 * layer + bi))
+                    for bi, B in enumerate((5, 8, 3))] for layer in range(3)}
+
+
+def test_calib_eval_oracle_reproduces_reference_json():
+    """oracle/ref_metrics.calib_eval_results against tests/golden/calib_eval.json = the file the reference's own
+    MultiLayerCalibEval.save_all_results wrote (metrics/calibeval.py:367-380): same keys, numbers within fp32 rounding."""
+    import json
+    import os
+    import numpy as np
+    from oracle import ref_metrics as RM
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "calib_eval.json")))
+    assert {"dataset", "model", "translation", "rotation", "distribution", "layer_0", "layer_1", "layer_2"} == set(gold)
+    for layer, batches in _calib_inputs().items():
+        got = RM.calib_eval_results([(g.numpy(), p.numpy()) for g, p in batches])
+        want = gold[f"layer_{layer}"]
+        assert list(got) == list(want)                                       # same keys, same order
+        for k in want:
+            tol = 2e-3 if k in ("pred_calib", "error_calib", "mean_error", "sd", "mean_sd", "mean_sd_dRT") else 0
+            assert np.abs(np.asarray(got[k]) - np.asarray(want[k])).max() < tol, (layer, k)
+
+
+def test_regression_head_oracle_reproduces_reference_outputs():
+    """oracle/ref_layers.regression_head against tests/golden/regression_head.npz = the reference's RegressionHead
+    (models/model_v2/layers.py:625-668)."""
+    from oracle import ref_layers as RL
+    g = load_golden("regression_head")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    rot, trans = RL.regression_head(sd, "", g["src"], g["cor"], g["w"])
+    assert float((rot - g["rotation"]).abs().max()) < 1e-6 and float((trans - g["translation"]).abs().max()) < 1e-6
+
+
 def test_preprocess_oracle_reproduces_reference_outputs():
     """oracle/ref_preprocess.py against tests/golden/preprocess.npz (reference PointCloudFilter / PointCloudResampler /
     SE3.exp outputs): kept sets and resampled clouds bit-identical, SE3.exp within fp32 rounding."""

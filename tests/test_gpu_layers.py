@@ -117,6 +117,11 @@ def test_pose_head_tolerance(nets, N):
     Rp, tp = R_gt, t_gt
     _, _, Rc, tc = engine.weighted_kabsch(src.to(DEV), cor.to(DEV), w.to(DEV), prev=(Rp.to(DEV), tp.to(DEV)))
     assert torch.allclose(Rc.cpu(), R @ Rp, atol=1e-6) and torch.allclose(tc.cpu(), (R @ tp[:, :, None])[:, :, 0] + t, atol=1e-5)
+    # packed rows [R | t] of the final pose (the message of the multi-GPU pose gather), written by the same kernel
+    _, _, Rc2, tc2 = engine.weighted_kabsch(src.to(DEV), cor.to(DEV), w.to(DEV), prev=(Rp.to(DEV), tp.to(DEV)), packed=True)
+    assert torch.equal(Rc2.hrn_pose12[:, :9].reshape(B, 3, 3), Rc2) and torch.equal(Rc2.hrn_pose12[:, 9:], tc2) and torch.equal(Rc2, Rc)
+    R3, t3 = engine.weighted_kabsch(src.to(DEV), cor.to(DEV), w.to(DEV), packed=True)
+    assert torch.equal(R3.hrn_pose12[:, :9].reshape(B, 3, 3), R3) and torch.equal(R3.hrn_pose12[:, 9:], t3)
 
 
 def test_pose_head_recovers_exact_transform(nets):
@@ -333,3 +338,27 @@ def test_knn_nan_point_does_not_fault():
         out = net(src.to(DEV), dst.to(DEV))
     torch.cuda.synchronize()
     assert out["rotation"][-1].shape == (1, 3, 3)
+
+
+def test_regression_heads():
+    """models/model_v2/layers.py:555-668: RegressionHead on the device against the reference's golden outputs (and the
+    oracle), same state_dict keys; Regression_6dR_3dt_Head keeps the reference's parameter shapes and its error."""
+    from pcd_reg_hregnet_b200.model_v2 import Regression_6dR_3dt_Head, RegressionHead
+    g = load_golden("regression_head")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    head = RegressionHead()
+    assert set(head.state_dict()) == set(sd)
+    head.load_state_dict(sd)
+    head = head.eval().to(DEV)
+    rot, trans = head(g["src"].to(DEV), g["cor"].to(DEV), g["w"].to(DEV))
+    assert rot.shape == (4, 3) and trans.shape == (4, 3)
+    assert float((rot.cpu() - g["rotation"]).abs().max()) < 1e-5 and float((trans.cpu() - g["translation"]).abs().max()) < 1e-5
+    r_o, t_o = RL.regression_head(sd, "", g["src"], g["cor"], g["w"])
+    assert float((rot.cpu() - r_o).abs().max()) < 1e-5 and float((trans.cpu() - t_o).abs().max()) < 1e-5
+    h6 = Regression_6dR_3dt_Head().to(DEV)
+    assert h6.fc3_trans.weight.shape == (3, 64) and h6.fc3_rot.weight.shape == (6, 32)
+    with pytest.raises(RuntimeError):
+        h6(g["src"].to(DEV), g["cor"].to(DEV), g["w"].to(DEV))
+    x6 = torch.randn(5, 6, device=DEV)
+    R = h6.compute_rotation_matrix_from_6d(x6)
+    assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=DEV).expand(5, 3, 3), atol=1e-4)

@@ -58,3 +58,40 @@ def test_calib_convention_and_running_means(B):
     gd = M.geodesic_distance(err.to(DEV))
     assert abs(gd[0] - RM.calib_error(gt1.numpy(), pr1.numpy())[0].mean()) < 5e-3
     assert abs(gd[1] - RM.calib_error(gt1.numpy(), pr1.numpy())[1].mean()) < 1e-4
+
+
+def test_calib_eval_classes_write_the_reference_json(tmp_path):
+    """pcd_reg_hregnet_b200.metrics.MultiLayerCalibEval / CalibEval (metrics/calibeval.py:11-337,344-380) on the device:
+    the same inputs the reference's own evaluator was fed (tests/golden/calib_eval.json) -> the same JSON document
+    (keys, order, list lengths; numbers within fp32 angle rounding), and the single-evaluator file name of save_results."""
+    import json
+    import os
+    import types
+    from test_golden_oracle import _calib_inputs
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "calib_eval.json")))
+    cfg = types.SimpleNamespace(dataset="synthetic", dataset_config=types.SimpleNamespace(
+        version="_v0", model="HRegNet", max_trans_error=0.5, max_rot_error=20.0, distribution="uniform", results_path=str(tmp_path)))
+    ev = M.MultiLayerCalibEval(cfg, num_layers=3)
+    for layer, batches in _calib_inputs().items():
+        for g, p in batches:
+            ev.add_batch(layer, g.to(DEV), p.to(DEV))
+    out = tmp_path / "all.json"
+    ev.save_all_results(str(out))
+    got = json.load(open(out))
+    assert list(got) == list(gold)
+    for k in ("dataset", "model", "translation", "rotation", "distribution"):
+        assert got[k] == gold[k]
+    for layer in range(3):
+        a, b = got[f"layer_{layer}"], gold[f"layer_{layer}"]
+        assert list(a) == list(b)
+        for k in b:
+            assert np.asarray(a[k]).shape == np.asarray(b[k]).shape
+            assert np.abs(np.asarray(a[k]) - np.asarray(b[k])).max() < 5e-3, (layer, k)
+    with pytest.raises(ValueError):
+        ev.add_batch(3, batches[0][0].to(DEV), batches[0][1].to(DEV))
+    ev.evaluators[0].save_results()
+    assert (tmp_path / "results__synthetic_uniform_20.0_0.5.json").exists()
+    assert ev.evaluators[0].compute_recall() == 0.0
+    ev.reset()
+    with pytest.raises(ValueError):
+        ev.evaluators[0].get_results()

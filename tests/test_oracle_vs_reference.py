@@ -188,3 +188,32 @@ def test_preprocess_oracle_matches_reference_classes():
     x = torch.tensor(rng.normal(size=(32, 6)) * 0.4, dtype=torch.float32)
     x[:4] *= 1e-3
     assert np.abs(RO.SE3().exp(x).numpy() - RP.se3_exp(x.numpy())).max() < 1e-6
+
+
+def test_calib_eval_oracle_matches_reference_class():
+    """oracle/ref_metrics.calib_eval_results == the unmodified reference CalibEval (metrics/calibeval.py) on fresh seeded
+    transforms (not the golden ones): dictionary keys / order identical, numbers within fp32 rounding of the angles."""
+    import numpy as np
+    from oracle import ref_metrics as RM
+    CE = H.load_reference_calibeval()
+    g = torch.Generator().manual_seed(77)
+
+    def tf(n):
+        q = torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=1)
+        w, x, y, z = q.unbind(1)
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                         2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                         2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1).view(n, 3, 3)
+        T = torch.eye(4).repeat(n, 1, 1)
+        T[:, :3, :3], T[:, :3, 3] = R, torch.randn(n, 3, generator=g) * 0.3
+        return T
+
+    batches = [(tf(n), tf(n)) for n in (4, 7, 2, 9)]
+    ev = CE.CalibEval(None)
+    for gt, pr in batches:
+        ev.add_batch(gt, pr)
+    want = ev.get_results()
+    got = RM.calib_eval_results([(a.numpy(), b.numpy()) for a, b in batches])
+    assert list(got) == list(want)
+    for k in want:
+        assert np.abs(np.asarray(got[k]) - np.asarray(want[k])).max() < 2e-3, k
