@@ -265,6 +265,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     precision = args.precision
     if precision == "auto":
+        # bf16x3 everywhere.  "tcf" (single-pass fp16 correspondence stages) also meets every stage gate, but with a 1.4x
+        # margin on the coarse correspondences and 2.5 % of step time to gain (profiles/r02b_bench_1gpu_tcf.json): opt-in
         precision = "tc"
     engine.set_precision(precision)
 
@@ -425,7 +427,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32" if precision == "fp32" else "bf16x3 (tcgen05, fp32 accumulate) + fp32",
+            "dtype": {"fp32": "fp32", "tc": "bf16x3 (tcgen05, fp32 accumulate) + fp32",
+                      "tcf": "bf16x3 (feature extraction) + fp16 single pass (correspondence stages), tcgen05, fp32 accumulate; fp32 elsewhere"}[precision],
             "data": "synthetic",
             "config": workload_config(args, world),
             "run": {"l2": "L2 flushed (256 MiB write) between timed iterations", "cuda_graph": not args.no_graph,
@@ -495,13 +498,15 @@ def _profile_families(reg, steps=3):
         s.record()
         r = orig(name, *a)
         e.record()
-        fl = 0.0
+        fl, passes = 0.0, 3
         if name.startswith("hrn_layer"):
+            passes = a[10] if name == "hrn_layer_tc" else (a[11] if name == "hrn_layer_tc_groupmax" else 0)
             view_rows, cout = a[6], a[7]
             rows_t = a[0]._obj
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
             fl = 2.0 * view_rows * K * cout
         elif name == "hrn_chain_tc":
+            passes = a[17]
             rows_t, nl, n1, n2, cout, view_rows = a[0]._obj, a[3], a[4], a[5], a[7], a[16]
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
             macs = K * n1 + (n1 * n2 + n2 * cout if nl == 3 else n1 * cout)
@@ -528,7 +533,7 @@ def _profile_families(reg, steps=3):
             Bc, Mc, Nc = a[3], a[4], a[5]
             Dc = a[6] if name == "hrn_knn" else 3
             other["knn"] = other.get("knn", 0.0) + float(Bc) * Mc * Nc * (3 * Dc - 1) / steps
-        rec.append((name, s, e, fl))
+        rec.append((name, s, e, fl, fl * passes))
         return r
 
     engine.call = timed
@@ -538,21 +543,26 @@ def _profile_families(reg, steps=3):
         torch.cuda.synchronize()
     finally:
         engine.call = orig
-    fam, flops = {}, {}
-    for name, s, e, fl in rec:
+    fam, flops, issued = {}, {}, {}
+    for name, s, e, fl, fli in rec:
         fam[name] = fam.get(name, 0.0) + s.elapsed_time(e) / steps
         flops[name] = flops.get(name, 0.0) + fl / steps
+        issued[name] = issued.get(name, 0.0) + fli / steps
     fam = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
     layer_names = [n for n in fam if n.startswith("hrn_layer") or n in ("hrn_level_fused", "hrn_level_ws", "hrn_chain_tc")]
     layer_ms = sum(fam[n] for n in layer_names)
     layer_fl = sum(flops[n] for n in layer_names)
+    layer_issued = sum(issued[n] for n in layer_names)
     n_layer = sum(1 for r in rec if r[0] in layer_names) / steps
 
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):          # DRAM bytes of the same kernel family over one step, from the committed ncu capture
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj["tensor_family_dram_bytes_per_step"], tj["source"]
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if tps:     # DRAM bytes of the same kernel family over one step: not measurable without a profiler, so it is read from the
+                # newest committed ncu launch list of this same command (profiles/step_breakdown.py), named in traffic_source
+        tj = json.load(open(tps[-1]))
+        traffic = tj["tensor_family_dram_bytes_per_step"]
+        traffic_src = f"profiles/{os.path.basename(tps[-1])} (committed capture, not measured in this run): " + tj["source"]
 
     def roofline(pk):
         ach = layer_fl / (layer_ms / 1e3) / 1e12 if layer_ms > 0 else 0.0
@@ -564,8 +574,10 @@ def _profile_families(reg, steps=3):
                 "algorithmic_gflop_per_step": layer_fl / 1e9,
                 # precision == "tc": every useful MAC is three bf16 tensor-core MACs (hi*hi + lo*hi + hi*lo), so the
                 # tensor pipe itself runs at 3x `frac`; 1/3 is the ceiling of `frac` for this arithmetic
-                "tensor_macs_per_useful_mac": 3 if engine.get_precision() == "tc" else 0,
-                "frac_of_tensor_pipe_issued": (3 * ach / pk["bf16_tflops_sustained"]) if engine.get_precision() == "tc" else None}
+                # tensor-core MACs issued per algorithmic MAC, FLOP-weighted over the family: 3 = bf16 hi/lo operands
+                # (hi*hi + lo*hi + hi*lo), 1 = single-pass fp16 (mode "tcf": the correspondence stages)
+                "tensor_macs_per_useful_mac": (layer_issued / layer_fl) if layer_fl > 0 else None,
+                "frac_of_tensor_pipe_issued": (layer_issued / layer_fl * ach / pk["bf16_tflops_sustained"]) if layer_fl > 0 else None}
 
     def kernel_rooflines(pk, sm_mhz):
         """The sampling and neighbour-search families against the FP32 issue rate of the chip at the measured clock

@@ -136,16 +136,19 @@ int hrn_layer_fp32(const hrn_rows_t* in, const float* W, const float* bias, int 
 /* Tensor-core variant of hrn_layer_fp32 (tcgen05.mma kind::f16, bf16 hi/lo split of both operands, three products
  * per MAC, fp32 accumulation in TMEM; relative error ~2^-16).  Wp = weights pre-split / pre-tiled on the host as
  * [n_stage][hi|lo][4][NP][8] bf16 (pcd_reg_hregnet_b200/engine_tc.py), NP = Cout padded to a multiple of 16
- * (512 if > 256), K padded per segment to a multiple of 8 and in total to 32 * n_stage. */
+ * (512 if > 256), K padded per segment to a multiple of 8 and in total to 32 * n_stage.
+ * prec = 3: as above.  prec = 1: single-pass fp16 operands (one product per MAC, relative error ~2^-11 per layer), Wp =
+ * [n_stage][4][NP][8] fp16 -- for the stages whose tolerance allows it (the correspondence stages; measured deltas in
+ * profiles/r02_precision_emulation.txt); 16-byte aligned segments only. */
 int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
-                 int Cout, int NP, int n_stage, void* stream);
+                 int Cout, int NP, int n_stage, int prec, void* stream);
 
 /* The same layer with the reference's max over the k neighbours (x.max(dim=3), layers.py:208) taken in the epilogue:
  * G [rows / k, ldg] = max over each k consecutive rows of act(W x + b); the per-row result is never written.
  * k = 8, 16 or 32; act = none or ReLU; Cout a multiple of 32 (= NP); 16-byte aligned segments, G and bias --
  * HRN_ERR_UNSUPPORTED otherwise (callers then run hrn_layer_tc + hrn_group_max). */
 int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* G, int ldg,
-                          long long rows, int Cout, int NP, int n_stage, int k, void* stream);
+                          long long rows, int Cout, int NP, int n_stage, int k, int prec, void* stream);
 
 /* Two or three fused shared-MLP layers with the activations kept in shared / tensor memory: the reference's conv
  * stacks `convs`, `convs_1`, `convs_2` (layers.py:118-121,249-260,420-423), the descriptor head mlp1+mlp2
@@ -154,9 +157,11 @@ int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const float* bia
  * rows of each group (+ Y rows if Y != NULL, layers.py:202,208); 2 = a = softmax_k(max_c Y), G[g,:] = sum_k a*Y, Y
  * (optional) = the rows Y*a (layers.py:150-159,329-332,384-390,446-450).  Hidden activations ReLU, last = `act`.
  * W = K=16 weight pieces of the layers in execution order (pcd_reg_hregnet_b200/engine_tc.pack_chain), bias = b1|b2|b3,
- * n1..n3 = issued widths (multiples of 16; the last = cout padded), chunks0 = 8-wide K chunks of the virtual input. */
+ * n1..n3 = issued widths (multiples of 16; the last = cout padded), chunks0 = 8-wide K chunks of the virtual input.
+ * prec = 3: bf16 hi/lo operands (pieces [hi|lo][2][N][8]); prec = 1: single-pass fp16 (pieces [2][N][8] fp16), see hrn_layer_tc. */
 int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl, int n1, int n2, int n3, int cout, int act,
-                 int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, void* stream);
+                 int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, int prec,
+                 void* stream);
 
 /* Levels 1 and 2 of HierFeatureExtraction (models/HRegNet/models.py:27-28,33-34: detector_l + desc_extractor_l;
  * level 1: in_channels 0, k = 64, widths 32/32/64, mlp 192->32->64; level 2: in_channels 64, k = 32, widths

@@ -42,12 +42,12 @@ SIGNATURES = {
     "hrn_gather_rows": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_transpose": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_layer_fp32": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp],
-    "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp],
-    "hrn_layer_tc_groupmax": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_vp],
+    "hrn_layer_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_vp],
+    "hrn_layer_tc_groupmax": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp],
     "hrn_level_fused": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_level_ws": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_chain_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
-                     c_int, c_vp, c_vp, c_ll, c_vp],
+                     c_int, c_vp, c_vp, c_ll, c_int, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
     "hrn_group_weighted_sum": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "hrn_group_attend": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp],

@@ -99,7 +99,9 @@ struct ChainWsArgs {
     int acc_stride, nbuf;    // TMEM accumulators: nbuf = 512 / acc_stride buffers (4 x 128 or 2 x 256 columns), used round-robin
 };
 
-template <int KSEG, int RAW>
+// PREC 3: bf16 hi/lo operands, three MMAs per K=16 piece; PREC 1: single fp16 plane, one MMA per piece (the hi plane of
+// every stage / slot is the only one written and read).
+template <int KSEG, int RAW, int PREC>
 __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsArgs AW) {
     const ChainArgs& A = AW.c;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -176,9 +178,14 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])), f2_pack(b0.z, b0.w)), s[2], s[3]);
                                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])), f2_pack(b1.x, b1.y)), s[4], s[5]);
                                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])), f2_pack(b1.z, b1.w)), s[6], s[7]);
-                                const float x[8] = {fmaxf(s[0], 0.f), fmaxf(s[1], 0.f), fmaxf(s[2], 0.f), fmaxf(s[3], 0.f),
-                                                    fmaxf(s[4], 0.f), fmaxf(s[5], 0.f), fmaxf(s[6], 0.f), fmaxf(s[7], 0.f)};
-                                split_store8(x, h_hi + ch * CTM + rt, h_lo + ch * CTM + rt);
+                                if (PREC == 1) {
+                                    h_hi[ch * CTM + rt] = make_uint4(pack_f16x2_relu(s[0], s[1]), pack_f16x2_relu(s[2], s[3]),
+                                                                     pack_f16x2_relu(s[4], s[5]), pack_f16x2_relu(s[6], s[7]));
+                                } else {
+                                    const float x[8] = {fmaxf(s[0], 0.f), fmaxf(s[1], 0.f), fmaxf(s[2], 0.f), fmaxf(s[3], 0.f),
+                                                        fmaxf(s[4], 0.f), fmaxf(s[5], 0.f), fmaxf(s[6], 0.f), fmaxf(s[7], 0.f)};
+                                    split_store8(x, h_hi + ch * CTM + rt, h_lo + ch * CTM + rt);
+                                }
                             }
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -393,12 +400,17 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     const float4 t = vv[2 * g + j];
                     const float s_ = ss[2 * g + j];
                     const float x0 = t.x * s_, x1 = t.y * s_, x2 = t.z * s_, x3 = t.w * s_;
+                    const int slot_a = (2 * j + cl) * CTM + pw * 16 + g * 8 + rsub;
+                    if (PREC == 1) {           // each lane stores its own 8 bytes of the 16-byte core-matrix row
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(g_hi + slot_a) + 8 * hf) =
+                            make_uint2(pack_f16x2(x0, x1), pack_f16x2(x2, x3));
+                        continue;
+                    }
                     uint32_t H0, H1, L0, L1;
                     split_pair(x0, x1, H0, L0);
                     split_pair(x2, x3, H1, L1);
                     const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hf ? H0 : L0, 8);
                     const uint32_t r1 = __shfl_xor_sync(0xffffffffu, hf ? H1 : L1, 8);
-                    const int slot_a = (2 * j + cl) * CTM + pw * 16 + g * 8 + rsub;
                     if (hf == 0) g_hi[slot_a] = make_uint4(H0, H1, r0, r1);
                     else         g_lo[slot_a] = make_uint4(r0, r1, L0, L1);
                 }
@@ -450,8 +462,10 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                 const uint64_t ah = a_desc0 | a16, al = a_desc0 | (a16 + LO16);
                 const uint64_t wh = w_desc0 | w16, wl = w_desc0 | (w16 + wlo16);
                 umma_bf16(d, ah, wh, idesc, accumulate);
-                umma_bf16(d, al, wh, idesc, 1u);
-                umma_bf16(d, ah, wl, idesc, 1u);
+                if (PREC == 3) {
+                    umma_bf16(d, al, wh, idesc, 1u);
+                    umma_bf16(d, ah, wl, idesc, 1u);
+                }
                 umma_commit(wempty0 + 8 * ws);
                 if (++ws == (uint32_t)RING) { ws = 0; wpar ^= 1; }
             };
@@ -462,7 +476,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     const uint32_t d = tmem + b * ACC;
                     claim(b);
                     if (nl == 1) fin_pending |= 1u << b;
-                    const uint32_t N = (uint32_t)A.n[0], idesc = ch_idesc(A.n[0]);
+                    const uint32_t N = (uint32_t)A.n[0], idesc = umma_idesc_m128<PREC>(A.n[0]);
                     const uint64_t w_desc0 = DESC_FIXED | ((uint64_t)N << 16);                      // LBO = N * 16 B
                     const uint32_t wlo16 = 2 * N;                                                   // lo plane: + 2 * N * 16 B
                     int left = (int)pieces[0];
@@ -483,7 +497,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     const uint32_t d = tmem + b * ACC;
                     claim(b);
                     if (l == nl - 1) fin_pending |= 1u << b;
-                    const uint32_t N = (uint32_t)A.n[l], idesc = ch_idesc(A.n[l]);
+                    const uint32_t N = (uint32_t)A.n[l], idesc = umma_idesc_m128<PREC>(A.n[l]);
                     const uint64_t w_desc0 = DESC_FIXED | ((uint64_t)N << 16);
                     const uint32_t wlo16 = 2 * N;
                     int left = A.n[l - 1] / 16;
@@ -506,7 +520,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const uint8_t* src = A.W;
                 for (int l = 0; l < nl; ++l) {
-                    const uint32_t bytes = (uint32_t)A.n[l] * 64u;
+                    const uint32_t bytes = (uint32_t)A.n[l] * (PREC == 1 ? 32u : 64u);     // hi (+ lo) plane of a K=16 piece
                     for (uint32_t p = 0; p < pieces[l]; ++p) {
                         mbar_wait_backoff(smem_u32(&s_wempty[ws]), wpar ^ 1);
                         mbar_expect_tx(smem_u32(&s_wfull[ws]), bytes);
@@ -524,16 +538,48 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+inline int grid_ws_of(int n_tiles) { return n_tiles < 148 ? n_tiles : 148; }
+
+template <int KSEG, int RAW, int PREC>
+cudaError_t launch_chain_one(const ChainWsArgs& AW, int grid, int smem, int budget, cudaStream_t st) {
+    static hrn_once_per_device attr;
+    if (attr.need()) {
+        cudaError_t e = cudaFuncSetAttribute(chain_ws_kernel<KSEG, RAW, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget);
+        if (e != cudaSuccess) return e;
+    }
+    chain_ws_kernel<KSEG, RAW, PREC><<<grid, CW_THREADS, smem, st>>>(AW);
+    return cudaSuccess;
+}
+
+template <int PREC>
+cudaError_t launch_chain_prec(const ChainWsArgs& AW, int kseg, bool narrow, int grid, int smem, int budget, cudaStream_t st) {
+    if (narrow) {
+        if (kseg == 8) return launch_chain_one<8, 4, PREC>(AW, grid, smem, budget, st);
+        if (kseg == 16) return launch_chain_one<16, 4, PREC>(AW, grid, smem, budget, st);
+        return launch_chain_one<32, 4, PREC>(AW, grid, smem, budget, st);
+    }
+    if (kseg == 8) return launch_chain_one<8, 2, PREC>(AW, grid, smem, budget, st);
+    if (kseg == 16) return launch_chain_one<16, 2, PREC>(AW, grid, smem, budget, st);
+    return launch_chain_one<32, 2, PREC>(AW, grid, smem, budget, st);
+}
+
+cudaError_t launch_chain(const ChainWsArgs& AW, int kseg, bool narrow, int prec, int grid, int smem, int budget, cudaStream_t st) {
+    return prec == 1 ? launch_chain_prec<1>(AW, kseg, narrow, grid, smem, budget, st)
+                     : launch_chain_prec<3>(AW, kseg, narrow, grid, smem, budget, st);
+}
+
 }  // namespace
 
 // Two or three fused layers on a virtual rows matrix.  W: packed K=16 pieces of the layers in execution order
-// (engine_tc.pack_chain), bias = b1|b2|b3 (last: `cout` entries), issued widths n1,n2,(n3) multiples of 16 and <= 256
+// (engine_tc.pack_chain; prec = 3: bf16 hi + lo planes, prec = 1: one fp16 plane), bias = b1|b2|b3 (last: `cout` entries),
+// issued widths n1,n2,(n3) multiples of 16 and <= 256
 // (the last one = cout padded to 16), hidden activations ReLU, last activation `act`.  mode / outputs as in the file
 // header; `kseg` = rows per group (8, 16 or 32; ignored for mode 0); rows must be a multiple of 128.
 HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl, int n1, int n2, int n3, int cout,
                          int act, int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows,
-                         void* stream) {
+                         int prec, void* stream) {
     if (!in || !W || !bias || rows < 0 || in->n_seg < 1 || in->n_seg > 4 || (nl != 2 && nl != 3)) return HRN_ERR_BAD_ARG;
+    if (prec != 1 && prec != 3) return HRN_ERR_BAD_ARG;
     const int nn[3] = {n1, n2, nl == 3 ? n3 : 16};
     for (int l = 0; l < 3; ++l) if (nn[l] % 16 || nn[l] > 256 || nn[l] < 16) return HRN_ERR_UNSUPPORTED;
     const int nlast = nl == 3 ? n3 : n2;
@@ -560,7 +606,7 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
     A.chunks0 = chunks0; A.mode = mode; A.kseg = kseg;
     int maxn = n1 > n2 ? n1 : n2;
     if (nl == 3 && n3 > maxn) maxn = n3;
-    A.slot_bytes = maxn * 64;
+    A.slot_bytes = maxn * (prec == 1 ? 32 : 64);
     cudaStream_t st = (cudaStream_t)stream;
     if (rows >= 0x7fffffffLL) return HRN_ERR_UNSUPPORTED;        // 32-bit row arithmetic in the producers
     {
@@ -587,25 +633,7 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
         AW.acc_stride = narrow ? 128 : 256;
         AW.nbuf = 512 / AW.acc_stride;
         const int smem_ws = fixed + ring * A.slot_bytes + (use_tile ? CW_TILE_BYTES : 0);
-        static hrn_once_per_device attr_ws;
-        if (attr_ws.need()) {
-            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            HRN_CUDA(cudaFuncSetAttribute(chain_ws_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        }
-        const int grid_ws = AW.n_tiles < 148 ? AW.n_tiles : 148;
-        if (narrow) {
-            if (kseg == 8) chain_ws_kernel<8, 4><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
-            else if (kseg == 16) chain_ws_kernel<16, 4><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
-            else chain_ws_kernel<32, 4><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
-        } else {
-            if (kseg == 8) chain_ws_kernel<8, 2><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
-            else if (kseg == 16) chain_ws_kernel<16, 2><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
-            else chain_ws_kernel<32, 2><<<grid_ws, CW_THREADS, smem_ws, st>>>(AW);
-        }
+        HRN_CUDA((launch_chain(AW, kseg, narrow, prec, grid_ws_of(AW.n_tiles), smem_ws, budget, st)));
         HRN_LAUNCH_CHECK();
         return HRN_OK;
     }

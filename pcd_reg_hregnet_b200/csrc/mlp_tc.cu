@@ -254,7 +254,9 @@ constexpr int WS_RAW = 4;                                             // raw fp3
 
 // SIMPLE: the input is one DIRECT segment without a row scale (every layer that reads the previous layer's output):
 // no segment table, no per-row source resolution -- the producers' instruction stream is what bounds these launches.
-template <bool SIMPLE>
+// PREC 3: bf16 hi/lo operands (six MMAs per 32-wide stage); PREC 1: one fp16 plane (two MMAs per stage; the stage's hi
+// planes are the only ones written and read, the weight slab of a stage is NS * 64 bytes).
+template <bool SIMPLE, int PREC>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ bias, int act,
                 float* __restrict__ Y, int ldy, long long rows, int Cout, int NPfull, int NS, int n_split, int n_stage,
@@ -267,7 +269,8 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t w_bytes = (uint32_t)NS * 128u;
+    constexpr int WPL = PREC == 1 ? 1 : 2;                               // weight / operand planes
+    const uint32_t w_bytes = (uint32_t)NS * 64u * WPL;
     const uint32_t stage_bytes = A_STAGE_BYTES + w_bytes;
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
@@ -492,12 +495,17 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                     const float s_ = SIMPLE ? 1.f : ss[2 * g + j];
                     const float x0 = SIMPLE ? t.x : t.x * s_, x1 = SIMPLE ? t.y : t.y * s_;
                     const float x2 = SIMPLE ? t.z : t.z * s_, x3 = SIMPLE ? t.w : t.w * s_;
+                    const int slot_a = (2 * j + cl) * TM + pw * 16 + g * 8 + rsub;
+                    if (PREC == 1) {           // each lane stores its own 8 bytes of the 16-byte core-matrix row
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a_hi + slot_a) + 8 * hf) =
+                            make_uint2(pack_f16x2(x0, x1), pack_f16x2(x2, x3));
+                        continue;
+                    }
                     uint32_t H0, H1, L0, L1;
                     split_pair(x0, x1, H0, L0);
                     split_pair(x2, x3, H1, L1);
                     const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hf ? H0 : L0, 8);
                     const uint32_t r1 = __shfl_xor_sync(0xffffffffu, hf ? H1 : L1, 8);
-                    const int slot_a = (2 * j + cl) * TM + pw * 16 + g * 8 + rsub;
                     if (hf == 0) a_hi[slot_a] = make_uint4(H0, H1, r0, r1);
                     else         a_lo[slot_a] = make_uint4(r0, r1, L0, L1);
                 }
@@ -522,7 +530,7 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
     } else if (warp == WS_EPI_WARPS + WS_PROD_WARPS) {
         // ================= MMA issue ==============================================================================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t idesc = umma_idesc_m128<PREC>(NS);
             const uint32_t w_lbo = (uint32_t)NS * 16;
             const uint64_t a_fix = umma_desc_fixed(TM * 16, 128), w_fix = umma_desc_fixed(w_lbo, 128);
             // offsets inside a stage, 16-byte units: lo planes, second k-step
@@ -539,11 +547,15 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a16 = (smem0 >> 4) + st * stage16, w16 = a16 + (A_STAGE_BYTES >> 4);
                     umma_bf16(d, a_fix | a16, w_fix | w16, idesc, i > 0 ? 1u : 0u);
-                    umma_bf16(d, a_fix | (a16 + A_LO), w_fix | w16, idesc, 1u);
-                    umma_bf16(d, a_fix | a16, w_fix | (w16 + w_lo), idesc, 1u);
+                    if (PREC == 3) {
+                        umma_bf16(d, a_fix | (a16 + A_LO), w_fix | w16, idesc, 1u);
+                        umma_bf16(d, a_fix | a16, w_fix | (w16 + w_lo), idesc, 1u);
+                    }
                     umma_bf16(d, a_fix | (a16 + A_K1), w_fix | (w16 + w_k1), idesc, 1u);
-                    umma_bf16(d, a_fix | (a16 + A_K1 + A_LO), w_fix | (w16 + w_k1), idesc, 1u);
-                    umma_bf16(d, a_fix | (a16 + A_K1), w_fix | (w16 + w_k1 + w_lo), idesc, 1u);
+                    if (PREC == 3) {
+                        umma_bf16(d, a_fix | (a16 + A_K1 + A_LO), w_fix | (w16 + w_k1), idesc, 1u);
+                        umma_bf16(d, a_fix | (a16 + A_K1), w_fix | (w16 + w_k1 + w_lo), idesc, 1u);
+                    }
                     umma_commit(empty0 + 8 * st);
                     if (++st == S) { st = 0; par ^= 1; }
                 }
@@ -553,7 +565,7 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
     } else {
         // ================= weight stream ==========================================================================
         if (lane == 0) {
-            const size_t w_full_stage = (size_t)NPfull * 64;                // bf16 elements per packed stage
+            const size_t w_full_stage = (size_t)NPfull * 32 * WPL;          // 16-bit elements per packed stage
             int st = 0; uint32_t par = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int n0 = (it % n_split) * NS;
@@ -567,7 +579,7 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                         bulk_g2s(dst, src, w_bytes, barw);
                     } else {
 #pragma unroll
-                        for (int pc = 0; pc < 2 * (KC / 8); ++pc)
+                        for (int pc = 0; pc < WPL * (KC / 8); ++pc)
                             bulk_g2s(dst + pc * NS * 16, src + ((size_t)pc * NPfull + n0) * 8, (uint32_t)NS * 16, barw);
                     }
                     if (++st == S) { st = 0; par ^= 1; }
@@ -581,34 +593,39 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+template <bool SIMPLE, int PREC>
+int layer_ws_launch_one(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
+                        int Cout, int NP, int NS, int n_split, int n_stage, int S, int n_items, int gk, int grid, size_t smem,
+                        size_t budget, cudaStream_t stream) {
+    static hrn_once_per_device attr_set;
+    if (attr_set.need())
+        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<SIMPLE, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    layer_ws_kernel<SIMPLE, PREC><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
+                                                                    NP, NS, n_split, n_stage, S, n_items, gk);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
 int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy, long long rows,
-                    int Cout, int NP, int n_stage, cudaStream_t stream, int gk = 0) {
+                    int Cout, int NP, int n_stage, cudaStream_t stream, int gk = 0, int prec = 3) {
     const int tiles = hrn_divup(rows, TM);
     int NS = NP > 256 ? 256 : NP;
     while (NS > 32 && (NS / 2) % 16 == 0 && tiles * (NP / NS) < 148) NS >>= 1;
     const int n_split = NP / NS;
     const int n_items = tiles * n_split;
-    const size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)NS * 128;
+    const size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)NS * (prec == 1 ? 64 : 128);
     const size_t fixed = WS_TILE_BYTES + (size_t)WS_RAW * A_STAGE_BYTES;
     const size_t budget = 226 * 1024;
     int S = (int)((budget - fixed) / stage_bytes);
     if (S > WS_MAX_STAGES) S = WS_MAX_STAGES;
     const size_t smem = (size_t)S * stage_bytes + fixed;
-    static hrn_once_per_device attr_set;
-    if (attr_set.need()) {
-        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        HRN_CUDA(cudaFuncSetAttribute(layer_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    }
     const int grid = n_items < 148 ? n_items : 148;
     const bool simple = in->n_seg == 1 && in->seg[0].mode == HRN_SEG_DIRECT && !in->seg[0].row_scale;
-    if (simple)
-        layer_ws_kernel<true><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
-                                                                  NP, NS, n_split, n_stage, S, n_items, gk);
-    else
-        layer_ws_kernel<false><<<grid, WS_THREADS, smem, stream>>>(*in, (const __nv_bfloat16*)Wp, bias, act, Y, ldy, rows, Cout,
-                                                                   NP, NS, n_split, n_stage, S, n_items, gk);
-    HRN_LAUNCH_CHECK();
-    return HRN_OK;
+#define HRN_LWS(SIMPLE_, PREC_) \
+    layer_ws_launch_one<SIMPLE_, PREC_>(in, Wp, bias, act, Y, ldy, rows, Cout, NP, NS, n_split, n_stage, S, n_items, gk, grid, smem, budget, stream)
+    if (prec == 1) return simple ? HRN_LWS(true, 1) : HRN_LWS(false, 1);
+    return simple ? HRN_LWS(true, 3) : HRN_LWS(false, 3);
+#undef HRN_LWS
 }
 
 }  // namespace
@@ -616,8 +633,9 @@ int layer_ws_launch(const hrn_rows_t* in, const void* Wp, const float* bias, int
 // Wp = weights packed by hrn_pack_weights_layout (see engine_tc.pack_weights): [n_stage][2][4][NP][8] bf16.
 // K_pad = 32 * n_stage must equal sum over segments of ceil8(channels), rounded up to 32.
 HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* Y, int ldy,
-                         long long rows, int Cout, int NP, int n_stage, void* stream) {
+                         long long rows, int Cout, int NP, int n_stage, int prec, void* stream) {
     if (!in || !Wp || !bias || !Y || rows < 0 || Cout <= 0 || in->n_seg < 1 || in->n_seg > 4) return HRN_ERR_BAD_ARG;
+    if (prec != 1 && prec != 3) return HRN_ERR_BAD_ARG;
     if (NP % 16 != 0 || NP < 16 || NP > 512 || NP < Cout || (NP > 256 && NP != 512)) return HRN_ERR_UNSUPPORTED;
     int chunks = 0;
     for (int s = 0; s < in->n_seg; ++s) {
@@ -652,7 +670,8 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
     // 16-byte aligned segments (every call of the registration path): persistent warp-specialised kernel; the
     // one-CTA-per-tile kernel below remains as the general fallback (odd channel counts, unaligned views)
     if (fast)
-        return layer_ws_launch(in, Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, (cudaStream_t)stream);
+        return layer_ws_launch(in, Wp, bias, act, Y, ldy, rows, Cout, NP, n_stage, (cudaStream_t)stream, 0, prec);
+    if (prec != 3) return HRN_ERR_UNSUPPORTED;        // the general fallback kernel exists for the bf16 hi/lo operands only
     dim3 grid(tiles, n_split);
     if (fast)
         layer_tc_kernel<true><<<grid, TM, smem, (cudaStream_t)stream>>>(
@@ -668,8 +687,9 @@ HRN_API int hrn_layer_tc(const hrn_rows_t* in, const void* Wp, const float* bias
 // act(W x + b)  (k = 8, 16 or 32; act = none / ReLU; Cout a multiple of 32; 16-byte aligned segments, G and bias).
 // Replaces hrn_layer_tc + hrn_group_max for the last DescExtractor layer (reference layers.py:207-208).
 HRN_API int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const float* bias, int act, float* G, int ldg,
-                                  long long rows, int Cout, int NP, int n_stage, int k, void* stream) {
+                                  long long rows, int Cout, int NP, int n_stage, int k, int prec, void* stream) {
     if (!in || !Wp || !bias || !G || rows < 0 || Cout <= 0 || in->n_seg < 1 || in->n_seg > 4) return HRN_ERR_BAD_ARG;
+    if (prec != 1 && prec != 3) return HRN_ERR_BAD_ARG;
     if (k != 8 && k != 16 && k != 32) return HRN_ERR_UNSUPPORTED;
     if (act != HRN_ACT_NONE && act != HRN_ACT_RELU) return HRN_ERR_UNSUPPORTED;
     if (rows % k != 0 || Cout % 32 != 0 || NP != Cout || NP > 512 || (NP > 256 && NP != 512)) return HRN_ERR_UNSUPPORTED;
@@ -685,5 +705,5 @@ HRN_API int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const fl
     }
     if (n_stage != (chunks * 8 + KC - 1) / KC) return HRN_ERR_BAD_ARG;
     if (rows == 0) return HRN_OK;
-    return layer_ws_launch(in, Wp, bias, act, G, ldg, rows, Cout, NP, n_stage, (cudaStream_t)stream, k);
+    return layer_ws_launch(in, Wp, bias, act, G, ldg, rows, Cout, NP, n_stage, (cudaStream_t)stream, k, prec);
 }

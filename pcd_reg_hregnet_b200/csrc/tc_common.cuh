@@ -111,3 +111,25 @@ __device__ __forceinline__ void split_store8(const float (&x)[8], uint4* dst_hi,
     *dst_hi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *dst_lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
+
+// ---- precision mode 1: single-pass fp16 operands (one MMA per MAC) ---------------------------------------------------------
+// Used where the 1e-3 feature gate leaves room for an 11-bit significand (the correspondence stages: measured
+// profiles/r02_precision_emulation.txt); everywhere else the operands are bf16 hi + lo (mode 3, three MMAs per MAC).
+// {lo, hi} -> packed f16x2, round to nearest, saturating (a value beyond 65504 stays finite instead of becoming inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// same with ReLU folded into the conversion (F2FP.SATFINITE.RELU: one instruction for two activations)
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// UMMA instruction descriptor, kind::f16, fp32 accumulate, M = 128: operand format bf16 (PREC 3) or f16 (PREC 1)
+template <int PREC>
+__device__ __forceinline__ uint32_t umma_idesc_m128(int N) {
+    const uint32_t fmt = PREC == 3 ? ((1u << 7) | (1u << 10)) : 0u;
+    return (1u << 4) | fmt | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}

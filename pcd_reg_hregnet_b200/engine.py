@@ -15,7 +15,37 @@ from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_EPS, SEG_BROADCAST, SEG_DIRECT, SEG_GATHER, Rows, call,
                    ptr, stream)
 
-_PRECISION = "tc"       # "tc": tcgen05 kernels (bf16x3, fp32-class accuracy); "fp32": exact CUDA-core layers
+# "fp32": exact CUDA-core layers; "tc": tcgen05 kernels, bf16 hi/lo operands everywhere (bf16x3, fp32-class accuracy);
+# "tcf" (opt-in): as "tc" for feature extraction, single-pass fp16 operands in the correspondence stages (CoarseReg /
+# FineReg).  Measured on the B200 (tests/test_gpu_layers.py, profiles/r02b_bench_1gpu_tcf.json): the stage gates hold -- coarse
+# correspondences 7e-4 of the 1e-3 gate, fine 3.5e-5, weights 3e-5 -- but the margin of the coarse stage is 1.4x and the step
+# gains 2.5 % (5.64 -> 5.50 ms), so "tc" stays the default.  No 2- or 1-pass mode meets the gate for feature extraction
+# (profiles/r02_precision_emulation.txt: descriptors up to 5.6e-3, sigmas 6.3e-3), which therefore always runs bf16x3.
+_PRECISION = "tc"
+PRECISIONS = ("fp32", "tc", "tcf")
+_fast_depth = 0          # > 0 while a correspondence stage is being enqueued
+
+
+def _tc():
+    return _PRECISION in ("tc", "tcf")
+
+
+def mma_prec():
+    """MMA operand mode of the launch being enqueued: 1 = single-pass fp16, 3 = bf16 hi/lo."""
+    return 1 if (_PRECISION == "tcf" and _fast_depth > 0) else 3
+
+
+class _fast_stage:
+    """with _fast_stage(): the shared-MLP launches inside may use the single-pass fp16 operands (mode "tcf" only)."""
+
+    def __enter__(self):
+        global _fast_depth
+        _fast_depth += 1
+
+    def __exit__(self, *exc):
+        global _fast_depth
+        _fast_depth -= 1
+
 _FUSED_CHAINS = True     # tc mode: three-layer conv stacks (<= 256 wide) + their group reductions in one kernel
 _SIDE_STREAM = True      # overlap independent branches of CoarseReg on a second CUDA stream
 _side_streams = {}
@@ -34,9 +64,10 @@ _LEVEL_WS = (2, 3)         # tc mode: levels that run on the warp-specialised fu
 
 
 def set_precision(mode: str):
-    """'fp32' = exact CUDA-core FFMA layers; 'tc' = tcgen05 tensor-core layers (bf16x3 split, fp32 accumulate)."""
+    """'fp32' = exact CUDA-core FFMA layers; 'tc' = tcgen05 tensor-core layers (bf16x3 split, fp32 accumulate); 'tcf' = 'tc'
+    with single-pass fp16 operands in the correspondence stages."""
     global _PRECISION
-    if mode not in ("fp32", "tc"):
+    if mode not in PRECISIONS:
         raise ValueError(mode)
     _PRECISION = mode
 
@@ -88,9 +119,12 @@ def layer(view: RowsView, W, b, act, out=None):
     assert K == view.K, (K, view.K)
     if out is None:
         out = torch.empty(view.rows, Cout, dtype=torch.float32, device=W.device)
-    if _PRECISION == "tc":
+    if _tc():
         from . import engine_tc
-        return engine_tc.layer_tc(view, W, b, act, out)
+        prec = mma_prec()
+        if prec == 1 and not engine_tc.fast_layer_ok(view):
+            prec = 3
+        return engine_tc.layer_tc(view, W, b, act, out, prec)
     _launch_layer_fp32(view, W, b, act, out)
     return out
 
@@ -102,7 +136,7 @@ def _launch_layer_fp32(view, W, b, act, out):
 
 def stack(view: RowsView, layers, last_act=None):
     """Chain of folded layers [(W, b, act), ...] starting from a virtual rows view."""
-    if _PRECISION == "tc" and _FUSED_CHAINS and _FUSED_HEADS and len(layers) == 3 and len(view.segs) == 1:
+    if _tc() and _FUSED_CHAINS and _FUSED_HEADS and len(layers) == 3 and len(view.segs) == 1:
         from . import engine_tc                      # per-keypoint heads mlp1 -> mlp2 -> mlp3 in one launch
         if engine_tc.chain_supported(view, layers, last_relu_only=False):
             return engine_tc.chain(view, layers, engine_tc.EPI_STORE, last_act=last_act)[0]
@@ -118,7 +152,7 @@ def stack(view: RowsView, layers, last_act=None):
 def stack_group_max(view: RowsView, layers, k):
     """group_max(stack(view, layers), k) with the maximum taken in the last layer's epilogue when the tensor-core
     kernel supports it (the per-row output of the last layer is then never written)."""
-    if _PRECISION == "tc" and len(layers) >= 1:
+    if _tc() and len(layers) >= 1:
         from . import engine_tc
         W, b, act = layers[-1]
         x = None
@@ -132,7 +166,7 @@ def stack_group_max(view: RowsView, layers, k):
 
 
 def _chain_ok(view, layers, k):
-    if _PRECISION != "tc" or not _FUSED_CHAINS or k not in (8, 16, 32):
+    if not _tc() or not _FUSED_CHAINS or k not in (8, 16, 32):
         return False
     from . import engine_tc
     return engine_tc.chain_supported(view, layers)
@@ -326,7 +360,7 @@ def detector_descriptor_level(xyz, feat_cl, weights, det, desc, M, k, want_maps=
     if presorted is not None:
         presorted.launch()
     idx, q = knn_idx(None, xyz, k, q_idx=fidx, presorted=presorted)
-    if _PRECISION == "tc" and _FUSED_LEVELS and not want_maps and (B * M * k) % 128 == 0:
+    if _tc() and _FUSED_LEVELS and not want_maps and (B * M * k) % 128 == 0:
         from . import engine_tc
         cin = 0 if feat_cl is None else feat_cl.shape[2]
         lw = engine_tc.which_level_ws(k, cin, det, desc) if feat_cl is not None else None
@@ -396,6 +430,11 @@ def _tail(F, a_k, idx, dxyz, B, N1, N2, head):
 
 def fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k=8, want_af=False):
     """FineReg.forward (reference layers.py:433-454) on channels-last features [B,N,C]."""
+    with _fast_stage():
+        return _fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k, want_af)
+
+
+def _fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k, want_af):
     B, N1, _ = sxyz.shape
     N2 = dxyz.shape[1]
     idx, _ = knn_idx(sxyz, dxyz, k)
@@ -449,6 +488,11 @@ def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None, wa
     both = (xyz [2B,N,3], desc_cl [2B,N,C]) with the source clouds in the first half and the target clouds in the
     second (the model path has them contiguous): the two neighbour-aware branches (layers.py:316-337) then run as ONE
     batch of 2B clouds instead of two."""
+    with _fast_stage():
+        return _coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k, both, want_dists)
+
+
+def _coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k, both, want_dists):
     B, N1, C = sdesc_cl.shape
     N2 = dxyz.shape[1]
 

@@ -24,8 +24,16 @@ def _remember(cache, key, owner, value):
     return value
 
 
-def pack_weights(W, seg_channels):
-    key = (W.data_ptr(), W._version, tuple(seg_channels), W.device)
+def _split_planes(Wp, prec):
+    """fp32 -> the operand planes of a precision mode: 3 = bf16 hi + bf16 lo (three MMAs per MAC), 1 = one fp16 plane."""
+    if prec == 1:
+        return [Wp.to(torch.float16).view(torch.bfloat16)]          # same 16-bit container type downstream
+    hi = Wp.to(torch.bfloat16)
+    return [hi, (Wp - hi.float()).to(torch.bfloat16)]
+
+
+def pack_weights(W, seg_channels, prec=3):
+    key = (W.data_ptr(), W._version, tuple(seg_channels), W.device, prec)
     hit = _cache.get(key)
     if hit is not None:
         return hit
@@ -43,19 +51,24 @@ def pack_weights(W, seg_channels):
         Wp[:Cout, dst:dst + c] = W[:, src:src + c]
         src += c
         dst += (c + 7) // 8 * 8
-    hi = Wp.to(torch.bfloat16)
-    lo = (Wp - hi.float()).to(torch.bfloat16)
-    t = torch.stack([hi, lo], 0).view(2, NP, n_stage, KC // 8, 8).permute(2, 0, 3, 1, 4).contiguous()
+    planes = _split_planes(Wp, prec)
+    t = torch.stack(planes, 0).view(len(planes), NP, n_stage, KC // 8, 8).permute(2, 0, 3, 1, 4).contiguous()
     return _remember(_cache, key, W, (t, NP, n_stage, None))
 
 
-def layer_tc(view, W, b, act, out):
+def fast_layer_ok(view):
+    """The single-pass fp16 variant of the per-layer kernel exists for 16-byte aligned segments only."""
+    return all(ch % 4 == 0 and col0 % 4 == 0 and mat.stride(0) % 4 == 0 and mat.data_ptr() % 16 == 0
+               for mat, mode, ch, col0, scale in view.segs)
+
+
+def layer_tc(view, W, b, act, out, prec=3):
     seg_channels = [s[2] for s in view.segs]
-    Wp, NP, n_stage, _ = pack_weights(W, seg_channels)
+    Wp, NP, n_stage, _ = pack_weights(W, seg_channels, prec)
     if b is None:
         b = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device)
     engine.call("hrn_layer_tc", ctypes.byref(view.c), engine.ptr(Wp), engine.ptr(b), act, engine.ptr(out), out.stride(0),
-                view.rows, W.shape[0], NP, n_stage, engine.stream())
+                view.rows, W.shape[0], NP, n_stage, prec, engine.stream())
     return out
 
 
@@ -72,15 +85,15 @@ def layer_tc_groupmax_ok(view, W, act, k):
     return True
 
 
-def layer_tc_groupmax(view, W, b, act, k):
+def layer_tc_groupmax(view, W, b, act, k, prec=3):
     """G [rows / k, Cout] = max over each k consecutive rows of act(W x + b): layer + reference max(dim=3) in one launch."""
     seg_channels = [s[2] for s in view.segs]
-    Wp, NP, n_stage, _ = pack_weights(W, seg_channels)
+    Wp, NP, n_stage, _ = pack_weights(W, seg_channels, prec)
     if b is None:
         b = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device)
     out = torch.empty(view.rows // k, W.shape[0], dtype=torch.float32, device=W.device)
     engine.call("hrn_layer_tc_groupmax", ctypes.byref(view.c), engine.ptr(Wp), engine.ptr(b), act, engine.ptr(out),
-                out.stride(0), view.rows, W.shape[0], NP, n_stage, k, engine.stream())
+                out.stride(0), view.rows, W.shape[0], NP, n_stage, k, prec, engine.stream())
     return out
 
 
@@ -229,14 +242,13 @@ EPI_STORE, EPI_GROUPMAX, EPI_ATTN = 0, 1, 2
 _chain_cache = {}
 
 
-def _pieces(W, K_pad):
-    """fp32 [N, K] -> packed K=16 pieces: [piece][hi|lo][2 chunks][N][8] bf16 (as uint8)."""
+def _pieces(W, K_pad, prec=3):
+    """fp32 [N, K] -> packed K=16 pieces: [piece][hi|lo][2 chunks][N][8] bf16, or [piece][2 chunks][N][8] fp16 (as uint8)."""
     N, K = W.shape
     Wp = torch.zeros(N, K_pad, dtype=torch.float32, device=W.device)
     Wp[:, :K] = W
-    hi = Wp.to(torch.bfloat16)
-    lo = (Wp - hi.float()).to(torch.bfloat16)
-    t = torch.stack([hi, lo], 0).view(2, N, K_pad // 16, 2, 8).permute(2, 0, 3, 1, 4).contiguous()
+    planes = _split_planes(Wp, prec)
+    t = torch.stack(planes, 0).view(len(planes), N, K_pad // 16, 2, 8).permute(2, 0, 3, 1, 4).contiguous()
     return t.view(-1).view(torch.uint8)
 
 
@@ -258,8 +270,8 @@ def chain_supported(view, layers, last_relu_only=True):
     return True
 
 
-def pack_chain(layers, seg_channels):
-    key = tuple((W.data_ptr(), W._version) for W, _, _ in layers) + (tuple(seg_channels),)
+def pack_chain(layers, seg_channels, prec=3):
+    key = tuple((W.data_ptr(), W._version) for W, _, _ in layers) + (tuple(seg_channels), prec)
     hit = _chain_cache.get(key)
     if hit is not None:
         return hit
@@ -279,15 +291,16 @@ def pack_chain(layers, seg_channels):
         pad = torch.zeros(np_last, mats[-1].shape[1], dtype=torch.float32, device=W1.device)
         pad[:cout] = mats[-1]
         mats[-1] = pad
-    Wpack = torch.cat([_pieces(m, m.shape[1]) for m in mats]).contiguous()
+    Wpack = torch.cat([_pieces(m, m.shape[1], prec) for m in mats]).contiguous()
     bias = torch.cat([b for _, b, _ in layers]).contiguous()
     widths = [m.shape[0] for m in mats]
     return _remember(_chain_cache, key, layers[0][0], (Wpack, bias, chunks0, widths, cout, None))
 
 
-def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act=None):
+def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act=None, prec=None):
     """Runs 2-3 folded layers on the virtual rows.  Returns (Y rows | None, G groups | None, a rows | None)."""
-    Wpack, bias, chunks0, widths, cout, _ = pack_chain(layers, [s[2] for s in view.segs])
+    prec = engine.mma_prec() if prec is None else prec
+    Wpack, bias, chunks0, widths, cout, _ = pack_chain(layers, [s[2] for s in view.segs], prec)
     nl = len(layers)
     act = layers[-1][2] if last_act is None else last_act
     n = widths + [16] * (3 - nl)
@@ -296,7 +309,7 @@ def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act
     G = torch.empty(view.rows // kseg, cout, dtype=torch.float32, device=dev) if (want_groups and mode != EPI_STORE) else None
     a = torch.empty(view.rows, dtype=torch.float32, device=dev) if mode == EPI_ATTN else None
     engine.call("hrn_chain_tc", ctypes.byref(view.c), engine.ptr(Wpack), engine.ptr(bias), nl, n[0], n[1], n[2], cout, act,
-                chunks0, mode, kseg, engine.ptr(Y), cout, engine.ptr(G), engine.ptr(a), view.rows, engine.stream())
+                chunks0, mode, kseg, engine.ptr(Y), cout, engine.ptr(G), engine.ptr(a), view.rows, prec, engine.stream())
     return Y, G, a
 
 

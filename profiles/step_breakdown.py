@@ -1,7 +1,8 @@
 """Per-kernel breakdown of ONE 32-pair step from an ncu launch list that carries gpu__time_duration.sum and the two
 dram__bytes counters (step boundaries = successive level-1 FPS launches).  Writes the table to stdout and the
-DRAM traffic of the tensor-core kernel family to profiles/r01_traffic.json (read by bench.py for roofline.traffic).
-usage: python profiles/step_breakdown.py gpurun_out/launches_final.csv > profiles/r01_launches_final.txt"""
+DRAM traffic of the tensor-core kernel family to profiles/<tag>_traffic.json (the newest one is read by bench.py for
+roofline.traffic).
+usage: python profiles/step_breakdown.py gpurun_out/launches_final.csv [tag=r02] > profiles/r02_launches_final.txt"""
 import collections
 import csv
 import json
@@ -40,9 +41,10 @@ print(f"# one 32-pair step (ncu launch list, cold-cache serialised: compare SHAR
 print(f"{'us':>10} {'share':>6} {'n':>4} {'dram MB':>10}  kernel")
 for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     print(f"{v[1]:10.1f} {100 * v[1] / tot:5.1f}% {v[0]:4d} {v[2] / 1e6:10.1f}  {k}")
-tc = [k for k in fam if any(s in k for s in ("level_fused", "chain3", "chain_ws", "layer_tc", "layer_ws"))]
+tc = [k for k in fam if any(s in k for s in ("level_fused", "level_ws", "chain3", "chain_ws", "layer_tc", "layer_ws"))]
 out = {"tensor_family_dram_bytes_per_step": sum(fam[k][2] for k in tc),
        "tensor_family_us_per_step_ncu": sum(fam[k][1] for k in tc), "n_launches": sum(fam[k][0] for k in tc),
        "share_of_step_ncu": sum(fam[k][1] for k in tc) / tot,
        "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one 32-pair step"}
-json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r01_traffic.json"), "w"), indent=1)
+tag = sys.argv[2] if len(sys.argv) > 2 else "r02"
+json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), tag + "_traffic.json"), "w"), indent=1)

@@ -12,9 +12,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.fixture(autouse=True, params=["fp32", "tc"])
+@pytest.fixture(autouse=True, params=["fp32", "tc", "tcf"])
 def precision(request):
-    """Every test runs in both shared-MLP modes: exact-fp32 CUDA cores and tcgen05 bf16x3."""
+    """Every test runs in all shared-MLP modes: exact-fp32 CUDA cores, tcgen05 bf16x3, and bf16x3 + single-pass fp16 in
+    the correspondence stages ("tcf", the bench default: the stage gates below are what admit it)."""
     from pcd_reg_hregnet_b200 import engine as _e
     _e.set_precision(request.param)
     yield request.param
@@ -38,6 +39,8 @@ def _cl(x):
 def test_feature_levels_teacher_forced(nets, n_points, precision):
     cpu, gpu = nets
     xyz_tol = 1e-5 if precision == "fp32" else 1e-4     # attention-weighted keypoints inherit the MLP's 4e-6 error
+    if precision == "tcf":
+        pytest.skip("feature extraction is identical in 'tc' and 'tcf'")
     src = synth.make_batch([31, 32], n_points)[0]
     trace = {}
     with torch.no_grad():
@@ -71,7 +74,7 @@ def test_feature_levels_teacher_forced(nets, n_points, precision):
             assert errs[0] < xyz_tol and max(errs[1:]) < FEAT_TOL, (lv, errs)
 
 
-def test_coarse_fine_and_pose_teacher_forced(nets):
+def test_coarse_fine_and_pose_teacher_forced(nets, precision):
     cpu, gpu = nets
     gd = load_golden("hregnet_b2_n2048")
     S, D = unflatten(gd, "src_feats."), unflatten(gd, "dst_feats.")
@@ -80,8 +83,10 @@ def test_coarse_fine_and_pose_teacher_forced(nets):
         cor, w = gpu.coarse_corres(g(S["xyz_3"]), g(S["desc_3"]), g(D["xyz_3"]), g(D["desc_3"]), g(S["sigmas_3"]), g(D["sigmas_3"]))
         idx, _ = engine.knn_idx(g(_cl(S["desc_3"])), g(_cl(D["desc_3"])), 8)
         assert torch.equal(idx.cpu().long(), gd["coarse_idx"])                       # 256-d kNN bit-exact
-        assert float((cor.cpu() - gd["src_xyz_corres_3"]).abs().max()) < 1e-3 * float(gd["src_xyz_corres_3"].abs().max())
-        assert float((w.cpu() - gd["src_dst_weights_3"]).abs().max()) < FEAT_TOL
+        e_c = float((cor.cpu() - gd["src_xyz_corres_3"]).abs().max()) / float(gd["src_xyz_corres_3"].abs().max())
+        e_w = float((w.cpu() - gd["src_dst_weights_3"]).abs().max())
+        print(f"coarse [{precision}]: corres rel err {e_c:.1e}, weights abs err {e_w:.1e}")
+        assert e_c < 1e-3 and e_w < FEAT_TOL
         for lv, mod in ((2, gpu.fine_corres_2), (1, gpu.fine_corres_1)):
             Rp, tp = gd[f"rotation.{2 - lv}"], gd[f"translation.{2 - lv}"]
             xt = RL._apply(Rp, tp, S[f"xyz_{lv}"])
@@ -90,8 +95,10 @@ def test_coarse_fine_and_pose_teacher_forced(nets):
             c2, w2 = mod(g(xt), g(S[f"desc_{lv}"]), g(D[f"xyz_{lv}"]), g(D[f"desc_{lv}"]), g(S[f"sigmas_{lv}"]), g(D[f"sigmas_{lv}"]))
             c_o, w_o = RL.fine_reg(cpu.state_dict(), f"fine_corres_{lv}.", xt, S[f"desc_{lv}"], D[f"xyz_{lv}"],
                                    D[f"desc_{lv}"], S[f"sigmas_{lv}"], D[f"sigmas_{lv}"])
-            assert float((c2.cpu() - c_o).abs().max()) < 1e-3 * float(c_o.abs().max())
-            assert float((w2.cpu() - w_o).abs().max()) < FEAT_TOL
+            e_c = float((c2.cpu() - c_o).abs().max()) / float(c_o.abs().max())
+            e_w = float((w2.cpu() - w_o).abs().max())
+            print(f"fine level {lv} [{precision}]: corres rel err {e_c:.1e}, weights abs err {e_w:.1e}")
+            assert e_c < 1e-3 and e_w < FEAT_TOL
 
 
 @pytest.mark.parametrize("N", [256, 512, 1024])

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.fixture(autouse=True, params=["fp32", "tc"])
+@pytest.fixture(autouse=True, params=["fp32", "tc", "tcf"])
 def precision(request):
-    """Every test runs in both shared-MLP modes: exact-fp32 CUDA cores and tcgen05 bf16x3."""
+    """Every test runs in all shared-MLP modes: exact-fp32 CUDA cores, tcgen05 bf16x3, bf16x3 + single-pass fp16
+    correspondence stages."""
     from pcd_reg_hregnet_b200 import engine as _e
     _e.set_precision(request.param)
     yield request.param
@@ -63,6 +64,12 @@ def test_golden_end_to_end(net, name, precision):
         # 5e-5 m here.  The rotation still meets 1e-4 deg; the translation is held at 1e-4 m free-running and at 1e-5 m on
         # identical correspondences (the cascade test).
         tol_m = 1e-4
+    tol_deg = POSE_DEG
+    if precision == "tcf":
+        # single-pass fp16 correspondence stages: correspondences within 4e-4 relative (gate 1e-3) = centimetres per point
+        # at LiDAR range; the solved pose averages them.  Free-running this mode is held at 1e-2 deg / 5e-3 m; its pose
+        # SOLVE is gated on identical correspondences like every mode (the cascade test).
+        tol_deg, tol_m = 1e-2, 5e-3
     n_checked, worst = 0, (0.0, 0.0)
     for b in range(B):
         same = all(rel_err(out[f"{s}_feats"][f"xyz_{lv}"][b].cpu(), gd[f"{s}_feats.xyz_{lv}"][b]) < 1e-4
@@ -77,7 +84,7 @@ def test_golden_end_to_end(net, name, precision):
             ang = float(RL.rotation_angle_deg(out["rotation"][lv][b].cpu(), gd[f"rotation.{lv}"][b]))
             dt = float((out["translation"][lv][b].cpu() - gd[f"translation.{lv}"][b]).abs().max())
             worst = (max(worst[0], ang), max(worst[1], dt))
-            assert ang < POSE_DEG and dt < tol_m, (b, lv, ang, dt)
+            assert ang < tol_deg and dt < tol_m, (b, lv, ang, dt)
     print(f"{name} [{precision}]: {n_checked}/{B} pairs had identical keypoint sets; worst pose delta "
           f"{worst[0]:.2e} deg / {worst[1]:.2e} m")
     # not vacuous: every fixture keeps at least one pair whose keypoint sets survive the cascade in this mode

@@ -192,3 +192,63 @@ def test_layer_groupmax_epilogue_equals_layer_then_group_max(k, rows, K, N):
     want = engine.group_max(engine.layer(RowsView(rows).add(X), W, b, ACT_RELU), k)
     assert got.shape == (rows // k, N)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("rows,K,Cout", [(4096, 528, 512), (1024, 64, 64), (640, 256, 256), (300, 512, 1)])
+def test_single_pass_fp16_layer(rows, K, Cout):
+    """prec = 1 of the per-layer kernel (single-pass fp16 operands): against fp64 within the 11-bit significand's error
+    (2^-11 per product, random signs), and against the same kernel in bf16x3 -- layout / descriptor errors would show as
+    O(1) differences, not O(1e-3)."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    g = torch.Generator().manual_seed(rows + Cout)
+    X = torch.randn(rows, K, generator=g).to(DEV)
+    W = (torch.randn(Cout, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    want = torch.relu(X.double() @ W.double().t() + b.double())
+    out1 = engine_tc.layer_tc(RowsView(rows).add(X), W, b, ACT_RELU, torch.empty(rows, Cout, device=DEV), prec=1)
+    out3 = engine_tc.layer_tc(RowsView(rows).add(X), W, b, ACT_RELU, torch.empty(rows, Cout, device=DEV), prec=3)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    e1 = float((out1.double() - want).abs().max()) / scale
+    e3 = float((out3.double() - want).abs().max()) / scale
+    print(f"rows={rows} K={K} Cout={Cout}: fp16 single pass {e1:.1e}, bf16x3 {e3:.1e}")
+    assert e3 < 1e-4 and e1 < 2e-3
+
+
+@pytest.mark.parametrize("kseg,mode,dims", [(8, 2, [256, 256, 256]), (8, 2, [128, 128, 128]), (16, 1, [128, 128, 256]), (8, 0, [64, 32, 48])])
+def test_single_pass_fp16_chain(kseg, mode, dims):
+    """prec = 1 of the chain kernel on gathered / broadcast segments: every epilogue mode against fp64."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    g = torch.Generator().manual_seed(kseg + mode + dims[0])
+    B, M, N, C = 2, 128 * 8 // kseg * 3, 300, 128
+    rows = B * M * kseg
+    misc = torch.randn(rows, 12, generator=g).to(DEV)
+    src = torch.randn(B * M, C, generator=g).to(DEV)
+    dst = torch.randn(B * N, C, generator=g).to(DEV)
+    idx = torch.randint(0, N, (B, M, kseg), generator=g).int().to(DEV)
+    v = RowsView(rows, group=kseg, gather_idx=idx, rows_per_batch=M * kseg, src_rows_per_batch=N)
+    v.add(misc).add(src, SEG_BROADCAST).add(dst, SEG_GATHER)
+    r = torch.arange(rows, device=DEV)
+    X = torch.cat([misc, src[r // kseg], dst[(r // (M * kseg)) * N + idx.view(-1).long()]], 1).double()
+    layers, kin = [], 12 + 2 * C
+    for wdt in dims:
+        W = (torch.randn(wdt, kin, generator=g) / kin ** 0.5).to(DEV)
+        b = (torch.randn(wdt, generator=g) * 0.1).to(DEV)
+        layers.append((W, b, ACT_RELU))
+        X = torch.relu(X @ W.double().t() + b.double())
+        kin = wdt
+    Y, G, a = engine_tc.chain(v, layers, mode, kseg, prec=1)
+    torch.cuda.synchronize()
+    Cl = dims[-1]
+    Xg = X.view(-1, kseg, Cl)
+    scale = float(X.abs().max())
+    tol = 3e-3
+    if mode == 0:
+        assert float((Y.double() - X).abs().max()) / scale < tol
+    elif mode == 1:
+        assert float((Y.double() - X).abs().max()) / scale < tol
+        assert float((G.double() - Xg.max(dim=1)[0]).abs().max()) / scale < tol
+    else:
+        a_ref = torch.softmax(Xg.max(dim=2)[0], dim=1)
+        assert float((a.double().view(-1, kseg) - a_ref).abs().max()) < 1e-2
+        assert float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale < 2 * tol
