@@ -234,6 +234,14 @@ int hrn_cosine_matrix(const float* S, const float* D, int B, int N1, int N2, int
 int hrn_cosine_pick(const float* cosm, const float* rowmax, const float* colmax, const int32_t* idx, int B, int N1,
                     int N2, int k, float* out, int ldo, int col_src_dst, int col_dst_src, void* stream);
 
+/* The same two feature columns as hrn_cosine_matrix + hrn_cosine_pick in ONE tcgen05 kernel per call (layers.py:29-41,
+ * 292-313, 341-362): the [N1 x C].[C x N2] contraction on the tensor cores (bf16 hi/lo operands, all four partial
+ * products, fp32 accumulation: ~1e-6 on the cosine), both families of maxima and the k picks taken from the accumulators --
+ * the cosine matrix itself is never written.  N1 = 128 or 256, N2 <= 256 (multiple of 16), C multiple of 32, k = 8,
+ * 16-byte aligned S / D; HRN_ERR_UNSUPPORTED otherwise. */
+int hrn_cosine_features_tc(const float* S, const float* D, const int32_t* idx, int B, int N1, int N2, int C, int k,
+                           float* out, int ldo, int col_src_dst, int col_dst_src, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * 5. Pose head (layers.py:456-504 WeightedSVDHead; models.py:100-110,120-127 pose composition)
  * ------------------------------------------------------------------------------------------------------- */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "hrn_sigma_to_weights": [c_vp, c_vp, c_int, c_int, c_vp],
     "hrn_transform_points": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
     "hrn_cosine_matrix": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "hrn_cosine_features_tc": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_cosine_pick": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "hrn_weighted_kabsch": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "hrn_regression_head": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],

@@ -60,6 +60,7 @@ def _side_stream(device):
 
 _FUSED_HEADS = True      # tc mode: per-keypoint heads (mlp1/mlp2/mlp3, width <= 256) as one chain launch
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
+_COSINE_TC = True        # tc modes: CoarseReg's cosine-similarity features as one tcgen05 kernel per similarity
 _LEVEL_WS = (2, 3)         # tc mode: levels that run on the warp-specialised fused level kernel (csrc/level_ws.cu)
 
 
@@ -472,6 +473,12 @@ def _cosine_features(S, D, idx, misc, col_sd, col_ds):
     N2 = D.shape[1]
     k = idx.shape[2]
     dev = S.device
+    if (_tc() and _COSINE_TC and N1 in (128, 256) and N2 <= 256 and N2 % 16 == 0 and C % 32 == 0 and k == 8
+            and S.data_ptr() % 16 == 0 and D.data_ptr() % 16 == 0):
+        # one tcgen05 kernel per similarity: contraction, both families of maxima and the picks (csrc/coarse_tc.cu)
+        call("hrn_cosine_features_tc", ptr(S), ptr(D), ptr(idx), B, N1, N2, C, k, ptr(misc), misc.stride(0), col_sd, col_ds,
+             stream())
+        return
     nS = torch.empty(B, N1, device=dev)
     nD = torch.empty(B, N2, device=dev)
     cosm = torch.empty(B, N2, N1, device=dev)

@@ -369,3 +369,38 @@ def test_regression_heads():
     x6 = torch.randn(5, 6, device=DEV)
     R = h6.compute_rotation_matrix_from_6d(x6)
     assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=DEV).expand(5, 3, 3), atol=1e-4)
+
+
+@pytest.mark.parametrize("N1,N2", [(256, 256), (128, 256), (256, 144)])
+def test_cosine_features_tensor_core_vs_fp32(N1, N2):
+    """csrc/coarse_tc.cu (tcgen05 contraction + maxima + picks in one kernel) against the exact-fp32 kernels of coarse.cu
+    and an fp64 evaluation of layers.py:29-41,296-313 on post-ReLU-like descriptors."""
+    g = torch.Generator().manual_seed(N1 + N2)
+    B, C, k = 3, 256, 8
+    S = torch.relu(torch.randn(B, N1, C, generator=g)).to(DEV)
+    D = torch.relu(torch.randn(B, N2, C, generator=g) + 0.3).to(DEV)
+    idx = torch.randint(0, N2, (B, N1, k), generator=g).int().to(DEV)
+    want = torch.empty(B * N1 * k, 16, device=DEV)
+    got = torch.zeros_like(want)
+    engine._COSINE_TC = False
+    try:
+        engine._cosine_features(S, D, idx, want, 12, 13)
+    finally:
+        engine._COSINE_TC = True
+    engine.set_precision("tc")
+    engine._cosine_features(S, D, idx, got, 12, 13)
+    torch.cuda.synchronize()
+    Sd, Dd = S.double().cpu(), D.double().cpu()
+    cos = torch.einsum("bmc,bnc->bmn", Dd, Sd) / (Dd.norm(dim=2)[:, :, None] * Sd.norm(dim=2)[:, None, :] + 1e-6)   # [B,N2,N1]
+    ii = idx.cpu().long()
+    bb = torch.arange(B)[:, None, None]
+    n1 = torch.arange(N1)[None, :, None]
+    pick = cos[bb, ii, n1]
+    sd = pick / (cos.max(dim=1)[0][:, :, None] + 1e-6)
+    ds = pick / (cos.max(dim=2)[0][bb, ii] + 1e-6)
+    g3 = got.view(B, N1, k, 16).cpu().double()
+    w3 = want.view(B, N1, k, 16).cpu().double()
+    e_tc = max(float((g3[..., 12] - sd).abs().max()), float((g3[..., 13] - ds).abs().max()))
+    e_32 = max(float((w3[..., 12] - sd).abs().max()), float((w3[..., 13] - ds).abs().max()))
+    print(f"cosine features N1={N1} N2={N2}: tcgen05 {e_tc:.1e}, fp32 kernels {e_32:.1e} (vs fp64)")
+    assert e_32 < 5e-6 and e_tc < 5e-6
