@@ -275,7 +275,7 @@ def main():
     src_h, dst_h, _, _ = synth.make_batch(range(1000 + lo, 1000 + lo + B), N)
     src_h, dst_h = src_h.pin_memory(), dst_h.pin_memory()
     net = synth.build_net(args.model, seed=7, device=dev)
-    reg = Registrar(net, B, N, use_cuda_graph=not args.no_graph)
+    reg = Registrar(net, B, N, use_cuda_graph=not args.no_graph, in_flight=int(os.environ.get("HRN_IN_FLIGHT", "2")))
     reg.load(src_h, dst_h)
     reg.capture()
 
