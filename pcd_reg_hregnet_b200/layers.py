@@ -3,13 +3,15 @@ forward argument order / return tuples and state_dict keys (so `ckpt/pretrained/
 checkpoints load unchanged) -- but `forward` launches the sm_100a kernels of libhregnet_b200.so instead of
 building the graph out of ATen ops.
 
-Inference only: BatchNorm uses its running statistics (folded into the 1x1 convolutions, fold.py).  Calling
-a module in training mode raises (the backward pass is outside the path this package covers).
+Inference (eval mode, no gradients recorded): the fused kernels; BatchNorm uses its running statistics, folded into the
+1x1 convolutions (fold.py).  Training mode, or gradients being recorded through the module: the differentiable forward of
+train_path.py (this package's index kernels and differentiable gather / kNN ops, the module's own Conv + BatchNorm
+containers under ATen's autograd, the Kabsch kernel with an analytic-by-autograd backward) -- same values, trainable.
 """
 import torch
 import torch.nn as nn
 
-from . import engine, fold
+from . import engine, fold, train_path
 from .engine import SEG_BROADCAST, SEG_GATHER, RowsView
 from .ops import knn_points
 
@@ -69,6 +71,8 @@ class KeypointDetector(_Folded):
         return dict(convs=fold.fold_sequential(self.convs), mlp=fold.fold_head(self.mlp1, self.mlp2, self.mlp3))
 
     def forward(self, xyz, features, weights=None):
+        if train_path.needs_autograd(self, xyz, features):
+            return train_path.keypoint_detector(self, xyz, features, weights)
         B, N, _ = xyz.shape
         M, k = self.nsample, self.k
         feat_cl = _cl(features) if features is not None else None
@@ -124,6 +128,8 @@ class DescExtractor(_Folded):
                     mlp=fold.fold_sequential(self.mlp1) + fold.fold_sequential(self.mlp2))
 
     def forward(self, grouped_features, attentive_feature_map):
+        if train_path.needs_autograd(self, grouped_features, attentive_feature_map):
+            return train_path.desc_extractor(self, grouped_features, attentive_feature_map)
         B, C, M, k = grouped_features.shape
         P = self.folded()
         G = engine.transpose(grouped_features.contiguous().view(B, C, M * k)).view(B * M * k, C)
@@ -159,6 +165,8 @@ class CoarseReg(_Folded):
     def forward(self, src_xyz, src_desc, dst_xyz, dst_desc, src_weights, dst_weights):
         if not (self.use_sim and self.use_neighbor):
             raise NotImplementedError("only use_sim=use_neighbor=True (the HRegNet configuration, models.py:71) is built")
+        if train_path.needs_autograd(self, src_xyz, src_desc, dst_xyz, dst_desc, src_weights, dst_weights):
+            return train_path.coarse_reg(self, src_xyz, src_desc, dst_xyz, dst_desc, src_weights, dst_weights)
         return engine.coarse_reg(src_xyz.contiguous(), _cl(src_desc), dst_xyz.contiguous(), _cl(dst_desc),
                                  src_weights.contiguous(), dst_weights.contiguous(), self.folded(), self.k)
 
@@ -182,6 +190,8 @@ class FineReg(_Folded):
                     mlp=fold.fold_head(self.mlp1, self.mlp2, self.mlp3))
 
     def forward(self, src_xyz, src_feat, dst_xyz, dst_feat, src_weights, dst_weights):
+        if train_path.needs_autograd(self, src_xyz, src_feat, dst_xyz, dst_feat, src_weights, dst_weights):
+            return train_path.fine_reg(self, src_xyz, src_feat, dst_xyz, dst_feat, src_weights, dst_weights)
         return engine.fine_reg(src_xyz.contiguous(), _cl(src_feat), dst_xyz.contiguous(), _cl(dst_feat),
                                src_weights.contiguous(), dst_weights.contiguous(), self.folded(), self.k)
 
@@ -193,6 +203,8 @@ class WeightedSVDHead(nn.Module):
     """Reference: layers.py:456-504.  forward(src [B,N,3], src_corres [B,N,3], weights [B,N]) -> (r [B,3,3], t [B,3])."""
 
     def forward(self, src, src_corres, weights):
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (src, src_corres, weights)):
+            return train_path.svd_head(src, src_corres, weights)
         return engine.weighted_kabsch(src.contiguous(), src_corres.contiguous(), weights.contiguous())
 
 

@@ -11,7 +11,7 @@ B200-first differences in HOW the graph runs (not in what it computes):
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import engine, train_path
 from .layers import CoarseReg, DescExtractor, FineReg, KeypointDetector, WeightedSVDHead
 
 
@@ -62,6 +62,8 @@ class HierFeatureExtraction(nn.Module):
         return out
 
     def forward(self, points):
+        if train_path.needs_autograd(self, points):
+            return train_path.hier_feature_extraction(self, points)
         cl = self.forward_cl(points)
         return {k: (engine.transpose(v) if k.startswith("desc_") else v) for k, v in cl.items()}
 
@@ -79,6 +81,8 @@ class HRegNet(nn.Module):
         self.svd_head = WeightedSVDHead()
 
     def forward(self, src_points, dst_points):
+        if train_path.needs_autograd(self, src_points, dst_points):
+            return train_path.hregnet_forward(self, src_points, dst_points)     # training: differentiable path
         B = src_points.shape[0]
         both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points), calls=2)
         S = {k: v[:B] for k, v in both.items()}
