@@ -163,12 +163,13 @@ int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl,
                  int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, int prec,
                  void* stream);
 
-/* Levels 1 and 2 of HierFeatureExtraction (models/HRegNet/models.py:27-28,33-34: detector_l + desc_extractor_l;
- * level 1: in_channels 0, k = 64, widths 32/32/64, mlp 192->32->64; level 2: in_channels 64, k = 32, widths
- * 64/64/128, mlp 384->64->128) as ONE persistent tcgen05 kernel each: grouping (layers.py:9-27), the two conv
+/* Level 1 of HierFeatureExtraction (models/HRegNet/models.py:27-28: detector_1 + desc_extractor_1; in_channels 0,
+ * k = 64, widths 32/32/64, mlp 192->32->64) as ONE persistent tcgen05 kernel: grouping (layers.py:9-27), the two conv
  * stacks, attention / keypoints / attentive feature (layers.py:150-159) and the descriptor head (layers.py:200-209)
- * with every per-neighbour tensor kept in shared / tensor memory.
- *   q [B*M,3] sampled keypoints, xyz [B,N,3], feat [B,N,CIN] channels-last (NULL at level 1), idx [B*M*k] int32;
+ * with every per-neighbour tensor kept in shared / tensor memory; weights resident in shared memory, four tiles in
+ * flight per SM; the repeated max_k(X1) input of mlp1 (layers.py:203-205) enters as a per-keypoint bias evaluated once
+ * per keypoint in fp32.  (Levels 2 and 3: hrn_level_ws; any other level returns HRN_ERR_UNSUPPORTED.)
+ *   q [B*M,3] sampled keypoints, xyz [B,N,3], feat = NULL, idx [B*M*k] int32;
  *   Wpack (hrn_level_pack_bytes(level) bytes) and biases (hrn_level_bias_count(level) floats) as laid out by
  *   pcd_reg_hregnet_b200/engine_tc.pack_level.  Outputs per keypoint: out_xyz [B*M,3], out_af [B*M,CO], out_desc [B*M,CD]. */
 int hrn_level_fused(int level, const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,

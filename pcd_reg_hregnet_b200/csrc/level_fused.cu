@@ -15,40 +15,51 @@
 //   G -[d1;x1]-> C1d | C1x   (the two first layers share their input: ONE step with the weights stacked along N)
 //   C1d -d2-> C2 -d3-> E(CO, stays in TMEM)          | max_c, softmax over the k neighbours, keypoint
 //   C1x -x2-> C2 -x3-> X1(CO)                        | column max over the group
-//   mlp1 = Wb.X1 + Wa.max_k(X1) + Wc.(E*a)  (three K-segments accumulated in TMEM) -> CMID -mlp2-> CD -> max_k
-// Several independent 128-thread groups per CTA, each with its own tile, operand buffer and TMEM columns, overlap each
-// other's MMA / epilogue phases.  Weights (bf16 hi/lo UMMA tiles, execution order):
-//   level 1 (60 KB): RESIDENT in shared memory, 4 groups;
-//   level 2 (264 KB): STREAMED block by block from L2 through a 2-slot ring (cp.async.bulk + mbarrier) shared by 2
-//   groups that run the same block sequence: a slot is refilled with block l+2 when both groups' MMAs of block l
-//   have completed.
+//   mlp1 = Wb.X1 + Wc.(E*a)  (two K-segments accumulated in TMEM)  + [Wa.max_k(X1) + b]  -> CMID -mlp2-> CD -> max_k
+// The reference's third mlp1 segment, max_k(X1) repeated over the k neighbours (layers.py:203-204), is constant inside a
+// group: Wa.max_k(X1) + b is evaluated ONCE per keypoint on the CUDA cores in fp32 (while the tensor core runs the X1
+// segment) and enters the mlp1 epilogue as a per-keypoint bias (as in level_ws.cu) -- 8 MMA steps per tile instead of 9.
+// Four independent 128-thread groups per CTA, each with its own tile, operand buffer and TMEM columns, overlap each
+// other's MMA / epilogue phases; the weights (52 KB of bf16 hi/lo UMMA tiles + the 8 KB fp32 Wa) are RESIDENT in shared
+// memory and shared by the groups.  (Levels 2 and 3, whose weights have to stream, run on level_ws.cu.)
+//
+// Epilogue instruction diet (the kernel is bound by the SIMT work between the MMAs, not by the tensor pipe):
+//   * ReLU is folded into the operand conversions: hi = cvt.rz.relu.bf16x2(x), lo = cvt.rn.relu.bf16x2(x - hi) -- with
+//     a TRUNCATED hi the residual of a non-negative x is non-negative, and for x < 0 both halves clamp to 0;
+//   * the biases of the merged first layer ride in the MMA: the grouped input has 12 spare K columns, one of them is
+//     the constant 1 and its weight column is the bias;
+//   * max_k relu(x) = relu(max_k x): the column maxima are taken on the pre-activations.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
+#include <type_traits>
 
 namespace {
 
 constexpr int TMR = 128;
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-template <int KNBR_, int CIN_, int C1_, int C2_, int CO_, int CMID_, int CD_, bool RESIDENT_>
+template <int KNBR_, int CIN_, int C1_, int C2_, int CO_, int CMID_, int CD_>
 struct LevelCfg {
     static constexpr int KNBR = KNBR_, CIN = CIN_, C1 = C1_, C2 = C2_, CO = CO_, CMID = CMID_, CD = CD_;
-    static constexpr bool RESIDENT = RESIDENT_;
-    static constexpr int KG = (CIN + 4 + 15) / 16 * 16;             // grouped input: [feat(CIN) | rel xyz, |rel| | 0-pad]
+    static constexpr int KG = (CIN + 5 + 15) / 16 * 16;             // grouped input: [feat(CIN) | rel xyz, |rel|, 1 | 0-pad]
     // weight blocks in execution order; block = hi plane [K/8][N][16 B] + lo plane = 4*K*N bytes
-    static constexpr int NL = 9;                                    // blocks: [d1;x1] d2 d3 x2 x3 mb ma mc m2
+    static constexpr int NL = 8;                                    // blocks: [d1;x1] d2 d3 x2 x3 mb mc m2
     __host__ __device__ static constexpr int lk(int l) {            // K of block l
-        return l == 0 ? KG : (l == 1 || l == 3) ? C1 : (l == 2 || l == 4) ? C2 : (l == 8) ? CMID : CO;
+        return l == 0 ? KG : (l == 1 || l == 3) ? C1 : (l == 2 || l == 4) ? C2 : (l == 7) ? CMID : CO;
     }
     __host__ __device__ static constexpr int ln(int l) {
-        return l == 0 ? 2 * C1 : (l == 1 || l == 3) ? C2 : (l == 2 || l == 4) ? CO : (l == 8) ? CD : CMID;
+        return l == 0 ? 2 * C1 : (l == 1 || l == 3) ? C2 : (l == 2 || l == 4) ? CO : (l == 7) ? CD : CMID;
     }
     __host__ __device__ static constexpr int woff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += 4 * lk(i) * ln(i); return o; }
     static constexpr int W_BYTES = woff(NL);
-    static constexpr int SLOT = 4 * cmax(cmax(KG * 2 * C1, C2 * CO), cmax(CO * CMID, CMID * CD));
-    static constexpr int W_SMEM = RESIDENT ? W_BYTES : 2 * SLOT;
-    // biases (floats): d1,d2,d3,x1,x2,x3,m1,m2
+    // fp32 Wa (the max_k(X1) block of mlp1) behind the MMA blocks: two half-matrices [CO/2][CMID] -- input channels c with
+    // (c >> 2) & 1 == h in half h -- 16 floats apart modulo the banks, so that the two threads of an output read
+    // different banks
+    static constexpr int WA_HALF = CO / 2 * CMID + 16;
+    static constexpr int WA_BYTES = 2 * WA_HALF * 4;
+    static constexpr int PACK_BYTES = W_BYTES + WA_BYTES;
+    // biases (floats): d1,d2,d3,x1,x2,x3,m1,m2 (d1 / x1 ride in the first MMA and are not read here)
     static constexpr int B_D1 = 0, B_D2 = B_D1 + C1, B_D3 = B_D2 + C2, B_X1 = B_D3 + CO, B_X2 = B_X1 + C1,
                          B_X3 = B_X2 + C2, B_M1 = B_X3 + CO, B_M2 = B_M1 + CMID, B_COUNT = B_M2 + CD;
     // in-place operand buffer (chunks of 8 channels); the grouped input is consumed by one step, so it lives here too
@@ -62,17 +73,18 @@ struct LevelCfg {
     static constexpr int T_ACCX = CO;
     static constexpr int T_USED = CO + cmax(cmax(cmax(2 * C1, C2), CMID), cmax(CO, CD));
     static_assert(C2 <= C1, "the second detector layer must not overwrite the parked first descriptor layer");
-    static constexpr int WPG = KNBR / 32;                           // warps per keypoint group (1 or 2)
-    // RESIDENT: NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns,
-    // all sharing ONE resident copy of the weights (4 tiles in flight per SM instead of 2 CTAs x 1)
-    static constexpr int NG = RESIDENT ? 4 : 2;
-    static constexpr int GRP_SMEM = OP_BYTES + 2 * 4 * CW * 4;
-    static constexpr int SMEM_NG = W_SMEM + B_COUNT * 4 + NG * GRP_SMEM + 256;
+    static constexpr int WPG = KNBR / 32;                           // warps per keypoint group
+    static constexpr int KPT = TMR / KNBR;                          // keypoints per tile
+    // NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns, all sharing
+    // ONE resident copy of the weights (4 tiles in flight per SM)
+    static constexpr int NG = 4;
+    static constexpr int GRP_SMEM = OP_BYTES + 2 * 4 * CW * 4 + KPT * CMID * 4;
+    static constexpr int SMEM_NG = PACK_BYTES + B_COUNT * 4 + NG * GRP_SMEM + 256;
     static constexpr int T_COLS_NG = NG * T_USED <= 256 ? 256 : 512;
     static_assert(NG * T_USED <= 512, "TMEM (groups)");
-    static_assert(KNBR == 32 || KNBR == 64, "group reductions are written for 32 or 64 neighbours");
-    static_assert(T_USED <= 512, "TMEM");
+    static_assert(KNBR == 64 && CMID == 32 && CO % 8 == 0, "the per-keypoint mat-vec maps 64 threads onto 32 outputs x 2 halves");
     static_assert(CIN % 8 == 0, "feature chunks must be 8-aligned");
+    static_assert(SMEM_NG <= 227 * 1024, "shared memory");
 };
 
 __device__ __forceinline__ uint32_t make_idesc(int N) {
@@ -97,20 +109,44 @@ __device__ __forceinline__ void issue_layer(uint32_t a_hi, uint32_t a_lo, int K,
     }
 }
 
-// f[e] = relu(acc[e] + bias[e]) for 32 consecutive columns; the biases come from shared memory as 8 x 16-byte loads
-// (one scalar LDS per element was a quarter of the epilogue's instruction count)
-__device__ __forceinline__ void bias_relu32(const uint32_t (&v)[32], const float* __restrict__ bb, float (&f)[32]) {
+// f[e] = acc[e] (+ bias[e]) for 32 consecutive columns, NO activation; the biases come from shared memory as 8 x 16-byte
+// loads and are added two at a time (packed fp32x2)
+template <bool HAS_BIAS>
+__device__ __forceinline__ void bias32(const uint32_t (&v)[32], const float* __restrict__ bb, float (&f)[32]) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * q);
-        float s0, s1, s2, s3;                                   // two packed fp32x2 adds for the four bias additions
-        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), f2_pack(b4.x, b4.y)), s0, s1);
-        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), f2_pack(b4.z, b4.w)), s2, s3);
-        f[4 * q + 0] = fmaxf(s0, 0.f);
-        f[4 * q + 1] = fmaxf(s1, 0.f);
-        f[4 * q + 2] = fmaxf(s2, 0.f);
-        f[4 * q + 3] = fmaxf(s3, 0.f);
+        if (HAS_BIAS) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * q);
+            f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), f2_pack(b4.x, b4.y)), f[4 * q], f[4 * q + 1]);
+            f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), f2_pack(b4.z, b4.w)), f[4 * q + 2], f[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[4 * q + e] = __uint_as_float(v[4 * q + e]);
+        }
     }
+}
+
+// relu(x) of a pair as bf16 hi / lo with the ReLU folded into the two conversions: hi = rz_bf16(max(x, 0)),
+// lo = rn_bf16(max(x - hi, 0)).  hi is TRUNCATED, so the residual of a non-negative x is non-negative; for x < 0
+// hi = 0 and the residual x clamps to 0.  |relu(x) - hi - lo| <= 2^-16 |x|.
+__device__ __forceinline__ void split_pair_relu(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    uint32_t hb;
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(x1), "f"(x0));
+    const unsigned long long hf = ((unsigned long long)(hb & 0xffff0000u) << 32) | (unsigned long long)(hb << 16);
+    unsigned long long xv, rv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(x0), "f"(x1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rv) : "l"(xv), "l"(hf));
+    float r0, r1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(rv));
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+    hi = hb;
+}
+__device__ __forceinline__ void split_store8_relu(const float* x, uint4* dst_hi, uint4* dst_lo) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pair_relu(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+    *dst_hi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *dst_lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // lane c receives the op-reduction over the 32 lanes of v[c]  (31 shuffles)
@@ -140,9 +176,8 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
                   CD = Cfg::CD, WPG = Cfg::WPG, CW = Cfg::CW;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NG = Cfg::NG;
-    __shared__ __align__(8) uint64_t s_bar[2 + NG];                       // [0,1] weight slot landed, [2+g] MMA done (group g)
+    __shared__ __align__(8) uint64_t s_bar[NG];                           // MMA done (group g)
     __shared__ uint32_t s_tmem;
-    __shared__ unsigned int s_done[2];                                    // groups that have finished with weight slot 0 / 1
     __shared__ float s_red_all[NG][4][8];
 
     const int cta_tid = threadIdx.x;
@@ -150,51 +185,30 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     const int tid = cta_tid % TMR, warp = tid >> 5, lane = tid & 31;      // group-local ids (warp = TMEM lane quarter)
     float (*s_red)[8] = s_red_all[grp_id];
     uint8_t* sW = smem;
-    float* sB = reinterpret_cast<float*>(smem + Cfg::W_SMEM);
-    uint8_t* sOp = smem + Cfg::W_SMEM + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
+    const float* sWa = reinterpret_cast<const float*>(smem + Cfg::W_BYTES);
+    float* sB = reinterpret_cast<float*>(smem + Cfg::PACK_BYTES);
+    uint8_t* sOp = smem + Cfg::PACK_BYTES + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
     float* sCol = reinterpret_cast<float*>(sOp + Cfg::OP_BYTES);          // [4][CW] per-warp column partials
     float* sCol2 = sCol + 4 * CW;
+    float* sKpb = sCol2 + 4 * CW;                                         // [KPT][CMID] per-keypoint bias of mlp1
     auto gsync = [&]() {                                                  // barrier of this group only
-        if (NG == 1) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(grp_id + 1), "n"(TMR) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(grp_id + 1), "n"(TMR) : "memory");
     };
 
     const int gw0 = (warp / WPG) * WPG;                                   // first warp of this row's keypoint group
     const bool leader = (warp == gw0);
-    const uint32_t bar = smem_u32(&s_bar[2 + grp_id]);
-    const uint32_t bar_w[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
+    const uint32_t bar = smem_u32(&s_bar[grp_id]);
     uint32_t phase = 0;
-    uint32_t lcount = 0;                                                  // layers executed by this CTA (streaming)
     const int vgrid = (int)gridDim.x * NG, vblock = (int)blockIdx.x * NG + grp_id;   // groups act as virtual CTAs
-    // every group of a CTA runs the same number of rounds (streaming: the weight slots advance in lockstep); a group
-    // without a tile in the last round only takes part in the slot accounting
-    const int vfirst = (int)blockIdx.x * NG;
-    const int rounds = vfirst < n_tiles ? (n_tiles - vfirst + vgrid - 1) / vgrid : 0;
-    const uint32_t total_layers = (uint32_t)rounds * (uint32_t)Cfg::NL;
     const uint32_t wbase = smem_u32(sW);
-
-    auto stream_weights = [&](uint32_t L) {   // thread 0: fetch the weights of this CTA's L-th layer into slot L&1
-        const int li = (int)(L % (uint32_t)Cfg::NL);
-        int off = 0, bytes = 0;
-#pragma unroll
-        for (int l = 0; l < Cfg::NL; ++l) if (l == li) { off = Cfg::woff(l); bytes = 4 * Cfg::lk(l) * Cfg::ln(l); }
-        mbar_expect_tx(bar_w[L & 1], (uint32_t)bytes);
-        bulk_g2s(wbase + (L & 1) * Cfg::SLOT, Wpack + off, (uint32_t)bytes, bar_w[L & 1]);
-    };
 
     // ---- one-time setup ---------------------------------------------------------------------------------------
     if (cta_tid == 0) {
-        for (int i = 0; i < 2 + NG; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
-        s_done[0] = 0; s_done[1] = 0;
+        for (int i = 0; i < NG; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (!Cfg::RESIDENT) {
-            if (total_layers > 0) stream_weights(0);
-            if (total_layers > 1) stream_weights(1);
-        }
     }
-    if (Cfg::RESIDENT)
-        for (int i = cta_tid; i < Cfg::W_BYTES / 16; i += TMR * NG)
-            reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
+    for (int i = cta_tid; i < Cfg::PACK_BYTES / 16; i += TMR * NG)
+        reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
     for (int i = cta_tid; i < Cfg::B_COUNT; i += TMR * NG) sB[i] = __ldg(biases + i);
     if (cta_tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS_NG) : "memory");
@@ -210,51 +224,38 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     uint4* op_hi = reinterpret_cast<uint4*>(sOp);
     uint4* op_lo = op_hi + Cfg::OPC * TMR;
 
-    // streaming: this group is done with the weights of its block `lcount`; the last group to get here refills the slot
-    auto release_slot = [&]() {
-        unsigned int* cnt = &s_done[lcount & 1];
-        if (atomicAdd(cnt, 1u) == (unsigned)(NG - 1)) {
-            *cnt = 0;
-            if (lcount + 2 < total_layers) stream_weights(lcount + 2);
-        }
-    };
-    // operand ready in smem -> one thread issues layer `li` -> everybody waits for the accumulator
-    auto run_layer = [&](uint32_t a_hi, uint32_t a_lo, int li, int tcol, bool acc) {
-        const int K = Cfg::lk(li), Nn = Cfg::ln(li);
+    // operand ready in smem -> one thread issues layer `li`
+    auto issue = [&](int li, int tcol, bool acc) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         gsync();
         if (tid == 0) {
-            uint32_t w_addr = wbase + Cfg::woff(li);
-            if (!Cfg::RESIDENT) {
-                mbar_wait(bar_w[lcount & 1], (lcount >> 1) & 1);
-                w_addr = wbase + (lcount & 1) * Cfg::SLOT;
-            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_layer(a_hi, a_lo, K, w_addr, Nn, tmem + tcol, acc);
+            issue_layer(aOp_hi, aOp_lo, Cfg::lk(li), wbase + Cfg::woff(li), Cfg::ln(li), tmem + tcol, acc);
             umma_commit(bar);
         }
+    };
+    // -> everybody waits for the accumulator
+    auto wait_layer = [&]() {
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!Cfg::RESIDENT && tid == 0) release_slot();
-        ++lcount;
     };
-    // accumulator [tcol, tcol+Nn) -> relu(x + b) -> bf16 hi/lo operand (in place)
-    auto epi_to_operand = [&](int tcol, int Nn, const float* bb) {
+    auto run_layer = [&](int li, int tcol, bool acc) { issue(li, tcol, acc); wait_layer(); };
+    // accumulator [tcol, tcol+Nn) -> relu(x (+ b)) -> bf16 hi/lo operand (in place)
+    auto epi_to_operand = [&](int tcol, int Nn, const float* bb, auto has_bias) {
         for (int c0 = 0; c0 < Nn; c0 += 32) {
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + tcol + c0, v);
-            bias_relu32(v, bb + c0, f);
+            bias32<decltype(has_bias)::value>(v, bb + c0, f);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
-                                    f[ch * 8 + 6], f[ch * 8 + 7]};
-                split_store8(x, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
-            }
+            for (int ch = 0; ch < 4; ++ch)
+                split_store8_relu(f + ch * 8, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
         }
     };
+    using yes_t = std::true_type;
+    using no_t = std::false_type;
     // value of column c for this row's keypoint group after the per-warp partials were published in `buf`
     auto col_max = [&](const float* buf, int c) {
         float v = buf[gw0 * CW + c];
@@ -262,18 +263,8 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         return v;
     };
 
-    for (int round = 0; round < rounds; ++round) {
-        const int tile = vblock + round * vgrid;
-        if (tile >= n_tiles) {                       // no tile left for this group: keep the weight slots moving
-            if (!Cfg::RESIDENT && tid == 0)
-                for (int l = 0; l < Cfg::NL; ++l) {
-                    mbar_wait(bar_w[lcount & 1], (lcount >> 1) & 1);       // stay in step with the groups that use the block
-                    release_slot();
-                    ++lcount;
-                }
-            continue;
-        }
-        // ---- grouped input  [feat[idx] | rel xyz, |rel|] -> operand buffer ------------------------------------
+    for (int tile = vblock; tile < n_tiles; tile += vgrid) {
+        // ---- grouped input  [feat[idx] | rel xyz, |rel|, 1] -> operand buffer ------------------------------------
         const long long r = (long long)tile * TMR + tid;
         const long long bm = r / KNBR;
         const long long b = bm / M;
@@ -299,7 +290,8 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             }
         }
         {
-            const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 0.f, 0.f, 0.f, 0.f};
+            // the constant 1 multiplies the bias column of the merged first layer
+            const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 1.f, 0.f, 0.f, 0.f};
             split_store8(x, op_hi + (CIN / 8) * TMR + tid, op_lo + (CIN / 8) * TMR + tid);
 #pragma unroll
             for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {             // K padding
@@ -308,12 +300,12 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             }
         }
         // ---- first layer of both chains: work columns [0, C1) = detector, [C1, 2 C1) = descriptor (parked) ------
-        run_layer(aOp_hi, aOp_lo, 0, Cfg::T_ACC0, false);
+        run_layer(0, Cfg::T_ACC0, false);
         // ---- detector chain ------------------------------------------------------------------------------------
-        epi_to_operand(Cfg::T_ACC0, C1, sB + Cfg::B_D1);
-        run_layer(aOp_hi, aOp_lo, 1, Cfg::T_ACC0, false);
-        epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_D2);
-        run_layer(aOp_hi, aOp_lo, 2, Cfg::T_ACCE, false);
+        epi_to_operand(Cfg::T_ACC0, C1, sB, no_t{});
+        run_layer(1, Cfg::T_ACC0, false);
+        epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_D2, yes_t{});
+        run_layer(2, Cfg::T_ACCE, false);
         // ---- attention: a = softmax_k(max_c E), keypoint = sum_k a * nn -------------------------------------
         float x1 = 0.f;                                                   // post-ReLU values are >= 0
         for (int c0 = 0; c0 < CO; c0 += 32) {
@@ -345,44 +337,52 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         const float a = ex / s0;
         if (leader && lane < 3) out_xyz[bm * 3 + lane] = (lane == 0 ? s1 : (lane == 1 ? s2 : s3)) / s0;
         // ---- descriptor chain ----------------------------------------------------------------------------------
-        epi_to_operand(Cfg::T_ACC0 + C1, C1, sB + Cfg::B_X1);
-        run_layer(aOp_hi, aOp_lo, 3, Cfg::T_ACC0, false);
-        epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_X2);
-        run_layer(aOp_hi, aOp_lo, 4, Cfg::T_ACCX, false);
-        // X1 -> operand, and its column maximum over the rows of the group
+        epi_to_operand(Cfg::T_ACC0 + C1, C1, sB, no_t{});
+        run_layer(3, Cfg::T_ACC0, false);
+        epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_X2, yes_t{});
+        run_layer(4, Cfg::T_ACCX, false);
+        // X1 -> operand, and its column maximum over the rows of the group (taken before the ReLU: max and ReLU commute)
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCX + c0, v);
-            bias_relu32(v, sB + Cfg::B_X3 + c0, f);
+            bias32<true>(v, sB + Cfg::B_X3 + c0, f);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
-                                    f[ch * 8 + 6], f[ch * 8 + 7]};
-                split_store8(x, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
-            }
+            for (int ch = 0; ch < 4; ++ch)
+                split_store8_relu(f + ch * 8, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
             const float cm = warp_transpose_reduce<true>(f, lane);
-            sCol[warp * CW + c0 + lane] = cm;
+            sCol[warp * CW + c0 + lane] = fmaxf(cm, 0.f);
         }
-        run_layer(aOp_hi, aOp_lo, 5, Cfg::T_ACC0, false);                 // mlp1 += Wb.X1 (barrier inside publishes sCol)
-        // max_k(X1) broadcast over the group's rows as the next K-segment
-#pragma unroll 4
-        for (int ch = 0; ch < CO / 8; ++ch) {
-            float x[8];
+        issue(5, Cfg::T_ACC0, false);                                     // mlp1 = Wb.X1 (the barrier inside publishes sCol)
+        // per-keypoint bias  Wa . max_k(X1) + b  on the CUDA cores (fp32) while the tensor core runs the X1 segment:
+        // thread (output j, half hf) of the keypoint of its own rows sums the input channels c with (c >> 2) & 1 == hf
+        {
+            const int u = tid & 63, j = u >> 1, hf = u & 1;
+            const float* wa = sWa + hf * Cfg::WA_HALF + j;
+            const float* m0 = sCol + gw0 * CW + 4 * hf;
+            float acc = hf ? 0.f : sB[Cfg::B_M1 + j];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = col_max(sCol, ch * 8 + e);
-            split_store8(x, op_hi + ch * TMR + tid, op_lo + ch * TMR + tid);
+            for (int i = 0; i < CO / 8; ++i) {
+                const float4 p0 = *reinterpret_cast<const float4*>(m0 + 8 * i);
+                const float4 p1 = *reinterpret_cast<const float4*>(m0 + CW + 8 * i);
+                acc = fmaf(wa[(4 * i + 0) * CMID], fmaxf(p0.x, p1.x), acc);
+                acc = fmaf(wa[(4 * i + 1) * CMID], fmaxf(p0.y, p1.y), acc);
+                acc = fmaf(wa[(4 * i + 2) * CMID], fmaxf(p0.z, p1.z), acc);
+                acc = fmaf(wa[(4 * i + 3) * CMID], fmaxf(p0.w, p1.w), acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (hf == 0) sKpb[(tid >> 6) * CMID + j] = acc;
         }
-        run_layer(aOp_hi, aOp_lo, 6, Cfg::T_ACC0, true);                  // mlp1 += Wa.max_k(X1)
-        // attentive feature map E*a as the third K-segment; attentive feature = its column sum over the group
+        wait_layer();
+        // attentive feature map E*a as the second K-segment; attentive feature = its column sum over the group
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCE + c0, v);
-            bias_relu32(v, sB + Cfg::B_D3 + c0, f);
+            bias32<true>(v, sB + Cfg::B_D3 + c0, f);
             const f32x2_t a2 = f2_pack(a, a);
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) f2_unpack(f2_mul(f2_pack(f[e], f[e + 1]), a2), f[e], f[e + 1]);
+            for (int e = 0; e < 32; e += 2) f2_unpack(f2_mul(f2_pack(fmaxf(f[e], 0.f), fmaxf(f[e + 1], 0.f)), a2), f[e], f[e + 1]);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
@@ -392,23 +392,23 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             const float cs = warp_transpose_reduce<false>(f, lane);
             sCol2[warp * CW + c0 + lane] = cs;
         }
-        run_layer(aOp_hi, aOp_lo, 7, Cfg::T_ACC0, true);                  // mlp1 += Wc.(E*a)
+        run_layer(6, Cfg::T_ACC0, true);                                  // mlp1 += Wc.(E*a)  (barrier: sCol2, sKpb published)
         if (leader)
             for (int c = lane; c < CO; c += 32) {
                 float v = sCol2[gw0 * CW + c];
                 if (WPG == 2) v += sCol2[(gw0 + 1) * CW + c];
                 out_af[bm * CO + c] = v;
             }
-        // ---- mlp1 epilogue -> mlp2 -> descriptor = max_k -------------------------------------------------------
-        epi_to_operand(Cfg::T_ACC0, CMID, sB + Cfg::B_M1);
-        run_layer(aOp_hi, aOp_lo, 8, Cfg::T_ACCX, false);
+        // ---- mlp1 epilogue (bias = per-keypoint row) -> mlp2 -> descriptor = max_k ------------------------------
+        epi_to_operand(Cfg::T_ACC0, CMID, sKpb + (tid >> 6) * CMID, yes_t{});
+        run_layer(7, Cfg::T_ACCX, false);
         for (int c0 = 0; c0 < CD; c0 += 32) {
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCX + c0, v);
-            bias_relu32(v, sB + Cfg::B_M2 + c0, f);
+            bias32<true>(v, sB + Cfg::B_M2 + c0, f);
             const float cm = warp_transpose_reduce<true>(f, lane);
-            sCol[warp * CW + c0 + lane] = cm;
+            sCol[warp * CW + c0 + lane] = fmaxf(cm, 0.f);
         }
         gsync();
         if (leader)
@@ -421,15 +421,15 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(Cfg::T_COLS_NG) : "memory");
 }
 
-using CfgL1 = LevelCfg<64, 0, 32, 32, 64, 32, 64, true>;       // detector_1 / desc_extractor_1 (models.py:14,22)
-using CfgL2 = LevelCfg<32, 64, 64, 64, 128, 64, 128, false>;   // detector_2 / desc_extractor_2 (models.py:15,23)
+using CfgL1 = LevelCfg<64, 0, 32, 32, 64, 32, 64>;             // detector_1 / desc_extractor_1 (models.py:14,22)
 
 template <class Cfg>
 int launch_level(const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,
                  const float* biases, float* out_xyz, float* out_af, float* out_desc, int B, int M, int N, cudaStream_t st) {
     const int n_tiles = (int)((long long)B * M * Cfg::KNBR / TMR);
     auto kern = level_fused_kernel<Cfg>;
-    HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_NG));
+    static hrn_once_per_device attr;
+    if (attr.need()) HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_NG));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -443,10 +443,9 @@ int launch_level(const float* q, const float* xyz, const float* feat, const int3
 
 }  // namespace
 
-// Fused detector + descriptor of hierarchy level `level` (1 or 2).  q [B*M,3] sampled keypoint coordinates,
-// xyz [B,N,3], feat [B,N,CIN] channels-last previous-level attentive features (level 2; NULL for level 1),
-// idx [B*M*k] int32 neighbour indices; Wpack / biases from engine_tc.pack_level (LevelCfg layout, execution order).
-// Outputs per keypoint: out_xyz [B*M,3], out_af [B*M,CO], out_desc [B*M,CD].
+// Fused detector + descriptor of hierarchy level 1.  q [B*M,3] sampled keypoint coordinates, xyz [B,N,3], feat = NULL
+// (level 1 has no input features), idx [B*M*k] int32 neighbour indices; Wpack / biases from engine_tc.pack_level (LevelCfg
+// layout, execution order, then the fp32 Wa halves).  Outputs per keypoint: out_xyz [B*M,3], out_af [B*M,CO], out_desc [B*M,CD].
 HRN_API int hrn_level_fused(int level, const float* q, const float* xyz, const float* feat, const int32_t* idx,
                             const void* Wpack, const float* biases, float* out_xyz, float* out_af, float* out_desc,
                             int B, int M, int N, int k, void* stream) {
@@ -455,10 +454,8 @@ HRN_API int hrn_level_fused(int level, const float* q, const float* xyz, const f
     if (B == 0) return HRN_OK;
     if (level == 1 && k == CfgL1::KNBR && !feat)
         return launch_level<CfgL1>(q, xyz, nullptr, idx, Wpack, biases, out_xyz, out_af, out_desc, B, M, N, (cudaStream_t)stream);
-    if (level == 2 && k == CfgL2::KNBR && feat)
-        return launch_level<CfgL2>(q, xyz, feat, idx, Wpack, biases, out_xyz, out_af, out_desc, B, M, N, (cudaStream_t)stream);
-    return HRN_ERR_UNSUPPORTED;
+    return HRN_ERR_UNSUPPORTED;     // levels 2 and 3: hrn_level_ws
 }
 
-HRN_API int hrn_level_pack_bytes(int level) { return level == 1 ? CfgL1::W_BYTES : level == 2 ? CfgL2::W_BYTES : -1; }
-HRN_API int hrn_level_bias_count(int level) { return level == 1 ? CfgL1::B_COUNT : level == 2 ? CfgL2::B_COUNT : -1; }
+HRN_API int hrn_level_pack_bytes(int level) { return level == 1 ? CfgL1::PACK_BYTES : -1; }
+HRN_API int hrn_level_bias_count(int level) { return level == 1 ? CfgL1::B_COUNT : -1; }

@@ -101,8 +101,7 @@ def layer_tc_groupmax(view, W, b, act, k, prec=3):
 # fused level kernels (csrc/level_fused.cu)
 # ------------------------------------------------------------------------------------------------------------------
 _level_cache = {}
-_LEVEL_DIMS = {1: dict(k=64, cin=0, c1=32, c2=32, co=64, cmid=32, cd=64),
-               2: dict(k=32, cin=64, c1=64, c2=64, co=128, cmid=64, cd=128)}
+_LEVEL_DIMS = {1: dict(k=64, cin=0, c1=32, c2=32, co=64, cmid=32, cd=64)}      # levels 2 / 3: level_ws below
 
 
 def _umma_tiles(W, K_pad):
@@ -131,10 +130,12 @@ def which_level(k, cin, det, desc):
 
 
 def pack_level(level, det, desc):
-    """Folded parameter dicts of detector_l / desc_extractor_l -> (Wpack uint8, biases fp32) in the LevelCfg layout of
-    csrc/level_fused.cu: blocks in execution order [d1;x1] d2 d3 x2 x3 mlp1[X1] mlp1[max X1] mlp1[E*a] mlp2.  The grouped
-    input channels are re-ordered from the reference's [rel(3), dist(1), feat(C)] (layers.py:21-26) to
-    [feat(C), rel(3), dist(1), 0-pad] so that the gathered feature row lands on 8-channel chunk boundaries."""
+    """Folded parameter dicts of detector_1 / desc_extractor_1 -> (Wpack uint8, biases fp32) in the LevelCfg layout of
+    csrc/level_fused.cu: MMA blocks in execution order [d1;x1] d2 d3 x2 x3 mlp1[X1] mlp1[E*a] mlp2, then the fp32 block
+    mlp1[max_k X1] for the per-keypoint mat-vec (two half-matrices [CO/2][CMID], input channels c with (c >> 2) & 1 == h
+    in half h, 16 floats of padding behind each).  The grouped input channels are re-ordered from the reference's
+    [rel(3), dist(1), feat(C)] (layers.py:21-26) to [feat(C), rel(3), dist(1), 1, 0-pad]: the gathered feature row lands
+    on 8-channel chunk boundaries, and the constant-1 channel multiplies the biases of d1 / x1 (stored as a weight column)."""
     key = (level,) + tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
     hit = _level_cache.get(key)
     if hit is not None:
@@ -143,14 +144,20 @@ def pack_level(level, det, desc):
     (d1, bd1, _), (d2, bd2, _), (d3, bd3, _) = det["convs"]
     (x1, bx1, _), (x2, bx2, _), (x3, bx3, _) = desc["convs"]
     (m1, bm1, _), (m2, bm2, _) = desc["mlp"]
-    CO, cin = d["co"], d["cin"]
-    KG = (cin + 4 + 15) // 16 * 16
+    CO, cin, CMID = d["co"], d["cin"], d["cmid"]
+    KG = (cin + 5 + 15) // 16 * 16
     perm = list(range(4, 4 + cin)) + [0, 1, 2, 3]
-    first = torch.cat([d1[:, perm], x1[:, perm]], 0).contiguous()       # both chains read the same grouped input
+    first = torch.cat([torch.cat([d1[:, perm], bd1[:, None]], 1), torch.cat([x1[:, perm], bx1[:, None]], 1)], 0).contiguous()
     parts = [_umma_tiles(first, KG), _umma_tiles(d2, d["c1"]), _umma_tiles(d3, d["c2"]),
              _umma_tiles(x2, d["c1"]), _umma_tiles(x3, d["c2"]),
-             _umma_tiles(m1[:, CO:2 * CO].contiguous(), CO), _umma_tiles(m1[:, :CO].contiguous(), CO),
-             _umma_tiles(m1[:, 2 * CO:].contiguous(), CO), _umma_tiles(m2, d["cmid"])]
+             _umma_tiles(m1[:, CO:2 * CO].contiguous(), CO), _umma_tiles(m1[:, 2 * CO:].contiguous(), CO),
+             _umma_tiles(m2, CMID)]
+    Wa = m1[:, :CO]                                                       # [CMID, CO]: the max_k(X1) block (layers.py:203-205)
+    c = torch.arange(CO, device=Wa.device)
+    pad = torch.zeros(16, dtype=torch.float32, device=Wa.device)
+    for h in (0, 1):
+        parts.append(Wa[:, c[((c >> 2) & 1) == h]].t().contiguous().view(-1).view(torch.uint8))
+        parts.append(pad.view(torch.uint8))
     Wpack = torch.cat(parts).contiguous()
     biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()
     from ._lib import lib
