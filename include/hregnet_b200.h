@@ -163,6 +163,17 @@ int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl,
                  int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, int prec,
                  void* stream);
 
+/* CoarseReg's conv stack convs_1 (528 -> 512 -> 512 -> 512, models/HRegNet/layers.py:364-375) + its attention tail
+ * (layers.py:384-390: a = softmax_k(max_c Y), attentive feature = sum_k a Y) on a CLUSTER OF TWO CTAs per 128-row tile: each
+ * CTA computes one half of every layer's output columns, the hidden activations travel between the two SMs as 32-column
+ * operand blocks through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster) and never reach HBM.
+ *   W: per column half (rank 0, rank 1; w_rank_bytes each) the K=16 weight pieces of the three layers, bias: per half
+ *   b1|b2|b3, both as laid out by pcd_reg_hregnet_b200/engine_tc.pack_chain_wide; n1..n3 full widths (multiples of 64,
+ *   <= 512), chunks0 = 8-wide K chunks of the virtual input (even), kseg = 8, rows % 128 == 0, prec as hrn_chain_tc.
+ *   Outputs: G [rows / kseg, n3] attentive feature, a [rows] attention weights (nullable). */
+int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2, int n3,
+                   int chunks0, int kseg, float* G, float* a, long long rows, int prec, void* stream);
+
 /* Level 1 of HierFeatureExtraction (models/HRegNet/models.py:27-28: detector_1 + desc_extractor_1; in_channels 0,
  * k = 64, widths 32/32/64, mlp 192->32->64) as ONE persistent tcgen05 kernel: grouping (layers.py:9-27), the two conv
  * stacks, attention / keypoints / attentive feature (layers.py:150-159) and the descriptor head (layers.py:200-209)

@@ -60,6 +60,7 @@ def _side_stream(device):
 
 _FUSED_HEADS = True      # tc mode: per-keypoint heads (mlp1/mlp2/mlp3, width <= 256) as one chain launch
 _FUSED_LEVELS = True     # tc mode: run levels 1 and 2 (detector + descriptor) as one persistent tcgen05 kernel each
+_WIDE_CHAIN = True       # tc modes: CoarseReg convs_1 + attention tail on a 2-CTA cluster per tile (csrc/chain_wide.cu)
 _COSINE_TC = True        # tc modes: CoarseReg's cosine-similarity features as one tcgen05 kernel per similarity
 _LEVEL_WS = (2, 3)         # tc mode: levels that run on the warp-specialised fused level kernel (csrc/level_ws.cu)
 
@@ -534,8 +535,18 @@ def _coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k, both, want_dis
     _cosine_features(s_nbr, d_nbr, idx, misc, 14, 15)
     v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
     v.add(misc).add(sdesc_cl.view(B * N1, C), SEG_BROADCAST).add(ddesc_cl.view(B * N2, C), SEG_GATHER)
-    F = stack(v, P["convs_1"])
-    cor, w, _ = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
+    wide = False
+    if _tc() and _FUSED_CHAINS and _WIDE_CHAIN:
+        from . import engine_tc
+        wide = engine_tc.chain_wide_supported(v, P["convs_1"], k)
+    if wide:
+        # conv stack + attention on a 2-CTA cluster per tile: the 512-wide activations never reach HBM (csrc/chain_wide.cu)
+        af, a = engine_tc.chain_wide(v, P["convs_1"], k)
+        cor = group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2).view(B, N1, 3)
+        w = stack(RowsView(B * N1).add(af), P["mlp"], last_act=ACT_SIGMOID).view(B, N1)
+    else:
+        F = stack(v, P["convs_1"])
+        cor, w, _ = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
     if want_dists:
         # model_v4's CoarseReg also returns two by-products of the feature assembly (model_v4/layers.py:252,282):
         # coord_dist = |candidate - source keypoint| (geometry column 3) and feats_dist = 1 - the normalised

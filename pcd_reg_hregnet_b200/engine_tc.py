@@ -320,5 +320,74 @@ def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act
     return Y, G, a
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# wide chain on a 2-CTA cluster (csrc/chain_wide.cu): CoarseReg convs_1 + attention tail
+# ------------------------------------------------------------------------------------------------------------------
+_wide_cache = {}
+
+
+def chain_wide_supported(view, layers, k):
+    """Three folded ReLU layers, every width a multiple of 64 and <= 512, groups of 8 rows, rows a multiple of 128."""
+    from ._lib import ACT_RELU
+    if len(layers) != 3 or k != 8 or view.rows % 128 != 0:
+        return False
+    for W, b, act in layers:
+        if W.shape[0] % 64 or W.shape[0] > 512 or act != ACT_RELU:
+            return False
+    if max(W.shape[0] for W, _, _ in layers) <= 256:
+        return False                                      # the single-CTA chain kernel covers these
+    for mat, mode, ch, col0, scale in view.segs:
+        if ch % 4 or col0 % 4 or mat.stride(0) % 4 or mat.data_ptr() % 16:
+            return False
+    return True
+
+
+def pack_chain_wide(layers, seg_channels, prec=3):
+    """-> (Wpack uint8 [2 * rank_bytes], rank_bytes, bias fp32 [2 * sum(n/2)], chunks0, widths).  Rank r of the cluster
+    computes output columns [r n/2, (r+1) n/2) of every layer.  Layer 1's K order = the virtual rows (segments padded to 8
+    channels, total to 16); layers 2 / 3 consume the previous layer's 32-column blocks in the order both CTAs produce
+    them -- block j of rank 0, block j of rank 1, ... -- so their weight columns are permuted accordingly."""
+    key = tuple((W.data_ptr(), W._version) for W, _, _ in layers) + (tuple(seg_channels), prec, "wide")
+    hit = _wide_cache.get(key)
+    if hit is not None:
+        return hit
+    W1 = layers[0][0]
+    chunks = sum((c + 7) // 8 for c in seg_channels)
+    chunks0 = (chunks + 1) // 2 * 2
+    W1p = torch.zeros(W1.shape[0], chunks0 * 8, dtype=torch.float32, device=W1.device)
+    src = dst = 0
+    for c in seg_channels:
+        W1p[:, dst:dst + c] = W1[:, src:src + c]
+        src += c
+        dst += (c + 7) // 8 * 8
+    mats = [W1p]
+    for li in (1, 2):
+        W = layers[li][0]
+        h = layers[li - 1][0].shape[0] // 2               # previous layer's columns per rank
+        order = torch.cat([torch.arange(rk * h + 32 * j, rk * h + 32 * j + 32) for j in range(h // 32) for rk in (0, 1)])
+        mats.append(W[:, order.to(W.device)].contiguous())
+    widths = [m.shape[0] for m in mats]
+    per_rank, bias = [], []
+    for rk in (0, 1):
+        per_rank.append(torch.cat([_pieces(m[rk * (n // 2):(rk + 1) * (n // 2)].contiguous(), m.shape[1], prec)
+                                   for m, n in zip(mats, widths)]))
+        bias += [b[rk * (n // 2):(rk + 1) * (n // 2)] for (_, b, _), n in zip(layers, widths)]
+    assert per_rank[0].numel() == per_rank[1].numel()
+    Wpack = torch.cat(per_rank).contiguous()
+    return _remember(_wide_cache, key, W1, (Wpack, per_rank[0].numel(), torch.cat(bias).contiguous(), chunks0, widths))
+
+
+def chain_wide(view, layers, kseg=8, prec=None):
+    """convs + attention tail on the virtual rows: returns (AF [rows / kseg, n3], a [rows])  (layers.py:364-390)."""
+    prec = engine.mma_prec() if prec is None else prec
+    Wpack, rank_bytes, bias, chunks0, widths = pack_chain_wide(layers, [s[2] for s in view.segs], prec)
+    dev = bias.device
+    G = torch.empty(view.rows // kseg, widths[2], dtype=torch.float32, device=dev)
+    a = torch.empty(view.rows, dtype=torch.float32, device=dev)
+    engine.call("hrn_chain_wide", ctypes.byref(view.c), engine.ptr(Wpack), rank_bytes, engine.ptr(bias), widths[0], widths[1],
+                widths[2], chunks0, kseg, engine.ptr(G), engine.ptr(a), view.rows, prec, engine.stream())
+    return G, a
+
+
 def chain3(view, layers, mode, kseg, want_rows=True, want_groups=True):
     return chain(view, layers, mode, kseg, want_rows, want_groups)

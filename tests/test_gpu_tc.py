@@ -252,3 +252,46 @@ def test_single_pass_fp16_chain(kseg, mode, dims):
         a_ref = torch.softmax(Xg.max(dim=2)[0], dim=1)
         assert float((a.double().view(-1, kseg) - a_ref).abs().max()) < 1e-2
         assert float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale < 2 * tol
+
+
+@pytest.mark.parametrize("B,M,dims,prec,tol", [
+    (2, 256, [512, 512, 512], 3, 1e-4),          # CoarseReg convs_1 as in the model (528 -> 512 -> 512 -> 512), 32 tiles
+    (1, 16, [512, 512, 512], 3, 1e-4),           # one tile: a single cluster
+    (5, 80, [512, 256, 384], 3, 1e-4),           # 25 tiles, unequal widths (blocks per rank 8 / 4 / 6)
+    (37, 256, [512, 512, 512], 3, 1e-4),         # 592 tiles: several rounds per cluster, ring / phase wrap-around
+    (2, 256, [512, 512, 512], 1, 3e-3),          # single-pass fp16 operands
+])
+def test_chain_wide_cluster_kernel(B, M, dims, prec, tol):
+    """csrc/chain_wide.cu (2-CTA cluster, hidden activations through DSMEM) against an fp64 evaluation of the three
+    layers + softmax_k(max_c) attention + attentive feature (reference layers.py:364-390)."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    kseg, N, C = 8, 300, 256
+    g = torch.Generator().manual_seed(B * 1000 + M + dims[1])
+    rows = B * M * kseg
+    misc = torch.randn(rows, 16, generator=g).to(DEV)
+    src = torch.randn(B * M, C, generator=g).to(DEV)
+    dst = torch.randn(B * N, C, generator=g).to(DEV)
+    idx = torch.randint(0, N, (B, M, kseg), generator=g).int().to(DEV)
+    v = RowsView(rows, group=kseg, gather_idx=idx, rows_per_batch=M * kseg, src_rows_per_batch=N)
+    v.add(misc).add(src, SEG_BROADCAST).add(dst, SEG_GATHER)
+    r = torch.arange(rows, device=DEV)
+    X = torch.cat([misc, src[r // kseg], dst[(r // (M * kseg)) * N + idx.view(-1).long()]], 1).double()
+    widths = [16 + 2 * C] + dims
+    layers = []
+    for i in range(3):
+        W = (torch.randn(widths[i + 1], widths[i], generator=g) / widths[i] ** 0.5).to(DEV)
+        b = (torch.randn(widths[i + 1], generator=g) * 0.1).to(DEV)
+        layers.append((W, b, ACT_RELU))
+        X = torch.relu(X @ W.double().t() + b.double())
+    assert engine_tc.chain_wide_supported(v, layers, kseg)
+    G, a = engine_tc.chain_wide(v, layers, kseg, prec=prec)
+    G2, a2 = engine_tc.chain_wide(v, layers, kseg, prec=prec)          # a second launch: same bits (no race between the CTAs)
+    torch.cuda.synchronize()
+    Xg = X.view(-1, kseg, dims[2])
+    scale = float(X.abs().max())
+    a_ref = torch.softmax(Xg.max(dim=2)[0], dim=1)
+    e_a = float((a.double().view(-1, kseg) - a_ref).abs().max())
+    e_g = float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale
+    print(f"chain_wide B={B} M={M} dims={dims} prec={prec}: a {e_a:.2e}  AF {e_g:.2e}")
+    assert e_a < tol and e_g < tol, (e_a, e_g)
+    assert torch.equal(G, G2) and torch.equal(a, a2)
