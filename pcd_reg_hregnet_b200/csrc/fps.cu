@@ -21,6 +21,7 @@
 //     memory (the caller's scratch buffer), same reduction.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -421,6 +422,274 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Culled cluster variant (unweighted, whole cloud in shared memory): the same iteration as fps_cluster_kernel, but
+// the points are first BINNED by a 10-bit Morton cell (one counting sort in shared memory), so that the 512 points of
+// a warp are neighbours in space, and every warp keeps the bounding box of its points.  A new centre can only lower
+// the min-distance of a point that is closer to it than that min-distance; per warp:
+//     bound = fma(bz,bz, fma(bx,bx, rn(by*by))),   b? = max(lo? - c?, c? - hi?, 0)      (the kernel's own rounding)
+// is a lower bound of every distance the update would compute (rn, x*x and fma are monotone), so if
+// bound >= max_p pt[p] the update cannot change anything: the warp skips it and resends its previous packet.  Late in
+// the sampling a centre touches 1-3 of the 32 warps of a cloud; the iteration is then the packet exchange alone.
+// The result is bit-identical: same arithmetic per point, the reference's tie-break key travels with every point
+// (the thread <-> point mapping is free, see fps_kernel).
+template <int THREADS, int Q>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int32_t* __restrict__ idx_out, int N, int M,
+                int log2T) {
+    constexpr int NWARP = THREADS / 32;
+    constexpr int CS = 2;
+    constexpr int PER_CTA = THREADS * Q;                   // sorted positions per CTA
+    constexpr int NBIN = 1024;
+    constexpr int S = CS * NWARP;                          // packets per iteration
+    static_assert(S == 32, "one packet per lane");
+    static_assert(Q % 2 == 0, "packed update");
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    unsigned long long* s_mail = reinterpret_cast<unsigned long long*>(s_dyn);      // [2][S]
+    float* s_cloud = reinterpret_cast<float*>(s_mail + 2 * S);                       // [N][3]
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_cloud + 3 * (size_t)N);          // [NBIN]
+    unsigned short* s_perm = reinterpret_cast<unsigned short*>(s_hist + NBIN);        // [PER_CTA]
+    __shared__ __align__(8) uint64_t s_mbar[2];
+    __shared__ float s_box[NWARP][6];
+    __shared__ unsigned s_wsum[NWARP];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int b = blockIdx.x / CS;
+    xyz += (size_t)b * N * 3;
+    if (temp_io) temp_io += (size_t)b * N;
+    idx_out += (size_t)b * M;
+    const unsigned tmask = (1u << log2T) - 1u;
+    auto key_of = [&](int k) -> unsigned {
+        const unsigned r = (log2T > 0) ? (__brev((unsigned)k & tmask) >> (32 - log2T)) : 0u;
+        return (r << 12) | ((unsigned)k >> log2T);
+    };
+    auto k_of_key = [&](unsigned key) -> int {
+        return ((log2T > 0) ? (int)(__brev(key >> 12) >> (32 - log2T)) : 0) + (int)((key & 0xfffu) << log2T);
+    };
+
+    // ---- the cloud, its bounding box ----------------------------------------------------------------------------
+    for (int i = tid; i < 3 * N; i += THREADS) s_cloud[i] = xyz[i];
+    for (int i = tid; i < 2 * S; i += THREADS) s_mail[i] = ~0ull;
+    for (int i = tid; i < NBIN; i += THREADS) s_hist[i] = 0u;
+    __syncthreads();
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int k = tid; k < N; k += THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = s_cloud[k * 3 + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_box[warp][a] = lo[a]; s_box[warp][3 + a] = hi[a]; }
+    }
+    __syncthreads();
+    float sc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float l = CUDART_INF_F, h = -CUDART_INF_F;
+        for (int w = 0; w < NWARP; ++w) { l = fminf(l, s_box[w][a]); h = fmaxf(h, s_box[w][3 + a]); }
+        lo[a] = l;
+        const float ext = h - l;
+        const float cells = a == 0 ? 16.f : 8.f;                          // 4 + 3 + 3 bits
+        sc[a] = (ext > 0.f && ext < CUDART_INF_F) ? cells / ext : 0.f;
+    }
+    // cell of a point: Morton interleave of the quantised coordinates (x: 4 bits, y, z: 3 bits); any total function of
+    // the coordinates would do -- the cells only decide which thread holds which point
+    auto cell_of = [&](int k) -> unsigned {
+        const unsigned qx = (unsigned)fminf(fmaxf((s_cloud[k * 3 + 0] - lo[0]) * sc[0], 0.f), 15.f);
+        const unsigned qy = (unsigned)fminf(fmaxf((s_cloud[k * 3 + 1] - lo[1]) * sc[1], 0.f), 7.f);
+        const unsigned qz = (unsigned)fminf(fmaxf((s_cloud[k * 3 + 2] - lo[2]) * sc[2], 0.f), 7.f);
+        unsigned c = (qx >> 3) << 9;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            c |= (((qx >> i) & 1u) << (3 * i + 2)) | (((qy >> i) & 1u) << (3 * i + 1)) | (((qz >> i) & 1u) << (3 * i));
+        return c;
+    };
+    // ---- counting sort by cell: histogram, exclusive scan, scatter.  The order inside a cell is whatever the atomics
+    // give, so ONE CTA (rank 0) sorts and writes the peer's half of the order into the peer's shared memory: two
+    // independent sorts would disagree about the cell that straddles the halves (points held twice or by nobody).
+    if (rank == 0) {
+        for (int k = tid; k < N; k += THREADS) atomicAdd(&s_hist[cell_of(k)], 1u);
+        __syncthreads();
+        constexpr int BPT = NBIN / THREADS;                              // bins per thread (2)
+        unsigned v[BPT], run = 0;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) { v[i] = s_hist[tid * BPT + i]; run += v[i]; }
+        unsigned inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        unsigned base = 0;
+        for (int w = 0; w < warp; ++w) base += s_wsum[w];
+        unsigned off = base + inc - run;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) { s_hist[tid * BPT + i] = off; off += v[i]; }
+        __syncthreads();
+        uint32_t perm_peer;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(perm_peer) : "r"(fps_smem_u32(s_perm)), "r"(1u));
+        for (int k = tid; k < N; k += THREADS) {
+            const unsigned pos = atomicAdd(&s_hist[cell_of(k)], 1u);
+            if (pos < (unsigned)PER_CTA) s_perm[pos] = (unsigned short)k;
+            else asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(perm_peer + 2u * (pos - (unsigned)PER_CTA)), "h"((unsigned short)k) : "memory");
+        }
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // ---- this thread's points: sorted positions warp*32*Q + q*32 + lane of this CTA's half ---------------------------
+    float px[Q], py[Q], pz[Q], pt[Q];
+    unsigned pkey[Q];
+    float wlo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, whi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int pl = warp * 32 * Q + q * 32 + lane;
+        const bool valid = (int)rank * PER_CTA + pl < N;
+        const int k = valid ? (int)s_perm[pl] : 0;
+        px[q] = valid ? s_cloud[k * 3 + 0] : 0.f;
+        py[q] = valid ? s_cloud[k * 3 + 1] : 0.f;
+        pz[q] = valid ? s_cloud[k * 3 + 2] : 0.f;
+        pkey[q] = valid ? key_of(k) : 0xffffffffu;
+        pt[q] = valid ? (temp_io ? temp_io[k] : 1e10f) : -CUDART_INF_F;
+        if (valid) {
+            wlo[0] = fminf(wlo[0], px[q]); whi[0] = fmaxf(whi[0], px[q]);
+            wlo[1] = fminf(wlo[1], py[q]); whi[1] = fmaxf(whi[1], py[q]);
+            wlo[2] = fminf(wlo[2], pz[q]); whi[2] = fmaxf(whi[2], pz[q]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wlo[a] = fminf(wlo[a], __shfl_xor_sync(0xffffffffu, wlo[a], o));
+            whi[a] = fmaxf(whi[a], __shfl_xor_sync(0xffffffffu, whi[a], o));
+        }
+    }
+    // ---- packet exchange set-up (as fps_cluster_kernel, mbarrier variant) -----------------------------------------
+    const uint32_t mail_u32 = fps_smem_u32(s_mail);
+    constexpr uint32_t mail_par_bytes = (uint32_t)S * 8u;
+    const uint32_t mbar_u32 = fps_smem_u32(&s_mbar[0]);
+    constexpr unsigned tx_bytes = (unsigned)S * 8u;
+    uint32_t rslot32 = 0u, rbar32 = 0u;
+    if (lane < CS) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot32)
+                     : "r"(mail_u32 + (uint32_t)((int)rank * NWARP + warp) * 8u), "r"((unsigned)lane));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar32) : "r"(mbar_u32), "r"((unsigned)lane));
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_u32) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_u32 + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_u32), "r"(tx_bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_u32 + 8u), "r"(tx_bytes) : "memory");
+    }
+    float x1 = s_cloud[0], y1 = s_cloud[1], z1 = s_cloud[2];
+    if (tid == 0 && rank == 0) idx_out[0] = 0;
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    unsigned wm = 0u, wkey = 0xffffffffu;                  // this warp's packet: ordered maximum, key of its holder
+    float wmf = CUDART_INF_F;                              // the warp maximum as a float
+#pragma unroll 1
+    for (int j = 1; j < M; ++j) {
+        // ---- A: can the new centre lower any min-distance of this warp?  (warp-uniform) -----------------------------
+        const float bx = fmaxf(fmaxf(__fsub_rn(wlo[0], x1), __fsub_rn(x1, whi[0])), 0.f);
+        const float by = fmaxf(fmaxf(__fsub_rn(wlo[1], y1), __fsub_rn(y1, whi[1])), 0.f);
+        const float bz = fmaxf(fmaxf(__fsub_rn(wlo[2], z1), __fsub_rn(z1, whi[2])), 0.f);
+        const float bound = __fmaf_rn(bz, bz, __fmaf_rn(bx, bx, __fmul_rn(by, by)));
+        if (j == 1 || !(bound >= wmf)) {                   // (a NaN bound runs the update, which then changes nothing)
+            float m = -CUDART_INF_F;
+            const f32x2_t cx2 = f2_pack(x1, x1), cy2 = f2_pack(y1, y1), cz2 = f2_pack(z1, z1);
+#pragma unroll
+            for (int p = 0; p < Q; p += 2) {
+                const f32x2_t d2 = fps_dist2(f2_pack(px[p], px[p + 1]), f2_pack(py[p], py[p + 1]), f2_pack(pz[p], pz[p + 1]), cx2, cy2, cz2);
+                float d0, d1;
+                f2_unpack(d2, d0, d1);
+                pt[p] = fminf(d0, pt[p]);
+                pt[p + 1] = fminf(d1, pt[p + 1]);
+                m = fmaxf(m, fmaxf(pt[p], pt[p + 1]));
+            }
+            // distances are >= +0 (or -inf for padding): flipping the sign bit is order preserving there
+            const unsigned om = __float_as_uint(m) ^ 0x80000000u;
+            wm = __reduce_max_sync(0xffffffffu, om);
+            unsigned key = 0xffffffffu;
+#pragma unroll
+            for (int p = 0; p < Q; ++p)
+                if (pt[p] == m && pkey[p] < key) key = pkey[p];
+            if (om != wm) key = 0xffffffffu;
+            wkey = __reduce_min_sync(0xffffffffu, key);
+            wmf = __uint_as_float(wm ^ 0x80000000u);
+        }
+        // ---- B: packet out (the previous one again if nothing changed) ---------------------------------------------
+        const int par = j & 1;
+        const unsigned tag = ((unsigned)j & 0x3ffu) << 22;
+        if (lane < CS) {
+            const unsigned long long v = ((unsigned long long)((wkey & 0x3fffffu) | tag) << 32) | wm;
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                         ::"r"(rslot32 + (par ? mail_par_bytes : 0u)), "l"(v), "r"(rbar32 + (par ? 8u : 0u)) : "memory");
+        }
+        {
+            const uint32_t mb = mbar_u32 + (par ? 8u : 0u);
+            const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
+            unsigned done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+            } while (!done);
+            if (tid == 0 && j + 2 < M)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tx_bytes) : "memory");
+        }
+        // ---- C: this iteration's packets (one per lane), the winner ---------------------------------------------------
+        unsigned bo, h;
+        {
+            const uint32_t mail = mail_u32 + (par ? mail_par_bytes : 0u) + (uint32_t)lane * 8u;
+            for (;;) {
+                asm volatile("ld.relaxed.cluster.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(bo), "=r"(h) : "r"(mail) : "memory");
+                if ((h & 0xffc00000u) == tag) break;
+            }
+        }
+        const unsigned bk = h & 0x3fffffu;
+        const unsigned g = __reduce_max_sync(0xffffffffu, bo);
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, (bo == g) ? bk : 0xffffffffu);
+        const int kw = k_of_key(kmin);
+        x1 = s_cloud[kw * 3 + 0]; y1 = s_cloud[kw * 3 + 1]; z1 = s_cloud[kw * 3 + 2];
+        if (tid == 0 && rank == 0) idx_out[j] = kw;
+    }
+    if (temp_io) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            if (pkey[q] != 0xffffffffu) temp_io[k_of_key(pkey[q])] = pt[q];
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int THREADS, int Q>
+int launch_fps_cull(const float* xyz, float* temp, int32_t* idx, int B, int N, int M, int log2T, cudaStream_t st) {
+    auto kern = fps_cull_kernel<THREADS, Q>;
+    const size_t smem = (size_t)2 * 2 * (THREADS / 32) * 8 + (size_t)N * 12 + 1024 * 4 + (size_t)THREADS * Q * 2;
+    static hrn_once_per_device attr;
+    if (attr.need()) HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * 2);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    HRN_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, N, M, log2T));
+    return HRN_OK;
+}
+
 template <int THREADS, int Q, int R, bool W, bool MONO, bool FULL>
 int launch_fps_cluster_t(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, int log2T,
                          int CS, cudaStream_t st) {
@@ -470,6 +739,12 @@ int launch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, int 
     return HRN_OK;
 }
 
+// HRN_FPS_CULL=0 in the environment selects the un-culled cluster kernel (A/B measurements)
+inline bool fps_cull_enabled() {
+    static const bool on = [] { const char* e = getenv("HRN_FPS_CULL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <bool W>
 int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, cudaStream_t st) {
     // opt_n_threads (cuda_utils.h:22-27): 2^floor(log2 N) clamped to [1,1024]  (defines the tie-break only)
@@ -493,6 +768,8 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
     } else {
         // (8 warps x 32 points -- two residues per thread, <256, 16, false, 2> -- is 4 % faster alone, 794 vs 827 us at 64
         // clouds, but not inside the step, where the Morton sort runs beside it: 6.30 vs 6.32 ms)
+        // spatially culled variant: the whole cloud, the cell histogram and this CTA's half of the sorted order fit in shared memory
+        if (N > 8192 && N <= 16384 && fps_cull_enabled()) return launch_fps_cull<512, 16>(xyz, temp, idx, B, N, M, log2T, st);
         if (N <= 16384) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 2, st);
         if (N <= 32768) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 4, st);
         if (N <= 65536) return launch_fps_cluster<512, 16, false>(xyz, w, temp, idx, B, N, M, log2T, 8, st);

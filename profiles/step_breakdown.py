@@ -41,7 +41,7 @@ print(f"# one 32-pair step (ncu launch list, cold-cache serialised: compare SHAR
 print(f"{'us':>10} {'share':>6} {'n':>4} {'dram MB':>10}  kernel")
 for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     print(f"{v[1]:10.1f} {100 * v[1] / tot:5.1f}% {v[0]:4d} {v[2] / 1e6:10.1f}  {k}")
-tc = [k for k in fam if any(s in k for s in ("level_fused", "level_ws", "chain3", "chain_ws", "layer_tc", "layer_ws"))]
+tc = [k for k in fam if any(s in k for s in ("level_fused", "level_ws", "chain3", "chain_ws", "chain_wide", "layer_tc", "layer_ws"))]
 out = {"tensor_family_dram_bytes_per_step": sum(fam[k][2] for k in tc),
        "tensor_family_us_per_step_ncu": sum(fam[k][1] for k in tc), "n_launches": sum(fam[k][0] for k in tc),
        "share_of_step_ncu": sum(fam[k][1] for k in tc) / tot,

@@ -41,6 +41,11 @@ def _clouds(kind, B, N, seed):
     ("uniform", 2, 4096, 3000), ("lidar", 1, 16384, 2500), ("uniform", 2, 1024, 1024),
     # 16-CTA clusters (65536 < N <= 131072), streaming kernel beyond
     ("uniform", 2, 131072, 100), ("lattice", 1, 100000, 64), ("uniform", 1, 140000, 40),
+    # the spatially culled kernel (8192 < N <= 16384): exact ties on a lattice, duplicate padding, far coordinates,
+    # ragged sizes around its limits, more samples than tags, LiDAR-like sweeps at the bench shape
+    ("lattice", 3, 16384, 600), ("lattice", 2, 9000, 400), ("dup", 3, 16384, 1024), ("dup", 2, 12000, 777),
+    ("far", 2, 16384, 512), ("uniform", 2, 8193, 300), ("lidar", 3, 16383, 1024), ("lidar", 2, 12345, 2000),
+    ("lidar", 64, 16384, 1024),
 ])
 def test_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=N + M)
