@@ -433,7 +433,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, const float* __restrict__ weig
 // the sampling a centre touches 1-3 of the 32 warps of a cloud; the iteration is then the packet exchange alone.
 // The result is bit-identical: same arithmetic per point, the reference's tie-break key travels with every point
 // (the thread <-> point mapping is free, see fps_kernel).
-template <int THREADS, int Q>
+template <int THREADS, int Q, bool MBAR>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int32_t* __restrict__ idx_out, int N, int M,
                 int log2T) {
@@ -579,12 +579,14 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
     const uint32_t mbar_u32 = fps_smem_u32(&s_mbar[0]);
     constexpr unsigned tx_bytes = (unsigned)S * 8u;
     uint32_t rslot32 = 0u, rbar32 = 0u;
+    unsigned long long rslot = 0ull;
     if (lane < CS) {
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot32)
                      : "r"(mail_u32 + (uint32_t)((int)rank * NWARP + warp) * 8u), "r"((unsigned)lane));
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar32) : "r"(mbar_u32), "r"((unsigned)lane));
+        asm volatile("cvta.shared::cluster.u64 %0, %1;" : "=l"(rslot) : "l"((unsigned long long)rslot32));
     }
-    if (tid == 0) {
+    if (MBAR && tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_u32) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_u32 + 8u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -600,6 +602,7 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
     float wmf = CUDART_INF_F;                              // the warp maximum as a float
 #pragma unroll 1
     for (int j = 1; j < M; ++j) {
+        FPS_STAMP(0);
         // ---- A: can the new centre lower any min-distance of this warp?  (warp-uniform) -----------------------------
         const float bx = fmaxf(fmaxf(__fsub_rn(wlo[0], x1), __fsub_rn(x1, whi[0])), 0.f);
         const float by = fmaxf(fmaxf(__fsub_rn(wlo[1], y1), __fsub_rn(y1, whi[1])), 0.f);
@@ -628,15 +631,20 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
             wkey = __reduce_min_sync(0xffffffffu, key);
             wmf = __uint_as_float(wm ^ 0x80000000u);
         }
+        FPS_STAMP(1);
         // ---- B: packet out (the previous one again if nothing changed) ---------------------------------------------
         const int par = j & 1;
         const unsigned tag = ((unsigned)j & 0x3ffu) << 22;
         if (lane < CS) {
             const unsigned long long v = ((unsigned long long)((wkey & 0x3fffffu) | tag) << 32) | wm;
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-                         ::"r"(rslot32 + (par ? mail_par_bytes : 0u)), "l"(v), "r"(rbar32 + (par ? 8u : 0u)) : "memory");
+            if (MBAR)
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                             ::"r"(rslot32 + (par ? mail_par_bytes : 0u)), "l"(v), "r"(rbar32 + (par ? 8u : 0u)) : "memory");
+            else
+                asm volatile("st.relaxed.cluster.b64 [%0], %1;" ::"l"(rslot + (par ? mail_par_bytes : 0u)), "l"(v) : "memory");
         }
-        {
+        FPS_STAMP(2);
+        if (MBAR) {
             const uint32_t mb = mbar_u32 + (par ? 8u : 0u);
             const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
             unsigned done;
@@ -647,6 +655,7 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
             if (tid == 0 && j + 2 < M)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tx_bytes) : "memory");
         }
+        FPS_STAMP(3);
         // ---- C: this iteration's packets (one per lane), the winner ---------------------------------------------------
         unsigned bo, h;
         {
@@ -661,6 +670,11 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
         const unsigned kmin = __reduce_min_sync(0xffffffffu, (bo == g) ? bk : 0xffffffffu);
         const int kw = k_of_key(kmin);
         x1 = s_cloud[kw * 3 + 0]; y1 = s_cloud[kw * 3 + 1]; z1 = s_cloud[kw * 3 + 2];
+#ifdef FPS_PROBE
+        if (__float_as_uint(x1) + __float_as_uint(y1) + __float_as_uint(z1) == 0x12345u) g_fps_sink = 3;   // consume
+        if (blockIdx.x == 0 && tid == FPS_PROBE_TID && j >= 500 && j < 564) g_fps_probe[(j - 500) * 8 + 5] = (long long)(!(bound >= wmf));
+#endif
+        FPS_STAMP(4);
         if (tid == 0 && rank == 0) idx_out[j] = kw;
     }
     if (temp_io) {
@@ -671,9 +685,19 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int THREADS, int Q, bool MBAR>
+int launch_fps_cull_t(const float* xyz, float* temp, int32_t* idx, int B, int N, int M, int log2T, cudaStream_t st);
+
 template <int THREADS, int Q>
 int launch_fps_cull(const float* xyz, float* temp, int32_t* idx, int B, int N, int M, int log2T, cudaStream_t st) {
-    auto kern = fps_cull_kernel<THREADS, Q>;
+    static const bool poll = [] { const char* e = getenv("HRN_FPS_POLL"); return e && e[0] == '1'; }();
+    if (poll) return launch_fps_cull_t<THREADS, Q, false>(xyz, temp, idx, B, N, M, log2T, st);
+    return launch_fps_cull_t<THREADS, Q, true>(xyz, temp, idx, B, N, M, log2T, st);
+}
+
+template <int THREADS, int Q, bool MBAR>
+int launch_fps_cull_t(const float* xyz, float* temp, int32_t* idx, int B, int N, int M, int log2T, cudaStream_t st) {
+    auto kern = fps_cull_kernel<THREADS, Q, MBAR>;
     const size_t smem = (size_t)2 * 2 * (THREADS / 32) * 8 + (size_t)N * 12 + 1024 * 4 + (size_t)THREADS * Q * 2;
     static hrn_once_per_device attr;
     if (attr.need()) HRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));

@@ -56,6 +56,7 @@ int main(int argc, char** argv) {
         acc[0] += p[j * 8 + 1] - p[j * 8 + 0]; acc[1] += p[j * 8 + 2] - p[j * 8 + 1]; acc[2] += p[j * 8 + 3] - p[j * 8 + 2];
         acc[3] += p[j * 8 + 4] - p[j * 8 + 3]; acc[4] += p[(j + 1) * 8 + 0] - p[j * 8 + 0];
     }
+    { int act = 0; for (int j = 0; j < n; ++j) act += (int)p[j * 8 + 5]; printf("  culled kernel: this warp's update ran (per stale bound) in %d of %d probed iterations\n", act, n); }
     double a2[4] = {0, 0, 0, 0};
     for (int j = 0; j < n; ++j) { a2[0] += p[j * 8 + 5] - p[j * 8 + 1]; a2[1] += p[j * 8 + 6] - p[j * 8 + 5]; a2[2] += p[j * 8 + 7] - p[j * 8 + 6]; a2[3] += p[j * 8 + 2] - p[j * 8 + 7]; }
     if (n) printf("  resolve detail: hold/pf/LDS %.0f | REDUX.min %.0f | 4x REDUX.OR %.0f | build+store %.0f\n", a2[0] / n, a2[1] / n, a2[2] / n, a2[3] / n);
