@@ -763,9 +763,90 @@ int launch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, int 
     return HRN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One WARP per cloud, for the small power-of-two clouds of the lower hierarchy levels (N = 256 / 512 / 1024: the
+// weighted samplings 1024 -> 512 and 512 -> 256 of models.py:31-39).  With 8 warps per cloud an iteration of these is
+// nothing but the packet exchange between the warps (~650 cycles for 4 points per thread); with P = N / 32 points per
+// lane there is nothing to exchange: update, two REDUX, one shared-memory lookup of the winner.
+// Slot s of lane l holds point k = l + 32 * bitrev_log2P(s): the reference's tie-break key of that point is
+// bitrev_log2N(k) = bitrev_5(l) << log2P | s (N = T here), i.e. a lane's smallest key is its FIRST slot with the maximum.
+template <int P, bool WEIGHTED>
+__global__ void __launch_bounds__(32)
+fps_warp_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, float* __restrict__ temp_io,
+                int32_t* __restrict__ idx_out, int M) {
+    constexpr int N = 32 * P;
+    constexpr int LOG2P = P == 32 ? 5 : P == 16 ? 4 : P == 8 ? 3 : -1;
+    static_assert(LOG2P > 0, "P = 8, 16 or 32");
+    __shared__ float s_cloud[3 * N];
+    const int lane = threadIdx.x, b = blockIdx.x;
+    xyz += (size_t)b * N * 3;
+    if (WEIGHTED) weights += (size_t)b * N;
+    if (temp_io) temp_io += (size_t)b * N;
+    idx_out += (size_t)b * M;
+    for (int i = lane; i < 3 * N; i += 32) s_cloud[i] = xyz[i];
+    __syncwarp();
+    float px[P], py[P], pz[P], pt[P], pw[WEIGHTED ? P : 1];
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+        const int k = lane + 32 * (int)(__brev((unsigned)s) >> (32 - LOG2P));
+        px[s] = s_cloud[k * 3 + 0]; py[s] = s_cloud[k * 3 + 1]; pz[s] = s_cloud[k * 3 + 2];
+        if (WEIGHTED) pw[s] = weights[k];
+        pt[s] = temp_io ? temp_io[k] : 1e10f;
+    }
+    const unsigned lanekey = (__brev((unsigned)lane) >> 27) << LOG2P;
+    float x1 = s_cloud[0], y1 = s_cloud[1], z1 = s_cloud[2];
+    if (lane == 0) idx_out[0] = 0;
+#pragma unroll 1
+    for (int j = 1; j < M; ++j) {
+        const f32x2_t cx2 = f2_pack(x1, x1), cy2 = f2_pack(y1, y1), cz2 = f2_pack(z1, z1);
+        float mm[P / 2];
+#pragma unroll
+        for (int s = 0; s < P; s += 2) {
+            f32x2_t d2 = fps_dist2(f2_pack(px[s], px[s + 1]), f2_pack(py[s], py[s + 1]), f2_pack(pz[s], pz[s + 1]), cx2, cy2, cz2);
+            if (WEIGHTED) d2 = f2_mul(f2_pack(pw[s], pw[s + 1]), d2);
+            float d0, d1;
+            f2_unpack(d2, d0, d1);
+            pt[s] = fminf(d0, pt[s]);
+            pt[s + 1] = fminf(d1, pt[s + 1]);
+            mm[s / 2] = fmaxf(pt[s], pt[s + 1]);
+        }
+#pragma unroll
+        for (int w = P / 4; w >= 1; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) mm[i] = fmaxf(mm[i], mm[i + w]);
+        const float m = mm[0];
+        const unsigned om = WEIGHTED ? hrn_ford(m) : (__float_as_uint(m) ^ 0x80000000u);
+        const unsigned wm = __reduce_max_sync(0xffffffffu, om);
+        unsigned sb = P - 1;
+#pragma unroll
+        for (int s = P - 2; s >= 0; --s)
+            if (pt[s] == m) sb = (unsigned)s;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, (om == wm) ? (lanekey | sb) : 0xffffffffu);
+        const int kw = (int)(__brev(kmin >> LOG2P) >> 27) + 32 * (int)(__brev(kmin & (unsigned)(P - 1)) >> (32 - LOG2P));
+        x1 = s_cloud[kw * 3 + 0]; y1 = s_cloud[kw * 3 + 1]; z1 = s_cloud[kw * 3 + 2];
+        if (lane == 0) idx_out[j] = kw;
+    }
+    if (temp_io) {
+#pragma unroll
+        for (int s = 0; s < P; ++s) temp_io[lane + 32 * (int)(__brev((unsigned)s) >> (32 - LOG2P))] = pt[s];
+    }
+}
+
+template <int P, bool W>
+int launch_fps_warp(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int M, cudaStream_t st) {
+    fps_warp_kernel<P, W><<<B, 32, 0, st>>>(xyz, w, temp, idx, M);
+    HRN_LAUNCH_CHECK();
+    return HRN_OK;
+}
+
 // HRN_FPS_CULL=0 in the environment selects the un-culled cluster kernel (A/B measurements)
 inline bool fps_cull_enabled() {
     static const bool on = [] { const char* e = getenv("HRN_FPS_CULL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+inline bool fps_warp_enabled() {       // HRN_FPS_WARP=0: the multi-warp cluster kernels also for the small clouds (A/B)
+    static const bool on = [] { const char* e = getenv("HRN_FPS_WARP"); return !(e && e[0] == '0'); }();
     return on;
 }
 
@@ -778,6 +859,12 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
     // slots than the distance update of 16 points per thread, so 512 threads x 16 points (8192 points per CTA) and the
     // smallest cluster that holds the cloud; clusters of >= 2 CTAs keep the stride a multiple of Tref (MONO).
     // B * CS may exceed the SM count: clusters are independent, the surplus simply runs as a second wave.
+    // small power-of-two clouds (N = T: the key is the bit-reversed index): one warp per cloud, no exchange at all
+    if (fps_warp_enabled()) {
+        if (N == 1024) return launch_fps_warp<32, W>(xyz, w, temp, idx, B, M, st);
+        if (N == 512) return launch_fps_warp<16, W>(xyz, w, temp, idx, B, M, st);
+        if (N == 256) return launch_fps_warp<8, W>(xyz, w, temp, idx, B, M, st);
+    }
     if (N <= 1024) {
         if (N <= 256) return launch_fps_cluster<256, 1, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
         if (N <= 512) return launch_fps_cluster<256, 2, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
