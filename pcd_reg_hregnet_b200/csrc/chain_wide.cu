@@ -30,6 +30,8 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -57,6 +59,16 @@ struct WideArgs {
 };
 #ifdef HRN_WIDE_DEBUG
 float* g_wide_dbg = nullptr;
+#endif
+// -DHRN_WIDE_PROF: cycles the MMA thread of CTA 0 spends waiting for [0] input stages, [1] own blocks, [2] the peer's
+// blocks, [3] weights, [4] a free accumulator, [5] total; read back with hrn_chain_wide_prof (tools/wide_probe.py)
+#ifdef HRN_WIDE_PROF
+__device__ long long g_wide_prof[8];
+#define WPROF_BEGIN() const long long wp_t0 = clock64()
+#define WPROF_END(i) wp[i] += clock64() - wp_t0
+#else
+#define WPROF_BEGIN() do { } while (0)
+#define WPROF_END(i) do { } while (0)
 #endif
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -413,14 +425,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
             int gs = 0, hs = 0; uint32_t gpar = 0, hpar = 0;
             int L = 0;
             uint32_t fin_pending = 0, finph = 0;
+#ifdef HRN_WIDE_PROF
+            long long wp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const long long wp_start = clock64();
+#endif
             auto claim = [&](int b) {
                 if (fin_pending >> b & 1) {
+                    WPROF_BEGIN();
                     mbar_wait(smem_u32(&s_fin[b]), (finph >> b) & 1);
+                    WPROF_END(4);
                     finph ^= 1u << b; fin_pending &= ~(1u << b);
                 }
             };
             auto piece_mma = [&](uint32_t a16, uint64_t w_desc0, uint32_t wlo16, uint32_t idesc, uint32_t d, uint32_t accumulate) {
-                mbar_wait(wfull0 + 8 * ws, wpar);
+                {
+                    WPROF_BEGIN();
+                    mbar_wait(wfull0 + 8 * ws, wpar);
+                    WPROF_END(3);
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t w16 = ((ring_a >> 4) & 0x3FFFu) + ws * slot16;
                 const uint64_t ah = a_desc0 | a16, al = a_desc0 | (a16 + LO16);
@@ -444,7 +466,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
                     const uint32_t wlo16 = 2 * N;
                     int left = A.chunks0 / 2;
                     for (int s = 0; s < n_st0; ++s, left -= 2) {
-                        mbar_wait(smem_u32(&s_gfull[gs]), gpar);
+                        {
+                            WPROF_BEGIN();
+                            mbar_wait(smem_u32(&s_gfull[gs]), gpar);
+                            WPROF_END(0);
+                        }
                         const uint32_t a16 = g_a + gs * ST16;
                         piece_mma(a16, w_desc0, wlo16, idesc, d, s > 0 ? 1u : 0u);
                         if (left > 1) piece_mma(a16 + P16, w_desc0, wlo16, idesc, d, 1u);
@@ -468,7 +494,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
 #pragma unroll
                         for (uint32_t rk = 0; rk < 2; ++rk) {
                             const bool own = rk == rank;
-                            mbar_wait(smem_u32(own ? &s_hlfull[hs] : &s_hrfull[hs]), hpar);
+                            {
+                                WPROF_BEGIN();
+                                mbar_wait(smem_u32(own ? &s_hlfull[hs] : &s_hrfull[hs]), hpar);
+                                WPROF_END(own ? 1 : 2);
+                            }
                             const uint32_t a16 = (own ? h_own : h_peer) + hs * ST16;
                             piece_mma(a16, w_desc0, wlo16, idesc, d, (j > 0 || rk > 0) ? 1u : 0u);
                             piece_mma(a16 + P16, w_desc0, wlo16, idesc, d, 1u);
@@ -479,6 +509,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
                     umma_commit(smem_u32(&s_accf[b]));
                 }
             }
+#ifdef HRN_WIDE_PROF
+            if (blockIdx.x == 0) {
+                wp[5] = clock64() - wp_start;
+                for (int i = 0; i < 8; ++i) g_wide_prof[i] = wp[i];
+            }
+#endif
         }
     } else if (warp == WW_EPI_WARPS + WW_PROD_WARPS + 1) {
         // ================= weight stream ==========================================================================
@@ -595,21 +631,38 @@ HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank
     A.slot_bytes = maxh * (prec == 1 ? 32 : 64);
     // shared memory: ring G | ring HL | ring HR (16 KB stages) | weight ring | raw fp32 ring | biases | row maxima
     const int budget = 227 * 1024 - 1024;
-    constexpr int RAW = 2;
+    int raw = 2;
     A.gs = 2; A.hs = 2;
-    const int fixed = (A.gs + 2 * A.hs + RAW) * WW_STAGE_BYTES + 3 * 256 * 4 + 4 * WTM * 4;
+    int ring_want = WW_RING_MAX;
+    if (const char* e = getenv("HRN_WIDE_CFG")) {               // tuning: "gs,hs,raw,ring"
+        int g_ = 0, h_ = 0, r_ = 0, w_ = 0;
+        if (sscanf(e, "%d,%d,%d,%d", &g_, &h_, &r_, &w_) == 4 && g_ >= 2 && g_ <= WW_GS_MAX && h_ >= 2 && h_ <= WW_HS_MAX &&
+            r_ >= 2 && r_ <= 4 && w_ >= 3 && w_ <= WW_RING_MAX) { A.gs = g_; A.hs = h_; raw = r_; ring_want = w_; }
+    }
+    const int fixed = (A.gs + 2 * A.hs + raw) * WW_STAGE_BYTES + 3 * 256 * 4 + 4 * WTM * 4;
     int ring = (budget - fixed) / A.slot_bytes;
-    if (ring > WW_RING_MAX) ring = WW_RING_MAX;
+    if (ring > ring_want) ring = ring_want;
     if (ring < 3) return HRN_ERR_UNSUPPORTED;
     A.ring = ring;
     const int smem = fixed + ring * A.slot_bytes;
     cudaStream_t st = (cudaStream_t)stream;
-    if (prec == 1) HRN_CUDA((launch_wide_one<8, RAW, 1>(A, smem, budget, st)));
-    else           HRN_CUDA((launch_wide_one<8, RAW, 3>(A, smem, budget, st)));
+    if (prec == 1) {
+        if (raw == 2) HRN_CUDA((launch_wide_one<8, 2, 1>(A, smem, budget, st)));
+        else if (raw == 3) HRN_CUDA((launch_wide_one<8, 3, 1>(A, smem, budget, st)));
+        else HRN_CUDA((launch_wide_one<8, 4, 1>(A, smem, budget, st)));
+    } else {
+        if (raw == 2) HRN_CUDA((launch_wide_one<8, 2, 3>(A, smem, budget, st)));
+        else if (raw == 3) HRN_CUDA((launch_wide_one<8, 3, 3>(A, smem, budget, st)));
+        else HRN_CUDA((launch_wide_one<8, 4, 3>(A, smem, budget, st)));
+    }
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
 
 #ifdef HRN_WIDE_DEBUG
 HRN_API int hrn_chain_wide_set_debug(float* p) { g_wide_dbg = p; return 0; }
+#endif
+
+#ifdef HRN_WIDE_PROF
+HRN_API int hrn_chain_wide_prof(long long* host8) { return (int)cudaMemcpyFromSymbol(host8, g_wide_prof, 8 * sizeof(long long)); }
 #endif
