@@ -170,9 +170,14 @@ int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl,
  *   W: per column half (rank 0, rank 1; w_rank_bytes each) the K=16 weight pieces of the three layers, bias: per half
  *   b1|b2|b3, both as laid out by pcd_reg_hregnet_b200/engine_tc.pack_chain_wide; n1..n3 full widths (multiples of 64,
  *   <= 512), chunks0 = 8-wide K chunks of the virtual input (even), kseg = 8, rows % 128 == 0, prec as hrn_chain_tc.
+ *   Zb [rows / kseg, ldz], Zg [source rows, ldz] (both or neither): fp32 rows ADDED to the first layer's pre-activations,
+ *   row r takes Zb[r / kseg] + Zg[b * src_rows_per_batch + gather_idx[r]] -- the part of the (linear) first layer that
+ *   is constant inside a group / depends on the gathered row only, applied once per point by the caller
+ *   (engine_tc._split_first_layer); `in` then only holds the per-row segments.
  *   Outputs: G [rows / kseg, n3] attentive feature, a [rows] attention weights (nullable). */
 int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2, int n3,
-                   int chunks0, int kseg, float* G, float* a, long long rows, int prec, void* stream);
+                   int chunks0, int kseg, const float* Zb, const float* Zg, int ldz, float* G, float* a, long long rows,
+                   int prec, void* stream);
 
 /* Level 1 of HierFeatureExtraction (models/HRegNet/models.py:27-28: detector_1 + desc_extractor_1; in_channels 0,
  * k = 64, widths 32/32/64, mlp 192->32->64) as ONE persistent tcgen05 kernel: grouping (layers.py:9-27), the two conv

@@ -41,6 +41,9 @@ constexpr int WW_THREADS = (WW_EPI_WARPS + WW_PROD_WARPS + 3) * 32;    // 608
 constexpr int WW_STAGE_BYTES = 4 * WTM * 32;                           // 128 rows x 32 K: fp32, or bf16 hi + lo = 16 KB
 constexpr int WW_RING_MAX = 8, WW_GS_MAX = 4, WW_HS_MAX = 4;
 constexpr int WW_ACC = 256;                                            // accumulator stride (TMEM columns)
+constexpr int WW_ZS_MAX = 4;
+constexpr int WW_ZG_BYTES = WTM * 32 * 4;                              // gathered rows of a 32-column block: 128 x 128 B
+constexpr int WW_ZSTAGE_BYTES = WW_ZG_BYTES + (WTM / 8) * 32 * 4;      // + the 16 group rows = 18 KB
 
 struct WideArgs {
     hrn_rows_t in;
@@ -53,6 +56,11 @@ struct WideArgs {
     int nh[3];                   // columns per CTA of the three layers (multiples of 32, <= 256)
     int chunks0;                 // 8-wide K chunks of the virtual input (even)
     int slot_bytes, ring, gs, hs;
+    // optional fp32 rows ADDED to the first layer's pre-activations (the part of that layer which is the same for the
+    // rows of a group / which only depends on the gathered source row, applied once per point by the caller):
+    const float* Zb;             // [rows / group, ldz]: row r takes Zb[r / group]
+    const float* Zg;             // [src rows, ldz]:     row r takes Zg[b * src_rows_per_batch + gather_idx[r]]
+    int ldz, zs;                 // leading dimension (floats), Z ring stages
 #ifdef HRN_WIDE_DEBUG
     float* dbg;                  // [2 layers][rows][512] pre-activations of the hidden layers as the epilogue sees them
 #endif
@@ -119,7 +127,8 @@ template <int KSEG, int RAW, int PREC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain_wide_kernel(const WideArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_wfull[WW_RING_MAX], s_wempty[WW_RING_MAX], s_gfull[WW_GS_MAX], s_gempty[WW_GS_MAX],
-        s_hlfull[WW_HS_MAX], s_hrfull[WW_HS_MAX], s_hfree[WW_HS_MAX], s_accf[2], s_fin[2], s_xbar;
+        s_hlfull[WW_HS_MAX], s_hrfull[WW_HS_MAX], s_hfree[WW_HS_MAX], s_accf[2], s_fin[2], s_xbar, s_zfull[WW_ZS_MAX],
+        s_zempty[WW_ZS_MAX];
     __shared__ uint32_t s_tmem;
 
     const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
@@ -134,6 +143,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
     float* sBias = reinterpret_cast<float*>(sRaw + RAW * WW_STAGE_BYTES);
     float* sX = sBias + 3 * 256;                            // [2][128] row maxima of the two epilogue groups
     float* sXr = sX + 2 * WTM;                              // [2][128] the peer's row maxima (by tile parity)
+    uint8_t* sZ = reinterpret_cast<uint8_t*>(sXr + 2 * WTM);  // Z ring: [zs][128 gathered rows x 128 B (16-byte chunks XOR-swizzled by row) | 16 group rows x 128 B]
+    const bool has_z = A.Zg != nullptr;
+    const int ZS = A.zs;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = A.n_tiles;
@@ -150,6 +162,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
         }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_accf[i]), 1); mbar_init(smem_u32(&s_fin[i]), WW_EPI_WARPS); }
         mbar_init(smem_u32(&s_xbar), WTM);                  // one remote arrival per row
+        for (int i = 0; i < WW_ZS_MAX; ++i) {
+            mbar_init(smem_u32(&s_zfull[i]), WW_PROD_WARPS * 32);   // every producer thread: cp.async.mbarrier.arrive.noinc
+            mbar_init(smem_u32(&s_zempty[i]), 4);                   // the four quadrant warps that consumed the block
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -176,6 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
         uint32_t accph = 0, xph = 0;
         int L = 0;
         int hs = 0; uint32_t hpar = 0; int hq = 0;
+        int zs = 0; uint32_t zpar = 0;
         int ti = 0;
         const uint32_t xbar_peer = map_peer(smem_u32(&s_xbar), peer);
         for (int tile = tile0; tile < n_tiles; tile += tstride, ++ti) {
@@ -189,6 +206,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
                     if ((hq & 1) == eg) {
                         uint32_t v[32];
                         tmem_ld32(tmem + lane_base + b * WW_ACC + c0, v);
+                        const bool zblk = has_z && l == 0;
+                        const float* zg = reinterpret_cast<const float*>(sZ + (size_t)zs * WW_ZSTAGE_BYTES) + rt * 32;
+                        const float* zb = reinterpret_cast<const float*>(sZ + (size_t)zs * WW_ZSTAGE_BYTES + WW_ZG_BYTES) + (rt >> 3) * 32;
+                        if (zblk) mbar_wait(smem_u32(&s_zfull[zs]), zpar);           // this block's Z rows have landed
                         mbar_wait(smem_u32(&s_hfree[hs]), hpar ^ 1);          // both CTAs are done with the slot's last pair
                         uint4* h_hi = reinterpret_cast<uint4*>(sHL + (size_t)hs * WW_STAGE_BYTES);
                         uint4* h_lo = h_hi + 4 * WTM;
@@ -201,6 +222,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
                             f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])), f2_pack(b0.z, b0.w)), s[2], s[3]);
                             f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])), f2_pack(b1.x, b1.y)), s[4], s[5]);
                             f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])), f2_pack(b1.z, b1.w)), s[6], s[7]);
+                            if (zblk) {     // + group row + gathered row (fp32)
+                                const float4 g0 = *reinterpret_cast<const float4*>(zg + (((2 * ch) ^ (rt & 7)) << 2));
+                                const float4 g1 = *reinterpret_cast<const float4*>(zg + (((2 * ch + 1) ^ (rt & 7)) << 2));
+                                const float4 q0 = *reinterpret_cast<const float4*>(zb + ch * 8);
+                                const float4 q1 = *reinterpret_cast<const float4*>(zb + ch * 8 + 4);
+                                f2_unpack(f2_add(f2_add(f2_pack(s[0], s[1]), f2_pack(q0.x, q0.y)), f2_pack(g0.x, g0.y)), s[0], s[1]);
+                                f2_unpack(f2_add(f2_add(f2_pack(s[2], s[3]), f2_pack(q0.z, q0.w)), f2_pack(g0.z, g0.w)), s[2], s[3]);
+                                f2_unpack(f2_add(f2_add(f2_pack(s[4], s[5]), f2_pack(q1.x, q1.y)), f2_pack(g1.x, g1.y)), s[4], s[5]);
+                                f2_unpack(f2_add(f2_add(f2_pack(s[6], s[7]), f2_pack(q1.z, q1.w)), f2_pack(g1.z, g1.w)), s[6], s[7]);
+                            }
 #ifdef HRN_WIDE_DEBUG
                             if (A.dbg)
                                 for (int e = 0; e < 8; ++e)
@@ -218,9 +249,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&s_hlfull[hs]));
+                        if (lane == 0) {
+                            mbar_arrive(smem_u32(&s_hlfull[hs]));
+                            if (zblk) mbar_arrive(smem_u32(&s_zempty[zs]));
+                        }
                     }
                     if (++hs == HS) { hs = 0; hpar ^= 1; }
+                    if (has_z && l == 0 && ++zs == ZS) { zs = 0; zpar ^= 1; }
                 }
             }
             // ---- last layer: attention over this CTA's column half, the row maxima of the halves meet through DSMEM ----
@@ -396,16 +431,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
             if (lane == 0) mbar_arrive(smem_u32(&s_gfull[gs]));
             if (++gs == GS) { gs = 0; gpar ^= 1; }
         };
+        // Z blocks of a tile (first-layer bias rows of this CTA's column half), one ring stage per 32-column block:
+        // warp pw copies the gathered rows pw*16 .. +16 (4 rows x 128 B per instruction) and the group rows 2pw, 2pw+1
+        int zs = 0; uint32_t zpar = 0;
+        auto z_blocks = [&](int tile) {
+            const int gl = 2 * pw + (lane >> 3), chunk = lane & 7;
+            const float* zsrc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned ru = (unsigned)tile * WTM + pw * 16 + i * 4 + (lane >> 3);
+                const long long zr = (long long)(ru / (unsigned)in.rows_per_batch) * in.src_rows_per_batch + in.gather_idx[ru];
+                zsrc[i] = A.Zg + zr * A.ldz + rank * A.nh[0] + chunk * 4;
+            }
+            const float* zbsrc = A.Zb + ((long long)tile * (WTM / 8) + gl) * A.ldz + rank * A.nh[0] + chunk * 4;
+            const int nb = A.nh[0] / 32;
+            for (int j = 0; j < nb; ++j) {
+                mbar_wait_backoff(smem_u32(&s_zempty[zs]), zpar ^ 1);
+                const uint32_t base = smem_u32(sZ + (size_t)zs * WW_ZSTAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = pw * 16 + i * 4 + (lane >> 3);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + rl * 128 + ((chunk ^ (rl & 7)) << 4)), "l"(zsrc[i] + 32 * j) : "memory");
+                }
+                if (lane < 16)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + WW_ZG_BYTES + gl * 128 + (chunk << 4)), "l"(zbsrc + 32 * j) : "memory");
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_zfull[zs])) : "memory");
+                if (++zs == ZS) { zs = 0; zpar ^= 1; }
+            }
+        };
         int my_tiles = 0;
         if (tile0 < n_tiles) my_tiles = (n_tiles - 1 - tile0) / tstride + 1;
         const int total = my_tiles * n_st0;
         if (total > 0) resolve(ltile);
 #pragma unroll
         for (int d = 0; d < RAW; ++d) issue(d, sc[d]);
+        int filled = 0;                                      // stages delivered: a tile's Z blocks follow its last stage
         for (int q = 0; q < total; q += RAW) {
 #pragma unroll
             for (int d = 0; d < RAW; ++d) {
-                if (q + d < total) { fill(d, sc[d]); issue(d, sc[d]); }
+                if (q + d < total) {
+                    fill(d, sc[d]); issue(d, sc[d]);
+                    if (++filled % n_st0 == 0 && has_z) z_blocks(tile0 + (filled / n_st0 - 1) * tstride);
+                }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -601,7 +668,8 @@ cudaError_t launch_wide_one(const WideArgs& A, int smem, int budget, cudaStream_
 // bias: per half b1 | b2 | b3; n1..n3 = full widths (multiples of 64, <= 512); kseg = rows per group (8).
 // Outputs: G [rows / kseg, n3] attentive feature, a [rows] attention weights (layers.py:384-390).  rows % 128 == 0.
 HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2,
-                           int n3, int chunks0, int kseg, float* G, float* a, long long rows, int prec, void* stream) {
+                           int n3, int chunks0, int kseg, const float* Zb, const float* Zg, int ldz, float* G, float* a,
+                           long long rows, int prec, void* stream) {
     if (!in || !W || !bias || !G || rows < 0 || in->n_seg < 1 || in->n_seg > 4 || w_rank_bytes <= 0) return HRN_ERR_BAD_ARG;
     if (prec != 1 && prec != 3) return HRN_ERR_BAD_ARG;
     const int nn[3] = {n1, n2, n3};
@@ -618,6 +686,9 @@ HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank
         chunks += (g.channels + 7) / 8;
     }
     if (chunks0 != ((chunks + 1) & ~1)) return HRN_ERR_BAD_ARG;
+    if ((Zb == nullptr) != (Zg == nullptr)) return HRN_ERR_BAD_ARG;
+    if (Zg && (!in->gather_idx || in->group != kseg || in->rows_per_batch <= 0 || ldz < n1 || (ldz & 3) || ((uintptr_t)Zb & 15) ||
+               ((uintptr_t)Zg & 15))) return HRN_ERR_BAD_ARG;
     if (rows == 0) return HRN_OK;
     WideArgs A;
     A.in = *in; A.W = (const uint8_t*)W; A.w_rank_bytes = w_rank_bytes; A.bias = bias; A.G = G; A.a = a;
@@ -625,6 +696,7 @@ HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank
     int maxh = 0;
     for (int l = 0; l < 3; ++l) { A.nh[l] = nn[l] / 2; if (A.nh[l] > maxh) maxh = A.nh[l]; }
     A.chunks0 = chunks0;
+    A.Zb = Zb; A.Zg = Zg; A.ldz = ldz;
 #ifdef HRN_WIDE_DEBUG
     A.dbg = g_wide_dbg;
 #endif
@@ -633,13 +705,19 @@ HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank
     const int budget = 227 * 1024 - 1024;
     int raw = 2;
     A.gs = 2; A.hs = 2;
+    A.zs = Zg ? 2 : 0;
+    // one input stage per tile: no need to run stages ahead; the shared memory goes to a third slot of the block rings
+    // instead (a 16 KB block takes ~800 cycles through DSMEM: with two slots the MMA thread waited 27 % of its time for
+    // the peer's blocks, with three 8 %)
+    if (Zg && chunks0 <= 4) { A.gs = 1; raw = 1; A.hs = 3; }
     int ring_want = WW_RING_MAX;
     if (const char* e = getenv("HRN_WIDE_CFG")) {               // tuning: "gs,hs,raw,ring"
         int g_ = 0, h_ = 0, r_ = 0, w_ = 0;
-        if (sscanf(e, "%d,%d,%d,%d", &g_, &h_, &r_, &w_) == 4 && g_ >= 2 && g_ <= WW_GS_MAX && h_ >= 2 && h_ <= WW_HS_MAX &&
-            r_ >= 2 && r_ <= 4 && w_ >= 3 && w_ <= WW_RING_MAX) { A.gs = g_; A.hs = h_; raw = r_; ring_want = w_; }
+        if (sscanf(e, "%d,%d,%d,%d", &g_, &h_, &r_, &w_) == 4 && g_ >= 1 && g_ <= WW_GS_MAX && h_ >= 2 && h_ <= WW_HS_MAX &&
+            r_ >= 1 && r_ <= 4 && w_ >= 3 && w_ <= WW_RING_MAX) { A.gs = g_; A.hs = h_; raw = r_; ring_want = w_; }
+        if (const char* z = getenv("HRN_WIDE_ZS")) { const int zz = atoi(z); if (Zg && zz >= 2 && zz <= WW_ZS_MAX) A.zs = zz; }
     }
-    const int fixed = (A.gs + 2 * A.hs + raw) * WW_STAGE_BYTES + 3 * 256 * 4 + 4 * WTM * 4;
+    const int fixed = (A.gs + 2 * A.hs + raw) * WW_STAGE_BYTES + 3 * 256 * 4 + 4 * WTM * 4 + A.zs * WW_ZSTAGE_BYTES;
     int ring = (budget - fixed) / A.slot_bytes;
     if (ring > ring_want) ring = ring_want;
     if (ring < 3) return HRN_ERR_UNSUPPORTED;
@@ -647,11 +725,13 @@ HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank
     const int smem = fixed + ring * A.slot_bytes;
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == 1) {
-        if (raw == 2) HRN_CUDA((launch_wide_one<8, 2, 1>(A, smem, budget, st)));
+        if (raw == 1) HRN_CUDA((launch_wide_one<8, 1, 1>(A, smem, budget, st)));
+        else if (raw == 2) HRN_CUDA((launch_wide_one<8, 2, 1>(A, smem, budget, st)));
         else if (raw == 3) HRN_CUDA((launch_wide_one<8, 3, 1>(A, smem, budget, st)));
         else HRN_CUDA((launch_wide_one<8, 4, 1>(A, smem, budget, st)));
     } else {
-        if (raw == 2) HRN_CUDA((launch_wide_one<8, 2, 3>(A, smem, budget, st)));
+        if (raw == 1) HRN_CUDA((launch_wide_one<8, 1, 3>(A, smem, budget, st)));
+        else if (raw == 2) HRN_CUDA((launch_wide_one<8, 2, 3>(A, smem, budget, st)));
         else if (raw == 3) HRN_CUDA((launch_wide_one<8, 3, 3>(A, smem, budget, st)));
         else HRN_CUDA((launch_wide_one<8, 4, 3>(A, smem, budget, st)));
     }

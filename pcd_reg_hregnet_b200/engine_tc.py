@@ -377,15 +377,67 @@ def pack_chain_wide(layers, seg_channels, prec=3):
     return _remember(_wide_cache, key, W1, (Wpack, per_rank[0].numel(), torch.cat(bias).contiguous(), chunks0, widths))
 
 
-def chain_wide(view, layers, kseg=8, prec=None):
+def _split_first_layer(view, layers):
+    """The first layer is linear in front of its ReLU, so the input segments that are constant inside a group (BROADCAST) or
+    depend on the gathered source row only (GATHER) can be applied ONCE PER POINT instead of once per row:
+        W1 x = W_direct x_direct + (W_b x_b)[r / k] + (W_g x_g)[b * N + idx[r]].
+    Returns (direct-only view, layers with the reduced first layer, Zb [groups, n1], Zg [src rows, n1]) or None when the
+    view does not have exactly that shape (one BROADCAST + one GATHER segment without row scales, >= 1 DIRECT segment)."""
+    from ._lib import ACT_NONE, SEG_BROADCAST, SEG_DIRECT, SEG_GATHER
+    W1, b1, act1 = layers[0]
+    kinds = [sg[1] for sg in view.segs]
+    if sorted(kinds).count(SEG_BROADCAST) != 1 or sorted(kinds).count(SEG_GATHER) != 1 or SEG_DIRECT not in kinds:
+        return None
+    if any(sg[4] is not None for sg in view.segs):
+        return None
+    reduced = engine.RowsView(view.rows, group=view.c.group, gather_idx=view.gather_idx, rows_per_batch=view.c.rows_per_batch,
+                              src_rows_per_batch=view.c.src_rows_per_batch)
+    cols, c0, pts = [], 0, {}
+    for mat, mode, ch, col0, _ in view.segs:
+        if mode == SEG_DIRECT:
+            reduced.add(mat, SEG_DIRECT, channels=ch, col0=col0)
+            cols.append(W1[:, c0:c0 + ch])
+        else:
+            pts[mode] = (mat, ch, col0, c0)
+        c0 += ch
+    Z = {}
+    for mode, (mat, ch, col0, cs) in pts.items():
+        key = (W1.data_ptr(), W1._version, cs, ch)
+        Wc = _wide_cache.get(key)
+        if Wc is None:
+            Wc = _remember(_wide_cache, key, W1, W1[:, cs:cs + ch].contiguous())
+        src = engine.RowsView(mat.shape[0]).add(mat, SEG_DIRECT, channels=ch, col0=col0)
+        Z[mode] = engine.layer(src, Wc, None, ACT_NONE)                      # [points, n1] fp32, once per point
+    Zb, Zg = Z[SEG_BROADCAST], Z[SEG_GATHER]
+    key = (W1.data_ptr(), W1._version, "direct")
+    Wd = _wide_cache.get(key)
+    if Wd is None:
+        Wd = _remember(_wide_cache, key, W1, torch.cat(cols, 1).contiguous())
+    return reduced, [(Wd, b1, act1)] + list(layers[1:]), Zb, Zg
+
+
+def _view_ptr(t):
+    """Device pointer of a 2-D view whose rows are contiguous (engine.ptr insists on fully contiguous tensors)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1
+    return t.data_ptr()
+
+
+def chain_wide(view, layers, kseg=8, prec=None, split_first=True):
     """convs + attention tail on the virtual rows: returns (AF [rows / kseg, n3], a [rows])  (layers.py:364-390)."""
     prec = engine.mma_prec() if prec is None else prec
+    Zb = Zg = None
+    split = _split_first_layer(view, layers) if split_first else None
+    if split is not None:
+        view, layers, Zb, Zg = split
     Wpack, rank_bytes, bias, chunks0, widths = pack_chain_wide(layers, [s[2] for s in view.segs], prec)
     dev = bias.device
     G = torch.empty(view.rows // kseg, widths[2], dtype=torch.float32, device=dev)
     a = torch.empty(view.rows, dtype=torch.float32, device=dev)
     engine.call("hrn_chain_wide", ctypes.byref(view.c), engine.ptr(Wpack), rank_bytes, engine.ptr(bias), widths[0], widths[1],
-                widths[2], chunks0, kseg, engine.ptr(G), engine.ptr(a), view.rows, prec, engine.stream())
+                widths[2], chunks0, kseg, _view_ptr(Zb), _view_ptr(Zg), Zg.stride(0) if Zg is not None else 0,
+                engine.ptr(G), engine.ptr(a), view.rows, prec, engine.stream())
     return G, a
 
 

@@ -254,6 +254,7 @@ def test_single_pass_fp16_chain(kseg, mode, dims):
         assert float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale < 2 * tol
 
 
+@pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("B,M,dims,prec,tol", [
     (2, 256, [512, 512, 512], 3, 1e-4),          # CoarseReg convs_1 as in the model (528 -> 512 -> 512 -> 512), 32 tiles
     (1, 16, [512, 512, 512], 3, 1e-4),           # one tile: a single cluster
@@ -261,9 +262,10 @@ def test_single_pass_fp16_chain(kseg, mode, dims):
     (37, 256, [512, 512, 512], 3, 1e-4),         # 592 tiles: several rounds per cluster, ring / phase wrap-around
     (2, 256, [512, 512, 512], 1, 3e-3),          # single-pass fp16 operands
 ])
-def test_chain_wide_cluster_kernel(B, M, dims, prec, tol):
+def test_chain_wide_cluster_kernel(B, M, dims, prec, tol, split):
     """csrc/chain_wide.cu (2-CTA cluster, hidden activations through DSMEM) against an fp64 evaluation of the three
-    layers + softmax_k(max_c) attention + attentive feature (reference layers.py:364-390)."""
+    layers + softmax_k(max_c) attention + attentive feature (reference layers.py:364-390).  split: the group-constant and
+    the gathered input segments of the first layer applied once per point and added as fp32 rows (the model's path)."""
     from pcd_reg_hregnet_b200 import engine_tc
     kseg, N, C = 8, 300, 256
     g = torch.Generator().manual_seed(B * 1000 + M + dims[1])
@@ -284,14 +286,14 @@ def test_chain_wide_cluster_kernel(B, M, dims, prec, tol):
         layers.append((W, b, ACT_RELU))
         X = torch.relu(X @ W.double().t() + b.double())
     assert engine_tc.chain_wide_supported(v, layers, kseg)
-    G, a = engine_tc.chain_wide(v, layers, kseg, prec=prec)
-    G2, a2 = engine_tc.chain_wide(v, layers, kseg, prec=prec)          # a second launch: same bits (no race between the CTAs)
+    G, a = engine_tc.chain_wide(v, layers, kseg, prec=prec, split_first=split)
+    G2, a2 = engine_tc.chain_wide(v, layers, kseg, prec=prec, split_first=split)     # a second launch: same bits (no race between the CTAs)
     torch.cuda.synchronize()
     Xg = X.view(-1, kseg, dims[2])
     scale = float(X.abs().max())
     a_ref = torch.softmax(Xg.max(dim=2)[0], dim=1)
     e_a = float((a.double().view(-1, kseg) - a_ref).abs().max())
     e_g = float((G.double() - (a_ref[:, :, None] * Xg).sum(1)).abs().max()) / scale
-    print(f"chain_wide B={B} M={M} dims={dims} prec={prec}: a {e_a:.2e}  AF {e_g:.2e}")
+    print(f"chain_wide B={B} M={M} dims={dims} prec={prec} split={split}: a {e_a:.2e}  AF {e_g:.2e}")
     assert e_a < tol and e_g < tol, (e_a, e_g)
     assert torch.equal(G, G2) and torch.equal(a, a2)
