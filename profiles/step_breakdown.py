@@ -22,7 +22,7 @@ for r in csv.DictReader(lines):
         d[r["Metric Name"]] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 ids = sorted(by)
 # a step starts with the level-1 furthest-point sampling: the only fps launch over the full clouds
-marks = [n for n, i in enumerate(ids) if "fps_cluster_kernel<512" in by[i]["name"]]
+marks = [n for n, i in enumerate(ids) if "fps_cluster_kernel<512" in by[i]["name"] or "fps_cull_kernel" in by[i]["name"]]
 a = marks[0]
 if len(marks) > 1:
     b = marks[1]
