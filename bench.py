@@ -505,6 +505,12 @@ def _profile_families(reg, steps=3):
             rows_t = a[0]._obj
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
             fl = 2.0 * view_rows * K * cout
+            from pcd_reg_hregnet_b200 import engine_tc as _et
+            if _et.IN_SPLIT:
+                # per-point part of a chain's first layer (engine_tc._split_first_layer): its algorithmic MACs are counted
+                # with the chain launch below, at the reference's rate of once per ROW; only the issued MACs count here
+                rec.append((name, s, e, 0.0, fl * passes))
+                return r
         elif name == "hrn_chain_tc":
             passes = a[17]
             rows_t, nl, n1, n2, cout, view_rows = a[0]._obj, a[3], a[4], a[5], a[7], a[16]
@@ -512,10 +518,15 @@ def _profile_families(reg, steps=3):
             macs = K * n1 + (n1 * n2 + n2 * cout if nl == 3 else n1 * cout)
             fl = 2.0 * view_rows * macs
         elif name == "hrn_chain_wide":
-            passes = a[12]
-            rows_t, n1, n2, n3, view_rows = a[0]._obj, a[4], a[5], a[6], a[11]
+            # (in, W, rank_bytes, bias, n1, n2, n3, chunks0, kseg, Zb, Zg, ldz, G, a, rows, prec, stream)
+            passes = a[15]
+            rows_t, n1, n2, n3, view_rows = a[0]._obj, a[4], a[5], a[6], a[14]
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
-            fl = 2.0 * view_rows * (K * n1 + n1 * n2 + n2 * n3)
+            from pcd_reg_hregnet_b200 import engine_tc as _et
+            # algorithmic = the reference's first layer over all its input channels for every row (layers.py:364-375)
+            fl = 2.0 * view_rows * ((K + _et.SPLIT_K) * n1 + n1 * n2 + n2 * n3)
+            rec.append((name, s, e, fl, 2.0 * view_rows * (K * n1 + n1 * n2 + n2 * n3) * passes))
+            return r
         elif name == "hrn_level_fused":
             # algorithmic MACs per neighbour row of a fused level: detector + descriptor conv stacks + mlp1 + mlp2
             lv, Bc, Mc, kc = a[0], a[10], a[11], a[13]
