@@ -65,6 +65,39 @@ _COSINE_TC = True        # tc modes: CoarseReg's cosine-similarity features as o
 _LEVEL_WS = (2, 3)         # tc mode: levels that run on the warp-specialised fused level kernel (csrc/level_ws.cu)
 
 
+def on_side_stream(fn, like):
+    """Runs fn() on a side stream forked from the current one (events: also valid under CUDA-graph capture) and returns a
+    function that joins the streams and hands back fn's result.  `like`: a tensor on the device the work goes to.
+    Falls back to running fn() in place when side streams are switched off."""
+    if not (_SIDE_STREAM and like.is_cuda):
+        res = fn()
+        return lambda: res
+    main = torch.cuda.current_stream(like.device)
+    side = _api_stream(like.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        res = fn()
+
+    def join():
+        torch.cuda.current_stream(like.device).wait_stream(side)
+        for t in (res.values() if isinstance(res, dict) else (res if isinstance(res, (list, tuple)) else [res])):
+            if torch.is_tensor(t):
+                t.record_stream(torch.cuda.current_stream(like.device))
+        return res
+    return join
+
+
+_api_streams = {}
+
+
+def _api_stream(device):
+    """A second side stream (the first one carries CoarseReg's descriptor branch and the Morton sorts)."""
+    key = torch.device(device).index
+    if key not in _api_streams:
+        _api_streams[key] = torch.cuda.Stream(device=device)
+    return _api_streams[key]
+
+
 def set_precision(mode: str):
     """'fp32' = exact CUDA-core FFMA layers; 'tc' = tcgen05 tensor-core layers (bf16x3 split, fp32 accumulate); 'tcf' = 'tc'
     with single-pass fp16 operands in the correspondence stages."""
@@ -446,8 +479,10 @@ def _fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k, want_af):
     if _chain_ok(v, P["convs_1"], k):
         from . import engine_tc
         _, af, a = engine_tc.chain3(v, P["convs_1"], engine_tc.EPI_ATTN, k, want_rows=False)
-        cor = group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2).view(B, N1, 3)
+        # the correspondence (a small gather) runs beside the confidence head: both only need the attention's results
+        cor = on_side_stream(lambda: group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2), a)
         w = stack(RowsView(B * N1).add(af), P["mlp"], last_act=ACT_SIGMOID).view(B, N1)
+        cor = cor().view(B, N1, 3)
     else:
         F = stack(v, P["convs_1"])
         cor, w, af = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])
@@ -542,8 +577,9 @@ def _coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k, both, want_dis
     if wide:
         # conv stack + attention on a 2-CTA cluster per tile: the 512-wide activations never reach HBM (csrc/chain_wide.cu)
         af, a = engine_tc.chain_wide(v, P["convs_1"], k)
-        cor = group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2).view(B, N1, 3)
+        cor = on_side_stream(lambda: group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2), a)
         w = stack(RowsView(B * N1).add(af), P["mlp"], last_act=ACT_SIGMOID).view(B, N1)
+        cor = cor().view(B, N1, 3)
     else:
         F = stack(v, P["convs_1"])
         cor, w, _ = _tail(F, k, idx, dxyz, B, N1, N2, P["mlp"])

@@ -87,6 +87,10 @@ class HRegNet(nn.Module):
         both = self.feature_extraction.forward_cl(engine.stack_clouds(src_points, dst_points), calls=2)
         S = {k: v[:B] for k, v in both.items()}
         D = {k: v[B:] for k, v in both.items()}
+        # API layout [B,C,N] of the descriptors: one transpose per level over the stacked source + target batch, on the
+        # side stream beside the registration stages (they only read the channels-last tensors)
+        api_desc = engine.on_side_stream(lambda: {k: engine.transpose(v) for k, v in both.items() if k.startswith("desc_")},
+                                         both["desc_1"])
 
         cor3, w3 = self.coarse_corres.forward_cl(S["xyz_3"], S["desc_3"], D["xyz_3"], D["desc_3"], S["sigmas_3"],
                                                  D["sigmas_3"], both=(both["xyz_3"], both["desc_3"]))
@@ -101,13 +105,14 @@ class HRegNet(nn.Module):
         cor1, w1 = self.fine_corres_1.forward_cl(xyz1_t, S["desc_1"], D["xyz_1"], D["desc_1"], S["sigmas_1"],
                                                  D["sigmas_1"])
         _, _, R1, t1 = engine.weighted_kabsch(xyz1_t, cor1, w1, prev=(R2, t2), packed=True)
+        api_desc = api_desc()                                                  # join the side stream
 
-        def api(d):
-            return {k: (engine.transpose(v) if k.startswith("desc_") else v) for k, v in d.items()}
+        def api(d, lo, hi):
+            return {k: (api_desc[k][lo:hi] if k.startswith("desc_") else v) for k, v in d.items()}
 
         return {
             "src_xyz_corres_3": cor3, "src_xyz_corres_2": cor2, "src_xyz_corres_1": cor1,
             "src_dst_weights_3": w3, "src_dst_weights_2": w2, "src_dst_weights_1": w1,
             "rotation": [R3, R2, R1], "translation": [t3, t2, t1],
-            "src_feats": api(S), "dst_feats": api(D),
+            "src_feats": api(S, 0, B), "dst_feats": api(D, B, 2 * B),
         }
