@@ -11,7 +11,8 @@
 // CTA = 128 rows = 128/k keypoints x k neighbours; thread t <-> row t <-> TMEM lane t; persistent over tiles.
 // Every layer: A operand in smem -> tcgen05.mma (bf16 hi/lo split of both operands, 3 MMAs per k-step, fp32
 // accumulate in TMEM) -> tcgen05.ld -> bias+ReLU -> bf16 hi/lo split -> written back IN PLACE as the next layer's
-// A operand.  Chain per tile (9 MMA steps):
+// A operand.  Chain per tile (the detector and the descriptor stack do not depend on each other, so their second and
+// third layers are issued TOGETHER -- six MMA round trips per tile, each one an issue -> commit -> mbarrier wait):
 //   G -[d1;x1]-> C1d | C1x   (the two first layers share their input: ONE step with the weights stacked along N)
 //   C1d -d2-> C2 -d3-> E(CO, stays in TMEM)          | max_c, softmax over the k neighbours, keypoint
 //   C1x -x2-> C2 -x3-> X1(CO)                        | column max over the group
@@ -72,7 +73,8 @@ struct LevelCfg {
     static constexpr int T_ACC0 = CO;
     static constexpr int T_ACCX = CO;
     static constexpr int T_USED = CO + cmax(cmax(cmax(2 * C1, C2), CMID), cmax(CO, CD));
-    static_assert(C2 <= C1, "the second detector layer must not overwrite the parked first descriptor layer");
+    static_assert(2 * C1 <= OPC * 8 && 2 * C2 <= OPC * 8, "the operand buffer holds the inputs of both chains side by side");
+    static_assert(2 * C2 <= cmax(cmax(cmax(2 * C1, C2), CMID), cmax(CO, CD)), "work region holds both second-layer results");
     static constexpr int WPG = KNBR / 32;                           // warps per keypoint group
     static constexpr int KPT = TMR / KNBR;                          // keypoints per tile
     // NG independent 128-thread groups per CTA, each with its own tile, operand buffers and TMEM columns, all sharing
@@ -224,17 +226,21 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     uint4* op_hi = reinterpret_cast<uint4*>(sOp);
     uint4* op_lo = op_hi + Cfg::OPC * TMR;
 
-    // operand ready in smem -> one thread issues layer `li`
-    auto issue = [&](int li, int tcol, bool acc) {
+    // operand ready in smem -> one thread issues layer `li` (operand = chunks [ch0, ch0 + K/8) of the buffer), optionally a
+    // second, independent layer `lj` behind it under the same commit
+    auto issue2 = [&](int li, int ch0, int tcol, bool acc, int lj, int ch1, int tcol1) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         gsync();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_layer(aOp_hi, aOp_lo, Cfg::lk(li), wbase + Cfg::woff(li), Cfg::ln(li), tmem + tcol, acc);
+            issue_layer(aOp_hi + ch0 * TMR * 16, aOp_lo + ch0 * TMR * 16, Cfg::lk(li), wbase + Cfg::woff(li), Cfg::ln(li), tmem + tcol, acc);
+            if (lj >= 0)
+                issue_layer(aOp_hi + ch1 * TMR * 16, aOp_lo + ch1 * TMR * 16, Cfg::lk(lj), wbase + Cfg::woff(lj), Cfg::ln(lj), tmem + tcol1, false);
             umma_commit(bar);
         }
     };
+    auto issue = [&](int li, int tcol, bool acc) { issue2(li, 0, tcol, acc, -1, 0, 0); };
     // -> everybody waits for the accumulator
     auto wait_layer = [&]() {
         mbar_wait(bar, phase);
@@ -243,7 +249,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     };
     auto run_layer = [&](int li, int tcol, bool acc) { issue(li, tcol, acc); wait_layer(); };
     // accumulator [tcol, tcol+Nn) -> relu(x (+ b)) -> bf16 hi/lo operand (in place)
-    auto epi_to_operand = [&](int tcol, int Nn, const float* bb, auto has_bias) {
+    auto epi_to_operand = [&](int tcol, int Nn, const float* bb, auto has_bias, int chd = 0) {
         for (int c0 = 0; c0 < Nn; c0 += 32) {
             uint32_t v[32];
             float f[32];
@@ -251,7 +257,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             bias32<decltype(has_bias)::value>(v, bb + c0, f);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
-                split_store8_relu(f + ch * 8, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
+                split_store8_relu(f + ch * 8, op_hi + (chd + c0 / 8 + ch) * TMR + tid, op_lo + (chd + c0 / 8 + ch) * TMR + tid);
         }
     };
     using yes_t = std::true_type;
@@ -299,13 +305,18 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
                 op_lo[c * TMR + tid] = make_uint4(0, 0, 0, 0);
             }
         }
-        // ---- first layer of both chains: work columns [0, C1) = detector, [C1, 2 C1) = descriptor (parked) ------
+        // ---- first layer of both chains: work columns [0, C1) = detector, [C1, 2 C1) = descriptor ------------------
         run_layer(0, Cfg::T_ACC0, false);
-        // ---- detector chain ------------------------------------------------------------------------------------
+        // ---- second layers d2 | x2 together: operands = chunks [0, C1/8) | [C1/8, 2 C1/8), results in work [0, C2) | [C2, 2 C2)
         epi_to_operand(Cfg::T_ACC0, C1, sB, no_t{});
-        run_layer(1, Cfg::T_ACC0, false);
+        epi_to_operand(Cfg::T_ACC0 + C1, C1, sB, no_t{}, C1 / 8);
+        issue2(1, 0, Cfg::T_ACC0, false, 3, C1 / 8, Cfg::T_ACC0 + C2);
+        wait_layer();
+        // ---- third layers d3 | x3 together: E -> its own columns, X1 -> the work region (its inputs are drained by then) ----
         epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_D2, yes_t{});
-        run_layer(2, Cfg::T_ACCE, false);
+        epi_to_operand(Cfg::T_ACC0 + C2, C2, sB + Cfg::B_X2, yes_t{}, C2 / 8);
+        issue2(2, 0, Cfg::T_ACCE, false, 4, C2 / 8, Cfg::T_ACCX);
+        wait_layer();
         // ---- attention: a = softmax_k(max_c E), keypoint = sum_k a * nn -------------------------------------
         float x1 = 0.f;                                                   // post-ReLU values are >= 0
         for (int c0 = 0; c0 < CO; c0 += 32) {
@@ -336,11 +347,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         }
         const float a = ex / s0;
         if (leader && lane < 3) out_xyz[bm * 3 + lane] = (lane == 0 ? s1 : (lane == 1 ? s2 : s3)) / s0;
-        // ---- descriptor chain ----------------------------------------------------------------------------------
-        epi_to_operand(Cfg::T_ACC0 + C1, C1, sB, no_t{});
-        run_layer(3, Cfg::T_ACC0, false);
-        epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_X2, yes_t{});
-        run_layer(4, Cfg::T_ACCX, false);
+        // ---- descriptor head ------------------------------------------------------------------------------------
         // X1 -> operand, and its column maximum over the rows of the group (taken before the ReLU: max and ReLU commute)
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
