@@ -11,10 +11,11 @@
 // Tile = 128 rows = 128/k keypoints x k neighbours.  Per tile and group (a group = 8 epilogue warps + 1 MMA warp +
 // 1 weight-stream warp; two threads per row, each draining alternate 32-column blocks of an accumulator):
 //
-//   G -[d1;x1]-> C1d | C1x            C1x stays parked in TMEM
+//   G -[d1;x1]-> C1d | C1x            both drained at once: the two conv stacks do not depend on each other
 //   C1d -d2-> C2d -d3-> E             attention a = softmax_k(max_c E), keypoint = sum_k a nn
+//   C1x -x2-> C2x -x3-> X1            issued BESIDE the detector chain (x2 right behind d2, x3 under the attention phase)
 //   E*a -Wc-> M1  (first K-segment of mlp1; its column sums over the group are the attentive feature)
-//   C1x -x2-> C2x -x3-> X1 -Wb-> M1 += (second K-segment); column max of X1 over the group
+//   X1 -Wb-> M1 += (second K-segment); column max of X1 over the group
 //   M1 + Wa.max_k(X1) + b -> relu -m2-> D -> max_k = descriptor
 //
 // The reference's third mlp1 segment, max_k(X1) repeated over the k neighbours (layers.py:203-204), is constant inside a
@@ -25,9 +26,11 @@
 // Pipelining: an accumulator is drained in 32-column blocks (TMEM -> bias/ReLU -> bf16 hi/lo -> operand buffer); every
 // block raises its own mbarrier, and the MMA warp issues the next layer's K=16 pieces as their blocks land, so the tensor
 // core works on layer l+1 while layer l is still being drained.  The weights of all layers stream from L2 as K=16 pieces
-// through a cp.async.bulk ring.  TMEM columns of a group (C = first width): L0 [0,2C), C2d [2C,3C), E [2C,4C),
-// M1 [0,C), C2x [3C,4C), X1 [C,3C), D [2C,4C) -- consecutive layers never share columns except d3 over C2d, which
-// therefore waits for the complete drain.
+// through a cp.async.bulk ring, in issue order: L0 d2 x2 d3 x3 m1c m1b m2.  TMEM columns of a group (C = first width):
+// L0 [0,2C), C2d [2C,3C), C2x [3C,4C), E [0,2C), X1 [2C,4C), M1 [0,C), D [2C,4C).  x3 overwrites the columns of C2d / C2x
+// and m1c those of E: these two wait for the complete drain of their input; every other layer starts on its first block.
+// The operand buffer holds the inputs of both stacks side by side (detector: chunks [0,C/8), descriptor: [C/8,2C/8));
+// the E*a drain may only enter the descriptor half when x3 has read it.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
@@ -63,12 +66,18 @@ struct LwCfg {
     static constexpr int KPT = LTM / KNBR;                              // keypoints per tile
     static constexpr int KSEG = KNBR;                                   // lanes per keypoint inside a warp
     static constexpr int PER = 32 / KSEG;
-    // layers in execution order: L0=[d1;x1]  d2  d3  m1c(E*a)  x2  x3  m1b(X1)  m2
-    __host__ __device__ static constexpr int lk(int l) { return l == 0 ? KG : (l == 3 || l == 6) ? CO : C; }
-    __host__ __device__ static constexpr int ln(int l) { return (l == 0 || l == 2 || l == 5 || l == 7) ? CO : C; }
+    // layers in issue order: L0=[d1;x1]  d2  x2  d3  x3  m1c(E*a)  m1b(X1)  m2
+    enum { L_0 = 0, L_D2 = 1, L_X2 = 2, L_D3 = 3, L_X3 = 4, L_M1C = 5, L_M1B = 6, L_M2 = 7 };
+    __host__ __device__ static constexpr int lk(int l) { return l == 0 ? KG : (l == L_M1C || l == L_M1B) ? CO : C; }
+    __host__ __device__ static constexpr int ln(int l) { return (l == 0 || l == L_D3 || l == L_X3 || l == L_M2) ? CO : C; }
     __host__ __device__ static constexpr int lacc(int l) {              // first TMEM column of the accumulator
-        return l == 0 ? 0 : l == 1 ? 2 * C : l == 2 ? 2 * C : l == 3 ? 0 : l == 4 ? 3 * C : l == 5 ? C : l == 6 ? 0 : 2 * C;
+        return l == L_D2 ? 2 * C : l == L_X2 ? 3 * C : (l == L_X3 || l == L_M2) ? 2 * C : 0;
     }
+    // descriptor-stack layers read the second half of the operand buffer: first K=16 piece / first 32-column block
+    __host__ __device__ static constexpr int lpiece0(int l) { return (l == L_X2 || l == L_X3) ? C / 16 : 0; }
+    __host__ __device__ static constexpr int lblock0(int l) { return (l == L_X2 || l == L_X3) ? C / 32 : 0; }
+    // layers that overwrite TMEM columns their own input is still being drained from: all input blocks first
+    __host__ __device__ static constexpr bool lwaitall(int l) { return l == L_X3 || l == L_M1C; }
     __host__ __device__ static constexpr int woff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += lk(i) * ln(i) * 4; return o; }
     static constexpr int W_BYTES = woff(LW_NL);
     // biases (floats): d1 d2 d3 x1 x2 x3 m1 m2
@@ -154,7 +163,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     constexpr int C = Cfg::C, CO = Cfg::CO, KNBR = Cfg::KNBR, CIN = Cfg::CIN, NG = Cfg::NG, RING = Cfg::RING,
                   KSEG = Cfg::KSEG, PER = Cfg::PER, KPT = Cfg::KPT, OPC = Cfg::OPC;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_wfull[NG][RING], s_wempty[NG][RING], s_opb[NG][LW_MAXBLK], s_accf[NG], s_gready[NG];
+    __shared__ __align__(8) uint64_t s_wfull[NG][RING], s_wempty[NG][RING], s_opb[NG][LW_MAXBLK], s_accf[NG][2], s_gready[NG];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp_all = tid >> 5, lane = tid & 31;
@@ -173,7 +182,8 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         for (int g = 0; g < NG; ++g) {
             for (int i = 0; i < RING; ++i) { mbar_init(smem_u32(&s_wfull[g][i]), 1); mbar_init(smem_u32(&s_wempty[g][i]), 1); }
             for (int i = 0; i < LW_MAXBLK; ++i) mbar_init(smem_u32(&s_opb[g][i]), 4);
-            mbar_init(smem_u32(&s_accf[g]), 1);
+            mbar_init(smem_u32(&s_accf[g][0]), 1);
+            mbar_init(smem_u32(&s_accf[g][1]), 1);
             mbar_init(smem_u32(&s_gready[g]), LW_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,7 +201,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     const int vgrid = (int)gridDim.x * NG, vblock = (int)blockIdx.x * NG + grp;        // groups act as virtual CTAs
     const uint32_t op_a = smem_u32(gsm), ring_a = op_a + Cfg::OP_BYTES;
     const uint32_t wfull0 = smem_u32(&s_wfull[grp][0]), wempty0 = smem_u32(&s_wempty[grp][0]);
-    const uint32_t opb0 = smem_u32(&s_opb[grp][0]), accf = smem_u32(&s_accf[grp]), gready = smem_u32(&s_gready[grp]);
+    const uint32_t opb0 = smem_u32(&s_opb[grp][0]), accf = smem_u32(&s_accf[grp][0]), gready = smem_u32(&s_gready[grp]);
 
     if (warp < LW_EPI_WARPS) {
         // ================= epilogue warps: gather, drains, attention, reductions ================================
@@ -203,11 +213,17 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         const int kp_local = wq * (32 / KSEG) + seg;             // keypoint of this row inside the tile
         uint4* op_hi = reinterpret_cast<uint4*>(gsm);
         uint4* op_lo = op_hi + OPC * LTM;
-        uint32_t accph = 0;
+        // Layer l completes on barrier l & 1 (eight layers per tile: the assignment repeats).  With ONE barrier the two
+        // stacks' layers, which no longer wait for each other, could complete two phases before the epilogue looks -- a
+        // parity wait cannot see that; on either barrier a layer's MMAs depend on a drain that follows the wait for the
+        // barrier's previous layer.
+        uint32_t accph = 0, acc_l = 0;
         auto ebar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(LW_EPI_WARPS * 32) : "memory"); };
-        auto wait_acc = [&]() {
-            mbar_wait(accf, accph);
-            accph ^= 1;
+        auto wait_acc = [&]() {                                  // waits are made in layer order
+            const uint32_t s_ = acc_l & 1u;
+            mbar_wait(accf + 8 * s_, (accph >> s_) & 1u);
+            accph ^= 1u << s_;
+            ++acc_l;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         };
         auto publish = [&](int b) {                              // operand block b is in shared memory
@@ -225,14 +241,14 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             }
         };
         // accumulator [tcol, tcol + ncols) -> relu(x + b) -> operand
-        auto drain_plain = [&](int tcol, int ncols, const float* bb) {
+        auto drain_plain = [&](int tcol, int ncols, const float* bb, int b0 = 0) {       // -> operand blocks b0 ..
             for (int b = h; b < ncols / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + tcol + 32 * b, v);
                 lw_bias_relu32(v, bb + 32 * b, f);
-                store_block(f, b);
-                publish(b);
+                store_block(f, b0 + b);
+                publish(b0 + b);
             }
         };
 
@@ -281,14 +297,17 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 if (lane == 0) mbar_arrive(gready);
             }
             LW_STAMP(0);                                                      // gather
-            // ---- detector chain -------------------------------------------------------------------------------------
+            // ---- first layers of both stacks, then the second ones as their results arrive ------------------------------
             wait_acc();                                                       // L0: C1d | C1x
             LW_STAMP(1);
-            drain_plain(Cfg::lacc(0), C, sB + Cfg::B_D1);
+            drain_plain(Cfg::lacc(0), C, sB + Cfg::B_D1);                     // -> d2
+            drain_plain(Cfg::lacc(0) + C, C, sB + Cfg::B_X1, C / 32);         // -> x2 (descriptor half of the buffer)
             LW_STAMP(2);
             wait_acc();                                                       // d2
             LW_STAMP(3);
-            drain_plain(Cfg::lacc(1), C, sB + Cfg::B_D2);
+            drain_plain(Cfg::lacc(Cfg::L_D2), C, sB + Cfg::B_D2);             // -> d3
+            wait_acc();                                                       // x2
+            drain_plain(Cfg::lacc(Cfg::L_X2), C, sB + Cfg::B_X2, C / 32);     // -> x3, which runs under the attention phase
             LW_STAMP(4);
             wait_acc();                                                       // d3: E
             LW_STAMP(5);
@@ -296,7 +315,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             float x1 = 0.f;                                                   // post-ReLU values are >= 0
             for (int b = h; b < CO / 32; b += 2) {
                 uint32_t v[32];
-                tmem_ld32(tmem + lane_base + Cfg::lacc(2) + 32 * b, v);
+                tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_D3) + 32 * b, v);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_D3 + 32 * b + 4 * e);
@@ -319,10 +338,12 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             }
             LW_STAMP(6);                                                      // attention
             // attentive feature map E*a = first K-segment of mlp1; its column sums = the attentive feature (layers.py:157-159)
+            bool x3_done = false;
             for (int b = h; b < CO / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
-                tmem_ld32(tmem + lane_base + Cfg::lacc(2) + 32 * b, v);
+                if (b >= C / 32 && !x3_done) { wait_acc(); x3_done = true; }      // x3 has read the descriptor half of the buffer
+                tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_D3) + 32 * b, v);
                 lw_bias_relu32(v, sB + Cfg::B_D3 + 32 * b, f);
                 const f32x2_t a2 = f2_pack(a, a);
 #pragma unroll
@@ -334,21 +355,14 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 for (int i = 0; i < PER; ++i) out_af[bm * CO + 32 * b + pos * PER + i] = f[i];
             }
             LW_STAMP(7);                                                      // E*a drain + attentive feature
-            // ---- descriptor chain -----------------------------------------------------------------------------------
-            wait_acc();                                                       // the E*a segment has been consumed
+            // ---- descriptor head ------------------------------------------------------------------------------------
+            wait_acc();                                                       // m1c: the E*a segment has been consumed
             LW_STAMP(8);
-            drain_plain(Cfg::lacc(0) + C, C, sB + Cfg::B_X1);                 // parked C1x
-            LW_STAMP(9);
-            wait_acc();                                                       // x2
-            LW_STAMP(10);
-            drain_plain(Cfg::lacc(4), C, sB + Cfg::B_X2);
-            LW_STAMP(11);
-            wait_acc();                                                       // x3: X1
             LW_STAMP(12);
             for (int b = h; b < CO / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
-                tmem_ld32(tmem + lane_base + Cfg::lacc(5) + 32 * b, v);
+                tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_X3) + 32 * b, v);
                 lw_bias_relu32(v, sB + Cfg::B_X3 + 32 * b, f);
                 store_block(f, b);
                 publish(b);
@@ -386,12 +400,12 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             }
             LW_STAMP(15);                                                     // mat-vec
             ebar();                                                           // sKpb complete
-            wait_acc();                                                       // M1 = Wc.(E*a) + Wb.X1
+            wait_acc();                                                       // m1b: M1 = Wc.(E*a) + Wb.X1
             LW_STAMP(16);
             for (int b = h; b < C / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
-                tmem_ld32(tmem + lane_base + Cfg::lacc(3) + 32 * b, v);
+                tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_M1B) + 32 * b, v);
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_M1 + 32 * b + e);
@@ -410,7 +424,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             for (int b = h; b < CO / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
-                tmem_ld32(tmem + lane_base + Cfg::lacc(7) + 32 * b, v);
+                tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_M2) + 32 * b, v);
                 lw_bias_relu32(v, sB + Cfg::B_M2 + 32 * b, f);
                 lw_seg_reduce<KSEG, true>(f, lane);
 #pragma unroll
@@ -442,26 +456,30 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                     const uint32_t d = tmem + Cfg::lacc(l), idesc = lw_idesc(Nn);
                     const uint64_t w_desc0 = DESC_FIXED | ((uint64_t)Nn << 16);                     // LBO = N * 16 B
                     const uint32_t wlo16 = 2 * Nn;
-                    if (l == 2) {                      // d3 overwrites the columns of C2d: the whole drain first
-                        for (int b = 0; b < K / 32; ++b) { mbar_wait(opb0 + 8 * b, (opph >> b) & 1); opph ^= 1u << b; }
+                    const int B0 = Cfg::lblock0(l), P0 = Cfg::lpiece0(l);
+                    if (Cfg::lwaitall(l)) {            // overwrites columns its input is drained from: the whole drain first
+                        for (int b = 0; b < K / 32; ++b) { mbar_wait(opb0 + 8 * (B0 + b), (opph >> (B0 + b)) & 1); opph ^= 1u << (B0 + b); }
                     }
                     for (int p = 0; p < K / 16; ++p) {
-                        if (l != 0 && l != 2 && (p & 1) == 0) { mbar_wait(opb0 + 8 * (p >> 1), (opph >> (p >> 1)) & 1); opph ^= 1u << (p >> 1); }
+                        if (l != 0 && !Cfg::lwaitall(l) && (p & 1) == 0) {
+                            const int bi = B0 + (p >> 1);
+                            mbar_wait(opb0 + 8 * bi, (opph >> bi) & 1); opph ^= 1u << bi;
+                        }
                         LW_STAMP(33);                                         // waiting for operand blocks
                         mbar_wait(wfull0 + 8 * ws, wpar);
                         LW_STAMP(34);                                         // waiting for weights
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a16 = (op_a >> 4) + p * P16, w16 = (ring_a >> 4) + ws * SLOT16;
+                        const uint32_t a16 = (op_a >> 4) + (P0 + p) * P16, w16 = (ring_a >> 4) + ws * SLOT16;
                         const uint64_t ah = a_desc0 | a16, al = a_desc0 | (a16 + LO16);
                         const uint64_t wh = w_desc0 | w16, wl = w_desc0 | (w16 + wlo16);
-                        umma_bf16(d, ah, wh, idesc, (p > 0 || l == 6) ? 1u : 0u);
+                        umma_bf16(d, ah, wh, idesc, (p > 0 || l == Cfg::L_M1B) ? 1u : 0u);
                         umma_bf16(d, al, wh, idesc, 1u);
                         umma_bf16(d, ah, wl, idesc, 1u);
                         umma_commit(wempty0 + 8 * ws);
                         if (++ws == (uint32_t)RING) { ws = 0; wpar ^= 1; }
                         LW_STAMP(35);                                         // issuing
                     }
-                    umma_commit(accf);
+                    umma_commit(accf + 8 * (l & 1));
                 }
             }
         }

@@ -198,8 +198,8 @@ def which_level_ws(k, cin, det, desc):
 
 def pack_level_ws(level, det, desc):
     """Folded parameter dicts of detector_l / desc_extractor_l -> (Wpack uint8, WaT fp32 [2C, C], biases fp32) in the
-    LwCfg layout of csrc/level_ws.cu: K=16 weight pieces of the 8 MMA layers in execution order
-    [d1;x1] d2 d3 mlp1[E*a] x2 x3 mlp1[X1] mlp2; the max_k(X1) block of mlp1 (its first 2C input channels,
+    LwCfg layout of csrc/level_ws.cu: K=16 weight pieces of the 8 MMA layers in issue order
+    [d1;x1] d2 x2 d3 x3 mlp1[E*a] mlp1[X1] mlp2; the max_k(X1) block of mlp1 (its first 2C input channels,
     layers.py:203-205) goes to the CUDA cores as the transposed fp32 matrix WaT.  Grouped input channels re-ordered as in
     pack_level: [feat(C), rel(3), dist(1), 0-pad]."""
     key = (level,) + tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
@@ -216,8 +216,8 @@ def pack_level_ws(level, det, desc):
     perm = list(range(4, 4 + cin)) + [0, 1, 2, 3]
     first = torch.zeros(2 * C, KG, dtype=torch.float32, device=d1.device)
     first[:, :cin + 4] = torch.cat([d1[:, perm], x1[:, perm]], 0)
-    parts = [_pieces(first, KG), _pieces(d2, C), _pieces(d3, C), _pieces(m1[:, 2 * CO:].contiguous(), CO),
-             _pieces(x2, C), _pieces(x3, C), _pieces(m1[:, CO:2 * CO].contiguous(), CO), _pieces(m2, C)]
+    parts = [_pieces(first, KG), _pieces(d2, C), _pieces(x2, C), _pieces(d3, C), _pieces(x3, C),
+             _pieces(m1[:, 2 * CO:].contiguous(), CO), _pieces(m1[:, CO:2 * CO].contiguous(), CO), _pieces(m2, C)]
     Wpack = torch.cat(parts).contiguous()
     WaT = m1[:, :CO].t().contiguous().view(CO // 4, 4, C).permute(0, 2, 1).contiguous()     # [CO/4][C][4]
     biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()
