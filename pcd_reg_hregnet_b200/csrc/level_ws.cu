@@ -28,7 +28,8 @@
 // core works on layer l+1 while layer l is still being drained.  The weights of all layers stream from L2 as K=16 pieces
 // through a cp.async.bulk ring, in issue order: L0 d2 x2 d3 x3 m1c m1b m2.  TMEM columns of a group (C = first width):
 // L0 [0,2C), C2d [2C,3C), C2x [3C,4C), E [0,2C), X1 [2C,4C), M1 [0,C), D [2C,4C).  x3 overwrites the columns of C2d / C2x
-// and m1c those of E: these two wait for the complete drain of their input; every other layer starts on its first block.
+// (it waits for the complete drain of C2x) and m1c the first half of E (it waits for that half of the E*a drain); every
+// other layer starts on its first block.
 // The operand buffer holds the inputs of both stacks side by side (detector: chunks [0,C/8), descriptor: [C/8,2C/8));
 // the E*a drain may only enter the descriptor half when x3 has read it.
 #include "common.cuh"
@@ -76,8 +77,10 @@ struct LwCfg {
     // descriptor-stack layers read the second half of the operand buffer: first K=16 piece / first 32-column block
     __host__ __device__ static constexpr int lpiece0(int l) { return (l == L_X2 || l == L_X3) ? C / 16 : 0; }
     __host__ __device__ static constexpr int lblock0(int l) { return (l == L_X2 || l == L_X3) ? C / 32 : 0; }
-    // layers that overwrite TMEM columns their own input is still being drained from: all input blocks first
-    __host__ __device__ static constexpr bool lwaitall(int l) { return l == L_X3 || l == L_M1C; }
+    // layers that overwrite TMEM columns their own input is still being drained from: that many leading input blocks must
+    // have left TMEM before the first MMA (x3 -> [2C,4C) over C2d | C2x: all of C2x; m1c -> M1 [0,C) over the first half
+    // of E: the blocks of that half, the second half of the E*a drain then overlaps the MMAs)
+    __host__ __device__ static constexpr int lprewait(int l) { return (l == L_X3 || l == L_M1C) ? C / 32 : 0; }
     __host__ __device__ static constexpr int woff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += lk(i) * ln(i) * 4; return o; }
     static constexpr int W_BYTES = woff(LW_NL);
     // biases (floats): d1 d2 d3 x1 x2 x3 m1 m2
@@ -378,24 +381,31 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 constexpr int TPK = LW_EPI_WARPS * 32 / C;                    // thread sets along the keypoints
                 constexpr int OPT = (KPT + TPK - 1) / TPK;                    // keypoints per thread
                 const int j = et % C, k0 = (et / C) * OPT;
-                float acc[OPT];
+                // two partial sums per keypoint (even / odd input channels of every group of four), packed fp32x2 FMAs:
+                // half the arithmetic instructions of the scalar chain
+                f32x2_t acc[OPT];
 #pragma unroll
-                for (int o = 0; o < OPT; ++o) acc[o] = 0.f;
+                for (int o = 0; o < OPT; ++o) acc[o] = f2_pack(0.f, 0.f);
                 if (k0 < KPT) {
                     const float4* w4 = reinterpret_cast<const float4*>(WaT) + j;      // Wa4 [CO/4][C][4]: 16 B per lane, coalesced
 #pragma unroll 2
                     for (int c = 0; c < CO; c += 8) {
                         const float4 wa = __ldg(w4 + (size_t)(c / 4) * C), wb = __ldg(w4 + (size_t)(c / 4 + 1) * C);
+                        const f32x2_t wa0 = f2_pack(wa.x, wa.y), wa1 = f2_pack(wa.z, wa.w), wb0 = f2_pack(wb.x, wb.y), wb1 = f2_pack(wb.z, wb.w);
 #pragma unroll
                         for (int o = 0; o < OPT; ++o) {
                             const float4 ma = *reinterpret_cast<const float4*>(sCol + (k0 + o) * CO + c);
                             const float4 mb = *reinterpret_cast<const float4*>(sCol + (k0 + o) * CO + c + 4);
-                            acc[o] = fmaf(wa.w, ma.w, fmaf(wa.z, ma.z, fmaf(wa.y, ma.y, fmaf(wa.x, ma.x, acc[o]))));
-                            acc[o] = fmaf(wb.w, mb.w, fmaf(wb.z, mb.z, fmaf(wb.y, mb.y, fmaf(wb.x, mb.x, acc[o]))));
+                            acc[o] = f2_fma(wa1, f2_pack(ma.z, ma.w), f2_fma(wa0, f2_pack(ma.x, ma.y), acc[o]));
+                            acc[o] = f2_fma(wb1, f2_pack(mb.z, mb.w), f2_fma(wb0, f2_pack(mb.x, mb.y), acc[o]));
                         }
                     }
 #pragma unroll
-                    for (int o = 0; o < OPT; ++o) sKpb[(k0 + o) * C + j] = acc[o];
+                    for (int o = 0; o < OPT; ++o) {
+                        float lo_, hi_;
+                        f2_unpack(acc[o], lo_, hi_);
+                        sKpb[(k0 + o) * C + j] = lo_ + hi_;
+                    }
                 }
             }
             LW_STAMP(15);                                                     // mat-vec
@@ -457,11 +467,10 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                     const uint64_t w_desc0 = DESC_FIXED | ((uint64_t)Nn << 16);                     // LBO = N * 16 B
                     const uint32_t wlo16 = 2 * Nn;
                     const int B0 = Cfg::lblock0(l), P0 = Cfg::lpiece0(l);
-                    if (Cfg::lwaitall(l)) {            // overwrites columns its input is drained from: the whole drain first
-                        for (int b = 0; b < K / 32; ++b) { mbar_wait(opb0 + 8 * (B0 + b), (opph >> (B0 + b)) & 1); opph ^= 1u << (B0 + b); }
-                    }
+                    const int PRE = Cfg::lprewait(l);
+                    for (int b = 0; b < PRE; ++b) { mbar_wait(opb0 + 8 * (B0 + b), (opph >> (B0 + b)) & 1); opph ^= 1u << (B0 + b); }
                     for (int p = 0; p < K / 16; ++p) {
-                        if (l != 0 && !Cfg::lwaitall(l) && (p & 1) == 0) {
+                        if (l != 0 && (p >> 1) >= PRE && (p & 1) == 0) {
                             const int bi = B0 + (p >> 1);
                             mbar_wait(opb0 + 8 * bi, (opph >> bi) & 1); opph ^= 1u << bi;
                         }

@@ -54,8 +54,8 @@ def main():
             run()
             torch.cuda.synchronize()
             L.hrn_level_ws_prof(buf, 0)
-            names = ["gather", "wait L0", "drain C1d", "wait d2", "drain C2d", "wait d3", "attention", "E*a drain", "wait m1c",
-                     "drain C1x", "wait x2", "drain C2x", "wait x3", "X1 drain", "bar", "mat-vec", "bar+wait m1b", "M1 drain",
+            names = ["gather", "wait L0", "drain C1d+C1x", "wait d2", "C2d|wait x2|C2x", "wait d3", "attention", "E*a drain+x3", "wait m1c",
+                     "-", "-", "-", "-", "X1 drain", "bar", "mat-vec", "bar+wait m1b", "M1 drain",
                      "wait m2", "desc epilogue"]
             tot = sum(buf[i] for i in range(20))
             print("epilogue warp 0 of CTA 0, cycles per phase (share):")
