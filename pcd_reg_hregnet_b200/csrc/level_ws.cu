@@ -98,7 +98,7 @@ struct LwCfg {
     static_assert(NG * T_GROUP <= 512, "TMEM");
     static_assert(KNBR == 16 || KNBR == 32, "group reductions are written for 16 or 32 neighbours (one warp holds whole groups)");
     static_assert(C % 64 == 0 && CO / 32 <= LW_MAXBLK, "two epilogue halves take alternate 32-column blocks");
-    static_assert(CIN % 16 == 0, "the feature chunks are split between the two threads of a row");
+    static_assert(CIN % 64 == 0 && KG - CIN <= 32, "each thread of a row converts whole 32-channel blocks; the geometry block is one block");
     static_assert(SMEM + 512 <= 227 * 1024, "shared memory (dynamic + the static barriers)");
     static_assert((KPT * C) % (LW_EPI_WARPS * 32) == 0 || (LW_EPI_WARPS * 32) % (KPT * C) == 0, "mat-vec mapping");
 };
@@ -166,7 +166,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     constexpr int C = Cfg::C, CO = Cfg::CO, KNBR = Cfg::KNBR, CIN = Cfg::CIN, NG = Cfg::NG, RING = Cfg::RING,
                   KSEG = Cfg::KSEG, PER = Cfg::PER, KPT = Cfg::KPT, OPC = Cfg::OPC;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_wfull[NG][RING], s_wempty[NG][RING], s_opb[NG][LW_MAXBLK], s_accf[NG][2], s_gready[NG];
+    __shared__ __align__(8) uint64_t s_wfull[NG][RING], s_wempty[NG][RING], s_opb[NG][LW_MAXBLK], s_accf[NG][2];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp_all = tid >> 5, lane = tid & 31;
@@ -187,7 +187,6 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             for (int i = 0; i < LW_MAXBLK; ++i) mbar_init(smem_u32(&s_opb[g][i]), 4);
             mbar_init(smem_u32(&s_accf[g][0]), 1);
             mbar_init(smem_u32(&s_accf[g][1]), 1);
-            mbar_init(smem_u32(&s_gready[g]), LW_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,7 +203,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     const int vgrid = (int)gridDim.x * NG, vblock = (int)blockIdx.x * NG + grp;        // groups act as virtual CTAs
     const uint32_t op_a = smem_u32(gsm), ring_a = op_a + Cfg::OP_BYTES;
     const uint32_t wfull0 = smem_u32(&s_wfull[grp][0]), wempty0 = smem_u32(&s_wempty[grp][0]);
-    const uint32_t opb0 = smem_u32(&s_opb[grp][0]), accf = smem_u32(&s_accf[grp][0]), gready = smem_u32(&s_gready[grp]);
+    const uint32_t opb0 = smem_u32(&s_opb[grp][0]), accf = smem_u32(&s_accf[grp][0]);
 
     if (warp < LW_EPI_WARPS) {
         // ================= epilogue warps: gather, drains, attention, reductions ================================
@@ -277,27 +276,26 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
 #pragma unroll
                 for (int i = 0; i < 2 * CH; ++i) fv[i] = __ldg(fr + i);
                 nx = __ldg(pp); ny = __ldg(pp + 1); nz = __ldg(pp + 2);
+                // every 32-channel block is published on its own: the first layer's MMAs start on the first block while
+                // the rest of the row is still being converted (feature blocks h*CH/4 .. by half h, the geometry block by h = 1)
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const float x[8] = {fv[2 * c].x, fv[2 * c].y, fv[2 * c].z, fv[2 * c].w,
                                         fv[2 * c + 1].x, fv[2 * c + 1].y, fv[2 * c + 1].z, fv[2 * c + 1].w};
                     split_store8(x, op_hi + (h * CH + c) * LTM + rt, op_lo + (h * CH + c) * LTM + rt);
+                    if ((c & 3) == 3) publish(h * (CH / 4) + (c >> 2));
                 }
-                if (h == 0) {
+                if (h == 1) {
                     const float rx = nx - __ldg(qq), ry = ny - __ldg(qq + 1), rz = nz - __ldg(qq + 2);
                     const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 0.f, 0.f, 0.f, 0.f};
                     split_store8(x, op_hi + (CIN / 8) * LTM + rt, op_lo + (CIN / 8) * LTM + rt);
-                } else {
 #pragma unroll
                     for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {         // K padding
                         op_hi[c * LTM + rt] = make_uint4(0, 0, 0, 0);
                         op_lo[c * LTM + rt] = make_uint4(0, 0, 0, 0);
                     }
+                    publish(CIN / 32);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(gready);
             }
             LW_STAMP(0);                                                      // gather
             // ---- first layers of both stacks, then the second ones as their results arrive ------------------------------
@@ -441,7 +439,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 for (int i = 0; i < PER; ++i) out_desc[bm * CO + 32 * b + pos * PER + i] = f[i];
             }
             LW_STAMP(19);                                                     // descriptor epilogue
-            // the TMEM reads of this tile are ordered before the next tile's first MMA by the gready arrival
+            // the TMEM reads of this tile are ordered before the next tile's first MMA by the block arrivals of its gather
             // (tcgen05.fence::before_thread_sync in front of it); sX / sCol / sKpb are rewritten only after the next
             // tile's named barriers
         }
@@ -451,15 +449,13 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             constexpr uint64_t DESC_FIXED = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);          // SBO = 128 B
             const uint64_t a_desc0 = DESC_FIXED | ((uint64_t)((LTM * 16) >> 4) << 16);             // LBO = 2048 B
             constexpr uint32_t LO16 = Cfg::OP_PLANE >> 4, P16 = (2 * LTM * 16) >> 4, SLOT16 = Cfg::SLOT >> 4;
-            uint32_t ws = 0, wpar = 0, gph = 0, opph = 0;
+            uint32_t ws = 0, wpar = 0, opph = 0;
 #ifdef LW_PROF
             const bool prof_on = blockIdx.x == 0 && grp == 0;
             long long prof_t = clock64();
 #endif
             for (int tile = vblock; tile < n_tiles; tile += vgrid) {
-                mbar_wait(gready, gph);
-                gph ^= 1;
-                LW_STAMP(32);                                                 // waiting for the gathered input
+                LW_STAMP(32);
 #pragma unroll
                 for (int l = 0; l < LW_NL; ++l) {
                     const int K = Cfg::lk(l), Nn = Cfg::ln(l);
@@ -470,7 +466,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                     const int PRE = Cfg::lprewait(l);
                     for (int b = 0; b < PRE; ++b) { mbar_wait(opb0 + 8 * (B0 + b), (opph >> (B0 + b)) & 1); opph ^= 1u << (B0 + b); }
                     for (int p = 0; p < K / 16; ++p) {
-                        if (l != 0 && (p >> 1) >= PRE && (p & 1) == 0) {
+                        if ((p >> 1) >= PRE && (p & 1) == 0) {
                             const int bi = B0 + (p >> 1);
                             mbar_wait(opb0 + 8 * bi, (opph >> bi) & 1); opph ^= 1u << bi;
                         }
