@@ -442,7 +442,7 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
     constexpr int PER_CTA = THREADS * Q;                   // sorted positions per CTA
     constexpr int NBIN = 1024;
     constexpr int S = CS * NWARP;                          // packets per iteration
-    static_assert(S == 32, "one packet per lane");
+    static_assert(S <= 32, "at most one packet per lane");
     static_assert(Q % 2 == 0, "packed update");
     extern __shared__ __align__(16) unsigned char s_dyn[];
     unsigned long long* s_mail = reinterpret_cast<unsigned long long*>(s_dyn);      // [2][S]
@@ -657,8 +657,8 @@ fps_cull_kernel(const float* __restrict__ xyz, float* __restrict__ temp_io, int3
         }
         FPS_STAMP(3);
         // ---- C: this iteration's packets (one per lane), the winner ---------------------------------------------------
-        unsigned bo, h;
-        {
+        unsigned bo = 0u, h = 0x3fffffu;
+        if (S == 32 || lane < S) {
             const uint32_t mail = mail_u32 + (par ? mail_par_bytes : 0u) + (uint32_t)lane * 8u;
             for (;;) {
                 asm volatile("ld.relaxed.cluster.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(bo), "=r"(h) : "r"(mail) : "memory");
@@ -691,6 +691,11 @@ int launch_fps_cull_t(const float* xyz, float* temp, int32_t* idx, int B, int N,
 template <int THREADS, int Q>
 int launch_fps_cull(const float* xyz, float* temp, int32_t* idx, int B, int N, int M, int log2T, cudaStream_t st) {
     static const bool poll = [] { const char* e = getenv("HRN_FPS_POLL"); return e && e[0] == '1'; }();
+    static const bool fat = [] { const char* e = getenv("HRN_FPS_FAT"); return e && e[0] == '1'; }();   // 8 warps x 32 points
+    if (fat && THREADS * Q == 8192) {
+        if (poll) return launch_fps_cull_t<256, 32, false>(xyz, temp, idx, B, N, M, log2T, st);
+        return launch_fps_cull_t<256, 32, true>(xyz, temp, idx, B, N, M, log2T, st);
+    }
     if (poll) return launch_fps_cull_t<THREADS, Q, false>(xyz, temp, idx, B, N, M, log2T, st);
     return launch_fps_cull_t<THREADS, Q, true>(xyz, temp, idx, B, N, M, log2T, st);
 }
