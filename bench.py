@@ -512,11 +512,16 @@ def _profile_families(reg, steps=3):
                 rec.append((name, s, e, 0.0, fl * passes))
                 return r
         elif name == "hrn_chain_tc":
+            # (..., rows a[16], prec a[17], Zb a[18], Zg a[19], ldz a[20], stream)
             passes = a[17]
             rows_t, nl, n1, n2, cout, view_rows = a[0]._obj, a[3], a[4], a[5], a[7], a[16]
             K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
-            macs = K * n1 + (n1 * n2 + n2 * cout if nl == 3 else n1 * cout)
-            fl = 2.0 * view_rows * macs
+            from pcd_reg_hregnet_b200 import engine_tc as _et
+            tail = (n1 * n2 + n2 * cout if nl == 3 else n1 * cout)
+            # algorithmic = the reference's first layer over all its input channels for every row
+            fl = 2.0 * view_rows * ((K + (_et.SPLIT_K if a[19] is not None else 0)) * n1 + tail)
+            rec.append((name, s, e, fl, 2.0 * view_rows * (K * n1 + tail) * passes))
+            return r
         elif name == "hrn_chain_wide":
             # (in, W, rank_bytes, bias, n1, n2, n3, chunks0, kseg, Zb, Zg, ldz, G, a, rows, prec, stream)
             passes = a[15]

@@ -158,10 +158,14 @@ int hrn_layer_tc_groupmax(const hrn_rows_t* in, const void* Wp, const float* bia
  * (optional) = the rows Y*a (layers.py:150-159,329-332,384-390,446-450).  Hidden activations ReLU, last = `act`.
  * W = K=16 weight pieces of the layers in execution order (pcd_reg_hregnet_b200/engine_tc.pack_chain), bias = b1|b2|b3,
  * n1..n3 = issued widths (multiples of 16; the last = cout padded), chunks0 = 8-wide K chunks of the virtual input.
- * prec = 3: bf16 hi/lo operands (pieces [hi|lo][2][N][8]); prec = 1: single-pass fp16 (pieces [2][N][8] fp16), see hrn_layer_tc. */
+ * prec = 3: bf16 hi/lo operands (pieces [hi|lo][2][N][8]); prec = 1: single-pass fp16 (pieces [2][N][8] fp16), see hrn_layer_tc.
+ * Zb [rows / kseg, ldz] (nullable; needs kseg = 8), Zg [source rows, ldz] (nullable): fp32 rows ADDED to the first layer's
+ * pre-activations -- row r takes Zb[r / kseg] + Zg[b * src_rows_per_batch + gather_idx[r]] -- the part of the (linear) first
+ * layer that is constant inside a group / depends on the gathered row only, applied once per point by the caller; `in` then
+ * only holds the per-row segments (n1 must be a multiple of 32). */
 int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl, int n1, int n2, int n3, int cout, int act,
                  int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows, int prec,
-                 void* stream);
+                 const float* Zb, const float* Zg, int ldz, void* stream);
 
 /* CoarseReg's conv stack convs_1 (528 -> 512 -> 512 -> 512, models/HRegNet/layers.py:364-375) + its attention tail
  * (layers.py:384-390: a = softmax_k(max_c Y), attentive feature = sum_k a Y) on a CLUSTER OF TWO CTAs per 128-row tile: each

@@ -47,7 +47,7 @@ SIGNATURES = {
     "hrn_level_fused": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_level_ws": [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "hrn_chain_tc": [ctypes.POINTER(Rows), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
-                     c_int, c_vp, c_vp, c_ll, c_int, c_vp],
+                     c_int, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_vp],
     "hrn_chain_wide": [ctypes.POINTER(Rows), c_vp, c_ll, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp,
                        c_ll, c_int, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],

@@ -42,6 +42,12 @@ struct ChainArgs {
     int chunks0;             // 8-wide K chunks of the virtual input (segments padded to 8, total padded to even)
     int mode;
     int kseg;                // rows per group (8, 16 or 32)
+    // optional fp32 rows ADDED to the first layer's pre-activations -- the part of that (linear) layer which is constant
+    // inside a group (Zb [rows / kseg, ldz], nullable) / depends on the gathered source row only (Zg [src rows, ldz]),
+    // applied once per point by the caller (engine_tc._split_first_layer); see chain_wide.cu
+    const float* Zb;
+    const float* Zg;
+    int ldz;
 };
 
 __device__ __forceinline__ uint32_t ch_idesc(int N) {
@@ -88,6 +94,9 @@ constexpr int CW_THREADS = (CW_EPI_WARPS + CW_PROD_WARPS + 2) * 32;   // 576
 constexpr int CW_STAGE_BYTES = 4 * CTM * 32;                          // 4 chunks x 128 rows x (8 fp32 | 8 bf16 hi + lo) = 16 KB
 constexpr int CW_RING_MAX = 8;                                        // weight slots
 constexpr int CW_GS_MAX = 4, CW_HS_MAX = 4;                           // operand ring depths
+constexpr int CW_ZS_MAX = 4;
+constexpr int CW_ZG_BYTES = CTM * 32 * 4;                             // gathered rows of a 32-column block: 128 x 128 B
+constexpr int CW_ZSTAGE_BYTES = CW_ZG_BYTES + (CTM / 8) * 32 * 4;     // + up to 16 group rows = 18 KB
 constexpr int CW_TP = 36;
 constexpr int CW_TILE_BYTES = CW_EPI_WARPS * 32 * CW_TP * 4;
 
@@ -97,6 +106,7 @@ struct ChainWsArgs {
     int use_tile;            // transpose tile for coalesced Y stores present
     int gs, hs;              // depths of ring G (gathered input stages) and ring H (hidden-layer blocks)
     int acc_stride, nbuf;    // TMEM accumulators: nbuf = 512 / acc_stride buffers (4 x 128 or 2 x 256 columns), used round-robin
+    int zs;                  // Z ring stages (0: no Z rows)
 };
 
 // PREC 3: bf16 hi/lo operands, three MMAs per K=16 piece; PREC 1: single fp16 plane, one MMA per piece (the hi plane of
@@ -106,10 +116,11 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
     const ChainArgs& A = AW.c;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_wfull[CW_RING_MAX], s_wempty[CW_RING_MAX], s_gfull[CW_GS_MAX], s_gempty[CW_GS_MAX],
-        s_hfull[CW_HS_MAX], s_hempty[CW_HS_MAX], s_accf[4], s_fin[4];
+        s_hfull[CW_HS_MAX], s_hempty[CW_HS_MAX], s_accf[4], s_fin[4], s_zfull[CW_ZS_MAX], s_zempty[CW_ZS_MAX];
     __shared__ uint32_t s_tmem;
 
-    const int RING = A.ring, GS = AW.gs, HS = AW.hs;
+    const int RING = A.ring, GS = AW.gs, HS = AW.hs, ZS = AW.zs;
+    const bool has_z = A.Zg != nullptr;
     const int ACC = AW.acc_stride, BM = AW.nbuf - 1;       // accumulator of layer L: columns (L & BM) * ACC
     const uint32_t SLOT_BYTES = (uint32_t)A.slot_bytes;
     uint8_t* sG = smem;
@@ -119,6 +130,8 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
     float* sBias = reinterpret_cast<float*>(sRaw + RAW * CW_STAGE_BYTES);
     float* sX = sBias + 3 * 256;                            // [2][128] row maxima exchanged by the epilogue groups
     float* sTile = sX + 2 * CTM;
+    // Z ring behind everything else: [zs][128 gathered rows x 128 B (16-byte chunks XOR-swizzled by row) | 16 group rows x 128 B]
+    uint8_t* sZ = reinterpret_cast<uint8_t*>(sTile) + (AW.use_tile ? CW_TILE_BYTES : 0);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nl = A.nl;
@@ -131,6 +144,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
         for (int i = 0; i < CW_GS_MAX; ++i) { mbar_init(smem_u32(&s_gfull[i]), CW_PROD_WARPS); mbar_init(smem_u32(&s_gempty[i]), 1); }
         for (int i = 0; i < CW_HS_MAX; ++i) { mbar_init(smem_u32(&s_hfull[i]), 4); mbar_init(smem_u32(&s_hempty[i]), 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&s_accf[i]), 1); mbar_init(smem_u32(&s_fin[i]), CW_EPI_WARPS); }
+        for (int i = 0; i < CW_ZS_MAX; ++i) { mbar_init(smem_u32(&s_zfull[i]), CW_PROD_WARPS * 32); mbar_init(smem_u32(&s_zempty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -154,6 +168,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
         uint32_t accph = 0;                                  // phase bits of s_accf[4]
         int L = 0;                                           // layers completed by this CTA -> accumulator L & BM
         int hs = 0; uint32_t hpar = 0; int hq = 0;           // ring H position, global block counter
+        int zs = 0; uint32_t zpar = 0;                       // Z ring position
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long r = (long long)tile * CTM + rt;
             for (int l = 0; l + 1 < nl; ++l, ++L) {
@@ -165,6 +180,10 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     if ((hq & 1) == eg) {
                         uint32_t v[32];
                         tmem_ld32(tmem + lane_base + b * ACC + c0, v);
+                        const bool zblk = has_z && l == 0;
+                        const float* zg = reinterpret_cast<const float*>(sZ + (size_t)zs * CW_ZSTAGE_BYTES) + rt * 32;
+                        const float* zb = reinterpret_cast<const float*>(sZ + (size_t)zs * CW_ZSTAGE_BYTES + CW_ZG_BYTES) + (rt / KSEG) * 32;
+                        if (zblk) mbar_wait(smem_u32(&s_zfull[zs]), zpar);      // this block's Z rows have landed
                         mbar_wait(smem_u32(&s_hempty[hs]), hpar ^ 1);
                         uint4* h_hi = reinterpret_cast<uint4*>(sH + (size_t)hs * CW_STAGE_BYTES);
                         uint4* h_lo = h_hi + 4 * CTM;
@@ -178,6 +197,19 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])), f2_pack(b0.z, b0.w)), s[2], s[3]);
                                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])), f2_pack(b1.x, b1.y)), s[4], s[5]);
                                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])), f2_pack(b1.z, b1.w)), s[6], s[7]);
+                                if (zblk) {       // + gathered row (+ group row), fp32
+                                    const float4 g0 = *reinterpret_cast<const float4*>(zg + (((2 * ch) ^ (rt & 7)) << 2));
+                                    const float4 g1 = *reinterpret_cast<const float4*>(zg + (((2 * ch + 1) ^ (rt & 7)) << 2));
+                                    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+                                    if (A.Zb) {
+                                        q0 = *reinterpret_cast<const float4*>(zb + ch * 8);
+                                        q1 = *reinterpret_cast<const float4*>(zb + ch * 8 + 4);
+                                    }
+                                    f2_unpack(f2_add(f2_add(f2_pack(s[0], s[1]), f2_pack(q0.x, q0.y)), f2_pack(g0.x, g0.y)), s[0], s[1]);
+                                    f2_unpack(f2_add(f2_add(f2_pack(s[2], s[3]), f2_pack(q0.z, q0.w)), f2_pack(g0.z, g0.w)), s[2], s[3]);
+                                    f2_unpack(f2_add(f2_add(f2_pack(s[4], s[5]), f2_pack(q1.x, q1.y)), f2_pack(g1.x, g1.y)), s[4], s[5]);
+                                    f2_unpack(f2_add(f2_add(f2_pack(s[6], s[7]), f2_pack(q1.z, q1.w)), f2_pack(g1.z, g1.w)), s[6], s[7]);
+                                }
                                 if (PREC == 1) {
                                     h_hi[ch * CTM + rt] = make_uint4(pack_f16x2_relu(s[0], s[1]), pack_f16x2_relu(s[2], s[3]),
                                                                      pack_f16x2_relu(s[4], s[5]), pack_f16x2_relu(s[6], s[7]));
@@ -191,9 +223,13 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&s_hfull[hs]));
+                        if (lane == 0) {
+                            mbar_arrive(smem_u32(&s_hfull[hs]));
+                            if (zblk) mbar_arrive(smem_u32(&s_zempty[zs]));
+                        }
                     }
                     if (++hs == HS) { hs = 0; hpar ^= 1; }
+                    if (has_z && l == 0 && ++zs == ZS) { zs = 0; zpar ^= 1; }
                 }
             }
             // ---- last layer: the groups take alternate 32-column chunks --------------------------------------------
@@ -419,16 +455,48 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
             if (lane == 0) mbar_arrive(smem_u32(&s_gfull[gs]));
             if (++gs == GS) { gs = 0; gpar ^= 1; }
         };
+        // Z blocks of a tile (first-layer bias rows), one ring stage per 32-column block: warp pw copies the gathered rows
+        // pw*16 .. +16 (4 rows x 128 B per instruction) and, for groups of 8 rows, the group rows 2pw, 2pw+1
+        int zs = 0; uint32_t zpar = 0;
+        auto z_blocks = [&](int tile) {
+            const int gl = 2 * pw + (lane >> 3), chunk = lane & 7;
+            const float* zsrc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned ru = (unsigned)tile * CTM + pw * 16 + i * 4 + (lane >> 3);
+                const long long zr = (long long)(ru / (unsigned)in.rows_per_batch) * in.src_rows_per_batch + in.gather_idx[ru];
+                zsrc[i] = A.Zg + zr * A.ldz + chunk * 4;
+            }
+            const float* zbsrc = A.Zb ? A.Zb + ((long long)tile * (CTM / 8) + gl) * A.ldz + chunk * 4 : nullptr;
+            const int nb = A.n[0] / 32;
+            for (int j = 0; j < nb; ++j) {
+                mbar_wait_backoff(smem_u32(&s_zempty[zs]), zpar ^ 1);
+                const uint32_t base = smem_u32(sZ + (size_t)zs * CW_ZSTAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = pw * 16 + i * 4 + (lane >> 3);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + rl * 128 + ((chunk ^ (rl & 7)) << 4)), "l"(zsrc[i] + 32 * j) : "memory");
+                }
+                if (zbsrc && lane < 16)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + CW_ZG_BYTES + gl * 128 + (chunk << 4)), "l"(zbsrc + 32 * j) : "memory");
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_zfull[zs])) : "memory");
+                if (++zs == ZS) { zs = 0; zpar ^= 1; }
+            }
+        };
         int my_tiles = 0;
         if ((int)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
         const int total = my_tiles * n_st0;
         if (total > 0) resolve(ltile);
 #pragma unroll
         for (int d = 0; d < RAW; ++d) issue(d, sc[d]);
+        int filled = 0;                                      // stages delivered: a tile's Z blocks follow its last stage
         for (int q = 0; q < total; q += RAW) {
 #pragma unroll
             for (int d = 0; d < RAW; ++d) {
-                if (q + d < total) { fill(d, sc[d]); issue(d, sc[d]); }
+                if (q + d < total) {
+                    fill(d, sc[d]); issue(d, sc[d]);
+                    if (++filled % n_st0 == 0 && has_z) z_blocks((int)blockIdx.x + (filled / n_st0 - 1) * (int)gridDim.x);
+                }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -577,7 +645,7 @@ cudaError_t launch_chain(const ChainWsArgs& AW, int kseg, bool narrow, int prec,
 // header; `kseg` = rows per group (8, 16 or 32; ignored for mode 0); rows must be a multiple of 128.
 HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias, int nl, int n1, int n2, int n3, int cout,
                          int act, int chunks0, int mode, int kseg, float* Y, int ldy, float* G, float* a, long long rows,
-                         int prec, void* stream) {
+                         int prec, const float* Zb, const float* Zg, int ldz, void* stream) {
     if (!in || !W || !bias || rows < 0 || in->n_seg < 1 || in->n_seg > 4 || (nl != 2 && nl != 3)) return HRN_ERR_BAD_ARG;
     if (prec != 1 && prec != 3) return HRN_ERR_BAD_ARG;
     const int nn[3] = {n1, n2, nl == 3 ? n3 : 16};
@@ -599,11 +667,15 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
     if (mode == EPI_STORE && !Y) return HRN_ERR_BAD_ARG;
     if (mode == EPI_ATTN && act != HRN_ACT_RELU) return HRN_ERR_UNSUPPORTED;
     if (Y && (cout & 3) == 0 && ((ldy & 3) || ((uintptr_t)Y & 15))) return HRN_ERR_UNSUPPORTED;
+    if (Zb && !Zg) return HRN_ERR_BAD_ARG;
+    if (Zg && (!in->gather_idx || in->rows_per_batch <= 0 || ldz < n1 || (ldz & 3) || ((uintptr_t)Zg & 15) || (n1 & 31))) return HRN_ERR_BAD_ARG;
+    if (Zb && (kseg != 8 || in->group != 8 || ((uintptr_t)Zb & 15))) return HRN_ERR_UNSUPPORTED;
     if (rows == 0) return HRN_OK;
     ChainArgs A;
     A.in = *in; A.W = (const uint8_t*)W; A.bias = bias; A.Y = Y; A.G = G; A.a = a; A.rows = rows; A.ldy = ldy;
     A.n[0] = n1; A.n[1] = n2; A.n[2] = nl == 3 ? n3 : 16; A.nl = nl; A.cout = cout; A.act = act;
     A.chunks0 = chunks0; A.mode = mode; A.kseg = kseg;
+    A.Zb = Zb; A.Zg = Zg; A.ldz = ldz;
     int maxn = n1 > n2 ? n1 : n2;
     if (nl == 3 && n3 > maxn) maxn = n3;
     A.slot_bytes = maxn * (prec == 1 ? 32 : 64);
@@ -616,10 +688,12 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
         const int raw = narrow ? 4 : 2;
         const int tile_b = Y ? CW_TILE_BYTES : 0;
         int gs = 3, hs = 3, fixed = 0, ring = 0, use_tile = Y ? 1 : 0;
+        const int zs = Zg ? 2 : 0;
+        const bool one_stage = Zg && chunks0 <= 4;                 // one input stage per tile: no need to run stages ahead
         for (int attempt = 0; attempt < 4; ++attempt) {            // keep >= 4 weight slots: shrink the operand rings, then drop the tile
-            gs = attempt >= 1 ? 2 : 3; hs = attempt >= 2 ? 2 : 3;
+            gs = one_stage ? 1 : (attempt >= 1 ? 2 : 3); hs = attempt >= 2 ? 2 : 3;
             use_tile = (Y && attempt < 3) ? 1 : 0;
-            fixed = (gs + hs + raw) * CW_STAGE_BYTES + 3 * 256 * 4 + 2 * CTM * 4;
+            fixed = (gs + hs + raw) * CW_STAGE_BYTES + 3 * 256 * 4 + 2 * CTM * 4 + zs * CW_ZSTAGE_BYTES;
             ring = (budget - fixed - (use_tile ? tile_b : 0)) / A.slot_bytes;
             if (ring >= 4) break;
         }
@@ -630,6 +704,7 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
         AW.n_tiles = (int)(rows / CTM);
         AW.use_tile = use_tile;
         AW.gs = gs; AW.hs = hs;
+        AW.zs = zs;
         AW.acc_stride = narrow ? 128 : 256;
         AW.nbuf = 512 / AW.acc_stride;
         const int smem_ws = fixed + ring * A.slot_bytes + (use_tile ? CW_TILE_BYTES : 0);

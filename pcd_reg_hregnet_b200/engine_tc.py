@@ -306,7 +306,14 @@ def pack_chain(layers, seg_channels, prec=3):
 
 def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act=None, prec=None):
     """Runs 2-3 folded layers on the virtual rows.  Returns (Y rows | None, G groups | None, a rows | None)."""
+    global SPLIT_K
     prec = engine.mma_prec() if prec is None else prec
+    Zb = Zg = None
+    SPLIT_K = 0
+    if SPLIT_CHAINS and len(layers) >= 2 and (kseg == 8 or all(sg[1] != engine.SEG_BROADCAST for sg in view.segs)):
+        split = _split_first_layer(view, layers)
+        if split is not None:
+            view, layers, Zb, Zg = split
     Wpack, bias, chunks0, widths, cout, _ = pack_chain(layers, [s[2] for s in view.segs], prec)
     nl = len(layers)
     act = layers[-1][2] if last_act is None else last_act
@@ -316,7 +323,8 @@ def chain(view, layers, mode, kseg=8, want_rows=True, want_groups=True, last_act
     G = torch.empty(view.rows // kseg, cout, dtype=torch.float32, device=dev) if (want_groups and mode != EPI_STORE) else None
     a = torch.empty(view.rows, dtype=torch.float32, device=dev) if mode == EPI_ATTN else None
     engine.call("hrn_chain_tc", ctypes.byref(view.c), engine.ptr(Wpack), engine.ptr(bias), nl, n[0], n[1], n[2], cout, act,
-                chunks0, mode, kseg, engine.ptr(Y), cout, engine.ptr(G), engine.ptr(a), view.rows, prec, engine.stream())
+                chunks0, mode, kseg, engine.ptr(Y), cout, engine.ptr(G), engine.ptr(a), view.rows, prec,
+                _view_ptr(Zb), _view_ptr(Zg), Zg.stride(0) if Zg is not None else 0, engine.stream())
     return Y, G, a
 
 
@@ -329,6 +337,7 @@ _wide_cache = {}
 # launches run (their MACs are part of that first layer, not extra algorithmic work)
 SPLIT_K = 0
 IN_SPLIT = False
+SPLIT_CHAINS = True      # apply the first-layer split in the single-CTA chain kernel too (FineReg convs_1, CoarseReg convs_2)
 
 
 def chain_wide_supported(view, layers, k):
@@ -386,12 +395,14 @@ def _split_first_layer(view, layers):
     """The first layer is linear in front of its ReLU, so the input segments that are constant inside a group (BROADCAST) or
     depend on the gathered source row only (GATHER) can be applied ONCE PER POINT instead of once per row:
         W1 x = W_direct x_direct + (W_b x_b)[r / k] + (W_g x_g)[b * N + idx[r]].
-    Returns (direct-only view, layers with the reduced first layer, Zb [groups, n1], Zg [src rows, n1]) or None when the
-    view does not have exactly that shape (one BROADCAST + one GATHER segment without row scales, >= 1 DIRECT segment)."""
+    Returns (direct-only view, layers with the reduced first layer, Zb [groups, n1] | None, Zg [src rows, n1]) or None when
+    the view does not have that shape (one GATHER segment, at most one BROADCAST segment, no row scales, >= 1 DIRECT segment)."""
     from ._lib import ACT_NONE, SEG_BROADCAST, SEG_DIRECT, SEG_GATHER
     W1, b1, act1 = layers[0]
     kinds = [sg[1] for sg in view.segs]
-    if sorted(kinds).count(SEG_BROADCAST) != 1 or sorted(kinds).count(SEG_GATHER) != 1 or SEG_DIRECT not in kinds:
+    if kinds.count(SEG_BROADCAST) > 1 or kinds.count(SEG_GATHER) != 1 or SEG_DIRECT not in kinds:
+        return None
+    if W1.shape[0] % 32:
         return None
     if any(sg[4] is not None for sg in view.segs):
         return None
@@ -418,7 +429,7 @@ def _split_first_layer(view, layers):
             Z[mode] = engine.layer(src, Wc, None, ACT_NONE)                  # [points, n1] fp32, once per point
     finally:
         IN_SPLIT = False
-    Zb, Zg = Z[SEG_BROADCAST], Z[SEG_GATHER]
+    Zb, Zg = Z.get(SEG_BROADCAST), Z[SEG_GATHER]
     key = (W1.data_ptr(), W1._version, "direct")
     Wd = _wide_cache.get(key)
     if Wd is None:
