@@ -769,38 +769,48 @@ int launch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One WARP per cloud, for the small power-of-two clouds of the lower hierarchy levels (N = 256 / 512 / 1024: the
-// weighted samplings 1024 -> 512 and 512 -> 256 of models.py:31-39).  With 8 warps per cloud an iteration of these is
-// nothing but the packet exchange between the warps (~650 cycles for 4 points per thread); with P = N / 32 points per
-// lane there is nothing to exchange: update, two REDUX, one shared-memory lookup of the winner.
-// Slot s of lane l holds point k = l + 32 * bitrev_log2P(s): the reference's tie-break key of that point is
-// bitrev_log2N(k) = bitrev_5(l) << log2P | s (N = T here), i.e. a lane's smallest key is its FIRST slot with the maximum.
-template <int P, bool WEIGHTED>
-__global__ void __launch_bounds__(32)
+// A few warps per cloud, for the small power-of-two clouds of the lower hierarchy levels (N = 256 / 512 / 1024: the
+// weighted samplings 1024 -> 512 and 512 -> 256 of models.py:31-39).  An iteration of these is a chain of dependent
+// steps (update -> REDUX -> key -> REDUX -> exchange -> winner lookup); with 8 warps and 4 points per thread the tagged
+// packet exchange alone cost ~650 cycles, with ONE warp (32 points per lane) the update runs at a single warp's issue
+// rate (588 cycles).  NW warps with P = N / (32 NW) points per lane and the cheapest possible exchange -- one 8-byte
+// packet per warp in shared memory, ONE named barrier per iteration (buffers alternate by iteration parity), every
+// thread compares the NW packets itself -- sit between the two.
+// Slot s of lane l of warp w holds point k = l + 32 * (w + NW * bitrev_logP(s)): the reference's tie-break key of that
+// point is bitrev_logN(k) = bitrev_5(l) << (logNW + logP) | bitrev_logNW(w) << logP | s  (N = T here), i.e. a lane's
+// smallest key is its FIRST slot with the maximum.
+template <int P, int NW, bool WEIGHTED>
+__global__ void __launch_bounds__(32 * NW)
 fps_warp_kernel(const float* __restrict__ xyz, const float* __restrict__ weights, float* __restrict__ temp_io,
                 int32_t* __restrict__ idx_out, int M) {
-    constexpr int N = 32 * P;
-    constexpr int LOG2P = P == 32 ? 5 : P == 16 ? 4 : P == 8 ? 3 : -1;
-    static_assert(LOG2P > 0, "P = 8, 16 or 32");
+    constexpr int N = 32 * P * NW;
+    constexpr int LOG2P = P == 32 ? 5 : P == 16 ? 4 : P == 8 ? 3 : P == 4 ? 2 : P == 2 ? 1 : -1;
+    constexpr int LOG2W = NW == 1 ? 0 : NW == 2 ? 1 : NW == 4 ? 2 : NW == 8 ? 3 : -1;
+    static_assert(LOG2P > 0 && LOG2W >= 0, "P = 2..32, NW = 1, 2, 4 or 8");
     __shared__ float s_cloud[3 * N];
-    const int lane = threadIdx.x, b = blockIdx.x;
+    __shared__ __align__(16) unsigned long long s_pkt[2][NW > 1 ? NW : 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x;
     xyz += (size_t)b * N * 3;
     if (WEIGHTED) weights += (size_t)b * N;
     if (temp_io) temp_io += (size_t)b * N;
     idx_out += (size_t)b * M;
-    for (int i = lane; i < 3 * N; i += 32) s_cloud[i] = xyz[i];
-    __syncwarp();
+    for (int i = threadIdx.x; i < 3 * N; i += 32 * NW) s_cloud[i] = xyz[i];
+    __syncthreads();
+    auto k_of_slot = [&](int l, int w, int s) -> int {
+        return l + 32 * (w + NW * (int)(__brev((unsigned)s) >> (32 - LOG2P)));
+    };
     float px[P], py[P], pz[P], pt[P], pw[WEIGHTED ? P : 1];
 #pragma unroll
     for (int s = 0; s < P; ++s) {
-        const int k = lane + 32 * (int)(__brev((unsigned)s) >> (32 - LOG2P));
+        const int k = k_of_slot(lane, warp, s);
         px[s] = s_cloud[k * 3 + 0]; py[s] = s_cloud[k * 3 + 1]; pz[s] = s_cloud[k * 3 + 2];
         if (WEIGHTED) pw[s] = weights[k];
         pt[s] = temp_io ? temp_io[k] : 1e10f;
     }
-    const unsigned lanekey = (__brev((unsigned)lane) >> 27) << LOG2P;
+    const unsigned bw = LOG2W ? (__brev((unsigned)warp) >> (32 - (LOG2W ? LOG2W : 1))) : 0u;
+    const unsigned lanekey = ((__brev((unsigned)lane) >> 27) << (LOG2W + LOG2P)) | (bw << LOG2P);
     float x1 = s_cloud[0], y1 = s_cloud[1], z1 = s_cloud[2];
-    if (lane == 0) idx_out[0] = 0;
+    if (threadIdx.x == 0) idx_out[0] = 0;
 #pragma unroll 1
     for (int j = 1; j < M; ++j) {
         const f32x2_t cx2 = f2_pack(x1, x1), cy2 = f2_pack(y1, y1), cz2 = f2_pack(z1, z1);
@@ -821,25 +831,39 @@ fps_warp_kernel(const float* __restrict__ xyz, const float* __restrict__ weights
             for (int i = 0; i < w; ++i) mm[i] = fmaxf(mm[i], mm[i + w]);
         const float m = mm[0];
         const unsigned om = WEIGHTED ? hrn_ford(m) : (__float_as_uint(m) ^ 0x80000000u);
-        const unsigned wm = __reduce_max_sync(0xffffffffu, om);
+        unsigned wm = __reduce_max_sync(0xffffffffu, om);
         unsigned sb = P - 1;
 #pragma unroll
         for (int s = P - 2; s >= 0; --s)
             if (pt[s] == m) sb = (unsigned)s;
-        const unsigned kmin = __reduce_min_sync(0xffffffffu, (om == wm) ? (lanekey | sb) : 0xffffffffu);
-        const int kw = (int)(__brev(kmin >> LOG2P) >> 27) + 32 * (int)(__brev(kmin & (unsigned)(P - 1)) >> (32 - LOG2P));
+        unsigned kmin = __reduce_min_sync(0xffffffffu, (om == wm) ? (lanekey | sb) : 0xffffffffu);
+        if (NW > 1) {
+            // one packet per warp, one barrier, everybody picks the best of the NW packets
+            const int par = j & 1;
+            if (lane == 0) s_pkt[par][warp] = ((unsigned long long)wm << 32) | kmin;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const unsigned long long pk = s_pkt[par][w];
+                const unsigned o = (unsigned)(pk >> 32), kk = (unsigned)pk;
+                if (w == 0 || o > wm || (o == wm && kk < kmin)) { wm = o; kmin = kk; }
+            }
+        }
+        const int wl = (int)(__brev(kmin >> (LOG2W + LOG2P)) >> 27);
+        const int ww = LOG2W ? (int)(__brev((kmin >> LOG2P) & (unsigned)(NW - 1)) >> (32 - (LOG2W ? LOG2W : 1))) : 0;
+        const int kw = k_of_slot(wl, ww, (int)(kmin & (unsigned)(P - 1)));
         x1 = s_cloud[kw * 3 + 0]; y1 = s_cloud[kw * 3 + 1]; z1 = s_cloud[kw * 3 + 2];
-        if (lane == 0) idx_out[j] = kw;
+        if (threadIdx.x == 0) idx_out[j] = kw;
     }
     if (temp_io) {
 #pragma unroll
-        for (int s = 0; s < P; ++s) temp_io[lane + 32 * (int)(__brev((unsigned)s) >> (32 - LOG2P))] = pt[s];
+        for (int s = 0; s < P; ++s) temp_io[k_of_slot(lane, warp, s)] = pt[s];
     }
 }
 
-template <int P, bool W>
+template <int P, int NW, bool W>
 int launch_fps_warp(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int M, cudaStream_t st) {
-    fps_warp_kernel<P, W><<<B, 32, 0, st>>>(xyz, w, temp, idx, M);
+    fps_warp_kernel<P, NW, W><<<B, 32 * NW, 0, st>>>(xyz, w, temp, idx, M);
     HRN_LAUNCH_CHECK();
     return HRN_OK;
 }
@@ -855,6 +879,12 @@ inline bool fps_warp_enabled() {       // HRN_FPS_WARP=0: the multi-warp cluster
     return on;
 }
 
+inline bool fps_warp_forced() { return getenv("HRN_FPS_WARPS") != nullptr; }
+inline int fps_warp_count() {          // HRN_FPS_WARPS = 1, 2, 4 (default) or 8 warps per small cloud (A/B)
+    static const int n = [] { const char* e = getenv("HRN_FPS_WARPS"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 8) ? v : 4; }();
+    return n;
+}
+
 template <bool W>
 int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, int B, int N, int M, cudaStream_t st) {
     // opt_n_threads (cuda_utils.h:22-27): 2^floor(log2 N) clamped to [1,1024]  (defines the tie-break only)
@@ -866,9 +896,20 @@ int dispatch_fps(const float* xyz, const float* w, float* temp, int32_t* idx, in
     // B * CS may exceed the SM count: clusters are independent, the surplus simply runs as a second wave.
     // small power-of-two clouds (N = T: the key is the bit-reversed index): one warp per cloud, no exchange at all
     if (fps_warp_enabled()) {
-        if (N == 1024) return launch_fps_warp<32, W>(xyz, w, temp, idx, B, M, st);
-        if (N == 512) return launch_fps_warp<16, W>(xyz, w, temp, idx, B, M, st);
-        if (N == 256) return launch_fps_warp<8, W>(xyz, w, temp, idx, B, M, st);
+        const int nw = fps_warp_count();
+        if (N == 1024) {                    // measured (64 clouds, 1024 -> 512): 1 / 2 / 4 / 8 warps = 152.9 / 162.8 / 126.1 / 177.3 us
+            if (nw == 1) return launch_fps_warp<32, 1, W>(xyz, w, temp, idx, B, M, st);
+            if (nw == 2) return launch_fps_warp<16, 2, W>(xyz, w, temp, idx, B, M, st);
+            if (nw == 8) return launch_fps_warp<4, 8, W>(xyz, w, temp, idx, B, M, st);
+            return launch_fps_warp<8, 4, W>(xyz, w, temp, idx, B, M, st);
+        }
+        if (N == 512) {                     // measured (64 clouds, 512 -> 256): 1 / 2 / 4 / 8 warps = 64.5 / 60.3 / 64.4 / 74.6 us
+            if (nw == 1) return launch_fps_warp<16, 1, W>(xyz, w, temp, idx, B, M, st);
+            if (nw == 8) return launch_fps_warp<2, 8, W>(xyz, w, temp, idx, B, M, st);
+            if (nw == 4 && fps_warp_forced()) return launch_fps_warp<4, 4, W>(xyz, w, temp, idx, B, M, st);
+            return launch_fps_warp<8, 2, W>(xyz, w, temp, idx, B, M, st);
+        }
+        if (N == 256) return launch_fps_warp<8, 1, W>(xyz, w, temp, idx, B, M, st);
     }
     if (N <= 1024) {
         if (N <= 256) return launch_fps_cluster<256, 1, W>(xyz, w, temp, idx, B, N, M, log2T, 1, st);
