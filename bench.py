@@ -532,6 +532,14 @@ def _profile_families(reg, steps=3):
             fl = 2.0 * view_rows * ((K + _et.SPLIT_K) * n1 + n1 * n2 + n2 * n3)
             rec.append((name, s, e, fl, 2.0 * view_rows * (K * n1 + n1 * n2 + n2 * n3) * passes))
             return r
+        elif name == "hrn_chain_wide_head":
+            # (in, W, rank_bytes, bias, n1, n2, n3 (padded), chunks0, act, Y, rows, prec, stream): c -> c -> c -> 1
+            passes = a[11]
+            rows_t, n1, n2, view_rows = a[0]._obj, a[4], a[5], a[10]
+            K = sum(rows_t.seg[i].channels for i in range(rows_t.n_seg))
+            fl = 2.0 * view_rows * (K * n1 + n1 * n2 + n2 * 1)
+            rec.append((name, s, e, fl, 2.0 * view_rows * (K * n1 + n1 * n2 + n2 * a[6]) * passes))
+            return r
         elif name == "hrn_level_fused":
             # algorithmic MACs per neighbour row of a fused level: detector + descriptor conv stacks + mlp1 + mlp2
             lv, Bc, Mc, kc = a[0], a[10], a[11], a[13]
@@ -570,7 +578,7 @@ def _profile_families(reg, steps=3):
         flops[name] = flops.get(name, 0.0) + fl / steps
         issued[name] = issued.get(name, 0.0) + fli / steps
     fam = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
-    layer_names = [n for n in fam if n.startswith("hrn_layer") or n in ("hrn_level_fused", "hrn_level_ws", "hrn_chain_tc", "hrn_chain_wide")]
+    layer_names = [n for n in fam if n.startswith("hrn_layer") or n in ("hrn_level_fused", "hrn_level_ws", "hrn_chain_tc", "hrn_chain_wide", "hrn_chain_wide_head")]
     layer_ms = sum(fam[n] for n in layer_names)
     layer_fl = sum(flops[n] for n in layer_names)
     layer_issued = sum(issued[n] for n in layer_names)

@@ -183,6 +183,13 @@ int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank_bytes, 
                    int chunks0, int kseg, const float* Zb, const float* Zg, int ldz, float* G, float* a, long long rows,
                    int prec, void* stream);
 
+/* Per-keypoint confidence head of CoarseReg (512 -> 512 -> 512 -> 1, sigmoid; models/HRegNet/layers.py:391-394) as ONE
+ * launch of the same 2-CTA-cluster kernel: Y[r] = act(column 0 of the third layer + bias).  W / bias as for hrn_chain_wide
+ * (engine_tc.pack_chain_wide) with the last layer zero-padded to n3 = 64 columns; n1, n2 multiples of 64, <= 512;
+ * rows % 128 == 0. */
+int hrn_chain_wide_head(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2,
+                        int n3, int chunks0, int act, float* Y, long long rows, int prec, void* stream);
+
 /* Level 1 of HierFeatureExtraction (models/HRegNet/models.py:27-28: detector_1 + desc_extractor_1; in_channels 0,
  * k = 64, widths 32/32/64, mlp 192->32->64) as ONE persistent tcgen05 kernel: grouping (layers.py:9-27), the two conv
  * stacks, attention / keypoints / attentive feature (layers.py:150-159) and the descriptor head (layers.py:200-209)

@@ -50,6 +50,7 @@ SIGNATURES = {
                      c_int, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_vp],
     "hrn_chain_wide": [ctypes.POINTER(Rows), c_vp, c_ll, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp,
                        c_ll, c_int, c_vp],
+    "hrn_chain_wide_head": [ctypes.POINTER(Rows), c_vp, c_ll, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp],
     "hrn_group_attention": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp],
     "hrn_group_weighted_sum": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     "hrn_group_attend": [c_vp, c_int, c_int, c_ll, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp],

@@ -61,6 +61,10 @@ struct WideArgs {
     const float* Zb;             // [rows / group, ldz]: row r takes Zb[r / group]
     const float* Zg;             // [src rows, ldz]:     row r takes Zg[b * src_rows_per_batch + gather_idx[r]]
     int ldz, zs;                 // leading dimension (floats), Z ring stages
+    // head mode (per-keypoint confidence heads, layers.py:391-394): no attention tail, Yh[r] = act(column 0 of the last
+    // layer + its bias); the last layer is zero-padded to 64 columns by the caller
+    float* Yh;
+    int head_act;
 #ifdef HRN_WIDE_DEBUG
     float* dbg;                  // [2 layers][rows][512] pre-activations of the hidden layers as the epilogue sees them
 #endif
@@ -266,6 +270,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
             const uint32_t acc = tmem + lane_base + b * WW_ACC;
             const float* b3 = sBias + A.nh[0] + A.nh[1];
             const int cout = A.nh[2];
+            if (A.Yh) {                                       // head mode: one output per row, from rank 0's first column
+                if (rank == 0 && eg == 0) {
+                    uint32_t v[32];
+                    tmem_ld32(acc, v);
+                    A.Yh[r] = act_fn(__uint_as_float(v[0]) + b3[0], A.head_act);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_fin[b]));
+                continue;
+            }
             const int pos = lane % KSEG;
             const long long grp = r / KSEG;
             constexpr int PER = 32 / KSEG;
@@ -667,10 +682,10 @@ cudaError_t launch_wide_one(const WideArgs& A, int smem, int budget, cudaStream_
 // order (engine_tc.pack_chain_wide: the K order of layers 2 / 3 interleaves 32-column blocks of the two halves);
 // bias: per half b1 | b2 | b3; n1..n3 = full widths (multiples of 64, <= 512); kseg = rows per group (8).
 // Outputs: G [rows / kseg, n3] attentive feature, a [rows] attention weights (layers.py:384-390).  rows % 128 == 0.
-HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2,
+static int chain_wide_impl(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2,
                            int n3, int chunks0, int kseg, const float* Zb, const float* Zg, int ldz, float* G, float* a,
-                           long long rows, int prec, void* stream) {
-    if (!in || !W || !bias || !G || rows < 0 || in->n_seg < 1 || in->n_seg > 4 || w_rank_bytes <= 0) return HRN_ERR_BAD_ARG;
+                           float* Yh, int head_act, long long rows, int prec, void* stream) {
+    if (!in || !W || !bias || (!G && !Yh) || rows < 0 || in->n_seg < 1 || in->n_seg > 4 || w_rank_bytes <= 0) return HRN_ERR_BAD_ARG;
     if (prec != 1 && prec != 3) return HRN_ERR_BAD_ARG;
     const int nn[3] = {n1, n2, n3};
     for (int l = 0; l < 3; ++l) if (nn[l] % 64 || nn[l] > 512 || nn[l] < 64) return HRN_ERR_UNSUPPORTED;
@@ -697,6 +712,7 @@ HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank
     for (int l = 0; l < 3; ++l) { A.nh[l] = nn[l] / 2; if (A.nh[l] > maxh) maxh = A.nh[l]; }
     A.chunks0 = chunks0;
     A.Zb = Zb; A.Zg = Zg; A.ldz = ldz;
+    A.Yh = Yh; A.head_act = head_act;
 #ifdef HRN_WIDE_DEBUG
     A.dbg = g_wide_dbg;
 #endif
@@ -746,3 +762,19 @@ HRN_API int hrn_chain_wide_set_debug(float* p) { g_wide_dbg = p; return 0; }
 #ifdef HRN_WIDE_PROF
 HRN_API int hrn_chain_wide_prof(long long* host8) { return (int)cudaMemcpyFromSymbol(host8, g_wide_prof, 8 * sizeof(long long)); }
 #endif
+
+HRN_API int hrn_chain_wide(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1, int n2,
+                           int n3, int chunks0, int kseg, const float* Zb, const float* Zg, int ldz, float* G, float* a,
+                           long long rows, int prec, void* stream) {
+    if (!G) return HRN_ERR_BAD_ARG;
+    return chain_wide_impl(in, W, w_rank_bytes, bias, n1, n2, n3, chunks0, kseg, Zb, Zg, ldz, G, a, nullptr, 0, rows, prec, stream);
+}
+
+// Per-keypoint head of up to 512-wide layers (CoarseReg's confidence head 512 -> 512 -> 512 -> 1, layers.py:391-394) on
+// the same 2-CTA-cluster kernel: Y[r] = act(column 0 of the third layer).  n3 = the last layer zero-padded to 64 columns.
+HRN_API int hrn_chain_wide_head(const hrn_rows_t* in, const void* W, long long w_rank_bytes, const float* bias, int n1,
+                                int n2, int n3, int chunks0, int act, float* Y, long long rows, int prec, void* stream) {
+    if (!Y) return HRN_ERR_BAD_ARG;
+    return chain_wide_impl(in, W, w_rank_bytes, bias, n1, n2, n3, chunks0, 8, nullptr, nullptr, 0, nullptr, nullptr, Y, act, rows, prec,
+                           stream);
+}

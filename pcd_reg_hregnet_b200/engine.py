@@ -578,7 +578,11 @@ def _coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k, both, want_dis
         # conv stack + attention on a 2-CTA cluster per tile: the 512-wide activations never reach HBM (csrc/chain_wide.cu)
         af, a = engine_tc.chain_wide(v, P["convs_1"], k)
         cor = on_side_stream(lambda: group_weighted_sum(a, dxyz.view(B * N2, 3), k, idx=idx, groups_per_batch=N1, N=N2), a)
-        w = stack(RowsView(B * N1).add(af), P["mlp"], last_act=ACT_SIGMOID).view(B, N1)
+        hv = RowsView(B * N1).add(af)
+        if engine_tc.chain_wide_head_supported(hv, P["mlp"]):
+            w = engine_tc.chain_wide_head(hv, P["mlp"], ACT_SIGMOID).view(B, N1)      # 512 -> 512 -> 512 -> 1 in one launch
+        else:
+            w = stack(hv, P["mlp"], last_act=ACT_SIGMOID).view(B, N1)
         cor = cor().view(B, N1, 3)
     else:
         F = stack(v, P["convs_1"])

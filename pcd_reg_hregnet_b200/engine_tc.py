@@ -445,6 +445,40 @@ def _view_ptr(t):
     return t.data_ptr()
 
 
+def chain_wide_head_supported(view, layers):
+    """Three layers, the two hidden ones ReLU and multiples of 64 up to 512 wide (at least one > 256), one output column."""
+    from ._lib import ACT_RELU
+    if len(layers) != 3 or view.rows % 128 != 0 or len(view.segs) != 1:
+        return False
+    (W1, _, a1), (W2, _, a2), (W3, _, _) = layers
+    if a1 != ACT_RELU or a2 != ACT_RELU or W3.shape[0] != 1:
+        return False
+    if W1.shape[0] % 64 or W2.shape[0] % 64 or max(W1.shape[0], W2.shape[0]) > 512 or max(W1.shape[0], W2.shape[0]) <= 256:
+        return False
+    mat, mode, ch, col0, scale = view.segs[0]
+    return not (ch % 4 or col0 % 4 or mat.stride(0) % 4 or mat.data_ptr() % 16 or scale is not None)
+
+
+def chain_wide_head(view, layers, act, prec=None):
+    """Per-keypoint head c -> c -> c -> 1 (layers.py:391-394) in ONE launch of the cluster kernel: returns act(y) [rows]."""
+    prec = engine.mma_prec() if prec is None else prec
+    W3, b3, a3 = layers[2]
+    key = (W3.data_ptr(), W3._version, "head64")
+    padded = _wide_cache.get(key)
+    if padded is None:                                     # last layer zero-padded to 64 output columns
+        Wp = torch.zeros(64, W3.shape[1], dtype=torch.float32, device=W3.device)
+        Wp[:1] = W3
+        bp = torch.zeros(64, dtype=torch.float32, device=W3.device)
+        bp[:1] = b3
+        padded = _remember(_wide_cache, key, W3, (Wp, bp))
+    lay = [layers[0], layers[1], (padded[0], padded[1], a3)]
+    Wpack, rank_bytes, bias, chunks0, widths = pack_chain_wide(lay, [s[2] for s in view.segs], prec)
+    Y = torch.empty(view.rows, dtype=torch.float32, device=bias.device)
+    engine.call("hrn_chain_wide_head", ctypes.byref(view.c), engine.ptr(Wpack), rank_bytes, engine.ptr(bias), widths[0],
+                widths[1], widths[2], chunks0, act, engine.ptr(Y), view.rows, prec, engine.stream())
+    return Y
+
+
 def chain_wide(view, layers, kseg=8, prec=None, split_first=True):
     """convs + attention tail on the virtual rows: returns (AF [rows / kseg, n3], a [rows])  (layers.py:364-390)."""
     prec = engine.mma_prec() if prec is None else prec

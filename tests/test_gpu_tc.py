@@ -297,3 +297,28 @@ def test_chain_wide_cluster_kernel(B, M, dims, prec, tol, split):
     print(f"chain_wide B={B} M={M} dims={dims} prec={prec} split={split}: a {e_a:.2e}  AF {e_g:.2e}")
     assert e_a < tol and e_g < tol, (e_a, e_g)
     assert torch.equal(G, G2) and torch.equal(a, a2)
+
+
+@pytest.mark.parametrize("rows,c", [(8192, 512), (128, 512), (1024 + 128, 384)])
+def test_chain_wide_head(rows, c):
+    """Per-keypoint confidence head c -> c -> c -> 1 + sigmoid (reference layers.py:391-394) as one launch of the cluster
+    kernel, against fp64."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    g = torch.Generator().manual_seed(rows + c)
+    X = torch.randn(rows, c, generator=g).to(DEV)
+    layers, Y = [], X.double()
+    for i, (n, act) in enumerate([(c, ACT_RELU), (c, ACT_RELU), (1, ACT_NONE)]):
+        W = (torch.randn(n, c, generator=g) / c ** 0.5).to(DEV)
+        b = (torch.randn(n, generator=g) * 0.1).to(DEV)
+        layers.append((W, b, act))
+        Y = Y @ W.double().t() + b.double()
+        if act == ACT_RELU:
+            Y = torch.relu(Y)
+    want = torch.sigmoid(Y)[:, 0]
+    v = RowsView(rows).add(X)
+    assert engine_tc.chain_wide_head_supported(v, layers)
+    got = engine_tc.chain_wide_head(v, layers, ACT_SIGMOID)
+    torch.cuda.synchronize()
+    e = float((got.double() - want).abs().max())
+    print(f"chain_wide_head rows={rows} c={c}: {e:.2e}")
+    assert got.shape == (rows,) and e < 1e-5, e
