@@ -100,6 +100,17 @@ constexpr int CW_ZSTAGE_BYTES = CW_ZG_BYTES + (CTM / 8) * 32 * 4;     // + up to
 constexpr int CW_TP = 36;
 constexpr int CW_TILE_BYTES = CW_EPI_WARPS * 32 * CW_TP * 4;
 
+// -DHRN_CHAIN_PROF: cycles the MMA thread of CTA 0 spends waiting for [0] input stages, [1] hidden-layer blocks, [2] weights,
+// [3] a free accumulator, [4] total; read back with hrn_chain_prof (tools/chain_probe.py)
+#ifdef HRN_CHAIN_PROF
+__device__ long long g_chain_prof[8];
+#define CPROF_BEGIN() const long long cp_t0 = clock64()
+#define CPROF_END(i) cp[i] += clock64() - cp_t0
+#else
+#define CPROF_BEGIN() do { } while (0)
+#define CPROF_END(i) do { } while (0)
+#endif
+
 struct ChainWsArgs {
     ChainArgs c;
     int n_tiles;
@@ -516,15 +527,25 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
             int gs = 0, hs = 0; uint32_t gpar = 0, hpar = 0;  // operand ring positions
             int L = 0, ti = 0;
             uint32_t fin_pending = 0, finph = 0;              // per accumulator: last result not yet drained by the epilogue / phase
+#ifdef HRN_CHAIN_PROF
+            long long cp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const long long cp_start = clock64();
+#endif
             auto claim = [&](int b) {                         // before the first MMA of a layer into accumulator b
                 if (fin_pending >> b & 1) {
+                    CPROF_BEGIN();
                     mbar_wait(smem_u32(&s_fin[b]), (finph >> b) & 1);
+                    CPROF_END(3);
                     finph ^= 1u << b; fin_pending &= ~(1u << b);
                 }
             };
             // one K=16 piece: A = chunks [2p, 2p+2) of the operand stage whose hi plane starts at a16 (16-byte units)
             auto piece_mma = [&](uint32_t a16, uint64_t w_desc0, uint32_t wlo16, uint32_t idesc, uint32_t d, uint32_t accumulate) {
-                mbar_wait(wfull0 + 8 * ws, wpar);
+                {
+                    CPROF_BEGIN();
+                    mbar_wait(wfull0 + 8 * ws, wpar);
+                    CPROF_END(2);
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t w16 = (ring_a >> 4) + ws * slot16;
                 const uint64_t ah = a_desc0 | a16, al = a_desc0 | (a16 + LO16);
@@ -549,7 +570,11 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     const uint32_t wlo16 = 2 * N;                                                   // lo plane: + 2 * N * 16 B
                     int left = (int)pieces[0];
                     for (int s = 0; s < n_st0; ++s, left -= 2) {
-                        mbar_wait(smem_u32(&s_gfull[gs]), gpar);
+                        {
+                            CPROF_BEGIN();
+                            mbar_wait(smem_u32(&s_gfull[gs]), gpar);
+                            CPROF_END(0);
+                        }
                         const uint32_t a16 = g_a + gs * ST16;
                         piece_mma(a16, w_desc0, wlo16, idesc, d, s > 0 ? 1u : 0u);
                         if (left > 1) piece_mma(a16 + P16, w_desc0, wlo16, idesc, d, 1u);
@@ -570,7 +595,11 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     const uint32_t wlo16 = 2 * N;
                     int left = A.n[l - 1] / 16;
                     for (int j = 0; left > 0; ++j, left -= 2) {
-                        mbar_wait(smem_u32(&s_hfull[hs]), hpar);
+                        {
+                            CPROF_BEGIN();
+                            mbar_wait(smem_u32(&s_hfull[hs]), hpar);
+                            CPROF_END(1);
+                        }
                         const uint32_t a16 = h_a + hs * ST16;
                         piece_mma(a16, w_desc0, wlo16, idesc, d, j > 0 ? 1u : 0u);
                         if (left > 1) piece_mma(a16 + P16, w_desc0, wlo16, idesc, d, 1u);
@@ -580,6 +609,12 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                     umma_commit(smem_u32(&s_accf[b]));
                 }
             }
+#ifdef HRN_CHAIN_PROF
+            if (blockIdx.x == 0) {
+                cp[4] = clock64() - cp_start;
+                for (int i = 0; i < 8; ++i) g_chain_prof[i] = cp[i];
+            }
+#endif
         }
     } else {
         // ================= weight stream ==========================================================================
@@ -713,3 +748,7 @@ HRN_API int hrn_chain_tc(const hrn_rows_t* in, const void* W, const float* bias,
         return HRN_OK;
     }
 }
+
+#ifdef HRN_CHAIN_PROF
+HRN_API int hrn_chain_prof(long long* host8) { return (int)cudaMemcpyFromSymbol(host8, g_chain_prof, 8 * sizeof(long long)); }
+#endif
