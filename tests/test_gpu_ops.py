@@ -46,6 +46,8 @@ def _clouds(kind, B, N, seed):
     ("lattice", 3, 16384, 600), ("lattice", 2, 9000, 400), ("dup", 3, 16384, 1024), ("dup", 2, 12000, 777),
     ("far", 2, 16384, 512), ("uniform", 2, 8193, 300), ("lidar", 3, 16383, 1024), ("lidar", 2, 12345, 2000),
     ("lidar", 64, 16384, 1024),
+    # the few-warps-per-cloud kernels of the small power-of-two clouds (256: one warp, 512: two, 1024: four)
+    ("lattice", 5, 256, 256), ("uniform", 3, 256, 100), ("lattice", 4, 1024, 700), ("dup", 3, 512, 300),
 ])
 def test_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=N + M)
@@ -58,7 +60,7 @@ def test_fps_bit_exact(kind, B, N, M):
 @pytest.mark.parametrize("kind,B,N,M", [
     ("uniform", 4, 1024, 512), ("lidar", 2, 1024, 512), ("lattice", 3, 512, 256), ("uniform", 2, 512, 256),
     ("dup", 2, 16384, 400), ("uniform", 1, 700, 128), ("lattice", 1, 24000, 100), ("uniform", 64, 1024, 512),
-    ("uniform", 80, 9000, 100), ("uniform", 3, 50000, 50),
+    ("uniform", 80, 9000, 100), ("uniform", 3, 50000, 50), ("lattice", 5, 256, 200), ("dup", 4, 1024, 1000),
 ])
 def test_weighted_fps_bit_exact(kind, B, N, M):
     xyz = _clouds(kind, B, N, seed=7 * N + M)

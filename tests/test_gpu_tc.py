@@ -322,3 +322,45 @@ def test_chain_wide_head(rows, c):
     e = float((got.double() - want).abs().max())
     print(f"chain_wide_head rows={rows} c={c}: {e:.2e}")
     assert got.shape == (rows,) and e < 1e-5, e
+
+
+@pytest.mark.parametrize("dims", [[256, 256, 256], [128, 128, 128]])
+def test_chain_first_layer_split_equals_unsplit(dims):
+    """FineReg-shaped conv stack through the single-CTA chain kernel with and without the first-layer split (group-constant and
+    gathered input segments applied once per point, added as fp32 rows): both within 1e-4 of fp64, and of each other."""
+    from pcd_reg_hregnet_b200 import engine_tc
+    kseg, B, M, N, C = 8, 3, 256, 200, dims[0] // 2
+    g = torch.Generator().manual_seed(dims[0])
+    rows = B * M * kseg
+    misc = torch.randn(rows, 12, generator=g).to(DEV)
+    src = torch.randn(B * M, C, generator=g).to(DEV)
+    dst = torch.randn(B * N, C, generator=g).to(DEV)
+    idx = torch.randint(0, N, (B, M, kseg), generator=g).int().to(DEV)
+
+    def view():
+        v = RowsView(rows, group=kseg, gather_idx=idx, rows_per_batch=M * kseg, src_rows_per_batch=N)
+        return v.add(misc).add(src, SEG_BROADCAST).add(dst, SEG_GATHER)
+    r = torch.arange(rows, device=DEV)
+    X = torch.cat([misc, src[r // kseg], dst[(r // (M * kseg)) * N + idx.view(-1).long()]], 1).double()
+    widths = [12 + 2 * C] + dims
+    layers = []
+    for i in range(3):
+        W = (torch.randn(widths[i + 1], widths[i], generator=g) / widths[i] ** 0.5).to(DEV)
+        b = (torch.randn(widths[i + 1], generator=g) * 0.1).to(DEV)
+        layers.append((W, b, ACT_RELU))
+        X = torch.relu(X @ W.double().t() + b.double())
+    Xg = X.view(-1, kseg, dims[2])
+    a_ref = torch.softmax(Xg.max(dim=2)[0], dim=1)
+    af_ref = (a_ref[:, :, None] * Xg).sum(1)
+    out = {}
+    try:
+        for split in (True, False):
+            engine_tc.SPLIT_CHAINS = split
+            _, af, a = engine_tc.chain3(view(), layers, engine_tc.EPI_ATTN, kseg, want_rows=False)
+            torch.cuda.synchronize()
+            out[split] = (af, a)
+            assert float((a.double().view(-1, kseg) - a_ref).abs().max()) < 1e-4
+            assert float((af.double() - af_ref).abs().max()) / float(X.abs().max()) < 1e-4
+    finally:
+        engine_tc.SPLIT_CHAINS = True
+    assert float((out[True][0] - out[False][0]).abs().max()) / float(X.abs().max()) < 1e-4
