@@ -8,6 +8,7 @@ features is a [rows, C] matrix with rows = (cloud, keypoint, neighbour) flattene
 Folded parameters (BatchNorm eval statistics merged into the 1x1 convolutions) come from fold.py.
 """
 import ctypes
+import os
 
 import torch
 
@@ -469,9 +470,26 @@ def fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k=8, want_af=False):
         return _fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k, want_af)
 
 
+_PREFETCH_Z = os.environ.get("HRN_PREFETCH_Z", "1") == "1"
+
+
+def _prefetch_stage(sfeat_cl, dfeat_cl, W1, misc_channels):
+    """Starts the per-point parts of a correspondence stage's first conv layer (column layout of its input:
+    [misc | source features | target features]) beside the stage's neighbour search."""
+    if not (_PREFETCH_Z and _tc() and _FUSED_CHAINS and _SIDE_STREAM and sfeat_cl.is_cuda):
+        return
+    from . import engine_tc
+    C = sfeat_cl.shape[-1]
+    if W1.shape[1] != misc_channels + 2 * C:
+        return
+    engine_tc.prefetch_point_layers(sfeat_cl, W1, [(sfeat_cl.reshape(-1, C), C, 0, misc_channels),
+                                                   (dfeat_cl.reshape(-1, C), C, 0, misc_channels + C)])
+
+
 def _fine_reg(sxyz, sfeat_cl, dxyz, dfeat_cl, ssig, dsig, P, k, want_af):
     B, N1, _ = sxyz.shape
     N2 = dxyz.shape[1]
+    _prefetch_stage(sfeat_cl, dfeat_cl, P["convs_1"][0][0], 12)
     idx, _ = knn_idx(sxyz, dxyz, k)
     misc, _ = group_geometry(sxyz, dxyz, idx, ssig, dsig)
     v = RowsView(B * N1 * k, group=k, gather_idx=idx, rows_per_batch=N1 * k, src_rows_per_batch=N2)
@@ -538,6 +556,7 @@ def coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k=8, both=None, wa
 def _coarse_reg(sxyz, sdesc_cl, dxyz, ddesc_cl, ssig, dsig, P, k, both, want_dists):
     B, N1, C = sdesc_cl.shape
     N2 = dxyz.shape[1]
+    _prefetch_stage(sdesc_cl, ddesc_cl, P["convs_1"][0][0], 16)
 
     def descriptor_branch():
         i, _ = knn_idx(sdesc_cl, ddesc_cl, k)                      # 256-d descriptor space (layers.py:278)

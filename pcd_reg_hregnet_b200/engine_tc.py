@@ -337,6 +337,7 @@ _wide_cache = {}
 # launches run (their MACs are part of that first layer, not extra algorithmic work)
 SPLIT_K = 0
 IN_SPLIT = False
+_zprefetch = {}          # (points data_ptr, rows, channels, col0, W1 data_ptr, W1 version, W1 column) -> (Z, side stream)
 SPLIT_CHAINS = True      # apply the first-layer split in the single-CTA chain kernel too (FineReg convs_1, CoarseReg convs_2)
 
 
@@ -416,25 +417,60 @@ def _split_first_layer(view, layers):
         else:
             pts[mode] = (mat, ch, col0, c0)
         c0 += ch
-    global SPLIT_K, IN_SPLIT
+    global SPLIT_K
     Z = {}
-    SPLIT_K, IN_SPLIT = sum(p[1] for p in pts.values()), True
-    try:
-        for mode, (mat, ch, col0, cs) in pts.items():
-            key = (W1.data_ptr(), W1._version, cs, ch)
-            Wc = _wide_cache.get(key)
-            if Wc is None:
-                Wc = _remember(_wide_cache, key, W1, W1[:, cs:cs + ch].contiguous())
-            src = engine.RowsView(mat.shape[0]).add(mat, SEG_DIRECT, channels=ch, col0=col0)
-            Z[mode] = engine.layer(src, Wc, None, ACT_NONE)                  # [points, n1] fp32, once per point
-    finally:
-        IN_SPLIT = False
+    SPLIT_K = sum(p[1] for p in pts.values())
+    for mode, (mat, ch, col0, cs) in pts.items():
+        hit = _zprefetch.pop(_zkey(mat, ch, col0, W1, cs), None)
+        if hit is not None:                      # launched ahead on a side stream (prefetch_point_layers): join it
+            torch.cuda.current_stream(mat.device).wait_stream(hit[1])
+            hit[0].record_stream(torch.cuda.current_stream(mat.device))
+            Z[mode] = hit[0]
+        else:
+            Z[mode] = _point_layer(mat, ch, col0, W1, cs)
     Zb, Zg = Z.get(SEG_BROADCAST), Z[SEG_GATHER]
     key = (W1.data_ptr(), W1._version, "direct")
     Wd = _wide_cache.get(key)
     if Wd is None:
         Wd = _remember(_wide_cache, key, W1, torch.cat(cols, 1).contiguous())
     return reduced, [(Wd, b1, act1)] + list(layers[1:]), Zb, Zg
+
+
+def _zkey(mat, ch, col0, W1, cs):
+    return (mat.data_ptr(), mat.shape[0], ch, col0, W1.data_ptr(), W1._version, cs)
+
+
+def _point_layer(mat, ch, col0, W1, cs):
+    """Z [points, n1] = points[:, col0:col0+ch] . W1[:, cs:cs+ch]^T  (fp32 out, no bias, no activation): the per-point part
+    of a chain's first layer."""
+    from ._lib import ACT_NONE, SEG_DIRECT
+    global IN_SPLIT
+    key = (W1.data_ptr(), W1._version, cs, ch)
+    Wc = _wide_cache.get(key)
+    if Wc is None:
+        Wc = _remember(_wide_cache, key, W1, W1[:, cs:cs + ch].contiguous())
+    src = engine.RowsView(mat.shape[0]).add(mat, SEG_DIRECT, channels=ch, col0=col0)
+    IN_SPLIT = True
+    try:
+        return engine.layer(src, Wc, None, ACT_NONE)
+    finally:
+        IN_SPLIT = False
+
+
+def prefetch_point_layers(like, W1, specs):
+    """Launches the per-point first-layer parts `specs` = [(points [P, C], channels, col0, W1 column), ...] on the API side
+    stream, forked from the current stream NOW, and parks the results for the chain launch that will ask for them
+    (_split_first_layer joins the stream).  They depend on the features only: a correspondence stage starts them before its
+    latency-bound neighbour search / geometry kernels."""
+    if not SPLIT_CHAINS or W1.shape[0] % 32 or not like.is_cuda:
+        return
+    if len(_zprefetch) > 16:                     # results nobody asked for (a stage that took another path)
+        _zprefetch.clear()
+    side = engine._api_stream(like.device)
+    side.wait_stream(torch.cuda.current_stream(like.device))
+    with torch.cuda.stream(side):
+        for mat, ch, col0, cs in specs:
+            _zprefetch[_zkey(mat, ch, col0, W1, cs)] = (_point_layer(mat, ch, col0, W1, cs), side)
 
 
 def _view_ptr(t):
