@@ -61,7 +61,7 @@ int hrn_gather_points_grad(const float* grad_out, const int32_t* idx, float* gra
 int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int B, int M, int N, int D, int K, float* dists,
             int64_t* idx64, int32_t* idx32, float* nn, float* q_out, void* stream);
 
-/* Same contract and bit-identical results as hrn_knn for D = 3, 1024 <= N <= 32768, with spatial culling: the
+/* Same contract and bit-identical results as hrn_knn for D = 3, 128 <= N <= 32768 (clouds below 1024 points are padded to 1024 sorted positions), with spatial culling: the
  * cloud is Morton-sorted once per call (scratch_pts [B*N2] float4, scratch_boxes [B*(N2/32)*6] floats, N2 = next
  * power of two >= N, caller-allocated) and each query opens only the 32-point boxes whose fp32 lower bound can still
  * beat its current K-th distance. */

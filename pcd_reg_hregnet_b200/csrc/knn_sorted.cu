@@ -1,4 +1,4 @@
-// Exact kNN in 3-D with spatial culling, for clouds of 1024 .. 32768 points (level 1: 1024 queries x 16384 points, K = 64).
+// Exact kNN in 3-D with spatial culling, for clouds of 128 .. 32768 points (level 1: 1024 queries x 16384 points, K = 64).
 //
 // Same contract as knn3_kernel (knn.cu): dist = fma(dz,dz, fma(dy,dy, dx*dx)), K smallest by (dist, index) -- the
 // result is bit-identical to the brute-force kernel, only the work changes:
@@ -326,7 +326,7 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
 }  // namespace knn_sorted
 
 // Scratch the caller provides for the culled search: pts [B*N2] float4 and boxes [B*(N2/32)*6] floats, N2 = next
-// power of two >= N.  Returns HRN_ERR_UNSUPPORTED outside 1024 <= N <= 32768 (callers then use hrn_knn).
+// power of two >= N.  Returns HRN_ERR_UNSUPPORTED outside 128 <= N <= 32768 (callers then use hrn_knn).
 // The two halves are also exported on their own: the sort depends on the reference cloud only, so a caller can run it
 // on a second stream while the queries are still being chosen (FPS).
 static int knn3_pow2(int N) {
@@ -338,7 +338,7 @@ static int knn3_pow2(int N) {
 HRN_API int hrn_knn3_sort(const float* p2, int B, int N, void* scratch_pts, float* scratch_boxes, void* stream) {
     using namespace knn_sorted;
     if (!p2 || !scratch_pts || !scratch_boxes || B < 0 || N <= 0) return HRN_ERR_BAD_ARG;
-    if (N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
+    if (N < 128 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0) return HRN_OK;
     const int N2 = knn3_pow2(N);
     static hrn_once_per_device attr_set;
@@ -365,7 +365,7 @@ HRN_API int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* 
                             int32_t* idx32, float* nn, float* q_out, void* stream) {
     using namespace knn_sorted;
     if (!p2 || (!p1 && !q_idx) || !sorted_pts || !sorted_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
-    if (K > N || K > 64 || N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
+    if (K > N || K > 64 || N < 128 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0 || M == 0) return HRN_OK;
     const int N2 = knn3_pow2(N);
     cudaStream_t st = (cudaStream_t)stream;
@@ -394,7 +394,7 @@ HRN_API int hrn_knn3_sorted(const float* p1, const int32_t* q_idx, const float* 
                             void* scratch_pts, float* scratch_boxes, float* dists, int64_t* idx64, int32_t* idx32,
                             float* nn, float* q_out, void* stream) {
     if (!p2 || (!p1 && !q_idx) || !scratch_pts || !scratch_boxes || B < 0 || M < 0 || N <= 0 || K <= 0) return HRN_ERR_BAD_ARG;
-    if (K > N || K > 64 || N < 1024 || N > 32768) return HRN_ERR_UNSUPPORTED;
+    if (K > N || K > 64 || N < 128 || N > 32768) return HRN_ERR_UNSUPPORTED;
     if (B == 0 || M == 0) return HRN_OK;
     const int rc = hrn_knn3_sort(p2, B, N, scratch_pts, scratch_boxes, stream);
     if (rc != HRN_OK) return rc;

@@ -91,7 +91,7 @@ def _knn_forward(p1, p2, K):
     N = p2.shape[1]
     dists = torch.empty(B, M, K, dtype=torch.float32, device=p1.device)
     idx = torch.empty(B, M, K, dtype=torch.int64, device=p1.device)
-    if D == 3 and 1024 <= N <= 32768:      # spatially culled exact search (same results, see csrc/knn_sorted.cu)
+    if D == 3 and 256 <= N <= 32768:       # spatially culled exact search (same results, see csrc/knn_sorted.cu)
         from .engine import knn_scratch
         pts, boxes = knn_scratch(B, N, p1.device)
         call("hrn_knn3_sorted", ptr(p1), None, ptr(p2), B, M, N, K, ptr(pts), ptr(boxes), ptr(dists), ptr(idx), None, None,
