@@ -27,9 +27,13 @@
 // Epilogue instruction diet (the kernel is bound by the SIMT work between the MMAs, not by the tensor pipe):
 //   * ReLU is folded into the operand conversions: hi = cvt.rz.relu.bf16x2(x), lo = cvt.rn.relu.bf16x2(x - hi) -- with
 //     a TRUNCATED hi the residual of a non-negative x is non-negative, and for x < 0 both halves clamp to 0;
-//   * the biases of the merged first layer ride in the MMA: the grouped input has 12 spare K columns, one of them is
-//     the constant 1 and its weight column is the bias;
+//   * the biases ride in the MMAs: the grouped input of the merged first layer has 12 spare K columns, one of them is the
+//     constant 1 and its weight column is the bias; the later layers get one extra K=16 piece (ones x [b_hi, b_lo]);
 //   * max_k relu(x) = relu(max_k x): the column maxima are taken on the pre-activations.
+// Biases of d2 d3 x2 x3 m2 as one more K=16 MMA piece per layer (a resident block of ones times the bias split into bf16
+// hi + lo) instead of additions in the drains: level 1 775 -> 676 us (the kernel is bound by its SIMT work, the tensor pipe
+// has room).  Comment the define out for the additive form.
+#define L1_BIAS_MMA 1
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
@@ -59,7 +63,18 @@ struct LevelCfg {
     // different banks
     static constexpr int WA_HALF = CO / 2 * CMID + 16;
     static constexpr int WA_BYTES = 2 * WA_HALF * 4;
-    static constexpr int PACK_BYTES = W_BYTES + WA_BYTES;
+#ifdef L1_BIAS_MMA
+    // biases of d2 d3 x2 x3 m2 as one more K=16 MMA piece per layer: A = a resident block of ones (columns 0 and 1), B = the
+    // bias split into bf16 hi (K column 0) and lo (K column 1) -- the drains then add nothing
+    __host__ __device__ static constexpr int bp_off(int l) {          // byte offset of layer l's bias piece behind the Wa halves
+        return l == 1 ? 0 : l == 2 ? 32 * C2 : l == 3 ? 32 * (C2 + CO) : l == 4 ? 32 * (2 * C2 + CO) : 32 * (2 * C2 + 2 * CO);
+    }
+    static constexpr int BP_BYTES = 32 * (2 * C2 + 2 * CO + CD);
+    static constexpr int ONES_BYTES = 2 * TMR * 16;
+#else
+    static constexpr int BP_BYTES = 0, ONES_BYTES = 0;
+#endif
+    static constexpr int PACK_BYTES = W_BYTES + WA_BYTES + BP_BYTES;
     // biases (floats): d1,d2,d3,x1,x2,x3,m1,m2 (d1 / x1 ride in the first MMA and are not read here)
     static constexpr int B_D1 = 0, B_D2 = B_D1 + C1, B_D3 = B_D2 + C2, B_X1 = B_D3 + CO, B_X2 = B_X1 + C1,
                          B_X3 = B_X2 + C2, B_M1 = B_X3 + CO, B_M2 = B_M1 + CMID, B_COUNT = B_M2 + CD;
@@ -81,7 +96,7 @@ struct LevelCfg {
     // ONE resident copy of the weights (4 tiles in flight per SM)
     static constexpr int NG = 4;
     static constexpr int GRP_SMEM = OP_BYTES + 2 * 4 * CW * 4 + KPT * CMID * 4;
-    static constexpr int SMEM_NG = PACK_BYTES + B_COUNT * 4 + NG * GRP_SMEM + 256;
+    static constexpr int SMEM_NG = PACK_BYTES + ONES_BYTES + B_COUNT * 4 + NG * GRP_SMEM + 256;
     static constexpr int T_COLS_NG = NG * T_USED <= 256 ? 256 : 512;
     static_assert(NG * T_USED <= 512, "TMEM (groups)");
     static_assert(KNBR == 64 && CMID == 32 && CO % 8 == 0, "the per-keypoint mat-vec maps 64 threads onto 32 outputs x 2 halves");
@@ -95,7 +110,7 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {
 
 // one thread: D[tmem_col] (+)= A(smem, K, hi/lo planes) x W(smem, [N x K], hi/lo planes)^T, bf16x3
 __device__ __forceinline__ void issue_layer(uint32_t a_hi, uint32_t a_lo, int K, uint32_t w_hi, int N, uint32_t tmem_d,
-                                            bool accumulate) {
+                                            bool accumulate, uint32_t ones = 0, uint32_t bias_piece = 0) {
     const uint32_t idesc = make_idesc(N);
     const uint32_t w_lbo = (uint32_t)N * 16;
     const uint64_t a_fix = umma_desc_fixed(TMR * 16, 128), w_fix = umma_desc_fixed(w_lbo, 128);
@@ -109,6 +124,7 @@ __device__ __forceinline__ void issue_layer(uint32_t a_hi, uint32_t a_lo, int K,
         umma_bf16(tmem_d, a_fix | ah, w_fix | wl, idesc, 1u);
         ah += a_step; al += a_step; wh += w_step; wl += w_step;
     }
+    if (bias_piece) umma_bf16(tmem_d, a_fix | (ones >> 4), w_fix | (bias_piece >> 4), idesc, 1u);      // + 1 * b_hi + 1 * b_lo
 }
 
 // f[e] = acc[e] (+ bias[e]) for 32 consecutive columns, NO activation; the biases come from shared memory as 8 x 16-byte
@@ -188,8 +204,9 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     float (*s_red)[8] = s_red_all[grp_id];
     uint8_t* sW = smem;
     const float* sWa = reinterpret_cast<const float*>(smem + Cfg::W_BYTES);
-    float* sB = reinterpret_cast<float*>(smem + Cfg::PACK_BYTES);
-    uint8_t* sOp = smem + Cfg::PACK_BYTES + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
+    uint8_t* sOnes = smem + Cfg::PACK_BYTES;
+    float* sB = reinterpret_cast<float*>(smem + Cfg::PACK_BYTES + Cfg::ONES_BYTES);
+    uint8_t* sOp = smem + Cfg::PACK_BYTES + Cfg::ONES_BYTES + Cfg::B_COUNT * 4 + grp_id * Cfg::GRP_SMEM;
     float* sCol = reinterpret_cast<float*>(sOp + Cfg::OP_BYTES);          // [4][CW] per-warp column partials
     float* sCol2 = sCol + 4 * CW;
     float* sKpb = sCol2 + 4 * CW;                                         // [KPT][CMID] per-keypoint bias of mlp1
@@ -212,6 +229,10 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
     for (int i = cta_tid; i < Cfg::PACK_BYTES / 16; i += TMR * NG)
         reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(Wpack) + i);
     for (int i = cta_tid; i < Cfg::B_COUNT; i += TMR * NG) sB[i] = __ldg(biases + i);
+#ifdef L1_BIAS_MMA
+    for (int i = cta_tid; i < 2 * TMR; i += TMR * NG)             // [2 chunks][128 rows][8 bf16]: columns 0 and 1 of chunk 0 = 1.0
+        reinterpret_cast<uint4*>(sOnes)[i] = i < TMR ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+#endif
     if (cta_tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS_NG) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -234,9 +255,17 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         gsync();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef L1_BIAS_MMA
+            const uint32_t ones = smem_u32(sOnes), bp0 = wbase + Cfg::W_BYTES + Cfg::WA_BYTES;
+            auto bp = [&](int l) -> uint32_t { return (l == 1 || l == 2 || l == 3 || l == 4 || l == 7) ? bp0 + Cfg::bp_off(l) : 0u; };
+            issue_layer(aOp_hi + ch0 * TMR * 16, aOp_lo + ch0 * TMR * 16, Cfg::lk(li), wbase + Cfg::woff(li), Cfg::ln(li), tmem + tcol, acc, ones, bp(li));
+            if (lj >= 0)
+                issue_layer(aOp_hi + ch1 * TMR * 16, aOp_lo + ch1 * TMR * 16, Cfg::lk(lj), wbase + Cfg::woff(lj), Cfg::ln(lj), tmem + tcol1, false, ones, bp(lj));
+#else
             issue_layer(aOp_hi + ch0 * TMR * 16, aOp_lo + ch0 * TMR * 16, Cfg::lk(li), wbase + Cfg::woff(li), Cfg::ln(li), tmem + tcol, acc);
             if (lj >= 0)
                 issue_layer(aOp_hi + ch1 * TMR * 16, aOp_lo + ch1 * TMR * 16, Cfg::lk(lj), wbase + Cfg::woff(lj), Cfg::ln(lj), tmem + tcol1, false);
+#endif
             umma_commit(bar);
         }
     };
@@ -313,8 +342,13 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         issue2(1, 0, Cfg::T_ACC0, false, 3, C1 / 8, Cfg::T_ACC0 + C2);
         wait_layer();
         // ---- third layers d3 | x3 together: E -> its own columns, X1 -> the work region (its inputs are drained by then) ----
+#ifdef L1_BIAS_MMA
+        epi_to_operand(Cfg::T_ACC0, C2, sB, no_t{});
+        epi_to_operand(Cfg::T_ACC0 + C2, C2, sB, no_t{}, C2 / 8);
+#else
         epi_to_operand(Cfg::T_ACC0, C2, sB + Cfg::B_D2, yes_t{});
         epi_to_operand(Cfg::T_ACC0 + C2, C2, sB + Cfg::B_X2, yes_t{}, C2 / 8);
+#endif
         issue2(2, 0, Cfg::T_ACCE, false, 4, C2 / 8, Cfg::T_ACCX);
         wait_layer();
         // ---- attention: a = softmax_k(max_c E), keypoint = sum_k a * nn -------------------------------------
@@ -322,6 +356,12 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
         for (int c0 = 0; c0 < CO; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCE + c0, v);
+#ifdef L1_BIAS_MMA
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                x1 = fmaxf(x1, fmaxf(fmaxf(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                     fmaxf(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]))));
+#else
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_D3 + c0 + 4 * q);
@@ -330,6 +370,7 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
                 f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), f2_pack(b4.z, b4.w)), s2, s3);
                 x1 = fmaxf(x1, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
             }
+#endif
         }
         float gmax = hrn_warp_max(x1);
         if (WPG == 2) {
@@ -353,7 +394,11 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCX + c0, v);
+#ifdef L1_BIAS_MMA
+            bias32<false>(v, sB, f);
+#else
             bias32<true>(v, sB + Cfg::B_X3 + c0, f);
+#endif
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
                 split_store8_relu(f + ch * 8, op_hi + (c0 / 8 + ch) * TMR + tid, op_lo + (c0 / 8 + ch) * TMR + tid);
@@ -386,7 +431,11 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCE + c0, v);
+#ifdef L1_BIAS_MMA
+            bias32<false>(v, sB, f);
+#else
             bias32<true>(v, sB + Cfg::B_D3 + c0, f);
+#endif
             const f32x2_t a2 = f2_pack(a, a);
 #pragma unroll
             for (int e = 0; e < 32; e += 2) f2_unpack(f2_mul(f2_pack(fmaxf(f[e], 0.f), fmaxf(f[e + 1], 0.f)), a2), f[e], f[e + 1]);
@@ -413,7 +462,11 @@ level_fused_kernel(const float* __restrict__ q, const float* __restrict__ xyz, c
             uint32_t v[32];
             float f[32];
             tmem_ld32(tmem + lane_base + Cfg::T_ACCX + c0, v);
+#ifdef L1_BIAS_MMA
+            bias32<false>(v, sB, f);
+#else
             bias32<true>(v, sB + Cfg::B_M2 + c0, f);
+#endif
             const float cm = warp_transpose_reduce<true>(f, lane);
             sCol[warp * CW + c0 + lane] = fmaxf(cm, 0.f);
         }

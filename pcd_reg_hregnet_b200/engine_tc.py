@@ -158,9 +158,18 @@ def pack_level(level, det, desc):
     for h in (0, 1):
         parts.append(Wa[:, c[((c >> 2) & 1) == h]].t().contiguous().view(-1).view(torch.uint8))
         parts.append(pad.view(torch.uint8))
+    from ._lib import lib
+    if lib().hrn_level_pack_bytes(level) > sum(p.numel() for p in parts):
+        # library built with the biases of d2 d3 x2 x3 m2 as MMA pieces: per layer [2 chunks][N][8] bf16 with the bias as
+        # hi (K column 0) + lo (K column 1), multiplied by a resident block of ones
+        for b in (bd2, bd3, bx2, bx3, bm2):
+            piece = torch.zeros(2, b.numel(), 8, dtype=torch.bfloat16, device=b.device)
+            hi = b.to(torch.bfloat16)
+            piece[0, :, 0] = hi
+            piece[0, :, 1] = (b - hi.float()).to(torch.bfloat16)
+            parts.append(piece.view(-1).view(torch.uint8))
     Wpack = torch.cat(parts).contiguous()
     biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()
-    from ._lib import lib
     assert Wpack.numel() == lib().hrn_level_pack_bytes(level) and biases.numel() == lib().hrn_level_bias_count(level)
     return _remember(_level_cache, key, d1, (Wpack, biases, None))
 

@@ -309,7 +309,17 @@ def test_golden_end_to_end_model_variants(which, precision):
         assert rel_err(out["src_dst_feats_2_prime"].cpu(), gd["src_dst_feats_2_prime"]) < 1e-3
         assert float((out["src_dst_weights_2_prime"].cpu() - gd["src_dst_weights_2_prime"]).abs().max()) < 1e-3
         if which == "v4":
-            assert rel_err(out["coord_dist"].cpu(), gd["coord_dist"]) < 1e-3
-            assert float((out["feats_dist"].cpu() - gd["feats_dist"]).abs().max()) < 1e-3
+            ocd, ofd = out["coord_dist"].cpu(), out["feats_dist"].cpu()
+            gcd, gfd = gd["coord_dist"], gd["feats_dist"]
+            if precision != "fp32":
+                # The candidates of a keypoint come in the order of their descriptor-space distances, and two candidates
+                # whose distances differ in the last bits swap places when desc_3 carries the 5e-6 of the bf16x3 mode
+                # (measured on this fixture: 4 of 512 keypoints, same candidate SETS).  Per keypoint the two tensors are
+                # therefore compared as sets: rows sorted by coord_dist, feats_dist carried along.
+                ocd, oix = ocd.sort(-1)
+                gcd, gix = gcd.sort(-1)
+                ofd, gfd = ofd.gather(-1, oix), gfd.gather(-1, gix)
+            assert rel_err(ocd, gcd) < 1e-3
+            assert float((ofd - gfd).abs().max()) < 1e-3
     print(f"model_{which} [{precision}]: {len(ok)}/{B} pairs had identical level-2 keypoint sets")
     assert len(ok) >= MIN_CHECKED.get(precision, 0), (which, precision, len(ok))
