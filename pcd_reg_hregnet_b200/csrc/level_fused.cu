@@ -144,29 +144,6 @@ __device__ __forceinline__ void bias32(const uint32_t (&v)[32], const float* __r
     }
 }
 
-// relu(x) of a pair as bf16 hi / lo with the ReLU folded into the two conversions: hi = rz_bf16(max(x, 0)),
-// lo = rn_bf16(max(x - hi, 0)).  hi is TRUNCATED, so the residual of a non-negative x is non-negative; for x < 0
-// hi = 0 and the residual x clamps to 0.  |relu(x) - hi - lo| <= 2^-16 |x|.
-__device__ __forceinline__ void split_pair_relu(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    uint32_t hb;
-    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(x1), "f"(x0));
-    const unsigned long long hf = ((unsigned long long)(hb & 0xffff0000u) << 32) | (unsigned long long)(hb << 16);
-    unsigned long long xv, rv;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(x0), "f"(x1));
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rv) : "l"(xv), "l"(hf));
-    float r0, r1;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(rv));
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
-    hi = hb;
-}
-__device__ __forceinline__ void split_store8_relu(const float* x, uint4* dst_hi, uint4* dst_lo) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_pair_relu(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
-    *dst_hi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *dst_lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-
 // lane c receives the op-reduction over the 32 lanes of v[c]  (31 shuffles)
 template <bool IS_MAX>
 __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {

@@ -32,6 +32,15 @@
 // other layer starts on its first block.
 // The operand buffer holds the inputs of both stacks side by side (detector: chunks [0,C/8), descriptor: [C/8,2C/8));
 // the E*a drain may only enter the descriptor half when x3 has read it.
+//
+// Drain instruction diet (as in level_fused.cu; the drains and the MMAs of a tile alternate, so every instruction of a drain
+// is on the tile's dependency chain):
+//   * the biases ride in the MMAs: d1 / x1 as the weight column of a constant-1 channel in the K padding of the grouped
+//     input, d2 x2 d3 x3 m2 as ONE extra MMA per layer -- a resident block of ones (K columns 0 and 1) times the bias split
+//     into bf16 hi (K column 0) + lo (K column 1), issued FIRST (it needs no operand block, so it runs while the layer waits
+//     for its first one); mlp1's bias enters the per-keypoint mat-vec;
+//   * ReLU is folded into the operand conversions (split_store8_relu: hi = cvt.rz.relu, lo = cvt.rn.relu of the residual);
+//   * max_k relu(x) = relu(max_k x): the group maxima of X1 and of the descriptor are taken on the pre-activations.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
@@ -59,7 +68,7 @@ constexpr int LW_MAXBLK = 8;                              // operand blocks (32 
 template <int C_, int KNBR_, int CIN_, int NG_, int RING_>
 struct LwCfg {
     static constexpr int C = C_, CO = 2 * C_, KNBR = KNBR_, CIN = CIN_, NG = NG_, RING = RING_;
-    static constexpr int KG = (CIN + 4 + 15) / 16 * 16;                 // grouped input [feat | rel xyz, |rel| | 0-pad]
+    static constexpr int KG = (CIN + 5 + 15) / 16 * 16;                 // grouped input [feat | rel xyz, |rel|, 1 | 0-pad]
     static constexpr int OPC = (CO > KG ? CO : KG) / 8;                 // 8-channel chunks of the operand buffer
     static constexpr int OP_PLANE = OPC * LTM * 16;
     static constexpr int OP_BYTES = 2 * OP_PLANE;
@@ -81,11 +90,18 @@ struct LwCfg {
     // have left TMEM before the first MMA (x3 -> [2C,4C) over C2d | C2x: all of C2x; m1c -> M1 [0,C) over the first half
     // of E: the blocks of that half, the second half of the E*a drain then overlaps the MMAs)
     __host__ __device__ static constexpr int lprewait(int l) { return (l == L_X3 || l == L_M1C) ? C / 32 : 0; }
-    __host__ __device__ static constexpr int woff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += lk(i) * ln(i) * 4; return o; }
+    // layers whose bias is one more MMA in front of their K pieces: ones x [b_hi, b_lo], a piece of ln * 32 bytes (hi plane only)
+    __host__ __device__ static constexpr bool lbias(int l) { return l == L_D2 || l == L_X2 || l == L_D3 || l == L_X3 || l == L_M2; }
+    __host__ __device__ static constexpr int woff(int l) {
+        int o = 0;
+        for (int i = 0; i < l; ++i) o += lk(i) * ln(i) * 4 + (lbias(i) ? ln(i) * 32 : 0);
+        return o;
+    }
     static constexpr int W_BYTES = woff(LW_NL);
-    // biases (floats): d1 d2 d3 x1 x2 x3 m1 m2
-    static constexpr int B_D1 = 0, B_D2 = C, B_D3 = 2 * C, B_X1 = 4 * C, B_X2 = 5 * C, B_X3 = 6 * C, B_M1 = 8 * C,
-                         B_M2 = 9 * C, B_COUNT = 11 * C;
+    static constexpr int ONES_BYTES = 2 * LTM * 16;                     // resident A operand of the bias MMAs, shared by the groups
+    // biases (floats): d1 d2 d3 x1 x2 x3 m1 m2 (only m1 is read by the kernel: the others ride in the MMAs)
+    // at d1 0, d2 C, d3 2C, x1 4C, x2 5C, x3 6C, m1 8C, m2 9C
+    static constexpr int B_M1 = 8 * C, B_COUNT = 11 * C;
     static constexpr int T_GROUP = 4 * C;
     static constexpr int T_COLS = NG * T_GROUP <= 256 ? 256 : 512;
     // shared memory of a group: operand buffer | weight ring | sCol [KPT][CO] | kpb [KPT][C] | sX [2][128]
@@ -93,11 +109,12 @@ struct LwCfg {
     static constexpr int G_KPB = G_SCOL + KPT * CO * 4;
     static constexpr int G_SX = G_KPB + KPT * C * 4;
     static constexpr int G_BYTES = G_SX + 2 * LTM * 4;
-    static constexpr int SMEM = NG * G_BYTES + B_COUNT * 4;
+    static constexpr int SMEM = NG * G_BYTES + ONES_BYTES;
     static constexpr int THREADS = NG * LW_GROUP_WARPS * 32;
     static_assert(NG * T_GROUP <= 512, "TMEM");
     static_assert(KNBR == 16 || KNBR == 32, "group reductions are written for 16 or 32 neighbours (one warp holds whole groups)");
     static_assert(C % 64 == 0 && CO / 32 <= LW_MAXBLK, "two epilogue halves take alternate 32-column blocks");
+    static_assert(KG == (CIN + 4 + 15) / 16 * 16, "the constant-1 channel must fit the K padding");
     static_assert(CIN % 64 == 0 && KG - CIN <= 32, "each thread of a row converts whole 32-channel blocks; the geometry block is one block");
     static_assert(SMEM + 512 <= 227 * 1024, "shared memory (dynamic + the static barriers)");
     static_assert((KPT * C) % (LW_EPI_WARPS * 32) == 0 || (LW_EPI_WARPS * 32) % (KPT * C) == 0, "mat-vec mapping");
@@ -105,21 +122,6 @@ struct LwCfg {
 
 __device__ __forceinline__ uint32_t lw_idesc(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LTM >> 4) << 24);
-}
-
-// f[e] = relu(acc[e] + bias[e]) for 32 consecutive columns (biases as 16-byte shared-memory loads, packed fp32x2 adds)
-__device__ __forceinline__ void lw_bias_relu32(const uint32_t (&v)[32], const float* __restrict__ bb, float (&f)[32]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * q);
-        float s0, s1, s2, s3;
-        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), f2_pack(b4.x, b4.y)), s0, s1);
-        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), f2_pack(b4.z, b4.w)), s2, s3);
-        f[4 * q + 0] = fmaxf(s0, 0.f);
-        f[4 * q + 1] = fmaxf(s1, 0.f);
-        f[4 * q + 2] = fmaxf(s2, 0.f);
-        f[4 * q + 3] = fmaxf(s3, 0.f);
-    }
 }
 
 // segmented transpose-reduce: lanes form groups of KSEG consecutive lanes; afterwards the lane at position p of its group
@@ -176,7 +178,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     const int grp = is_epi ? warp_all / LW_EPI_WARPS : (warp_all - NG * LW_EPI_WARPS) / 2;
     const int warp = is_epi ? warp_all % LW_EPI_WARPS : LW_EPI_WARPS + ((warp_all - NG * LW_EPI_WARPS) & 1);
     uint8_t* gsm = smem + (size_t)grp * Cfg::G_BYTES;
-    float* sB = reinterpret_cast<float*>(smem + (size_t)NG * Cfg::G_BYTES);
+    uint4* sOnes = reinterpret_cast<uint4*>(smem + (size_t)NG * Cfg::G_BYTES);     // [2 chunks][128 rows][16 B]
     float* sCol = reinterpret_cast<float*>(gsm + Cfg::G_SCOL);
     float* sKpb = reinterpret_cast<float*>(gsm + Cfg::G_KPB);
     float* sX = reinterpret_cast<float*>(gsm + Cfg::G_SX);
@@ -194,7 +196,9 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(Cfg::T_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < Cfg::B_COUNT; i += Cfg::THREADS) sB[i] = __ldg(biases + i);
+    // A operand of the bias MMAs: bf16 ones in K columns 0 and 1 of every row, zeros elsewhere
+    for (int i = tid; i < 2 * LTM; i += Cfg::THREADS) sOnes[i] = i < LTM ? make_uint4(0x3f803f80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -234,7 +238,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             __syncwarp();
             if (lane == 0) mbar_arrive(opb0 + 8 * b);
         };
-        auto store_block = [&](const float (&f)[32], int b) {    // 32 columns -> bf16 hi/lo operand chunks 4b .. 4b+3
+        auto store_block = [&](const float (&f)[32], int b) {    // 32 non-negative columns -> bf16 hi/lo operand chunks 4b .. 4b+3
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const float x[8] = {f[ch * 8], f[ch * 8 + 1], f[ch * 8 + 2], f[ch * 8 + 3], f[ch * 8 + 4], f[ch * 8 + 5],
@@ -242,14 +246,20 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 split_store8(x, op_hi + (4 * b + ch) * LTM + rt, op_lo + (4 * b + ch) * LTM + rt);
             }
         };
-        // accumulator [tcol, tcol + ncols) -> relu(x + b) -> operand
-        auto drain_plain = [&](int tcol, int ncols, const float* bb, int b0 = 0) {       // -> operand blocks b0 ..
+        auto store_block_relu = [&](const float (&f)[32], int b) {       // relu(f) -> operand chunks, ReLU inside the conversions
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                split_store8_relu(f + ch * 8, op_hi + (4 * b + ch) * LTM + rt, op_lo + (4 * b + ch) * LTM + rt);
+        };
+        // accumulator [tcol, tcol + ncols) (bias included by the MMAs) -> relu -> operand
+        auto drain_plain = [&](int tcol, int ncols, int b0 = 0) {                        // -> operand blocks b0 ..
             for (int b = h; b < ncols / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + tcol + 32 * b, v);
-                lw_bias_relu32(v, bb + 32 * b, f);
-                store_block(f, b0 + b);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+                store_block_relu(f, b0 + b);
                 publish(b0 + b);
             }
         };
@@ -287,7 +297,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 }
                 if (h == 1) {
                     const float rx = nx - __ldg(qq), ry = ny - __ldg(qq + 1), rz = nz - __ldg(qq + 2);
-                    const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 0.f, 0.f, 0.f, 0.f};
+                    const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 1.f, 0.f, 0.f, 0.f};   // 1: bias column of d1 / x1
                     split_store8(x, op_hi + (CIN / 8) * LTM + rt, op_lo + (CIN / 8) * LTM + rt);
 #pragma unroll
                     for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {         // K padding
@@ -301,14 +311,14 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             // ---- first layers of both stacks, then the second ones as their results arrive ------------------------------
             wait_acc();                                                       // L0: C1d | C1x
             LW_STAMP(1);
-            drain_plain(Cfg::lacc(0), C, sB + Cfg::B_D1);                     // -> d2
-            drain_plain(Cfg::lacc(0) + C, C, sB + Cfg::B_X1, C / 32);         // -> x2 (descriptor half of the buffer)
+            drain_plain(Cfg::lacc(0), C);                                     // -> d2
+            drain_plain(Cfg::lacc(0) + C, C, C / 32);                         // -> x2 (descriptor half of the buffer)
             LW_STAMP(2);
             wait_acc();                                                       // d2
             LW_STAMP(3);
-            drain_plain(Cfg::lacc(Cfg::L_D2), C, sB + Cfg::B_D2);             // -> d3
+            drain_plain(Cfg::lacc(Cfg::L_D2), C);                             // -> d3
             wait_acc();                                                       // x2
-            drain_plain(Cfg::lacc(Cfg::L_X2), C, sB + Cfg::B_X2, C / 32);     // -> x3, which runs under the attention phase
+            drain_plain(Cfg::lacc(Cfg::L_X2), C, C / 32);                     // -> x3, which runs under the attention phase
             LW_STAMP(4);
             wait_acc();                                                       // d3: E
             LW_STAMP(5);
@@ -318,13 +328,9 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_D3) + 32 * b, v);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_D3 + 32 * b + 4 * e);
-                    float s0, s1, s2, s3;
-                    f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1])), f2_pack(b4.x, b4.y)), s0, s1);
-                    f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3])), f2_pack(b4.z, b4.w)), s2, s3);
-                    x1 = fmaxf(x1, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
-                }
+                for (int e = 0; e < 8; ++e)
+                    x1 = fmaxf(x1, fmaxf(fmaxf(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1])),
+                                         fmaxf(__uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))));
             }
             sX[h * LTM + rt] = x1;
             ebar();
@@ -345,10 +351,11 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 float f[32];
                 if (b >= C / 32 && !x3_done) { wait_acc(); x3_done = true; }      // x3 has read the descriptor half of the buffer
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_D3) + 32 * b, v);
-                lw_bias_relu32(v, sB + Cfg::B_D3 + 32 * b, f);
                 const f32x2_t a2 = f2_pack(a, a);
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) f2_unpack(f2_mul(f2_pack(f[e], f[e + 1]), a2), f[e], f[e + 1]);
+                for (int e = 0; e < 32; e += 2) {                 // relu(x) * a: the column sums below need the clamped values
+                    f2_unpack(f2_mul(f2_pack(fmaxf(__uint_as_float(v[e]), 0.f), fmaxf(__uint_as_float(v[e + 1]), 0.f)), a2), f[e], f[e + 1]);
+                }
                 store_block(f, b);
                 publish(b);
                 lw_seg_reduce<KSEG, false>(f, lane);
@@ -364,12 +371,13 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_X3) + 32 * b, v);
-                lw_bias_relu32(v, sB + Cfg::B_X3 + 32 * b, f);
-                store_block(f, b);
-                publish(b);
-                lw_seg_reduce<KSEG, true>(f, lane);                           // max over the group (layers.py:202)
 #pragma unroll
-                for (int i = 0; i < PER; ++i) sCol[kp_local * CO + 32 * b + pos * PER + i] = f[i];
+                for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+                store_block_relu(f, b);
+                publish(b);
+                lw_seg_reduce<KSEG, true>(f, lane);                           // max over the group (layers.py:202), relu(max) = max(relu)
+#pragma unroll
+                for (int i = 0; i < PER; ++i) sCol[kp_local * CO + 32 * b + pos * PER + i] = fmaxf(f[i], 0.f);
             }
             LW_STAMP(13);                                                     // X1 drain + group max
             ebar();                                                           // sCol complete
@@ -385,6 +393,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
 #pragma unroll
                 for (int o = 0; o < OPT; ++o) acc[o] = f2_pack(0.f, 0.f);
                 if (k0 < KPT) {
+                    const float bj = __ldg(biases + Cfg::B_M1 + j);               // mlp1's bias rides in the per-keypoint row
                     const float4* w4 = reinterpret_cast<const float4*>(WaT) + j;      // Wa4 [CO/4][C][4]: 16 B per lane, coalesced
 #pragma unroll 2
                     for (int c = 0; c < CO; c += 8) {
@@ -402,7 +411,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                     for (int o = 0; o < OPT; ++o) {
                         float lo_, hi_;
                         f2_unpack(acc[o], lo_, hi_);
-                        sKpb[(k0 + o) * C + j] = lo_ + hi_;
+                        sKpb[(k0 + o) * C + j] = (lo_ + hi_) + bj;
                     }
                 }
             }
@@ -416,14 +425,11 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_M1B) + 32 * b, v);
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(sB + Cfg::B_M1 + 32 * b + e);
                     const float4 k4 = *reinterpret_cast<const float4*>(sKpb + kp_local * C + 32 * b + e);
-                    f[e + 0] = fmaxf((__uint_as_float(v[e + 0]) + k4.x) + b4.x, 0.f);
-                    f[e + 1] = fmaxf((__uint_as_float(v[e + 1]) + k4.y) + b4.y, 0.f);
-                    f[e + 2] = fmaxf((__uint_as_float(v[e + 2]) + k4.z) + b4.z, 0.f);
-                    f[e + 3] = fmaxf((__uint_as_float(v[e + 3]) + k4.w) + b4.w, 0.f);
+                    f2_unpack(f2_add(f2_pack(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), f2_pack(k4.x, k4.y)), f[e], f[e + 1]);
+                    f2_unpack(f2_add(f2_pack(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])), f2_pack(k4.z, k4.w)), f[e + 2], f[e + 3]);
                 }
-                store_block(f, b);
+                store_block_relu(f, b);
                 publish(b);
             }
             LW_STAMP(17);                                                     // M1 drain
@@ -433,10 +439,11 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_M2) + 32 * b, v);
-                lw_bias_relu32(v, sB + Cfg::B_M2 + 32 * b, f);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
                 lw_seg_reduce<KSEG, true>(f, lane);
 #pragma unroll
-                for (int i = 0; i < PER; ++i) out_desc[bm * CO + 32 * b + pos * PER + i] = f[i];
+                for (int i = 0; i < PER; ++i) out_desc[bm * CO + 32 * b + pos * PER + i] = fmaxf(f[i], 0.f);
             }
             LW_STAMP(19);                                                     // descriptor epilogue
             // the TMEM reads of this tile are ordered before the next tile's first MMA by the block arrivals of its gather
@@ -450,6 +457,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             const uint64_t a_desc0 = DESC_FIXED | ((uint64_t)((LTM * 16) >> 4) << 16);             // LBO = 2048 B
             constexpr uint32_t LO16 = Cfg::OP_PLANE >> 4, P16 = (2 * LTM * 16) >> 4, SLOT16 = Cfg::SLOT >> 4;
             uint32_t ws = 0, wpar = 0, opph = 0;
+            const uint32_t ones16 = smem_u32(sOnes) >> 4;
 #ifdef LW_PROF
             const bool prof_on = blockIdx.x == 0 && grp == 0;
             long long prof_t = clock64();
@@ -465,6 +473,13 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                     const int B0 = Cfg::lblock0(l), P0 = Cfg::lpiece0(l);
                     const int PRE = Cfg::lprewait(l);
                     for (int b = 0; b < PRE; ++b) { mbar_wait(opb0 + 8 * (B0 + b), (opph >> (B0 + b)) & 1); opph ^= 1u << (B0 + b); }
+                    if (Cfg::lbias(l)) {                                      // D = 1 * b_hi + 1 * b_lo, before any operand block is needed
+                        mbar_wait(wfull0 + 8 * ws, wpar);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        umma_bf16(d, a_desc0 | ones16, w_desc0 | ((ring_a >> 4) + ws * SLOT16), idesc, 0u);
+                        umma_commit(wempty0 + 8 * ws);
+                        if (++ws == (uint32_t)RING) { ws = 0; wpar ^= 1; }
+                    }
                     for (int p = 0; p < K / 16; ++p) {
                         if ((p >> 1) >= PRE && (p & 1) == 0) {
                             const int bi = B0 + (p >> 1);
@@ -477,7 +492,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                         const uint32_t a16 = (op_a >> 4) + (P0 + p) * P16, w16 = (ring_a >> 4) + ws * SLOT16;
                         const uint64_t ah = a_desc0 | a16, al = a_desc0 | (a16 + LO16);
                         const uint64_t wh = w_desc0 | w16, wl = w_desc0 | (w16 + wlo16);
-                        umma_bf16(d, ah, wh, idesc, (p > 0 || l == Cfg::L_M1B) ? 1u : 0u);
+                        umma_bf16(d, ah, wh, idesc, (p > 0 || l == Cfg::L_M1B || Cfg::lbias(l)) ? 1u : 0u);
                         umma_bf16(d, al, wh, idesc, 1u);
                         umma_bf16(d, ah, wl, idesc, 1u);
                         umma_commit(wempty0 + 8 * ws);
@@ -496,8 +511,9 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 const uint8_t* src = Wpack;
 #pragma unroll
                 for (int l = 0; l < LW_NL; ++l) {
-                    const uint32_t bytes = (uint32_t)Cfg::ln(l) * 64u;
-                    for (int p = 0; p < Cfg::lk(l) / 16; ++p) {
+                    // a layer's bias piece (hi plane only) goes first, then its K=16 pieces
+                    for (int p = Cfg::lbias(l) ? -1 : 0; p < Cfg::lk(l) / 16; ++p) {
+                        const uint32_t bytes = (uint32_t)Cfg::ln(l) * (p < 0 ? 32u : 64u);
                         mbar_wait(wempty0 + 8 * ws, wpar ^ 1);    // no sleep: the refill latency of a slot bounds the stream
                         mbar_expect_tx(wfull0 + 8 * ws, bytes);
                         bulk_g2s(ring_a + ws * Cfg::SLOT, src, bytes, wfull0 + 8 * ws);

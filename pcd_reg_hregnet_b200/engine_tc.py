@@ -208,9 +208,9 @@ def which_level_ws(k, cin, det, desc):
 def pack_level_ws(level, det, desc):
     """Folded parameter dicts of detector_l / desc_extractor_l -> (Wpack uint8, WaT fp32 [2C, C], biases fp32) in the
     LwCfg layout of csrc/level_ws.cu: K=16 weight pieces of the 8 MMA layers in issue order
-    [d1;x1] d2 x2 d3 x3 mlp1[E*a] mlp1[X1] mlp2; the max_k(X1) block of mlp1 (its first 2C input channels,
+    [d1;x1] d2 x2 d3 x3 mlp1[E*a] mlp1[X1] mlp2 (d2 x2 d3 x3 mlp2 each preceded by their bias piece); the max_k(X1) block of mlp1 (its first 2C input channels,
     layers.py:203-205) goes to the CUDA cores as the transposed fp32 matrix WaT.  Grouped input channels re-ordered as in
-    pack_level: [feat(C), rel(3), dist(1), 0-pad]."""
+    pack_level: [feat(C), rel(3), dist(1), 1, 0-pad]."""
     key = (level,) + tuple((W.data_ptr(), W._version) for W, _, _ in det["convs"] + desc["convs"] + desc["mlp"])
     hit = _level_ws_cache.get(key)
     if hit is not None:
@@ -221,12 +221,28 @@ def pack_level_ws(level, det, desc):
     (d1, bd1, _), (d2, bd2, _), (d3, bd3, _) = det["convs"]
     (x1, bx1, _), (x2, bx2, _), (x3, bx3, _) = desc["convs"]
     (m1, bm1, _), (m2, bm2, _) = desc["mlp"]
-    KG = (cin + 4 + 15) // 16 * 16
+    KG = (cin + 5 + 15) // 16 * 16
     perm = list(range(4, 4 + cin)) + [0, 1, 2, 3]
     first = torch.zeros(2 * C, KG, dtype=torch.float32, device=d1.device)
     first[:, :cin + 4] = torch.cat([d1[:, perm], x1[:, perm]], 0)
-    parts = [_pieces(first, KG), _pieces(d2, C), _pieces(x2, C), _pieces(d3, C), _pieces(x3, C),
-             _pieces(m1[:, 2 * CO:].contiguous(), CO), _pieces(m1[:, CO:2 * CO].contiguous(), CO), _pieces(m2, C)]
+    first[:, cin + 4] = torch.cat([bd1, bx1])            # weight column of the constant-1 channel = the biases of d1 / x1
+
+    def bias_piece(b):
+        # [2 chunks][N][8] bf16 with the bias as hi (K column 0) + lo (K column 1): multiplied by a resident block of ones,
+        # the layer's first MMA (csrc/level_ws.cu)
+        piece = torch.zeros(2, b.numel(), 8, dtype=torch.bfloat16, device=b.device)
+        hi = b.to(torch.bfloat16)
+        piece[0, :, 0] = hi
+        piece[0, :, 1] = (b - hi.float()).to(torch.bfloat16)
+        return piece.view(-1).view(torch.uint8)
+
+    parts = [_pieces(first, KG), bias_piece(bd2), _pieces(d2, C), bias_piece(bx2), _pieces(x2, C),
+             bias_piece(bd3), _pieces(d3, C), bias_piece(bx3), _pieces(x3, C),
+             _pieces(m1[:, 2 * CO:].contiguous(), CO), _pieces(m1[:, CO:2 * CO].contiguous(), CO),
+             bias_piece(bm2), _pieces(m2, C)]
+    from ._lib import lib
+    if lib().hrn_level_ws_pack_bytes(level) < sum(p.numel() for p in parts):
+        parts = [p for i, p in enumerate(parts) if i not in (1, 3, 5, 7, 11)]     # a library built with additive biases (A/B runs)
     Wpack = torch.cat(parts).contiguous()
     WaT = m1[:, :CO].t().contiguous().view(CO // 4, 4, C).permute(0, 2, 1).contiguous()     # [CO/4][C][4]
     biases = torch.cat([bd1, bd2, bd3, bx1, bx2, bx3, bm1, bm2]).contiguous()

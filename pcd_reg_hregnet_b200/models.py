@@ -58,7 +58,7 @@ class HierFeatureExtraction(nn.Module):
                                                  sample_idx=None if draws is None else draws[lv - 1])
             out[f"xyz_{lv}"], out[f"sigmas_{lv}"], out[f"desc_{lv}"] = r["xyz"], r["sigmas"], r["desc"]
             xyz, feat = r["xyz"], r["af"]
-            w = engine.sigma_to_weights(r["sigmas"]) if self.use_weights else None
+            w = engine.sigma_to_weights(r["sigmas"]) if self.use_weights and lv < 3 else None     # sampling weights of the next level
         return out
 
     def forward(self, points):

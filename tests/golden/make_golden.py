@@ -192,7 +192,7 @@ def variants_golden():
     """Model_V2 / Model_V4 of the UNMODIFIED reference on CPU (seeded like tests/common.build_product_model_v2 / _v4)."""
     from common import Args
     ns = H.load_reference()
-    for name, cls, seeds in (("model_v2_b2_n2048", ns.Model_V2, [1105, 1208]), ("model_v4_b2_n2048", ns.Model_V4, [1105, 1208])):
+    for name, cls, seeds in (("model_v2_b2_n2048", ns.Model_V2, [1105, 1208]), ("model_v4_b2_n2048", ns.Model_V4, [1105, 1062])):
         assert cls is not None
         torch.manual_seed(7)
         ref = cls(Args())

@@ -1,8 +1,8 @@
-# in-box A/B of two builds of the library: tools/ab_lib.sh other.so
+# in-box A/B of two builds of the library: tools/ab_lib.sh other.so   (alternating runs on ONE box; "base" = the library in the tree)
 cp pcd_reg_hregnet_b200/libhregnet_b200.so /tmp/base.so
 for i in 1 2; do for v in base other; do
   if [ $v = other ]; then cp $1 pcd_reg_hregnet_b200/libhregnet_b200.so; else cp /tmp/base.so pcd_reg_hregnet_b200/libhregnet_b200.so; fi
-  timeout 200 python bench.py --steps 30 --warmup 5 2>/dev/null | tail -1 > /tmp/o.json
-  python -c "import json; d=json.load(open('/tmp/o.json')); print('$v', round(d['ms_per_step'],4), round(d['in_flight']['ms_per_step'],4))"
+  timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-gpu-reference --no-parity 2>/dev/null | tail -1 > /tmp/o.json
+  python -c "import json; d=json.load(open('/tmp/o.json')); k=d['kernel_breakdown_ms_per_step']; print('$v', round(d['ms_per_step'],4), round(d['in_flight']['ms_per_step'],4), {n: k[n] for n in ('hrn_level_ws','hrn_level_fused','hrn_chain_tc','hrn_chain_wide','hrn_layer_tc')})"
 done; done
 cp /tmp/base.so pcd_reg_hregnet_b200/libhregnet_b200.so
