@@ -37,8 +37,8 @@
 // is on the tile's dependency chain):
 //   * the biases ride in the MMAs: d1 / x1 as the weight column of a constant-1 channel in the K padding of the grouped
 //     input, d2 x2 d3 x3 m2 as ONE extra MMA per layer -- a resident block of ones (K columns 0 and 1) times the bias split
-//     into bf16 hi (K column 0) + lo (K column 1), issued FIRST (it needs no operand block, so it runs while the layer waits
-//     for its first one); mlp1's bias enters the per-keypoint mat-vec;
+//     into bf16 hi (K column 0) + lo (K column 1), issued in front of the layer's K pieces; mlp1's bias enters the
+//     per-keypoint mat-vec;
 //   * ReLU is folded into the operand conversions (split_store8_relu: hi = cvt.rz.relu, lo = cvt.rn.relu of the residual);
 //   * max_k relu(x) = relu(max_k x): the group maxima of X1 and of the descriptor are taken on the pre-activations.
 #include "common.cuh"
@@ -268,46 +268,53 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         const bool prof_on = blockIdx.x == 0 && grp == 0 && warp == 0 && lane == 0;
         long long prof_t = clock64();
 #endif
+        // Grouped input [feat[idx] | rel xyz, |rel|, 1 | 0] -> operand buffer (both threads of a row), software-pipelined across
+        // tiles: the loads of tile t+1 are issued before the wait for tile t's last layer (mlp2) and converted right after it --
+        // the operand buffer is free then, and the first layer's MMAs of tile t+1 run under tile t's descriptor epilogue
+        // (L0 accumulates in TMEM [0,2C), the descriptor is read from [2C,4C)).
+        constexpr int CH = CIN / 16;                                          // feature chunks of this thread
+        float4 fv[2 * CH];                                                    // the whole half row in flight at once
+        float gx = 0.f, gy = 0.f, gz = 0.f, gqx = 0.f, gqy = 0.f, gqz = 0.f;
         int n_next = vblock < n_tiles ? __ldg(idx + (long long)vblock * LTM + rt) : 0;
+        auto gather_load = [&](int t) {
+            const long long bm_ = ((long long)t * LTM + rt) / KNBR;
+            const long long b_ = bm_ / M;
+            const int n = n_next;                                             // loaded one tile ahead
+            if (t + vgrid < n_tiles) n_next = __ldg(idx + (long long)(t + vgrid) * LTM + rt);
+            const float* pp = xyz + (b_ * N + n) * 3;
+            const float4* fr = reinterpret_cast<const float4*>(feat + (b_ * N + n) * CIN) + h * CH * 2;
+#pragma unroll
+            for (int i = 0; i < 2 * CH; ++i) fv[i] = __ldg(fr + i);
+            gx = __ldg(pp); gy = __ldg(pp + 1); gz = __ldg(pp + 2);
+            if (h == 1) { const float* qq = q + bm_ * 3; gqx = __ldg(qq); gqy = __ldg(qq + 1); gqz = __ldg(qq + 2); }
+        };
+        auto gather_store = [&]() {
+            // every 32-channel block is published on its own: the first layer's MMAs start on the first block while
+            // the rest of the row is still being converted (feature blocks h*CH/4 .. by half h, the geometry block by h = 1)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float x[8] = {fv[2 * c].x, fv[2 * c].y, fv[2 * c].z, fv[2 * c].w,
+                                    fv[2 * c + 1].x, fv[2 * c + 1].y, fv[2 * c + 1].z, fv[2 * c + 1].w};
+                split_store8(x, op_hi + (h * CH + c) * LTM + rt, op_lo + (h * CH + c) * LTM + rt);
+                if ((c & 3) == 3) publish(h * (CH / 4) + (c >> 2));
+            }
+            if (h == 1) {
+                const float rx = gx - gqx, ry = gy - gqy, rz = gz - gqz;
+                const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 1.f, 0.f, 0.f, 0.f};   // 1: bias column of d1 / x1
+                split_store8(x, op_hi + (CIN / 8) * LTM + rt, op_lo + (CIN / 8) * LTM + rt);
+#pragma unroll
+                for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {         // K padding
+                    op_hi[c * LTM + rt] = make_uint4(0, 0, 0, 0);
+                    op_lo[c * LTM + rt] = make_uint4(0, 0, 0, 0);
+                }
+                publish(CIN / 32);
+            }
+        };
+        if (vblock < n_tiles) { gather_load(vblock); gather_store(); }
         for (int tile = vblock; tile < n_tiles; tile += vgrid) {
-            float nx, ny, nz;
-            // ---- grouped input [feat[idx] | rel xyz, |rel| | 0] -> operand buffer (both threads of a row) ----------
             const long long r = (long long)tile * LTM + rt;
             const long long bm = r / KNBR;
-            const long long b_ = bm / M;
-            const int n = n_next;                                             // loaded one tile ahead
-            if (tile + vgrid < n_tiles) n_next = __ldg(idx + (long long)(tile + vgrid) * LTM + rt);
-            const float* pp = xyz + (b_ * N + n) * 3;
-            const float* qq = q + bm * 3;
-            {
-                constexpr int CH = CIN / 16;                                  // feature chunks of this thread
-                const float4* fr = reinterpret_cast<const float4*>(feat + (b_ * N + n) * CIN) + h * CH * 2;
-                float4 fv[2 * CH];                                            // the whole half row in flight at once
-#pragma unroll
-                for (int i = 0; i < 2 * CH; ++i) fv[i] = __ldg(fr + i);
-                nx = __ldg(pp); ny = __ldg(pp + 1); nz = __ldg(pp + 2);
-                // every 32-channel block is published on its own: the first layer's MMAs start on the first block while
-                // the rest of the row is still being converted (feature blocks h*CH/4 .. by half h, the geometry block by h = 1)
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const float x[8] = {fv[2 * c].x, fv[2 * c].y, fv[2 * c].z, fv[2 * c].w,
-                                        fv[2 * c + 1].x, fv[2 * c + 1].y, fv[2 * c + 1].z, fv[2 * c + 1].w};
-                    split_store8(x, op_hi + (h * CH + c) * LTM + rt, op_lo + (h * CH + c) * LTM + rt);
-                    if ((c & 3) == 3) publish(h * (CH / 4) + (c >> 2));
-                }
-                if (h == 1) {
-                    const float rx = nx - __ldg(qq), ry = ny - __ldg(qq + 1), rz = nz - __ldg(qq + 2);
-                    const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 1.f, 0.f, 0.f, 0.f};   // 1: bias column of d1 / x1
-                    split_store8(x, op_hi + (CIN / 8) * LTM + rt, op_lo + (CIN / 8) * LTM + rt);
-#pragma unroll
-                    for (int c = CIN / 8 + 1; c < Cfg::KG / 8; ++c) {         // K padding
-                        op_hi[c * LTM + rt] = make_uint4(0, 0, 0, 0);
-                        op_lo[c * LTM + rt] = make_uint4(0, 0, 0, 0);
-                    }
-                    publish(CIN / 32);
-                }
-            }
-            LW_STAMP(0);                                                      // gather
+            const float nx = gx, ny = gy, nz = gz;                            // this tile's neighbour (the attention phase needs it)
             // ---- first layers of both stacks, then the second ones as their results arrive ------------------------------
             wait_acc();                                                       // L0: C1d | C1x
             LW_STAMP(1);
@@ -395,7 +402,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 if (k0 < KPT) {
                     const float bj = __ldg(biases + Cfg::B_M1 + j);               // mlp1's bias rides in the per-keypoint row
                     const float4* w4 = reinterpret_cast<const float4*>(WaT) + j;      // Wa4 [CO/4][C][4]: 16 B per lane, coalesced
-#pragma unroll 2
+#pragma unroll 8
                     for (int c = 0; c < CO; c += 8) {
                         const float4 wa = __ldg(w4 + (size_t)(c / 4) * C), wb = __ldg(w4 + (size_t)(c / 4 + 1) * C);
                         const f32x2_t wa0 = f2_pack(wa.x, wa.y), wa1 = f2_pack(wa.z, wa.w), wb0 = f2_pack(wb.x, wb.y), wb1 = f2_pack(wb.z, wb.w);
@@ -433,8 +440,12 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 publish(b);
             }
             LW_STAMP(17);                                                     // M1 drain
+            const bool more = tile + vgrid < n_tiles;
+            if (more) gather_load(tile + vgrid);                              // in flight under the wait
             wait_acc();                                                       // mlp2: descriptor = max_k (layers.py:207-208)
             LW_STAMP(18);
+            if (more) gather_store();                                         // every MMA of this tile is complete: the buffer is free
+            LW_STAMP(0);                                                      // gather (of the next tile)
             for (int b = h; b < CO / 32; b += 2) {
                 uint32_t v[32];
                 float f[32];
@@ -446,9 +457,11 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 for (int i = 0; i < PER; ++i) out_desc[bm * CO + 32 * b + pos * PER + i] = fmaxf(f[i], 0.f);
             }
             LW_STAMP(19);                                                     // descriptor epilogue
-            // the TMEM reads of this tile are ordered before the next tile's first MMA by the block arrivals of its gather
-            // (tcgen05.fence::before_thread_sync in front of it); sX / sCol / sKpb are rewritten only after the next
-            // tile's named barriers
+            // The next tile's L0 (already running) leaves [2C,4C) alone; its d2 writes there and is issued once the first
+            // C1d block is published -- by warps of ONE column half.  All eight warps must have read the descriptor by
+            // then: a named barrier closes the tile.  sX / sCol / sKpb are rewritten only after the next tile's barriers.
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            ebar();
         }
     } else if (warp == LW_EPI_WARPS) {
         // ================= MMA issue ==================================================================================
@@ -473,19 +486,27 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                     const int B0 = Cfg::lblock0(l), P0 = Cfg::lpiece0(l);
                     const int PRE = Cfg::lprewait(l);
                     for (int b = 0; b < PRE; ++b) { mbar_wait(opb0 + 8 * (B0 + b), (opph >> (B0 + b)) & 1); opph ^= 1u << (B0 + b); }
-                    if (Cfg::lbias(l)) {                                      // D = 1 * b_hi + 1 * b_lo, before any operand block is needed
+                    // D = 1 * b_hi + 1 * b_lo in front of the layer's K pieces.  d3 / x3 / m2 issue it at once (it needs no
+                    // operand block: it runs while the layer waits for its first one; their target columns are free by
+                    // then, see the header).  d2 / x2 must see their first block: the next tile's L0 is issued under this
+                    // tile's descriptor epilogue, d2 / x2 overwrite the columns that epilogue reads, and their first block
+                    // is published behind the barrier that closes it.
+                    auto bias_mma = [&]() {
                         mbar_wait(wfull0 + 8 * ws, wpar);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         umma_bf16(d, a_desc0 | ones16, w_desc0 | ((ring_a >> 4) + ws * SLOT16), idesc, 0u);
                         umma_commit(wempty0 + 8 * ws);
                         if (++ws == (uint32_t)RING) { ws = 0; wpar ^= 1; }
-                    }
+                    };
+                    const bool late_bias = (l == Cfg::L_D2 || l == Cfg::L_X2);         // the layer loop is fully unrolled: a constant
+                    if (Cfg::lbias(l) && !late_bias) bias_mma();
                     for (int p = 0; p < K / 16; ++p) {
                         if ((p >> 1) >= PRE && (p & 1) == 0) {
                             const int bi = B0 + (p >> 1);
                             mbar_wait(opb0 + 8 * bi, (opph >> bi) & 1); opph ^= 1u << bi;
                         }
                         LW_STAMP(33);                                         // waiting for operand blocks
+                        if (p == 0 && late_bias) bias_mma();
                         mbar_wait(wfull0 + 8 * ws, wpar);
                         LW_STAMP(34);                                         // waiting for weights
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
