@@ -9,7 +9,7 @@
 // 32-pair step through HBM (the [rows, 256] tensors E*a, X1 and the mlp1 output); here nothing per-neighbour leaves the SM.
 //
 // Tile = 128 rows = 128/k keypoints x k neighbours.  Per tile and group (a group = 8 epilogue warps + 1 MMA warp +
-// 1 weight-stream warp; two threads per row, each draining alternate 32-column blocks of an accumulator):
+// 1 weight-stream warp; NH = 2 threads per row, each draining alternate 32-column blocks of an accumulator):
 //
 //   G -[d1;x1]-> C1d | C1x            both drained at once: the two conv stacks do not depend on each other
 //   C1d -d2-> C2d -d3-> E             attention a = softmax_k(max_c E), keypoint = sum_k a nn
@@ -57,17 +57,22 @@ __device__ unsigned long long g_lw_prof[64];
 #define LW_STAMP(slot) do { } while (0)
 #endif
 
+#ifndef LW3_EW
+#define LW3_EW 8         // epilogue warps of the level-3 kernel.  16 (four threads per row) measured SLOWER in-box: step 4.585 vs
+                         // 4.558 ms -- the tile is bound by the MMA <-> drain hand-offs of its dependency chain, not by SIMT throughput
+#endif
+
 namespace {
 
 constexpr int LTM = 128;
-constexpr int LW_EPI_WARPS = 8;
-constexpr int LW_GROUP_WARPS = LW_EPI_WARPS + 2;
 constexpr int LW_NL = 8;                                  // MMA layers per tile
 constexpr int LW_MAXBLK = 8;                              // operand blocks (32 columns) per layer, at most
 
-template <int C_, int KNBR_, int CIN_, int NG_, int RING_>
+// EW_: epilogue warps per group, 8 or 16 -- NH = EW / 4 threads per row, each draining every NH-th 32-column block of an
+// accumulator (a warp can only read its own TMEM lane quadrant, so more warps means more threads per row, not fewer rows)
+template <int C_, int KNBR_, int CIN_, int NG_, int RING_, int EW_>
 struct LwCfg {
-    static constexpr int C = C_, CO = 2 * C_, KNBR = KNBR_, CIN = CIN_, NG = NG_, RING = RING_;
+    static constexpr int C = C_, CO = 2 * C_, KNBR = KNBR_, CIN = CIN_, NG = NG_, RING = RING_, EW = EW_, NH = EW_ / 4;
     static constexpr int KG = (CIN + 5 + 15) / 16 * 16;                 // grouped input [feat | rel xyz, |rel|, 1 | 0-pad]
     static constexpr int OPC = (CO > KG ? CO : KG) / 8;                 // 8-channel chunks of the operand buffer
     static constexpr int OP_PLANE = OPC * LTM * 16;
@@ -108,16 +113,17 @@ struct LwCfg {
     static constexpr int G_SCOL = OP_BYTES + RING * SLOT;
     static constexpr int G_KPB = G_SCOL + KPT * CO * 4;
     static constexpr int G_SX = G_KPB + KPT * C * 4;
-    static constexpr int G_BYTES = G_SX + 2 * LTM * 4;
+    static constexpr int G_BYTES = G_SX + NH * LTM * 4;
     static constexpr int SMEM = NG * G_BYTES + ONES_BYTES;
-    static constexpr int THREADS = NG * LW_GROUP_WARPS * 32;
+    static constexpr int THREADS = NG * (EW + 2) * 32;
     static_assert(NG * T_GROUP <= 512, "TMEM");
     static_assert(KNBR == 16 || KNBR == 32, "group reductions are written for 16 or 32 neighbours (one warp holds whole groups)");
     static_assert(C % 64 == 0 && CO / 32 <= LW_MAXBLK, "two epilogue halves take alternate 32-column blocks");
     static_assert(KG == (CIN + 4 + 15) / 16 * 16, "the constant-1 channel must fit the K padding");
     static_assert(CIN % 64 == 0 && KG - CIN <= 32, "each thread of a row converts whole 32-channel blocks; the geometry block is one block");
     static_assert(SMEM + 512 <= 227 * 1024, "shared memory (dynamic + the static barriers)");
-    static_assert((KPT * C) % (LW_EPI_WARPS * 32) == 0 || (LW_EPI_WARPS * 32) % (KPT * C) == 0, "mat-vec mapping");
+    static_assert((KPT * C) % (EW * 32) == 0 || (EW * 32) % (KPT * C) == 0, "mat-vec mapping");
+    static_assert((EW == 8 || EW == 16) && (C / 32) % NH == 0 && (CIN / 32) % NH == 0, "every thread of a row takes whole 32-column blocks");
 };
 
 __device__ __forceinline__ uint32_t lw_idesc(int N) {
@@ -174,9 +180,10 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     const int tid = threadIdx.x, warp_all = tid >> 5, lane = tid & 31;
     // Warp roles: the epilogue warps of all groups first (a warp reads the TMEM lane quadrant warp_id % 4 of the CTA, so
     // every group's eight epilogue warps must start at a multiple of four), then per group one MMA and one weight warp.
-    const bool is_epi = warp_all < NG * LW_EPI_WARPS;
-    const int grp = is_epi ? warp_all / LW_EPI_WARPS : (warp_all - NG * LW_EPI_WARPS) / 2;
-    const int warp = is_epi ? warp_all % LW_EPI_WARPS : LW_EPI_WARPS + ((warp_all - NG * LW_EPI_WARPS) & 1);
+    constexpr int EW = Cfg::EW, NH = Cfg::NH;
+    const bool is_epi = warp_all < NG * EW;
+    const int grp = is_epi ? warp_all / EW : (warp_all - NG * EW) / 2;
+    const int warp = is_epi ? warp_all % EW : EW + ((warp_all - NG * EW) & 1);
     uint8_t* gsm = smem + (size_t)grp * Cfg::G_BYTES;
     uint4* sOnes = reinterpret_cast<uint4*>(smem + (size_t)NG * Cfg::G_BYTES);     // [2 chunks][128 rows][16 B]
     float* sCol = reinterpret_cast<float*>(gsm + Cfg::G_SCOL);
@@ -209,9 +216,9 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
     const uint32_t wfull0 = smem_u32(&s_wfull[grp][0]), wempty0 = smem_u32(&s_wempty[grp][0]);
     const uint32_t opb0 = smem_u32(&s_opb[grp][0]), accf = smem_u32(&s_accf[grp][0]);
 
-    if (warp < LW_EPI_WARPS) {
+    if (warp < EW) {
         // ================= epilogue warps: gather, drains, attention, reductions ================================
-        const int h = warp >> 2, wq = warp & 3;                  // column half (alternate 32-column blocks), TMEM lane quadrant
+        const int h = warp >> 2, wq = warp & 3;                  // which of the row's NH threads (every NH-th 32-column block), TMEM lane quadrant
         const int rt = wq * 32 + lane;                           // row inside the tile = TMEM lane
         const int et = warp * 32 + lane;                         // epilogue thread id inside the group, 0..255
         const uint32_t lane_base = ((uint32_t)(wq * 32) << 16);
@@ -224,7 +231,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         // parity wait cannot see that; on either barrier a layer's MMAs depend on a drain that follows the wait for the
         // barrier's previous layer.
         uint32_t accph = 0, acc_l = 0;
-        auto ebar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(LW_EPI_WARPS * 32) : "memory"); };
+        auto ebar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(EW * 32) : "memory"); };
         auto wait_acc = [&]() {                                  // waits are made in layer order
             const uint32_t s_ = acc_l & 1u;
             mbar_wait(accf + 8 * s_, (accph >> s_) & 1u);
@@ -253,7 +260,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         };
         // accumulator [tcol, tcol + ncols) (bias included by the MMAs) -> relu -> operand
         auto drain_plain = [&](int tcol, int ncols, int b0 = 0) {                        // -> operand blocks b0 ..
-            for (int b = h; b < ncols / 32; b += 2) {
+            for (int b = h; b < ncols / 32; b += NH) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + tcol + 32 * b, v);
@@ -268,11 +275,11 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         const bool prof_on = blockIdx.x == 0 && grp == 0 && warp == 0 && lane == 0;
         long long prof_t = clock64();
 #endif
-        // Grouped input [feat[idx] | rel xyz, |rel|, 1 | 0] -> operand buffer (both threads of a row), software-pipelined across
+        // Grouped input [feat[idx] | rel xyz, |rel|, 1 | 0] -> operand buffer (all NH threads of a row), software-pipelined across
         // tiles: the loads of tile t+1 are issued before the wait for tile t's last layer (mlp2) and converted right after it --
         // the operand buffer is free then, and the first layer's MMAs of tile t+1 run under tile t's descriptor epilogue
         // (L0 accumulates in TMEM [0,2C), the descriptor is read from [2C,4C)).
-        constexpr int CH = CIN / 16;                                          // feature chunks of this thread
+        constexpr int CH = CIN / 8 / NH;                                      // feature chunks of this thread
         float4 fv[2 * CH];                                                    // the whole half row in flight at once
         float gx = 0.f, gy = 0.f, gz = 0.f, gqx = 0.f, gqy = 0.f, gqz = 0.f;
         int n_next = vblock < n_tiles ? __ldg(idx + (long long)vblock * LTM + rt) : 0;
@@ -286,11 +293,11 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
 #pragma unroll
             for (int i = 0; i < 2 * CH; ++i) fv[i] = __ldg(fr + i);
             gx = __ldg(pp); gy = __ldg(pp + 1); gz = __ldg(pp + 2);
-            if (h == 1) { const float* qq = q + bm_ * 3; gqx = __ldg(qq); gqy = __ldg(qq + 1); gqz = __ldg(qq + 2); }
+            if (h == NH - 1) { const float* qq = q + bm_ * 3; gqx = __ldg(qq); gqy = __ldg(qq + 1); gqz = __ldg(qq + 2); }
         };
         auto gather_store = [&]() {
             // every 32-channel block is published on its own: the first layer's MMAs start on the first block while
-            // the rest of the row is still being converted (feature blocks h*CH/4 .. by half h, the geometry block by h = 1)
+            // the rest of the row is still being converted (feature blocks h*CH/4 .. by thread h of the row, the geometry block by the last one)
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 const float x[8] = {fv[2 * c].x, fv[2 * c].y, fv[2 * c].z, fv[2 * c].w,
@@ -298,7 +305,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 split_store8(x, op_hi + (h * CH + c) * LTM + rt, op_lo + (h * CH + c) * LTM + rt);
                 if ((c & 3) == 3) publish(h * (CH / 4) + (c >> 2));
             }
-            if (h == 1) {
+            if (h == NH - 1) {
                 const float rx = gx - gqx, ry = gy - gqy, rz = gz - gqz;
                 const float x[8] = {rx, ry, rz, sqrtf(rx * rx + ry * ry + rz * rz), 1.f, 0.f, 0.f, 0.f};   // 1: bias column of d1 / x1
                 split_store8(x, op_hi + (CIN / 8) * LTM + rt, op_lo + (CIN / 8) * LTM + rt);
@@ -331,7 +338,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             LW_STAMP(5);
             // attention: a = softmax_k(max_c E), keypoint = sum_k a * nn (layers.py:151-155)
             float x1 = 0.f;                                                   // post-ReLU values are >= 0
-            for (int b = h; b < CO / 32; b += 2) {
+            for (int b = h; b < CO / 32; b += NH) {
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_D3) + 32 * b, v);
 #pragma unroll
@@ -341,7 +348,8 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             }
             sX[h * LTM + rt] = x1;
             ebar();
-            x1 = fmaxf(x1, sX[(h ^ 1) * LTM + rt]);
+#pragma unroll
+            for (int o = 1; o < NH; ++o) x1 = fmaxf(x1, sX[((h + o) % NH) * LTM + rt]);
             const float gmax = lw_seg_max<KSEG>(x1);
             const float ex = expf(x1 - gmax);
             const float s0 = lw_seg_sum<KSEG>(ex);
@@ -353,7 +361,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             LW_STAMP(6);                                                      // attention
             // attentive feature map E*a = first K-segment of mlp1; its column sums = the attentive feature (layers.py:157-159)
             bool x3_done = false;
-            for (int b = h; b < CO / 32; b += 2) {
+            for (int b = h; b < CO / 32; b += NH) {
                 uint32_t v[32];
                 float f[32];
                 if (b >= C / 32 && !x3_done) { wait_acc(); x3_done = true; }      // x3 has read the descriptor half of the buffer
@@ -374,7 +382,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             wait_acc();                                                       // m1c: the E*a segment has been consumed
             LW_STAMP(8);
             LW_STAMP(12);
-            for (int b = h; b < CO / 32; b += 2) {
+            for (int b = h; b < CO / 32; b += NH) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_X3) + 32 * b, v);
@@ -391,7 +399,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             LW_STAMP(14);
             // per-keypoint bias  Wa . max_k(X1)  on the CUDA cores (fp32), while the tensor core runs the X1 segment
             {
-                constexpr int TPK = LW_EPI_WARPS * 32 / C;                    // thread sets along the keypoints
+                constexpr int TPK = EW * 32 / C;                    // thread sets along the keypoints
                 constexpr int OPT = (KPT + TPK - 1) / TPK;                    // keypoints per thread
                 const int j = et % C, k0 = (et / C) * OPT;
                 // two partial sums per keypoint (even / odd input channels of every group of four), packed fp32x2 FMAs:
@@ -402,7 +410,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
                 if (k0 < KPT) {
                     const float bj = __ldg(biases + Cfg::B_M1 + j);               // mlp1's bias rides in the per-keypoint row
                     const float4* w4 = reinterpret_cast<const float4*>(WaT) + j;      // Wa4 [CO/4][C][4]: 16 B per lane, coalesced
-#pragma unroll 8
+#pragma unroll (EW == 16 ? 4 : 8)
                     for (int c = 0; c < CO; c += 8) {
                         const float4 wa = __ldg(w4 + (size_t)(c / 4) * C), wb = __ldg(w4 + (size_t)(c / 4 + 1) * C);
                         const f32x2_t wa0 = f2_pack(wa.x, wa.y), wa1 = f2_pack(wa.z, wa.w), wb0 = f2_pack(wb.x, wb.y), wb1 = f2_pack(wb.z, wb.w);
@@ -426,7 +434,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             ebar();                                                           // sKpb complete
             wait_acc();                                                       // m1b: M1 = Wc.(E*a) + Wb.X1
             LW_STAMP(16);
-            for (int b = h; b < C / 32; b += 2) {
+            for (int b = h; b < C / 32; b += NH) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_M1B) + 32 * b, v);
@@ -446,7 +454,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             LW_STAMP(18);
             if (more) gather_store();                                         // every MMA of this tile is complete: the buffer is free
             LW_STAMP(0);                                                      // gather (of the next tile)
-            for (int b = h; b < CO / 32; b += 2) {
+            for (int b = h; b < CO / 32; b += NH) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(tmem + lane_base + Cfg::lacc(Cfg::L_M2) + 32 * b, v);
@@ -463,7 +471,7 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             ebar();
         }
-    } else if (warp == LW_EPI_WARPS) {
+    } else if (warp == EW) {
         // ================= MMA issue ==================================================================================
         if (lane == 0) {
             constexpr uint64_t DESC_FIXED = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);          // SBO = 128 B
@@ -551,8 +559,8 @@ level_ws_kernel(const float* __restrict__ q, const float* __restrict__ xyz, cons
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(Cfg::T_COLS) : "memory");
 }
 
-using CfgW3 = LwCfg<128, 16, 128, 1, 5>;       // detector_3 / desc_extractor_3 (models.py:16,24)
-using CfgW2 = LwCfg<64, 32, 64, 2, 5>;         // detector_2 / desc_extractor_2 (models.py:15,23)
+using CfgW3 = LwCfg<128, 16, 128, 1, 5, LW3_EW>;       // detector_3 / desc_extractor_3 (models.py:16,24)
+using CfgW2 = LwCfg<64, 32, 64, 2, 5, 8>;         // detector_2 / desc_extractor_2 (models.py:15,23)
 
 template <class Cfg>
 int launch_level_ws(const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,
