@@ -57,6 +57,48 @@ group_weighted_sum_kernel(const float* __restrict__ a, const float* __restrict__
     }
 }
 
+// The same for C % 4 == 0 and 16-byte aligned rows: C/4 lanes per group, each with a float4 of channels (a quarter of the
+// load instructions), several groups per 128-thread CTA; narrow outputs (the 3 correspondence coordinates) go through the
+// third kernel, which packs 128 (group, channel) pairs into a CTA instead of one group per 32-thread CTA.  Per output the
+// fma chain over j is unchanged: same bits.
+__global__ void __launch_bounds__(128)
+group_weighted_sum_vec4_kernel(const float* __restrict__ a, const float* __restrict__ V, int ldV, int C4, int k,
+                               const int32_t* __restrict__ idx, int groups_per_batch, int N, float* __restrict__ out,
+                               int ldo, long long groups) {
+    const int per_cta = 128 / C4;                           // groups per CTA (C4 <= 128 divides 128)
+    const long long g = (long long)blockIdx.x * per_cta + threadIdx.x / C4;
+    const int c = threadIdx.x % C4;
+    if (g >= groups) return;
+    const long long b = g / groups_per_batch;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < k; ++j) {
+        const long long r = g * k + j;
+        const long long sr = idx ? b * N + __ldg(idx + r) : r;
+        const float w = __ldg(a + r);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(V + sr * ldV) + c);
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + g * ldo + 4 * c) = acc;
+}
+
+__global__ void __launch_bounds__(128)
+group_weighted_sum_narrow_kernel(const float* __restrict__ a, const float* __restrict__ V, int ldV, int C, int k,
+                                 const int32_t* __restrict__ idx, int groups_per_batch, int N, float* __restrict__ out,
+                                 int ldo, long long groups) {
+    const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+    const long long g = t / C;
+    const int c = (int)(t - g * C);
+    if (g >= groups) return;
+    const long long b = g / groups_per_batch;
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const long long r = g * k + j;
+        const long long sr = idx ? b * N + __ldg(idx + r) : r;
+        acc = fmaf(__ldg(a + r), __ldg(V + sr * ldV + c), acc);
+    }
+    out[g * ldo + c] = acc;
+}
+
 // Attention tail of the correspondence heads in ONE pass over the k rows of a group (layers.py:385-390, 447-450):
 //   a = softmax_k(max_c E), af[g,:] = sum_j a_j E[g*k+j,:], cor[g,:] = sum_j a_j xyz[b*N + idx[g*k+j],:]
 // The rows are read once (float4, coalesced) into shared memory while their maxima are taken; the three separate
@@ -198,6 +240,22 @@ HRN_API int hrn_group_weighted_sum(const float* a, const float* V, int ldV, int 
                                    void* stream) {
     if (!a || !V || !out || C <= 0 || k <= 0 || groups < 0) return HRN_ERR_BAD_ARG;
     if (groups == 0) return HRN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C4 = C >> 2;
+    if ((C & 3) == 0 && C4 <= 128 && 128 % C4 == 0 && (ldV & 3) == 0 && (ldo & 3) == 0 && ((uintptr_t)V & 15) == 0 &&
+        ((uintptr_t)out & 15) == 0) {
+        const int per_cta = 128 / C4;
+        group_weighted_sum_vec4_kernel<<<(unsigned)((groups + per_cta - 1) / per_cta), 128, 0, st>>>(
+            a, V, ldV, C4, k, idx, groups_per_batch, N, out, ldo, groups);
+        HRN_LAUNCH_CHECK();
+        return HRN_OK;
+    }
+    if (C <= 8) {
+        group_weighted_sum_narrow_kernel<<<(unsigned)((groups * C + 127) / 128), 128, 0, st>>>(
+            a, V, ldV, C, k, idx, groups_per_batch, N, out, ldo, groups);
+        HRN_LAUNCH_CHECK();
+        return HRN_OK;
+    }
     const int threads = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
     group_weighted_sum_kernel<<<(unsigned)groups, threads, 0, (cudaStream_t)stream>>>(a, V, ldV, C, k, idx,
                                                                                      groups_per_batch, N, out, ldo);
