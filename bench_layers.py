@@ -19,9 +19,14 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="", help="substring filter on the case name")
     ap.add_argument("--chains", action="store_true", help="time the fused chains instead of single layers")
+    ap.add_argument("--bars", action="store_true",
+                    help="library bars (BASELINE.md plan B4): cuBLAS GEMMs in fp32 / tf32 / bf16 on the conv-stack shapes and "
+                         "torch.linalg.svd on the pose solve, next to this package's kernels on the same data")
     args = ap.parse_args()
     if args.chains:
         return chains(args)
+    if args.bars:
+        return bars(args)
     from pcd_reg_hregnet_b200 import engine, engine_tc
     from pcd_reg_hregnet_b200.engine import RowsView, SEG_BROADCAST, SEG_GATHER, ACT_RELU
 
@@ -141,6 +146,91 @@ def chains(args):
         flops = 2.0 * v.rows * sum(a * b for a, b in zip([K] + widths[:-1], widths))
         print(json.dumps({"chain": name, "rows": v.rows, "K": K, "widths": widths, "us": round(us, 1),
                           "useful_tflops": round(flops / us / 1e6, 1)}))
+        sys.stdout.flush()
+
+
+def bars(args):
+    """BASELINE.md plan B4: what the vendor libraries do with the same shapes on the same B200.  GEMM bars: torch.matmul
+    (cuBLAS) on a materialised [rows, K] input (the reference materialises it; ours reads the virtual rows) in exact fp32,
+    TF32 and bf16, next to hrn_layer_tc (bf16x3, fp32-class accuracy) -- with the error of each against fp64, because the
+    1e-3 feature gate is what decides which of them may be used.  Pose bar: the reference's WeightedSVDHead arithmetic
+    (weighted covariance + torch.linalg.svd + determinant fix, layers.py:469-504) next to hrn_weighted_kabsch."""
+    from pcd_reg_hregnet_b200 import engine, engine_tc
+    from pcd_reg_hregnet_b200.engine import RowsView, ACT_NONE
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(9)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    shapes = [("coarse convs_1 528->512", 65536, 528, 512), ("coarse convs_1 512->512", 65536, 512, 512),
+              ("L3 mlp1 768->256", 262144, 768, 256), ("L3 convs 128->256", 262144, 128, 256),
+              ("L1 convs 32->64", 4194304, 32, 64)]
+    for name, rows, K, N in shapes:
+        if args.only and args.only not in name:
+            continue
+        X = torch.randn(rows, K, device=dev, generator=g)
+        W = torch.randn(N, K, device=dev, generator=g) / K ** 0.5
+        sel = torch.arange(0, rows, max(1, rows // 2048), device=dev)
+        ref = X[sel].double() @ W.double().t()
+        scale = ref.abs().max().item()
+        flop = 2.0 * rows * K * N
+        out = torch.empty(rows, N, device=dev)
+        res = {"bar": name, "rows": rows, "K": K, "N": N}
+
+        def rec(tag, us, y):
+            res[tag] = {"us": round(us, 1), "tflops": round(flop / us / 1e6, 1),
+                        "rel_err": float((y[sel].double() - ref).abs().max().item() / scale)}
+
+        torch.backends.cuda.matmul.allow_tf32 = False
+        rec("cublas_fp32", timed(lambda: torch.matmul(X, W.t(), out=out)), out)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        rec("cublas_tf32", timed(lambda: torch.matmul(X, W.t(), out=out)), out)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        Xb, Wb = X.bfloat16(), W.bfloat16()
+        outb = torch.empty(rows, N, device=dev, dtype=torch.bfloat16)
+        rec("cublas_bf16 (inputs already bf16)", timed(lambda: torch.matmul(Xb, Wb.t(), out=outb)), outb)
+        if K % 4 == 0:
+            bias = torch.zeros(N, device=dev)
+            v = RowsView(rows).add(X)
+            rec("hrn_layer_tc (bf16x3)", timed(lambda: engine_tc.layer_tc(v, W, bias, ACT_NONE, out)), out)
+        print(json.dumps(res))
+        sys.stdout.flush()
+    # pose solve: 32 pairs x 256 / 512 / 1024 correspondences
+    for n in (256, 512, 1024):
+        src = torch.randn(32, n, 3, device=dev, generator=g) * 20
+        cor = src + 0.05 * torch.randn(32, n, 3, device=dev, generator=g)
+        w = torch.rand(32, n, device=dev, generator=g)
+
+        def ref_head():
+            ww = w / (w.sum(1, keepdim=True) + 1e-4)
+            sc = (src * ww[..., None]).sum(1, keepdim=True)
+            cc = (cor * ww[..., None]).sum(1, keepdim=True)
+            H = ((src - sc) * ww[..., None]).transpose(1, 2) @ (cor - cc)
+            U, _, Vh = torch.linalg.svd(H)
+            V = Vh.transpose(1, 2)
+            d = torch.det(V @ U.transpose(1, 2))
+            D = torch.diag_embed(torch.stack([torch.ones_like(d), torch.ones_like(d), d], 1))
+            R = V @ D @ U.transpose(1, 2)
+            return R, cc.squeeze(1) - (R @ sc.transpose(1, 2)).squeeze(2)
+
+        print(json.dumps({"bar": f"pose solve, 32 pairs x {n} correspondences",
+                          "torch (weighted covariance + linalg.svd + det fix, eager)": {"us": round(timed(ref_head), 1)},
+                          "hrn_weighted_kabsch": {"us": round(timed(lambda: engine.weighted_kabsch(src, cor, w)), 1)}}))
         sys.stdout.flush()
 
 

@@ -165,6 +165,34 @@ def test_group_attend_equals_separate_kernels():
     assert torch.equal(a, a2) and torch.equal(af, af2) and torch.equal(cor, cor2)
 
 
+def test_group_weighted_sum_kernel_variants_agree():
+    """hrn_group_weighted_sum picks one of three kernels by shape and alignment (float4 lanes with several groups per CTA,
+    128 narrow outputs per CTA, one group per CTA): the same fma chain over the k rows in each -- bit-identical results --
+    and all of them within fp32 rounding of the fp64 sum.  Odd group counts exercise the tail guards."""
+    from pcd_reg_hregnet_b200.engine import call, ptr, stream
+    g = torch.Generator(device=DEV).manual_seed(11)
+    B, N1, N2, k = 3, 37, 50, 8
+    a = torch.rand(B * N1 * k, device=DEV, generator=g)
+    idx = torch.randint(0, N2, (B, N1, k), device=DEV, generator=g, dtype=torch.int32)
+    for C in (256, 64, 12, 4, 3):
+        Vpad = torch.randn(B * N2, C + 1, device=DEV, generator=g)
+        V_un = Vpad[:, :C]                        # row pitch C + 1: unaligned rows -> the one-group-per-CTA kernel (C > 8)
+        V_al = V_un.contiguous()                  # aligned rows -> float4 lanes (C % 4 == 0) / narrow kernel (C <= 8)
+        got_al = engine.group_weighted_sum(a, V_al, k, idx=idx, groups_per_batch=N1, N=N2)
+        got_un = torch.empty_like(got_al)         # through the C ABI: the first C columns of the padded matrix
+        call("hrn_group_weighted_sum", ptr(a), ptr(Vpad), Vpad.stride(0), C, B * N1, k, ptr(idx), N1, N2, ptr(got_un),
+             got_un.stride(0), stream())
+        assert torch.equal(got_al, got_un), C
+        rows = (torch.arange(B * N1, device=DEV) // N1)[:, None] * N2 + idx.view(B * N1, k).long()
+        want = (a.view(-1, k, 1).double() * V_al.double()[rows]).sum(1)
+        assert float((got_al.double() - want).abs().max()) < 1e-5, C
+        # direct rows (no index)
+        R = torch.randn(B * N1 * k, C, device=DEV, generator=g)
+        got = engine.group_weighted_sum(a, R, k)
+        want = (a.view(-1, k, 1).double() * R.double().view(-1, k, C)).sum(1)
+        assert float((got.double() - want).abs().max()) < 1e-5, C
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # round 2: pose cascade on the reference's own correspondences, the BASELINE configs[1] shape, the layer-class API
 # ------------------------------------------------------------------------------------------------------------------
