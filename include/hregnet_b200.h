@@ -211,7 +211,10 @@ int hrn_level_bias_count(int level);
  * layer's MMAs are issued block by block while the current accumulator is still being drained, and the reference's
  * repeated max_k(X1) input of mlp1 (layers.py:203-205) enters as a per-keypoint bias evaluated once per keypoint in fp32.
  *   Wpack (hrn_level_ws_pack_bytes(level) bytes), WaT [2C, C] fp32 and biases (hrn_level_ws_bias_count(level) floats)
- *   as laid out by pcd_reg_hregnet_b200/engine_tc.pack_level_ws.  Arguments and outputs as hrn_level_fused. */
+ *   as laid out by pcd_reg_hregnet_b200/engine_tc.pack_level_ws: the biases of the conv stacks and of mlp2 travel INSIDE Wpack
+ *   (d1 / x1 as the weight column of a constant-1 input channel, d2 x2 d3 x3 mlp2 as one bias piece in front of the layer's
+ *   K=16 pieces -- one extra MMA against a block of ones); of `biases` only mlp1's entries are read.  Arguments and outputs
+ *   as hrn_level_fused. */
 int hrn_level_ws(int level, const float* q, const float* xyz, const float* feat, const int32_t* idx, const void* Wpack,
                  const float* WaT, const float* biases, float* out_xyz, float* out_af, float* out_desc, int B, int M,
                  int N, int k, void* stream);
