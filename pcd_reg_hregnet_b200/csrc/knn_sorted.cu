@@ -206,9 +206,16 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
                    const float4* __restrict__ pts, const float* __restrict__ boxes, float* __restrict__ out_d,
                    int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn,
                    float* __restrict__ out_q, int M, int N, int N2, int K) {
-    extern __shared__ float s_box[];                        // [nbox][6]
+    extern __shared__ float s_box[];                        // [nbox][6], then (BPL >= 4) [QWARPS][BPL * 32] box bounds
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbox = N2 >> 5;
+    // Large clouds keep the per-query box bounds in shared memory, entry g * 32 + lane of the warp's row (a lane only ever
+    // touches its own column): with them in BPL registers every loop over them is unrolled BPL times, the sweep with its
+    // inlined insertion code included -- 3.5 K instructions at 16 boxes per lane, and 20 % of the level-1 search's stall
+    // samples were instruction fetches (profiles/r02zz_ncu_knn3_search_l1.txt).  As run-time loops the body exists once,
+    // and 16 registers per thread go back to the occupancy.
+    constexpr bool SBD = BPL >= 4;
+    float* sbd = s_box + nbox * 6 + warp * (BPL * 32) + lane;
     const float* bsrc = boxes + (size_t)b * nbox * 6;
     for (int i = threadIdx.x; i < nbox * 6; i += blockDim.x) s_box[i] = bsrc[i];
     __syncthreads();
@@ -221,33 +228,47 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
     if (out_q && lane < 3) out_q[((size_t)b * M + m) * 3 + lane] = q[lane];
 
     // lower bound of the squared distance to every box (same operation order as the point distance)
-    float bd[BPL];
-#pragma unroll
-    for (int g = 0; g < BPL; ++g) {
-        const int bx = g * 32 + lane;
-        bd[g] = CUDART_NAN_F;                               // NaN = "never open": out of range or already visited
+    auto box_bound = [&](int bx) -> float {
+        float v = CUDART_NAN_F;                             // NaN = "never open": out of range or already visited
         if (bx < nbox) {
             const float* o = s_box + bx * 6;
             const float dx = fmaxf(fmaxf(o[0] - qx, qx - o[3]), 0.f);
             const float dy = fmaxf(fmaxf(o[1] - qy, qy - o[4]), 0.f);
             const float dz = fmaxf(fmaxf(o[2] - qz, qz - o[5]), 0.f);
-            bd[g] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            v = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
         }
+        return v;
+    };
+    float bd[SBD ? 1 : BPL];
+    if (SBD) {
+#pragma unroll 1
+        for (int g = 0; g < BPL; ++g) sbd[g * 32] = box_bound(g * 32 + lane);
+    } else {
+#pragma unroll
+        for (int g = 0; g < BPL; ++g) bd[g] = box_bound(g * 32 + lane);
     }
     WarpSet<KPL> top;
     // pick the box with the smallest bound among the not yet visited ones (warp-uniform result, -1 = none left)
     auto closest_box = [&]() -> int {
         float best = CUDART_INF_F; int bg = 0;
+        if (SBD) {
+#pragma unroll 4
+            for (int g = 0; g < BPL; ++g) { const float v = sbd[g * 32]; if (v < best) { best = v; bg = g; } }
+        } else {
 #pragma unroll
-        for (int g = 0; g < BPL; ++g) if (bd[g] < best) { best = bd[g]; bg = g; }
+            for (int g = 0; g < BPL; ++g) if (bd[g] < best) { best = bd[g]; bg = g; }
+        }
         const unsigned ob = hrn_ford(best);
         const unsigned wmin = __reduce_min_sync(0xffffffffu, ob);
         if (wmin == hrn_ford(CUDART_INF_F)) return -1;
         const int src = __ffs(__ballot_sync(0xffffffffu, ob == wmin)) - 1;
         const int g_sel = __shfl_sync(0xffffffffu, bg, src);
         if (lane == src) {
+            if (SBD) sbd[g_sel * 32] = CUDART_NAN_F;        // visited
+            else {
 #pragma unroll
-            for (int g = 0; g < BPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;   // visited
+                for (int g = 0; g < BPL; ++g) if (g == g_sel) bd[g] = CUDART_NAN_F;
+            }
         }
         return g_sel * 32 + src;
     };
@@ -290,15 +311,26 @@ knn3_sorted_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_i
         }
     }
     // sweep: every box whose bound can still beat the K-th candidate
-#pragma unroll
-    for (int g = 0; g < BPL; ++g) {
-        if (g * 32 >= nbox) break;
-        unsigned mask = __ballot_sync(0xffffffffu, bd[g] <= top.thr_d);
+    auto sweep_chunk = [&](int g, float v) {
+        unsigned mask = __ballot_sync(0xffffffffu, v <= top.thr_d);
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
-            const float bnd = __shfl_sync(0xffffffffu, bd[g], src);
+            const float bnd = __shfl_sync(0xffffffffu, v, src);
             if (bnd <= top.thr_d) open_box(g * 32 + src);
+        }
+    };
+    if (SBD) {
+#pragma unroll 1
+        for (int g = 0; g < BPL; ++g) {
+            if (g * 32 >= nbox) break;
+            sweep_chunk(g, sbd[g * 32]);
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < BPL; ++g) {
+            if (g * 32 >= nbox) break;
+            sweep_chunk(g, bd[g]);
         }
     }
     top.sort_set(lane);                                     // dummies (-1, -1) sort first
@@ -370,10 +402,18 @@ HRN_API int hrn_knn3_search(const float* p1, const int32_t* q_idx, const float* 
     const int N2 = knn3_pow2(N);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(hrn_divup(M, QWARPS), B);
-    const size_t bsm = (size_t)(N2 / 32) * 6 * sizeof(float);
+    const size_t bsm0 = (size_t)(N2 / 32) * 6 * sizeof(float);
+    static hrn_once_per_device attr32;
+    if (N2 > 16384 && attr32.need()) {                       // 24 KB of boxes + 32 KB of bounds
+        HRN_CUDA(cudaFuncSetAttribute(knn3_sorted_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        HRN_CUDA(cudaFuncSetAttribute(knn3_sorted_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    }
 #define HRN_KNN3_LAUNCH(KPL, BPL)                                                                                     \
-    knn3_sorted_kernel<KPL, BPL><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts, sorted_boxes, \
-                                                                 dists, idx64, idx32, nn, q_out, M, N, N2, K)
+    do {                                                                                                              \
+        const size_t bsm = bsm0 + ((BPL) >= 4 ? (size_t)QWARPS * (BPL) * 32 * sizeof(float) : 0);                      \
+        knn3_sorted_kernel<KPL, BPL><<<grid, QWARPS * 32, bsm, st>>>(p1, q_idx, p2, (const float4*)sorted_pts,          \
+                                                                     sorted_boxes, dists, idx64, idx32, nn, q_out, M, N, N2, K); \
+    } while (0)
     if (K <= 32) {
         if (N2 <= 1024) HRN_KNN3_LAUNCH(1, 1);
         else if (N2 <= 4096) HRN_KNN3_LAUNCH(1, 4);
