@@ -497,18 +497,20 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
         int my_tiles = 0;
         if ((int)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
         const int total = my_tiles * n_st0;
-        if (total > 0) resolve(ltile);
-#pragma unroll
-        for (int d = 0; d < RAW; ++d) issue(d, sc[d]);
         int filled = 0;                                      // stages delivered: a tile's Z blocks follow its last stage
-        for (int q = 0; q < total; q += RAW) {
-#pragma unroll
-            for (int d = 0; d < RAW; ++d) {
-                if (q + d < total) {
-                    fill(d, sc[d]); issue(d, sc[d]);
-                    if (++filled % n_st0 == 0 && has_z) z_blocks((int)blockIdx.x + (filled / n_st0 - 1) * (int)gridDim.x);
-                }
+        if (total > 0) resolve(ltile);
+        // One copy of the stage code: unrolled over the RAW slots (prologue + main loop) it was 8 K of the kernel's 14 K
+        // instructions, the warps of the four roles run different regions of it at the same time, and ncu showed 12 % of
+        // the big chains' stall samples (27 % of the 50 us heads') on instruction fetches.  A slot's four row scales go
+        // through local memory instead of registers (sc[d] with a run-time d).
+#pragma unroll 1
+        for (int d = -RAW; d < total; ++d) {
+            const int slot = (d + RAW) % RAW;
+            if (d >= 0) {
+                fill(slot, sc[slot]);
+                if (++filled % n_st0 == 0 && has_z) z_blocks((int)blockIdx.x + (filled / n_st0 - 1) * (int)gridDim.x);
             }
+            issue(slot, sc[slot]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == CW_EPI_WARPS + CW_PROD_WARPS) {
