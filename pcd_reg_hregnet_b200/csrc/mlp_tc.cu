@@ -518,13 +518,13 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         if ((int)blockIdx.x < n_items) my_items = (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
         const int total = my_items * n_stage;
         if (total > 0) resolve(lit);
-#pragma unroll
-        for (int d = 0; d < WS_RAW; ++d) issue(d, sc[d]);
-        for (int q = 0; q < total; q += WS_RAW) {
-#pragma unroll
-            for (int d = 0; d < WS_RAW; ++d) {
-                if (q + d < total) { fill(d, sc[d]); issue(d, sc[d]); }
-            }
+        // one copy of the stage code (run-time slot; unrolled over the raw ring, prologue + main loop, it dominated the
+        // kernel's instruction footprint -- see chain_tc.cu)
+#pragma unroll 1
+        for (int d = -WS_RAW; d < total; ++d) {
+            const int slot = (d + WS_RAW) % WS_RAW;
+            if (d >= 0) fill(slot, sc[slot]);
+            issue(slot, sc[slot]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == WS_EPI_WARPS + WS_PROD_WARPS) {
