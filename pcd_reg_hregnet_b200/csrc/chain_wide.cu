@@ -478,17 +478,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
         if (tile0 < n_tiles) my_tiles = (n_tiles - 1 - tile0) / tstride + 1;
         const int total = my_tiles * n_st0;
         if (total > 0) resolve(ltile);
-#pragma unroll
-        for (int d = 0; d < RAW; ++d) issue(d, sc[d]);
         int filled = 0;                                      // stages delivered: a tile's Z blocks follow its last stage
-        for (int q = 0; q < total; q += RAW) {
-#pragma unroll
-            for (int d = 0; d < RAW; ++d) {
-                if (q + d < total) {
-                    fill(d, sc[d]); issue(d, sc[d]);
-                    if (++filled % n_st0 == 0 && has_z) z_blocks(tile0 + (filled / n_st0 - 1) * tstride);
-                }
+        // one copy of the stage code (run-time slot instead of prologue + main loop unrolled over the raw ring, see chain_tc.cu)
+#pragma unroll 1
+        for (int d = -RAW; d < total; ++d) {
+            const int slot = (d + RAW) % RAW;
+            if (d >= 0) {
+                fill(slot, sc[slot]);
+                if (++filled % n_st0 == 0 && has_z) z_blocks(tile0 + (filled / n_st0 - 1) * tstride);
             }
+            issue(slot, sc[slot]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == WW_EPI_WARPS + WW_PROD_WARPS) {
