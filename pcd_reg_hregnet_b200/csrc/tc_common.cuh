@@ -77,11 +77,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-    if (act == HRN_ACT_RELU) return fmaxf(v, 0.f);
+// The two transcendental activations (sigma heads: softplus + eps, confidence heads: sigmoid) are ONE out-of-line copy: inlined
+// into loops unrolled over the 32 columns of an accumulator block they were ~2 K instructions per kernel, and the short head
+// launches stalled on instruction fetches (ncu: no_inst).  Same arithmetic, same bits.
+static __device__ __noinline__ float act_fn_slow(float v, int act) {
     if (act == HRN_ACT_SOFTPLUS_EPS) return (v > 20.f ? v : log1pf(expf(v))) + 0.001f;
     if (act == HRN_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
+}
+__device__ __forceinline__ float act_fn(float v, int act) {
+    if (act == HRN_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == HRN_ACT_NONE) return v;
+    return act_fn_slow(v, act);
 }
 
 // bf16 hi / lo split of a pair: hi = rn_bf16(x) packed, lo = rn_bf16(x - float(hi)) packed; the two residuals are taken
