@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
         float rsc[2][4];
         float sc[RAW][4];
         int ltile = blockIdx.x, li = 0;                      // copy cursor: tile, stage within the tile
+        bool need_resolve = false;                           // the rows of tile `ltile` have to be resolved before its first copy
         int gs = 0; uint32_t gpar = 0;                       // ring G position
         uint8_t* raw0 = sRaw + (size_t)(pw * 4) * 512 + lane * 16;
         auto resolve = [&](int tile) {
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
                         copy_piece(rp[g], rsc[g], li * 4 + 2 * j + cl, raw0 + (size_t)slot * CW_STAGE_BYTES + (g * 2 + j) * 512, ss[2 * g + j]);
                 if (++li == n_st0) {
                     li = 0; ltile += gridDim.x;
-                    if (ltile < n_tiles) resolve(ltile);
+                    need_resolve = ltile < n_tiles;      // done at the top of the stage loop: ONE inlined copy of resolve()
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
         if ((int)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
         const int total = my_tiles * n_st0;
         int filled = 0;                                      // stages delivered: a tile's Z blocks follow its last stage
-        if (total > 0) resolve(ltile);
+        need_resolve = total > 0;
         // One copy of the stage code: unrolled over the RAW slots (prologue + main loop) it was 8 K of the kernel's 14 K
         // instructions, the warps of the four roles run different regions of it at the same time, and ncu showed 12 % of
         // the big chains' stall samples (27 % of the 50 us heads') on instruction fetches.  A slot's four row scales go
@@ -506,6 +507,8 @@ __global__ void __launch_bounds__(CW_THREADS, 1) chain_ws_kernel(const ChainWsAr
 #pragma unroll 1
         for (int d = -RAW; d < total; ++d) {
             const int slot = (d + RAW) % RAW;
+            // the next tile's index / scale loads are issued here, in front of the wait inside fill()
+            if (need_resolve) { resolve(ltile); need_resolve = false; }
             if (d >= 0) {
                 fill(slot, sc[slot]);
                 if (++filled % n_st0 == 0 && has_z) z_blocks((int)blockIdx.x + (filled / n_st0 - 1) * (int)gridDim.x);

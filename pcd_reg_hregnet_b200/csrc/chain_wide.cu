@@ -363,6 +363,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
         float rsc[2][4];
         float sc[RAW][4];
         int ltile = tile0, li = 0;                           // copy cursor: tile, stage within the tile
+        bool need_resolve = false;                           // the rows of tile `ltile` have to be resolved before its first copy
         int gs = 0; uint32_t gpar = 0;                       // ring G position
         uint8_t* raw0 = sRaw + (size_t)(pw * 4) * 512 + lane * 16;
         auto resolve = [&](int tile) {
@@ -407,7 +408,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
                         copy_piece(rp[g], rsc[g], li * 4 + 2 * j + cl, raw0 + (size_t)slot * WW_STAGE_BYTES + (g * 2 + j) * 512, ss[2 * g + j]);
                 if (++li == n_st0) {
                     li = 0; ltile += tstride;
-                    if (ltile < n_tiles) resolve(ltile);
+                    need_resolve = ltile < n_tiles;      // done at the top of the stage loop: ONE inlined copy of resolve()
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -477,12 +478,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WW_THREADS, 1) chain
         int my_tiles = 0;
         if (tile0 < n_tiles) my_tiles = (n_tiles - 1 - tile0) / tstride + 1;
         const int total = my_tiles * n_st0;
-        if (total > 0) resolve(ltile);
+        need_resolve = total > 0;
         int filled = 0;                                      // stages delivered: a tile's Z blocks follow its last stage
         // one copy of the stage code (run-time slot instead of prologue + main loop unrolled over the raw ring, see chain_tc.cu)
 #pragma unroll 1
         for (int d = -RAW; d < total; ++d) {
             const int slot = (d + RAW) % RAW;
+            if (need_resolve) { resolve(ltile); need_resolve = false; }    // index / scale loads in front of the wait inside fill()
             if (d >= 0) {
                 fill(slot, sc[slot]);
                 if (++filled % n_st0 == 0 && has_z) z_blocks(tile0 + (filled / n_st0 - 1) * tstride);

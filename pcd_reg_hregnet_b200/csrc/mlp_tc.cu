@@ -412,6 +412,7 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         int st = 0; uint32_t par = 0;                          // ring position of the next stage to fill
         float sc[WS_RAW][4];                                   // per-piece row scale of the stages in flight
         int lit = blockIdx.x, li = 0;                          // copy cursor: item, stage within the item
+        bool need_resolve = false;                             // the rows of item `lit` have to be resolved before its first copy
         uint8_t* raw0 = smem + (size_t)S * stage_bytes + WS_TILE_BYTES + (size_t)(pw * 4) * 512 + lane * 16;
         const bool small = rows < 0x7fffffffLL;
         auto resolve = [&](int it) {
@@ -474,7 +475,7 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
                         copy_piece(rp[g], rsc[g], li * 4 + 2 * j + cl, raw0 + (size_t)slot * A_STAGE_BYTES + (g * 2 + j) * 512, ss[2 * g + j]);
                 if (++li == n_stage) {
                     li = 0; lit += gridDim.x;
-                    if (lit < n_items) resolve(lit);
+                    need_resolve = lit < n_items;        // done at the top of the stage loop: ONE inlined copy of resolve()
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -517,12 +518,13 @@ layer_ws_kernel(const hrn_rows_t in, const __nv_bfloat16* __restrict__ Wp, const
         int my_items = 0;
         if ((int)blockIdx.x < n_items) my_items = (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
         const int total = my_items * n_stage;
-        if (total > 0) resolve(lit);
+        need_resolve = total > 0;
         // one copy of the stage code (run-time slot; unrolled over the raw ring, prologue + main loop, it dominated the
         // kernel's instruction footprint -- see chain_tc.cu)
 #pragma unroll 1
         for (int d = -WS_RAW; d < total; ++d) {
             const int slot = (d + WS_RAW) % WS_RAW;
+            if (need_resolve) { resolve(lit); need_resolve = false; }      // index / scale loads in front of the wait inside fill()
             if (d >= 0) fill(slot, sc[slot]);
             issue(slot, sc[slot]);
         }
