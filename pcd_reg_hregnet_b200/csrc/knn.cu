@@ -78,88 +78,138 @@ knn3_kernel(const float* __restrict__ p1, const int32_t* __restrict__ q_idx, con
 
 // Generic D (descriptor space, D = 256 in CoarseReg).  Sequential fma chain over d per (query, ref) pair, so the
 // distances are bit-identical to the oracle; register-tiled: a CTA owns 32 queries, a warp 4 of them, a lane 4
-// references of the current 128-reference tile -> 16 independent accumulators per thread, 8 shared-memory loads per
-// 16 FMAs.  8 warps per CTA: with 4 warps x 8 queries the coarse-level search (32 pairs x 256 x 256 x 256) put fewer
-// than two warps on a scheduler and ran at the dependent-issue latency of a single warp (175 us, ncu: 33 % issue).  References stream through shared memory in [128 refs] x [64 dims] slices (padded rows: conflict-free),
-// double-buffered with cp.async.
+// references of the current 128-reference tile -> 16 independent accumulators per thread.  8 warps per CTA: with 4 warps
+// x 8 queries the coarse-level search (32 pairs x 256 x 256 x 256) put fewer than two warps on a scheduler and ran at the
+// dependent-issue latency of a single warp (175 us, ncu: 33 % issue).  References stream through shared memory in
+// [128 refs] x [64 dims] slices, double-buffered with 16-byte cp.async (4-byte copies when D or the base address is not
+// 16-byte aligned).  The accumulators are fp32x2 pairs over two QUERIES of the warp: the queries are stored
+// pair-interleaved ([pair][d][2]), so one broadcast 16-byte load hands every lane two ready-made fp32x2 operands, a
+// lane's reference values come four dims at a time (rows of 68 words: conflict-free for 16-byte loads) and enter
+// FADD2 as the scalar-broadcast operand: a chunk of 4 dims costs 4 + 4 LDS.128 for 64 packed instructions (the scalar
+// version: 32 LDS, each right in front of its first use, and 4-byte cp.async only).  (r - q)^2 == (q - r)^2 exactly.
+// Dims beyond D are zero on both sides (padded query rows, zero-filled slices): fma(0, 0, acc) = acc, so whole chunks
+// of 4 stay bit-exact.
 constexpr int KD_Q = 32;         // queries per CTA
 constexpr int KD_R = 128;        // references per tile
 constexpr int KD_D = 64;         // dims per slice
 constexpr int KD_WARPS = 8;      // warps per CTA
 constexpr int KD_QW = KD_Q / KD_WARPS;   // queries per warp
+constexpr int KD_LD = KD_D + 4;          // words per reference row of a slice
+constexpr int KD_RBUF = KD_R * KD_LD;    // words per slice buffer
+static_assert(KD_QW == 4, "two query pairs per warp");
 template <int KPL>
 __global__ void __launch_bounds__(KD_WARPS * 32)
 knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* __restrict__ out_d,
             int64_t* __restrict__ out_i64, int32_t* __restrict__ out_i32, float* __restrict__ out_nn, int M, int N,
-            int D, int K) {
-    extern __shared__ float smem[];
-    float* s_q = smem;                          // [KD_Q][D]
-    float* s_r = smem + KD_Q * D;               // [KD_R][KD_D + 1]
+            int D, int K, int vec16) {
+    extern __shared__ __align__(16) float smem[];
+    const int Dp = (D + 3) & ~3;                // query rows padded to whole chunks
+    float* s_q = smem;                          // [KD_Q / 2 pairs][Dp][2]
+    float* s_r = smem + KD_Q * Dp;              // 2 x [KD_R][KD_LD]
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * KD_Q;
     p1 += (size_t)b * M * D;
     p2 += (size_t)b * N * D;
-    for (int i = threadIdx.x; i < KD_Q * D; i += blockDim.x) {
-        const int q = i / D;
-        s_q[i] = (m0 + q < M) ? p1[(size_t)(m0 + q) * D + (i - q * D)] : 0.f;
+    for (int i = threadIdx.x; i < KD_Q * Dp; i += blockDim.x) {
+        const int q = i / Dp, d = i - q * Dp;
+        s_q[((q >> 1) * Dp + d) * 2 + (q & 1)] = (m0 + q < M && d < D) ? p1[(size_t)(m0 + q) * D + d] : 0.f;
     }
     WarpSet<KPL> top[KD_QW];
 #pragma unroll
     for (int q = 0; q < KD_QW; ++q) top[q].init_empty(K, lane);
-    constexpr int LDR = KD_D + 1;
-    // reference slices [128 refs] x [64 dims] are double-buffered with 4-byte cp.async (the padded rows that make the
-    // column reads conflict-free are not 16-byte aligned): slice s+1 is in flight while slice s is consumed
+    // reference slices [128 refs] x [64 dims]: slice s+1 is in flight while slice s is consumed; missing references /
+    // dims are zero-filled
     const int n_dslice = (D + KD_D - 1) / KD_D;
     const int n_slice = ((N + KD_R - 1) / KD_R) * n_dslice;
     auto fill = [&](int sl, int buf) {
         const int t0s = (sl / n_dslice) * KD_R, d0s = (sl % n_dslice) * KD_D;
-        float* dst = s_r + buf * (KD_R * LDR);
-        for (int i = threadIdx.x; i < KD_R * KD_D; i += blockDim.x) {
-            const int rr = i / KD_D, dd = i - rr * KD_D;
-            const bool ok = t0s + rr < N && d0s + dd < D;
-            const float* src = ok ? p2 + (size_t)(t0s + rr) * D + d0s + dd : p2;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + rr * LDR + dd)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        float* dst = s_r + buf * KD_RBUF;
+        if (vec16) {
+            for (int i = threadIdx.x; i < KD_R * (KD_D / 4); i += blockDim.x) {
+                const int rr = i / (KD_D / 4), dd = (i - rr * (KD_D / 4)) * 4;
+                const int nb = (t0s + rr < N) ? max(0, min(4, D - d0s - dd)) * 4 : 0;
+                const float* src = nb ? p2 + (size_t)(t0s + rr) * D + d0s + dd : p2;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + rr * KD_LD + dd)), "l"(src), "r"(nb) : "memory");
+            }
+        } else {
+            for (int i = threadIdx.x; i < KD_R * KD_D; i += blockDim.x) {
+                const int rr = i / KD_D, dd = i - rr * KD_D;
+                const bool ok = t0s + rr < N && d0s + dd < D;
+                const float* src = ok ? p2 + (size_t)(t0s + rr) * D + d0s + dd : p2;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + rr * KD_LD + dd)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     fill(0, 0);
     int sl = 0;
     for (int t0 = 0; t0 < N; t0 += KD_R) {
-        // accumulators of references (lane, lane+32) and (lane+64, lane+96) packed as fp32x2: FADD2 / FFMA2 round each
-        // half like the scalar instructions, so the sequential chain over d stays bit-identical to the oracle
-        f32x2_t acc[KD_QW][2];
+        // acc[qp][j]: queries (2 qp, 2 qp + 1) of the warp x reference lane + 32 j, packed as fp32x2: FADD2 / FFMA2
+        // round each half like the scalar instructions, so the sequential chain over d stays bit-identical to the oracle
+        f32x2_t acc[2][4];
 #pragma unroll
-        for (int q = 0; q < KD_QW; ++q) { acc[q][0] = f2_pack(0.f, 0.f); acc[q][1] = acc[q][0]; }
+        for (int qp = 0; qp < 2; ++qp)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[qp][j] = f2_pack(0.f, 0.f);
         for (int d0 = 0; d0 < D; d0 += KD_D, ++sl) {
-            const int dn = min(KD_D, D - d0);
+            const int n4 = (min(KD_D, D - d0) + 3) >> 2;       // chunks of 4 dims in this slice
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();                                   // slice sl visible; everybody is done with slice sl-1
             if (sl + 1 < n_slice) fill(sl + 1, (sl + 1) & 1);
-            const float* sr = s_r + (sl & 1) * (KD_R * LDR);
-            const float* qb = s_q + (warp * KD_QW) * D + d0;
-            for (int d = 0; d < dn; ++d) {
-                const f32x2_t r01 = f2_pack(sr[lane * LDR + d], sr[(lane + 32) * LDR + d]);
-                const f32x2_t r23 = f2_pack(sr[(lane + 64) * LDR + d], sr[(lane + 96) * LDR + d]);
+            const float* sr = s_r + (sl & 1) * KD_RBUF + lane * KD_LD;
+            const float* qb = s_q + ((warp * 2) * Dp + d0) * 2;
+            float4 R[4], Qv[2][2];
 #pragma unroll
-                for (int q = 0; q < KD_QW; ++q) {
-                    const float qv = qb[q * D + d];
-                    const f32x2_t q2 = f2_pack(qv, qv);
-                    const f32x2_t e0 = f2_sub(q2, r01), e1 = f2_sub(q2, r23);
-                    acc[q][0] = f2_fma(e0, e0, acc[q][0]);
-                    acc[q][1] = f2_fma(e1, e1, acc[q][1]);
+            for (int j = 0; j < 4; ++j) R[j] = *reinterpret_cast<const float4*>(sr + 32 * j * KD_LD);
+#pragma unroll
+            for (int qp = 0; qp < 2; ++qp)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) Qv[qp][h] = *reinterpret_cast<const float4*>(qb + qp * Dp * 2 + 4 * h);
+#pragma unroll 2
+            for (int c = 0; c < n4; ++c) {
+                const int cn = min(c + 1, n4 - 1);             // next chunk's operands in flight under this chunk's math
+                float4 nR[4], nQ[2][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nR[j] = *reinterpret_cast<const float4*>(sr + 32 * j * KD_LD + 4 * cn);
+#pragma unroll
+                for (int qp = 0; qp < 2; ++qp)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        nQ[qp][h] = *reinterpret_cast<const float4*>(qb + qp * Dp * 2 + 8 * cn + 4 * h);
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd) {               // dims 4c .. 4c+3, in order
+#pragma unroll
+                    for (int qp = 0; qp < 2; ++qp) {
+                        const float4 qq = Qv[qp][dd >> 1];
+                        const f32x2_t q2 = (dd & 1) ? f2_pack(qq.z, qq.w) : f2_pack(qq.x, qq.y);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float rv = dd == 0 ? R[j].x : dd == 1 ? R[j].y : dd == 2 ? R[j].z : R[j].w;
+                            const f32x2_t e = f2_sub(f2_pack(rv, rv), q2);
+                            acc[qp][j] = f2_fma(e, e, acc[qp][j]);
+                        }
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) R[j] = nR[j];
+#pragma unroll
+                for (int qp = 0; qp < 2; ++qp)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) Qv[qp][h] = nQ[qp][h];
             }
         }
+        float a[KD_QW][4];
+#pragma unroll
+        for (int qp = 0; qp < 2; ++qp)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f2_unpack(acc[qp][j], a[2 * qp][j], a[2 * qp + 1][j]);
 #pragma unroll
         for (int q = 0; q < KD_QW; ++q) {
             if (m0 + warp * KD_QW + q < M) {
-                float a[4];
-                f2_unpack(acc[q][0], a[0], a[1]);
-                f2_unpack(acc[q][1], a[2], a[3]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = t0 + lane + 32 * j;
-                    top[q].offer(n < N ? a[j] : CUDART_INF_F, n < N ? n : 0x7fffffff);
+                    top[q].offer(n < N ? a[q][j] : CUDART_INF_F, n < N ? n : 0x7fffffff);
                 }
             }
         }
@@ -208,15 +258,16 @@ HRN_API int hrn_knn(const float* p1, const int32_t* q_idx, const float* p2, int 
         if (K <= 32) knn3_kernel<1><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
         else knn3_kernel<2><<<grid, KNN_WARPS * 32, 0, st>>>(p1, q_idx, p2, dists, idx64, idx32, nn, q_out, M, N, K);
     } else {
-        const size_t smem = ((size_t)KD_Q * D + 2 * (size_t)KD_R * (KD_D + 1)) * sizeof(float);
+        const size_t smem = ((size_t)KD_Q * ((D + 3) & ~3) + 2 * (size_t)KD_RBUF) * sizeof(float);
+        const int vec16 = (D % 4 == 0) && ((uintptr_t)p2 % 16 == 0);
         if (smem > 200 * 1024) return HRN_ERR_UNSUPPORTED;
         dim3 gridd(hrn_divup(M, KD_Q), B);
         if (K <= 32) {
             if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnd_kernel<1><<<gridd, KD_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+            knnd_kernel<1><<<gridd, KD_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K, vec16);
         } else {
             if (smem > 48 * 1024) HRN_CUDA(cudaFuncSetAttribute(knnd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnd_kernel<2><<<gridd, KD_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K);
+            knnd_kernel<2><<<gridd, KD_WARPS * 32, smem, st>>>(p1, p2, dists, idx64, idx32, nn, M, N, D, K, vec16);
         }
     }
     HRN_LAUNCH_CHECK();
