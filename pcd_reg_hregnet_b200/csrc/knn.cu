@@ -110,13 +110,23 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
     const int m0 = blockIdx.x * KD_Q;
     p1 += (size_t)b * M * D;
     p2 += (size_t)b * N * D;
-    for (int i = threadIdx.x; i < KD_Q * Dp; i += blockDim.x) {
-        const int q = i / Dp, d = i - q * Dp;
-        s_q[((q >> 1) * Dp + d) * 2 + (q & 1)] = (m0 + q < M && d < D) ? p1[(size_t)(m0 + q) * D + d] : 0.f;
-    }
     WarpSet<KPL> top[KD_QW];
 #pragma unroll
     for (int q = 0; q < KD_QW; ++q) top[q].init_empty(K, lane);
+    // Small searches (K <= 16 of N <= 512 references, the CoarseReg shape: 8 of 256): the running top-K of a query is
+    // kept SORTED (rank r in lane 32 - K + r) and merged with a tile's 128 distances by K rounds of "extract the
+    // minimum" (two REDUX + a rescan of the winner lane's five candidates per round) instead of one replace-the-maximum
+    // per candidate below the threshold: K (1 + ln(N / K)) ~ 34 replacements of ~60 instructions per query were 60 % of
+    // the kernel's instructions at that shape (ncu).  Same total order (distance bits, index), same "empty" members
+    // (+inf, 0x7fffffff - pos), NaN distances never selected -> the same set in the same order as the WarpSet path.
+    constexpr int XS_TAKEN = 0x7fffffff;
+    const bool xsel = (KPL == 1) && K <= 16 && N <= 512;
+    int car_k[KD_QW], car_i[KD_QW];
+#pragma unroll
+    for (int q = 0; q < KD_QW; ++q) {
+        car_k[q] = lane >= 32 - K ? 0x7f800000 : XS_TAKEN;
+        car_i[q] = lane >= 32 - K ? 0x7fffffff - (31 - lane) : 0x7fffffff;
+    }
     // reference slices [128 refs] x [64 dims]: slice s+1 is in flight while slice s is consumed; missing references /
     // dims are zero-filled
     const int n_dslice = (D + KD_D - 1) / KD_D;
@@ -142,6 +152,32 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     fill(0, 0);
+    // queries of the CTA, pair-interleaved; 16-byte loads, all of a thread's loads in flight before its stores
+    if (vec16 && ((uintptr_t)p1 & 15) == 0) {
+        const int dq = Dp >> 2, nq4 = KD_Q * dq;
+        for (int base = 0; base < nq4; base += 8 * KD_WARPS * 32) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * KD_WARPS * 32 + threadIdx.x, q = i / dq;
+                v[u] = (i < nq4 && m0 + q < M) ? __ldg(reinterpret_cast<const float4*>(p1 + (size_t)(m0 + q) * D) + (i - q * dq))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * KD_WARPS * 32 + threadIdx.x, q = i / dq, d = (i - q * dq) * 4;
+                if (i < nq4) {
+                    float* o = s_q + ((q >> 1) * Dp + d) * 2 + (q & 1);
+                    o[0] = v[u].x; o[2] = v[u].y; o[4] = v[u].z; o[6] = v[u].w;
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < KD_Q * Dp; i += blockDim.x) {
+            const int q = i / Dp, d = i - q * Dp;
+            s_q[((q >> 1) * Dp + d) * 2 + (q & 1)] = (m0 + q < M && d < D) ? p1[(size_t)(m0 + q) * D + d] : 0.f;
+        }
+    }
     int sl = 0;
     for (int t0 = 0; t0 < N; t0 += KD_R) {
         // acc[qp][j]: queries (2 qp, 2 qp + 1) of the warp x reference lane + 32 j, packed as fp32x2: FADD2 / FFMA2
@@ -203,13 +239,52 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         for (int qp = 0; qp < 2; ++qp)
 #pragma unroll
             for (int j = 0; j < 4; ++j) f2_unpack(acc[qp][j], a[2 * qp][j], a[2 * qp + 1][j]);
+        if (xsel) {
+            int ck[KD_QW][4], bk[KD_QW], bi[KD_QW], nk[KD_QW], ni[KD_QW];
 #pragma unroll
-        for (int q = 0; q < KD_QW; ++q) {
-            if (m0 + warp * KD_QW + q < M) {
+            for (int q = 0; q < KD_QW; ++q) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    ck[q][j] = (t0 + lane + 32 * j < N && a[q][j] == a[q][j]) ? __float_as_int(a[q][j]) : XS_TAKEN;
+                nk[q] = XS_TAKEN; ni[q] = 0x7fffffff;
+            }
+            auto local_best = [&](int q) {
+                int k = car_k[q], i = car_i[q];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = t0 + lane + 32 * j;
-                    top[q].offer(n < N ? a[q][j] : CUDART_INF_F, n < N ? n : 0x7fffffff);
+                    if (ck[q][j] < k || (ck[q][j] == k && n < i)) { k = ck[q][j]; i = n; }
+                }
+                bk[q] = k; bi[q] = i;
+            };
+#pragma unroll
+            for (int q = 0; q < KD_QW; ++q) local_best(q);
+            for (int r = 0; r < K; ++r) {
+#pragma unroll
+                for (int q = 0; q < KD_QW; ++q) {
+                    const int mk = __reduce_min_sync(0xffffffffu, bk[q]);
+                    const int wi = __reduce_min_sync(0xffffffffu, bk[q] == mk ? bi[q] : 0x7fffffff);
+                    if (lane == 32 - K + r) { nk[q] = mk; ni[q] = wi; }
+                    if (bk[q] == mk && bi[q] == wi) {          // the winner's lane: remove it, rescan
+                        if (car_k[q] == mk && car_i[q] == wi) car_k[q] = XS_TAKEN;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (ck[q][j] == mk && t0 + lane + 32 * j == wi) ck[q][j] = XS_TAKEN;
+                        local_best(q);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < KD_QW; ++q) { car_k[q] = nk[q]; car_i[q] = ni[q]; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < KD_QW; ++q) {
+                if (m0 + warp * KD_QW + q < M) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = t0 + lane + 32 * j;
+                        top[q].offer(n < N ? a[q][j] : CUDART_INF_F, n < N ? n : 0x7fffffff);
+                    }
                 }
             }
         }
@@ -219,7 +294,12 @@ knnd_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* _
         const int m = m0 + warp * KD_QW + q;
         if (m >= M) continue;
         const size_t base = ((size_t)b * M + m) * K;
-        top[q].sort_set(lane);
+        if (xsel) {                              // already sorted: rank r in lane 32 - K + r, dummies in front
+            top[q].d[0] = lane >= 32 - K ? __int_as_float(car_k[q]) : -1.f;
+            top[q].i[0] = lane >= 32 - K ? car_i[q] : -1;
+        } else {
+            top[q].sort_set(lane);
+        }
         top[q].sanitize(N);
         top[q].for_each_sorted(K, lane, [&](int pos, float d, int i) {
             if (out_d) out_d[base + pos] = d;

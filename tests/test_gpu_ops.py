@@ -178,6 +178,29 @@ def test_knn_descriptor_space_bit_exact(B, M, N, D, K):
     assert torch.equal(i.cpu(), i_o) and torch.equal(d.cpu(), d_o) and torch.equal(nn.cpu(), nn_o)
 
 
+@pytest.mark.parametrize("B,M,N,D,K", [(2, 100, 512, 32, 16), (1, 40, 130, 8, 5), (2, 64, 256, 256, 8), (1, 37, 513, 12, 16),
+                                       (1, 20, 16, 6, 16)])
+def test_knn_descriptor_space_ties_and_overflow(B, M, N, D, K):
+    """Both selection paths of the descriptor-space search (sorted extract-min for K <= 16 of N <= 512, the running set
+    otherwise) on what separates them from a plain sort: exact distance ties (every reference stored twice or more, so
+    the order is decided by the index), queries that coincide with references, squared distances that overflow to +inf
+    (ordered by index among themselves and in front of nothing), unaligned views (4-byte copy path)."""
+    g = torch.Generator().manual_seed(N + K)
+    base = torch.rand(B, max(N // 3, 1), D, generator=g)
+    p2 = base[:, torch.randint(0, base.shape[1], (N,), generator=g)].contiguous()       # duplicates: exact ties
+    p1 = torch.rand(B, M, D, generator=g)
+    p1[:, ::3] = p2[:, : p1[:, ::3].shape[1]]                                            # zero distances
+    p2[:, 1::7] *= 3e19                                                                  # (3e19)^2 overflows fp32
+    d_o, i_o, _ = native.knn_points(p1, p2, K=K)
+    d, i, _ = ops.knn_points(p1.to(DEV), p2.to(DEV), K=K)
+    assert torch.equal(i.cpu(), i_o) and torch.equal(d.cpu(), d_o)
+    # the same through views that start 4 bytes off a 16-byte boundary
+    q1 = torch.empty(p1.numel() + 1, device=DEV)[1:].view_as(p1).copy_(p1)
+    q2 = torch.empty(p2.numel() + 1, device=DEV)[1:].view_as(p2).copy_(p2)
+    d, i, _ = ops.knn_points(q1, q2, K=K)
+    assert torch.equal(i.cpu(), i_o) and torch.equal(d.cpu(), d_o)
+
+
 def test_knn_fused_query_gather_and_knn_gather():
     xyz = _clouds("lidar", 2, 4096, 5)
     fidx = native.fps(xyz, 256)
