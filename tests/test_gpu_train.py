@@ -129,7 +129,7 @@ def test_training_mode_steps_reduce_the_loss_and_update_batchnorm():
         loss = sum(((R - R_gt) ** 2).mean() + ((t - t_gt) ** 2).mean() for R, t in zip(out["rotation"], out["translation"]))
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0], losses
     assert not torch.equal(rm0, net.coarse_corres.convs_1[1].running_mean)
     missing = [n for n, p in net.named_parameters() if p.grad is None]
